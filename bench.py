@@ -1,0 +1,297 @@
+#!/usr/bin/env python
+"""bench.py - FDFD operator throughput (GDOF/s) on B200, BASELINE.json metric.
+
+A "step" is ONE application y = A x of the matrix-free operator A = curl mu^-1 curl - w^2 eps on the
+workload of BASELINE.json configs[1] (200^3 Si strip waveguide, full 3x3 eps, 10-cell PML); with N GPUs
+the grid is 200 x 200 x (200 N) split into N z-slabs (weak scaling, one NCCL halo exchange per apply).
+    value     GDOF/s, x / eps resident in HBM, CUDA events on the library's stream, max over ranks
+    e2e       the same metric through the C-ABI call with HOST (pinned) buffers: H2D of x and D2H of y
+              inside the timed region
+    roofline  algorithmic bytes (80 B/DOF full-tensor, 48 B/DOF diagonal) / apply time
+              against the measured HBM copy bandwidth (MEASURED_PEAKS.json)
+    cpu_baseline   the oracle's Julia-style single-thread CSC mul! on a bounded sample of the workload
+--impl reference times the reference's CPU path stand-in (CSC assembled by the oracle restatement,
+product on all host cores) - the reference itself is Julia and cannot run here.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "fdfd_operator_apply_throughput"
+UNIT = "GDOF/s"
+PER_GPU_N = (200, 200, 200)
+SAMPLE_PLANES = 8
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                f = [s.strip() for s in out.strip().split(",")]
+                if len(f) >= 6:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        self.stop_flag = True
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(self.samples[0][1]),
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def sample_workload():
+    """Bounded sample of the C2 workload for the CPU legs: the SAMPLE_PLANES z-planes through the core."""
+    import workloads
+    Nx, Ny, Nz = PER_GPU_N
+    k0 = Nz // 2 - SAMPLE_PLANES // 2
+    w = workloads.c2_waveguide(PER_GPU_N, k0, k0 + SAMPLE_PLANES)
+    return w, k0
+
+
+def oracle_sample_matrix():
+    """CSC of the sample slab assembled by the ORACLE (treated as a periodic-in-z stack of the 8 planes)."""
+    import numpy as np
+    from oracle import operators as op
+    w, k0 = sample_workload()
+    sl = slice(k0, k0 + SAMPLE_PLANES)
+    sdl_e = (w["sdl_e"][0], w["sdl_e"][1], w["sdl_e"][2][sl])
+    sdl_m = (w["sdl_m"][0], w["sdl_m"][1], w["sdl_m"][2][sl])
+    sei = tuple(1 / a for a in sdl_e)
+    smi = tuple(1 / a for a in sdl_m)
+    isbloch = (False, False, True)
+    ph = np.ones(3, complex)
+    mu = np.zeros(w["eps"].shape, complex)
+    for v in range(3):
+        mu[..., v, v] = 1
+    Ce, Cm = op.create_curls(sei, smi, (0, 0, 0), isbloch, ph)
+    Pe, Pm = op.create_paramops(w["eps"], mu, sdl_e, sdl_m, sei, smi, (0, 0, 0), isbloch, ph)
+    A = op.create_A(0, w["omega"], Pe, Pm, Ce, Cm)
+    return A, f"{PER_GPU_N[0]}x{PER_GPU_N[1]}x{SAMPLE_PLANES} planes through the core of the C2 workload " \
+              f"({A.shape[0]} DOF, nnz {A.nnz}), periodic in z"
+
+
+def cpu_baseline_port(reps=5):
+    import numpy as np
+    from oracle import cbaseline as cb
+    A, desc = oracle_sample_matrix()
+    x = np.random.default_rng(1).standard_normal(A.shape[0]) + 0j
+    y = np.empty_like(x)
+    cb.csc_mul_serial(A, x, y)
+    ts = []
+    for _ in range(reps):
+        t = time.perf_counter()
+        cb.csc_mul_serial(A, x, y)
+        ts.append(time.perf_counter() - t)
+    return {"value": A.shape[0] / min(ts) / 1e9, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": desc + f"; Julia-style single-thread CSC mul!, best of {reps}"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (stand-in) on all host cores; rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import numpy as np
+    from oracle import cbaseline as cb
+    A, desc = oracle_sample_matrix()
+    R = cb.CsrOmp(A)
+    n = A.shape[0]
+    x = np.random.default_rng(1).standard_normal(n) + 1j * np.random.default_rng(2).standard_normal(n)
+    y = np.empty_like(x)
+    for _ in range(max(args.warmup, 1)):
+        R.mul(x, y)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        R.mul(x, y)
+    dt = (time.perf_counter() - t0) / args.steps
+    cores = cb.num_threads()
+    val = n / dt / 1e9
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "c128 (complex fp64)", "data": "synthetic",
+            "config": {"workload": "C2 Si strip waveguide 200x200x200, full 3x3 eps, 10-cell PML",
+                       "sample": desc, "l2": "matrix stream larger than LLC"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": desc + "; OpenMP CSR product of the oracle-assembled matrix (stand-in for the "
+                                              "Julia SparseMatrixCSC mul!, which cannot run here: no julia binary)"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--krylov-iters", type=int, default=20)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--diag", action="store_true", help="diagonal-eps variant of the workload (48 B/DOF)")
+    ap.add_argument("--n", type=int, nargs=3, default=None, help="override the per-GPU grid (debug)")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import workloads
+    import maxwellfdm_jl_b200 as fb
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N > 1")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    per = tuple(args.n) if args.n else PER_GPU_N
+    N = (per[0], per[1], per[2] * world)
+    k0, k1 = fb.partition(N[2], world, rank)
+    w = workloads.c2_waveguide(N, k0, k1, period_z=per[2])
+    if args.diag:
+        for v in range(3):
+            for u in range(3):
+                if u != v:
+                    w["eps"][..., v, u] = 0
+        w["full_eps"] = False
+    A = workloads.make_operator(w, device=local, rank=rank, nranks=world)
+    if world > 1:
+        uid = [fb.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        A.comm_init(uid[0])
+    n_loc = A.n
+    n_tot = 3 * N[0] * N[1] * N[2]
+    g = torch.Generator(device="cuda").manual_seed(20261017 + rank)
+    x = torch.randn(n_loc, 2, device="cuda", dtype=torch.float64, generator=g).view(torch.complex128).reshape(-1)
+    y = torch.empty_like(x)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident operator throughput ------------------------------------------------
+    A.bench_apply(x, y, warmup=args.warmup, iters=1)
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    l0 = A.launch_count
+    ms_total, _ = A.bench_apply(x, y, warmup=0, iters=args.steps)
+    barrier()
+    launches = A.launch_count - l0
+    clocks = sampler.summary()
+    t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    gdofs = n_tot / (ms_step * 1e-3) / 1e9
+
+    # ---- Krylov iterations / s (2 applies + fused vector updates per BiCGSTAB iteration) ---------
+    b = torch.randn(n_loc, 2, device="cuda", dtype=torch.float64, generator=g).view(torch.complex128).reshape(-1)
+    xs = torch.zeros_like(b)
+    barrier()
+    ms_k = A.bench_solve(b, xs, "bicgstab", warmup=2, iters=args.krylov_iters)
+    tk = torch.tensor([ms_k], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tk, op=dist.ReduceOp.MAX)
+    it_per_s = args.krylov_iters / (float(tk.item()) * 1e-3)
+    del b, xs
+
+    # ---- end to end through the C ABI with host buffers ------------------------------------------
+    xh = torch.empty(n_loc, dtype=torch.complex128).pin_memory()
+    yh = torch.empty(n_loc, dtype=torch.complex128).pin_memory()
+    xh.copy_(x.cpu())
+    e2e_steps = max(3, min(args.steps, 5))
+    A.mul(yh.numpy(), xh.numpy())
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        A.mul(yh.numpy(), xh.numpy())
+    barrier()
+    te = torch.tensor([(time.perf_counter() - t0) / e2e_steps], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e = n_tot / float(te.item()) / 1e9
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        bpd = 80 if w["full_eps"] else 48
+        achieved = bpd * (n_tot / world) / (ms_step * 1e-3) / 1e9      # per GPU
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                traffic = json.load(f).get("full" if w["full_eps"] else "diag")
+        except Exception:
+            pass
+        line = {
+            "metric": METRIC, "value": gdofs, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "c128 (complex fp64)", "data": "synthetic",
+            "config": {"workload": w["name"] + (" [diagonal-eps variant]" if args.diag else ""),
+                       "grid": list(N), "per_gpu_grid": list(per), "dof": n_tot, "parallelism": f"z-slab x{world}",
+                       "l2": "inputs (x, y, eps: > 1 GB per GPU) larger than the 126 MB L2; no flush needed",
+                       "bytes_per_dof": bpd},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src,
+                         "kernel": "apply_tiled_kernel (one launch per apply)"},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 16 * n_loc * world,
+                    "d2h_bytes_per_step": 16 * n_loc * world, "steps": e2e_steps,
+                    "note": "fdfd_apply(FDFD_HOST) with pinned host buffers"},
+            "gpu_launches": launches, "clocks": clocks,
+            "krylov": {"method": "bicgstab", "iters": args.krylov_iters, "iter_per_s": it_per_s,
+                       "bytes_per_dof_model": 2 * bpd + 288,
+                       "hbm_frac": (2 * bpd + 288) * (n_tot / world) * it_per_s / 1e9 / peak},
+        }
+        if world == 1 and not args.no_cpu:
+            try:
+                line["cpu_baseline"] = cpu_baseline_port()
+            except Exception as e:  # the baseline is a report, never a reason to lose the GPU numbers
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "port",
+                                        "sample": f"failed: {e}"}
+        print(json.dumps(line))
+    A.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,154 @@
+/*
+ * fdfd_b200.h - C ABI of libfdfd_b200.so: matrix-free FDFD operator A = curl mu^-1 curl - w^2 eps
+ * and its Krylov solve on NVIDIA B200 (sm_100a).
+ *
+ * Drop-in boundary.  The reference (MaxwellFDFD.jl) has no FFI; the seam this library replaces is
+ * the VALUE returned by create_linsys / create_A (reference src/model/model.jl:209-246) - a
+ * SparseMatrixCSC the user multiplies by (`mul!`, `*`) or solves with (`\`).  Each entry point
+ * below cites the reference interface whose role it takes.  All functions are `extern "C"`, take
+ * plain pointers and sizes, return an int status (0 = ok) and never let a C++ exception escape.
+ *
+ * Conventions
+ *   fdfd_c128      {double re, im}: layout-identical to Julia ComplexF64 / C double _Complex /
+ *                  CUDA double2.
+ *   DOF order      reference model.jl:75-83.  order_cmpfirst=1: r = c + 3*(i + Nx*(j + Ny*k));
+ *                  order_cmpfirst=0: r = i + Nx*(j + Ny*(k + Nz*c))   (0-based here).
+ *   z-slabs        one process per GPU.  Rank p of P owns the contiguous planes
+ *                  [k0,k1) given by fdfd_slab_range(); every vector / eps / mu pointer passed by
+ *                  that rank covers ITS OWN planes only (Nz_local = k1-k0 in the formulas above).
+ *                  With nranks == 1 the slab is the whole grid.
+ *   ownership      caller owns every buffer it passes; set_* copy; the library owns its device
+ *                  memory until fdfd_destroy.
+ *   threading      a handle is not thread-safe; every call blocks until its results are visible
+ *                  to the host (the library synchronises its own CUDA stream before returning).
+ */
+#ifndef FDFD_B200_H
+#define FDFD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct { double re, im; } fdfd_c128;
+typedef struct fdfd_ctx *fdfd_handle;
+
+/* status codes (reference: ArgumentError at source.jl:214,230 and @error at model.jl:242,270) */
+enum {
+    FDFD_OK = 0,
+    FDFD_EINVAL = 1,   /* bad argument / unsupported configuration */
+    FDFD_ECUDA = 2,    /* CUDA runtime error (message in fdfd_last_error) */
+    FDFD_ENCCL = 3,    /* NCCL error or NCCL not loadable */
+    FDFD_ENOMEM = 4,   /* host or device allocation failed */
+    FDFD_ENOCONV = 5,  /* solver stopped at maxit; x, iters, relres are still valid */
+    FDFD_ESTATE = 6    /* call sequence error (e.g. apply before set_eps) */
+};
+
+enum { FDFD_HOST = 0, FDFD_DEVICE = 1 };            /* where x / y / b live */
+enum { FDFD_BICGSTAB = 0, FDFD_QMR = 1 };            /* Krylov method (BASELINE.json north_star) */
+enum { FDFD_FT_EE = 0, FDFD_FT_HH = 1 };             /* reference FieldType, model.jl:235,238 */
+enum { FDFD_KERNEL_AUTO = 0, FDFD_KERNEL_NAIVE = 1, FDFD_KERNEL_TILED = 2 };
+
+/* Problem descriptor: the fields of the reference Model that the hot path consumes
+ * (model.jl:32-73): grid.N, grid.isbloch (:40), boundft (:46), order_cmpfirst (:72). */
+typedef struct {
+    int64_t N[3];             /* global Yee grid size Nx,Ny,Nz */
+    int32_t isbloch[3];       /* 1: Bloch-periodic, 0: symmetry boundary, per axis */
+    int32_t boundft_is_E[3];  /* 1: boundft[w]==EE (default), 0: HH */
+    int32_t order_cmpfirst;   /* DOF layout flag, model.jl:72 */
+    int32_t field_type;       /* FDFD_FT_EE: A = Cm (Pmu\Ce) - w^2 Peps ; FDFD_FT_HH: A = Ce (Peps\Cm) - w^2 Pmu */
+    int32_t device;           /* CUDA device ordinal for this process; -1 = current device;
+                                 -2 = host-only handle: fdfd_export_pattern works, every GPU call fails */
+    int32_t rank, nranks;     /* z-slab owner / number of slabs (processes) */
+    int32_t weighted_out_avg; /* 0: unweighted output average in create_paramop (default), 1: weighted */
+    int32_t kernel;           /* FDFD_KERNEL_*; AUTO picks the tiled kernel when it applies */
+} fdfd_desc;
+
+const char *fdfd_version(void);
+
+/* Lifetime.  fdfd_create replaces constructing the operator value of create_A (model.jl:225). */
+int fdfd_create(fdfd_handle *out, const fdfd_desc *desc);
+int fdfd_destroy(fdfd_handle h);
+/* Last error message of this handle (h == NULL: last error of a failed fdfd_create in this thread). */
+const char *fdfd_last_error(fdfd_handle h);
+
+/* This rank's plane range [k0,k1) of the global z axis. */
+int fdfd_slab_range(fdfd_handle h, int64_t *k0, int64_t *k1);
+/* Pure host helper (no GPU needed): the partition rule itself, for planning and tests. */
+int fdfd_partition(int64_t Nz, int32_t nranks, int32_t rank, int64_t *k0, int64_t *k1);
+
+/* Operator inputs - exactly what create_curls / create_paramops hand to MaxwellBase
+ * (model.jl:152-155,171-172):
+ *   sdl_e[w], sdl_m[w]: the NON-inverted stretched cell sizes s*dl centred at E-field / H-field
+ *   plane locations (create_stretched_dls, model.jl:122-139), GLOBAL length N[w], host pointers. */
+int fdfd_set_coeffs(fdfd_handle h, const fdfd_c128 *const sdl_e[3], const fdfd_c128 *const sdl_m[3]);
+/* e^{-i k L} per axis (create_e^{-ikL}, model.jl:91). Default (1,1,1). */
+int fdfd_set_bloch(fdfd_handle h, const fdfd_c128 e_mikL[3]);
+/* omega of create_A (model.jl:226); omega == 0 skips the mass term (model.jl:237). */
+int fdfd_set_omega(fdfd_handle h, fdfd_c128 omega);
+/* eps array of the model (model.jl:51): host pointer, Julia column-major layout
+ * (Nx,Ny,Nz_local,3,3); diagonal entries at the E_v locations, off-diagonal at voxel corners.
+ * has_offdiag == 0 promises every off-diagonal entry is zero (they are not read). */
+int fdfd_set_eps(fdfd_handle h, const fdfd_c128 *eps, int has_offdiag);
+/* mu array (model.jl:52), same layout; NULL = identity.  For FT_EE mu must be diagonal
+ * (model.jl:236: `Pmu \ Ce` is only defined for diagonal Pmu) else FDFD_EINVAL. */
+int fdfd_set_mu(fdfd_handle h, const fdfd_c128 *mu_or_null);
+
+/* y = A x : the per-iteration `mul!(y, A, x)` of the reference path (SparseMatrixCSC product).
+ * x, y: this rank's slab of the DOF vector, `where` = FDFD_HOST or FDFD_DEVICE. x != y. */
+int fdfd_apply(fdfd_handle h, const fdfd_c128 *x, fdfd_c128 *y, int where);
+/* y = A^T x (plain transpose, needed by QMR). */
+int fdfd_apply_transpose(fdfd_handle h, const fdfd_c128 *x, fdfd_c128 *y, int where);
+
+/* x = A \ b by a Krylov method (the solve the reference leaves to the user, README.md:27-33).
+ * x: in = initial guess, out = solution.  Stops when ||b - A x|| <= rtol*||b|| (recurrence
+ * residual) or at maxit (-> FDFD_ENOCONV).  hist_or_null: maxit+1 doubles, relative residual per
+ * iteration.  check_every: residual is read back to the host every that many iterations (>=1). */
+int fdfd_solve(fdfd_handle h, int method, const fdfd_c128 *b, fdfd_c128 *x, int where,
+               double rtol, int maxit, int check_every,
+               int *iters, double *relres, double *hist_or_null);
+
+/* Debug export of the assembled operator in Julia CSC form (1-based Int64 colptr/rowval,
+ * SparseMatrixCSC{ComplexF64,Int64} of create_A, model.jl:236-237; pattern rule set of
+ * SURVEY.md A.6).  Single-slab handles only.  Call with colptr/rowval/nzval == NULL to get nnz.
+ * nnz_inout: in = capacity of rowval/nzval, out = nnz.  nzval_or_null may be NULL. */
+int fdfd_export_pattern(fdfd_handle h, int64_t *colptr, int64_t *rowval, fdfd_c128 *nzval_or_null,
+                        int64_t *nnz_inout);
+
+/* Post-processing next to the solve: h = (i/w) mu^-1 (Ce e + jm)  (h_from_e, model.jl:276-279).
+ * jm_or_null == NULL means jm = 0. */
+int fdfd_h_from_e(fdfd_handle h, const fdfd_c128 *e, const fdfd_c128 *jm_or_null, fdfd_c128 *hout, int where);
+/* RHS: b = -Cm (mu^-1 jm) - i w je   (create_b, model.jl:251-274, EE branch). */
+int fdfd_create_b(fdfd_handle h, const fdfd_c128 *je, const fdfd_c128 *jm_or_null, fdfd_c128 *b, int where);
+
+/* Multi-GPU plumbing: NCCL communicator over the z-slab ranks (halo send/recv + allreduce).
+ * Rank 0 calls fdfd_comm_unique_id, ships the 128 bytes to the other ranks by any means
+ * (torch.distributed broadcast, MPI, a file), then every rank calls fdfd_comm_init. */
+int fdfd_comm_unique_id(char id[128]);
+int fdfd_comm_init(fdfd_handle h, const char id[128]);
+
+/* Measurement (CUDA events on the library's own stream; device pointers only).
+ * Runs `warmup` untimed + `iters` timed applies back to back; *ms_total = time of the `iters`
+ * applies; if flush_l2 != 0 a >L2-sized buffer is rewritten before every timed apply and excluded
+ * from the time (events bracket each apply). */
+int fdfd_bench_apply(fdfd_handle h, const fdfd_c128 *x_dev, fdfd_c128 *y_dev, int warmup, int iters,
+                     int flush_l2, double *ms_total, double *ms_min);
+/* Fixed-iteration Krylov run without convergence exit (iterations/s): *ms_total for `iters`. */
+int fdfd_bench_solve(fdfd_handle h, int method, const fdfd_c128 *b_dev, fdfd_c128 *x_dev,
+                     int warmup, int iters, double *ms_total);
+/* Number of kernels this handle has launched since creation (for bench.py's gpu_launches). */
+int64_t fdfd_launch_count(fdfd_handle h);
+
+/* Pinned host memory for callers that want full PCIe speed on FDFD_HOST calls. */
+int fdfd_host_alloc(void **p, uint64_t bytes);
+int fdfd_host_free(void *p);
+/* Raw device memory on the handle's device, for hosts without their own CUDA allocator. */
+int fdfd_dev_alloc(fdfd_handle h, void **p, uint64_t bytes);
+int fdfd_dev_free(fdfd_handle h, void *p);
+int fdfd_memcpy(fdfd_handle h, void *dst, const void *src, uint64_t bytes, int dst_where, int src_where);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FDFD_B200_H */

@@ -1,0 +1,91 @@
+"""ctypes binding of libfdfd_b200.so (C ABI declared in include/fdfd_b200.h).
+
+The product path has NO CPU fallback: if the shared library is missing this raises at import of the
+binding, and if no CUDA device is present fdfd_create fails with FDFD_ECUDA.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libfdfd_b200.so")
+
+OK, EINVAL, ECUDA, ENCCL, ENOMEM, ENOCONV, ESTATE = range(7)
+HOST, DEVICE = 0, 1
+BICGSTAB, QMR = 0, 1
+FT_EE, FT_HH = 0, 1
+KERNEL_AUTO, KERNEL_NAIVE, KERNEL_TILED = 0, 1, 2
+
+
+class c128(C.Structure):
+    _fields_ = [("re", C.c_double), ("im", C.c_double)]
+
+
+class Desc(C.Structure):
+    _fields_ = [("N", C.c_int64 * 3), ("isbloch", C.c_int32 * 3), ("boundft_is_E", C.c_int32 * 3),
+                ("order_cmpfirst", C.c_int32), ("field_type", C.c_int32), ("device", C.c_int32),
+                ("rank", C.c_int32), ("nranks", C.c_int32), ("weighted_out_avg", C.c_int32),
+                ("kernel", C.c_int32)]
+
+
+class FdfdError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"fdfd_b200 error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+# name -> (restype, argtypes); every symbol include/fdfd_b200.h declares
+P = C.c_void_p
+SYMBOLS = {
+    "fdfd_version": (C.c_char_p, []),
+    "fdfd_create": (C.c_int, [C.POINTER(P), C.POINTER(Desc)]),
+    "fdfd_destroy": (C.c_int, [P]),
+    "fdfd_last_error": (C.c_char_p, [P]),
+    "fdfd_slab_range": (C.c_int, [P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "fdfd_partition": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "fdfd_set_coeffs": (C.c_int, [P, C.POINTER(P), C.POINTER(P)]),
+    "fdfd_set_bloch": (C.c_int, [P, P]),
+    "fdfd_set_omega": (C.c_int, [P, c128]),
+    "fdfd_set_eps": (C.c_int, [P, P, C.c_int]),
+    "fdfd_set_mu": (C.c_int, [P, P]),
+    "fdfd_apply": (C.c_int, [P, P, P, C.c_int]),
+    "fdfd_apply_transpose": (C.c_int, [P, P, P, C.c_int]),
+    "fdfd_solve": (C.c_int, [P, C.c_int, P, P, C.c_int, C.c_double, C.c_int, C.c_int,
+                             C.POINTER(C.c_int), C.POINTER(C.c_double), P]),
+    "fdfd_export_pattern": (C.c_int, [P, P, P, P, C.POINTER(C.c_int64)]),
+    "fdfd_h_from_e": (C.c_int, [P, P, P, P, C.c_int]),
+    "fdfd_create_b": (C.c_int, [P, P, P, P, C.c_int]),
+    "fdfd_comm_unique_id": (C.c_int, [C.c_char_p]),
+    "fdfd_comm_init": (C.c_int, [P, C.c_char_p]),
+    "fdfd_bench_apply": (C.c_int, [P, P, P, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "fdfd_bench_solve": (C.c_int, [P, C.c_int, P, P, C.c_int, C.c_int, C.POINTER(C.c_double)]),
+    "fdfd_launch_count": (C.c_int64, [P]),
+    "fdfd_host_alloc": (C.c_int, [C.POINTER(P), C.c_uint64]),
+    "fdfd_host_free": (C.c_int, [P]),
+    "fdfd_dev_alloc": (C.c_int, [P, C.POINTER(P), C.c_uint64]),
+    "fdfd_dev_free": (C.c_int, [P, P]),
+    "fdfd_memcpy": (C.c_int, [P, P, P, C.c_uint64, C.c_int, C.c_int]),
+}
+
+
+def lib():
+    """Load the CUDA shared library; raise loudly if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; "
+                              f"g.build()'` (there is no CPU fallback)")
+        l = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+        for name, (res, args) in SYMBOLS.items():
+            f = getattr(l, name)
+            f.restype, f.argtypes = res, args
+        _lib = l
+    return _lib
+
+
+def check(code, handle=None, ok=(OK,)):
+    if code not in ok:
+        msg = lib().fdfd_last_error(handle)
+        raise FdfdError(code, msg.decode() if msg else "")
+    return code

@@ -1,0 +1,731 @@
+// C ABI of libfdfd_b200.so (see include/fdfd_b200.h for the contract and the reference lines each entry
+// point stands in for).  Host-side state handling, device array construction, launches.
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "cplx.cuh"
+#include "fdfd_internal.h"
+
+namespace fdfd {
+
+static thread_local std::string g_create_err;
+
+int set_err(Ctx *c, int code, const std::string &msg) {
+    if (c) c->err = msg;
+    else g_create_err = msg;
+    return code;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// small device kernels used while building the material arrays
+// ---------------------------------------------------------------------------------------------------
+__global__ void scale_copy_kernel(double2 *dst, const double2 *src, int64_t n, double2 f) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        dst[i] = c_mul(f, src[i]);
+}
+__global__ void recip_copy_kernel(double2 *dst, const double2 *src, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double2 a = src[i];
+        const double d = a.x * a.x + a.y * a.y;
+        dst[i] = make_double2(a.x / d, -a.y / d);
+    }
+}
+__global__ void fill_kernel(double2 *dst, int64_t n, double2 v) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        dst[i] = v;
+}
+__global__ void flush_kernel(float4 *p, int64_t n, float v) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        p[i] = make_float4(v, v, v, v);
+}
+
+static inline int nblocks(int64_t n) {
+    int64_t b = (n + 255) / 256;
+    return (int)(b > 148 * 16 ? 148 * 16 : (b < 1 ? 1 : b));
+}
+
+static void free_device(Ctx *c) {
+    auto F = [](auto *&p) { if (p) cudaFree((void *)p); p = nullptr; };
+    F(c->coef_dev); F(c->mat_dev); F(c->halo_lo); F(c->halo_hi); F(c->work); F(c->scal); F(c->partial);
+    F(c->stage_x); F(c->stage_y); F(c->flush_buf);
+    if (c->scal_host) cudaFreeHost(c->scal_host);
+    c->scal_host = nullptr;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// device arrays
+// ---------------------------------------------------------------------------------------------------
+static int upload_coefs(Ctx *c) {
+    CoefHost f, t;
+    build_coefs(c->d, c->sdl_e, c->sdl_m, c->phase, f);
+    transpose_coefs(f, t);
+    for (int w = 0; w < 3; ++w) c->s1[w] = f.a[w].shift;
+    const int64_t Ns = c->d.N[0] + c->d.N[1] + c->d.N[2];
+    const size_t bytes = (size_t)(2 * 8 * Ns) * sizeof(double2);
+    std::vector<cplx> host((size_t)2 * 8 * Ns);
+    if (c->coef_bytes != bytes) {
+        if (c->coef_dev) cudaFree(c->coef_dev);
+        c->coef_dev = nullptr;
+        FDFD_CUDA(c, cudaMalloc((void **)&c->coef_dev, bytes));
+        c->coef_bytes = bytes;
+    }
+    size_t off = 0;
+    auto put = [&](const std::vector<cplx> &v, const double2 *&dst) {
+        std::memcpy(&host[off], v.data(), v.size() * sizeof(cplx));
+        dst = c->coef_dev + off;
+        off += v.size();
+    };
+    for (int set = 0; set < 2; ++set) {
+        const CoefHost &h = set == 0 ? f : t;
+        CoefDev &d = set == 0 ? c->cf : c->ct;
+        for (int w = 0; w < 3; ++w) {
+            put(h.a[w].t0, d.a0[w]); put(h.a[w].t1, d.a1[w]);
+            put(h.b[w].t0, d.b0[w]); put(h.b[w].t1, d.b1[w]);
+            put(h.mi[w].t0, d.mi0[w]); put(h.mi[w].t1, d.mi1[w]);
+            put(h.mo[w].t0, d.mo0[w]); put(h.mo[w].t1, d.mo1[w]);
+        }
+    }
+    FDFD_CUDA(c, cudaMemcpyAsync(c->coef_dev, host.data(), bytes, cudaMemcpyHostToDevice, c->stream));
+    FDFD_CUDA(c, cudaStreamSynchronize(c->stream));
+    return FDFD_OK;
+}
+
+// Build md (3), mo (6, optional), q (3, optional) as z-ghosted component-major arrays on the device.
+static int upload_materials(Ctx *c) {
+    const int64_t Nxy = c->d.N[0] * c->d.N[1];
+    const int64_t nzl = c->k1 - c->k0;
+    const int64_t M = Nxy * nzl, Mg = Nxy * (nzl + 2);
+    const bool ee = c->d.field_type == FDFD_FT_EE;
+    // mass parameter / middle parameter in reference terms
+    const std::vector<cplx> &mass = ee ? c->eps_host : c->mu_host;
+    const std::vector<cplx> &mid = ee ? c->mu_host : c->eps_host;
+    const bool mass_given = !mass.empty(), mid_given = !mid.empty();
+    const bool has_mass = c->omega != cplx(0.0);
+    const bool has_off = has_mass && mass_given && (ee ? c->eps_off : c->have_mu && false);
+    const int narr = (has_mass ? 3 : 0) + (has_off ? 6 : 0) + (mid_given ? 3 : 0);
+    const size_t bytes = (size_t)narr * Mg * sizeof(double2);
+    if (bytes != c->mat_bytes) {
+        if (c->mat_dev) cudaFree(c->mat_dev);
+        c->mat_dev = nullptr;
+        if (bytes) FDFD_CUDA(c, cudaMalloc((void **)&c->mat_dev, bytes));
+        c->mat_bytes = bytes;
+    }
+    for (int i = 0; i < 3; ++i) c->md[i] = c->q[i] = nullptr;
+    for (int i = 0; i < 6; ++i) c->mo[i] = c->mo_t[i] = nullptr;
+    if (!narr) return FDFD_OK;
+    double2 *tmp = nullptr;
+    FDFD_CUDA(c, cudaMalloc((void **)&tmp, (size_t)M * sizeof(double2)));
+    double2 *cur = c->mat_dev;
+    const cplx w2 = -(c->omega * c->omega);
+    const double2 f = make_double2(w2.real(), w2.imag());
+    std::vector<double2 *> ghosted;
+    auto build = [&](const std::vector<cplx> *src, int v, int u, int mode, const double2 *&slot) -> int {
+        // mode 0: f * src, mode 1: 1/src; src == nullptr: identity parameter (1 on the diagonal)
+        if (src) {
+            FDFD_CUDA(c, cudaMemcpyAsync(tmp, src->data() + (size_t)M * (v + 3 * u), (size_t)M * sizeof(double2),
+                                         cudaMemcpyHostToDevice, c->stream));
+            if (mode == 0) scale_copy_kernel<<<nblocks(M), 256, 0, c->stream>>>(cur + Nxy, tmp, M, f);
+            else           recip_copy_kernel<<<nblocks(M), 256, 0, c->stream>>>(cur + Nxy, tmp, M);
+        } else {
+            fill_kernel<<<nblocks(M), 256, 0, c->stream>>>(cur + Nxy, M, mode == 0 ? f : make_double2(1.0, 0.0));
+        }
+        FDFD_CUDA(c, cudaGetLastError());
+        FDFD_CUDA(c, cudaStreamSynchronize(c->stream));  // tmp is reused
+        slot = cur;
+        ghosted.push_back(cur);
+        cur += Mg;
+        return FDFD_OK;
+    };
+    int rc = FDFD_OK;
+    if (has_mass)
+        for (int v = 0; v < 3 && rc == FDFD_OK; ++v) rc = build(mass_given ? &mass : nullptr, v, v, 0, c->md[v]);
+    if (has_off && rc == FDFD_OK) {
+        int e = 0;
+        for (int v = 0; v < 3; ++v)
+            for (int u = 0; u < 3; ++u)
+                if (u != v && rc == FDFD_OK) rc = build(&mass, v, u, 0, c->mo[e++]);
+        // transposed operator uses P'_{uv} = P_{vu}
+        int idx[3][3];
+        e = 0;
+        for (int v = 0; v < 3; ++v)
+            for (int u = 0; u < 3; ++u)
+                if (u != v) idx[v][u] = e++;
+        for (int v = 0; v < 3; ++v)
+            for (int u = 0; u < 3; ++u)
+                if (u != v) c->mo_t[idx[v][u]] = c->mo[idx[u][v]];
+    }
+    if (mid_given && rc == FDFD_OK)
+        for (int v = 0; v < 3 && rc == FDFD_OK; ++v) rc = build(&mid, v, v, 1, c->q[v]);
+    cudaFree(tmp);
+    if (rc != FDFD_OK) return rc;
+    // ghost planes: periodic wrap (single slab), neighbour exchange (multi slab), zero at symmetry ends
+    for (double2 *g : ghosted) {
+        FDFD_CUDA(c, cudaMemsetAsync(g, 0, (size_t)Nxy * sizeof(double2), c->stream));
+        FDFD_CUDA(c, cudaMemsetAsync(g + (nzl + 1) * Nxy, 0, (size_t)Nxy * sizeof(double2), c->stream));
+        if (c->d.nranks == 1) {
+            if (c->d.isbloch[2]) {
+                FDFD_CUDA(c, cudaMemcpyAsync(g, g + nzl * Nxy, (size_t)Nxy * sizeof(double2),
+                                             cudaMemcpyDeviceToDevice, c->stream));
+                FDFD_CUDA(c, cudaMemcpyAsync(g + (nzl + 1) * Nxy, g + Nxy, (size_t)Nxy * sizeof(double2),
+                                             cudaMemcpyDeviceToDevice, c->stream));
+            }
+        } else {
+            if (!c->comm) return set_err(c, FDFD_ESTATE, "nranks > 1: call fdfd_comm_init before the first apply");
+            int r = halo_exchange_ghosted(c, g, c->stream);
+            if (r != FDFD_OK) return r;
+        }
+    }
+    FDFD_CUDA(c, cudaStreamSynchronize(c->stream));
+    return FDFD_OK;
+}
+
+int ensure_ready(Ctx *c) {
+    if (c->dev == -2) return set_err(c, FDFD_ESTATE, "host-only handle (device = -2): only fdfd_export_pattern is available");
+    if (!c->dirty) return FDFD_OK;
+    if (!c->have_coeffs) return set_err(c, FDFD_ESTATE, "fdfd_set_coeffs has not been called");
+    const bool ee = c->d.field_type == FDFD_FT_EE;
+    if (c->omega != cplx(0.0) && ee && !c->have_eps)
+        return set_err(c, FDFD_ESTATE, "fdfd_set_eps has not been called (needed when omega != 0)");
+    if (!ee && !c->have_eps) return set_err(c, FDFD_ESTATE, "FT_HH needs fdfd_set_eps (A = Ce (Peps \\ Cm) - w^2 Pmu)");
+    FDFD_CUDA(c, cudaSetDevice(c->dev));
+    int r = upload_coefs(c);
+    if (r != FDFD_OK) return r;
+    r = upload_materials(c);
+    if (r != FDFD_OK) return r;
+    c->dirty = false;
+    return FDFD_OK;
+}
+
+void fill_params(Ctx *c, ApplyParams &p, const double2 *x, double2 *y, bool transpose) {
+    std::memset(&p, 0, sizeof(p));
+    const int64_t Nx = c->d.N[0], Ny = c->d.N[1], nzl = c->k1 - c->k0;
+    p.Nx = (int)Nx; p.Ny = (int)Ny; p.nzl = (int)nzl; p.Nz = (int)c->d.N[2]; p.kz0 = (int)c->k0;
+    for (int w = 0; w < 3; ++w) { p.s1[w] = c->s1[w]; p.wrap[w] = c->d.isbloch[w] ? 1 : 0; }
+    p.cmpfirst = c->d.order_cmpfirst ? 1 : 0;
+    p.has_mass = c->md[0] != nullptr;
+    p.has_off = c->mo[0] != nullptr;
+    p.has_q = c->q[0] != nullptr;
+    p.c = transpose ? c->ct : c->cf;
+    for (int i = 0; i < 3; ++i) { p.md[i] = c->md[i]; p.q[i] = c->q[i]; }
+    for (int i = 0; i < 6; ++i) p.mo[i] = transpose ? c->mo_t[i] : c->mo[i];
+    const int64_t Nxy = Nx * Ny;
+    p.x.base = x;
+    if (p.cmpfirst) { p.x.pstride = 3 * Nxy; p.x.cs = 1; p.x.es = 3; }
+    else            { p.x.pstride = Nxy; p.x.cs = Nxy * nzl; p.x.es = 1; }
+    if (c->d.nranks == 1) {
+        // periodic wrap inside the slab (for symmetry boundaries the planes are only multiplied by zeros)
+        p.x.lo = x + (nzl - 1) * p.x.pstride; p.x.cs_lo = p.x.cs;
+        p.x.hi = x;                           p.x.cs_hi = p.x.cs;
+    } else {
+        p.x.lo = c->halo_lo; p.x.hi = c->halo_hi;
+        p.x.cs_lo = p.x.cs_hi = p.cmpfirst ? 1 : Nxy;
+    }
+    p.y = y; p.y_pstride = p.x.pstride; p.y_cs = p.x.cs; p.y_es = p.x.es;
+}
+
+int apply_device(Ctx *c, const double2 *x, double2 *y, bool transpose) {
+    int r = ensure_ready(c);
+    if (r != FDFD_OK) return r;
+    if (x == y) return set_err(c, FDFD_EINVAL, "fdfd_apply: x and y must not alias");
+    ApplyParams p;
+    fill_params(c, p, x, y, transpose);
+    if (c->d.nranks > 1) {
+        r = halo_exchange(c, x, c->halo_lo, c->halo_hi, c->stream);
+        if (r != FDFD_OK) return r;
+    }
+    const bool can_tile = tiled_supported(p);
+    if (c->d.kernel == FDFD_KERNEL_TILED && !can_tile)
+        return set_err(c, FDFD_EINVAL, "tiled kernel requires the first curl to be forward on every axis");
+    if (c->d.kernel != FDFD_KERNEL_NAIVE && can_tile) {
+        int nl = 0;
+        FDFD_CUDA(c, launch_apply_tiled(p, 0, p.nzl, c->stream, &nl));
+        c->launches += nl;
+    } else {
+        FDFD_CUDA(c, launch_apply_naive(p, c->stream));
+        c->launches += 1;
+    }
+    return FDFD_OK;
+}
+
+static int stage_buffers(Ctx *c) {
+    if (c->dev == -2) return set_err(c, FDFD_ESTATE, "host-only handle (device = -2): only fdfd_export_pattern is available");
+    if (!c->stage_x) FDFD_CUDA(c, cudaMalloc((void **)&c->stage_x, (size_t)c->nloc * sizeof(double2)));
+    if (!c->stage_y) FDFD_CUDA(c, cudaMalloc((void **)&c->stage_y, (size_t)c->nloc * sizeof(double2)));
+    return FDFD_OK;
+}
+
+}  // namespace fdfd
+
+using namespace fdfd;
+
+#define CHECK_H(h)                                                             \
+    if (!(h)) return set_err(nullptr, FDFD_EINVAL, "null handle");            \
+    Ctx *c = static_cast<Ctx *>(h);                                            \
+    if (c->dev != -2) {                                                        \
+        cudaError_t e_ = cudaSetDevice(c->dev);                                \
+        if (e_ != cudaSuccess) return set_err(c, FDFD_ECUDA, cudaGetErrorString(e_)); \
+    }
+
+extern "C" {
+
+const char *fdfd_version(void) { return "fdfd_b200 0.1.0 (sm_100a)"; }
+
+const char *fdfd_last_error(fdfd_handle h) { return h ? static_cast<Ctx *>(h)->err.c_str() : g_create_err.c_str(); }
+
+int fdfd_partition(int64_t Nz, int32_t nranks, int32_t rank, int64_t *k0, int64_t *k1) {
+    if (Nz < 1 || nranks < 1 || rank < 0 || rank >= nranks || nranks > Nz || !k0 || !k1) return FDFD_EINVAL;
+    *k0 = (Nz * rank) / nranks;
+    *k1 = (Nz * (rank + 1)) / nranks;
+    return FDFD_OK;
+}
+
+int fdfd_create(fdfd_handle *out, const fdfd_desc *d) {
+    if (!out || !d) return set_err(nullptr, FDFD_EINVAL, "fdfd_create: null argument");
+    *out = nullptr;
+    for (int w = 0; w < 3; ++w)
+        if (d->N[w] < 1 || d->N[w] > (1 << 30)) return set_err(nullptr, FDFD_EINVAL, "fdfd_create: bad grid size");
+    if (d->field_type != FDFD_FT_EE && d->field_type != FDFD_FT_HH)
+        return set_err(nullptr, FDFD_EINVAL, "ft is unsupported.");  // reference @error model.jl:242
+    if (d->nranks < 1 || d->rank < 0 || d->rank >= d->nranks || d->nranks > d->N[2])
+        return set_err(nullptr, FDFD_EINVAL, "fdfd_create: bad rank/nranks (need 1 <= nranks <= Nz)");
+    if (d->kernel < FDFD_KERNEL_AUTO || d->kernel > FDFD_KERNEL_TILED)
+        return set_err(nullptr, FDFD_EINVAL, "fdfd_create: bad kernel selector");
+    for (int w = 0; w < 3; ++w)
+        if (!d->isbloch[w] && d->N[w] < 2 && false) return FDFD_EINVAL;
+    if (d->device == -2) {
+        // host-only handle: debug pattern export (integer work on the host) and nothing else
+        fdfd_ctx *hc = new (std::nothrow) fdfd_ctx();
+        if (!hc) return set_err(nullptr, FDFD_ENOMEM, "out of host memory");
+        hc->d = *d;
+        hc->dev = -2;
+        fdfd_partition(d->N[2], d->nranks, d->rank, &hc->k0, &hc->k1);
+        hc->plane = 3 * d->N[0] * d->N[1];
+        hc->nloc = hc->plane * (hc->k1 - hc->k0);
+        *out = hc;
+        return FDFD_OK;
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev < 1)
+        return set_err(nullptr, FDFD_ECUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                                                " (libfdfd_b200 has no CPU fallback)");
+    fdfd_ctx *c = new (std::nothrow) fdfd_ctx();
+    if (!c) return set_err(nullptr, FDFD_ENOMEM, "out of host memory");
+    c->d = *d;
+    if (d->device >= 0) c->dev = d->device;
+    else cudaGetDevice(&c->dev);
+    if (c->dev >= ndev) { delete c; return set_err(nullptr, FDFD_EINVAL, "fdfd_create: device ordinal out of range"); }
+    fdfd_partition(d->N[2], d->nranks, d->rank, &c->k0, &c->k1);
+    c->plane = 3 * d->N[0] * d->N[1];
+    c->nloc = c->plane * (c->k1 - c->k0);
+    auto fail = [&](cudaError_t ee, const char *what) {
+        std::string m = std::string(what) + ": " + cudaGetErrorString(ee);
+        free_device(c);
+        delete c;
+        return set_err(nullptr, FDFD_ECUDA, m);
+    };
+    if ((e = cudaSetDevice(c->dev)) != cudaSuccess) return fail(e, "cudaSetDevice");
+    if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
+    if ((e = cudaStreamCreateWithFlags(&c->stream_copy, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
+    if (d->nranks > 1) {
+        const size_t pb = (size_t)c->plane * sizeof(double2);
+        if ((e = cudaMalloc((void **)&c->halo_lo, pb)) != cudaSuccess) return fail(e, "cudaMalloc(halo)");
+        if ((e = cudaMalloc((void **)&c->halo_hi, pb)) != cudaSuccess) return fail(e, "cudaMalloc(halo)");
+        cudaMemset(c->halo_lo, 0, pb);
+        cudaMemset(c->halo_hi, 0, pb);
+    }
+    *out = c;
+    return FDFD_OK;
+}
+
+int fdfd_destroy(fdfd_handle h) {
+    if (!h) return FDFD_OK;
+    Ctx *c = static_cast<Ctx *>(h);
+    if (c->dev == -2) { delete static_cast<fdfd_ctx *>(h); return FDFD_OK; }
+    cudaSetDevice(c->dev);
+    cudaDeviceSynchronize();
+    comm_destroy(c);
+    free_device(c);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->stream_copy) cudaStreamDestroy(c->stream_copy);
+    delete static_cast<fdfd_ctx *>(h);
+    return FDFD_OK;
+}
+
+int fdfd_slab_range(fdfd_handle h, int64_t *k0, int64_t *k1) {
+    if (!h || !k0 || !k1) return FDFD_EINVAL;
+    Ctx *c = static_cast<Ctx *>(h);
+    *k0 = c->k0;
+    *k1 = c->k1;
+    return FDFD_OK;
+}
+
+int fdfd_set_coeffs(fdfd_handle h, const fdfd_c128 *const sdl_e[3], const fdfd_c128 *const sdl_m[3]) {
+    CHECK_H(h);
+    if (!sdl_e || !sdl_m) return set_err(c, FDFD_EINVAL, "fdfd_set_coeffs: null argument");
+    for (int w = 0; w < 3; ++w) {
+        if (!sdl_e[w] || !sdl_m[w]) return set_err(c, FDFD_EINVAL, "fdfd_set_coeffs: null axis array");
+        const cplx *pe = reinterpret_cast<const cplx *>(sdl_e[w]);
+        const cplx *pm = reinterpret_cast<const cplx *>(sdl_m[w]);
+        c->sdl_e[w].assign(pe, pe + c->d.N[w]);
+        c->sdl_m[w].assign(pm, pm + c->d.N[w]);
+        for (int64_t i = 0; i < c->d.N[w]; ++i)
+            if (c->sdl_e[w][i] == cplx(0.0) || c->sdl_m[w][i] == cplx(0.0))
+                return set_err(c, FDFD_EINVAL, "fdfd_set_coeffs: zero cell size");
+    }
+    c->have_coeffs = true;
+    c->dirty = true;
+    return FDFD_OK;
+}
+
+int fdfd_set_bloch(fdfd_handle h, const fdfd_c128 e_mikL[3]) {
+    CHECK_H(h);
+    if (!e_mikL) return set_err(c, FDFD_EINVAL, "fdfd_set_bloch: null argument");
+    for (int w = 0; w < 3; ++w) {
+        c->phase[w] = cplx(e_mikL[w].re, e_mikL[w].im);
+        if (c->phase[w] == cplx(0.0)) return set_err(c, FDFD_EINVAL, "fdfd_set_bloch: zero phase factor");
+    }
+    c->dirty = true;
+    return FDFD_OK;
+}
+
+int fdfd_set_omega(fdfd_handle h, fdfd_c128 omega) {
+    CHECK_H(h);
+    c->omega = cplx(omega.re, omega.im);
+    c->have_omega = true;
+    c->dirty = true;
+    return FDFD_OK;
+}
+
+static bool offdiag_nonzero(const std::vector<cplx> &a, int64_t M) {
+    for (int v = 0; v < 3; ++v)
+        for (int u = 0; u < 3; ++u)
+            if (u != v) {
+                const cplx *p = a.data() + (size_t)M * (v + 3 * u);
+                for (int64_t i = 0; i < M; ++i)
+                    if (p[i] != cplx(0.0)) return true;
+            }
+    return false;
+}
+
+int fdfd_set_eps(fdfd_handle h, const fdfd_c128 *eps, int has_offdiag) {
+    CHECK_H(h);
+    if (!eps) return set_err(c, FDFD_EINVAL, "fdfd_set_eps: null argument");
+    const int64_t M = c->d.N[0] * c->d.N[1] * (c->k1 - c->k0);
+    const cplx *p = reinterpret_cast<const cplx *>(eps);
+    try {
+        c->eps_host.assign(p, p + 9 * M);
+    } catch (const std::bad_alloc &) {
+        return set_err(c, FDFD_ENOMEM, "fdfd_set_eps: out of host memory");
+    }
+    if (!has_offdiag) {
+        c->eps_off = false;
+    } else {
+        c->eps_off = offdiag_nonzero(c->eps_host, M);
+    }
+    if (c->d.field_type == FDFD_FT_HH && c->eps_off)
+        return set_err(c, FDFD_EINVAL, "FT_HH: Peps must be diagonal (reference model.jl:239)");
+    c->have_eps = true;
+    c->dirty = true;
+    return FDFD_OK;
+}
+
+int fdfd_set_mu(fdfd_handle h, const fdfd_c128 *mu) {
+    CHECK_H(h);
+    const int64_t M = c->d.N[0] * c->d.N[1] * (c->k1 - c->k0);
+    if (!mu) {
+        c->mu_host.clear();
+        c->mu_host.shrink_to_fit();
+        c->have_mu = false;
+    } else {
+        const cplx *p = reinterpret_cast<const cplx *>(mu);
+        try {
+            c->mu_host.assign(p, p + 9 * M);
+        } catch (const std::bad_alloc &) {
+            return set_err(c, FDFD_ENOMEM, "fdfd_set_mu: out of host memory");
+        }
+        if (offdiag_nonzero(c->mu_host, M)) {
+            c->mu_host.clear();
+            // reference: `Pmu \ Ce` (model.jl:236) is unsupported for non-diagonal Pmu; for FT_HH the mass
+            // operator with off-diagonal mu is not built yet either.
+            return set_err(c, FDFD_EINVAL, "mu must be diagonal (reference model.jl:236)");
+        }
+        c->have_mu = true;
+    }
+    c->dirty = true;
+    return FDFD_OK;
+}
+
+int fdfd_apply(fdfd_handle h, const fdfd_c128 *x, fdfd_c128 *y, int where) {
+    CHECK_H(h);
+    if (!x || !y) return set_err(c, FDFD_EINVAL, "fdfd_apply: null argument");
+    int r;
+    if (where == FDFD_DEVICE) {
+        r = apply_device(c, reinterpret_cast<const double2 *>(x), reinterpret_cast<double2 *>(y), false);
+        if (r != FDFD_OK) return r;
+    } else if (where == FDFD_HOST) {
+        if ((r = stage_buffers(c)) != FDFD_OK) return r;
+        const size_t bytes = (size_t)c->nloc * sizeof(double2);
+        FDFD_CUDA(c, cudaMemcpyAsync(c->stage_x, x, bytes, cudaMemcpyHostToDevice, c->stream));
+        if ((r = apply_device(c, c->stage_x, c->stage_y, false)) != FDFD_OK) return r;
+        FDFD_CUDA(c, cudaMemcpyAsync(y, c->stage_y, bytes, cudaMemcpyDeviceToHost, c->stream));
+    } else {
+        return set_err(c, FDFD_EINVAL, "fdfd_apply: bad `where`");
+    }
+    FDFD_CUDA(c, cudaStreamSynchronize(c->stream));
+    return FDFD_OK;
+}
+
+int fdfd_apply_transpose(fdfd_handle h, const fdfd_c128 *x, fdfd_c128 *y, int where) {
+    CHECK_H(h);
+    if (!x || !y) return set_err(c, FDFD_EINVAL, "fdfd_apply_transpose: null argument");
+    int r;
+    if (where == FDFD_DEVICE) {
+        r = apply_device(c, reinterpret_cast<const double2 *>(x), reinterpret_cast<double2 *>(y), true);
+        if (r != FDFD_OK) return r;
+    } else if (where == FDFD_HOST) {
+        if ((r = stage_buffers(c)) != FDFD_OK) return r;
+        const size_t bytes = (size_t)c->nloc * sizeof(double2);
+        FDFD_CUDA(c, cudaMemcpyAsync(c->stage_x, x, bytes, cudaMemcpyHostToDevice, c->stream));
+        if ((r = apply_device(c, c->stage_x, c->stage_y, true)) != FDFD_OK) return r;
+        FDFD_CUDA(c, cudaMemcpyAsync(y, c->stage_y, bytes, cudaMemcpyDeviceToHost, c->stream));
+    } else {
+        return set_err(c, FDFD_EINVAL, "fdfd_apply_transpose: bad `where`");
+    }
+    FDFD_CUDA(c, cudaStreamSynchronize(c->stream));
+    return FDFD_OK;
+}
+
+int fdfd_solve(fdfd_handle h, int method, const fdfd_c128 *b, fdfd_c128 *x, int where, double rtol, int maxit,
+               int check_every, int *iters, double *relres, double *hist) {
+    CHECK_H(h);
+    if (!b || !x || maxit < 0 || !(rtol >= 0)) return set_err(c, FDFD_EINVAL, "fdfd_solve: bad argument");
+    if (method != FDFD_BICGSTAB && method != FDFD_QMR) return set_err(c, FDFD_EINVAL, "fdfd_solve: unknown method");
+    if (check_every < 1) check_every = 1;
+    int r, it = 0;
+    double rr = 0;
+    if (where == FDFD_DEVICE) {
+        r = krylov_solve(c, method, reinterpret_cast<const double2 *>(b), reinterpret_cast<double2 *>(x), rtol, maxit,
+                         check_every, false, &it, &rr, hist);
+    } else if (where == FDFD_HOST) {
+        if ((r = stage_buffers(c)) != FDFD_OK) return r;
+        const size_t bytes = (size_t)c->nloc * sizeof(double2);
+        FDFD_CUDA(c, cudaMemcpyAsync(c->stage_x, b, bytes, cudaMemcpyHostToDevice, c->stream));
+        FDFD_CUDA(c, cudaMemcpyAsync(c->stage_y, x, bytes, cudaMemcpyHostToDevice, c->stream));
+        r = krylov_solve(c, method, c->stage_x, c->stage_y, rtol, maxit, check_every, false, &it, &rr, hist);
+        if (r == FDFD_OK || r == FDFD_ENOCONV) {
+            FDFD_CUDA(c, cudaMemcpyAsync(x, c->stage_y, bytes, cudaMemcpyDeviceToHost, c->stream));
+            FDFD_CUDA(c, cudaStreamSynchronize(c->stream));
+        }
+    } else {
+        return set_err(c, FDFD_EINVAL, "fdfd_solve: bad `where`");
+    }
+    if (iters) *iters = it;
+    if (relres) *relres = rr;
+    return r;
+}
+
+int fdfd_export_pattern(fdfd_handle h, int64_t *colptr, int64_t *rowval, fdfd_c128 *nzval, int64_t *nnz_inout) {
+    CHECK_H(h);
+    return export_pattern(c, colptr, rowval, nzval, nnz_inout);
+}
+
+int fdfd_h_from_e(fdfd_handle h, const fdfd_c128 *e, const fdfd_c128 *jm, fdfd_c128 *hout, int where) {
+    CHECK_H(h);
+    if (!e || !hout) return set_err(c, FDFD_EINVAL, "fdfd_h_from_e: null argument");
+    if (c->d.field_type != FDFD_FT_EE) return set_err(c, FDFD_EINVAL, "fdfd_h_from_e needs an FT_EE handle");
+    if (c->omega == cplx(0.0)) return set_err(c, FDFD_EINVAL, "fdfd_h_from_e: omega == 0");
+    int r = ensure_ready(c);
+    if (r != FDFD_OK) return r;
+    const size_t bytes = (size_t)c->nloc * sizeof(double2);
+    const double2 *de = reinterpret_cast<const double2 *>(e), *dj = reinterpret_cast<const double2 *>(jm);
+    double2 *dh = reinterpret_cast<double2 *>(hout);
+    double2 *tmpj = nullptr;
+    if (where == FDFD_HOST) {
+        if ((r = stage_buffers(c)) != FDFD_OK) return r;
+        FDFD_CUDA(c, cudaMemcpyAsync(c->stage_x, e, bytes, cudaMemcpyHostToDevice, c->stream));
+        if (jm) {
+            FDFD_CUDA(c, cudaMalloc((void **)&tmpj, bytes));
+            FDFD_CUDA(c, cudaMemcpyAsync(tmpj, jm, bytes, cudaMemcpyHostToDevice, c->stream));
+            dj = tmpj;
+        }
+        de = c->stage_x;
+        dh = c->stage_y;
+    }
+    ApplyParams p;
+    fill_params(c, p, de, dh, false);
+    if (c->d.nranks > 1 && (r = halo_exchange(c, de, c->halo_lo, c->halo_hi, c->stream)) != FDFD_OK) return r;
+    const cplx a = cplx(0.0, 1.0) / c->omega;
+    FDFD_CUDA(c, launch_curl1(p, dj, make_double2(a.real(), a.imag()), c->stream));
+    c->launches += 1;
+    if (where == FDFD_HOST) FDFD_CUDA(c, cudaMemcpyAsync(hout, c->stage_y, bytes, cudaMemcpyDeviceToHost, c->stream));
+    FDFD_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (tmpj) cudaFree(tmpj);
+    return FDFD_OK;
+}
+
+int fdfd_create_b(fdfd_handle h, const fdfd_c128 *je, const fdfd_c128 *jm, fdfd_c128 *b, int where) {
+    CHECK_H(h);
+    if (!je || !b) return set_err(c, FDFD_EINVAL, "fdfd_create_b: null argument");
+    if (c->d.field_type != FDFD_FT_EE) return set_err(c, FDFD_EINVAL, "fdfd_create_b needs an FT_EE handle");
+    int r = ensure_ready(c);
+    if (r != FDFD_OK) return r;
+    const size_t bytes = (size_t)c->nloc * sizeof(double2);
+    const double2 *dje = reinterpret_cast<const double2 *>(je), *djm = reinterpret_cast<const double2 *>(jm);
+    double2 *db = reinterpret_cast<double2 *>(b);
+    double2 *tmp = nullptr;
+    if (where == FDFD_HOST) {
+        if ((r = stage_buffers(c)) != FDFD_OK) return r;
+        FDFD_CUDA(c, cudaMemcpyAsync(c->stage_x, je, bytes, cudaMemcpyHostToDevice, c->stream));
+        dje = c->stage_x;
+        if (jm) {
+            FDFD_CUDA(c, cudaMalloc((void **)&tmp, bytes));
+            FDFD_CUDA(c, cudaMemcpyAsync(tmp, jm, bytes, cudaMemcpyHostToDevice, c->stream));
+            djm = tmp;
+        }
+        db = c->stage_y;
+    }
+    ApplyParams p;
+    fill_params(c, p, djm ? djm : dje, db, false);
+    if (djm && c->d.nranks > 1 && (r = halo_exchange(c, djm, c->halo_lo, c->halo_hi, c->stream)) != FDFD_OK) return r;
+    // b = -Cm (mu^-1 jm) - i w je ; the second term is skipped for w == 0 (model.jl:265)
+    const cplx gm = -cplx(0.0, 1.0) * c->omega;
+    FDFD_CUDA(c, launch_curl2(p, c->omega == cplx(0.0) ? nullptr : dje, make_double2(-1.0, 0.0),
+                              make_double2(gm.real(), gm.imag()), djm ? 1 : 0, c->stream));
+    c->launches += 1;
+    if (where == FDFD_HOST) FDFD_CUDA(c, cudaMemcpyAsync(b, c->stage_y, bytes, cudaMemcpyDeviceToHost, c->stream));
+    FDFD_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (tmp) cudaFree(tmp);
+    return FDFD_OK;
+}
+
+int fdfd_comm_unique_id(char id[128]) {
+    std::string err;
+    int r = comm_unique_id(id, err);
+    if (r != FDFD_OK) set_err(nullptr, r, err);
+    return r;
+}
+
+int fdfd_comm_init(fdfd_handle h, const char id[128]) {
+    CHECK_H(h);
+    if (c->d.nranks == 1) return FDFD_OK;
+    return comm_init(c, id);
+}
+
+int fdfd_bench_apply(fdfd_handle h, const fdfd_c128 *x, fdfd_c128 *y, int warmup, int iters, int flush_l2,
+                     double *ms_total, double *ms_min) {
+    CHECK_H(h);
+    if (!x || !y || iters < 1 || warmup < 0) return set_err(c, FDFD_EINVAL, "fdfd_bench_apply: bad argument");
+    { int r0 = ensure_ready(c); if (r0 != FDFD_OK) return r0; }
+    const double2 *dx = reinterpret_cast<const double2 *>(x);
+    double2 *dy = reinterpret_cast<double2 *>(y);
+    int r;
+    if (flush_l2 && !c->flush_buf) {
+        c->flush_bytes = (size_t)512 << 20;
+        FDFD_CUDA(c, cudaMalloc(&c->flush_buf, c->flush_bytes));
+    }
+    for (int i = 0; i < warmup; ++i)
+        if ((r = apply_device(c, dx, dy, false)) != FDFD_OK) return r;
+    cudaEvent_t e0, e1;
+    FDFD_CUDA(c, cudaEventCreate(&e0));
+    FDFD_CUDA(c, cudaEventCreate(&e1));
+    double total = 0, mn = 1e300;
+    FDFD_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (!flush_l2) {
+        // back-to-back applies, one event pair around the whole run (inputs must exceed L2)
+        FDFD_CUDA(c, cudaEventRecord(e0, c->stream));
+        for (int i = 0; i < iters; ++i)
+            if ((r = apply_device(c, dx, dy, false)) != FDFD_OK) return r;
+        FDFD_CUDA(c, cudaEventRecord(e1, c->stream));
+        FDFD_CUDA(c, cudaEventSynchronize(e1));
+        float ms = 0;
+        FDFD_CUDA(c, cudaEventElapsedTime(&ms, e0, e1));
+        total = ms;
+        mn = ms / iters;
+    } else {
+        for (int i = 0; i < iters; ++i) {
+            flush_kernel<<<148 * 8, 256, 0, c->stream>>>((float4 *)c->flush_buf, (int64_t)(c->flush_bytes / 16), (float)i);
+            FDFD_CUDA(c, cudaEventRecord(e0, c->stream));
+            if ((r = apply_device(c, dx, dy, false)) != FDFD_OK) return r;
+            FDFD_CUDA(c, cudaEventRecord(e1, c->stream));
+            FDFD_CUDA(c, cudaEventSynchronize(e1));
+            float ms = 0;
+            FDFD_CUDA(c, cudaEventElapsedTime(&ms, e0, e1));
+            total += ms;
+            if (ms < mn) mn = ms;
+        }
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (ms_total) *ms_total = total;
+    if (ms_min) *ms_min = mn;
+    return FDFD_OK;
+}
+
+int fdfd_bench_solve(fdfd_handle h, int method, const fdfd_c128 *b, fdfd_c128 *x, int warmup, int iters,
+                     double *ms_total) {
+    CHECK_H(h);
+    if (!b || !x || iters < 1 || warmup < 0) return set_err(c, FDFD_EINVAL, "fdfd_bench_solve: bad argument");
+    { int r0 = ensure_ready(c); if (r0 != FDFD_OK) return r0; }
+    int it = 0, r;
+    double rr = 0;
+    const double2 *db = reinterpret_cast<const double2 *>(b);
+    double2 *dx = reinterpret_cast<double2 *>(x);
+    if (warmup > 0) {
+        r = krylov_solve(c, method, db, dx, 0.0, warmup, 1 << 30, true, &it, &rr, nullptr);
+        if (r != FDFD_OK && r != FDFD_ENOCONV) return r;
+    }
+    cudaEvent_t e0, e1;
+    FDFD_CUDA(c, cudaEventCreate(&e0));
+    FDFD_CUDA(c, cudaEventCreate(&e1));
+    FDFD_CUDA(c, cudaStreamSynchronize(c->stream));
+    FDFD_CUDA(c, cudaEventRecord(e0, c->stream));
+    r = krylov_solve(c, method, db, dx, 0.0, iters, 1 << 30, true, &it, &rr, nullptr);
+    FDFD_CUDA(c, cudaEventRecord(e1, c->stream));
+    FDFD_CUDA(c, cudaEventSynchronize(e1));
+    float ms = 0;
+    FDFD_CUDA(c, cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (ms_total) *ms_total = ms;
+    if (r == FDFD_ENOCONV) r = FDFD_OK;
+    return r;
+}
+
+int64_t fdfd_launch_count(fdfd_handle h) { return h ? static_cast<Ctx *>(h)->launches : 0; }
+
+int fdfd_host_alloc(void **p, uint64_t bytes) {
+    if (!p) return FDFD_EINVAL;
+    cudaError_t e = cudaMallocHost(p, bytes);
+    if (e != cudaSuccess) return set_err(nullptr, FDFD_ENOMEM, cudaGetErrorString(e));
+    return FDFD_OK;
+}
+int fdfd_host_free(void *p) { return cudaFreeHost(p) == cudaSuccess ? FDFD_OK : FDFD_ECUDA; }
+
+int fdfd_dev_alloc(fdfd_handle h, void **p, uint64_t bytes) {
+    CHECK_H(h);
+    if (c->dev == -2) return set_err(c, FDFD_ESTATE, "host-only handle");
+    if (!p) return set_err(c, FDFD_EINVAL, "null argument");
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess) return set_err(c, FDFD_ENOMEM, cudaGetErrorString(e));
+    return FDFD_OK;
+}
+int fdfd_dev_free(fdfd_handle h, void *p) {
+    CHECK_H(h);
+    if (c->dev == -2) return set_err(c, FDFD_ESTATE, "host-only handle");
+    FDFD_CUDA(c, cudaFree(p));
+    return FDFD_OK;
+}
+int fdfd_memcpy(fdfd_handle h, void *dst, const void *src, uint64_t bytes, int dst_where, int src_where) {
+    CHECK_H(h);
+    if (c->dev == -2) return set_err(c, FDFD_ESTATE, "host-only handle");
+    cudaMemcpyKind k = dst_where == FDFD_DEVICE
+                           ? (src_where == FDFD_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice)
+                           : (src_where == FDFD_DEVICE ? cudaMemcpyDeviceToHost : cudaMemcpyHostToHost);
+    FDFD_CUDA(c, cudaMemcpyAsync(dst, src, bytes, k, c->stream));
+    FDFD_CUDA(c, cudaStreamSynchronize(c->stream));
+    return FDFD_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,201 @@
+// General (any boundft / layout / field type) matrix-free apply: one thread per cell, gathers through
+// L1/L2.  It is the on-device cross-check of the tiled kernel and the path for configurations the
+// tiled kernel does not cover.  Not tuned; see apply_tiled.cu for the roofline kernel.
+//
+// Computes, per SURVEY.md App. A.4-A.5 (reference composition model.jl:236-237):
+//   y = C2 ( q .* (C1 x) ) + massd .* x + Mout[ masso .* (Min x) ]
+// where C1/C2/Min/Mout are given by 1-D coefficient arrays (coeffs.cpp) and massd/masso are the
+// material entries pre-multiplied by -w^2.
+#include "cplx.cuh"
+#include "fdfd_internal.h"
+
+namespace fdfd {
+
+namespace {
+
+struct Gather {
+    const ApplyParams &p;
+    __device__ __forceinline__ int wrapx(int i) const { return i < 0 ? i + p.Nx : (i >= p.Nx ? i - p.Nx : i); }
+    __device__ __forceinline__ int wrapy(int j) const { return j < 0 ? j + p.Ny : (j >= p.Ny ? j - p.Ny : j); }
+    __device__ __forceinline__ int kglob(int kl) const {
+        int k = p.kz0 + kl;
+        return k < 0 ? k + p.Nz : (k >= p.Nz ? k - p.Nz : k);
+    }
+    // E_c at (i,j,kl): i,j in range, kl in [-1, nzl]
+    __device__ __forceinline__ double2 E(int c, int i, int j, int kl) const {
+        const double2 *base;
+        int64_t cs;
+        if (kl < 0) { base = p.x.lo; cs = p.x.cs_lo; }
+        else if (kl >= p.nzl) { base = p.x.hi; cs = p.x.cs_hi; }
+        else { base = p.x.base + (int64_t)kl * p.x.pstride; cs = p.x.cs; }
+        return base[(int64_t)c * cs + ((int64_t)j * p.Nx + i) * p.x.es];
+    }
+    __device__ __forceinline__ int64_t gidx(int i, int j, int kl) const {
+        return ((int64_t)(kl + 1) * p.Ny + j) * p.Nx + i;
+    }
+    // E_c at cell shifted by s along axis w
+    __device__ __forceinline__ double2 Esh(int c, int i, int j, int kl, int w, int s) const {
+        if (w == 0) return E(c, wrapx(i + s), j, kl);
+        if (w == 1) return E(c, i, wrapy(j + s), kl);
+        return E(c, i, j, kl + s);
+    }
+    __device__ __forceinline__ int cidx(int w, int i, int j, int kl) const {
+        return w == 0 ? i : (w == 1 ? j : kglob(kl));
+    }
+    // first curl, component u, at (i,j,kl)
+    __device__ double2 H(int u, int i, int j, int kl) const {
+        const int wa = (u + 1) % 3, ca = (u + 2) % 3;
+        const int wb = (u + 2) % 3, cb = (u + 1) % 3;
+        const int ia = cidx(wa, i, j, kl), ib = cidx(wb, i, j, kl);
+        double2 t = c_mul(p.c.a0[wa][ia], E(ca, i, j, kl));
+        t = c_fma(p.c.a1[wa][ia], Esh(ca, i, j, kl, wa, p.s1[wa]), t);
+        t = c_fms(p.c.a0[wb][ib], E(cb, i, j, kl), t);
+        t = c_fms(p.c.a1[wb][ib], Esh(cb, i, j, kl, wb, p.s1[wb]), t);
+        if (p.has_q) t = c_mul(p.q[u][gidx(i, j, kl)], t);
+        return t;
+    }
+    __device__ __forceinline__ double2 Hsh(int u, int i, int j, int kl, int w, int s) const {
+        if (w == 0) return H(u, wrapx(i + s), j, kl);
+        if (w == 1) return H(u, i, wrapy(j + s), kl);
+        return H(u, i, j, kl + s);
+    }
+    // input average of component u along its own axis, at corner (i,j,kl)
+    __device__ double2 Ain(int u, int i, int j, int kl) const {
+        const int iu = cidx(u, i, j, kl);
+        double2 t = c_mul(p.c.mi0[u][iu], E(u, i, j, kl));
+        return c_fma(p.c.mi1[u][iu], Esh(u, i, j, kl, u, -p.s1[u]), t);
+    }
+    // corner quantity G_v = sum_{u != v} masso_vu * Ain_u
+    __device__ double2 G(int v, int i, int j, int kl) const {
+        const int u1 = (v + 1) % 3, u2 = (v + 2) % 3;
+        const int64_t g = gidx(i, j, kl);
+        // index of (v,u) in the off-diagonal list (0,1),(0,2),(1,0),(1,2),(2,0),(2,1)
+        const int e1 = 2 * v + (u1 > v ? u1 - 1 : u1);
+        const int e2 = 2 * v + (u2 > v ? u2 - 1 : u2);
+        double2 t = c_mul(p.mo[e1][g], Ain(u1, i, j, kl));
+        return c_fma(p.mo[e2][g], Ain(u2, i, j, kl), t);
+    }
+    __device__ __forceinline__ double2 Gsh(int v, int i, int j, int kl, int s) const {
+        if (v == 0) return G(v, wrapx(i + s), j, kl);
+        if (v == 1) return G(v, i, wrapy(j + s), kl);
+        return G(v, i, j, kl + s);
+    }
+};
+
+__global__ void __launch_bounds__(128) apply_naive_kernel(const __grid_constant__ ApplyParams p) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    const int kl = blockIdx.z;
+    if (i >= p.Nx) return;
+    Gather g{p};
+#pragma unroll
+    for (int v = 0; v < 3; ++v) {
+        const int w1 = (v + 1) % 3, u1 = (v + 2) % 3;
+        const int w2 = (v + 2) % 3, u2 = (v + 1) % 3;
+        const int i1 = g.cidx(w1, i, j, kl), i2 = g.cidx(w2, i, j, kl);
+        double2 y = c_mul(p.c.b0[w1][i1], g.H(u1, i, j, kl));
+        y = c_fma(p.c.b1[w1][i1], g.Hsh(u1, i, j, kl, w1, -p.s1[w1]), y);
+        y = c_fms(p.c.b0[w2][i2], g.H(u2, i, j, kl), y);
+        y = c_fms(p.c.b1[w2][i2], g.Hsh(u2, i, j, kl, w2, -p.s1[w2]), y);
+        if (p.has_mass) {
+            y = c_fma(p.md[v][g.gidx(i, j, kl)], g.E(v, i, j, kl), y);
+            if (p.has_off) {
+                const int iv = g.cidx(v, i, j, kl);
+                y = c_fma(p.c.mo0[v][iv], g.G(v, i, j, kl), y);
+                y = c_fma(p.c.mo1[v][iv], g.Gsh(v, i, j, kl, p.s1[v]), y);
+            }
+        }
+        p.y[(int64_t)kl * p.y_pstride + (int64_t)v * p.y_cs + ((int64_t)j * p.Nx + i) * p.y_es] = y;
+    }
+}
+
+// h = alpha * q .* (C1 e + jm)       (h_from_e, reference model.jl:276-279)
+__global__ void __launch_bounds__(128) curl1_kernel(const __grid_constant__ ApplyParams p, const double2 *jm,
+                                                     double2 alpha) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    const int kl = blockIdx.z;
+    if (i >= p.Nx) return;
+    Gather g{p};
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+        const int wa = (u + 1) % 3, ca = (u + 2) % 3;
+        const int wb = (u + 2) % 3, cb = (u + 1) % 3;
+        const int ia = g.cidx(wa, i, j, kl), ib = g.cidx(wb, i, j, kl);
+        double2 t = c_mul(p.c.a0[wa][ia], g.E(ca, i, j, kl));
+        t = c_fma(p.c.a1[wa][ia], g.Esh(ca, i, j, kl, wa, p.s1[wa]), t);
+        t = c_fms(p.c.a0[wb][ib], g.E(cb, i, j, kl), t);
+        t = c_fms(p.c.a1[wb][ib], g.Esh(cb, i, j, kl, wb, p.s1[wb]), t);
+        const int64_t o = (int64_t)kl * p.y_pstride + (int64_t)u * p.y_cs + ((int64_t)j * p.Nx + i) * p.y_es;
+        if (jm) t = c_add(t, jm[o]);
+        if (p.has_q) t = c_mul(p.q[u][g.gidx(i, j, kl)], t);
+        p.y[o] = c_mul(alpha, t);
+    }
+}
+
+
+// y = beta * C2 (q .* h) + gamma * je      (create_b, reference model.jl:262-265: b = -Cm (Pmu \ jm) - i w je)
+// p.x holds h (may be null planes when has_h == 0).
+__global__ void __launch_bounds__(128) curl2_kernel(const __grid_constant__ ApplyParams p, const double2 *je,
+                                                     double2 beta, double2 gamma, int has_h) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    const int kl = blockIdx.z;
+    if (i >= p.Nx) return;
+    Gather g{p};
+    auto Hq = [&](int u, int ii, int jj, int kk) -> double2 {
+        double2 t = g.E(u, ii, jj, kk);
+        if (p.has_q) t = c_mul(p.q[u][g.gidx(ii, jj, kk)], t);
+        return t;
+    };
+    auto Hqsh = [&](int u, int w, int s) -> double2 {
+        if (w == 0) return Hq(u, g.wrapx(i + s), j, kl);
+        if (w == 1) return Hq(u, i, g.wrapy(j + s), kl);
+        return Hq(u, i, j, kl + s);
+    };
+#pragma unroll
+    for (int v = 0; v < 3; ++v) {
+        const int64_t o = (int64_t)kl * p.y_pstride + (int64_t)v * p.y_cs + ((int64_t)j * p.Nx + i) * p.y_es;
+        double2 y = c_zero();
+        if (has_h) {
+            const int w1 = (v + 1) % 3, u1 = (v + 2) % 3;
+            const int w2 = (v + 2) % 3, u2 = (v + 1) % 3;
+            const int i1 = g.cidx(w1, i, j, kl), i2 = g.cidx(w2, i, j, kl);
+            double2 t = c_mul(p.c.b0[w1][i1], Hq(u1, i, j, kl));
+            t = c_fma(p.c.b1[w1][i1], Hqsh(u1, w1, -p.s1[w1]), t);
+            t = c_fms(p.c.b0[w2][i2], Hq(u2, i, j, kl), t);
+            t = c_fms(p.c.b1[w2][i2], Hqsh(u2, w2, -p.s1[w2]), t);
+            y = c_mul(beta, t);
+        }
+        if (je) y = c_fma(gamma, je[o], y);
+        p.y[o] = y;
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_apply_naive(const ApplyParams &p, cudaStream_t s) {
+    dim3 block(128, 1, 1);
+    dim3 grid((p.Nx + 127) / 128, p.Ny, p.nzl);
+    apply_naive_kernel<<<grid, block, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_curl1(const ApplyParams &p, const double2 *jm, double2 alpha, cudaStream_t s) {
+    dim3 block(128, 1, 1);
+    dim3 grid((p.Nx + 127) / 128, p.Ny, p.nzl);
+    curl1_kernel<<<grid, block, 0, s>>>(p, jm, alpha);
+    return cudaGetLastError();
+}
+
+}  // namespace fdfd
+
+namespace fdfd {
+cudaError_t launch_curl2(const ApplyParams &p, const double2 *je, double2 beta, double2 gamma, int has_h,
+                         cudaStream_t s) {
+    dim3 block(128, 1, 1);
+    dim3 grid((p.Nx + 127) / 128, p.Ny, p.nzl);
+    curl2_kernel<<<grid, block, 0, s>>>(p, je, beta, gamma, has_h);
+    return cudaGetLastError();
+}
+}  // namespace fdfd

@@ -1,0 +1,441 @@
+// K1 - the roofline kernel: matrix-free y = C2 (q .* C1 x) + mass(x) for the default Yee arrangement
+// (first curl forward on every axis, i.e. boundft = (EE,EE,EE) for FT_EE), any boundary condition,
+// both DOF layouts, diagonal or full 3x3 material tensor.
+//
+// Replaces the per-iteration CSC SpMV `mul!(y, A, x)` on the matrix assembled by the reference's
+// create_A (src/model/model.jl:225-246); stencil per SURVEY.md App. A.4-A.6.
+//
+// Structure (2.5-D blocking, B200):
+//   * a CTA owns an x-y tile of TX x TY cells (thread (tx,ty) <-> one cell, all 3 components) and marches
+//     over a chunk of z-planes;
+//   * x planes are staged global -> shared by the TMA unit with 1-D bulk copies (cp.async.bulk, one per
+//     tile row [+ wrap pieces for Bloch boundaries]) completing on an mbarrier per ring stage; NST planes
+//     are in flight, so HBM latency is hidden by the copy engine, not by occupancy;
+//   * the intermediate field H = q .* C1 x never leaves the SM: own-cell values stay in registers, the
+//     3 neighbour values travel through a double-buffered shared tile (one __syncthreads per plane);
+//   * boundary conditions are pure data (1-D coefficient tables, coeffs.cpp): no divergent branches;
+//   * each x element is read from HBM once (+ halo re-reads that hit L2), y written once, material read once.
+// Tile: thread tile TX x TY covers cells [ox, ox+TX) x [oy, oy+TY); outputs are the inner (TX-2) x (TY-2).
+#include <cstdio>
+
+#include "cplx.cuh"
+#include "fdfd_internal.h"
+
+namespace fdfd {
+
+namespace {
+
+constexpr int NST = 3;  // ring stages (planes in flight)
+
+struct TiledParams {
+    ApplyParams a;
+    int32_t wrapx, wrapy;     // Bloch-periodic (load wrapped halo) vs symmetry (halo reads as zero)
+    int32_t ntx, nty, nchunk; // tiles and z-chunks
+    int32_t lz;               // planes per chunk
+    int32_t kl_begin, kl_end; // local plane range of this launch
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// TMA-unit 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <bool CMPFIRST, int TX, int TY>
+struct TileIdx {
+    // element index (in double2) of component c at tile position (tx,ty) inside one ring stage
+    __device__ __forceinline__ static int e(int c, int tx, int ty) {
+        return CMPFIRST ? (ty * TX + tx) * 3 + c : (c * TY + ty) * TX + tx;
+    }
+    // H / G tiles are always component-major (conflict-free 16-B lane stride)
+    __device__ __forceinline__ static int h(int c, int tx, int ty) { return (c * TY + ty) * TX + tx; }
+};
+
+template <bool CMPFIRST, bool HAS_OFF, bool HAS_Q, int TX, int TY>
+__global__ void __launch_bounds__(TX *TY, 1) apply_tiled_kernel(const __grid_constant__ TiledParams tp) {
+    using TI = TileIdx<CMPFIRST, TX, TY>;
+    constexpr int NT = TX * TY;
+    constexpr int STAGE = NT * 3;  // double2 per ring stage
+
+    const ApplyParams &p = tp.a;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double2 *ering = reinterpret_cast<double2 *>(smem_raw);           // NST * STAGE
+    double2 *hbuf = ering + NST * STAGE;                              // 2 * STAGE
+    double2 *gbuf = hbuf + 2 * STAGE;                                 // HAS_OFF ? 2 * 2 * NT : 0
+    double2 *cxs = gbuf + (HAS_OFF ? 4 * NT : 0);                     // 8 * TX  x-coefficient tables
+    double2 *cys = cxs + 8 * TX;                                      // 8 * TY
+    uint64_t *bars = reinterpret_cast<uint64_t *>(cys + 8 * TY);      // NST
+
+    const int tid = threadIdx.x;
+    const int tx = tid % TX, ty = tid / TX;
+
+    // ---- work item -----------------------------------------------------------------------------
+    int b = blockIdx.x;
+    const int tile_x = b % tp.ntx;
+    b /= tp.ntx;
+    const int tile_y = b % tp.nty;
+    const int chunk = b / tp.nty;
+    const int ox = tile_x * (TX - 2) - 1, oy = tile_y * (TY - 2) - 1;
+    const int kc0 = tp.kl_begin + chunk * tp.lz;
+    const int kc1 = min(kc0 + tp.lz, tp.kl_end);
+    const int nplanes = kc1 - kc0 + 2;  // planes kc0-1 .. kc1
+
+    const int Nx = p.Nx, Ny = p.Ny;
+    const int gi = ox + tx, gj = oy + ty;
+    // coefficient / material indices: wrapped into range (positions far outside the domain are masked)
+    const int ci = ((gi % Nx) + Nx) % Nx, cj = ((gj % Ny) + Ny) % Ny;
+    const bool out_ok = (tx >= 1) && (tx <= TX - 2) && (ty >= 1) && (ty <= TY - 2) && (gi < Nx) && (gj < Ny);
+
+    // ---- geometry of the bulk copies of one plane (identical for every plane of this CTA) ----------
+    const int xlo = max(ox, 0), xhi = min(ox + TX, Nx);                // main segment, cells [xlo,xhi)
+    const bool lwrap = (ox < 0) && tp.wrapx;                           // cell Nx-1 -> tile pos 0
+    const bool rwrap = (ox + TX > Nx) && tp.wrapx;                     // cell 0    -> tile pos Nx-ox
+    auto row_src = [&](int r) -> int {                                 // source row of tile row r, or -1
+        const int j = oy + r;
+        if (j >= 0 && j < Ny) return j;
+        if (tp.wrapy && (j == -1 || j == Ny)) return j < 0 ? Ny - 1 : 0;
+        return -1;
+    };
+    int nrows = 0;
+    for (int r = 0; r < TY; ++r) nrows += (row_src(r) >= 0);
+    const uint32_t stage_bytes = (uint32_t)nrows * (uint32_t)((xhi - xlo) + (lwrap ? 1 : 0) + (rwrap ? 1 : 0)) * 48u;
+
+    auto plane_ptr = [&](int kk, int64_t &cs) -> const double2 * {
+        if (kk < 0) { cs = p.x.cs_lo; return p.x.lo; }
+        if (kk >= p.nzl) { cs = p.x.cs_hi; return p.x.hi; }
+        cs = p.x.cs;
+        return p.x.base + (int64_t)kk * p.x.pstride;
+    };
+    // issue the copies of load #n (plane kc0-1+n) into ring stage n % NST; executed by warp 0
+    auto issue_load = [&](int n) {
+        const int lane = tid;  // tid < 32
+        uint64_t *bar = &bars[n % NST];
+        double2 *dst = ering + (n % NST) * STAGE;
+        int64_t cs;
+        const double2 *src = plane_ptr(kc0 - 1 + n, cs);
+        if (lane == 0) mbar_arrive_expect_tx(bar, stage_bytes);
+        __syncwarp();
+        if (CMPFIRST) {
+            for (int r = lane; r < TY; r += 32) {
+                const int j = row_src(r);
+                if (j < 0) continue;
+                const double2 *srow = src + (int64_t)j * Nx * 3;
+                double2 *drow = dst + r * TX * 3;
+                bulk_g2s(drow + (xlo - ox) * 3, srow + (int64_t)xlo * 3, (uint32_t)(xhi - xlo) * 48u, bar);
+                if (lwrap) bulk_g2s(drow, srow + (int64_t)(Nx - 1) * 3, 48u, bar);
+                if (rwrap) bulk_g2s(drow + (Nx - ox) * 3, srow, 48u, bar);
+            }
+        } else {
+            for (int q = lane; q < 3 * TY; q += 32) {
+                const int c = q / TY, r = q % TY;
+                const int j = row_src(r);
+                if (j < 0) continue;
+                const double2 *srow = src + (int64_t)c * cs + (int64_t)j * Nx;
+                double2 *drow = dst + (c * TY + r) * TX;
+                bulk_g2s(drow + (xlo - ox), srow + xlo, (uint32_t)(xhi - xlo) * 16u, bar);
+                if (lwrap) bulk_g2s(drow, srow + (Nx - 1), 16u, bar);
+                if (rwrap) bulk_g2s(drow + (Nx - ox), srow, 16u, bar);
+            }
+        }
+    };
+
+    // ---- prologue ---------------------------------------------------------------------------------
+    if (tid == 0) {
+        for (int s = 0; s < NST; ++s) mbar_init(&bars[s], 1);
+        fence_barrier_init();
+    }
+    {   // zero the tile positions no copy ever writes (symmetry-boundary halos, overhang): their values are
+        // multiplied by zero coefficients or feed masked outputs, but must be finite
+        const bool xcov = (gi >= 0 && gi < Nx) || (tp.wrapx && (gi == -1 || gi == Nx));
+        const bool ycov = row_src(ty) >= 0;
+        if (!(xcov && ycov)) {
+            for (int s = 0; s < NST; ++s)
+                for (int c = 0; c < 3; ++c) ering[s * STAGE + TI::e(c, tx, ty)] = c_zero();
+        }
+        // coefficient tables
+        for (int t = tid; t < 8 * TX; t += NT) {
+            const int a = t / TX, x = t % TX;
+            const int i = (((ox + x) % Nx) + Nx) % Nx;
+            const double2 *src = a == 0 ? p.c.a0[0] : a == 1 ? p.c.a1[0] : a == 2 ? p.c.b0[0] : a == 3 ? p.c.b1[0]
+                               : a == 4 ? p.c.mi0[0] : a == 5 ? p.c.mi1[0] : a == 6 ? p.c.mo0[0] : p.c.mo1[0];
+            cxs[t] = src[i];
+        }
+        for (int t = tid; t < 8 * TY; t += NT) {
+            const int a = t / TY, y = t % TY;
+            const int j = (((oy + y) % Ny) + Ny) % Ny;
+            const double2 *src = a == 0 ? p.c.a0[1] : a == 1 ? p.c.a1[1] : a == 2 ? p.c.b0[1] : a == 3 ? p.c.b1[1]
+                               : a == 4 ? p.c.mi0[1] : a == 5 ? p.c.mi1[1] : a == 6 ? p.c.mo0[1] : p.c.mo1[1];
+            cys[t] = src[j];
+        }
+    }
+    __syncthreads();
+    if (tid < 32) {
+        const int npre = min(NST, nplanes);
+        for (int n = 0; n < npre; ++n) issue_load(n);
+    }
+
+    // loop-invariant shared offsets (neighbour positions clamped into the tile; clamped reads feed masked lanes)
+    const int txp = min(tx + 1, TX - 1), typ = min(ty + 1, TY - 1);
+    const int txm = max(tx - 1, 0), tym = max(ty - 1, 0);
+    const int eo0 = TI::e(0, tx, ty), eo1 = TI::e(1, tx, ty), eo2 = TI::e(2, tx, ty);
+    const int exp1 = TI::e(1, txp, ty), exp2 = TI::e(2, txp, ty);   // E_y, E_z at x+1
+    const int eyp0 = TI::e(0, tx, typ), eyp2 = TI::e(2, tx, typ);   // E_x, E_z at y+1
+    const int exm0 = TI::e(0, txm, ty);                             // E_x at x-1 (in-average)
+    const int eym1 = TI::e(1, tx, tym);                             // E_y at y-1
+    const int ho0 = TI::h(0, tx, ty), ho1 = TI::h(1, tx, ty), ho2 = TI::h(2, tx, ty);
+    const int hxm1 = TI::h(1, txm, ty), hxm2 = TI::h(2, txm, ty);   // H_y, H_z at x-1
+    const int hym0 = TI::h(0, tx, tym), hym2 = TI::h(2, tx, tym);   // H_x, H_z at y-1
+    const int go0 = tid, go1 = NT + tid;                            // G_x, G_y own
+    const int gxp0 = ty * TX + txp, gyp1 = NT + typ * TX + tx;      // G_x at x+1, G_y at y+1
+
+    const double2 a0x = cxs[0 * TX + tx], a1x = cxs[1 * TX + tx];
+    const double2 a0y = cys[0 * TY + ty], a1y = cys[1 * TY + ty];
+
+    const int64_t Nxy = (int64_t)Nx * Ny;
+    const int64_t mcell = (int64_t)cj * Nx + ci;  // in-plane index into the ghosted material arrays
+
+    // E(k) own, H(k-1) own, G state
+    mbar_wait(&bars[0], 0);
+    double2 Eo0 = ering[eo0], Eo1 = ering[eo1], Eo2 = ering[eo2];
+    double2 Hpx = c_zero(), Hpy = c_zero();
+    double2 Gcx = c_zero(), Gcy = c_zero(), Gcz = c_zero();   // G(k) own
+    double2 Gnx_x = c_zero(), Gny_y = c_zero();               // G_x(k) at x+1, G_y(k) at y+1
+
+    for (int n = 0; n + 1 < nplanes; ++n) {
+        const int k = kc0 - 1 + n;                 // local plane whose H is computed (and y, if k >= kc0)
+        int kg = p.kz0 + k;                        // global z index for the coefficient tables
+        kg = kg < 0 ? kg + p.Nz : (kg >= p.Nz ? kg - p.Nz : kg);
+        int kg1 = kg + 1 >= p.Nz ? kg + 1 - p.Nz : kg + 1;
+        const double2 *es = ering + (n % NST) * STAGE;         // plane k
+        const double2 *en = ering + ((n + 1) % NST) * STAGE;   // plane k+1
+        const bool do_out = out_ok && (n >= 1);
+
+        // global loads issued early: material of plane k (outputs) and z coefficients
+        const double2 a0z = ldg2(&p.c.a0[2][kg]), a1z = ldg2(&p.c.a1[2][kg]);
+        const double2 b0z = ldg2(&p.c.b0[2][kg]), b1z = ldg2(&p.c.b1[2][kg]);
+        double2 md0 = c_zero(), md1 = c_zero(), md2 = c_zero();
+        const int64_t mk = (int64_t)(k + 1) * Nxy + mcell;     // ghosted plane index k+1
+        if (p.has_mass && do_out) {
+            md0 = ldg2(&p.md[0][mk]);
+            md1 = ldg2(&p.md[1][mk]);
+            md2 = ldg2(&p.md[2][mk]);
+        }
+        double2 q0, q1, q2;
+        if (HAS_Q) {
+            q0 = ldg2(&p.q[0][mk]);
+            q1 = ldg2(&p.q[1][mk]);
+            q2 = ldg2(&p.q[2][mk]);
+        }
+        double2 o01, o02, o10, o12, o20, o21, mi0z, mi1z;
+        if (HAS_OFF) {
+            const int64_t mk1 = mk + Nxy;                      // plane k+1
+            o01 = ldg2(&p.mo[0][mk1]); o02 = ldg2(&p.mo[1][mk1]);
+            o10 = ldg2(&p.mo[2][mk1]); o12 = ldg2(&p.mo[3][mk1]);
+            o20 = ldg2(&p.mo[4][mk1]); o21 = ldg2(&p.mo[5][mk1]);
+            mi0z = ldg2(&p.c.mi0[2][kg1]);
+            mi1z = ldg2(&p.c.mi1[2][kg1]);
+        }
+
+        mbar_wait(&bars[(n + 1) % NST], ((n + 1) / NST) & 1);
+        const double2 En0 = en[eo0], En1 = en[eo1], En2 = en[eo2];
+        const double2 Exp1 = es[exp1], Exp2 = es[exp2];
+        const double2 Eyp0 = es[eyp0], Eyp2 = es[eyp2];
+
+        // H(k) = C1 E :  Hx = Dy Ez - Dz Ey,  Hy = Dz Ex - Dx Ez,  Hz = Dx Ey - Dy Ex
+        double2 Hx = c_mul(a0y, Eo2);
+        Hx = c_fma(a1y, Eyp2, Hx);
+        Hx = c_fms(a0z, Eo1, Hx);
+        Hx = c_fms(a1z, En1, Hx);
+        double2 Hy = c_mul(a0z, Eo0);
+        Hy = c_fma(a1z, En0, Hy);
+        Hy = c_fms(a0x, Eo2, Hy);
+        Hy = c_fms(a1x, Exp2, Hy);
+        double2 Hz = c_mul(a0x, Eo1);
+        Hz = c_fma(a1x, Exp1, Hz);
+        Hz = c_fms(a0y, Eo0, Hz);
+        Hz = c_fms(a1y, Eyp0, Hz);
+        if (HAS_Q) {
+            Hx = c_mul(q0, Hx);
+            Hy = c_mul(q1, Hy);
+            Hz = c_mul(q2, Hz);
+        }
+        double2 *hb = hbuf + (n & 1) * STAGE;
+        hb[ho0] = Hx;
+        hb[ho1] = Hy;
+        hb[ho2] = Hz;
+
+        double2 Gnz = c_zero();   // G_z(k+1) own
+        double2 Gx1 = c_zero(), Gy1 = c_zero();
+        if (HAS_OFF) {
+            // neighbours of G(k) (written one iteration ago, visible since the previous barrier)
+            const double2 *gc = gbuf + (n & 1) * 2 * NT;
+            Gnx_x = gc[gxp0];
+            Gny_y = gc[gyp1];
+            // G(k+1) at this corner: in-averages of plane k+1, then the off-diagonal material entries
+            const double2 Ax = c_fma(cxs[5 * TX + tx], en[exm0], c_mul(cxs[4 * TX + tx], En0));
+            const double2 Ay = c_fma(cys[5 * TY + ty], en[eym1], c_mul(cys[4 * TY + ty], En1));
+            const double2 Az = c_fma(mi1z, Eo2, c_mul(mi0z, En2));
+            Gx1 = c_fma(o02, Az, c_mul(o01, Ay));
+            Gy1 = c_fma(o12, Az, c_mul(o10, Ax));
+            Gnz = c_fma(o21, Ay, c_mul(o20, Ax));
+            double2 *gn = gbuf + ((n + 1) & 1) * 2 * NT;
+            gn[go0] = Gx1;
+            gn[go1] = Gy1;
+        }
+        __syncthreads();
+
+        // ring stage of plane k is free now: refill it with load #(n + NST)
+        if (tid < 32 && n + NST < nplanes) issue_load(n + NST);
+
+        if (do_out) {
+            const double2 b0x = cxs[2 * TX + tx], b1x = cxs[3 * TX + tx];
+            const double2 b0y = cys[2 * TY + ty], b1y = cys[3 * TY + ty];
+            const double2 Hy_xm = hb[hxm1], Hz_xm = hb[hxm2];
+            const double2 Hx_ym = hb[hym0], Hz_ym = hb[hym2];
+            // y = C2 H :  yx = Dy Hz - Dz Hy,  yy = Dz Hx - Dx Hz,  yz = Dx Hy - Dy Hx   (backward differences)
+            double2 yx = c_mul(b0y, Hz);
+            yx = c_fma(b1y, Hz_ym, yx);
+            yx = c_fms(b0z, Hy, yx);
+            yx = c_fms(b1z, Hpy, yx);
+            double2 yy = c_mul(b0z, Hx);
+            yy = c_fma(b1z, Hpx, yy);
+            yy = c_fms(b0x, Hz, yy);
+            yy = c_fms(b1x, Hz_xm, yy);
+            double2 yz = c_mul(b0x, Hy);
+            yz = c_fma(b1x, Hy_xm, yz);
+            yz = c_fms(b0y, Hx, yz);
+            yz = c_fms(b1y, Hx_ym, yz);
+            if (p.has_mass) {
+                yx = c_fma(md0, Eo0, yx);
+                yy = c_fma(md1, Eo1, yy);
+                yz = c_fma(md2, Eo2, yz);
+                if (HAS_OFF) {
+                    const double2 mo0z = ldg2(&p.c.mo0[2][kg]), mo1z = ldg2(&p.c.mo1[2][kg]);
+                    yx = c_fma(cxs[6 * TX + tx], Gcx, yx);
+                    yx = c_fma(cxs[7 * TX + tx], Gnx_x, yx);
+                    yy = c_fma(cys[6 * TY + ty], Gcy, yy);
+                    yy = c_fma(cys[7 * TY + ty], Gny_y, yy);
+                    yz = c_fma(mo0z, Gcz, yz);
+                    yz = c_fma(mo1z, Gnz, yz);
+                }
+            }
+            double2 *yo = p.y + (int64_t)k * p.y_pstride + ((int64_t)gj * Nx + gi) * p.y_es;
+            yo[0] = yx;
+            yo[p.y_cs] = yy;
+            yo[2 * p.y_cs] = yz;
+        }
+        Hpx = Hx;
+        Hpy = Hy;
+        Eo0 = En0;
+        Eo1 = En1;
+        Eo2 = En2;
+        if (HAS_OFF) {
+            Gcx = Gx1;
+            Gcy = Gy1;
+            Gcz = Gnz;
+        }
+    }
+}
+
+template <bool CMPFIRST, bool HAS_OFF, bool HAS_Q, int TX, int TY>
+size_t tiled_smem_bytes() {
+    const size_t NT = TX * TY;
+    return (NST * NT * 3 + 2 * NT * 3 + (HAS_OFF ? 4 * NT : 0) + 8 * TX + 8 * TY) * sizeof(double2) + NST * 8 + 128;
+}
+
+template <bool CMPFIRST, bool HAS_OFF, bool HAS_Q, int TX, int TY>
+cudaError_t launch_variant(const TiledParams &tp, cudaStream_t s) {
+    auto kern = apply_tiled_kernel<CMPFIRST, HAS_OFF, HAS_Q, TX, TY>;
+    const size_t smem = tiled_smem_bytes<CMPFIRST, HAS_OFF, HAS_Q, TX, TY>();
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    const int grid = tp.ntx * tp.nty * tp.nchunk;
+    kern<<<grid, TX * TY, smem, s>>>(tp);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+bool tiled_supported(const ApplyParams &p) {
+    return p.s1[0] == 1 && p.s1[1] == 1 && p.s1[2] == 1 && p.nzl >= 1;
+}
+
+// Pick the z-chunk length: enough CTAs to fill 148 SMs for several waves, little ring-prologue overhead.
+static int pick_lz(int ncols, int nplanes) {
+    if (nplanes < 4) return nplanes;
+    const int sms = 148;
+    int best_lz = nplanes > 64 ? 64 : nplanes;
+    double best_cost = 1e300;
+    for (int lz = 4; lz <= 64 && lz <= nplanes; ++lz) {
+        const int nch = (nplanes + lz - 1) / lz;
+        const long ncta = (long)ncols * nch;
+        const long waves = (ncta + sms - 1) / sms;
+        // time ~ waves * (lz + ring prologue); the tail inefficiency is inside `waves`
+        const double cost = (double)waves * (lz + 2.5);
+        if (cost < best_cost) { best_cost = cost; best_lz = lz; }
+    }
+    return best_lz;
+}
+
+cudaError_t launch_apply_tiled(const ApplyParams &p, int kl_begin, int kl_end, cudaStream_t s, int *nlaunch) {
+    if (!tiled_supported(p)) return cudaErrorNotSupported;
+    if (kl_end <= kl_begin) return cudaSuccess;
+    constexpr int TX = 32, TY = 16;
+    TiledParams tp;
+    tp.a = p;
+    tp.wrapx = p.wrap[0];
+    tp.wrapy = p.wrap[1];
+    tp.ntx = (p.Nx + (TX - 2) - 1) / (TX - 2);
+    tp.nty = (p.Ny + (TY - 2) - 1) / (TY - 2);
+    tp.lz = pick_lz(tp.ntx * tp.nty, kl_end - kl_begin);
+    tp.nchunk = (kl_end - kl_begin + tp.lz - 1) / tp.lz;
+    tp.kl_begin = kl_begin;
+    tp.kl_end = kl_end;
+    const bool cf = tp.a.cmpfirst != 0, off = p.has_off != 0 && p.has_mass != 0, q = p.has_q != 0;
+    cudaError_t e;
+#define V(CF, OFF, Q) e = launch_variant<CF, OFF, Q, TX, TY>(tp, s)
+    if (cf) {
+        if (off) { if (q) V(true, true, true); else V(true, true, false); }
+        else     { if (q) V(true, false, true); else V(true, false, false); }
+    } else {
+        if (off) { if (q) V(false, true, true); else V(false, true, false); }
+        else     { if (q) V(false, false, true); else V(false, false, false); }
+    }
+#undef V
+    if (nlaunch) *nlaunch += 1;
+    return e;
+}
+
+}  // namespace fdfd

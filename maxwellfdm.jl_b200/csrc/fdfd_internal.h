@@ -1,0 +1,182 @@
+// Internal declarations of libfdfd_b200 (not part of the C ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <complex>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/fdfd_b200.h"
+
+namespace fdfd {
+
+using cplx = std::complex<double>;
+
+// ---------------------------------------------------------------------------------------------
+// Generic two-term 1-D operator:  (T f)[i] = t0[i] f[i] + t1[i] f[(i+s) mod N]
+// Every difference / averaging operator of the reference (create_∂, create_mean: SURVEY App. A.2,
+// A.3) with any boundary rule (Bloch phase, symmetry zeros, "0's and 2's") is of this form, so the
+// device code never branches on boundary conditions: they live in the 1-D coefficient arrays.
+// ---------------------------------------------------------------------------------------------
+struct AxisOp {
+    std::vector<cplx> t0, t1;
+    int shift = +1;
+};
+
+// Device view of the coefficient set of one operator application y = C2 q C1 x + (mass) x
+struct CoefDev {
+    const double2 *a0[3], *a1[3];    // first curl  (shift s1[w])
+    const double2 *b0[3], *b1[3];    // second curl (shift -s1[w])
+    const double2 *mi0[3], *mi1[3];  // input average of the mass operator  (shift -s1[w])
+    const double2 *mo0[3], *mo1[3];  // output average of the mass operator (shift +s1[w])
+};
+
+// A z-plane of a DOF vector: element (c,i,j) = p[c*cs + (j*Nx+i)*es]
+struct PlaneSet {
+    const double2 *base;  // plane kl=0 of this rank's slab
+    int64_t pstride;      // elements between consecutive planes
+    int64_t cs;           // component stride
+    int32_t es;           // cell stride (3 for cmp-first, 1 otherwise)
+    const double2 *lo;    // plane kl=-1   (same es; component stride cs_halo)
+    const double2 *hi;    // plane kl=nzl
+    int64_t cs_lo, cs_hi;
+};
+
+struct ApplyParams {
+    int32_t Nx, Ny, nzl;  // local slab extent
+    int32_t Nz;           // global
+    int32_t kz0;          // global index of local plane 0
+    int32_t s1[3];        // shift of the first curl per axis (+1 forward, -1 backward)
+    int32_t wrap[3];      // 1: Bloch-periodic axis (halo = wrapped cells), 0: symmetry boundary
+    int32_t cmpfirst;
+    int32_t has_mass, has_off, has_q;
+    CoefDev c;
+    // material arrays, SoA, ghosted in z: plane index kl+1, i.e. element (kl,j,i) at
+    // [(kl+1)*Nx*Ny + j*Nx + i]
+    const double2 *md[3];   // -w^2 * P_vv
+    const double2 *mo[6];   // -w^2 * P_vu, order (0,1),(0,2),(1,0),(1,2),(2,0),(2,1)
+    const double2 *q[3];    // inverse of the middle diagonal parameter (mu^-1 for FT_EE)
+    PlaneSet x;
+    double2 *y;             // output slab, same layout as x.base
+    int64_t y_pstride, y_cs;
+    int32_t y_es;
+    // fused epilogue/aux (unused by the naive kernel)
+};
+
+// ---------------------------------------------------------------------------------------------
+// Host context
+// ---------------------------------------------------------------------------------------------
+struct NcclApi;  // comm.cpp
+
+struct Ctx {
+    fdfd_desc d{};
+    int dev = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t stream_copy = nullptr;
+    std::string err;
+    int64_t launches = 0;
+
+    int64_t k0 = 0, k1 = 0;  // slab
+    int64_t nloc = 0;        // local DOFs
+    int64_t plane = 0;       // DOFs per z-plane (3*Nx*Ny)
+
+    // host copies of inputs
+    std::vector<cplx> sdl_e[3], sdl_m[3];
+    cplx phase[3] = {1.0, 1.0, 1.0};
+    cplx omega = 0.0;
+    bool have_coeffs = false, have_eps = false, have_omega = false;
+    bool eps_off = false, have_mu = false;
+    std::vector<cplx> eps_host;  // local slab, Julia layout (kept for re-scaling by omega and export)
+    std::vector<cplx> mu_host;
+
+    // device state
+    bool dirty = true;               // coefficient / material device arrays need rebuilding
+    double2 *coef_dev = nullptr;     // all 1-D coefficient arrays, forward and transposed sets
+    size_t coef_bytes = 0;
+    CoefDev cf{}, ct{};              // forward operator / transposed operator
+    double2 *mat_dev = nullptr;      // md[3], mo[6], q[3] ghosted slabs
+    size_t mat_bytes = 0;
+    const double2 *md[3]{}, *mo[6]{}, *mo_t[6]{}, *q[3]{};
+    int s1[3]{+1, +1, +1};
+
+    // halo buffers (device): 2 receive planes, 2 send staging not needed (planes are contiguous
+    // or 3 contiguous pieces)
+    double2 *halo_lo = nullptr, *halo_hi = nullptr;
+
+    // Krylov workspace
+    double2 *work = nullptr;
+    size_t work_bytes = 0;
+    double *scal = nullptr;          // device scalars
+    double *partial = nullptr;       // per-block partial sums
+    double *scal_host = nullptr;     // pinned
+    // staging for FDFD_HOST calls
+    double2 *stage_x = nullptr, *stage_y = nullptr;
+    void *flush_buf = nullptr;
+    size_t flush_bytes = 0;
+
+    // NCCL
+    void *comm = nullptr;
+    NcclApi *nccl = nullptr;
+};
+
+int set_err(Ctx *c, int code, const std::string &msg);
+
+#define FDFD_CUDA(c, call)                                                                         \
+    do {                                                                                            \
+        cudaError_t e__ = (call);                                                                   \
+        if (e__ != cudaSuccess)                                                                     \
+            return fdfd::set_err((c), FDFD_ECUDA,                                                   \
+                                 std::string(#call) + ": " + cudaGetErrorString(e__) + " (" +      \
+                                     __FILE__ + ":" + std::to_string(__LINE__) + ")");              \
+    } while (0)
+
+// coeffs.cpp ---------------------------------------------------------------------------------------
+struct CoefHost {
+    AxisOp a[3], b[3], mi[3], mo[3];  // first curl, second curl, in-average, out-average
+};
+// Build the coefficient set of the forward operator from the reference-level inputs.
+void build_coefs(const fdfd_desc &d, const std::vector<cplx> sdl_e[3], const std::vector<cplx> sdl_m[3],
+                 const cplx phase[3], CoefHost &out);
+// Coefficient set of the plain transpose A^T.
+void transpose_coefs(const CoefHost &in, CoefHost &out);
+AxisOp make_diff(bool isfwd, const std::vector<cplx> &dinv, bool isbloch, cplx ph);
+AxisOp make_mean(bool isfwd, const std::vector<cplx> *dl, const std::vector<cplx> *dlo_inv, bool isbloch,
+                 cplx ph, int N);
+AxisOp transpose_op(const AxisOp &t);
+
+// pattern.cpp --------------------------------------------------------------------------------------
+int export_pattern(Ctx *c, int64_t *colptr, int64_t *rowval, fdfd_c128 *nzval, int64_t *nnz_inout);
+
+// apply_naive.cu / apply_tiled.cu ------------------------------------------------------------------
+cudaError_t launch_apply_naive(const ApplyParams &p, cudaStream_t s);
+// returns cudaErrorNotSupported when the tiled kernel does not cover this configuration
+cudaError_t launch_apply_tiled(const ApplyParams &p, int kl_begin, int kl_end, cudaStream_t s, int *nlaunch);
+bool tiled_supported(const ApplyParams &p);
+// first-curl only: h = scale * q .* (C1 e + jm)   (h_from_e), naive kernel
+cudaError_t launch_curl1(const ApplyParams &p, const double2 *jm, double2 alpha, cudaStream_t s);
+// second-curl only: y = beta * C2 (q .* h) + gamma * je   (create_b), naive kernel
+cudaError_t launch_curl2(const ApplyParams &p, const double2 *je, double2 beta, double2 gamma, int has_h,
+                         cudaStream_t s);
+
+// krylov.cu ----------------------------------------------------------------------------------------
+int krylov_solve(Ctx *c, int method, const double2 *b, double2 *x, double rtol, int maxit, int check_every,
+                 bool fixed_iters, int *iters, double *relres, double *hist);
+
+// comm.cpp -----------------------------------------------------------------------------------------
+int comm_unique_id(char id[128], std::string &err);
+int comm_init(Ctx *c, const char id[128]);
+void comm_destroy(Ctx *c);
+// exchange the z-halo planes of a slab vector (AoS: one contiguous plane; SoA: 3 pieces)
+int halo_exchange(Ctx *c, const double2 *v, double2 *lo, double2 *hi, cudaStream_t s);
+int halo_exchange_ghosted(Ctx *c, double2 *arr, cudaStream_t s);
+int allreduce_sum(Ctx *c, double *dev, int count, cudaStream_t s);
+
+// api.cu -------------------------------------------------------------------------------------------
+int ensure_ready(Ctx *c);
+int apply_device(Ctx *c, const double2 *x, double2 *y, bool transpose);
+void fill_params(Ctx *c, ApplyParams &p, const double2 *x, double2 *y, bool transpose);
+
+}  // namespace fdfd
+
+struct fdfd_ctx : fdfd::Ctx {};

@@ -1,0 +1,227 @@
+// K2 - Krylov drivers on the device: BiCGSTAB (van der Vorst) and QMR for A x = b with the matrix-free
+// operator.  The reference stops at create_linsys -> (A, b) (src/model/model.jl:209-220) and leaves the
+// solve to the user (README.md:27-33); BASELINE.json's north_star defines this loop.
+//
+// All scalars (rho, alpha, omega, inner products) live in device memory; the vector kernels read them
+// and derive what they need, so an iteration is a pure stream of launches with no host round trip.
+// Inner products are reduced with warp shuffles -> one partial per block -> the last block (atomic
+// ticket) adds the partials in a fixed order, so results are deterministic for a given grid.  With
+// several z-slabs the local sums are combined by ncclAllReduce on the same stream.
+#include <cmath>
+#include <cstdio>
+
+#include "krylov_common.cuh"
+
+namespace fdfd {
+
+namespace {
+
+using namespace kry;
+
+// complex scalar slots
+
+// complex scalar slots (index into double2 array)
+enum { S_RHO0 = 0, S_RR0 = 1, S_RHO1 = 2, S_RR1 = 3, S_SIGMA = 4, S_TS = 5, S_TT = 6, S_ALPHA = 7, S_OMEGA = 8,
+       S_BNORM = 9, S_TMP0 = 10, S_TMP1 = 11, S_TMP2 = 12 };
+
+// r = b - r ; rhat = r ; p = r ;  RHO0 = RR0 = (r,r) ; BNORM = (b,b)
+__global__ void __launch_bounds__(RB) k_init(int64_t n, const double2 *__restrict__ b, double2 *__restrict__ r,
+                                             double2 *__restrict__ rhat, double2 *__restrict__ p, Red rd) {
+    double2 acc[2] = {c_zero(), c_zero()};
+    double2 accb[1] = {c_zero()};
+    GRID_STRIDE(i, n) {
+        const double2 bb = b[i];
+        const double2 rr = c_sub(bb, r[i]);
+        r[i] = rr;
+        rhat[i] = rr;
+        p[i] = rr;
+        dot_acc(acc[0], rr, rr);
+        dot_acc(accb[0], bb, bb);
+    }
+    acc[1] = acc[0];
+    reduce_publish<2>(acc, rd, S_RHO0);
+    reduce_publish<1>(accb, rd, S_BNORM);
+}
+
+// SIGMA = (rhat, v)
+__global__ void __launch_bounds__(RB) k_dot1(int64_t n, const double2 *__restrict__ a, const double2 *__restrict__ b,
+                                             Red rd, int slot) {
+    double2 acc[1] = {c_zero()};
+    GRID_STRIDE(i, n) dot_acc(acc[0], a[i], b[i]);
+    reduce_publish<1>(acc, rd, slot);
+}
+
+// alpha = rho/sigma ; s = r - alpha v
+__global__ void __launch_bounds__(RB) k_s(int64_t n, const double2 *__restrict__ r, const double2 *__restrict__ v,
+                                          double2 *__restrict__ s, Red rd, int rho_slot) {
+    const double2 alpha = c_div(rd.scal[rho_slot], rd.scal[S_SIGMA]);
+    GRID_STRIDE(i, n) s[i] = c_fms(alpha, v[i], r[i]);
+    if (blockIdx.x == 0 && threadIdx.x == 0) rd.scal[S_ALPHA] = alpha;
+}
+
+// TS = (t,s), TT = (t,t)
+__global__ void __launch_bounds__(RB) k_dot2(int64_t n, const double2 *__restrict__ t, const double2 *__restrict__ s,
+                                             Red rd) {
+    double2 acc[2] = {c_zero(), c_zero()};
+    GRID_STRIDE(i, n) {
+        const double2 tt = t[i];
+        dot_acc(acc[0], tt, s[i]);
+        dot_acc(acc[1], tt, tt);
+    }
+    reduce_publish<2>(acc, rd, S_TS);
+}
+
+// omega = TS/TT ; x += alpha p + omega s ; r = s - omega t ; RHO' = (rhat, r) ; RR' = (r,r)
+__global__ void __launch_bounds__(RB) k_xr(int64_t n, double2 *__restrict__ x, const double2 *__restrict__ p,
+                                           const double2 *__restrict__ s, const double2 *__restrict__ t,
+                                           const double2 *__restrict__ rhat, double2 *__restrict__ r, Red rd,
+                                           int rho_new_slot) {
+    const double2 alpha = rd.scal[S_ALPHA];
+    const double2 omega = c_div(rd.scal[S_TS], rd.scal[S_TT]);
+    double2 acc[2] = {c_zero(), c_zero()};
+    GRID_STRIDE(i, n) {
+        const double2 ss = s[i];
+        double2 xx = c_fma(alpha, p[i], x[i]);
+        xx = c_fma(omega, ss, xx);
+        x[i] = xx;
+        const double2 rr = c_fms(omega, t[i], ss);
+        r[i] = rr;
+        dot_acc(acc[0], rhat[i], rr);
+        dot_acc(acc[1], rr, rr);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) rd.scal[S_OMEGA] = omega;
+    reduce_publish<2>(acc, rd, rho_new_slot);
+}
+
+// beta = (rho'/rho)(alpha/omega) ; p = r + beta (p - omega v)
+__global__ void __launch_bounds__(RB) k_p(int64_t n, const double2 *__restrict__ r, const double2 *__restrict__ v,
+                                          double2 *__restrict__ p, Red rd, int rho_old_slot, int rho_new_slot) {
+    const double2 omega = rd.scal[S_OMEGA];
+    const double2 beta = c_mul(c_div(rd.scal[rho_new_slot], rd.scal[rho_old_slot]), c_div(rd.scal[S_ALPHA], omega));
+    GRID_STRIDE(i, n) {
+        const double2 q = c_fms(omega, v[i], p[i]);
+        p[i] = c_fma(beta, q, r[i]);
+    }
+}
+
+__global__ void k_store_hist(double *hist, int idx, const double2 *scal, int rr_slot) {
+    hist[idx] = sqrt(scal[rr_slot].x / scal[S_BNORM].x);
+}
+
+}  // namespace
+
+using kry::Red;
+using kry::RB;
+using kry::NSLOT;
+
+static int bicgstab(Ctx *c, const double2 *b, double2 *x, double rtol, int maxit, int check_every, bool fixed_iters,
+                    int *iters, double *relres, double *hist) {
+    int rc = ensure_ready(c);
+    if (rc != FDFD_OK) return rc;
+    if ((rc = kry::workspace(c, 6)) != FDFD_OK) return rc;
+    const int64_t n = c->nloc;
+    double2 *r = c->work, *rhat = r + n, *p = rhat + n, *v = p + n, *s = v + n, *t = s + n;
+    Red rd = kry::make_red(c);
+    double *sc = c->scal;
+    const int g = kry::grid_for(n);
+    cudaStream_t st = c->stream;
+    double *hist_dev = nullptr;
+    if (hist) FDFD_CUDA(c, cudaMalloc((void **)&hist_dev, sizeof(double) * (size_t)(maxit + 1)));
+    auto cleanup = [&]() { if (hist_dev) cudaFree(hist_dev); };
+#define KCHK(expr) do { int r__ = (expr); if (r__ != FDFD_OK) { cleanup(); return r__; } } while (0)
+#define LCHK() do { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) { cleanup(); return set_err(c, FDFD_ECUDA, cudaGetErrorString(e__)); } } while (0)
+
+    // r = b - A x0
+    KCHK(apply_device(c, x, r, false));
+    k_init<<<g, RB, 0, st>>>(n, b, r, rhat, p, rd);
+    LCHK();
+    c->launches += 1;
+    KCHK(allreduce_sum(c, sc + 2 * S_RHO0, 4, st));
+    KCHK(allreduce_sum(c, sc + 2 * S_BNORM, 2, st));
+    if (c->d.nranks > 1) {
+        // RHO0 and RR0 were reduced as one pair; nothing else to fix up
+    }
+    if (hist_dev) { k_store_hist<<<1, 1, 0, st>>>(hist_dev, 0, rd.scal, S_RR0); c->launches += 1; }
+
+    auto read_relres = [&](int rr_slot, double &out) -> int {
+        FDFD_CUDA(c, cudaMemcpyAsync(c->scal_host, sc, sizeof(double2) * NSLOT, cudaMemcpyDeviceToHost, st));
+        FDFD_CUDA(c, cudaStreamSynchronize(st));
+        const double rr = c->scal_host[2 * rr_slot], bn = c->scal_host[2 * S_BNORM];
+        out = bn > 0 ? std::sqrt(rr / bn) : std::sqrt(rr);
+        return FDFD_OK;
+    };
+
+    double rel = 1.0;
+    int it = 0;
+    bool converged = false;
+    if (!fixed_iters) {
+        KCHK(read_relres(S_RR0, rel));
+        if (c->scal_host[2 * S_BNORM] == 0.0) {
+            // b == 0: x = 0 is the solution (matches what a direct solve would return)
+            FDFD_CUDA(c, cudaMemsetAsync(x, 0, sizeof(double2) * (size_t)n, st));
+            FDFD_CUDA(c, cudaStreamSynchronize(st));
+            if (iters) *iters = 0;
+            if (relres) *relres = 0.0;
+            if (hist) hist[0] = 0.0;
+            cleanup();
+            return FDFD_OK;
+        }
+        converged = rel <= rtol;
+    }
+    while (!converged && it < maxit) {
+        const int par = it & 1;
+        const int rho_old = par ? S_RHO1 : S_RHO0, rho_new = par ? S_RHO0 : S_RHO1;
+        const int rr_new = rho_new + 1;
+        KCHK(apply_device(c, p, v, false));
+        k_dot1<<<g, RB, 0, st>>>(n, rhat, v, rd, S_SIGMA);
+        LCHK();
+        KCHK(allreduce_sum(c, sc + 2 * S_SIGMA, 2, st));
+        k_s<<<g, RB, 0, st>>>(n, r, v, s, rd, rho_old);
+        LCHK();
+        KCHK(apply_device(c, s, t, false));
+        k_dot2<<<g, RB, 0, st>>>(n, t, s, rd);
+        LCHK();
+        KCHK(allreduce_sum(c, sc + 2 * S_TS, 4, st));
+        k_xr<<<g, RB, 0, st>>>(n, x, p, s, t, rhat, r, rd, rho_new);
+        LCHK();
+        KCHK(allreduce_sum(c, sc + 2 * rho_new, 4, st));
+        k_p<<<g, RB, 0, st>>>(n, r, v, p, rd, rho_old, rho_new);
+        LCHK();
+        c->launches += 5;
+        ++it;
+        if (hist_dev) { k_store_hist<<<1, 1, 0, st>>>(hist_dev, it, rd.scal, rr_new); c->launches += 1; }
+        if (!fixed_iters && (it % check_every == 0 || it == maxit)) {
+            KCHK(read_relres(rr_new, rel));
+            if (!(rel == rel)) break;  // NaN: breakdown
+            converged = rel <= rtol;
+        }
+    }
+    if (fixed_iters) {
+        const int rr_last = (it & 1) ? S_RR1 : S_RR0;
+        KCHK(read_relres(rr_last, rel));
+    }
+    if (hist) {
+        FDFD_CUDA(c, cudaMemcpyAsync(hist, hist_dev, sizeof(double) * (size_t)(it + 1), cudaMemcpyDeviceToHost, st));
+        FDFD_CUDA(c, cudaStreamSynchronize(st));
+    }
+    cleanup();
+#undef KCHK
+#undef LCHK
+    if (iters) *iters = it;
+    if (relres) *relres = rel;
+    if (fixed_iters) return FDFD_OK;
+    if (!converged) return set_err(c, FDFD_ENOCONV, "BiCGSTAB: not converged within maxit");
+    return FDFD_OK;
+}
+
+int qmr(Ctx *c, const double2 *b, double2 *x, double rtol, int maxit, int check_every, bool fixed_iters, int *iters,
+        double *relres, double *hist);
+
+int krylov_solve(Ctx *c, int method, const double2 *b, double2 *x, double rtol, int maxit, int check_every,
+                 bool fixed_iters, int *iters, double *relres, double *hist) {
+    if (method == FDFD_BICGSTAB) return bicgstab(c, b, x, rtol, maxit, check_every, fixed_iters, iters, relres, hist);
+    if (method == FDFD_QMR) return qmr(c, b, x, rtol, maxit, check_every, fixed_iters, iters, relres, hist);
+    return set_err(c, FDFD_EINVAL, "unknown Krylov method");
+}
+
+}  // namespace fdfd

@@ -1,0 +1,244 @@
+"""GPU operator object: what `create_A` returns in the reference (src/model/model.jl:225-246) -
+something that supports `A * x`, `mul!(y, A, x)` and a solve - backed by libfdfd_b200.so."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+
+
+def _ptr(a):
+    """Raw address of a numpy array, a torch tensor, an int, or None."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return a
+    if hasattr(a, "data_ptr"):
+        return a.data_ptr()
+    return a.ctypes.data
+
+
+def _where(a):
+    return L.DEVICE if (hasattr(a, "is_cuda") and a.is_cuda) else L.HOST
+
+
+def _c128(z):
+    z = complex(z)
+    return L.c128(z.real, z.imag)
+
+
+class FdfdOperator:
+    """Matrix-free A = C2 q C1 - w^2 P on one z-slab of the grid.
+
+    Parameters mirror the quantities the reference passes to create_curl / create_paramop
+    (model.jl:152-155,171-172): stretched cell sizes, Bloch flags and phases, eps/mu arrays.
+    eps / mu are numpy arrays indexed [i,j,k,v,u] of THIS slab (shape (Nx,Ny,nzl,3,3))."""
+
+    def __init__(self, N, isbloch, sdl_e, sdl_m, omega, eps, mu=None, e_mikL=(1, 1, 1),
+                 boundft=("E", "E", "E"), ft="E", order_cmpfirst=True, device=-1, rank=0, nranks=1,
+                 weighted_out_avg=False, kernel=L.KERNEL_AUTO, eps_has_offdiag=None):
+        self._h = None
+        lib = L.lib()
+        d = L.Desc()
+        d.N[:] = [int(n) for n in N]
+        d.isbloch[:] = [1 if b else 0 for b in isbloch]
+        d.boundft_is_E[:] = [1 if str(b).upper().startswith("E") or b == 0 else 0 for b in boundft]
+        d.order_cmpfirst = 1 if order_cmpfirst else 0
+        d.field_type = L.FT_EE if (str(ft).upper().startswith("E") or ft == 0) else L.FT_HH
+        d.device, d.rank, d.nranks = int(device), int(rank), int(nranks)
+        d.weighted_out_avg = 1 if weighted_out_avg else 0
+        d.kernel = int(kernel)
+        h = C.c_void_p()
+        L.check(lib.fdfd_create(C.byref(h), C.byref(d)))
+        self._h = h
+        self.N = tuple(int(n) for n in N)
+        self.order_cmpfirst = bool(order_cmpfirst)
+        k0, k1 = C.c_int64(), C.c_int64()
+        L.check(lib.fdfd_slab_range(h, C.byref(k0), C.byref(k1)), h)
+        self.k0, self.k1 = k0.value, k1.value
+        self.nzl = self.k1 - self.k0
+        self.n = 3 * self.N[0] * self.N[1] * self.nzl          # local DOFs
+        self.shape = (self.n, self.n)
+        self.set_coeffs(sdl_e, sdl_m)
+        self.set_bloch(e_mikL)
+        self.set_omega(omega)
+        if eps is not None:
+            self.set_eps(eps, eps_has_offdiag)
+        self.set_mu(mu)
+
+    # -- lifetime ---------------------------------------------------------------------------
+    def close(self):
+        if self._h is not None:
+            L.lib().fdfd_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- inputs -----------------------------------------------------------------------------
+    def set_coeffs(self, sdl_e, sdl_m):
+        keep = [np.ascontiguousarray(a, dtype=np.complex128) for a in list(sdl_e) + list(sdl_m)]
+        for a, n in zip(keep, self.N * 2):
+            if a.shape != (n,):
+                raise ValueError("sdl arrays must have the global axis length")
+        pe = (C.c_void_p * 3)(*[a.ctypes.data for a in keep[:3]])
+        pm = (C.c_void_p * 3)(*[a.ctypes.data for a in keep[3:]])
+        L.check(L.lib().fdfd_set_coeffs(self._h, pe, pm), self._h)
+
+    def set_bloch(self, e_mikL):
+        ph = np.ascontiguousarray(e_mikL, dtype=np.complex128)
+        L.check(L.lib().fdfd_set_bloch(self._h, ph.ctypes.data), self._h)
+
+    def set_omega(self, omega):
+        self.omega = complex(omega)
+        L.check(L.lib().fdfd_set_omega(self._h, _c128(omega)), self._h)
+
+    @staticmethod
+    def _julia_layout(p):
+        """(Nx,Ny,nzl,3,3)-indexed numpy array -> memory of a Julia column-major array of that size."""
+        p = np.asarray(p, dtype=np.complex128)
+        return np.ascontiguousarray(p.transpose(4, 3, 2, 1, 0))
+
+    def set_eps(self, eps, has_offdiag=None):
+        eps = np.asarray(eps)
+        if eps.shape != (self.N[0], self.N[1], self.nzl, 3, 3):
+            raise ValueError(f"eps must have shape (Nx,Ny,nzl,3,3) = {(self.N[0], self.N[1], self.nzl, 3, 3)}")
+        buf = self._julia_layout(eps)
+        if has_offdiag is None:
+            has_offdiag = True  # the library scans and drops the flag if every off-diagonal entry is 0
+        L.check(L.lib().fdfd_set_eps(self._h, buf.ctypes.data, 1 if has_offdiag else 0), self._h)
+
+    def set_mu(self, mu):
+        if mu is None:
+            L.check(L.lib().fdfd_set_mu(self._h, None), self._h)
+            return
+        mu = np.asarray(mu)
+        if mu.shape != (self.N[0], self.N[1], self.nzl, 3, 3):
+            raise ValueError("mu must have shape (Nx,Ny,nzl,3,3)")
+        buf = self._julia_layout(mu)
+        L.check(L.lib().fdfd_set_mu(self._h, buf.ctypes.data), self._h)
+
+    def comm_init(self, unique_id: bytes):
+        L.check(L.lib().fdfd_comm_init(self._h, unique_id), self._h)
+
+    # -- operator ---------------------------------------------------------------------------
+    def _out_like(self, x):
+        if hasattr(x, "is_cuda"):
+            import torch
+            return torch.empty_like(x)
+        return np.empty(self.n, dtype=np.complex128)
+
+    def _chk_vec(self, x, name):
+        if hasattr(x, "is_cuda"):
+            import torch
+            if x.dtype != torch.complex128 or x.numel() != self.n or not x.is_contiguous():
+                raise ValueError(f"{name} must be a contiguous complex128 tensor of {self.n} elements")
+            if x.is_cuda:
+                torch.cuda.current_stream(x.device).synchronize()
+            return x
+        x = np.ascontiguousarray(x, dtype=np.complex128)
+        if x.shape != (self.n,):
+            raise ValueError(f"{name} must have {self.n} elements")
+        return x
+
+    def mul(self, y, x, transpose=False):
+        """mul!(y, A, x)"""
+        x = self._chk_vec(x, "x")
+        f = L.lib().fdfd_apply_transpose if transpose else L.lib().fdfd_apply
+        L.check(f(self._h, _ptr(x), _ptr(y), _where(x)), self._h)
+        return y
+
+    def __matmul__(self, x):
+        x = self._chk_vec(x, "x")
+        return self.mul(self._out_like(x), x)
+
+    __mul__ = __matmul__
+
+    def rmatvec_T(self, x):
+        x = self._chk_vec(x, "x")
+        return self.mul(self._out_like(x), x, transpose=True)
+
+    def solve(self, b, x0=None, method="bicgstab", rtol=1e-8, maxit=10000, check_every=10, history=False):
+        """x = A \\ b by BiCGSTAB or QMR.  Returns (x, info)."""
+        b = self._chk_vec(b, "b")
+        if x0 is None:
+            if hasattr(b, "is_cuda"):
+                import torch
+                x = torch.zeros_like(b)
+            else:
+                x = np.zeros(self.n, dtype=np.complex128)
+        else:
+            x = self._chk_vec(x0, "x0")
+            x = x.clone() if hasattr(x, "clone") else x.copy()
+        m = L.BICGSTAB if str(method).lower().startswith("bi") else L.QMR
+        iters, relres = C.c_int(), C.c_double()
+        hist = np.full(maxit + 1, np.nan) if history else None
+        code = L.lib().fdfd_solve(self._h, m, _ptr(b), _ptr(x), _where(b), float(rtol), int(maxit),
+                                  int(check_every), C.byref(iters), C.byref(relres),
+                                  hist.ctypes.data if history else None)
+        L.check(code, self._h, ok=(L.OK, L.ENOCONV))
+        info = {"iters": iters.value, "relres": relres.value, "converged": code == L.OK}
+        if history:
+            info["history"] = hist[: iters.value + 1]
+        return x, info
+
+    def export_pattern(self, values=True):
+        """(colptr, rowval, nzval) of the assembled A as Julia stores it (1-based Int64)."""
+        nnz = C.c_int64(0)
+        L.check(L.lib().fdfd_export_pattern(self._h, None, None, None, C.byref(nnz)), self._h)
+        colptr = np.empty(self.n + 1, dtype=np.int64)
+        rowval = np.empty(nnz.value, dtype=np.int64)
+        nzval = np.empty(nnz.value, dtype=np.complex128) if values else None
+        L.check(L.lib().fdfd_export_pattern(self._h, colptr.ctypes.data, rowval.ctypes.data,
+                                            nzval.ctypes.data if values else None, C.byref(nnz)), self._h)
+        return colptr, rowval, nzval
+
+    def h_from_e(self, e, jm=None):
+        e = self._chk_vec(e, "e")
+        if jm is not None:
+            jm = self._chk_vec(jm, "jm")
+        h = self._out_like(e)
+        L.check(L.lib().fdfd_h_from_e(self._h, _ptr(e), _ptr(jm), _ptr(h), _where(e)), self._h)
+        return h
+
+    def create_b(self, je, jm=None):
+        je = self._chk_vec(je, "je")
+        if jm is not None:
+            jm = self._chk_vec(jm, "jm")
+        b = self._out_like(je)
+        L.check(L.lib().fdfd_create_b(self._h, _ptr(je), _ptr(jm), _ptr(b), _where(je)), self._h)
+        return b
+
+    # -- measurement ------------------------------------------------------------------------
+    def bench_apply(self, x_dev, y_dev, warmup=3, iters=10, flush_l2=False):
+        tot, mn = C.c_double(), C.c_double()
+        L.check(L.lib().fdfd_bench_apply(self._h, _ptr(x_dev), _ptr(y_dev), warmup, iters, 1 if flush_l2 else 0,
+                                         C.byref(tot), C.byref(mn)), self._h)
+        return tot.value, mn.value
+
+    def bench_solve(self, b_dev, x_dev, method="bicgstab", warmup=2, iters=20):
+        m = L.BICGSTAB if str(method).lower().startswith("bi") else L.QMR
+        tot = C.c_double()
+        L.check(L.lib().fdfd_bench_solve(self._h, m, _ptr(b_dev), _ptr(x_dev), warmup, iters, C.byref(tot)), self._h)
+        return tot.value
+
+    @property
+    def launch_count(self):
+        return int(L.lib().fdfd_launch_count(self._h))
+
+
+def comm_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    L.check(L.lib().fdfd_comm_unique_id(buf))
+    return buf.raw
+
+
+def partition(Nz, nranks, rank):
+    k0, k1 = C.c_int64(), C.c_int64()
+    code = L.lib().fdfd_partition(int(Nz), int(nranks), int(rank), C.byref(k0), C.byref(k1))
+    if code != L.OK:
+        raise ValueError("bad partition arguments")
+    return k0.value, k1.value

@@ -1,0 +1,74 @@
+"""Seeded synthetic problems shared by the CPU and GPU tests (oracle side + product-side inputs)."""
+import itertools
+
+import numpy as np
+
+from oracle.grid import Grid, EE, HH, create_stretched_dls, create_e_mikL
+from oracle import operators as op
+from oracle.matfree import MatFreeOperator
+
+SEED = 20261017
+
+
+def crandn(rng, *shape):
+    return rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
+
+
+def rel(a, b):
+    return float(np.linalg.norm(np.asarray(a) - np.asarray(b)) / max(np.linalg.norm(b), 1e-300))
+
+
+class Problem:
+    """One operator instance: inputs in the form the C ABI takes + oracle builders."""
+
+    def __init__(self, N, isbloch=(True, True, True), boundft=(EE, EE, EE), full_eps=False, with_mu=False,
+                 ft=EE, omega=1.1 - 0.05j, npml=1, uniform=False, seed=SEED, cmpfirst=True, weighted_out=False,
+                 kb_scale=1.0):
+        rng = np.random.default_rng(seed)
+        self.N = tuple(int(n) for n in N)
+        self.isbloch = tuple(bool(b) for b in isbloch)
+        self.boundft = tuple(boundft)
+        self.ft, self.omega, self.cmpfirst, self.weighted_out = ft, omega, cmpfirst, weighted_out
+        if uniform:
+            lprim = tuple(np.arange(n + 1, dtype=float) for n in self.N)
+        else:
+            lprim = tuple(np.concatenate(([0.0], np.cumsum(0.5 + rng.random(n)))) for n in self.N)
+        self.grid = Grid(lprim, self.isbloch)
+        Npml = (tuple(min(npml, n // 2) for n in self.N),) * 2
+        self.sdl_e, self.sdl_m, self.sei, self.smi = create_stretched_dls(0.9 + 0.1j, self.grid, Npml, self.boundft)
+        kb = np.where(self.isbloch, kb_scale * rng.random(3), 0.0)
+        self.ph = create_e_mikL(kb, self.grid)
+        self.eps = np.zeros(self.N + (3, 3), complex)
+        self.mu = np.zeros(self.N + (3, 3), complex)
+        for v in range(3):
+            self.eps[..., v, v] = 2 + 0.3 * crandn(rng, *self.N)
+            self.mu[..., v, v] = (1.5 + 0.2 * crandn(rng, *self.N)) if with_mu else 1.0
+        if full_eps:
+            for v, u in itertools.permutations(range(3), 2):
+                self.eps[..., v, u] = 0.3 * crandn(rng, *self.N)
+        self.with_mu, self.full_eps = with_mu, full_eps
+        self.n = 3 * int(np.prod(self.N))
+        self.rng = rng
+
+    # ---- oracle ---------------------------------------------------------------------------
+    def oracle_csc(self):
+        Ce, Cm = op.create_curls(self.sei, self.smi, self.boundft, self.isbloch, self.ph, self.cmpfirst)
+        Pe, Pm = op.create_paramops(self.eps, self.mu, self.sdl_e, self.sdl_m, self.sei, self.smi, self.boundft,
+                                    self.isbloch, self.ph, self.cmpfirst, self.weighted_out)
+        return op.create_A(self.ft, self.omega, Pe, Pm, Ce, Cm), (Pe, Pm, Ce, Cm)
+
+    def oracle_matfree(self):
+        return MatFreeOperator(self.ft, self.omega, self.eps, self.mu if self.with_mu else None, self.sdl_e,
+                               self.sdl_m, self.boundft, self.isbloch, self.ph, self.cmpfirst, self.weighted_out)
+
+    def random_x(self, seed=1):
+        return crandn(np.random.default_rng(SEED + seed), self.n)
+
+    # ---- product --------------------------------------------------------------------------
+    def operator(self, **kw):
+        import maxwellfdm_jl_b200 as fb
+        return fb.FdfdOperator(self.N, self.isbloch, self.sdl_e, self.sdl_m, self.omega, self.eps,
+                               self.mu if self.with_mu else None, self.ph,
+                               boundft=["E" if b == EE else "H" for b in self.boundft],
+                               ft="E" if self.ft == EE else "H", order_cmpfirst=self.cmpfirst,
+                               weighted_out_avg=self.weighted_out, **kw)

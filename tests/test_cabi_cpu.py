@@ -1,0 +1,134 @@
+"""CPU-side checks of the C-ABI library (no compute calls): it loads, exports every symbol the header
+declares, refuses to run without a GPU, and its host-only debug export reproduces the oracle's sparse
+index pattern BIT-EXACTLY (reference-defined integer work) and its values to 1e-13."""
+import ctypes as C
+import itertools
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle.grid import EE, HH
+from problems import Problem, rel
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _lib():
+    import maxwellfdm_jl_b200 as fb
+    return fb._lib
+
+
+def test_library_exports_every_declared_symbol():
+    L = _lib()
+    hdr = open(os.path.join(ROOT, "include", "fdfd_b200.h")).read()
+    declared = set(re.findall(r"\b(fdfd_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 25
+    lib = L.lib()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/fdfd_b200.h but not exported"
+    assert declared == set(L.SYMBOLS), declared ^ set(L.SYMBOLS)
+    assert b"sm_100a" in lib.fdfd_version()
+
+
+def test_partition_rule():
+    import maxwellfdm_jl_b200 as fb
+    for Nz, P in [(1, 1), (7, 3), (768, 8), (512, 8), (5, 5), (200, 7)]:
+        edges = [fb.partition(Nz, P, r) for r in range(P)]
+        assert edges[0][0] == 0 and edges[-1][1] == Nz
+        for a, b in zip(edges[:-1], edges[1:]):
+            assert a[1] == b[0]
+        sizes = [b - a for a, b in edges]
+        assert min(sizes) >= 1 and max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        fb.partition(3, 4, 0)
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    L = _lib()
+    p = Problem((3, 3, 3))
+    with pytest.raises(L.FdfdError) as ei:
+        p.operator()
+    assert ei.value.code == L.ECUDA and "no CPU fallback" in str(ei.value)
+    # a host-only handle exports patterns but refuses every compute call
+    A = p.operator(device=-2)
+    with pytest.raises(L.FdfdError) as ei:
+        A @ p.random_x()
+    assert ei.value.code == L.ESTATE
+    with pytest.raises(L.FdfdError):
+        A.solve(p.random_x())
+
+
+def _check_export(p):
+    A, _ = p.oracle_csc()
+    cp_ref, rv_ref = A.julia_pattern()
+    op_ = p.operator(device=-2)
+    cp, rv, nz = op_.export_pattern()
+    assert cp.dtype == np.int64 and rv.dtype == np.int64
+    assert np.array_equal(cp, cp_ref), "colptr differs"
+    assert np.array_equal(rv, rv_ref), "rowval differs"
+    scale = np.abs(A.nzval).max()
+    assert np.abs(nz - A.nzval).max() <= 1e-13 * scale
+    op_.close()
+
+
+SIZES = [(1, 1, 1), (2, 1, 3), (3, 2, 1), (5, 3, 2), (3, 5, 8)]
+
+
+@pytest.mark.parametrize("N", SIZES)
+@pytest.mark.parametrize("isbloch", list(itertools.product([True, False], repeat=3)))
+def test_export_pattern_default_boundft(N, isbloch):
+    for full_eps, with_mu in ((False, False), (True, True)):
+        _check_export(Problem(N, isbloch, full_eps=full_eps, with_mu=with_mu))
+
+
+@pytest.mark.parametrize("boundft", list(itertools.product([EE, HH], repeat=3)))
+def test_export_pattern_all_boundft(boundft):
+    for isbloch in ((True, False, True), (False, True, False)):
+        for full_eps in (False, True):
+            _check_export(Problem((4, 3, 5), isbloch, boundft, full_eps=full_eps, with_mu=True))
+
+
+def test_export_pattern_variants():
+    # w == 0: structural pattern with explicit zeros kept (model.jl:237 skips the subtraction)
+    for isbloch in ((True,) * 3, (False,) * 3):
+        p = Problem((4, 5, 3), isbloch, omega=0.0, uniform=True, npml=0)
+        A, _ = p.oracle_csc()
+        cp, rv, nz = p.operator(device=-2).export_pattern()
+        assert np.array_equal(cp, A.julia_pattern()[0]) and np.array_equal(rv, A.julia_pattern()[1])
+        assert np.all(np.diff(cp) == 13)
+        if not any(isbloch):
+            assert (nz == 0).any()
+    # component-major DOF order, weighted output average, HH formulation
+    _check_export(Problem((4, 3, 5), (True, False, True), full_eps=True, with_mu=True, cmpfirst=False))
+    _check_export(Problem((4, 3, 5), (False, True, True), full_eps=True, weighted_out=True))
+    _check_export(Problem((4, 3, 5), (True, False, True), with_mu=True, ft=HH))
+    _check_export(Problem((4, 3, 5), (True, True, False), (HH, EE, HH), with_mu=True, ft=HH, cmpfirst=False))
+    # exact zeros are dropped when w != 0 (symmetry boundaries on a uniform grid)
+    p = Problem((5, 6, 7), (False,) * 3, uniform=True, npml=0, omega=1.0)
+    A, _ = p.oracle_csc()
+    cp, rv, nz = p.operator(device=-2).export_pattern()
+    assert np.array_equal(rv, A.julia_pattern()[1]) and np.all(nz != 0) and (np.diff(cp) < 13).any()
+
+
+def test_export_capacity_and_errors():
+    L = _lib()
+    p = Problem((3, 3, 3))
+    A = p.operator(device=-2)
+    nnz = C.c_int64(5)
+    cp = np.zeros(A.n + 1, np.int64)
+    rv = np.zeros(5, np.int64)
+    code = L.lib().fdfd_export_pattern(A._h, cp.ctypes.data, rv.ctypes.data, None, C.byref(nnz))
+    assert code == L.EINVAL and nnz.value == 13 * A.n
+    d = L.Desc()
+    d.N[:] = [3, 3, 0]
+    h = C.c_void_p()
+    assert L.lib().fdfd_create(C.byref(h), C.byref(d)) == L.EINVAL
+    with pytest.raises(L.FdfdError):       # mu with off-diagonal entries (reference model.jl:236)
+        mu = p.mu.copy()
+        mu[..., 0, 1] = 0.1
+        A.set_mu(mu)

@@ -1,0 +1,303 @@
+"""GPU parity tests proper (run with -m gpu on the B200 box): the CUDA path, called through the C ABI,
+against the CPU oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): A*x within 1e-12 relative of the oracle's CSC product;
+index pattern bit-exact; converged fields within 1e-8 relative.
+"""
+import itertools
+import os
+
+import numpy as np
+import pytest
+
+from oracle.grid import EE, HH
+from oracle import operators as op
+from problems import Problem, rel, crandn, SEED
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12
+
+
+def _fb():
+    import maxwellfdm_jl_b200 as fb
+    return fb
+
+
+def _torch():
+    import torch
+    return torch
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu():
+    torch = _torch()
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    torch.cuda.set_device(0)
+
+
+def _apply_dev(A, x, transpose=False):
+    torch = _torch()
+    xd = torch.from_numpy(np.ascontiguousarray(x)).cuda()
+    yd = torch.empty_like(xd)
+    A.mul(yd, xd, transpose=transpose)
+    return yd.cpu().numpy()
+
+
+KERNELS = {"naive": 1, "tiled": 2}
+
+SMALL = [(1, 1, 1), (2, 1, 3), (3, 2, 1), (5, 3, 2), (3, 5, 8), (31, 15, 4), (33, 17, 9), (70, 45, 6)]
+
+
+@pytest.mark.parametrize("kernel", ["tiled", "naive"])
+@pytest.mark.parametrize("N", SMALL)
+def test_apply_all_boundary_conditions(kernel, N):
+    """every Bloch/symmetry combination, diagonal and full eps, with and without mu, odd shapes that are
+    not multiples of the tile, N_w = 1..3 edge cases (SURVEY §8c parity procedure (ii))."""
+    for isbloch in itertools.product([True, False], repeat=3):
+        for full_eps, with_mu in ((False, False), (True, False), (True, True)):
+            p = Problem(N, isbloch, full_eps=full_eps, with_mu=with_mu)
+            A_ref, _ = p.oracle_csc()
+            A = p.operator(device=0, kernel=KERNELS[kernel])
+            x = p.random_x()
+            err = rel(_apply_dev(A, x), A_ref.matvec(x))
+            A.close()
+            assert err < TOL, (kernel, N, isbloch, full_eps, with_mu, err)
+
+
+@pytest.mark.parametrize("boundft", list(itertools.product([EE, HH], repeat=3)))
+def test_apply_all_boundft(boundft):
+    """all 2^3 boundft choices (general kernel; the tiled kernel covers the default all-EE arrangement)."""
+    for isbloch in ((True, False, True), (False, True, False)):
+        for ft in (EE, HH):
+            p = Problem((9, 6, 7), isbloch, boundft, full_eps=(ft == EE), with_mu=True, ft=ft)
+            A_ref, _ = p.oracle_csc()
+            A = p.operator(device=0)
+            x = p.random_x()
+            err = rel(_apply_dev(A, x), A_ref.matvec(x))
+            A.close()
+            assert err < TOL, (boundft, isbloch, ft, err)
+
+
+@pytest.mark.parametrize("kernel", ["tiled", "naive"])
+def test_component_major_layout_and_weighted_out(kernel):
+    for cmpfirst, wo in ((False, False), (True, True), (False, True)):
+        p = Problem((37, 20, 11), (True, False, True), full_eps=True, with_mu=True, cmpfirst=cmpfirst, weighted_out=wo)
+        A_ref, _ = p.oracle_csc()
+        A = p.operator(device=0, kernel=KERNELS[kernel])
+        x = p.random_x()
+        err = rel(_apply_dev(A, x), A_ref.matvec(x))
+        A.close()
+        assert err < TOL, (cmpfirst, wo, err)
+
+
+@pytest.mark.parametrize("kernel", ["tiled", "naive"])
+def test_transpose_apply(kernel):
+    for isbloch, full_eps, with_mu in (((True, True, True), True, True), ((False, True, False), True, False),
+                                       ((False, False, False), False, True)):
+        p = Problem((12, 35, 9), isbloch, full_eps=full_eps, with_mu=with_mu)
+        A_ref, _ = p.oracle_csc()
+        At = A_ref.to_scipy().T.tocsc()
+        A = p.operator(device=0, kernel=KERNELS[kernel])
+        x = p.random_x()
+        err = rel(_apply_dev(A, x, transpose=True), At @ x)
+        A.close()
+        assert err < TOL, (isbloch, full_eps, err)
+
+
+def test_omega_zero_skips_mass_term():
+    p = Problem((10, 9, 8), (True, False, True), omega=0.0)
+    A_ref, _ = p.oracle_csc()
+    for k in (1, 2):
+        A = p.operator(device=0, kernel=k)
+        x = p.random_x()
+        assert rel(_apply_dev(A, x), A_ref.matvec(x)) < TOL
+        A.close()
+
+
+def test_host_and_device_paths_agree_and_errors():
+    fb = _fb()
+    p = Problem((20, 18, 10), (False, True, False), full_eps=True)
+    A = p.operator(device=0)
+    x = p.random_x()
+    yh = A @ x                       # FDFD_HOST
+    yd = _apply_dev(A, x)            # FDFD_DEVICE
+    assert np.array_equal(yh, yd)
+    with pytest.raises(ValueError):
+        A @ x[:-1]
+    torch = _torch()
+    xd = torch.from_numpy(x).cuda()
+    with pytest.raises(fb._lib.FdfdError):      # aliasing is rejected
+        A.mul(xd, xd)
+    # changing omega re-scales the mass term
+    A.set_omega(0.7)
+    p2 = Problem((20, 18, 10), (False, True, False), full_eps=True, omega=0.7)
+    assert rel(A @ x, p2.oracle_csc()[0].matvec(x)) < TOL
+    A.close()
+
+
+def test_export_pattern_on_gpu_handle_is_bit_exact():
+    p = Problem((7, 6, 5), (False, True, False), full_eps=True, with_mu=True)
+    A_ref, _ = p.oracle_csc()
+    A = p.operator(device=0)
+    cp, rv, nz = A.export_pattern()
+    assert np.array_equal(cp, A_ref.julia_pattern()[0]) and np.array_equal(rv, A_ref.julia_pattern()[1])
+    # the exported matrix and the matrix-free kernel are the same operator
+    import scipy.sparse as sp
+    S = sp.csc_matrix((nz, rv - 1, cp - 1), shape=A_ref.shape)
+    x = p.random_x()
+    assert rel(_apply_dev(A, x), S @ x) < TOL
+    A.close()
+
+
+def test_config_shapes_against_oracle():
+    """BASELINE configs: C1 (40^3, CSC oracle) and reduced C2 / C3 (matrix-free oracle), real inputs."""
+    import workloads
+    from oracle.matfree import MatFreeOperator
+    rng = np.random.default_rng(SEED)
+    for w in (workloads.c1_vacuum_box(), workloads.c2_waveguide((72, 60, 40)), workloads.c3_phc_slab((64, 64, 40))):
+        A = workloads.make_operator(w, device=0)
+        mf = MatFreeOperator(EE, w["omega"], w["eps"], None, w["sdl_e"], w["sdl_m"], (EE,) * 3, w["isbloch"], w["e_mikL"])
+        x = crandn(rng, A.n)
+        err = rel(_apply_dev(A, x), mf(x))
+        A.close()
+        assert err < TOL, (w["name"], err)
+
+
+def test_golden_fixture():
+    """committed oracle output (tests/golden/make_golden.py) - guards against oracle AND kernel drift."""
+    path = os.path.join(os.path.dirname(__file__), "golden", "apply_golden.npz")
+    g = np.load(path)
+    for tag in ("bloch_full", "sym_diag"):
+        kw = dict(N=tuple(g[f"{tag}_N"]), isbloch=tuple(bool(b) for b in g[f"{tag}_isbloch"]),
+                  full_eps=bool(g[f"{tag}_full"]), with_mu=bool(g[f"{tag}_mu"]))
+        p = Problem(**kw)
+        x = p.random_x()
+        assert np.array_equal(x, g[f"{tag}_x"])
+        for k in (1, 2):
+            A = p.operator(device=0, kernel=k)
+            assert rel(_apply_dev(A, x), g[f"{tag}_y"]) < TOL
+            cp, rv, _ = A.export_pattern(values=False)
+            assert np.array_equal(cp, g[f"{tag}_colptr"]) and np.array_equal(rv, g[f"{tag}_rowval"])
+            A.close()
+
+
+def test_large_grid_properties():
+    """full-size-style properties where the CSC oracle does not fit: tiled == general kernel, linearity,
+    and agreement with the matrix-free oracle on a z-sub-slab."""
+    import workloads
+    from oracle.matfree import MatFreeOperator
+    torch = _torch()
+    w = workloads.c2_waveguide((200, 200, 48))
+    At = workloads.make_operator(w, device=0, kernel=2)
+    An = workloads.make_operator(w, device=0, kernel=1)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x1 = torch.randn(At.n, 2, device="cuda", dtype=torch.float64, generator=g).view(torch.complex128).reshape(-1)
+    x2 = torch.randn(At.n, 2, device="cuda", dtype=torch.float64, generator=g).view(torch.complex128).reshape(-1)
+    y1, y2 = At @ x1, At @ x2
+    yn = An @ x1
+    assert float((y1 - yn).norm() / yn.norm()) < 1e-13
+    a = 0.3 - 1.7j
+    y12 = At @ (x1 + a * x2)
+    assert float((y12 - (y1 + a * y2)).norm() / y12.norm()) < 1e-13
+    mf = MatFreeOperator(EE, w["omega"], w["eps"], None, w["sdl_e"], w["sdl_m"], (EE,) * 3, w["isbloch"], w["e_mikL"])
+    assert rel(y1.cpu().numpy(), mf(x1.cpu().numpy())) < TOL
+    At.close()
+    An.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# solve / RHS / post-processing
+# ---------------------------------------------------------------------------------------------------
+def _pml_box(n=20, npml=5):
+    from oracle.grid import Grid, create_stretched_dls
+    d, lam = 1.0, 10.0
+    omega = 2 * np.pi / lam
+    lp = (np.arange(n + 1) - n / 2) * d
+    grid = Grid((lp, lp, lp), (False, False, False))
+    sdl = create_stretched_dls(omega, grid, ((npml,) * 3, (npml,) * 3))
+    N = grid.N
+    eps = np.zeros(N + (3, 3), complex)
+    mu = np.zeros(N + (3, 3), complex)
+    for v in range(3):
+        eps[..., v, v] = 1 + 0.5 * (np.abs(np.arange(n) - n / 2)[:, None, None] < 3)
+        mu[..., v, v] = 1
+    return grid, sdl, omega, eps, mu
+
+
+@pytest.mark.parametrize("method", ["bicgstab", "qmr"])
+def test_solve_matches_direct_solve(method):
+    import scipy.sparse.linalg as spla
+    from oracle.source import PointSrc, add_src, create_field_array
+    fb = _fb()
+    grid, (sdl_e, sdl_m, sei, smi), omega, eps, mu = _pml_box()
+    ph = np.ones(3, complex)
+    Ce, Cm = op.create_curls(sei, smi, (EE,) * 3, grid.isbloch, ph)
+    Pe, Pm = op.create_paramops(eps, mu, sdl_e, sdl_m, sei, smi, (EE,) * 3, grid.isbloch, ph)
+    A_ref = op.create_A(EE, omega, Pe, Pm, Ce, Cm)
+    je = create_field_array(grid.N)
+    add_src(je, EE, (EE,) * 3, grid, PointSrc([0.3, 0.2, 0.1], [0, 0, 1]))
+    b = op.create_b(EE, omega, Pe, Pm, Ce, Cm, op.field_arr2vec(je), np.zeros(A_ref.shape[0]))
+    e_ref = spla.splu(A_ref.to_scipy().tocsc()).solve(b)
+    A = fb.FdfdOperator(grid.N, grid.isbloch, sdl_e, sdl_m, omega, eps, None, ph, device=0)
+    # RHS through the GPU create_b equals the oracle's
+    assert rel(A.create_b(op.field_arr2vec(je)), b) < TOL
+    torch = _torch()
+    x, info = A.solve(torch.from_numpy(b).cuda(), method=method, rtol=1e-10, maxit=20000, check_every=25, history=True)
+    assert info["converged"], info
+    e = x.cpu().numpy()
+    assert rel(A_ref.matvec(e), b) < 1e-8                       # true residual
+    assert rel(e, e_ref) < 1e-8 * 50                            # field vs direct solve (cond. number slack)
+    h = info["history"]
+    assert h[0] == pytest.approx(1.0) and np.isfinite(h).all() and h[-1] <= 1e-10
+    # post-processing: h_from_e
+    h_ref = op.h_from_e(e_ref, omega, Pm, Ce, np.zeros_like(e_ref))
+    assert rel(A.h_from_e(e_ref), h_ref) < TOL
+    # host-buffer solve gives the same answer
+    xh, info_h = A.solve(b, method=method, rtol=1e-10, maxit=20000, check_every=25)
+    assert info_h["converged"] and rel(xh, e) < 1e-6
+    A.close()
+
+
+def test_solve_edge_cases():
+    fb = _fb()
+    p = Problem((8, 7, 6), (True, True, True))
+    A = p.operator(device=0)
+    x, info = A.solve(np.zeros(A.n, complex))                    # b == 0
+    assert info["converged"] and info["iters"] == 0 and not x.any()
+    b = p.oracle_csc()[0].matvec(p.random_x(5))
+    x, info = A.solve(b, maxit=3, rtol=1e-14)                    # maxit hit: ENOCONV, x still valid
+    assert not info["converged"] and info["iters"] == 3 and np.isfinite(x).all()
+    A.close()
+
+
+def test_create_b_with_magnetic_current_and_h_from_e_with_mu():
+    p = Problem((9, 8, 7), (True, False, True), with_mu=True)
+    A_ref, (Pe, Pm, Ce, Cm) = p.oracle_csc()
+    A = p.operator(device=0)
+    je, jm, e = p.random_x(11), p.random_x(12), p.random_x(13)
+    assert rel(A.create_b(je, jm), op.create_b(EE, p.omega, Pe, Pm, Ce, Cm, je, jm)) < TOL
+    assert rel(A.h_from_e(e, jm), op.h_from_e(e, p.omega, Pm, Ce, jm)) < TOL
+    A.close()
+
+
+def test_model_api_end_to_end():
+    """reference-shaped host API: ModelFull -> add_srce -> create_linsys -> solve -> h_from_e."""
+    fb = _fb()
+    n = 16
+    lp = (np.arange(n + 1) - n / 2) * 1.0
+    mdl = fb.ModelFull(fb.Grid((lp, lp, lp), (False, False, False)))
+    w = 2 * np.pi / 8.0
+    fb.set_wpml(mdl, w)
+    fb.set_Npml(mdl, ((4,) * 3, (4,) * 3))
+    for v in range(3):
+        mdl.eps_arr[..., v, v] = 1.0
+    fb.add_srce(mdl, fb.PointSrc([0.0, 0.0, 0.0], [0, 0, 1]))
+    A, b = fb.create_linsys(fb.EE, w, mdl)
+    e, info = fb.solve(A, b, rtol=1e-9, maxit=5000)
+    assert info["converged"]
+    assert rel(A @ e, b) < 1e-8
+    h = fb.h_from_e(e, w, A)
+    assert np.isfinite(h).all() and np.abs(h).max() > 0
+    A.close()

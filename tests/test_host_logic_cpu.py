@@ -1,0 +1,110 @@
+"""Host-side logic of the product (grid geometry, PML stretch, sources, DOF ordering, model API plumbing)
+against the oracle and the reference's own source fixtures (test/source.jl) - no GPU needed."""
+import numpy as np
+import pytest
+
+import maxwellfdm_jl_b200 as fb
+from oracle import grid as og, source as osrc, operators as oop
+
+
+def _rand_grid(rng, N, isbloch):
+    lprim = tuple(np.concatenate(([0.0], np.cumsum(0.5 + rng.random(n)))) - 3.0 for n in N)
+    return fb.Grid(lprim, isbloch), og.Grid(lprim, isbloch)
+
+
+def test_grid_and_pml_match_oracle():
+    rng = np.random.default_rng(5)
+    for isbloch in ((True, False, True), (False, True, False)):
+        g, o = _rand_grid(rng, (9, 7, 8), isbloch)
+        assert g.N == o.N and np.allclose(g.L, o.L) and g.bounds == o.bounds
+        for t in (0, 1):
+            for w in range(3):
+                assert np.array_equal(g.l[t][w], o.l[t][w]) and np.array_equal(g.dl[t][w], o.dl[t][w])
+        for boundft in ((fb.EE,) * 3, (fb.HH, fb.EE, fb.HH)):
+            mdl = fb.ModelFull(g)
+            fb.set_wpml(mdl, 0.8 - 0.1j)
+            fb.set_Npml(mdl, ((2, 0, 3), (1, 2, 0)))
+            fb.set_boundft(mdl, boundft)
+            fb.set_kbloch(mdl, (0.1, 0.0, -0.2))
+            mine = fb.create_stretched_dls(mdl)
+            ref = og.create_stretched_dls(0.8 - 0.1j, o, ((2, 0, 3), (1, 2, 0)), boundft)
+            for a, b in zip(mine, ref):
+                for w in range(3):
+                    assert np.allclose(a[w], b[w], rtol=1e-15, atol=0)
+            assert np.allclose(fb.create_e_mikL(mdl), og.create_e_mikL((0.1, 0.0, -0.2), o), rtol=1e-15)
+
+
+def test_distweights_reference_table():
+    """reference test/source.jl:17-60,64-104 (spot rows; the full table is in test_oracle_source.py)."""
+    lp = np.cumsum(np.concatenate(([-1], np.arange(2, 23, 2))))
+    lprim_g, ldual_g = 0.5 * (lp[:-1] + lp[1:]), lp[:-1]
+    dom = (lprim_g[0], lprim_g[-1])
+    lprim, dlprim, ldual, dldual = lprim_g[:-1], np.diff(ldual_g), ldual_g[1:], np.diff(lprim_g)
+    r = (105 - 99) / (120 - 99)
+    ind, wt = fb.distweights(105, fb.PRIM, dom, lprim, dlprim, True)
+    assert ind == (9, 0) and np.allclose(wt, [1 / dlprim[9] * (1 - r), 1 / dlprim[0] * r])
+    ind, wt = fb.distweights(0, fb.PRIM, dom, lprim, dlprim, False)
+    assert ind == (1, 1) and wt == (0.0, 0.0)
+    r = (1 - 0.5) / ((1 - 0) + (120 - 109))
+    ind, wt = fb.distweights(0.5, fb.DUAL, dom, ldual, dldual, True)
+    assert ind == (0, 9) and np.allclose(wt, [1 / dldual[0] * (1 - r), 1 / dldual[9] * r])
+    with pytest.raises(ValueError):
+        fb.distweights(-0.5, fb.DUAL, dom, ldual, dldual, False)
+    with pytest.raises(ValueError):
+        fb.distweights(1.0, fb.PRIM, (0, 2), [0], [9], False)
+
+
+def test_distweights_and_sources_match_oracle_randomised():
+    rng = np.random.default_rng(11)
+    for isbloch in ((True, True, True), (False, False, False), (True, False, True)):
+        g, o = _rand_grid(rng, (7, 6, 8), isbloch)
+        for gt in (fb.PRIM, fb.DUAL):
+            for w in range(3):
+                for c in np.concatenate((rng.uniform(g.bounds[0][w], g.bounds[1][w], 20), g.l[gt][w][:3],
+                                         [g.bounds[0][w], g.bounds[1][w]])):
+                    a = fb.distweights(c, gt, (g.bounds[0][w], g.bounds[1][w]), g.l[gt][w], g.dl[gt][w], isbloch[w])
+                    b = osrc.distweights(c, gt, (o.bounds[0][w], o.bounds[1][w]), o.l[gt][w], o.dl[gt][w], isbloch[w])
+                    assert a[0] == b[0] and np.allclose(a[1], b[1], rtol=1e-14, atol=0)
+        mdl = fb.ModelFull(g)
+        c = [rng.uniform(g.bounds[0][w], g.bounds[1][w]) for w in range(3)]
+        fb.add_srce(mdl, fb.PointSrc(c, [1, 2, -1], 0.3 + 0.1j))
+        fb.add_srce(mdl, fb.PlaneSrc([0, 1, 0], c[1], [1, 0, 1], 2.0))
+        fb.add_srcm(mdl, fb.PlaneSrc([0, 0, 1], c[2], [0, 1, 0]))
+        je, jm = osrc.create_field_array(o.N), osrc.create_field_array(o.N)
+        osrc.add_src(je, og.EE, (og.EE,) * 3, o, osrc.PointSrc(c, [1, 2, -1], 0.3 + 0.1j))
+        osrc.add_src(je, og.EE, (og.EE,) * 3, o, osrc.PlaneSrc([0, 1, 0], c[1], [1, 0, 1], 2.0))
+        osrc.add_src(jm, og.HH, (og.EE,) * 3, o, osrc.PlaneSrc([0, 0, 1], c[2], [0, 1, 0]))
+        assert np.allclose(mdl.je_arr, je, rtol=1e-14, atol=0) and np.allclose(mdl.jm_arr, jm, rtol=1e-14, atol=0)
+        vje, vjm = fb.create_srcs(mdl)
+        assert np.array_equal(vje, oop.field_arr2vec(mdl.je_arr)) and vje is not mdl.je_arr
+        fb.clear_srcs(mdl)
+        assert not mdl.je_arr.any() and not mdl.jm_arr.any()
+
+
+def test_pointsrc_conservation_exact():
+    """reference test/source.jl:172-204: 8 non-zeros per component and exact sum on a uniform grid."""
+    g = fb.Grid((np.arange(-10, 11.0),) * 3, (True, True, True))
+    mdl = fb.ModelFull(g)
+    src = fb.PointSrc([0.7, 0.7, 0.7], [1, 1, 1])
+    fb.add_srce(mdl, src)
+    for c in range(3):
+        assert np.count_nonzero(mdl.je_arr[..., c]) == 8
+        assert mdl.je_arr[..., c].sum() == src.Idr * src.p[c]
+    with pytest.raises(ValueError):
+        fb.PlaneSrc([1, 1, 0], 0, [1, 0, 0])
+
+
+def test_dof_ordering_rule():
+    """model.jl:75-83: r = c + 3*(i + Nx*(j + Ny*k)) (cmp-first) or i + Nx*(j + Ny*(k + Nz*c))."""
+    N = (4, 3, 5)
+    F = np.arange(np.prod(N) * 3).reshape(N + (3,)).astype(complex)
+    v = fb.field_arr2vec(F, True)
+    w = fb.field_arr2vec(F, False)
+    for (i, j, k, c) in ((0, 0, 0, 0), (3, 2, 4, 2), (1, 2, 3, 1)):
+        assert v[c + 3 * (i + N[0] * (j + N[1] * k))] == F[i, j, k, c]
+        assert w[i + N[0] * (j + N[1] * (k + N[2] * c))] == F[i, j, k, c]
+    assert np.array_equal(fb.field_vec2arr(v, N, True), F) and np.array_equal(fb.field_vec2arr(w, N, False), F)
+    mdl = fb.ModelFull(fb.Grid(tuple(np.arange(n + 1.0) for n in N), (True,) * 3))
+    assert mdl.size(fb.EE) == (3,) + N and mdl.length(fb.EE) == 3 * 60
+    with pytest.raises(ValueError):
+        fb.create_A(7, 1.0, mdl)      # reference: @error "ft = ... is unsupported." (model.jl:242)

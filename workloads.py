@@ -1,0 +1,177 @@
+"""Synthetic inputs for the BASELINE.json configurations (SURVEY.md §8d recipes) - bench/test infrastructure.
+
+Everything here is host-side numpy and uses only the PRODUCT's host modules (grid geometry, PML), never
+the oracle.  Lengths are in nm; lambda = 1550 nm; boundft = (EE,EE,EE); order_cmpfirst = True; mu = 1.
+
+Each builder returns a dict:
+    N (global), isbloch, kbloch, Npml, grid, omega, sdl_e, sdl_m, e_mikL, eps (this rank's slab
+    [Nx,Ny,k1-k0,3,3]), k0, k1, full_eps, name
+The reference has no mode solver and no TF/SF source (model.jl:30-31, README.md:40); sources are the
+stand-ins of §8d and are built on demand by `rhs()` from PlaneSrc / PointSrc.
+"""
+import numpy as np
+
+import maxwellfdm_jl_b200 as fb
+
+LAMBDA = 1550.0
+OMEGA = 2 * np.pi / LAMBDA
+
+
+def _common(N, delta, isbloch, Npml, kbloch=(0.0, 0.0, 0.0)):
+    lprim = tuple((np.arange(n + 1) - n / 2.0) * delta for n in N)
+    grid = fb.Grid(lprim, isbloch)
+    mdl = fb.ModelFull(grid)
+    fb.set_wpml(mdl, OMEGA)
+    fb.set_Npml(mdl, Npml)
+    fb.set_kbloch(mdl, kbloch)
+    sdl_e, sdl_m, _, _ = fb.create_stretched_dls(mdl)
+    return dict(N=tuple(N), isbloch=tuple(isbloch), kbloch=tuple(kbloch), Npml=Npml, grid=grid, omega=OMEGA,
+                sdl_e=sdl_e, sdl_m=sdl_m, e_mikL=fb.create_e_mikL(mdl), model=mdl)
+
+
+def _fill_1d(centers, delta, half_width):
+    """fraction of the cell [c-d/2, c+d/2] that lies inside |u| <= half_width"""
+    lo = np.maximum(centers - delta / 2, -half_width)
+    hi = np.minimum(centers + delta / 2, half_width)
+    return np.clip(hi - lo, 0.0, None) / delta
+
+
+def _mix(fill, e_in, e_out, harmonic):
+    a = fill * e_in + (1 - fill) * e_out
+    h = 1.0 / (fill / e_in + (1 - fill) / e_out)
+    return np.where(harmonic, h, a)
+
+
+def c1_vacuum_box(N=(40, 40, 40), k0=0, k1=None):
+    """C1: vacuum, 10-cell SC-PML on every side, z-polarised point dipole at the origin."""
+    w = _common(N, LAMBDA / 20, (False, False, False), ((10,) * 3, (10,) * 3))
+    k1 = N[2] if k1 is None else k1
+    eps = np.zeros((N[0], N[1], k1 - k0, 3, 3), np.complex128)
+    for v in range(3):
+        eps[..., v, v] = 1.0
+    w.update(eps=eps, k0=k0, k1=k1, full_eps=False, name=f"C1 vacuum box {N[0]}x{N[1]}x{N[2]} + 10-cell PML")
+    return w
+
+
+def c1_rhs(w):
+    mdl = w["model"]
+    fb.clear_srcs(mdl)
+    fb.add_srce(mdl, fb.PointSrc([0.0, 0.0, 0.0], [0, 0, 1], 1.0))
+    return fb.create_srcs(mdl)
+
+
+def c2_waveguide(N=(200, 200, 200), k0=0, k1=None, period_z=None, seed=20261017, delta=20.0):
+    """C2: Si strip (eps 12.085, 500 x 220 nm, along x) in SiO2 (eps 2.085), 10-cell PML on all sides.
+    Subpixel-smoothing stand-in: arithmetic/harmonic mixing on cells cut by the (axis-aligned) interfaces
+    for the diagonal entries, plus a seeded random SYMMETRIC off-diagonal perturbation 0.2*(U-0.5) on
+    the interface cells so the full-tensor path is exercised.  For weak scaling the cross-section repeats
+    every `period_z` planes so that every z-slab carries the same work."""
+    Nx, Ny, Nz = N
+    w = _common(N, delta, (False, False, False), ((10,) * 3, (10,) * 3))
+    k1 = Nz if k1 is None else k1
+    period_z = Nz if period_z is None else period_z
+    e_si, e_ox = 12.085, 2.085
+    g = w["grid"]
+    yp, yd = g.l[fb.PRIM][1], g.l[fb.DUAL][1]
+    kk = np.arange(k0, k1)
+    zc = ((kk % period_z) - period_z / 2.0) * delta          # primal z of each plane, periodic cross-section
+    zp, zd = zc, zc + delta / 2
+    eps = np.zeros((Nx, Ny, k1 - k0, 3, 3), np.complex128)
+    hw_y, hw_z = 250.0, 110.0
+    # E_x at (dual x, primal y, primal z); E_y at (primal, dual, primal); E_z at (primal, primal, dual)
+    for v, (yy, zz) in enumerate(((yp, zp), (yd, zp), (yp, zd))):
+        fy = _fill_1d(yy, delta, hw_y)[:, None]
+        fz = _fill_1d(zz, delta, hw_z)[None, :]
+        fill = fy * fz
+        cut_y = (fy > 0) & (fy < 1) & (fz > 0)
+        cut_z = (fz > 0) & (fz < 1) & (fy > 0)
+        harmonic = cut_y if v == 1 else (cut_z if v == 2 else np.zeros_like(cut_y))
+        eps[..., v, v] = _mix(fill, e_si, e_ox, harmonic)[None, :, :]
+    # off-diagonal entries live at the voxel corners (primal,primal,primal)
+    fy = _fill_1d(yp, delta, hw_y)[:, None]
+    fz = _fill_1d(zp, delta, hw_z)[None, :]
+    fill = fy * fz
+    iface = ((fill > 0) & (fill < 1))[None, :, :]
+    # include the cells next to the core faces so the perturbed region is a closed shell
+    shell = np.zeros((Ny, k1 - k0), bool)
+    inside = (fill >= 1)
+    for s in (-1, 1):
+        shell |= np.roll(inside, s, axis=0) & ~inside
+        shell |= np.roll(inside, s, axis=1) & ~inside
+    iface = iface | shell[None, :, :]
+    rng = np.random.default_rng(seed + 1000 * k0)
+    for (v, u) in ((0, 1), (0, 2), (1, 2)):
+        pert = 0.2 * (rng.random((Nx, Ny, k1 - k0)) - 0.5) * iface
+        eps[..., v, u] = pert
+        eps[..., u, v] = pert
+    w.update(eps=eps, k0=k0, k1=k1, full_eps=True,
+             name=f"C2 Si strip waveguide in SiO2 {Nx}x{Ny}x{Nz}, full 3x3 eps, 10-cell PML")
+    return w
+
+
+def c2_rhs(w):
+    """'mode-plane source' stand-in: y-polarised PlaneSrc at x = -1500 nm with a Gaussian transverse window."""
+    mdl = w["model"]
+    fb.clear_srcs(mdl)
+    fb.add_srce(mdl, fb.PlaneSrc([1, 0, 0], -1500.0 if w["N"][0] >= 160 else 0.0, [0, 1, 0], 1.0))
+    g = w["grid"]
+    Y = g.l[fb.DUAL][1][None, :, None]
+    Z = g.l[fb.PRIM][2][None, None, :]
+    mdl.je_arr[..., 1] *= np.exp(-(Y / 300.0) ** 2 - (Z / 200.0) ** 2)
+    return fb.create_srcs(mdl)
+
+
+def c3_phc_slab(N=(256, 256, 128), k0=0, k1=None, seed=20261017, delta=15.0):
+    """C3: photonic-crystal slab, Bloch-periodic in x,y (non-zero k), 10-cell PML in z; eps 12 slab of 16
+    cells with an 8x8 supercell of air holes (a = Nx/8 cells, r = 0.3a); hole walls get the seeded
+    symmetric off-diagonal perturbation (stand-in for Kottke smoothing on cylinders)."""
+    Nx, Ny, Nz = N
+    Lx, Ly = Nx * delta, Ny * delta
+    kb = (0.30 * 2 * np.pi / Lx, 0.10 * 2 * np.pi / Ly, 0.0)
+    w = _common(N, delta, (True, True, False), ((0, 0, 10), (0, 0, 10)), kb)
+    k1 = Nz if k1 is None else k1
+    g = w["grid"]
+    a = Nx / 8.0 * delta
+    r = 0.3 * a
+    eps = np.zeros((Nx, Ny, k1 - k0, 3, 3), np.complex128)
+
+    def hole_dist(x, y):
+        X = (x[:, None] + Lx / 2) % a - a / 2
+        Y = (y[None, :] + Ly / 2) % a - a / 2
+        return np.sqrt(X * X + Y * Y)
+
+    zpl = g.l[fb.PRIM][2][k0:k1]
+    zdl = g.l[fb.DUAL][2][k0:k1]
+    half_t = 8 * delta
+    xp, xd = g.l[fb.PRIM][0], g.l[fb.DUAL][0]
+    yp, yd = g.l[fb.PRIM][1], g.l[fb.DUAL][1]
+    for v, (xx, yy, zz) in enumerate(((xd, yp, zpl), (xp, yd, zpl), (xp, yp, zdl))):
+        d = hole_dist(xx, yy)
+        fxy = np.clip((d - r) / delta + 0.5, 0.0, 1.0)          # 0 in hole, 1 in dielectric, linear ramp
+        fz = _fill_1d(zz, delta, half_t)
+        fill = fxy[:, :, None] * fz[None, None, :]
+        eps[..., v, v] = 1.0 + 11.0 * fill
+    d = hole_dist(xp, yp)
+    wall = (np.abs(d - r) < delta)[:, :, None] & (_fill_1d(zpl, delta, half_t) > 0)[None, None, :]
+    rng = np.random.default_rng(seed + 1000 * k0)
+    for (v, u) in ((0, 1), (0, 2), (1, 2)):
+        pert = 0.2 * (rng.random((Nx, Ny, k1 - k0)) - 0.5) * wall
+        eps[..., v, u] = pert
+        eps[..., u, v] = pert
+    w.update(eps=eps, k0=k0, k1=k1, full_eps=True,
+             name=f"C3 PhC slab {Nx}x{Ny}x{Nz}, Bloch x/y (k != 0), PML z, full 3x3 eps")
+    return w
+
+
+def c3_rhs(w):
+    mdl = w["model"]
+    fb.clear_srcs(mdl)
+    zsrc = w["grid"].l[fb.PRIM][2][int(0.75 * w["N"][2])]
+    fb.add_srce(mdl, fb.PlaneSrc([0, 0, 1], zsrc, [1, 0, 0], 1.0))
+    return fb.create_srcs(mdl)
+
+
+def make_operator(w, device=-1, rank=0, nranks=1, kernel=0, **kw):
+    return fb.FdfdOperator(w["N"], w["isbloch"], w["sdl_e"], w["sdl_m"], w["omega"], w["eps"], None, w["e_mikL"],
+                           device=device, rank=rank, nranks=nranks, kernel=kernel,
+                           eps_has_offdiag=w["full_eps"], **kw)
