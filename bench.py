@@ -40,35 +40,53 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled through NVML every ~2 ms while the timed region runs
+    (an nvidia-smi subprocess is too slow for a region of a few tens of ms)."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], False
+        self.index, self.samples, self.stop_flag, self.err = index, [], False, None
+        self.max_mhz = None
 
     def run(self):
-        while not self.stop_flag:
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            # honour CUDA_VISIBLE_DEVICES-style remapping by matching the torch device's UUID when possible
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
-                f = [s.strip() for s in out.strip().split(",")]
-                if len(f) >= 6:
-                    self.samples.append(f)
+                import torch
+                uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+                for i in range(nv.nvmlDeviceGetCount()):
+                    hh = nv.nvmlDeviceGetHandleByIndex(i)
+                    u = nv.nvmlDeviceGetUUID(hh)
+                    u = u.decode() if isinstance(u, bytes) else u
+                    if uuid in u:
+                        h = hh
+                        break
             except Exception:
                 pass
-            time.sleep(0.1)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            while not self.stop_flag:
+                self.samples.append((float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), int(get_reasons(h))))
+                time.sleep(0.002)
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
 
     def summary(self):
         self.stop_flag = True
+        self.join(timeout=2)
         if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(self.samples[0][1]),
-                "reasons": reasons, "samples": len(self.samples)}
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable: " + str(self.err)]}
+        bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+                "hw_power_brake_slowdown": 0x80}
+        allr = 0
+        for _, r in self.samples:
+            allr |= r
+        return {"sm_mhz": statistics.median(c for c, _ in self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": [n for n, b in bits.items() if allr & b], "samples": len(self.samples)}
 
 
 def sample_workload():

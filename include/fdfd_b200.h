@@ -78,6 +78,13 @@ int fdfd_slab_range(fdfd_handle h, int64_t *k0, int64_t *k1);
 /* Pure host helper (no GPU needed): the partition rule itself, for planning and tests. */
 int fdfd_partition(int64_t Nz, int32_t nranks, int32_t rank, int64_t *k0, int64_t *k1);
 
+/* Pure host helper: the halo-exchange plan of rank `rank`.  *up / *dn = the rank that owns plane k1
+ * (above) / plane k0-1 (below), or -1 when that side is a symmetry boundary; the global z boundary
+ * wraps (rank 0 <-> rank P-1) only when wrapz != 0 (Bloch).  Message order used by the library when
+ * up == dn (P == 2 with wrap): first {send my LAST plane -> up, recv my LO halo <- dn}, then
+ * {send my FIRST plane -> dn, recv my HI halo <- up}. */
+int fdfd_halo_plan(int32_t nranks, int32_t rank, int32_t wrapz, int32_t *up, int32_t *dn);
+
 /* Operator inputs - exactly what create_curls / create_paramops hand to MaxwellBase
  * (model.jl:152-155,171-172):
  *   sdl_e[w], sdl_m[w]: the NON-inverted stretched cell sizes s*dl centred at E-field / H-field

@@ -9,7 +9,7 @@ from .sources import PointSrc, PlaneSrc, distweights
 from .model import (Model, ModelFull, set_wpml, set_boundft, set_Npml, set_kbloch, create_e_mikL, clear_srcs,
                     add_srce, add_srcm, create_srcs, create_stretched_dls, create_A, create_b, create_linsys,
                     h_from_e, solve, field_arr2vec, field_vec2arr)
-from .operator import FdfdOperator, comm_unique_id, partition
+from .operator import FdfdOperator, comm_unique_id, partition, halo_plan
 from . import _lib
 
 __all__ = [n for n in dir() if not n.startswith("_")]

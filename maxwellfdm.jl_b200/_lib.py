@@ -44,6 +44,7 @@ SYMBOLS = {
     "fdfd_last_error": (C.c_char_p, [P]),
     "fdfd_slab_range": (C.c_int, [P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "fdfd_partition": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "fdfd_halo_plan": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "fdfd_set_coeffs": (C.c_int, [P, C.POINTER(P), C.POINTER(P)]),
     "fdfd_set_bloch": (C.c_int, [P, P]),
     "fdfd_set_omega": (C.c_int, [P, c128]),

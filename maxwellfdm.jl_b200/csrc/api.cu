@@ -280,6 +280,12 @@ int fdfd_partition(int64_t Nz, int32_t nranks, int32_t rank, int64_t *k0, int64_
     return FDFD_OK;
 }
 
+int fdfd_halo_plan(int32_t nranks, int32_t rank, int32_t wrapz, int32_t *up, int32_t *dn) {
+    if (nranks < 1 || rank < 0 || rank >= nranks || !up || !dn) return FDFD_EINVAL;
+    halo_neighbours(nranks, rank, wrapz != 0, up, dn);
+    return FDFD_OK;
+}
+
 int fdfd_create(fdfd_handle *out, const fdfd_desc *d) {
     if (!out || !d) return set_err(nullptr, FDFD_EINVAL, "fdfd_create: null argument");
     *out = nullptr;

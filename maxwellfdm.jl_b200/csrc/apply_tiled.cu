@@ -25,7 +25,9 @@ namespace fdfd {
 
 namespace {
 
-constexpr int NST = 3;  // ring stages (planes in flight)
+constexpr int NST = 3;     // ring stages (planes in flight)
+constexpr int LZMAX = 64;  // max planes per z-chunk
+constexpr int LZP = LZMAX + 2;
 
 struct TiledParams {
     ApplyParams a;
@@ -92,7 +94,8 @@ __global__ void __launch_bounds__(TX *TY, 1) apply_tiled_kernel(const __grid_con
     double2 *gbuf = hbuf + 2 * STAGE;                                 // HAS_OFF ? 2 * 2 * NT : 0
     double2 *cxs = gbuf + (HAS_OFF ? 4 * NT : 0);                     // 8 * TX  x-coefficient tables
     double2 *cys = cxs + 8 * TX;                                      // 8 * TY
-    uint64_t *bars = reinterpret_cast<uint64_t *>(cys + 8 * TY);      // NST
+    double2 *czs = cys + 8 * TY;                                      // 8 * LZP z-coefficient tables of the chunk
+    uint64_t *bars = reinterpret_cast<uint64_t *>(czs + 8 * LZP);     // NST
 
     const int tid = threadIdx.x;
     const int tx = tid % TX, ty = tid / TX;
@@ -195,6 +198,15 @@ __global__ void __launch_bounds__(TX *TY, 1) apply_tiled_kernel(const __grid_con
                                : a == 4 ? p.c.mi0[1] : a == 5 ? p.c.mi1[1] : a == 6 ? p.c.mo0[1] : p.c.mo1[1];
             cys[t] = src[j];
         }
+        // z tables: entry n <-> local plane kc0-1+n (global index wrapped)
+        for (int t = tid; t < 8 * nplanes; t += NT) {
+            const int a = t / nplanes, n = t % nplanes;
+            int kg = p.kz0 + kc0 - 1 + n;
+            kg = ((kg % p.Nz) + p.Nz) % p.Nz;
+            const double2 *src = a == 0 ? p.c.a0[2] : a == 1 ? p.c.a1[2] : a == 2 ? p.c.b0[2] : a == 3 ? p.c.b1[2]
+                               : a == 4 ? p.c.mi0[2] : a == 5 ? p.c.mi1[2] : a == 6 ? p.c.mo0[2] : p.c.mo1[2];
+            czs[a * LZP + n] = src[kg];
+        }
     }
     __syncthreads();
     if (tid < 32) {
@@ -227,47 +239,37 @@ __global__ void __launch_bounds__(TX *TY, 1) apply_tiled_kernel(const __grid_con
     double2 Eo0 = ering[eo0], Eo1 = ering[eo1], Eo2 = ering[eo2];
     double2 Hpx = c_zero(), Hpy = c_zero();
     double2 Gcx = c_zero(), Gcy = c_zero(), Gcz = c_zero();   // G(k) own
-    double2 Gnx_x = c_zero(), Gny_y = c_zero();               // G_x(k) at x+1, G_y(k) at y+1
+    // software-prefetched material: md of the plane whose outputs come next, q of the plane whose H comes next
+    double2 mdc0 = c_zero(), mdc1 = c_zero(), mdc2 = c_zero();
+    double2 qc0 = c_zero(), qc1 = c_zero(), qc2 = c_zero();
+    if (HAS_Q) {
+        const int64_t mk = (int64_t)kc0 * Nxy + mcell;          // ghosted index of plane kc0-1
+        qc0 = ldg2(&p.q[0][mk]);
+        qc1 = ldg2(&p.q[1][mk]);
+        qc2 = ldg2(&p.q[2][mk]);
+    }
 
     for (int n = 0; n + 1 < nplanes; ++n) {
-        const int k = kc0 - 1 + n;                 // local plane whose H is computed (and y, if k >= kc0)
-        int kg = p.kz0 + k;                        // global z index for the coefficient tables
-        kg = kg < 0 ? kg + p.Nz : (kg >= p.Nz ? kg - p.Nz : kg);
-        int kg1 = kg + 1 >= p.Nz ? kg + 1 - p.Nz : kg + 1;
-        const double2 *es = ering + (n % NST) * STAGE;         // plane k
-        const double2 *en = ering + ((n + 1) % NST) * STAGE;   // plane k+1
+        const int k = kc0 - 1 + n;                              // local plane whose H is computed (and y, if n >= 1)
+        const double2 *es = ering + (n % NST) * STAGE;          // plane k
+        const double2 *en = ering + ((n + 1) % NST) * STAGE;    // plane k+1
         const bool do_out = out_ok && (n >= 1);
+        const int64_t mk = (int64_t)(k + 1) * Nxy + mcell;      // ghosted material index of plane k
 
-        // global loads issued early: material of plane k (outputs) and z coefficients
-        const double2 a0z = ldg2(&p.c.a0[2][kg]), a1z = ldg2(&p.c.a1[2][kg]);
-        const double2 b0z = ldg2(&p.c.b0[2][kg]), b1z = ldg2(&p.c.b1[2][kg]);
-        double2 md0 = c_zero(), md1 = c_zero(), md2 = c_zero();
-        const int64_t mk = (int64_t)(k + 1) * Nxy + mcell;     // ghosted plane index k+1
-        if (p.has_mass && do_out) {
-            md0 = ldg2(&p.md[0][mk]);
-            md1 = ldg2(&p.md[1][mk]);
-            md2 = ldg2(&p.md[2][mk]);
-        }
-        double2 q0, q1, q2;
-        if (HAS_Q) {
-            q0 = ldg2(&p.q[0][mk]);
-            q1 = ldg2(&p.q[1][mk]);
-            q2 = ldg2(&p.q[2][mk]);
-        }
-        double2 o01, o02, o10, o12, o20, o21, mi0z, mi1z;
+        // off-diagonal material of plane k+1: needed after the barrier, issued now
+        double2 o01, o02, o10, o12, o20, o21;
         if (HAS_OFF) {
-            const int64_t mk1 = mk + Nxy;                      // plane k+1
+            const int64_t mk1 = mk + Nxy;
             o01 = ldg2(&p.mo[0][mk1]); o02 = ldg2(&p.mo[1][mk1]);
             o10 = ldg2(&p.mo[2][mk1]); o12 = ldg2(&p.mo[3][mk1]);
             o20 = ldg2(&p.mo[4][mk1]); o21 = ldg2(&p.mo[5][mk1]);
-            mi0z = ldg2(&p.c.mi0[2][kg1]);
-            mi1z = ldg2(&p.c.mi1[2][kg1]);
         }
 
         mbar_wait(&bars[(n + 1) % NST], ((n + 1) / NST) & 1);
         const double2 En0 = en[eo0], En1 = en[eo1], En2 = en[eo2];
         const double2 Exp1 = es[exp1], Exp2 = es[exp2];
         const double2 Eyp0 = es[eyp0], Eyp2 = es[eyp2];
+        const double2 a0z = czs[0 * LZP + n], a1z = czs[1 * LZP + n];
 
         // H(k) = C1 E :  Hx = Dy Ez - Dz Ey,  Hy = Dz Ex - Dx Ez,  Hz = Dx Ey - Dy Ex
         double2 Hx = c_mul(a0y, Eo2);
@@ -283,41 +285,51 @@ __global__ void __launch_bounds__(TX *TY, 1) apply_tiled_kernel(const __grid_con
         Hz = c_fms(a0y, Eo0, Hz);
         Hz = c_fms(a1y, Eyp0, Hz);
         if (HAS_Q) {
-            Hx = c_mul(q0, Hx);
-            Hy = c_mul(q1, Hy);
-            Hz = c_mul(q2, Hz);
+            Hx = c_mul(qc0, Hx);
+            Hy = c_mul(qc1, Hy);
+            Hz = c_mul(qc2, Hz);
         }
         double2 *hb = hbuf + (n & 1) * STAGE;
         hb[ho0] = Hx;
         hb[ho1] = Hy;
         hb[ho2] = Hz;
-
-        double2 Gnz = c_zero();   // G_z(k+1) own
-        double2 Gx1 = c_zero(), Gy1 = c_zero();
-        if (HAS_OFF) {
-            // neighbours of G(k) (written one iteration ago, visible since the previous barrier)
-            const double2 *gc = gbuf + (n & 1) * 2 * NT;
-            Gnx_x = gc[gxp0];
-            Gny_y = gc[gyp1];
-            // G(k+1) at this corner: in-averages of plane k+1, then the off-diagonal material entries
-            const double2 Ax = c_fma(cxs[5 * TX + tx], en[exm0], c_mul(cxs[4 * TX + tx], En0));
-            const double2 Ay = c_fma(cys[5 * TY + ty], en[eym1], c_mul(cys[4 * TY + ty], En1));
-            const double2 Az = c_fma(mi1z, Eo2, c_mul(mi0z, En2));
-            Gx1 = c_fma(o02, Az, c_mul(o01, Ay));
-            Gy1 = c_fma(o12, Az, c_mul(o10, Ax));
-            Gnz = c_fma(o21, Ay, c_mul(o20, Ax));
-            double2 *gn = gbuf + ((n + 1) & 1) * 2 * NT;
-            gn[go0] = Gx1;
-            gn[go1] = Gy1;
-        }
         __syncthreads();
 
         // ring stage of plane k is free now: refill it with load #(n + NST)
         if (tid < 32 && n + NST < nplanes) issue_load(n + NST);
 
+        // prefetch the material of the next plane (a full plane-time ahead of its use)
+        double2 mdn0 = c_zero(), mdn1 = c_zero(), mdn2 = c_zero();
+        if (p.has_mass && out_ok && n + 2 < nplanes) {
+            mdn0 = ldg2(&p.md[0][mk + Nxy]);
+            mdn1 = ldg2(&p.md[1][mk + Nxy]);
+            mdn2 = ldg2(&p.md[2][mk + Nxy]);
+        }
+        if (HAS_Q && n + 2 < nplanes) {
+            qc0 = ldg2(&p.q[0][mk + Nxy]);
+            qc1 = ldg2(&p.q[1][mk + Nxy]);
+            qc2 = ldg2(&p.q[2][mk + Nxy]);
+        }
+
+        double2 Gx1 = c_zero(), Gy1 = c_zero(), Gz1 = c_zero();   // G(k+1) own
+        if (HAS_OFF) {
+            // G(k+1) at this corner: in-averages of plane k+1 (still resident in the ring), then the off-diagonal
+            // material entries; G_x, G_y go to the buffer the NEXT iteration reads after its barrier
+            const double2 Ax = c_fma(cxs[5 * TX + tx], en[exm0], c_mul(cxs[4 * TX + tx], En0));
+            const double2 Ay = c_fma(cys[5 * TY + ty], en[eym1], c_mul(cys[4 * TY + ty], En1));
+            const double2 Az = c_fma(czs[5 * LZP + n + 1], Eo2, c_mul(czs[4 * LZP + n + 1], En2));
+            Gx1 = c_fma(o02, Az, c_mul(o01, Ay));
+            Gy1 = c_fma(o12, Az, c_mul(o10, Ax));
+            Gz1 = c_fma(o21, Ay, c_mul(o20, Ax));
+            double2 *gn = gbuf + ((n + 1) & 1) * 2 * NT;
+            gn[go0] = Gx1;
+            gn[go1] = Gy1;
+        }
+
         if (do_out) {
             const double2 b0x = cxs[2 * TX + tx], b1x = cxs[3 * TX + tx];
             const double2 b0y = cys[2 * TY + ty], b1y = cys[3 * TY + ty];
+            const double2 b0z = czs[2 * LZP + n], b1z = czs[3 * LZP + n];
             const double2 Hy_xm = hb[hxm1], Hz_xm = hb[hxm2];
             const double2 Hx_ym = hb[hym0], Hz_ym = hb[hym2];
             // y = C2 H :  yx = Dy Hz - Dz Hy,  yy = Dz Hx - Dx Hz,  yz = Dx Hy - Dy Hx   (backward differences)
@@ -334,17 +346,18 @@ __global__ void __launch_bounds__(TX *TY, 1) apply_tiled_kernel(const __grid_con
             yz = c_fms(b0y, Hx, yz);
             yz = c_fms(b1y, Hx_ym, yz);
             if (p.has_mass) {
-                yx = c_fma(md0, Eo0, yx);
-                yy = c_fma(md1, Eo1, yy);
-                yz = c_fma(md2, Eo2, yz);
+                yx = c_fma(mdc0, Eo0, yx);
+                yy = c_fma(mdc1, Eo1, yy);
+                yz = c_fma(mdc2, Eo2, yz);
                 if (HAS_OFF) {
-                    const double2 mo0z = ldg2(&p.c.mo0[2][kg]), mo1z = ldg2(&p.c.mo1[2][kg]);
+                    // G(k) neighbours were written in the previous iteration (before this iteration's barrier)
+                    const double2 *gc = gbuf + (n & 1) * 2 * NT;
                     yx = c_fma(cxs[6 * TX + tx], Gcx, yx);
-                    yx = c_fma(cxs[7 * TX + tx], Gnx_x, yx);
+                    yx = c_fma(cxs[7 * TX + tx], gc[gxp0], yx);
                     yy = c_fma(cys[6 * TY + ty], Gcy, yy);
-                    yy = c_fma(cys[7 * TY + ty], Gny_y, yy);
-                    yz = c_fma(mo0z, Gcz, yz);
-                    yz = c_fma(mo1z, Gnz, yz);
+                    yy = c_fma(cys[7 * TY + ty], gc[gyp1], yy);
+                    yz = c_fma(czs[6 * LZP + n], Gcz, yz);
+                    yz = c_fma(czs[7 * LZP + n], Gz1, yz);
                 }
             }
             double2 *yo = p.y + (int64_t)k * p.y_pstride + ((int64_t)gj * Nx + gi) * p.y_es;
@@ -357,10 +370,13 @@ __global__ void __launch_bounds__(TX *TY, 1) apply_tiled_kernel(const __grid_con
         Eo0 = En0;
         Eo1 = En1;
         Eo2 = En2;
+        mdc0 = mdn0;
+        mdc1 = mdn1;
+        mdc2 = mdn2;
         if (HAS_OFF) {
             Gcx = Gx1;
             Gcy = Gy1;
-            Gcz = Gnz;
+            Gcz = Gz1;
         }
     }
 }
@@ -368,7 +384,7 @@ __global__ void __launch_bounds__(TX *TY, 1) apply_tiled_kernel(const __grid_con
 template <bool CMPFIRST, bool HAS_OFF, bool HAS_Q, int TX, int TY>
 size_t tiled_smem_bytes() {
     const size_t NT = TX * TY;
-    return (NST * NT * 3 + 2 * NT * 3 + (HAS_OFF ? 4 * NT : 0) + 8 * TX + 8 * TY) * sizeof(double2) + NST * 8 + 128;
+    return (NST * NT * 3 + 2 * NT * 3 + (HAS_OFF ? 4 * NT : 0) + 8 * TX + 8 * TY + 8 * LZP) * sizeof(double2) + NST * 8 + 128;
 }
 
 template <bool CMPFIRST, bool HAS_OFF, bool HAS_Q, int TX, int TY>
@@ -396,9 +412,9 @@ bool tiled_supported(const ApplyParams &p) {
 static int pick_lz(int ncols, int nplanes) {
     if (nplanes < 4) return nplanes;
     const int sms = 148;
-    int best_lz = nplanes > 64 ? 64 : nplanes;
+    int best_lz = nplanes > LZMAX ? LZMAX : nplanes;
     double best_cost = 1e300;
-    for (int lz = 4; lz <= 64 && lz <= nplanes; ++lz) {
+    for (int lz = 4; lz <= LZMAX && lz <= nplanes; ++lz) {
         const int nch = (nplanes + lz - 1) / lz;
         const long ncta = (long)ncols * nch;
         const long waves = (ncta + sms - 1) / sms;

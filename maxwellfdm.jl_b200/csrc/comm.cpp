@@ -73,6 +73,11 @@ static NcclApi *load_nccl(std::string &err) {
             return set_err((c), FDFD_ENCCL, std::string(#call) + ": " + (c)->nccl->GetErrorString(r__)); \
     } while (0)
 
+void halo_neighbours(int P, int r, bool wrapz, int *up, int *dn) {
+    *up = (r + 1 < P) ? r + 1 : (wrapz ? 0 : -1);
+    *dn = (r > 0) ? r - 1 : (wrapz ? P - 1 : -1);
+}
+
 int comm_unique_id(char id[128], std::string &err) {
     NcclApi *api = load_nccl(err);
     if (!api) return FDFD_ENCCL;
@@ -111,10 +116,8 @@ void comm_destroy(Ctx *c) {
 // (halo buffers) elements.  The global z boundary wraps (rank 0 <-> rank P-1) only for Bloch.
 static int exchange_planes(Ctx *c, const double2 *first, const double2 *last, int64_t src_stride, double2 *lo,
                            double2 *hi, int64_t dst_stride, int npieces, int64_t count, cudaStream_t s) {
-    const int P = c->d.nranks, r = c->d.rank;
-    const bool wrapz = c->d.isbloch[2] != 0;
-    const int up = (r + 1 < P) ? r + 1 : (wrapz ? 0 : -1);
-    const int dn = (r > 0) ? r - 1 : (wrapz ? P - 1 : -1);
+    int up, dn;
+    halo_neighbours(c->d.nranks, c->d.rank, c->d.isbloch[2] != 0, &up, &dn);
     ncclComm_t comm = (ncclComm_t)c->comm;
     NcclApi *n = c->nccl;
     // Message order matters when up == dn (P == 2 with Bloch wrap): NCCL matches several send/recv

@@ -164,6 +164,7 @@ int krylov_solve(Ctx *c, int method, const double2 *b, double2 *x, double rtol, 
                  bool fixed_iters, int *iters, double *relres, double *hist);
 
 // comm.cpp -----------------------------------------------------------------------------------------
+void halo_neighbours(int nranks, int rank, bool wrapz, int *up, int *dn);
 int comm_unique_id(char id[128], std::string &err);
 int comm_init(Ctx *c, const char id[128]);
 void comm_destroy(Ctx *c);

@@ -8,7 +8,9 @@ namespace kry {
 
 constexpr int RB = 256;          // threads per block of the vector kernels
 constexpr int MAXB = 148 * 8;    // blocks (persistent grid-stride)
-constexpr int NSLOT = 16;        struct Red {
+constexpr int NSLOT = 24;         // complex scalar slots
+
+struct Red {
     double2 *partial;      // [NSLOT][MAXB]
     unsigned int *ticket;  // [NSLOT]
     double2 *scal;         // [NSLOT]

@@ -242,3 +242,11 @@ def partition(Nz, nranks, rank):
     if code != L.OK:
         raise ValueError("bad partition arguments")
     return k0.value, k1.value
+
+
+def halo_plan(nranks, rank, wrapz):
+    """(up, dn) neighbour ranks of the z-slab halo exchange (-1: symmetry boundary, no message)."""
+    up, dn = C.c_int32(), C.c_int32()
+    if L.lib().fdfd_halo_plan(int(nranks), int(rank), 1 if wrapz else 0, C.byref(up), C.byref(dn)) != L.OK:
+        raise ValueError("bad halo_plan arguments")
+    return up.value, dn.value
