@@ -17,6 +17,7 @@
 //   * each x element is read from HBM once (+ halo re-reads that hit L2), y written once, material read once.
 // Tile: thread tile TX x TY covers cells [ox, ox+TX) x [oy, oy+TY); outputs are the inner (TX-2) x (TY-2).
 #include <cstdio>
+#include <cstdlib>
 
 #include "cplx.cuh"
 #include "fdfd_internal.h"
@@ -69,6 +70,7 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 __device__ __forceinline__ void fence_barrier_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 template <bool CMPFIRST, int TX, int TY>
@@ -137,32 +139,41 @@ __global__ void __launch_bounds__(TX *TY, 1) apply_tiled_kernel(const __grid_con
         cs = p.x.cs;
         return p.x.base + (int64_t)kk * p.x.pstride;
     };
-    // issue the copies of load #n (plane kc0-1+n) into ring stage n % NST; executed by warp 0
+    // Per-lane copy descriptors (lane r <-> tile row r; component-major layout: up to two (component,row)
+    // pairs per lane), computed once so that issuing a plane costs a handful of instructions.
+    const int lane = tid & 31, wid = tid >> 5;
+    constexpr int NW = NT / 32;
+    constexpr int NPAIR = CMPFIRST ? 1 : (3 * TY + 31) / 32;
+    int cp_j[NPAIR], cp_c[NPAIR], cp_r[NPAIR];
+#pragma unroll
+    for (int q = 0; q < NPAIR; ++q) {
+        const int idx = lane + 32 * q;
+        if (CMPFIRST) { cp_c[q] = 0; cp_r[q] = idx; }
+        else          { cp_c[q] = idx / TY; cp_r[q] = idx % TY; }
+        const bool inr = CMPFIRST ? (idx < TY) : (idx < 3 * TY);
+        cp_j[q] = inr ? row_src(cp_r[q]) : -1;
+    }
+    // issue the copies of load #n (plane kc0-1+n) into ring stage n % NST; executed by ONE warp (any)
     auto issue_load = [&](int n) {
-        const int lane = tid;  // tid < 32
         uint64_t *bar = &bars[n % NST];
         double2 *dst = ering + (n % NST) * STAGE;
         int64_t cs;
         const double2 *src = plane_ptr(kc0 - 1 + n, cs);
         if (lane == 0) mbar_arrive_expect_tx(bar, stage_bytes);
         __syncwarp();
-        if (CMPFIRST) {
-            for (int r = lane; r < TY; r += 32) {
-                const int j = row_src(r);
-                if (j < 0) continue;
+#pragma unroll
+        for (int q = 0; q < NPAIR; ++q) {
+            const int j = cp_j[q];
+            if (j < 0) continue;
+            if (CMPFIRST) {
                 const double2 *srow = src + (int64_t)j * Nx * 3;
-                double2 *drow = dst + r * TX * 3;
+                double2 *drow = dst + cp_r[q] * TX * 3;
                 bulk_g2s(drow + (xlo - ox) * 3, srow + (int64_t)xlo * 3, (uint32_t)(xhi - xlo) * 48u, bar);
                 if (lwrap) bulk_g2s(drow, srow + (int64_t)(Nx - 1) * 3, 48u, bar);
                 if (rwrap) bulk_g2s(drow + (Nx - ox) * 3, srow, 48u, bar);
-            }
-        } else {
-            for (int q = lane; q < 3 * TY; q += 32) {
-                const int c = q / TY, r = q % TY;
-                const int j = row_src(r);
-                if (j < 0) continue;
-                const double2 *srow = src + (int64_t)c * cs + (int64_t)j * Nx;
-                double2 *drow = dst + (c * TY + r) * TX;
+            } else {
+                const double2 *srow = src + (int64_t)cp_c[q] * cs + (int64_t)j * Nx;
+                double2 *drow = dst + (cp_c[q] * TY + cp_r[q]) * TX;
                 bulk_g2s(drow + (xlo - ox), srow + xlo, (uint32_t)(xhi - xlo) * 16u, bar);
                 if (lwrap) bulk_g2s(drow, srow + (Nx - 1), 16u, bar);
                 if (rwrap) bulk_g2s(drow + (Nx - ox), srow, 16u, bar);
@@ -209,10 +220,7 @@ __global__ void __launch_bounds__(TX *TY, 1) apply_tiled_kernel(const __grid_con
         }
     }
     __syncthreads();
-    if (tid < 32) {
-        const int npre = min(NST, nplanes);
-        for (int n = 0; n < npre; ++n) issue_load(n);
-    }
+    if (wid < min(NST, nplanes)) issue_load(wid);   // warp m issues the initial load #m
 
     // loop-invariant shared offsets (neighbour positions clamped into the tile; clamped reads feed masked lanes)
     const int txp = min(tx + 1, TX - 1), typ = min(ty + 1, TY - 1);
@@ -239,8 +247,7 @@ __global__ void __launch_bounds__(TX *TY, 1) apply_tiled_kernel(const __grid_con
     double2 Eo0 = ering[eo0], Eo1 = ering[eo1], Eo2 = ering[eo2];
     double2 Hpx = c_zero(), Hpy = c_zero();
     double2 Gcx = c_zero(), Gcy = c_zero(), Gcz = c_zero();   // G(k) own
-    // software-prefetched material: md of the plane whose outputs come next, q of the plane whose H comes next
-    double2 mdc0 = c_zero(), mdc1 = c_zero(), mdc2 = c_zero();
+    // q of the plane whose H comes next is kept one phase ahead in registers
     double2 qc0 = c_zero(), qc1 = c_zero(), qc2 = c_zero();
     if (HAS_Q) {
         const int64_t mk = (int64_t)kc0 * Nxy + mcell;          // ghosted index of plane kc0-1
@@ -256,13 +263,34 @@ __global__ void __launch_bounds__(TX *TY, 1) apply_tiled_kernel(const __grid_con
         const bool do_out = out_ok && (n >= 1);
         const int64_t mk = (int64_t)(k + 1) * Nxy + mcell;      // ghosted material index of plane k
 
-        // off-diagonal material of plane k+1: needed after the barrier, issued now
+        // Material of this iteration (used after the barrier) is loaded now; it was pulled into L2 two
+        // iterations ago by the prefetches below, so these loads are L2 hits with a whole phase to land.
+        double2 mdc0 = c_zero(), mdc1 = c_zero(), mdc2 = c_zero();
+        if (p.has_mass && do_out) {
+            mdc0 = ldg2(&p.md[0][mk]);
+            mdc1 = ldg2(&p.md[1][mk]);
+            mdc2 = ldg2(&p.md[2][mk]);
+        }
         double2 o01, o02, o10, o12, o20, o21;
         if (HAS_OFF) {
             const int64_t mk1 = mk + Nxy;
             o01 = ldg2(&p.mo[0][mk1]); o02 = ldg2(&p.mo[1][mk1]);
             o10 = ldg2(&p.mo[2][mk1]); o12 = ldg2(&p.mo[3][mk1]);
             o20 = ldg2(&p.mo[4][mk1]); o21 = ldg2(&p.mo[5][mk1]);
+        }
+        if (p.has_mass && k + 2 <= p.nzl) {
+            prefetch_l2(&p.md[0][mk + 2 * Nxy]);
+            prefetch_l2(&p.md[1][mk + 2 * Nxy]);
+            prefetch_l2(&p.md[2][mk + 2 * Nxy]);
+            if (HAS_OFF && k + 3 <= p.nzl) {
+#pragma unroll
+                for (int e = 0; e < 6; ++e) prefetch_l2(&p.mo[e][mk + 3 * Nxy]);
+            }
+        }
+        if (HAS_Q && k + 3 <= p.nzl) {
+            prefetch_l2(&p.q[0][mk + 3 * Nxy]);
+            prefetch_l2(&p.q[1][mk + 3 * Nxy]);
+            prefetch_l2(&p.q[2][mk + 3 * Nxy]);
         }
 
         mbar_wait(&bars[(n + 1) % NST], ((n + 1) / NST) & 1);
@@ -295,16 +323,10 @@ __global__ void __launch_bounds__(TX *TY, 1) apply_tiled_kernel(const __grid_con
         hb[ho2] = Hz;
         __syncthreads();
 
-        // ring stage of plane k is free now: refill it with load #(n + NST)
-        if (tid < 32 && n + NST < nplanes) issue_load(n + NST);
+        // ring stage of plane k is free now: refill it with load #(n + NST); the duty rotates over the warps so
+        // that no warp is systematically late at the next barrier
+        if (wid == n % NW && n + NST < nplanes) issue_load(n + NST);
 
-        // prefetch the material of the next plane (a full plane-time ahead of its use)
-        double2 mdn0 = c_zero(), mdn1 = c_zero(), mdn2 = c_zero();
-        if (p.has_mass && out_ok && n + 2 < nplanes) {
-            mdn0 = ldg2(&p.md[0][mk + Nxy]);
-            mdn1 = ldg2(&p.md[1][mk + Nxy]);
-            mdn2 = ldg2(&p.md[2][mk + Nxy]);
-        }
         if (HAS_Q && n + 2 < nplanes) {
             qc0 = ldg2(&p.q[0][mk + Nxy]);
             qc1 = ldg2(&p.q[1][mk + Nxy]);
@@ -370,9 +392,6 @@ __global__ void __launch_bounds__(TX *TY, 1) apply_tiled_kernel(const __grid_con
         Eo0 = En0;
         Eo1 = En1;
         Eo2 = En2;
-        mdc0 = mdn0;
-        mdc1 = mdn1;
-        mdc2 = mdn2;
         if (HAS_OFF) {
             Gcx = Gx1;
             Gcy = Gy1;
@@ -436,6 +455,10 @@ cudaError_t launch_apply_tiled(const ApplyParams &p, int kl_begin, int kl_end, c
     tp.ntx = (p.Nx + (TX - 2) - 1) / (TX - 2);
     tp.nty = (p.Ny + (TY - 2) - 1) / (TY - 2);
     tp.lz = pick_lz(tp.ntx * tp.nty, kl_end - kl_begin);
+    if (const char *e = getenv("FDFD_LZ")) {   // tuning/debug override of the z-chunk length
+        const int v = atoi(e);
+        if (v >= 1 && v <= LZMAX) tp.lz = v < kl_end - kl_begin ? v : kl_end - kl_begin;
+    }
     tp.nchunk = (kl_end - kl_begin + tp.lz - 1) / tp.lz;
     tp.kl_begin = kl_begin;
     tp.kl_end = kl_end;
