@@ -1,6 +1,7 @@
 // C ABI of libfdfd_b200.so (see include/fdfd_b200.h for the contract and the reference lines each entry
 // point stands in for).  Host-side state handling, device array construction, launches.
 #include <cstdio>
+#include <algorithm>
 #include <cstring>
 #include <new>
 
@@ -255,6 +256,73 @@ static int stage_buffers(Ctx *c) {
     return FDFD_OK;
 }
 
+// fdfd_apply with HOST buffers, pipelined over z sub-slabs: H2D of sub-slab s+1, the kernel of sub-slab s and
+// D2H of sub-slab s-1 run concurrently on three streams (PCIe is full duplex), so the call costs about one
+// direction's transfer time instead of H2D + kernel + D2H.  Needs a single slab, the cmp-first layout (a
+// z sub-slab is contiguous) and the tiled kernel; other configurations use the plain staged path.
+static bool can_pipeline(Ctx *c) {
+    return c->d.nranks == 1 && c->d.order_cmpfirst && c->d.kernel != FDFD_KERNEL_NAIVE && c->s1[0] == 1 &&
+           c->s1[1] == 1 && c->s1[2] == 1 && (c->k1 - c->k0) >= 16;
+}
+
+static int apply_host_pipelined(Ctx *c, const double2 *xh, double2 *yh, bool transpose) {
+    const int64_t nzl = c->k1 - c->k0, pl = c->plane;
+    const int S = (int)std::min<int64_t>(16, nzl / 4);
+    if (!c->stream_d2h) FDFD_CUDA(c, cudaStreamCreateWithFlags(&c->stream_d2h, cudaStreamNonBlocking));
+    while ((int)c->ev_h2d.size() < S + 1) {
+        cudaEvent_t e;
+        FDFD_CUDA(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        c->ev_h2d.push_back(e);
+    }
+    while ((int)c->ev_k.size() < S) {
+        cudaEvent_t e;
+        FDFD_CUDA(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        c->ev_k.push_back(e);
+    }
+    ApplyParams p;
+    fill_params(c, p, c->stage_x, c->stage_y, transpose);
+    auto bound = [&](int s) { return (int)((nzl * s) / S); };
+    // the wrap plane (x_lo = plane nzl-1) first, then the sub-slabs in order
+    FDFD_CUDA(c, cudaMemcpyAsync(c->stage_x + (nzl - 1) * pl, xh + (nzl - 1) * pl, (size_t)pl * sizeof(double2),
+                                 cudaMemcpyHostToDevice, c->stream_copy));
+    FDFD_CUDA(c, cudaEventRecord(c->ev_h2d[S], c->stream_copy));
+    for (int s = 0; s < S; ++s) {
+        const int64_t o = (int64_t)bound(s) * pl, n = (int64_t)(bound(s + 1) - bound(s)) * pl;
+        FDFD_CUDA(c, cudaMemcpyAsync(c->stage_x + o, xh + o, (size_t)n * sizeof(double2), cudaMemcpyHostToDevice,
+                                     c->stream_copy));
+        FDFD_CUDA(c, cudaEventRecord(c->ev_h2d[s], c->stream_copy));
+    }
+    FDFD_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_h2d[S], 0));
+    for (int s = 0; s < S; ++s) {
+        FDFD_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_h2d[std::min(s + 1, S - 1)], 0));
+        int nl = 0;
+        FDFD_CUDA(c, launch_apply_tiled(p, bound(s), bound(s + 1), c->stream, &nl));
+        c->launches += nl;
+        FDFD_CUDA(c, cudaEventRecord(c->ev_k[s], c->stream));
+        FDFD_CUDA(c, cudaStreamWaitEvent(c->stream_d2h, c->ev_k[s], 0));
+        const int64_t o = (int64_t)bound(s) * pl, n = (int64_t)(bound(s + 1) - bound(s)) * pl;
+        FDFD_CUDA(c, cudaMemcpyAsync(yh + o, c->stage_y + o, (size_t)n * sizeof(double2), cudaMemcpyDeviceToHost,
+                                     c->stream_d2h));
+    }
+    FDFD_CUDA(c, cudaStreamSynchronize(c->stream_d2h));
+    FDFD_CUDA(c, cudaStreamSynchronize(c->stream));
+    return FDFD_OK;
+}
+
+static int apply_host(Ctx *c, const fdfd_c128 *x, fdfd_c128 *y, bool transpose) {
+    int r;
+    if ((r = stage_buffers(c)) != FDFD_OK) return r;
+    if ((r = ensure_ready(c)) != FDFD_OK) return r;
+    if (can_pipeline(c))
+        return apply_host_pipelined(c, reinterpret_cast<const double2 *>(x), reinterpret_cast<double2 *>(y), transpose);
+    const size_t bytes = (size_t)c->nloc * sizeof(double2);
+    FDFD_CUDA(c, cudaMemcpyAsync(c->stage_x, x, bytes, cudaMemcpyHostToDevice, c->stream));
+    if ((r = apply_device(c, c->stage_x, c->stage_y, transpose)) != FDFD_OK) return r;
+    FDFD_CUDA(c, cudaMemcpyAsync(y, c->stage_y, bytes, cudaMemcpyDeviceToHost, c->stream));
+    FDFD_CUDA(c, cudaStreamSynchronize(c->stream));
+    return FDFD_OK;
+}
+
 }  // namespace fdfd
 
 using namespace fdfd;
@@ -355,6 +423,9 @@ int fdfd_destroy(fdfd_handle h) {
     free_device(c);
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->stream_copy) cudaStreamDestroy(c->stream_copy);
+    if (c->stream_d2h) cudaStreamDestroy(c->stream_d2h);
+    for (auto e : c->ev_h2d) cudaEventDestroy(e);
+    for (auto e : c->ev_k) cudaEventDestroy(e);
     delete static_cast<fdfd_ctx *>(h);
     return FDFD_OK;
 }
@@ -466,19 +537,10 @@ int fdfd_set_mu(fdfd_handle h, const fdfd_c128 *mu) {
 int fdfd_apply(fdfd_handle h, const fdfd_c128 *x, fdfd_c128 *y, int where) {
     CHECK_H(h);
     if (!x || !y) return set_err(c, FDFD_EINVAL, "fdfd_apply: null argument");
-    int r;
-    if (where == FDFD_DEVICE) {
-        r = apply_device(c, reinterpret_cast<const double2 *>(x), reinterpret_cast<double2 *>(y), false);
-        if (r != FDFD_OK) return r;
-    } else if (where == FDFD_HOST) {
-        if ((r = stage_buffers(c)) != FDFD_OK) return r;
-        const size_t bytes = (size_t)c->nloc * sizeof(double2);
-        FDFD_CUDA(c, cudaMemcpyAsync(c->stage_x, x, bytes, cudaMemcpyHostToDevice, c->stream));
-        if ((r = apply_device(c, c->stage_x, c->stage_y, false)) != FDFD_OK) return r;
-        FDFD_CUDA(c, cudaMemcpyAsync(y, c->stage_y, bytes, cudaMemcpyDeviceToHost, c->stream));
-    } else {
-        return set_err(c, FDFD_EINVAL, "fdfd_apply: bad `where`");
-    }
+    if (where == FDFD_HOST) return apply_host(c, x, y, false);
+    if (where != FDFD_DEVICE) return set_err(c, FDFD_EINVAL, "fdfd_apply: bad `where`");
+    int r = apply_device(c, reinterpret_cast<const double2 *>(x), reinterpret_cast<double2 *>(y), false);
+    if (r != FDFD_OK) return r;
     FDFD_CUDA(c, cudaStreamSynchronize(c->stream));
     return FDFD_OK;
 }
@@ -486,19 +548,10 @@ int fdfd_apply(fdfd_handle h, const fdfd_c128 *x, fdfd_c128 *y, int where) {
 int fdfd_apply_transpose(fdfd_handle h, const fdfd_c128 *x, fdfd_c128 *y, int where) {
     CHECK_H(h);
     if (!x || !y) return set_err(c, FDFD_EINVAL, "fdfd_apply_transpose: null argument");
-    int r;
-    if (where == FDFD_DEVICE) {
-        r = apply_device(c, reinterpret_cast<const double2 *>(x), reinterpret_cast<double2 *>(y), true);
-        if (r != FDFD_OK) return r;
-    } else if (where == FDFD_HOST) {
-        if ((r = stage_buffers(c)) != FDFD_OK) return r;
-        const size_t bytes = (size_t)c->nloc * sizeof(double2);
-        FDFD_CUDA(c, cudaMemcpyAsync(c->stage_x, x, bytes, cudaMemcpyHostToDevice, c->stream));
-        if ((r = apply_device(c, c->stage_x, c->stage_y, true)) != FDFD_OK) return r;
-        FDFD_CUDA(c, cudaMemcpyAsync(y, c->stage_y, bytes, cudaMemcpyDeviceToHost, c->stream));
-    } else {
-        return set_err(c, FDFD_EINVAL, "fdfd_apply_transpose: bad `where`");
-    }
+    if (where == FDFD_HOST) return apply_host(c, x, y, true);
+    if (where != FDFD_DEVICE) return set_err(c, FDFD_EINVAL, "fdfd_apply_transpose: bad `where`");
+    int r = apply_device(c, reinterpret_cast<const double2 *>(x), reinterpret_cast<double2 *>(y), true);
+    if (r != FDFD_OK) return r;
     FDFD_CUDA(c, cudaStreamSynchronize(c->stream));
     return FDFD_OK;
 }

@@ -26,9 +26,8 @@ namespace fdfd {
 
 namespace {
 
-constexpr int NST = 3;     // ring stages (planes in flight)
-constexpr int LZMAX = 64;  // max planes per z-chunk
-constexpr int LZP = LZMAX + 2;
+constexpr int nst_for(int nthreads) { return nthreads <= 256 ? 4 : 3; }   // ring stages (planes in flight)
+constexpr int lzmax_for(int nthreads) { return nthreads <= 256 ? 32 : 64; }     // max planes per z-chunk
 
 struct TiledParams {
     ApplyParams a;
@@ -70,6 +69,14 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 __device__ __forceinline__ void fence_barrier_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
+// TMA-unit 1-D bulk copy shared -> global (bulk async-group completion)
+__device__ __forceinline__ void bulk_s2g(void *dst, const void *src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -84,17 +91,22 @@ struct TileIdx {
 };
 
 template <bool CMPFIRST, bool HAS_OFF, bool HAS_Q, int TX, int TY>
-__global__ void __launch_bounds__(TX *TY, 1) apply_tiled_kernel(const __grid_constant__ TiledParams tp) {
+__global__ void __launch_bounds__(TX *TY, (TX * TY <= 256 ? 2 : 1)) apply_tiled_kernel(const __grid_constant__ TiledParams tp) {
     using TI = TileIdx<CMPFIRST, TX, TY>;
     constexpr int NT = TX * TY;
-    constexpr int STAGE = NT * 3;  // double2 per ring stage
+    constexpr int NST = nst_for(NT);
+    constexpr int LZP = lzmax_for(NT) + 2;
+    constexpr int STAGE = NT * 3 + 4;  // double2 per ring stage / H buffer / y buffer, incl. a 4-element gap
+    constexpr int FPAD = 8;            // slack below stage 0 (x-1 read of the first tile position)
+    constexpr int GST = 2 * NT + 4;    // G buffer (2 components) incl. gap
 
     const ApplyParams &p = tp.a;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    double2 *ering = reinterpret_cast<double2 *>(smem_raw);           // NST * STAGE
+    double2 *ering = reinterpret_cast<double2 *>(smem_raw) + FPAD;    // NST * STAGE (front pad: x-1 / y-1 reads)
     double2 *hbuf = ering + NST * STAGE;                              // 2 * STAGE
     double2 *gbuf = hbuf + 2 * STAGE;                                 // HAS_OFF ? 2 * 2 * NT : 0
-    double2 *cxs = gbuf + (HAS_OFF ? 4 * NT : 0);                     // 8 * TX  x-coefficient tables
+    double2 *ybuf = gbuf + (HAS_OFF ? 2 * GST : 0);                   // 2 * STAGE  y staging for the bulk stores
+    double2 *cxs = ybuf + 2 * STAGE;                                  // 8 * TX  x-coefficient tables
     double2 *cys = cxs + 8 * TX;                                      // 8 * TY
     double2 *czs = cys + 8 * TY;                                      // 8 * LZP z-coefficient tables of the chunk
     uint64_t *bars = reinterpret_cast<uint64_t *>(czs + 8 * LZP);     // NST
@@ -181,6 +193,30 @@ __global__ void __launch_bounds__(TX *TY, 1) apply_tiled_kernel(const __grid_con
         }
     };
 
+    // bulk-store the outputs written at iteration m (plane kc0-1+m) from ybuf[m & 1]: one copy per tile row
+    // (x range = the tile's output columns inside the domain); executed by ONE warp, one async-group per lane
+    auto issue_store = [&](int m) {
+        const double2 *src = ybuf + (m & 1) * STAGE;
+        double2 *dstp = p.y + (int64_t)(kc0 - 1 + m) * p.y_pstride;
+        const int c0 = ox + 1, c1 = min(ox + TX - 1, Nx);
+        if (CMPFIRST) {
+            for (int r = 1 + lane; r <= TY - 2; r += 32) {
+                const int j = oy + r;
+                if (j < Ny) bulk_s2g(dstp + ((int64_t)j * Nx + c0) * 3, src + (r * TX + 1) * 3, (uint32_t)(c1 - c0) * 48u);
+            }
+        } else {
+            for (int q = lane; q < 3 * (TY - 2); q += 32) {
+                const int c = q / (TY - 2), r = 1 + q % (TY - 2);
+                const int j = oy + r;
+                if (j < Ny)
+                    bulk_s2g(dstp + (int64_t)c * p.y_cs + (int64_t)j * Nx + c0, src + (c * TY + r) * TX + 1,
+                             (uint32_t)(c1 - c0) * 16u);
+            }
+        }
+        bulk_commit();
+    };
+    auto store_warp = [&](int m) { return (m + NW / 2) % NW; };   // which warp stores iteration m's outputs
+
     // ---- prologue ---------------------------------------------------------------------------------
     if (tid == 0) {
         for (int s = 0; s < NST; ++s) mbar_init(&bars[s], 1);
@@ -222,31 +258,27 @@ __global__ void __launch_bounds__(TX *TY, 1) apply_tiled_kernel(const __grid_con
     __syncthreads();
     if (wid < min(NST, nplanes)) issue_load(wid);   // warp m issues the initial load #m
 
-    // loop-invariant shared offsets (neighbour positions clamped into the tile; clamped reads feed masked lanes)
-    const int txp = min(tx + 1, TX - 1), typ = min(ty + 1, TY - 1);
-    const int txm = max(tx - 1, 0), tym = max(ty - 1, 0);
-    const int eo0 = TI::e(0, tx, ty), eo1 = TI::e(1, tx, ty), eo2 = TI::e(2, tx, ty);
-    const int exp1 = TI::e(1, txp, ty), exp2 = TI::e(2, txp, ty);   // E_y, E_z at x+1
-    const int eyp0 = TI::e(0, tx, typ), eyp2 = TI::e(2, tx, typ);   // E_x, E_z at y+1
-    const int exm0 = TI::e(0, txm, ty);                             // E_x at x-1 (in-average)
-    const int eym1 = TI::e(1, tx, tym);                             // E_y at y-1
-    const int ho0 = TI::h(0, tx, ty), ho1 = TI::h(1, tx, ty), ho2 = TI::h(2, tx, ty);
-    const int hxm1 = TI::h(1, txm, ty), hxm2 = TI::h(2, txm, ty);   // H_y, H_z at x-1
-    const int hym0 = TI::h(0, tx, tym), hym2 = TI::h(2, tx, tym);   // H_x, H_z at y-1
-    const int go0 = tid, go1 = NT + tid;                            // G_x, G_y own
-    const int gxp0 = ty * TX + txp, gyp1 = NT + typ * TX + tx;      // G_x at x+1, G_y at y+1
-
-    const double2 a0x = cxs[0 * TX + tx], a1x = cxs[1 * TX + tx];
-    const double2 a0y = cys[0 * TY + ty], a1y = cys[1 * TY + ty];
+    // Shared-memory addressing: ONE per-thread base index per tile; every neighbour / component offset is a
+    // compile-time constant (immediate in the LDS/STS).  Reads that leave the tile (tx-1 at tx = 0, ...) land in
+    // padding or in an adjacent buffer: such values only ever feed masked (non-output) lanes.
+    constexpr int EC = CMPFIRST ? 1 : NT;        // E tile: component stride
+    constexpr int EX = CMPFIRST ? 3 : 1;         //         x-neighbour stride
+    constexpr int EY = CMPFIRST ? 3 * TX : TX;   //         y-neighbour stride
+    const int eo = TI::e(0, tx, ty);
+    const int ho = ty * TX + tx;                 // H / G tiles: component stride NT, x stride 1, y stride TX
+    // y-neighbour offsets collapse to 0 on the first / last tile row and x-neighbour reads of the first / last tile
+    // position land in the gaps between buffers, so no read ever touches memory another agent may be writing.
+    const int eyp = ty == TY - 1 ? 0 : EY, eym = ty == 0 ? 0 : EY;
+    const int hyp = ty == TY - 1 ? 0 : TX, hym = ty == 0 ? 0 : TX;
 
     const int64_t Nxy = (int64_t)Nx * Ny;
     const int64_t mcell = (int64_t)cj * Nx + ci;  // in-plane index into the ghosted material arrays
 
     // E(k) own, H(k-1) own, G state
     mbar_wait(&bars[0], 0);
-    double2 Eo0 = ering[eo0], Eo1 = ering[eo1], Eo2 = ering[eo2];
+    double2 Eo0 = ering[eo], Eo1 = ering[eo + EC], Eo2 = ering[eo + 2 * EC];
     double2 Hpx = c_zero(), Hpy = c_zero();
-    double2 Gcx = c_zero(), Gcy = c_zero(), Gcz = c_zero();   // G(k) own
+    double2 Gcz = c_zero();                                   // G_z(k) own
     // q of the plane whose H comes next is kept one phase ahead in registers
     double2 qc0 = c_zero(), qc1 = c_zero(), qc2 = c_zero();
     if (HAS_Q) {
@@ -263,40 +295,37 @@ __global__ void __launch_bounds__(TX *TY, 1) apply_tiled_kernel(const __grid_con
         const bool do_out = out_ok && (n >= 1);
         const int64_t mk = (int64_t)(k + 1) * Nxy + mcell;      // ghosted material index of plane k
 
-        // Material of this iteration (used after the barrier) is loaded now; it was pulled into L2 two
-        // iterations ago by the prefetches below, so these loads are L2 hits with a whole phase to land.
+        // Diagonal-material kernel: md of this plane is loaded now and used after the barrier (it was pulled
+        // into L2 two iterations ago by the prefetch below).  The full-tensor kernel is register-bound, so it
+        // loads its material after the barrier instead (see below).
         double2 mdc0 = c_zero(), mdc1 = c_zero(), mdc2 = c_zero();
-        if (p.has_mass && do_out) {
+        if (!HAS_OFF && p.has_mass && do_out) {
             mdc0 = ldg2(&p.md[0][mk]);
             mdc1 = ldg2(&p.md[1][mk]);
             mdc2 = ldg2(&p.md[2][mk]);
         }
-        double2 o01, o02, o10, o12, o20, o21;
-        if (HAS_OFF) {
-            const int64_t mk1 = mk + Nxy;
-            o01 = ldg2(&p.mo[0][mk1]); o02 = ldg2(&p.mo[1][mk1]);
-            o10 = ldg2(&p.mo[2][mk1]); o12 = ldg2(&p.mo[3][mk1]);
-            o20 = ldg2(&p.mo[4][mk1]); o21 = ldg2(&p.mo[5][mk1]);
-        }
-        if (p.has_mass && k + 2 <= p.nzl) {
+        // L2 prefetch of the material two iterations ahead, bounded by what this chunk will consume
+        if (p.has_mass && n + 3 < nplanes) {
             prefetch_l2(&p.md[0][mk + 2 * Nxy]);
             prefetch_l2(&p.md[1][mk + 2 * Nxy]);
             prefetch_l2(&p.md[2][mk + 2 * Nxy]);
-            if (HAS_OFF && k + 3 <= p.nzl) {
-#pragma unroll
-                for (int e = 0; e < 6; ++e) prefetch_l2(&p.mo[e][mk + 3 * Nxy]);
-            }
         }
-        if (HAS_Q && k + 3 <= p.nzl) {
+        if (HAS_OFF && n + 3 < nplanes) {
+#pragma unroll
+            for (int e = 0; e < 6; ++e) prefetch_l2(&p.mo[e][mk + 3 * Nxy]);
+        }
+        if (HAS_Q && n + 4 < nplanes) {
             prefetch_l2(&p.q[0][mk + 3 * Nxy]);
             prefetch_l2(&p.q[1][mk + 3 * Nxy]);
             prefetch_l2(&p.q[2][mk + 3 * Nxy]);
         }
 
         mbar_wait(&bars[(n + 1) % NST], ((n + 1) / NST) & 1);
-        const double2 En0 = en[eo0], En1 = en[eo1], En2 = en[eo2];
-        const double2 Exp1 = es[exp1], Exp2 = es[exp2];
-        const double2 Eyp0 = es[eyp0], Eyp2 = es[eyp2];
+        const double2 En0 = en[eo], En1 = en[eo + EC], En2 = en[eo + 2 * EC];
+        const double2 Exp1 = es[eo + EC + EX], Exp2 = es[eo + 2 * EC + EX];       // E_y, E_z at x+1
+        const double2 Eyp0 = es[eo + eyp], Eyp2 = es[eo + 2 * EC + eyp];            // E_x, E_z at y+1
+        const double2 a0x = cxs[0 * TX + tx], a1x = cxs[1 * TX + tx];
+        const double2 a0y = cys[0 * TY + ty], a1y = cys[1 * TY + ty];
         const double2 a0z = czs[0 * LZP + n], a1z = czs[1 * LZP + n];
 
         // H(k) = C1 E :  Hx = Dy Ez - Dz Ey,  Hy = Dz Ex - Dx Ez,  Hz = Dx Ey - Dy Ex
@@ -318,14 +347,19 @@ __global__ void __launch_bounds__(TX *TY, 1) apply_tiled_kernel(const __grid_con
             Hz = c_mul(qc2, Hz);
         }
         double2 *hb = hbuf + (n & 1) * STAGE;
-        hb[ho0] = Hx;
-        hb[ho1] = Hy;
-        hb[ho2] = Hz;
+        hb[ho] = Hx;
+        hb[ho + NT] = Hy;
+        hb[ho + 2 * NT] = Hz;
+        // the warp that bulk-stored one iteration ago makes sure those copies have finished READING ybuf before
+        // the barrier lets this iteration's outputs overwrite that buffer
+        if (n >= 3 && wid == store_warp(n - 2)) bulk_wait_read0();
         __syncthreads();
 
         // ring stage of plane k is free now: refill it with load #(n + NST); the duty rotates over the warps so
         // that no warp is systematically late at the next barrier
         if (wid == n % NW && n + NST < nplanes) issue_load(n + NST);
+        // outputs of the previous iteration are complete in ybuf[(n-1)&1] (ordered by the barrier): store them
+        if (n >= 2 && wid == store_warp(n - 1)) issue_store(n - 1);
 
         if (HAS_Q && n + 2 < nplanes) {
             qc0 = ldg2(&p.q[0][mk + Nxy]);
@@ -333,77 +367,97 @@ __global__ void __launch_bounds__(TX *TY, 1) apply_tiled_kernel(const __grid_con
             qc2 = ldg2(&p.q[2][mk + Nxy]);
         }
 
-        double2 Gx1 = c_zero(), Gy1 = c_zero(), Gz1 = c_zero();   // G(k+1) own
+        // full-tensor kernel: issue this phase's material loads first (L2 hits), then do work that does not
+        // depend on them (the curl part of y) while they land
+        double2 o01, o02, o10, o12, o20, o21;
         if (HAS_OFF) {
-            // G(k+1) at this corner: in-averages of plane k+1 (still resident in the ring), then the off-diagonal
-            // material entries; G_x, G_y go to the buffer the NEXT iteration reads after its barrier
-            const double2 Ax = c_fma(cxs[5 * TX + tx], en[exm0], c_mul(cxs[4 * TX + tx], En0));
-            const double2 Ay = c_fma(cys[5 * TY + ty], en[eym1], c_mul(cys[4 * TY + ty], En1));
-            const double2 Az = c_fma(czs[5 * LZP + n + 1], Eo2, c_mul(czs[4 * LZP + n + 1], En2));
-            Gx1 = c_fma(o02, Az, c_mul(o01, Ay));
-            Gy1 = c_fma(o12, Az, c_mul(o10, Ax));
-            Gz1 = c_fma(o21, Ay, c_mul(o20, Ax));
-            double2 *gn = gbuf + ((n + 1) & 1) * 2 * NT;
-            gn[go0] = Gx1;
-            gn[go1] = Gy1;
+            const int64_t mk1 = mk + Nxy;                       // plane k+1
+            o01 = ldg2(&p.mo[0][mk1]); o02 = ldg2(&p.mo[1][mk1]);
+            o10 = ldg2(&p.mo[2][mk1]); o12 = ldg2(&p.mo[3][mk1]);
+            o20 = ldg2(&p.mo[4][mk1]); o21 = ldg2(&p.mo[5][mk1]);
+            if (p.has_mass && do_out) {
+                mdc0 = ldg2(&p.md[0][mk]);
+                mdc1 = ldg2(&p.md[1][mk]);
+                mdc2 = ldg2(&p.md[2][mk]);
+            }
         }
 
+        double2 yx = c_zero(), yy = c_zero(), yz = c_zero();
         if (do_out) {
             const double2 b0x = cxs[2 * TX + tx], b1x = cxs[3 * TX + tx];
             const double2 b0y = cys[2 * TY + ty], b1y = cys[3 * TY + ty];
             const double2 b0z = czs[2 * LZP + n], b1z = czs[3 * LZP + n];
-            const double2 Hy_xm = hb[hxm1], Hz_xm = hb[hxm2];
-            const double2 Hx_ym = hb[hym0], Hz_ym = hb[hym2];
+            const double2 Hy_xm = hb[ho + NT - 1], Hz_xm = hb[ho + 2 * NT - 1];       // H_y, H_z at x-1
+            const double2 Hx_ym = hb[ho - hym], Hz_ym = hb[ho + 2 * NT - hym];          // H_x, H_z at y-1
             // y = C2 H :  yx = Dy Hz - Dz Hy,  yy = Dz Hx - Dx Hz,  yz = Dx Hy - Dy Hx   (backward differences)
-            double2 yx = c_mul(b0y, Hz);
+            yx = c_mul(b0y, Hz);
             yx = c_fma(b1y, Hz_ym, yx);
             yx = c_fms(b0z, Hy, yx);
             yx = c_fms(b1z, Hpy, yx);
-            double2 yy = c_mul(b0z, Hx);
+            yy = c_mul(b0z, Hx);
             yy = c_fma(b1z, Hpx, yy);
             yy = c_fms(b0x, Hz, yy);
             yy = c_fms(b1x, Hz_xm, yy);
-            double2 yz = c_mul(b0x, Hy);
+            yz = c_mul(b0x, Hy);
             yz = c_fma(b1x, Hy_xm, yz);
             yz = c_fms(b0y, Hx, yz);
             yz = c_fms(b1y, Hx_ym, yz);
+        }
+
+        double2 Gz1 = c_zero();                                 // G_z(k+1) own
+        if (HAS_OFF) {
+            // G(k+1) at this corner: in-averages of plane k+1 (still resident in the ring), then the off-diagonal
+            // material entries; G_x, G_y go to the buffer the NEXT iteration reads after its barrier
+            const double2 Ax = c_fma(cxs[5 * TX + tx], en[eo - EX], c_mul(cxs[4 * TX + tx], En0));
+            const double2 Ay = c_fma(cys[5 * TY + ty], en[eo + EC - eym], c_mul(cys[4 * TY + ty], En1));
+            const double2 Az = c_fma(czs[5 * LZP + n + 1], Eo2, c_mul(czs[4 * LZP + n + 1], En2));
+            double2 *gn = gbuf + ((n + 1) & 1) * GST;
+            gn[ho] = c_fma(o02, Az, c_mul(o01, Ay));
+            gn[ho + NT] = c_fma(o12, Az, c_mul(o10, Ax));
+            Gz1 = c_fma(o21, Ay, c_mul(o20, Ax));
+        }
+
+        if (do_out) {
             if (p.has_mass) {
                 yx = c_fma(mdc0, Eo0, yx);
                 yy = c_fma(mdc1, Eo1, yy);
                 yz = c_fma(mdc2, Eo2, yz);
                 if (HAS_OFF) {
-                    // G(k) neighbours were written in the previous iteration (before this iteration's barrier)
-                    const double2 *gc = gbuf + (n & 1) * 2 * NT;
-                    yx = c_fma(cxs[6 * TX + tx], Gcx, yx);
-                    yx = c_fma(cxs[7 * TX + tx], gc[gxp0], yx);
-                    yy = c_fma(cys[6 * TY + ty], Gcy, yy);
-                    yy = c_fma(cys[7 * TY + ty], gc[gyp1], yy);
+                    // G(k): own values and neighbours were written in the previous iteration
+                    const double2 *gc = gbuf + (n & 1) * GST;
+                    yx = c_fma(cxs[6 * TX + tx], gc[ho], yx);
+                    yx = c_fma(cxs[7 * TX + tx], gc[ho + 1], yx);
+                    yy = c_fma(cys[6 * TY + ty], gc[ho + NT], yy);
+                    yy = c_fma(cys[7 * TY + ty], gc[ho + NT + hyp], yy);
                     yz = c_fma(czs[6 * LZP + n], Gcz, yz);
                     yz = c_fma(czs[7 * LZP + n], Gz1, yz);
                 }
             }
-            double2 *yo = p.y + (int64_t)k * p.y_pstride + ((int64_t)gj * Nx + gi) * p.y_es;
-            yo[0] = yx;
-            yo[p.y_cs] = yy;
-            yo[2 * p.y_cs] = yz;
+            double2 *yb = ybuf + (n & 1) * STAGE;
+            yb[eo] = yx;
+            yb[eo + EC] = yy;
+            yb[eo + 2 * EC] = yz;
+            fence_proxy_async();   // make the generic-proxy writes visible to the bulk-copy (async) proxy
         }
         Hpx = Hx;
         Hpy = Hy;
         Eo0 = En0;
         Eo1 = En1;
         Eo2 = En2;
-        if (HAS_OFF) {
-            Gcx = Gx1;
-            Gcy = Gy1;
-            Gcz = Gz1;
-        }
+        if (HAS_OFF) Gcz = Gz1;
     }
+    // outputs of the last iteration
+    __syncthreads();
+    if (nplanes >= 3 && wid == 0) issue_store(nplanes - 2);
+    bulk_wait0();   // every outstanding bulk store of this thread has completed before the CTA exits
 }
 
 template <bool CMPFIRST, bool HAS_OFF, bool HAS_Q, int TX, int TY>
 size_t tiled_smem_bytes() {
-    const size_t NT = TX * TY;
-    return (NST * NT * 3 + 2 * NT * 3 + (HAS_OFF ? 4 * NT : 0) + 8 * TX + 8 * TY + 8 * LZP) * sizeof(double2) + NST * 8 + 128;
+    const size_t NT = TX * TY, NST = nst_for(TX * TY), LZP = lzmax_for(TX * TY) + 2;
+    const size_t STAGE = NT * 3 + 4, GST = 2 * NT + 4, FPAD = 8;
+    return (FPAD + NST * STAGE + 2 * STAGE + (HAS_OFF ? 2 * GST : 0) + 2 * STAGE + 8 * TX + 8 * TY + 8 * LZP) *
+               sizeof(double2) + NST * 8 + 128;
 }
 
 template <bool CMPFIRST, bool HAS_OFF, bool HAS_Q, int TX, int TY>
@@ -428,9 +482,9 @@ bool tiled_supported(const ApplyParams &p) {
 }
 
 // Pick the z-chunk length: enough CTAs to fill 148 SMs for several waves, little ring-prologue overhead.
-static int pick_lz(int ncols, int nplanes) {
+static int pick_lz(int ncols, int nplanes, int cta_per_sm, int LZMAX) {
     if (nplanes < 4) return nplanes;
-    const int sms = 148;
+    const int sms = 148 * cta_per_sm;
     int best_lz = nplanes > LZMAX ? LZMAX : nplanes;
     double best_cost = 1e300;
     for (int lz = 4; lz <= LZMAX && lz <= nplanes; ++lz) {
@@ -444,17 +498,16 @@ static int pick_lz(int ncols, int nplanes) {
     return best_lz;
 }
 
-cudaError_t launch_apply_tiled(const ApplyParams &p, int kl_begin, int kl_end, cudaStream_t s, int *nlaunch) {
-    if (!tiled_supported(p)) return cudaErrorNotSupported;
-    if (kl_end <= kl_begin) return cudaSuccess;
-    constexpr int TX = 32, TY = 16;
+template <int TX, int TY>
+static cudaError_t launch_tile(const ApplyParams &p, int kl_begin, int kl_end, cudaStream_t s) {
     TiledParams tp;
     tp.a = p;
     tp.wrapx = p.wrap[0];
     tp.wrapy = p.wrap[1];
     tp.ntx = (p.Nx + (TX - 2) - 1) / (TX - 2);
     tp.nty = (p.Ny + (TY - 2) - 1) / (TY - 2);
-    tp.lz = pick_lz(tp.ntx * tp.nty, kl_end - kl_begin);
+    constexpr int LZMAX = lzmax_for(TX * TY);
+    tp.lz = pick_lz(tp.ntx * tp.nty, kl_end - kl_begin, TX * TY <= 256 ? 2 : 1, LZMAX);
     if (const char *e = getenv("FDFD_LZ")) {   // tuning/debug override of the z-chunk length
         const int v = atoi(e);
         if (v >= 1 && v <= LZMAX) tp.lz = v < kl_end - kl_begin ? v : kl_end - kl_begin;
@@ -473,6 +526,18 @@ cudaError_t launch_apply_tiled(const ApplyParams &p, int kl_begin, int kl_end, c
         else     { if (q) V(false, false, true); else V(false, false, false); }
     }
 #undef V
+    return e;
+}
+
+cudaError_t launch_apply_tiled(const ApplyParams &p, int kl_begin, int kl_end, cudaStream_t s, int *nlaunch) {
+    if (!tiled_supported(p)) return cudaErrorNotSupported;
+    if (kl_end <= kl_begin) return cudaSuccess;
+    // Tile choice: diagonal material -> 32x8 tiles, two independent CTAs per SM (more concurrency beats the
+    // better halo ratio of the large tile); full tensor -> 32x16 (its shared-memory footprint allows one CTA).
+    static const int ty_env = [] { const char *e = getenv("FDFD_TY"); return e ? atoi(e) : 0; }();
+    const bool full = p.has_off != 0 && p.has_mass != 0;
+    const int ty_sel = ty_env ? ty_env : (full ? 16 : 8);
+    cudaError_t e = ty_sel == 8 ? launch_tile<32, 8>(p, kl_begin, kl_end, s) : launch_tile<32, 16>(p, kl_begin, kl_end, s);
     if (nlaunch) *nlaunch += 1;
     return e;
 }

@@ -73,7 +73,9 @@ struct Ctx {
     fdfd_desc d{};
     int dev = 0;
     cudaStream_t stream = nullptr;
-    cudaStream_t stream_copy = nullptr;
+    cudaStream_t stream_copy = nullptr;   // H2D leg of the pipelined host apply
+    cudaStream_t stream_d2h = nullptr;    // D2H leg
+    std::vector<cudaEvent_t> ev_h2d, ev_k;
     std::string err;
     int64_t launches = 0;
 

@@ -1,0 +1,112 @@
+"""Multi-GPU (z-slab) correctness check, launched with torch.distributed.run, one rank per GPU.
+
+Every rank builds the same seeded global problem, creates its slab operator (NCCL halo exchange +
+allreduce inside libfdfd_b200.so), applies / solves on its slab, and rank 0 compares the gathered result
+with the CPU oracle (small grids) and with a single-slab GPU operator (larger grid)."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from problems import Problem, rel
+import maxwellfdm_jl_b200 as fb
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    fails = []
+
+    def slab_operator(p, **kw):
+        k0, k1 = fb.partition(p.N[2], world, rank)
+        A = fb.FdfdOperator(p.N, p.isbloch, p.sdl_e, p.sdl_m, p.omega, p.eps[:, :, k0:k1],
+                            p.mu[:, :, k0:k1] if p.with_mu else None, p.ph, order_cmpfirst=p.cmpfirst,
+                            device=local, rank=rank, nranks=world, **kw)
+        uid = [fb.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        A.comm_init(uid[0])
+        return A, k0, k1
+
+    def slab_of(p, v, k0, k1):
+        """this rank's slab of a global DOF vector"""
+        Nx, Ny, Nz = p.N
+        if p.cmpfirst:
+            return v[3 * Nx * Ny * k0:3 * Nx * Ny * k1].copy()
+        return np.ascontiguousarray(v.reshape(3, Nz, Ny * Nx)[:, k0:k1]).ravel()
+
+    def gather(p, ys, k0, k1):
+        parts = [None] * world
+        dist.all_gather_object(parts, (k0, k1, ys))
+        Nx, Ny, Nz = p.N
+        if p.cmpfirst:
+            return np.concatenate([a[2] for a in sorted(parts, key=lambda t: t[0])])
+        out = np.empty((3, Nz, Ny * Nx), complex)
+        for a0, a1, a in parts:
+            out[:, a0:a1] = a.reshape(3, a1 - a0, Ny * Nx)
+        return out.ravel()
+
+    cases = []
+    for isbloch in ((True, True, True), (False, True, False), (True, False, True)):
+        for full, mu, cf, kern in ((True, True, True, 0), (False, False, True, 0), (True, False, False, 0),
+                                   (True, True, True, 1)):
+            cases.append(dict(N=(21, 18, 2 * world + 3), isbloch=isbloch, full_eps=full, with_mu=mu, cmpfirst=cf,
+                              kernel=kern))
+    cases.append(dict(N=(9, 7, world), isbloch=(True, True, True), full_eps=True, with_mu=True, cmpfirst=True, kernel=0))
+    for cs in cases:
+        kern = cs.pop("kernel")
+        p = Problem(**cs)
+        A_ref, _ = p.oracle_csc()
+        x = p.random_x()
+        A, k0, k1 = slab_operator(p, kernel=kern)
+        y = gather(p, A @ slab_of(p, x, k0, k1), k0, k1)
+        e1 = rel(y, A_ref.matvec(x))
+        yt = gather(p, A.rmatvec_T(slab_of(p, x, k0, k1)), k0, k1)
+        e2 = rel(yt, A_ref.to_scipy().T @ x)
+        if not (e1 < 1e-12 and e2 < 1e-12):
+            fails.append(("apply", cs, kern, e1, e2))
+        A.close()
+
+    # Krylov across slabs: same iterates as the single-slab solve (allreduced dots), PML box
+    p = Problem((20, 18, max(12, 4 * world)), (False, False, False), npml=3, omega=0.9)
+    A_ref, _ = p.oracle_csc()
+    b = A_ref.matvec(p.random_x(5))
+    A, k0, k1 = slab_operator(p)
+    for method in ("bicgstab", "qmr"):
+        xs, info = A.solve(torch.from_numpy(slab_of(p, b, k0, k1)).cuda(), method=method, rtol=1e-9, maxit=4000,
+                           check_every=10)
+        xg = gather(p, xs.cpu().numpy(), k0, k1)
+        res = rel(A_ref.matvec(xg), b)
+        if not (info["converged"] and res < 1e-8):
+            fails.append(("solve", method, info, res))
+    A.close()
+
+    # larger grid: slab result == single-slab GPU result (tiled kernel, several tiles and chunks)
+    p = Problem((70, 45, 8 * world + 5), (True, False, True), full_eps=True)
+    x = p.random_x()
+    A, k0, k1 = slab_operator(p)
+    y = gather(p, A @ slab_of(p, x, k0, k1), k0, k1)
+    A.close()
+    if rank == 0:
+        A1 = p.operator(device=local)
+        e = rel(y, A1 @ x)
+        if not e < 1e-13:
+            fails.append(("vs single slab", e))
+        A1.close()
+    flag = torch.tensor([len(fails)], device="cuda")
+    dist.all_reduce(flag)
+    if rank == 0:
+        print("DIST_CHECK", "FAIL" if flag.item() else "OK", "world", world, "cases", len(cases), fails[:5])
+    dist.destroy_process_group()
+    sys.exit(1 if flag.item() else 0)
+
+
+if __name__ == "__main__":
+    main()
