@@ -177,6 +177,8 @@ def main():
     ap.add_argument("--krylov-iters", type=int, default=20)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--diag", action="store_true", help="diagonal-eps variant of the workload (48 B/DOF)")
+    ap.add_argument("--dense-off", action="store_true",
+                    help="variant with non-zero off-diagonal eps in EVERY cell (80 B/DOF: dense full-tensor kernel path)")
     ap.add_argument("--n", type=int, nargs=3, default=None, help="override the per-GPU grid (debug)")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -210,6 +212,12 @@ def main():
                 if u != v:
                     w["eps"][..., v, u] = 0
         w["full_eps"] = False
+    if args.dense_off:
+        rng = np.random.default_rng(7 + rank)
+        for (v, u) in ((0, 1), (0, 2), (1, 2)):
+            pert = 0.05 * (rng.random(w["eps"].shape[:3]) - 0.5)
+            w["eps"][..., v, u] = pert
+            w["eps"][..., u, v] = pert
     A = workloads.make_operator(w, device=local, rank=rank, nranks=world)
     if world > 1:
         uid = [fb.comm_unique_id() if rank == 0 else None]
@@ -272,7 +280,10 @@ def main():
 
     if rank == 0:
         peak, peak_src = peaks()
-        bpd = 80 if w["full_eps"] else 48
+        # bytes an apply must move per DOF: x 16 + y 16 + eps_diag 16, + 32 for the six off-diagonal entries on the
+        # (tile, plane) blocks that hold any (the kernel skips empty blocks; dense off-diagonals -> 80)
+        off_frac = A.offdiag_fraction if w["full_eps"] else 0.0
+        bpd = 48 + 32 * off_frac
         achieved = bpd * (n_tot / world) / (ms_step * 1e-3) / 1e9      # per GPU
         traffic = None
         try:
@@ -284,7 +295,9 @@ def main():
             "metric": METRIC, "value": gdofs, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "c128 (complex fp64)", "data": "synthetic",
-            "config": {"workload": w["name"] + (" [diagonal-eps variant]" if args.diag else ""),
+            "config": {"workload": w["name"] + (" [diagonal-eps variant]" if args.diag else "") +
+                       (" [dense off-diagonal variant]" if args.dense_off else ""),
+                       "offdiag_block_fraction": off_frac, "bytes_per_dof_if_dense": 80 if w["full_eps"] else 48,
                        "grid": list(N), "per_gpu_grid": list(per), "dof": n_tot, "parallelism": f"z-slab x{world}",
                        "l2": "inputs (x, y, eps: > 1 GB per GPU) larger than the 126 MB L2; no flush needed",
                        "bytes_per_dof": bpd},

@@ -144,6 +144,10 @@ int fdfd_bench_apply(fdfd_handle h, const fdfd_c128 *x_dev, fdfd_c128 *y_dev, in
 /* Fixed-iteration Krylov run without convergence exit (iterations/s): *ms_total for `iters`. */
 int fdfd_bench_solve(fdfd_handle h, int method, const fdfd_c128 *b_dev, fdfd_c128 *x_dev,
                      int warmup, int iters, double *ms_total);
+/* Fraction of the (x-y tile, z-plane) blocks of this slab that hold a non-zero off-diagonal eps entry.  The
+ * tiled kernel skips the six off-diagonal streams on empty blocks (subpixel smoothing puts off-diagonal
+ * entries only at material interfaces), so the bytes an apply must move are (48 + 32*frac) B/DOF. */
+int fdfd_offdiag_fraction(fdfd_handle h, double *frac);
 /* Number of kernels this handle has launched since creation (for bench.py's gpu_launches). */
 int64_t fdfd_launch_count(fdfd_handle h);
 

@@ -49,7 +49,7 @@ static inline int nblocks(int64_t n) {
 static void free_device(Ctx *c) {
     auto F = [](auto *&p) { if (p) cudaFree((void *)p); p = nullptr; };
     F(c->coef_dev); F(c->mat_dev); F(c->halo_lo); F(c->halo_hi); F(c->work); F(c->scal); F(c->partial);
-    F(c->stage_x); F(c->stage_y); F(c->flush_buf);
+    F(c->stage_x); F(c->stage_y); F(c->flush_buf); F(c->offmask); F(c->corr_list);
     if (c->scal_host) cudaFreeHost(c->scal_host);
     c->scal_host = nullptr;
 }
@@ -194,6 +194,18 @@ int ensure_ready(Ctx *c) {
     if (r != FDFD_OK) return r;
     r = upload_materials(c);
     if (r != FDFD_OK) return r;
+    // occupancy mask of the off-diagonal material for the tiled kernel
+    if (c->offmask) { cudaFree(c->offmask); c->offmask = nullptr; }
+    if (c->corr_list) { cudaFree(c->corr_list); c->corr_list = nullptr; }
+    c->corr_count = 0;
+    c->offmask_ty = 0;
+    c->off_frac = c->mo[0] ? 1.0 : 0.0;
+    if (c->mo[0] && c->d.kernel != FDFD_KERNEL_NAIVE) {
+        ApplyParams p;
+        fill_params(c, p, nullptr, nullptr, false);
+        FDFD_CUDA(c, tiled_build_offmask(p, &c->offmask, &c->offmask_ty, &c->off_frac, &c->corr_list, &c->corr_count,
+                                         c->stream));
+    }
     c->dirty = false;
     return FDFD_OK;
 }
@@ -223,6 +235,8 @@ void fill_params(Ctx *c, ApplyParams &p, const double2 *x, double2 *y, bool tran
         p.x.cs_lo = p.x.cs_hi = p.cmpfirst ? 1 : Nxy;
     }
     p.y = y; p.y_pstride = p.x.pstride; p.y_cs = p.x.cs; p.y_es = p.x.es;
+    p.offmask = c->offmask; p.offmask_ty = c->offmask_ty;
+    p.corr_list = c->corr_list; p.corr_count = c->corr_count;
 }
 
 int apply_device(Ctx *c, const double2 *x, double2 *y, bool transpose) {
@@ -750,6 +764,15 @@ int fdfd_bench_solve(fdfd_handle h, int method, const fdfd_c128 *b, fdfd_c128 *x
     if (ms_total) *ms_total = ms;
     if (r == FDFD_ENOCONV) r = FDFD_OK;
     return r;
+}
+
+int fdfd_offdiag_fraction(fdfd_handle h, double *frac) {
+    CHECK_H(h);
+    if (!frac) return set_err(c, FDFD_EINVAL, "null argument");
+    int r = ensure_ready(c);
+    if (r != FDFD_OK) return r;
+    *frac = c->off_frac;
+    return FDFD_OK;
 }
 
 int64_t fdfd_launch_count(fdfd_handle h) { return h ? static_cast<Ctx *>(h)->launches : 0; }

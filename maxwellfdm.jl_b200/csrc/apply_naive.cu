@@ -172,12 +172,39 @@ __global__ void __launch_bounds__(128) curl2_kernel(const __grid_constant__ Appl
     }
 }
 
+
+// y += Mout[ masso .* (Min x) ] on a list of (tile, plane) output blocks: the off-diagonal part of the mass
+// operator, added after the diagonal-material kernel when off-diagonal entries are sparse (material interfaces).
+// Block = one (30 x 6)-cell output tile of one z-plane; gathers through L1/L2 like the general kernel.
+__global__ void __launch_bounds__(192) offdiag_correction_kernel(const __grid_constant__ ApplyParams p,
+                                                                  const int2 *__restrict__ list, int ntx) {
+    const int2 item = list[blockIdx.x];
+    const int tile = item.x, kl = item.y;
+    const int i = (tile % ntx) * 30 + (int)(threadIdx.x % 32), j = (tile / ntx) * 6 + (int)(threadIdx.x / 32);
+    if ((threadIdx.x % 32) >= 30 || i >= p.Nx || j >= p.Ny) return;
+    Gather g{p};
+#pragma unroll
+    for (int v = 0; v < 3; ++v) {
+        const int iv = g.cidx(v, i, j, kl);
+        double2 t = c_mul(p.c.mo0[v][iv], g.G(v, i, j, kl));
+        t = c_fma(p.c.mo1[v][iv], g.Gsh(v, i, j, kl, p.s1[v]), t);
+        double2 *yo = &p.y[(int64_t)kl * p.y_pstride + (int64_t)v * p.y_cs + ((int64_t)j * p.Nx + i) * p.y_es];
+        *yo = c_add(*yo, t);
+    }
+}
+
 }  // namespace
 
 cudaError_t launch_apply_naive(const ApplyParams &p, cudaStream_t s) {
     dim3 block(128, 1, 1);
     dim3 grid((p.Nx + 127) / 128, p.Ny, p.nzl);
     apply_naive_kernel<<<grid, block, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_offdiag_correction(const ApplyParams &p, const int2 *list, int count, int ntx, cudaStream_t s) {
+    if (count <= 0) return cudaSuccess;
+    offdiag_correction_kernel<<<count, 192, 0, s>>>(p, list, ntx);
     return cudaGetLastError();
 }
 

@@ -18,6 +18,7 @@
 // Tile: thread tile TX x TY covers cells [ox, ox+TX) x [oy, oy+TY); outputs are the inner (TX-2) x (TY-2).
 #include <cstdio>
 #include <cstdlib>
+#include <vector>
 
 #include "cplx.cuh"
 #include "fdfd_internal.h"
@@ -35,6 +36,8 @@ struct TiledParams {
     int32_t ntx, nty, nchunk; // tiles and z-chunks
     int32_t lz;               // planes per chunk
     int32_t kl_begin, kl_end; // local plane range of this launch
+    const unsigned char *offmask;  // [ghosted plane][tile]: 1 if any off-diagonal material entry is non-zero there
+    int32_t filter;           // 0: all work items; 1: only items WITHOUT off-diagonal material; 2: only items WITH
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -121,9 +124,19 @@ __global__ void __launch_bounds__(TX *TY, (TX * TY <= 256 ? 2 : 1)) apply_tiled_
     const int tile_y = b % tp.nty;
     const int chunk = b / tp.nty;
     const int ox = tile_x * (TX - 2) - 1, oy = tile_y * (TY - 2) - 1;
+    const int tile = tile_y * tp.ntx + tile_x, ntile = tp.ntx * tp.nty;
     const int kc0 = tp.kl_begin + chunk * tp.lz;
     const int kc1 = min(kc0 + tp.lz, tp.kl_end);
     const int nplanes = kc1 - kc0 + 2;  // planes kc0-1 .. kc1
+    if (tp.filter != 0) {
+        // split launch: this (tile, z-chunk) work item belongs to exactly one of the two kernels, decided by
+        // whether any plane whose corner terms it needs (kc0 .. kc1) holds off-diagonal material
+        int f = 0;
+        for (int kk = kc0 + (int)threadIdx.x; kk <= kc1; kk += TX * TY)
+            f |= __ldg(&tp.offmask[(int64_t)(kk + 1) * (tp.ntx * tp.nty) + tile_y * tp.ntx + tile_x]);
+        const int any = __syncthreads_or(f);
+        if ((tp.filter == 1 && any) || (tp.filter == 2 && !any)) return;
+    }
 
     const int Nx = p.Nx, Ny = p.Ny;
     const int gi = ox + tx, gj = oy + ty;
@@ -279,6 +292,7 @@ __global__ void __launch_bounds__(TX *TY, (TX * TY <= 256 ? 2 : 1)) apply_tiled_
     double2 Eo0 = ering[eo], Eo1 = ering[eo + EC], Eo2 = ering[eo + 2 * EC];
     double2 Hpx = c_zero(), Hpy = c_zero();
     double2 Gcz = c_zero();                                   // G_z(k) own
+    bool hasc = false;                                        // does plane k of this tile hold off-diagonal material?
     // q of the plane whose H comes next is kept one phase ahead in registers
     double2 qc0 = c_zero(), qc1 = c_zero(), qc2 = c_zero();
     if (HAS_Q) {
@@ -310,7 +324,11 @@ __global__ void __launch_bounds__(TX *TY, (TX * TY <= 256 ? 2 : 1)) apply_tiled_
             prefetch_l2(&p.md[1][mk + 2 * Nxy]);
             prefetch_l2(&p.md[2][mk + 2 * Nxy]);
         }
-        if (HAS_OFF && n + 3 < nplanes) {
+        // Off-diagonal material exists only at material interfaces: a per-(tile, plane) occupancy mask (CTA-uniform)
+        // lets the kernel skip the six off-diagonal streams and the corner terms on empty blocks (exact zeros).
+        const bool hasn = HAS_OFF && (tp.offmask == nullptr || __ldg(&tp.offmask[(int64_t)(k + 2) * ntile + tile]) != 0);
+        if (HAS_OFF && n + 3 < nplanes &&
+            (tp.offmask == nullptr || __ldg(&tp.offmask[(int64_t)(k + 4) * ntile + tile]) != 0)) {
 #pragma unroll
             for (int e = 0; e < 6; ++e) prefetch_l2(&p.mo[e][mk + 3 * Nxy]);
         }
@@ -369,12 +387,14 @@ __global__ void __launch_bounds__(TX *TY, (TX * TY <= 256 ? 2 : 1)) apply_tiled_
 
         // full-tensor kernel: issue this phase's material loads first (L2 hits), then do work that does not
         // depend on them (the curl part of y) while they land
-        double2 o01, o02, o10, o12, o20, o21;
+        double2 o01 = c_zero(), o02 = c_zero(), o10 = c_zero(), o12 = c_zero(), o20 = c_zero(), o21 = c_zero();
         if (HAS_OFF) {
-            const int64_t mk1 = mk + Nxy;                       // plane k+1
-            o01 = ldg2(&p.mo[0][mk1]); o02 = ldg2(&p.mo[1][mk1]);
-            o10 = ldg2(&p.mo[2][mk1]); o12 = ldg2(&p.mo[3][mk1]);
-            o20 = ldg2(&p.mo[4][mk1]); o21 = ldg2(&p.mo[5][mk1]);
+            if (hasn) {
+                const int64_t mk1 = mk + Nxy;                   // plane k+1
+                o01 = ldg2(&p.mo[0][mk1]); o02 = ldg2(&p.mo[1][mk1]);
+                o10 = ldg2(&p.mo[2][mk1]); o12 = ldg2(&p.mo[3][mk1]);
+                o20 = ldg2(&p.mo[4][mk1]); o21 = ldg2(&p.mo[5][mk1]);
+            }
             if (p.has_mass && do_out) {
                 mdc0 = ldg2(&p.md[0][mk]);
                 mdc1 = ldg2(&p.md[1][mk]);
@@ -405,7 +425,7 @@ __global__ void __launch_bounds__(TX *TY, (TX * TY <= 256 ? 2 : 1)) apply_tiled_
         }
 
         double2 Gz1 = c_zero();                                 // G_z(k+1) own
-        if (HAS_OFF) {
+        if (HAS_OFF && hasn) {
             // G(k+1) at this corner: in-averages of plane k+1 (still resident in the ring), then the off-diagonal
             // material entries; G_x, G_y go to the buffer the NEXT iteration reads after its barrier
             const double2 Ax = c_fma(cxs[5 * TX + tx], en[eo - EX], c_mul(cxs[4 * TX + tx], En0));
@@ -422,13 +442,15 @@ __global__ void __launch_bounds__(TX *TY, (TX * TY <= 256 ? 2 : 1)) apply_tiled_
                 yx = c_fma(mdc0, Eo0, yx);
                 yy = c_fma(mdc1, Eo1, yy);
                 yz = c_fma(mdc2, Eo2, yz);
-                if (HAS_OFF) {
+                if (HAS_OFF && hasc) {
                     // G(k): own values and neighbours were written in the previous iteration
                     const double2 *gc = gbuf + (n & 1) * GST;
                     yx = c_fma(cxs[6 * TX + tx], gc[ho], yx);
                     yx = c_fma(cxs[7 * TX + tx], gc[ho + 1], yx);
                     yy = c_fma(cys[6 * TY + ty], gc[ho + NT], yy);
                     yy = c_fma(cys[7 * TY + ty], gc[ho + NT + hyp], yy);
+                }
+                if (HAS_OFF && (hasc || hasn)) {
                     yz = c_fma(czs[6 * LZP + n], Gcz, yz);
                     yz = c_fma(czs[7 * LZP + n], Gz1, yz);
                 }
@@ -444,12 +466,32 @@ __global__ void __launch_bounds__(TX *TY, (TX * TY <= 256 ? 2 : 1)) apply_tiled_
         Eo0 = En0;
         Eo1 = En1;
         Eo2 = En2;
-        if (HAS_OFF) Gcz = Gz1;
+        if (HAS_OFF) { Gcz = Gz1; hasc = hasn; }
     }
     // outputs of the last iteration
     __syncthreads();
     if (nplanes >= 3 && wid == 0) issue_store(nplanes - 2);
     bulk_wait0();   // every outstanding bulk store of this thread has completed before the CTA exits
+}
+
+// occupancy mask of the off-diagonal material: one CTA per (tile, ghosted plane)
+template <int TX, int TY>
+__global__ void __launch_bounds__(TX *TY) build_offmask_kernel(const __grid_constant__ ApplyParams p, int ntx,
+                                                               unsigned char *mask) {
+    const int tile = blockIdx.x, g = blockIdx.y, ntile = gridDim.x;
+    const int tile_x = tile % ntx, tile_y = tile / ntx;
+    const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+    const int gi = tile_x * (TX - 2) - 1 + tx, gj = tile_y * (TY - 2) - 1 + ty;
+    const int ci = ((gi % p.Nx) + p.Nx) % p.Nx, cj = ((gj % p.Ny) + p.Ny) % p.Ny;
+    const int64_t idx = ((int64_t)g * p.Ny + cj) * p.Nx + ci;
+    bool nz = false;
+#pragma unroll
+    for (int e = 0; e < 6; ++e) {
+        const double2 v = p.mo[e][idx];
+        nz |= (v.x != 0.0) || (v.y != 0.0);
+    }
+    const int any = __syncthreads_or(nz ? 1 : 0);
+    if (threadIdx.x == 0) mask[(int64_t)g * ntile + tile] = any ? 1 : 0;
 }
 
 template <bool CMPFIRST, bool HAS_OFF, bool HAS_Q, int TX, int TY>
@@ -499,7 +541,7 @@ static int pick_lz(int ncols, int nplanes, int cta_per_sm, int LZMAX) {
 }
 
 template <int TX, int TY>
-static cudaError_t launch_tile(const ApplyParams &p, int kl_begin, int kl_end, cudaStream_t s) {
+static cudaError_t launch_tile(const ApplyParams &p, int kl_begin, int kl_end, cudaStream_t s, int filter = 0) {
     TiledParams tp;
     tp.a = p;
     tp.wrapx = p.wrap[0];
@@ -515,7 +557,9 @@ static cudaError_t launch_tile(const ApplyParams &p, int kl_begin, int kl_end, c
     tp.nchunk = (kl_end - kl_begin + tp.lz - 1) / tp.lz;
     tp.kl_begin = kl_begin;
     tp.kl_end = kl_end;
-    const bool cf = tp.a.cmpfirst != 0, off = p.has_off != 0 && p.has_mass != 0, q = p.has_q != 0;
+    tp.offmask = (p.offmask && p.offmask_ty == TY) ? p.offmask : nullptr;
+    tp.filter = (tp.offmask && filter != 3) ? filter : 0;
+    const bool cf = tp.a.cmpfirst != 0, off = p.has_off != 0 && p.has_mass != 0 && filter != 1 && filter != 3, q = p.has_q != 0;
     cudaError_t e;
 #define V(CF, OFF, Q) e = launch_variant<CF, OFF, Q, TX, TY>(tp, s)
     if (cf) {
@@ -529,16 +573,103 @@ static cudaError_t launch_tile(const ApplyParams &p, int kl_begin, int kl_end, c
     return e;
 }
 
+// Tile choice.  Diagonal material: 32x8 tiles, two independent CTAs per SM (more concurrency beats the better halo
+// ratio of the large tile).  Full tensor: if most (tile, plane) blocks hold off-diagonal material, one launch of the
+// 32x16 full-tensor kernel; otherwise (the usual case: subpixel smoothing touches only material interfaces) a SPLIT
+// launch on 32x8 tiles - the diagonal kernel takes every work item without off-diagonal material, the full-tensor
+// kernel only the flagged ones.
+static int env_ty() {
+    static const int ty_env = [] { const char *e = getenv("FDFD_TY"); return e ? atoi(e) : 0; }();
+    return (ty_env == 8 || ty_env == 16) ? ty_env : 0;
+}
+
+static cudaError_t build_mask_for(const ApplyParams &p, int TY, unsigned char **mask, double *frac, cudaStream_t s,
+                                  std::vector<unsigned char> *host = nullptr) {
+    constexpr int TX = 32;
+    const int ntx = (p.Nx + (TX - 2) - 1) / (TX - 2), nty = (p.Ny + (TY - 2) - 1) / (TY - 2);
+    const size_t bytes = (size_t)(p.nzl + 2) * ntx * nty;
+    cudaError_t e = cudaMalloc((void **)mask, bytes);
+    if (e != cudaSuccess) return e;
+    dim3 grid(ntx * nty, p.nzl + 2);
+    if (TY == 8) build_offmask_kernel<TX, 8><<<grid, TX * 8, 0, s>>>(p, ntx, *mask);
+    else         build_offmask_kernel<TX, 16><<<grid, TX * 16, 0, s>>>(p, ntx, *mask);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    std::vector<unsigned char> h(bytes);
+    if ((e = cudaMemcpyAsync(h.data(), *mask, bytes, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
+    if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
+    size_t on = 0;
+    const size_t nt = (size_t)ntx * nty;
+    for (size_t i = nt; i < nt * (p.nzl + 1); ++i) on += h[i];
+    *frac = (double)on / (double)(nt * p.nzl);
+    if (host) host->swap(h);
+    return cudaSuccess;
+}
+
+// Build the off-diagonal occupancy mask; *mask is cudaMalloc'ed ((nzl+2) * ntiles bytes), *ty_used the tile height
+// it is valid for (8: split launch, 16: single full-tensor launch), *frac the fraction of (tile, own plane) blocks
+// that hold off-diagonal material.
+cudaError_t tiled_build_offmask(const ApplyParams &p, unsigned char **mask, int *ty_used, double *frac, int2 **corr_list,
+                                int *corr_count, cudaStream_t s) {
+    *mask = nullptr;
+    *ty_used = 0;
+    *frac = 1.0;
+    *corr_list = nullptr;
+    *corr_count = 0;
+    if (!tiled_supported(p) || !p.has_off || !p.has_mass) return cudaSuccess;
+    int TY = env_ty() ? env_ty() : 8;
+    std::vector<unsigned char> h;
+    cudaError_t e = build_mask_for(p, TY, mask, frac, s, &h);
+    if (e != cudaSuccess) return e;
+    if (!env_ty() && *frac > 0.25) {   // dense off-diagonals: the single fused 32x16 launch is the better plan
+        cudaFree(*mask);
+        *mask = nullptr;
+        TY = 16;
+        if ((e = build_mask_for(p, TY, mask, frac, s)) != cudaSuccess) return e;
+    }
+    *ty_used = TY;
+    if (TY == 8) {
+        // output blocks (tile, plane k) whose corner terms G(k) / G(k+1) can be non-zero
+        const int ntx = (p.Nx + 29) / 30, nty = (p.Ny + 5) / 6;
+        const size_t nt = (size_t)ntx * nty;
+        std::vector<int2> list;
+        for (int k = 0; k < p.nzl; ++k)
+            for (size_t t = 0; t < nt; ++t)
+                if (h[(size_t)(k + 1) * nt + t] | h[(size_t)(k + 2) * nt + t]) list.push_back(make_int2((int)t, k));
+        *corr_count = (int)list.size();
+        if (!list.empty()) {
+            if ((e = cudaMalloc((void **)corr_list, list.size() * sizeof(int2))) != cudaSuccess) return e;
+            if ((e = cudaMemcpyAsync(*corr_list, list.data(), list.size() * sizeof(int2), cudaMemcpyHostToDevice, s)) !=
+                cudaSuccess)
+                return e;
+            if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
+        }
+    }
+    return cudaSuccess;
+}
+
 cudaError_t launch_apply_tiled(const ApplyParams &p, int kl_begin, int kl_end, cudaStream_t s, int *nlaunch) {
     if (!tiled_supported(p)) return cudaErrorNotSupported;
     if (kl_end <= kl_begin) return cudaSuccess;
-    // Tile choice: diagonal material -> 32x8 tiles, two independent CTAs per SM (more concurrency beats the
-    // better halo ratio of the large tile); full tensor -> 32x16 (its shared-memory footprint allows one CTA).
-    static const int ty_env = [] { const char *e = getenv("FDFD_TY"); return e ? atoi(e) : 0; }();
     const bool full = p.has_off != 0 && p.has_mass != 0;
-    const int ty_sel = ty_env ? ty_env : (full ? 16 : 8);
-    cudaError_t e = ty_sel == 8 ? launch_tile<32, 8>(p, kl_begin, kl_end, s) : launch_tile<32, 16>(p, kl_begin, kl_end, s);
-    if (nlaunch) *nlaunch += 1;
+    cudaError_t e;
+    if (!full) {
+        e = (env_ty() == 16) ? launch_tile<32, 16>(p, kl_begin, kl_end, s) : launch_tile<32, 8>(p, kl_begin, kl_end, s);
+        if (nlaunch) *nlaunch += 1;
+    } else if (p.offmask && p.offmask_ty == 8 && kl_begin == 0 && kl_end == p.nzl) {
+        // sparse off-diagonals (material interfaces only): diagonal kernel everywhere, then the off-diagonal part
+        // of the mass operator is added on the few flagged (tile, plane) blocks (the operator is linear)
+        e = launch_tile<32, 8>(p, kl_begin, kl_end, s, 3);
+        if (e == cudaSuccess) e = launch_offdiag_correction(p, p.corr_list, p.corr_count, (p.Nx + 29) / 30, s);
+        if (nlaunch) *nlaunch += p.corr_count > 0 ? 2 : 1;
+    } else if (p.offmask && p.offmask_ty == 8) {
+        // sub-range launch (pipelined host path): split launch by work item
+        e = launch_tile<32, 8>(p, kl_begin, kl_end, s, 2);               // flagged items: full-tensor kernel
+        if (e == cudaSuccess) e = launch_tile<32, 8>(p, kl_begin, kl_end, s, 1);   // the rest: diagonal kernel
+        if (nlaunch) *nlaunch += 2;
+    } else {
+        e = launch_tile<32, 16>(p, kl_begin, kl_end, s);
+        if (nlaunch) *nlaunch += 1;
+    }
     return e;
 }
 

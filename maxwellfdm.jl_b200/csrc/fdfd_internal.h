@@ -58,6 +58,10 @@ struct ApplyParams {
     const double2 *mo[6];   // -w^2 * P_vu, order (0,1),(0,2),(1,0),(1,2),(2,0),(2,1)
     const double2 *q[3];    // inverse of the middle diagonal parameter (mu^-1 for FT_EE)
     PlaneSet x;
+    const unsigned char *offmask;  // occupancy mask of the off-diagonal material (tiled kernel), or null
+    int32_t offmask_ty;            // tile height the mask was built for
+    const int2 *corr_list;         // sparse off-diagonals: (tile, plane) output blocks needing the correction pass
+    int32_t corr_count;
     double2 *y;             // output slab, same layout as x.base
     int64_t y_pstride, y_cs;
     int32_t y_es;
@@ -100,6 +104,11 @@ struct Ctx {
     double2 *mat_dev = nullptr;      // md[3], mo[6], q[3] ghosted slabs
     size_t mat_bytes = 0;
     const double2 *md[3]{}, *mo[6]{}, *mo_t[6]{}, *q[3]{};
+    unsigned char *offmask = nullptr;  // device, (nzl+2) x ntiles
+    int offmask_ty = 0;
+    int2 *corr_list = nullptr;         // device list of (tile, plane) output blocks for the correction pass
+    int corr_count = 0;
+    double off_frac = 1.0;             // fraction of (tile, plane) blocks holding off-diagonal material
     int s1[3]{+1, +1, +1};
 
     // halo buffers (device): 2 receive planes, 2 send staging not needed (planes are contiguous
@@ -155,6 +164,9 @@ cudaError_t launch_apply_naive(const ApplyParams &p, cudaStream_t s);
 // returns cudaErrorNotSupported when the tiled kernel does not cover this configuration
 cudaError_t launch_apply_tiled(const ApplyParams &p, int kl_begin, int kl_end, cudaStream_t s, int *nlaunch);
 bool tiled_supported(const ApplyParams &p);
+cudaError_t tiled_build_offmask(const ApplyParams &p, unsigned char **mask, int *ty_used, double *frac, int2 **corr_list,
+                                int *corr_count, cudaStream_t s);
+cudaError_t launch_offdiag_correction(const ApplyParams &p, const int2 *list, int count, int ntx, cudaStream_t s);
 // first-curl only: h = scale * q .* (C1 e + jm)   (h_from_e), naive kernel
 cudaError_t launch_curl1(const ApplyParams &p, const double2 *jm, double2 alpha, cudaStream_t s);
 // second-curl only: y = beta * C2 (q .* h) + gamma * je   (create_b), naive kernel

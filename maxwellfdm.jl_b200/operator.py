@@ -226,6 +226,12 @@ class FdfdOperator:
         return tot.value
 
     @property
+    def offdiag_fraction(self):
+        f = C.c_double()
+        L.check(L.lib().fdfd_offdiag_fraction(self._h, C.byref(f)), self._h)
+        return f.value
+
+    @property
     def launch_count(self):
         return int(L.lib().fdfd_launch_count(self._h))
 

@@ -74,15 +74,37 @@ def main():
             fails.append(("apply", cs, kern, e1, e2))
         A.close()
 
-    # Krylov across slabs: same iterates as the single-slab solve (allreduced dots), PML box
-    p = Problem((20, 18, max(12, 4 * world)), (False, False, False), npml=3, omega=0.9)
-    A_ref, _ = p.oracle_csc()
-    b = A_ref.matvec(p.random_x(5))
-    A, k0, k1 = slab_operator(p)
+    # Krylov across slabs (allreduced dots): vacuum-like PML box with a point-like right-hand side
+    from oracle.grid import Grid, create_stretched_dls
+    n, nz = 16, max(16, 4 * world)
+    lam = 8.0
+    omega = 2 * np.pi / lam
+    grid = Grid(((np.arange(n + 1) - n / 2) * 1.0, (np.arange(n + 1) - n / 2) * 1.0, (np.arange(nz + 1) - nz / 2) * 1.0),
+                (False, False, False))
+    sdl_e, sdl_m, sei, smi = create_stretched_dls(omega, grid, ((4,) * 3, (4,) * 3))
+    eps = np.zeros(grid.N + (3, 3), complex)
+    for v in range(3):
+        eps[..., v, v] = 1.0
+    from oracle import operators as oop
+    Ce, Cm = oop.create_curls(sei, smi, (0, 0, 0), grid.isbloch, np.ones(3, complex))
+    Pe, Pm = oop.create_paramops(eps, np.broadcast_to(np.eye(3), grid.N + (3, 3)), sdl_e, sdl_m, sei, smi, (0, 0, 0),
+                                 grid.isbloch, np.ones(3, complex))
+    A_ref = oop.create_A(0, omega, Pe, Pm, Ce, Cm)
+    b = np.zeros(A_ref.shape[0], complex)
+    b[3 * (n // 2 + n * (n // 2 + n * (nz // 2))) + 2] = 1.0
+
+    class PB:
+        N, cmpfirst = grid.N, True
+    k0, k1 = fb.partition(nz, world, rank)
+    A = fb.FdfdOperator(grid.N, grid.isbloch, sdl_e, sdl_m, omega, eps[:, :, k0:k1], None, np.ones(3, complex),
+                        device=local, rank=rank, nranks=world)
+    uid = [fb.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    A.comm_init(uid[0])
     for method in ("bicgstab", "qmr"):
-        xs, info = A.solve(torch.from_numpy(slab_of(p, b, k0, k1)).cuda(), method=method, rtol=1e-9, maxit=4000,
+        xs, info = A.solve(torch.from_numpy(slab_of(PB, b, k0, k1)).cuda(), method=method, rtol=1e-9, maxit=6000,
                            check_every=10)
-        xg = gather(p, xs.cpu().numpy(), k0, k1)
+        xg = gather(PB, xs.cpu().numpy(), k0, k1)
         res = rel(A_ref.matvec(xg), b)
         if not (info["converged"] and res < 1e-8):
             fails.append(("solve", method, info, res))
