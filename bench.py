@@ -288,7 +288,7 @@ def main():
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-                traffic = json.load(f).get("full" if w["full_eps"] else "diag")
+                traffic = json.load(f).get("dense" if args.dense_off else ("c2" if w["full_eps"] else "diag"))
         except Exception:
             pass
         line = {
@@ -303,7 +303,9 @@ def main():
                        "bytes_per_dof": bpd},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "apply_tiled_kernel (one launch per apply)"},
+                         "kernel": "apply_tiled_kernel (+ offdiag_correction_kernel on flagged blocks when off-diagonal "
+                                   "eps is sparse); traffic from the ncu --set full capture in profiles/",
+                         "bytes_per_dof": bpd},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 16 * n_loc * world,
                     "d2h_bytes_per_step": 16 * n_loc * world, "steps": e2e_steps,
                     "note": "fdfd_apply(FDFD_HOST) with pinned host buffers"},

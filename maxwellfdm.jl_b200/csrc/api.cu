@@ -198,13 +198,14 @@ int ensure_ready(Ctx *c) {
     if (c->offmask) { cudaFree(c->offmask); c->offmask = nullptr; }
     if (c->corr_list) { cudaFree(c->corr_list); c->corr_list = nullptr; }
     c->corr_count = 0;
+    c->corr_off.clear();
     c->offmask_ty = 0;
     c->off_frac = c->mo[0] ? 1.0 : 0.0;
     if (c->mo[0] && c->d.kernel != FDFD_KERNEL_NAIVE) {
         ApplyParams p;
         fill_params(c, p, nullptr, nullptr, false);
         FDFD_CUDA(c, tiled_build_offmask(p, &c->offmask, &c->offmask_ty, &c->off_frac, &c->corr_list, &c->corr_count,
-                                         c->stream));
+                                         &c->corr_off, c->stream));
     }
     c->dirty = false;
     return FDFD_OK;
@@ -237,6 +238,7 @@ void fill_params(Ctx *c, ApplyParams &p, const double2 *x, double2 *y, bool tran
     p.y = y; p.y_pstride = p.x.pstride; p.y_cs = p.x.cs; p.y_es = p.x.es;
     p.offmask = c->offmask; p.offmask_ty = c->offmask_ty;
     p.corr_list = c->corr_list; p.corr_count = c->corr_count;
+    p.corr_off = c->corr_off.empty() ? nullptr : c->corr_off.data();
 }
 
 int apply_device(Ctx *c, const double2 *x, double2 *y, bool transpose) {
@@ -245,14 +247,30 @@ int apply_device(Ctx *c, const double2 *x, double2 *y, bool transpose) {
     if (x == y) return set_err(c, FDFD_EINVAL, "fdfd_apply: x and y must not alias");
     ApplyParams p;
     fill_params(c, p, x, y, transpose);
+    const bool can_tile = tiled_supported(p);
+    if (c->d.kernel == FDFD_KERNEL_TILED && !can_tile)
+        return set_err(c, FDFD_EINVAL, "tiled kernel requires the first curl to be forward on every axis");
+    const bool use_tiled = c->d.kernel != FDFD_KERNEL_NAIVE && can_tile;
+    if (c->d.nranks > 1 && use_tiled && p.nzl >= 4) {
+        // z-slabs: the halo exchange (NCCL, own stream) overlaps the interior planes, which only need this rank's
+        // own planes; the two boundary planes run once the halos have landed (SURVEY.md 8e "Overlap").
+        FDFD_CUDA(c, cudaEventRecord(c->ev_x, c->stream));
+        FDFD_CUDA(c, cudaStreamWaitEvent(c->stream_comm, c->ev_x, 0));
+        if ((r = halo_exchange(c, x, c->halo_lo, c->halo_hi, c->stream_comm)) != FDFD_OK) return r;
+        FDFD_CUDA(c, cudaEventRecord(c->ev_halo, c->stream_comm));
+        int nl = 0;
+        FDFD_CUDA(c, launch_apply_tiled(p, 1, p.nzl - 1, c->stream, &nl));
+        FDFD_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_halo, 0));
+        FDFD_CUDA(c, launch_apply_tiled(p, 0, 1, c->stream, &nl));
+        FDFD_CUDA(c, launch_apply_tiled(p, p.nzl - 1, p.nzl, c->stream, &nl));
+        c->launches += nl;
+        return FDFD_OK;
+    }
     if (c->d.nranks > 1) {
         r = halo_exchange(c, x, c->halo_lo, c->halo_hi, c->stream);
         if (r != FDFD_OK) return r;
     }
-    const bool can_tile = tiled_supported(p);
-    if (c->d.kernel == FDFD_KERNEL_TILED && !can_tile)
-        return set_err(c, FDFD_EINVAL, "tiled kernel requires the first curl to be forward on every axis");
-    if (c->d.kernel != FDFD_KERNEL_NAIVE && can_tile) {
+    if (use_tiled) {
         int nl = 0;
         FDFD_CUDA(c, launch_apply_tiled(p, 0, p.nzl, c->stream, &nl));
         c->launches += nl;
@@ -422,6 +440,9 @@ int fdfd_create(fdfd_handle *out, const fdfd_desc *d) {
         if ((e = cudaMalloc((void **)&c->halo_hi, pb)) != cudaSuccess) return fail(e, "cudaMalloc(halo)");
         cudaMemset(c->halo_lo, 0, pb);
         cudaMemset(c->halo_hi, 0, pb);
+        if ((e = cudaStreamCreateWithFlags(&c->stream_comm, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
+        if ((e = cudaEventCreateWithFlags(&c->ev_x, cudaEventDisableTiming)) != cudaSuccess) return fail(e, "cudaEventCreate");
+        if ((e = cudaEventCreateWithFlags(&c->ev_halo, cudaEventDisableTiming)) != cudaSuccess) return fail(e, "cudaEventCreate");
     }
     *out = c;
     return FDFD_OK;
@@ -438,6 +459,9 @@ int fdfd_destroy(fdfd_handle h) {
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->stream_copy) cudaStreamDestroy(c->stream_copy);
     if (c->stream_d2h) cudaStreamDestroy(c->stream_d2h);
+    if (c->stream_comm) cudaStreamDestroy(c->stream_comm);
+    if (c->ev_x) cudaEventDestroy(c->ev_x);
+    if (c->ev_halo) cudaEventDestroy(c->ev_halo);
     for (auto e : c->ev_h2d) cudaEventDestroy(e);
     for (auto e : c->ev_k) cudaEventDestroy(e);
     delete static_cast<fdfd_ctx *>(h);

@@ -609,7 +609,7 @@ static cudaError_t build_mask_for(const ApplyParams &p, int TY, unsigned char **
 // it is valid for (8: split launch, 16: single full-tensor launch), *frac the fraction of (tile, own plane) blocks
 // that hold off-diagonal material.
 cudaError_t tiled_build_offmask(const ApplyParams &p, unsigned char **mask, int *ty_used, double *frac, int2 **corr_list,
-                                int *corr_count, cudaStream_t s) {
+                                int *corr_count, std::vector<int32_t> *corr_off, cudaStream_t s) {
     *mask = nullptr;
     *ty_used = 0;
     *frac = 1.0;
@@ -632,9 +632,13 @@ cudaError_t tiled_build_offmask(const ApplyParams &p, unsigned char **mask, int 
         const int ntx = (p.Nx + 29) / 30, nty = (p.Ny + 5) / 6;
         const size_t nt = (size_t)ntx * nty;
         std::vector<int2> list;
-        for (int k = 0; k < p.nzl; ++k)
+        corr_off->assign((size_t)p.nzl + 1, 0);
+        for (int k = 0; k < p.nzl; ++k) {
+            (*corr_off)[k] = (int32_t)list.size();
             for (size_t t = 0; t < nt; ++t)
                 if (h[(size_t)(k + 1) * nt + t] | h[(size_t)(k + 2) * nt + t]) list.push_back(make_int2((int)t, k));
+        }
+        (*corr_off)[p.nzl] = (int32_t)list.size();
         *corr_count = (int)list.size();
         if (!list.empty()) {
             if ((e = cudaMalloc((void **)corr_list, list.size() * sizeof(int2))) != cudaSuccess) return e;
@@ -655,17 +659,13 @@ cudaError_t launch_apply_tiled(const ApplyParams &p, int kl_begin, int kl_end, c
     if (!full) {
         e = (env_ty() == 16) ? launch_tile<32, 16>(p, kl_begin, kl_end, s) : launch_tile<32, 8>(p, kl_begin, kl_end, s);
         if (nlaunch) *nlaunch += 1;
-    } else if (p.offmask && p.offmask_ty == 8 && kl_begin == 0 && kl_end == p.nzl) {
+    } else if (p.offmask && p.offmask_ty == 8 && p.corr_off) {
         // sparse off-diagonals (material interfaces only): diagonal kernel everywhere, then the off-diagonal part
-        // of the mass operator is added on the few flagged (tile, plane) blocks (the operator is linear)
+        // of the mass operator is added on the few flagged (tile, plane) blocks of this plane range (linearity)
         e = launch_tile<32, 8>(p, kl_begin, kl_end, s, 3);
-        if (e == cudaSuccess) e = launch_offdiag_correction(p, p.corr_list, p.corr_count, (p.Nx + 29) / 30, s);
-        if (nlaunch) *nlaunch += p.corr_count > 0 ? 2 : 1;
-    } else if (p.offmask && p.offmask_ty == 8) {
-        // sub-range launch (pipelined host path): split launch by work item
-        e = launch_tile<32, 8>(p, kl_begin, kl_end, s, 2);               // flagged items: full-tensor kernel
-        if (e == cudaSuccess) e = launch_tile<32, 8>(p, kl_begin, kl_end, s, 1);   // the rest: diagonal kernel
-        if (nlaunch) *nlaunch += 2;
+        const int first = p.corr_off[kl_begin], cnt = p.corr_off[kl_end] - first;
+        if (e == cudaSuccess) e = launch_offdiag_correction(p, p.corr_list + first, cnt, (p.Nx + 29) / 30, s);
+        if (nlaunch) *nlaunch += cnt > 0 ? 2 : 1;
     } else {
         e = launch_tile<32, 16>(p, kl_begin, kl_end, s);
         if (nlaunch) *nlaunch += 1;
