@@ -56,6 +56,8 @@ SYMBOLS = {
                              C.POINTER(C.c_int), C.POINTER(C.c_double), P]),
     "fdfd_export_pattern": (C.c_int, [P, P, P, P, C.POINTER(C.c_int64)]),
     "fdfd_h_from_e": (C.c_int, [P, P, P, P, C.c_int]),
+    "fdfd_e_from_h": (C.c_int, [P, P, P, P, C.c_int]),
+    "fdfd_interp_corners": (C.c_int, [P, C.c_int, P, P, C.c_int]),
     "fdfd_create_b": (C.c_int, [P, P, P, P, C.c_int]),
     "fdfd_comm_unique_id": (C.c_int, [C.c_char_p]),
     "fdfd_comm_init": (C.c_int, [P, C.c_char_p]),

@@ -63,8 +63,8 @@ static int upload_coefs(Ctx *c) {
     transpose_coefs(f, t);
     for (int w = 0; w < 3; ++w) c->s1[w] = f.a[w].shift;
     const int64_t Ns = c->d.N[0] + c->d.N[1] + c->d.N[2];
-    const size_t bytes = (size_t)(2 * 8 * Ns) * sizeof(double2);
-    std::vector<cplx> host((size_t)2 * 8 * Ns);
+    const size_t bytes = (size_t)(2 * 10 * Ns) * sizeof(double2);
+    std::vector<cplx> host((size_t)2 * 10 * Ns);
     if (c->coef_bytes != bytes) {
         if (c->coef_dev) cudaFree(c->coef_dev);
         c->coef_dev = nullptr;
@@ -85,6 +85,7 @@ static int upload_coefs(Ctx *c) {
             put(h.b[w].t0, d.b0[w]); put(h.b[w].t1, d.b1[w]);
             put(h.mi[w].t0, d.mi0[w]); put(h.mi[w].t1, d.mi1[w]);
             put(h.mo[w].t0, d.mo0[w]); put(h.mo[w].t1, d.mo1[w]);
+            put(h.mh[w].t0, d.mh0[w]); put(h.mh[w].t1, d.mh1[w]);
         }
     }
     FDFD_CUDA(c, cudaMemcpyAsync(c->coef_dev, host.data(), bytes, cudaMemcpyHostToDevice, c->stream));
@@ -253,16 +254,19 @@ int apply_device(Ctx *c, const double2 *x, double2 *y, bool transpose) {
     const bool use_tiled = c->d.kernel != FDFD_KERNEL_NAIVE && can_tile;
     if (c->d.nranks > 1 && use_tiled && p.nzl >= 4) {
         // z-slabs: the halo exchange (NCCL, own stream) overlaps the interior planes, which only need this rank's
-        // own planes; the two boundary planes run once the halos have landed (SURVEY.md 8e "Overlap").
+        // own planes; the two boundary planes run on a high-priority stream as soon as the halos have landed,
+        // concurrently with the interior kernel (SURVEY.md 8e "Overlap").
         FDFD_CUDA(c, cudaEventRecord(c->ev_x, c->stream));
         FDFD_CUDA(c, cudaStreamWaitEvent(c->stream_comm, c->ev_x, 0));
         if ((r = halo_exchange(c, x, c->halo_lo, c->halo_hi, c->stream_comm)) != FDFD_OK) return r;
         FDFD_CUDA(c, cudaEventRecord(c->ev_halo, c->stream_comm));
         int nl = 0;
+        FDFD_CUDA(c, cudaStreamWaitEvent(c->stream_bnd, c->ev_halo, 0));
+        FDFD_CUDA(c, launch_apply_tiled(p, 0, 1, c->stream_bnd, &nl));
+        FDFD_CUDA(c, launch_apply_tiled(p, p.nzl - 1, p.nzl, c->stream_bnd, &nl));
+        FDFD_CUDA(c, cudaEventRecord(c->ev_bnd, c->stream_bnd));
         FDFD_CUDA(c, launch_apply_tiled(p, 1, p.nzl - 1, c->stream, &nl));
-        FDFD_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_halo, 0));
-        FDFD_CUDA(c, launch_apply_tiled(p, 0, 1, c->stream, &nl));
-        FDFD_CUDA(c, launch_apply_tiled(p, p.nzl - 1, p.nzl, c->stream, &nl));
+        FDFD_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_bnd, 0));
         c->launches += nl;
         return FDFD_OK;
     }
@@ -443,6 +447,13 @@ int fdfd_create(fdfd_handle *out, const fdfd_desc *d) {
         if ((e = cudaStreamCreateWithFlags(&c->stream_comm, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
         if ((e = cudaEventCreateWithFlags(&c->ev_x, cudaEventDisableTiming)) != cudaSuccess) return fail(e, "cudaEventCreate");
         if ((e = cudaEventCreateWithFlags(&c->ev_halo, cudaEventDisableTiming)) != cudaSuccess) return fail(e, "cudaEventCreate");
+        if ((e = cudaEventCreateWithFlags(&c->ev_bnd, cudaEventDisableTiming)) != cudaSuccess) return fail(e, "cudaEventCreate");
+        {
+            int lo_pri = 0, hi_pri = 0;
+            cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri);
+            if ((e = cudaStreamCreateWithPriority(&c->stream_bnd, cudaStreamNonBlocking, hi_pri)) != cudaSuccess)
+                return fail(e, "cudaStreamCreate");
+        }
     }
     *out = c;
     return FDFD_OK;
@@ -462,6 +473,8 @@ int fdfd_destroy(fdfd_handle h) {
     if (c->stream_comm) cudaStreamDestroy(c->stream_comm);
     if (c->ev_x) cudaEventDestroy(c->ev_x);
     if (c->ev_halo) cudaEventDestroy(c->ev_halo);
+    if (c->ev_bnd) cudaEventDestroy(c->ev_bnd);
+    if (c->stream_bnd) cudaStreamDestroy(c->stream_bnd);
     for (auto e : c->ev_h2d) cudaEventDestroy(e);
     for (auto e : c->ev_k) cudaEventDestroy(e);
     delete static_cast<fdfd_ctx *>(h);
@@ -694,6 +707,70 @@ int fdfd_create_b(fdfd_handle h, const fdfd_c128 *je, const fdfd_c128 *jm, fdfd_
     if (where == FDFD_HOST) FDFD_CUDA(c, cudaMemcpyAsync(b, c->stage_y, bytes, cudaMemcpyDeviceToHost, c->stream));
     FDFD_CUDA(c, cudaStreamSynchronize(c->stream));
     if (tmp) cudaFree(tmp);
+    return FDFD_OK;
+}
+
+int fdfd_e_from_h(fdfd_handle h, const fdfd_c128 *hf, const fdfd_c128 *je, fdfd_c128 *eout, int where) {
+    CHECK_H(h);
+    if (!hf || !eout) return set_err(c, FDFD_EINVAL, "fdfd_e_from_h: null argument");
+    if (c->d.field_type != FDFD_FT_EE) return set_err(c, FDFD_EINVAL, "fdfd_e_from_h needs an FT_EE handle");
+    if (c->omega == cplx(0.0)) return set_err(c, FDFD_EINVAL, "fdfd_e_from_h: omega == 0");
+    int r = ensure_ready(c);
+    if (r != FDFD_OK) return r;
+    if (c->mo[0]) return set_err(c, FDFD_EINVAL, "fdfd_e_from_h: Peps must be diagonal (reference model.jl:239,283)");
+    const size_t bytes = (size_t)c->nloc * sizeof(double2);
+    const double2 *dh = reinterpret_cast<const double2 *>(hf), *dj = reinterpret_cast<const double2 *>(je);
+    double2 *de = reinterpret_cast<double2 *>(eout);
+    double2 *tmp = nullptr;
+    if (where == FDFD_HOST) {
+        if ((r = stage_buffers(c)) != FDFD_OK) return r;
+        FDFD_CUDA(c, cudaMemcpyAsync(c->stage_x, hf, bytes, cudaMemcpyHostToDevice, c->stream));
+        dh = c->stage_x;
+        if (je) {
+            FDFD_CUDA(c, cudaMalloc((void **)&tmp, bytes));
+            FDFD_CUDA(c, cudaMemcpyAsync(tmp, je, bytes, cudaMemcpyHostToDevice, c->stream));
+            dj = tmp;
+        }
+        de = c->stage_y;
+    }
+    ApplyParams p;
+    fill_params(c, p, dh, de, false);
+    p.has_q = 0;   // Cm acts on h itself here, not on mu^-1 h
+    if (c->d.nranks > 1 && (r = halo_exchange(c, dh, c->halo_lo, c->halo_hi, c->stream)) != FDFD_OK) return r;
+    // e = (-i/w) (Cm h - je) / eps = (i w) (Cm h - je) / (-w^2 eps) = (i w) (Cm h - je) / md
+    const cplx f = cplx(0.0, 1.0) * c->omega;
+    FDFD_CUDA(c, launch_curl2(p, dj, make_double2(f.real(), f.imag()), make_double2(-f.real(), -f.imag()), 1,
+                              c->stream, 1));
+    c->launches += 1;
+    if (where == FDFD_HOST) FDFD_CUDA(c, cudaMemcpyAsync(eout, c->stage_y, bytes, cudaMemcpyDeviceToHost, c->stream));
+    FDFD_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (tmp) cudaFree(tmp);
+    return FDFD_OK;
+}
+
+int fdfd_interp_corners(fdfd_handle h, int which, const fdfd_c128 *f, fdfd_c128 *out, int where) {
+    CHECK_H(h);
+    if (!f || !out) return set_err(c, FDFD_EINVAL, "fdfd_interp_corners: null argument");
+    if (which != FDFD_FT_EE && which != FDFD_FT_HH) return set_err(c, FDFD_EINVAL, "ft is unsupported.");
+    int r = ensure_ready(c);
+    if (r != FDFD_OK) return r;
+    const size_t bytes = (size_t)c->nloc * sizeof(double2);
+    const double2 *df = reinterpret_cast<const double2 *>(f);
+    double2 *dout = reinterpret_cast<double2 *>(out);
+    if (where == FDFD_HOST) {
+        if ((r = stage_buffers(c)) != FDFD_OK) return r;
+        FDFD_CUDA(c, cudaMemcpyAsync(c->stage_x, f, bytes, cudaMemcpyHostToDevice, c->stream));
+        df = c->stage_x;
+        dout = c->stage_y;
+    }
+    ApplyParams p;
+    fill_params(c, p, df, dout, false);
+    if (c->d.nranks > 1 && (r = halo_exchange(c, df, c->halo_lo, c->halo_hi, c->stream)) != FDFD_OK) return r;
+    // the handle's own field type uses the in-average tables (shift -s1), the other field the mh tables (+s1)
+    FDFD_CUDA(c, launch_interp(p, which == c->d.field_type ? 0 : 1, c->stream));
+    c->launches += 1;
+    if (where == FDFD_HOST) FDFD_CUDA(c, cudaMemcpyAsync(out, c->stage_y, bytes, cudaMemcpyDeviceToHost, c->stream));
+    FDFD_CUDA(c, cudaStreamSynchronize(c->stream));
     return FDFD_OK;
 }
 

@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(128) curl1_kernel(const __grid_constant__ Appl
 // y = beta * C2 (q .* h) + gamma * je      (create_b, reference model.jl:262-265: b = -Cm (Pmu \ jm) - i w je)
 // p.x holds h (may be null planes when has_h == 0).
 __global__ void __launch_bounds__(128) curl2_kernel(const __grid_constant__ ApplyParams p, const double2 *je,
-                                                     double2 beta, double2 gamma, int has_h) {
+                                                     double2 beta, double2 gamma, int has_h, int divide_by_md) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y;
     const int kl = blockIdx.z;
@@ -168,10 +168,29 @@ __global__ void __launch_bounds__(128) curl2_kernel(const __grid_constant__ Appl
             y = c_mul(beta, t);
         }
         if (je) y = c_fma(gamma, je[o], y);
+        if (divide_by_md) y = c_div(y, p.md[v][g.gidx(i, j, kl)]);   // e_from_h: divide by -w^2 eps_vv
         p.y[o] = y;
     }
 }
 
+
+// out_w = (M f)_w : two-point weighted mean of component w along its own axis w (create_Mcs, model.jl:287-306)
+__global__ void __launch_bounds__(128) interp_kernel(const __grid_constant__ ApplyParams p, int which_other) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    const int kl = blockIdx.z;
+    if (i >= p.Nx) return;
+    Gather g{p};
+#pragma unroll
+    for (int w = 0; w < 3; ++w) {
+        const int iw = g.cidx(w, i, j, kl);
+        const double2 *t0 = which_other ? p.c.mh0[w] : p.c.mi0[w], *t1 = which_other ? p.c.mh1[w] : p.c.mi1[w];
+        const int sh = which_other ? p.s1[w] : -p.s1[w];
+        double2 t = c_mul(t0[iw], g.E(w, i, j, kl));
+        t = c_fma(t1[iw], g.Esh(w, i, j, kl, w, sh), t);
+        p.y[(int64_t)kl * p.y_pstride + (int64_t)w * p.y_cs + ((int64_t)j * p.Nx + i) * p.y_es] = t;
+    }
+}
 
 // y += Mout[ masso .* (Min x) ] on a list of (tile, plane) output blocks: the off-diagonal part of the mass
 // operator, added after the diagonal-material kernel when off-diagonal entries are sparse (material interfaces).
@@ -208,6 +227,13 @@ cudaError_t launch_offdiag_correction(const ApplyParams &p, const int2 *list, in
     return cudaGetLastError();
 }
 
+cudaError_t launch_interp(const ApplyParams &p, int which_other, cudaStream_t s) {
+    dim3 block(128, 1, 1);
+    dim3 grid((p.Nx + 127) / 128, p.Ny, p.nzl);
+    interp_kernel<<<grid, block, 0, s>>>(p, which_other);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_curl1(const ApplyParams &p, const double2 *jm, double2 alpha, cudaStream_t s) {
     dim3 block(128, 1, 1);
     dim3 grid((p.Nx + 127) / 128, p.Ny, p.nzl);
@@ -219,10 +245,10 @@ cudaError_t launch_curl1(const ApplyParams &p, const double2 *jm, double2 alpha,
 
 namespace fdfd {
 cudaError_t launch_curl2(const ApplyParams &p, const double2 *je, double2 beta, double2 gamma, int has_h,
-                         cudaStream_t s) {
+                         cudaStream_t s, int divide_by_md) {
     dim3 block(128, 1, 1);
     dim3 grid((p.Nx + 127) / 128, p.Ny, p.nzl);
-    curl2_kernel<<<grid, block, 0, s>>>(p, je, beta, gamma, has_h);
+    curl2_kernel<<<grid, block, 0, s>>>(p, je, beta, gamma, has_h, divide_by_md);
     return cudaGetLastError();
 }
 }  // namespace fdfd

@@ -91,6 +91,8 @@ void build_coefs(const fdfd_desc &d, const std::vector<cplx> sdl_e[3], const std
             out.mi[w] = make_mean(!bE, &sdl_m[w], &sei, bl, phase[w], N);
             if (d.weighted_out_avg) out.mo[w] = make_mean(bE, &sdl_e[w], &smi, bl, phase[w], N);
             else                    out.mo[w] = make_mean(bE, nullptr, nullptr, bl, phase[w], N);
+            // create_Mcs (model.jl:299-303): Mc_e == the in-average above; Mc_m: isfwd = boundft.!=HH, (sdl_e, 1/sdl_m)
+            out.mh[w] = make_mean(bE, &sdl_e[w], &smi, bl, phase[w], N);
         } else {
             // A = Ce (Peps \ Cm) - w^2 Pmu (model.jl:238-240); Pmu: isfwd_in = boundft.!=HH, (sdl_e, 1/sdl_m) (:150,155)
             out.a[w] = make_diff(!bE, sei, bl, phase[w]);
@@ -98,6 +100,7 @@ void build_coefs(const fdfd_desc &d, const std::vector<cplx> sdl_e[3], const std
             out.mi[w] = make_mean(bE, &sdl_e[w], &smi, bl, phase[w], N);
             if (d.weighted_out_avg) out.mo[w] = make_mean(!bE, &sdl_m[w], &sei, bl, phase[w], N);
             else                    out.mo[w] = make_mean(!bE, nullptr, nullptr, bl, phase[w], N);
+            out.mh[w] = make_mean(!bE, &sdl_m[w], &sei, bl, phase[w], N);   // Mc_e for an FT_HH handle
         }
     }
 }
@@ -116,6 +119,7 @@ void transpose_coefs(const CoefHost &in, CoefHost &out) {
         for (auto &z : out.b[w].t1) z = -z;
         out.mi[w] = transpose_op(in.mo[w]);
         out.mo[w] = transpose_op(in.mi[w]);
+        out.mh[w] = in.mh[w];
     }
 }
 

@@ -30,6 +30,7 @@ struct CoefDev {
     const double2 *b0[3], *b1[3];    // second curl (shift -s1[w])
     const double2 *mi0[3], *mi1[3];  // input average of the mass operator  (shift -s1[w])
     const double2 *mo0[3], *mo1[3];  // output average of the mass operator (shift +s1[w])
+    const double2 *mh0[3], *mh1[3];  // corner interpolation of the OTHER field (create_Mcs), shift +s1[w]
 };
 
 // A z-plane of a DOF vector: element (c,i,j) = p[c*cs + (j*Nx+i)*es]
@@ -111,7 +112,8 @@ struct Ctx {
     int corr_count = 0;
     std::vector<int32_t> corr_off;     // host: first list entry of each plane
     cudaStream_t stream_comm = nullptr; // halo exchange overlapped with interior compute
-    cudaEvent_t ev_x = nullptr, ev_halo = nullptr;
+    cudaStream_t stream_bnd = nullptr;  // boundary planes (high priority), concurrent with the interior kernel
+    cudaEvent_t ev_x = nullptr, ev_halo = nullptr, ev_bnd = nullptr;
     double off_frac = 1.0;             // fraction of (tile, plane) blocks holding off-diagonal material
     int s1[3]{+1, +1, +1};
 
@@ -149,6 +151,7 @@ int set_err(Ctx *c, int code, const std::string &msg);
 // coeffs.cpp ---------------------------------------------------------------------------------------
 struct CoefHost {
     AxisOp a[3], b[3], mi[3], mo[3];  // first curl, second curl, in-average, out-average
+    AxisOp mh[3];                     // corner interpolation of the other field type (create_Mcs)
 };
 // Build the coefficient set of the forward operator from the reference-level inputs.
 void build_coefs(const fdfd_desc &d, const std::vector<cplx> sdl_e[3], const std::vector<cplx> sdl_m[3],
@@ -175,7 +178,9 @@ cudaError_t launch_offdiag_correction(const ApplyParams &p, const int2 *list, in
 cudaError_t launch_curl1(const ApplyParams &p, const double2 *jm, double2 alpha, cudaStream_t s);
 // second-curl only: y = beta * C2 (q .* h) + gamma * je   (create_b), naive kernel
 cudaError_t launch_curl2(const ApplyParams &p, const double2 *je, double2 beta, double2 gamma, int has_h,
-                         cudaStream_t s);
+                         cudaStream_t s, int divide_by_md = 0);
+// out_w = mean along w of component w (create_Mcs); which_other = 0: in-average tables (mi), 1: mh tables
+cudaError_t launch_interp(const ApplyParams &p, int which_other, cudaStream_t s);
 
 // krylov.cu ----------------------------------------------------------------------------------------
 int krylov_solve(Ctx *c, int method, const double2 *b, double2 *x, double rtol, int maxit, int check_every,

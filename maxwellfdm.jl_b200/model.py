@@ -158,5 +158,15 @@ def h_from_e(e, w, A, jm=None):
     return A.h_from_e(e, jm)
 
 
+def e_from_h(h, w, A, je=None):
+    """e_from_h (model.jl:281-284)"""
+    return A.e_from_h(h, je)
+
+
+def create_Mcs(A):
+    """create_Mcs (model.jl:287-306): returns two callables (Mc_e, Mc_m) interpolating E / H to the voxel corners."""
+    return (lambda e: A.interp_corners(e, "E")), (lambda h: A.interp_corners(h, "H"))
+
+
 def solve(A, b, **kw):
     return A.solve(b, **kw)

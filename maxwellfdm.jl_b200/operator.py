@@ -204,6 +204,22 @@ class FdfdOperator:
         L.check(L.lib().fdfd_h_from_e(self._h, _ptr(e), _ptr(jm), _ptr(h), _where(e)), self._h)
         return h
 
+    def e_from_h(self, h, je=None):
+        h = self._chk_vec(h, "h")
+        if je is not None:
+            je = self._chk_vec(je, "je")
+        e = self._out_like(h)
+        L.check(L.lib().fdfd_e_from_h(self._h, _ptr(h), _ptr(je), _ptr(e), _where(h)), self._h)
+        return e
+
+    def interp_corners(self, f, ft="E"):
+        """Mc_e * f (ft='E') or Mc_m * f (ft='H'): fields interpolated to the voxel corners (create_Mcs)."""
+        f = self._chk_vec(f, "f")
+        out = self._out_like(f)
+        which = L.FT_EE if (str(ft).upper().startswith("E") or ft == 0) else L.FT_HH
+        L.check(L.lib().fdfd_interp_corners(self._h, which, _ptr(f), _ptr(out), _where(f)), self._h)
+        return out
+
     def create_b(self, je, jm=None):
         je = self._chk_vec(je, "je")
         if jm is not None:

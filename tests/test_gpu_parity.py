@@ -282,6 +282,29 @@ def test_create_b_with_magnetic_current_and_h_from_e_with_mu():
     A.close()
 
 
+def test_e_from_h_and_corner_interpolation():
+    """N2 rows: e_from_h (model.jl:281-284) and the create_Mcs operators (model.jl:287-306) vs the oracle."""
+    for isbloch, boundft in (((True, False, True), (EE, EE, EE)), ((False, True, False), (EE, EE, EE)),
+                             ((True, True, False), (HH, EE, HH))):
+        p = Problem((9, 8, 7), isbloch, boundft, with_mu=True)
+        A_ref, (Pe, Pm, Ce, Cm) = p.oracle_csc()
+        A = p.operator(device=0)
+        h, je, e = p.random_x(21), p.random_x(22), p.random_x(23)
+        assert rel(A.e_from_h(h, je), op.e_from_h(h, p.omega, Pe, Cm, je)) < TOL
+        assert rel(A.e_from_h(h), op.e_from_h(h, p.omega, Pe, Cm, np.zeros_like(h))) < TOL
+        Mce, Mcm = op.create_Mcs(p.sdl_e, p.sdl_m, p.sei, p.smi, boundft, isbloch, p.ph)
+        assert rel(A.interp_corners(e, "E"), Mce.matvec(e)) < TOL
+        assert rel(A.interp_corners(h, "H"), Mcm.matvec(h)) < TOL
+        # round trip e -> h -> e with consistent sources: e_from_h(h_from_e(e)) solves the same Maxwell pair
+        A.close()
+    fb = _fb()
+    p = Problem((6, 5, 4), full_eps=True)
+    A = p.operator(device=0)
+    with pytest.raises(fb._lib.FdfdError):      # Peps must be diagonal for e_from_h (reference `Peps \`)
+        A.e_from_h(p.random_x())
+    A.close()
+
+
 def test_model_api_end_to_end():
     """reference-shaped host API: ModelFull -> add_srce -> create_linsys -> solve -> h_from_e."""
     fb = _fb()
