@@ -199,14 +199,13 @@ int ensure_ready(Ctx *c) {
     if (c->offmask) { cudaFree(c->offmask); c->offmask = nullptr; }
     if (c->corr_list) { cudaFree(c->corr_list); c->corr_list = nullptr; }
     c->corr_count = 0;
-    c->corr_off.clear();
     c->offmask_ty = 0;
     c->off_frac = c->mo[0] ? 1.0 : 0.0;
     if (c->mo[0] && c->d.kernel != FDFD_KERNEL_NAIVE) {
         ApplyParams p;
         fill_params(c, p, nullptr, nullptr, false);
         FDFD_CUDA(c, tiled_build_offmask(p, &c->offmask, &c->offmask_ty, &c->off_frac, &c->corr_list, &c->corr_count,
-                                         &c->corr_off, c->stream));
+                                         c->stream));
     }
     c->dirty = false;
     return FDFD_OK;
@@ -239,7 +238,6 @@ void fill_params(Ctx *c, ApplyParams &p, const double2 *x, double2 *y, bool tran
     p.y = y; p.y_pstride = p.x.pstride; p.y_cs = p.x.cs; p.y_es = p.x.es;
     p.offmask = c->offmask; p.offmask_ty = c->offmask_ty;
     p.corr_list = c->corr_list; p.corr_count = c->corr_count;
-    p.corr_off = c->corr_off.empty() ? nullptr : c->corr_off.data();
 }
 
 int apply_device(Ctx *c, const double2 *x, double2 *y, bool transpose) {

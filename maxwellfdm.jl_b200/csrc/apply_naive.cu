@@ -192,23 +192,69 @@ __global__ void __launch_bounds__(128) interp_kernel(const __grid_constant__ App
     }
 }
 
-// y += Mout[ masso .* (Min x) ] on a list of (tile, plane) output blocks: the off-diagonal part of the mass
-// operator, added after the diagonal-material kernel when off-diagonal entries are sparse (material interfaces).
-// Block = one (30 x 6)-cell output tile of one z-plane; gathers through L1/L2 like the general kernel.
-__global__ void __launch_bounds__(192) offdiag_correction_kernel(const __grid_constant__ ApplyParams p,
-                                                                  const int2 *__restrict__ list, int ntx) {
-    const int2 item = list[blockIdx.x];
-    const int tile = item.x, kl = item.y;
-    const int i = (tile % ntx) * 30 + (int)(threadIdx.x % 32), j = (tile / ntx) * 6 + (int)(threadIdx.x / 32);
-    if ((threadIdx.x % 32) >= 30 || i >= p.Nx || j >= p.Ny) return;
+// y += Mout[ masso .* (Min x) ]: the off-diagonal part of the mass operator, added after the diagonal-material
+// kernel when off-diagonal entries are sparse (material interfaces only).  Work item = (tile, [ks,ke)): a run of
+// consecutive z-planes of one 32x8 thread tile (outputs: inner 30x6) whose corner terms can be non-zero.  The CTA
+// marches the run: the corner quantity G(k+1) is computed once per plane (11 loads per thread) and reused as
+// G(k) in the next step; x/y neighbours of G travel through a double-buffered shared tile.  Default Yee
+// arrangement only (first curl forward: in-average looks back, out-average looks forward).
+__global__ void __launch_bounds__(256) offdiag_march_kernel(const __grid_constant__ ApplyParams p,
+                                                             const int4 *__restrict__ items, int ntx, int kl_begin,
+                                                             int kl_end) {
+    const int4 item = items[blockIdx.x];
+    const int ks = max(item.y, kl_begin), ke = min(item.z, kl_end);
+    if (ks >= ke) return;
+    __shared__ double2 gs[2][2][256];   // [plane parity][G_x, G_y][thread]
+    const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+    const int gi = (item.x % ntx) * 30 - 1 + tx, gj = (item.x / ntx) * 6 - 1 + ty;
+    const int ci = ((gi % p.Nx) + p.Nx) % p.Nx, cj = ((gj % p.Ny) + p.Ny) % p.Ny;
+    const int cim = ci == 0 ? p.Nx - 1 : ci - 1, cjm = cj == 0 ? p.Ny - 1 : cj - 1;
+    const bool out_ok = tx >= 1 && tx <= 30 && ty >= 1 && ty <= 6 && gi < p.Nx && gj < p.Ny;
     Gather g{p};
-#pragma unroll
-    for (int v = 0; v < 3; ++v) {
-        const int iv = g.cidx(v, i, j, kl);
-        double2 t = c_mul(p.c.mo0[v][iv], g.G(v, i, j, kl));
-        t = c_fma(p.c.mo1[v][iv], g.Gsh(v, i, j, kl, p.s1[v]), t);
-        double2 *yo = &p.y[(int64_t)kl * p.y_pstride + (int64_t)v * p.y_cs + ((int64_t)j * p.Nx + i) * p.y_es];
-        *yo = c_add(*yo, t);
+    const double2 mi0x = p.c.mi0[0][ci], mi1x = p.c.mi1[0][ci], mi0y = p.c.mi0[1][cj], mi1y = p.c.mi1[1][cj];
+    const int txp = min(tx + 1, 31), typ = min(ty + 1, 7);
+
+    // corner quantity G(kk) at this thread's cell; ezm = E_z of plane kk-1 at this cell (in), E_z(kk) (out)
+    auto corner = [&](int kk, double2 &ezm, double2 &Gx, double2 &Gy, double2 &Gz) {
+        const double2 ex = g.E(0, ci, cj, kk), ey = g.E(1, ci, cj, kk), ez = g.E(2, ci, cj, kk);
+        const int kg = g.kglob(kk);
+        const double2 Ax = c_fma(mi1x, g.E(0, cim, cj, kk), c_mul(mi0x, ex));
+        const double2 Ay = c_fma(mi1y, g.E(1, ci, cjm, kk), c_mul(mi0y, ey));
+        const double2 Az = c_fma(p.c.mi1[2][kg], ezm, c_mul(p.c.mi0[2][kg], ez));
+        const int64_t m = g.gidx(ci, cj, kk);
+        Gx = c_fma(p.mo[1][m], Az, c_mul(p.mo[0][m], Ay));
+        Gy = c_fma(p.mo[3][m], Az, c_mul(p.mo[2][m], Ax));
+        Gz = c_fma(p.mo[5][m], Ay, c_mul(p.mo[4][m], Ax));
+        ezm = ez;
+    };
+
+    double2 ezm = g.E(2, ci, cj, ks - 1);
+    double2 Gcx, Gcy, Gcz;
+    corner(ks, ezm, Gcx, Gcy, Gcz);
+    gs[ks & 1][0][tid] = Gcx;
+    gs[ks & 1][1][tid] = Gcy;
+    __syncthreads();
+    for (int k = ks; k < ke; ++k) {
+        // neighbours of G(k): written one step ago, visible since the last barrier; read BEFORE this step's barrier
+        const double2 Gx_xp = gs[k & 1][0][ty * 32 + txp], Gy_yp = gs[k & 1][1][typ * 32 + tx];
+        double2 Gnx, Gny, Gnz;
+        corner(k + 1, ezm, Gnx, Gny, Gnz);
+        gs[(k + 1) & 1][0][tid] = Gnx;
+        gs[(k + 1) & 1][1][tid] = Gny;
+        if (out_ok) {
+            const int kg = g.kglob(k);
+            double2 *yo = &p.y[(int64_t)k * p.y_pstride + ((int64_t)gj * p.Nx + gi) * p.y_es];
+            double2 t = c_fma(p.c.mo1[0][ci], Gx_xp, c_mul(p.c.mo0[0][ci], Gcx));
+            yo[0] = c_add(yo[0], t);
+            t = c_fma(p.c.mo1[1][cj], Gy_yp, c_mul(p.c.mo0[1][cj], Gcy));
+            yo[p.y_cs] = c_add(yo[p.y_cs], t);
+            t = c_fma(p.c.mo1[2][kg], Gnz, c_mul(p.c.mo0[2][kg], Gcz));
+            yo[2 * p.y_cs] = c_add(yo[2 * p.y_cs], t);
+        }
+        Gcx = Gnx;
+        Gcy = Gny;
+        Gcz = Gnz;
+        __syncthreads();
     }
 }
 
@@ -221,9 +267,10 @@ cudaError_t launch_apply_naive(const ApplyParams &p, cudaStream_t s) {
     return cudaGetLastError();
 }
 
-cudaError_t launch_offdiag_correction(const ApplyParams &p, const int2 *list, int count, int ntx, cudaStream_t s) {
+cudaError_t launch_offdiag_correction(const ApplyParams &p, const int4 *items, int count, int ntx, int kl_begin,
+                                      int kl_end, cudaStream_t s) {
     if (count <= 0) return cudaSuccess;
-    offdiag_correction_kernel<<<count, 192, 0, s>>>(p, list, ntx);
+    offdiag_march_kernel<<<count, 256, 0, s>>>(p, items, ntx, kl_begin, kl_end);
     return cudaGetLastError();
 }
 

@@ -16,6 +16,7 @@
 //   * boundary conditions are pure data (1-D coefficient tables, coeffs.cpp): no divergent branches;
 //   * each x element is read from HBM once (+ halo re-reads that hit L2), y written once, material read once.
 // Tile: thread tile TX x TY covers cells [ox, ox+TX) x [oy, oy+TY); outputs are the inner (TX-2) x (TY-2).
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -608,8 +609,8 @@ static cudaError_t build_mask_for(const ApplyParams &p, int TY, unsigned char **
 // Build the off-diagonal occupancy mask; *mask is cudaMalloc'ed ((nzl+2) * ntiles bytes), *ty_used the tile height
 // it is valid for (8: split launch, 16: single full-tensor launch), *frac the fraction of (tile, own plane) blocks
 // that hold off-diagonal material.
-cudaError_t tiled_build_offmask(const ApplyParams &p, unsigned char **mask, int *ty_used, double *frac, int2 **corr_list,
-                                int *corr_count, std::vector<int32_t> *corr_off, cudaStream_t s) {
+cudaError_t tiled_build_offmask(const ApplyParams &p, unsigned char **mask, int *ty_used, double *frac, int4 **corr_list,
+                                int *corr_count, cudaStream_t s) {
     *mask = nullptr;
     *ty_used = 0;
     *frac = 1.0;
@@ -628,21 +629,32 @@ cudaError_t tiled_build_offmask(const ApplyParams &p, unsigned char **mask, int 
     }
     *ty_used = TY;
     if (TY == 8) {
-        // output blocks (tile, plane k) whose corner terms G(k) / G(k+1) can be non-zero
+        // work items of the correction pass: per tile, runs [ks,ke) of consecutive output planes whose corner terms
+        // G(k) / G(k+1) can be non-zero.  A run of L planes costs L+1 corner evaluations but is a serial march, so
+        // the cut length adapts to the amount of flagged work: enough CTAs for several waves first, longer runs
+        // (less redundancy) only when there is plenty of work.
         const int ntx = (p.Nx + 29) / 30, nty = (p.Ny + 5) / 6;
         const size_t nt = (size_t)ntx * nty;
-        std::vector<int2> list;
-        corr_off->assign((size_t)p.nzl + 1, 0);
-        for (int k = 0; k < p.nzl; ++k) {
-            (*corr_off)[k] = (int32_t)list.size();
-            for (size_t t = 0; t < nt; ++t)
-                if (h[(size_t)(k + 1) * nt + t] | h[(size_t)(k + 2) * nt + t]) list.push_back(make_int2((int)t, k));
+        auto flagged = [&](size_t t, int k) { return (h[(size_t)(k + 1) * nt + t] | h[(size_t)(k + 2) * nt + t]) != 0; };
+        size_t nblocks = 0;
+        for (size_t t = 0; t < nt; ++t)
+            for (int k = 0; k < p.nzl; ++k) nblocks += flagged(t, k);
+        const int maxrun = (int)std::max<size_t>(1, std::min<size_t>(16, nblocks / 1200));
+        std::vector<int4> list;
+        for (size_t t = 0; t < nt; ++t) {
+            int k = 0;
+            while (k < p.nzl) {
+                if (!flagged(t, k)) { ++k; continue; }
+                int ke = k;
+                while (ke < p.nzl && ke - k < maxrun && flagged(t, ke)) ++ke;
+                list.push_back(make_int4((int)t, k, ke, 0));
+                k = ke;
+            }
         }
-        (*corr_off)[p.nzl] = (int32_t)list.size();
         *corr_count = (int)list.size();
         if (!list.empty()) {
-            if ((e = cudaMalloc((void **)corr_list, list.size() * sizeof(int2))) != cudaSuccess) return e;
-            if ((e = cudaMemcpyAsync(*corr_list, list.data(), list.size() * sizeof(int2), cudaMemcpyHostToDevice, s)) !=
+            if ((e = cudaMalloc((void **)corr_list, list.size() * sizeof(int4))) != cudaSuccess) return e;
+            if ((e = cudaMemcpyAsync(*corr_list, list.data(), list.size() * sizeof(int4), cudaMemcpyHostToDevice, s)) !=
                 cudaSuccess)
                 return e;
             if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
@@ -659,13 +671,13 @@ cudaError_t launch_apply_tiled(const ApplyParams &p, int kl_begin, int kl_end, c
     if (!full) {
         e = (env_ty() == 16) ? launch_tile<32, 16>(p, kl_begin, kl_end, s) : launch_tile<32, 8>(p, kl_begin, kl_end, s);
         if (nlaunch) *nlaunch += 1;
-    } else if (p.offmask && p.offmask_ty == 8 && p.corr_off) {
+    } else if (p.offmask && p.offmask_ty == 8) {
         // sparse off-diagonals (material interfaces only): diagonal kernel everywhere, then the off-diagonal part
-        // of the mass operator is added on the few flagged (tile, plane) blocks of this plane range (linearity)
+        // of the mass operator is added on the flagged runs of this plane range (the operator is linear)
         e = launch_tile<32, 8>(p, kl_begin, kl_end, s, 3);
-        const int first = p.corr_off[kl_begin], cnt = p.corr_off[kl_end] - first;
-        if (e == cudaSuccess) e = launch_offdiag_correction(p, p.corr_list + first, cnt, (p.Nx + 29) / 30, s);
-        if (nlaunch) *nlaunch += cnt > 0 ? 2 : 1;
+        if (e == cudaSuccess)
+            e = launch_offdiag_correction(p, p.corr_list, p.corr_count, (p.Nx + 29) / 30, kl_begin, kl_end, s);
+        if (nlaunch) *nlaunch += p.corr_count > 0 ? 2 : 1;
     } else {
         e = launch_tile<32, 16>(p, kl_begin, kl_end, s);
         if (nlaunch) *nlaunch += 1;

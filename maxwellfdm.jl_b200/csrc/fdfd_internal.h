@@ -61,9 +61,8 @@ struct ApplyParams {
     PlaneSet x;
     const unsigned char *offmask;  // occupancy mask of the off-diagonal material (tiled kernel), or null
     int32_t offmask_ty;            // tile height the mask was built for
-    const int2 *corr_list;         // sparse off-diagonals: (tile, plane) output blocks needing the correction pass
+    const int4 *corr_list;         // sparse off-diagonals: work items (tile, ks, ke) of the correction pass
     int32_t corr_count;
-    const int32_t *corr_off;       // HOST array [nzl+1]: first list entry of each plane (list is sorted by plane)
     double2 *y;             // output slab, same layout as x.base
     int64_t y_pstride, y_cs;
     int32_t y_es;
@@ -108,9 +107,8 @@ struct Ctx {
     const double2 *md[3]{}, *mo[6]{}, *mo_t[6]{}, *q[3]{};
     unsigned char *offmask = nullptr;  // device, (nzl+2) x ntiles
     int offmask_ty = 0;
-    int2 *corr_list = nullptr;         // device list of (tile, plane) output blocks for the correction pass
+    int4 *corr_list = nullptr;         // device list of (tile, ks, ke) runs for the correction pass
     int corr_count = 0;
-    std::vector<int32_t> corr_off;     // host: first list entry of each plane
     cudaStream_t stream_comm = nullptr; // halo exchange overlapped with interior compute
     cudaStream_t stream_bnd = nullptr;  // boundary planes (high priority), concurrent with the interior kernel
     cudaEvent_t ev_x = nullptr, ev_halo = nullptr, ev_bnd = nullptr;
@@ -171,9 +169,10 @@ cudaError_t launch_apply_naive(const ApplyParams &p, cudaStream_t s);
 // returns cudaErrorNotSupported when the tiled kernel does not cover this configuration
 cudaError_t launch_apply_tiled(const ApplyParams &p, int kl_begin, int kl_end, cudaStream_t s, int *nlaunch);
 bool tiled_supported(const ApplyParams &p);
-cudaError_t tiled_build_offmask(const ApplyParams &p, unsigned char **mask, int *ty_used, double *frac, int2 **corr_list,
-                                int *corr_count, std::vector<int32_t> *corr_off, cudaStream_t s);
-cudaError_t launch_offdiag_correction(const ApplyParams &p, const int2 *list, int count, int ntx, cudaStream_t s);
+cudaError_t tiled_build_offmask(const ApplyParams &p, unsigned char **mask, int *ty_used, double *frac, int4 **corr_list,
+                                int *corr_count, cudaStream_t s);
+cudaError_t launch_offdiag_correction(const ApplyParams &p, const int4 *items, int count, int ntx, int kl_begin,
+                                      int kl_end, cudaStream_t s);
 // first-curl only: h = scale * q .* (C1 e + jm)   (h_from_e), naive kernel
 cudaError_t launch_curl1(const ApplyParams &p, const double2 *jm, double2 alpha, cudaStream_t s);
 // second-curl only: y = beta * C2 (q .* h) + gamma * je   (create_b), naive kernel

@@ -9,6 +9,7 @@
 // several z-slabs the local sums are combined by ncclAllReduce on the same stream.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 
 #include "krylov_common.cuh"
 
@@ -168,34 +169,69 @@ static int bicgstab(Ctx *c, const double2 *b, double2 *x, double rtol, int maxit
         }
         converged = rel <= rtol;
     }
-    while (!converged && it < maxit) {
-        const int par = it & 1;
+    // one iteration = a pure stream of launches (no host round trip), so it can be captured into a CUDA graph
+    auto enqueue_iter = [&](int i) -> int {
+        const int par = i & 1;
         const int rho_old = par ? S_RHO1 : S_RHO0, rho_new = par ? S_RHO0 : S_RHO1;
-        const int rr_new = rho_new + 1;
-        KCHK(apply_device(c, p, v, false));
+        int r1 = apply_device(c, p, v, false);
+        if (r1 != FDFD_OK) return r1;
         k_dot1<<<g, RB, 0, st>>>(n, rhat, v, rd, S_SIGMA);
-        LCHK();
-        KCHK(allreduce_sum(c, sc + 2 * S_SIGMA, 2, st));
+        if ((r1 = allreduce_sum(c, sc + 2 * S_SIGMA, 2, st)) != FDFD_OK) return r1;
         k_s<<<g, RB, 0, st>>>(n, r, v, s, rd, rho_old);
-        LCHK();
-        KCHK(apply_device(c, s, t, false));
+        if ((r1 = apply_device(c, s, t, false)) != FDFD_OK) return r1;
         k_dot2<<<g, RB, 0, st>>>(n, t, s, rd);
-        LCHK();
-        KCHK(allreduce_sum(c, sc + 2 * S_TS, 4, st));
+        if ((r1 = allreduce_sum(c, sc + 2 * S_TS, 4, st)) != FDFD_OK) return r1;
         k_xr<<<g, RB, 0, st>>>(n, x, p, s, t, rhat, r, rd, rho_new);
-        LCHK();
-        KCHK(allreduce_sum(c, sc + 2 * rho_new, 4, st));
+        if ((r1 = allreduce_sum(c, sc + 2 * rho_new, 4, st)) != FDFD_OK) return r1;
         k_p<<<g, RB, 0, st>>>(n, r, v, p, rd, rho_old, rho_new);
-        LCHK();
+        cudaError_t e1 = cudaGetLastError();
+        if (e1 != cudaSuccess) return set_err(c, FDFD_ECUDA, cudaGetErrorString(e1));
         c->launches += 5;
-        ++it;
+        return FDFD_OK;
+    };
+    // Small grids are launch-bound (40^3: ~50 us of launches per iteration): replay two iterations (both scalar
+    // parities) from a CUDA graph.  Single slab only (no NCCL in the graph), no per-iteration history.
+    cudaGraphExec_t gexec = nullptr;
+    int64_t graph_launches = 0;
+    if (c->d.nranks == 1 && n <= 6000000 && !hist_dev && maxit >= 4 && !getenv("FDFD_NO_GRAPH")) {
+        cudaGraph_t graph = nullptr;
+        const int64_t l0 = c->launches;
+        if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            int rc1 = enqueue_iter(0);
+            if (rc1 == FDFD_OK) rc1 = enqueue_iter(1);
+            cudaError_t ec = cudaStreamEndCapture(st, &graph);
+            if (rc1 == FDFD_OK && ec == cudaSuccess && graph) {
+                if (cudaGraphInstantiate(&gexec, graph, 0) != cudaSuccess) gexec = nullptr;
+            }
+            if (graph) cudaGraphDestroy(graph);
+            (void)cudaGetLastError();
+        }
+        graph_launches = c->launches - l0;
+        c->launches = l0;
+    }
+    auto cleanup2 = [&]() { if (gexec) cudaGraphExecDestroy(gexec); };
+    while (!converged && it < maxit) {
+        const int to_check = check_every - (it % check_every);   // iterations until the next residual read-back
+        if (gexec && (it & 1) == 0 && it + 2 <= maxit && (fixed_iters || to_check >= 2)) {
+            cudaError_t eg = cudaGraphLaunch(gexec, st);
+            if (eg != cudaSuccess) { cleanup2(); cleanup(); return set_err(c, FDFD_ECUDA, cudaGetErrorString(eg)); }
+            c->launches += graph_launches;
+            it += 2;
+        } else {
+            int ri = enqueue_iter(it);
+            if (ri != FDFD_OK) { cleanup2(); cleanup(); return ri; }
+            ++it;
+        }
+        const int rr_new = ((it & 1) ? S_RHO1 : S_RHO0) + 1;   // RR slot written by the last finished iteration
         if (hist_dev) { k_store_hist<<<1, 1, 0, st>>>(hist_dev, it, rd.scal, rr_new); c->launches += 1; }
-        if (!fixed_iters && (it % check_every == 0 || it == maxit)) {
-            KCHK(read_relres(rr_new, rel));
+        if (!fixed_iters && (it % check_every == 0 || it >= maxit)) {
+            int rq = read_relres(rr_new, rel);
+            if (rq != FDFD_OK) { cleanup2(); cleanup(); return rq; }
             if (!(rel == rel)) break;  // NaN: breakdown
             converged = rel <= rtol;
         }
     }
+    cleanup2();
     if (fixed_iters) {
         const int rr_last = (it & 1) ? S_RR1 : S_RR0;
         KCHK(read_relres(rr_last, rel));

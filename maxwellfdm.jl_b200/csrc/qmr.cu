@@ -8,6 +8,7 @@
 // Scalars are double-buffered by iteration parity so that a kernel never reads a slot another block of
 // the same launch is writing.
 #include <cmath>
+#include <cstdlib>
 
 #include "krylov_common.cuh"
 
@@ -189,30 +190,64 @@ int qmr(Ctx *c, const double2 *b, double2 *x, double rtol, int maxit, int check_
         }
         converged = rel <= rtol;
     }
-    while (!converged && it < maxit) {
-        const int par = it & 1;
+    auto enqueue_iter = [&](int i) -> int {
+        const int par = i & 1;
+        int r1;
         q_pq<<<g, kry::RB, 0, st>>>(n, vt, wt, p, q, rd, par);
-        LCHK();
-        KCHK(apply_device(c, p, pt, false));
-        KCHK(apply_device(c, q, qt, true));
+        if ((r1 = apply_device(c, p, pt, false)) != FDFD_OK) return r1;
+        if ((r1 = apply_device(c, q, qt, true)) != FDFD_OK) return r1;
         q_eps<<<g, kry::RB, 0, st>>>(n, q, pt, rd, par);
-        LCHK();
-        KCHK(allreduce_sum(c, sc + 2 * (QB(par ^ 1) + Q_EPS), 2, st));
+        if ((r1 = allreduce_sum(c, sc + 2 * (QB(par ^ 1) + Q_EPS), 2, st)) != FDFD_OK) return r1;
         q_vw<<<g, kry::RB, 0, st>>>(n, pt, qt, vt, wt, rd, par);
-        LCHK();
-        KCHK(allreduce_sum(c, sc + 2 * (QB(par ^ 1) + Q_RHO2), 6, st));
+        if ((r1 = allreduce_sum(c, sc + 2 * (QB(par ^ 1) + Q_RHO2), 6, st)) != FDFD_OK) return r1;
         q_xr<<<g, kry::RB, 0, st>>>(n, p, pt, d, s, x, r, rd, par);
-        LCHK();
-        KCHK(allreduce_sum(c, sc + 2 * Q_RR, 2, st));
+        if ((r1 = allreduce_sum(c, sc + 2 * Q_RR, 2, st)) != FDFD_OK) return r1;
+        cudaError_t e1 = cudaGetLastError();
+        if (e1 != cudaSuccess) return set_err(c, FDFD_ECUDA, cudaGetErrorString(e1));
         c->launches += 4;
-        ++it;
+        return FDFD_OK;
+    };
+    // small grids: replay two iterations (both scalar parities) from a CUDA graph (see krylov.cu)
+    cudaGraphExec_t gexec = nullptr;
+    int64_t graph_launches = 0;
+    if (c->d.nranks == 1 && n <= 6000000 && !hist_dev && maxit >= 4 && !getenv("FDFD_NO_GRAPH")) {
+        cudaGraph_t graph = nullptr;
+        const int64_t l0 = c->launches;
+        if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            int rc1 = enqueue_iter(0);
+            if (rc1 == FDFD_OK) rc1 = enqueue_iter(1);
+            cudaError_t ec = cudaStreamEndCapture(st, &graph);
+            if (rc1 == FDFD_OK && ec == cudaSuccess && graph) {
+                if (cudaGraphInstantiate(&gexec, graph, 0) != cudaSuccess) gexec = nullptr;
+            }
+            if (graph) cudaGraphDestroy(graph);
+            (void)cudaGetLastError();
+        }
+        graph_launches = c->launches - l0;
+        c->launches = l0;
+    }
+    auto cleanup2 = [&]() { if (gexec) cudaGraphExecDestroy(gexec); };
+    while (!converged && it < maxit) {
+        const int to_check = check_every - (it % check_every);
+        if (gexec && (it & 1) == 0 && it + 2 <= maxit && (fixed_iters || to_check >= 2)) {
+            cudaError_t eg = cudaGraphLaunch(gexec, st);
+            if (eg != cudaSuccess) { cleanup2(); cleanup(); return set_err(c, FDFD_ECUDA, cudaGetErrorString(eg)); }
+            c->launches += graph_launches;
+            it += 2;
+        } else {
+            int ri = enqueue_iter(it);
+            if (ri != FDFD_OK) { cleanup2(); cleanup(); return ri; }
+            ++it;
+        }
         if (hist_dev) { q_store_hist<<<1, 1, 0, st>>>(hist_dev, it, rd.scal); c->launches += 1; }
-        if (!fixed_iters && (it % check_every == 0 || it == maxit)) {
-            KCHK(read_relres(rel));
+        if (!fixed_iters && (it % check_every == 0 || it >= maxit)) {
+            int rq = read_relres(rel);
+            if (rq != FDFD_OK) { cleanup2(); cleanup(); return rq; }
             if (!(rel == rel)) break;
             converged = rel <= rtol;
         }
     }
+    cleanup2();
     if (fixed_iters) KCHK(read_relres(rel));
     if (hist) {
         FDFD_CUDA(c, cudaMemcpyAsync(hist, hist_dev, sizeof(double) * (size_t)(it + 1), cudaMemcpyDeviceToHost, st));
