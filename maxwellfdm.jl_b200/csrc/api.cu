@@ -2,6 +2,7 @@
 // point stands in for).  Host-side state handling, device array construction, launches.
 #include <cstdio>
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -250,13 +251,39 @@ int apply_device(Ctx *c, const double2 *x, double2 *y, bool transpose) {
     if (c->d.kernel == FDFD_KERNEL_TILED && !can_tile)
         return set_err(c, FDFD_EINVAL, "tiled kernel requires the first curl to be forward on every axis");
     const bool use_tiled = c->d.kernel != FDFD_KERNEL_NAIVE && can_tile;
-    if (c->d.nranks > 1 && use_tiled && p.nzl >= 4) {
+    // timing experiments only (results are wrong with FDFD_DEBUG_SKIP_HALO): where does the multi-slab overhead go?
+    static const bool dbg_skip_halo = getenv("FDFD_DEBUG_SKIP_HALO") != nullptr;
+    // The interior/boundary split (exchange overlapped with the interior planes) costs more than it hides on
+    // NVLink (measured: +21 us for the split vs 25 us for the exchange), so it is opt-in; the default is exchange,
+    // then one launch - and inside the Krylov loops the exchange is started early by the kernel that produces the
+    // vector (halo_prefetch), so the apply only waits on an event.
+    static const bool split_overlap = getenv("FDFD_SPLIT_OVERLAP") != nullptr;
+    if (c->d.nranks > 1 && c->halo_for == x && x != nullptr) {
+        c->halo_for = nullptr;
+        c->comm_pending = false;
+        FDFD_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_halo, 0));
+        if (use_tiled) {
+            int nl = 0;
+            FDFD_CUDA(c, launch_apply_tiled(p, 0, p.nzl, c->stream, &nl));
+            c->launches += nl;
+        } else {
+            FDFD_CUDA(c, launch_apply_naive(p, c->stream));
+            c->launches += 1;
+        }
+        return FDFD_OK;
+    }
+    c->halo_for = nullptr;
+    if (c->comm_pending) {   // NCCL operations on one communicator must not overlap: order after the prefetch
+        FDFD_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_halo, 0));
+        c->comm_pending = false;
+    }
+    if (c->d.nranks > 1 && use_tiled && p.nzl >= 4 && split_overlap) {
         // z-slabs: the halo exchange (NCCL, own stream) overlaps the interior planes, which only need this rank's
         // own planes; the two boundary planes run on a high-priority stream as soon as the halos have landed,
         // concurrently with the interior kernel (SURVEY.md 8e "Overlap").
         FDFD_CUDA(c, cudaEventRecord(c->ev_x, c->stream));
         FDFD_CUDA(c, cudaStreamWaitEvent(c->stream_comm, c->ev_x, 0));
-        if ((r = halo_exchange(c, x, c->halo_lo, c->halo_hi, c->stream_comm)) != FDFD_OK) return r;
+        if (!dbg_skip_halo && (r = halo_exchange(c, x, c->halo_lo, c->halo_hi, c->stream_comm)) != FDFD_OK) return r;
         FDFD_CUDA(c, cudaEventRecord(c->ev_halo, c->stream_comm));
         int nl = 0;
         FDFD_CUDA(c, cudaStreamWaitEvent(c->stream_bnd, c->ev_halo, 0));
@@ -268,7 +295,7 @@ int apply_device(Ctx *c, const double2 *x, double2 *y, bool transpose) {
         c->launches += nl;
         return FDFD_OK;
     }
-    if (c->d.nranks > 1) {
+    if (c->d.nranks > 1 && !dbg_skip_halo) {
         r = halo_exchange(c, x, c->halo_lo, c->halo_hi, c->stream);
         if (r != FDFD_OK) return r;
     }
@@ -280,6 +307,23 @@ int apply_device(Ctx *c, const double2 *x, double2 *y, bool transpose) {
         FDFD_CUDA(c, launch_apply_naive(p, c->stream));
         c->launches += 1;
     }
+    return FDFD_OK;
+}
+
+bool halo_prefetch_usable(const Ctx *c) {
+    return c->d.nranks > 1 && c->d.order_cmpfirst && (c->k1 - c->k0) >= 3 && c->comm != nullptr &&
+           getenv("FDFD_NO_HALO_PREFETCH") == nullptr;
+}
+
+int halo_prefetch(Ctx *c, const double2 *v) {
+    if (!halo_prefetch_usable(c)) return FDFD_OK;
+    FDFD_CUDA(c, cudaEventRecord(c->ev_x, c->stream));
+    FDFD_CUDA(c, cudaStreamWaitEvent(c->stream_comm, c->ev_x, 0));
+    int r = halo_exchange(c, v, c->halo_lo, c->halo_hi, c->stream_comm);
+    if (r != FDFD_OK) return r;
+    FDFD_CUDA(c, cudaEventRecord(c->ev_halo, c->stream_comm));
+    c->halo_for = v;
+    c->comm_pending = true;
     return FDFD_OK;
 }
 

@@ -159,6 +159,10 @@ int halo_exchange_ghosted(Ctx *c, double2 *arr, cudaStream_t s) {
 
 int allreduce_sum(Ctx *c, double *dev, int count, cudaStream_t s) {
     if (c->d.nranks == 1) return FDFD_OK;
+    if (c->comm_pending) {   // keep NCCL operations on this communicator totally ordered
+        FDFD_CUDA(c, cudaStreamWaitEvent(s, c->ev_halo, 0));
+        c->comm_pending = false;
+    }
     if (!c->comm) return set_err(c, FDFD_ESTATE, "nranks > 1 but fdfd_comm_init was not called");
     FDFD_NCCL(c, c->nccl->AllReduce(dev, dev, (size_t)count, ncclFloat64, ncclSum, (ncclComm_t)c->comm, s));
     return FDFD_OK;

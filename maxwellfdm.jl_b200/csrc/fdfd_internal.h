@@ -112,6 +112,8 @@ struct Ctx {
     cudaStream_t stream_comm = nullptr; // halo exchange overlapped with interior compute
     cudaStream_t stream_bnd = nullptr;  // boundary planes (high priority), concurrent with the interior kernel
     cudaEvent_t ev_x = nullptr, ev_halo = nullptr, ev_bnd = nullptr;
+    const double2 *halo_for = nullptr;  // vector whose halo planes are (being) exchanged ahead of its apply
+    bool comm_pending = false;          // an NCCL op may still be running on stream_comm (ordered by ev_halo)
     double off_frac = 1.0;             // fraction of (tile, plane) blocks holding off-diagonal material
     int s1[3]{+1, +1, +1};
 
@@ -198,6 +200,10 @@ int allreduce_sum(Ctx *c, double *dev, int count, cudaStream_t s);
 // api.cu -------------------------------------------------------------------------------------------
 int ensure_ready(Ctx *c);
 int apply_device(Ctx *c, const double2 *x, double2 *y, bool transpose);
+// Start the halo exchange of slab vector v on the comm stream (v's boundary planes must already be enqueued on the
+// main stream); the next apply_device(v) then only waits for it.  No-op unless nranks > 1 and cmp-first layout.
+int halo_prefetch(Ctx *c, const double2 *v);
+bool halo_prefetch_usable(const Ctx *c);
 void fill_params(Ctx *c, ApplyParams &p, const double2 *x, double2 *y, bool transpose);
 
 }  // namespace fdfd

@@ -169,6 +169,11 @@ static int bicgstab(Ctx *c, const double2 *b, double2 *x, double rtol, int maxit
         }
         converged = rel <= rtol;
     }
+    // z-slabs: the kernels that produce s and p handle the two boundary planes first so that the NCCL halo exchange
+    // of the next apply runs behind their interior part (halo_prefetch)
+    const bool pre = halo_prefetch_usable(c);
+    const int64_t pl = c->plane;
+    const int gb = kry::grid_for(pl);
     // one iteration = a pure stream of launches (no host round trip), so it can be captured into a CUDA graph
     auto enqueue_iter = [&](int i) -> int {
         const int par = i & 1;
@@ -177,13 +182,29 @@ static int bicgstab(Ctx *c, const double2 *b, double2 *x, double rtol, int maxit
         if (r1 != FDFD_OK) return r1;
         k_dot1<<<g, RB, 0, st>>>(n, rhat, v, rd, S_SIGMA);
         if ((r1 = allreduce_sum(c, sc + 2 * S_SIGMA, 2, st)) != FDFD_OK) return r1;
-        k_s<<<g, RB, 0, st>>>(n, r, v, s, rd, rho_old);
+        if (pre) {   // boundary planes first, start their halo exchange, then the interior behind which it hides
+            k_s<<<gb, RB, 0, st>>>(pl, r, v, s, rd, rho_old);
+            k_s<<<gb, RB, 0, st>>>(pl, r + n - pl, v + n - pl, s + n - pl, rd, rho_old);
+            if ((r1 = halo_prefetch(c, s)) != FDFD_OK) return r1;
+            k_s<<<g, RB, 0, st>>>(n - 2 * pl, r + pl, v + pl, s + pl, rd, rho_old);
+            c->launches += 2;
+        } else {
+            k_s<<<g, RB, 0, st>>>(n, r, v, s, rd, rho_old);
+        }
         if ((r1 = apply_device(c, s, t, false)) != FDFD_OK) return r1;
         k_dot2<<<g, RB, 0, st>>>(n, t, s, rd);
         if ((r1 = allreduce_sum(c, sc + 2 * S_TS, 4, st)) != FDFD_OK) return r1;
         k_xr<<<g, RB, 0, st>>>(n, x, p, s, t, rhat, r, rd, rho_new);
         if ((r1 = allreduce_sum(c, sc + 2 * rho_new, 4, st)) != FDFD_OK) return r1;
-        k_p<<<g, RB, 0, st>>>(n, r, v, p, rd, rho_old, rho_new);
+        if (pre) {
+            k_p<<<gb, RB, 0, st>>>(pl, r, v, p, rd, rho_old, rho_new);
+            k_p<<<gb, RB, 0, st>>>(pl, r + n - pl, v + n - pl, p + n - pl, rd, rho_old, rho_new);
+            if ((r1 = halo_prefetch(c, p)) != FDFD_OK) return r1;
+            k_p<<<g, RB, 0, st>>>(n - 2 * pl, r + pl, v + pl, p + pl, rd, rho_old, rho_new);
+            c->launches += 2;
+        } else {
+            k_p<<<g, RB, 0, st>>>(n, r, v, p, rd, rho_old, rho_new);
+        }
         cudaError_t e1 = cudaGetLastError();
         if (e1 != cudaSuccess) return set_err(c, FDFD_ECUDA, cudaGetErrorString(e1));
         c->launches += 5;
