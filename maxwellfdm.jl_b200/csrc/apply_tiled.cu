@@ -38,7 +38,6 @@ struct TiledParams {
     int32_t lz;               // planes per chunk
     int32_t kl_begin, kl_end; // local plane range of this launch
     const unsigned char *offmask;  // [ghosted plane][tile]: 1 if any off-diagonal material entry is non-zero there
-    int32_t filter;           // 0: all work items; 1: only items WITHOUT off-diagonal material; 2: only items WITH
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -129,15 +128,6 @@ __global__ void __launch_bounds__(TX *TY, (TX * TY <= 256 ? 2 : 1)) apply_tiled_
     const int kc0 = tp.kl_begin + chunk * tp.lz;
     const int kc1 = min(kc0 + tp.lz, tp.kl_end);
     const int nplanes = kc1 - kc0 + 2;  // planes kc0-1 .. kc1
-    if (tp.filter != 0) {
-        // split launch: this (tile, z-chunk) work item belongs to exactly one of the two kernels, decided by
-        // whether any plane whose corner terms it needs (kc0 .. kc1) holds off-diagonal material
-        int f = 0;
-        for (int kk = kc0 + (int)threadIdx.x; kk <= kc1; kk += TX * TY)
-            f |= __ldg(&tp.offmask[(int64_t)(kk + 1) * (tp.ntx * tp.nty) + tile_y * tp.ntx + tile_x]);
-        const int any = __syncthreads_or(f);
-        if ((tp.filter == 1 && any) || (tp.filter == 2 && !any)) return;
-    }
 
     const int Nx = p.Nx, Ny = p.Ny;
     const int gi = ox + tx, gj = oy + ty;
@@ -542,7 +532,7 @@ static int pick_lz(int ncols, int nplanes, int cta_per_sm, int LZMAX) {
 }
 
 template <int TX, int TY>
-static cudaError_t launch_tile(const ApplyParams &p, int kl_begin, int kl_end, cudaStream_t s, int filter = 0) {
+static cudaError_t launch_tile(const ApplyParams &p, int kl_begin, int kl_end, cudaStream_t s, bool diag_only = false) {
     TiledParams tp;
     tp.a = p;
     tp.wrapx = p.wrap[0];
@@ -559,8 +549,7 @@ static cudaError_t launch_tile(const ApplyParams &p, int kl_begin, int kl_end, c
     tp.kl_begin = kl_begin;
     tp.kl_end = kl_end;
     tp.offmask = (p.offmask && p.offmask_ty == TY) ? p.offmask : nullptr;
-    tp.filter = (tp.offmask && filter != 3) ? filter : 0;
-    const bool cf = tp.a.cmpfirst != 0, off = p.has_off != 0 && p.has_mass != 0 && filter != 1 && filter != 3, q = p.has_q != 0;
+    const bool cf = tp.a.cmpfirst != 0, off = p.has_off != 0 && p.has_mass != 0 && !diag_only, q = p.has_q != 0;
     cudaError_t e;
 #define V(CF, OFF, Q) e = launch_variant<CF, OFF, Q, TX, TY>(tp, s)
     if (cf) {
@@ -674,7 +663,7 @@ cudaError_t launch_apply_tiled(const ApplyParams &p, int kl_begin, int kl_end, c
     } else if (p.offmask && p.offmask_ty == 8) {
         // sparse off-diagonals (material interfaces only): diagonal kernel everywhere, then the off-diagonal part
         // of the mass operator is added on the flagged runs of this plane range (the operator is linear)
-        e = launch_tile<32, 8>(p, kl_begin, kl_end, s, 3);
+        e = launch_tile<32, 8>(p, kl_begin, kl_end, s, true);
         if (e == cudaSuccess)
             e = launch_offdiag_correction(p, p.corr_list, p.corr_count, (p.Nx + 29) / 30, kl_begin, kl_end, s);
         if (nlaunch) *nlaunch += p.corr_count > 0 ? 2 : 1;

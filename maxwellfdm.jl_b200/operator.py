@@ -103,10 +103,17 @@ class FdfdOperator:
         return np.ascontiguousarray(p.transpose(4, 3, 2, 1, 0))
 
     def set_eps(self, eps, has_offdiag=None):
+        """eps indexed [i,j,k,v,u] (shape (Nx,Ny,nzl,3,3)), or - to avoid a transposing copy of a large array - a
+        C-contiguous complex128 array of shape (3,3,nzl,Ny,Nx) indexed [u,v,k,j,i], which IS the memory of the Julia
+        column-major (Nx,Ny,nzl,3,3) array."""
         eps = np.asarray(eps)
-        if eps.shape != (self.N[0], self.N[1], self.nzl, 3, 3):
+        if eps.shape == (3, 3, self.nzl, self.N[1], self.N[0]) and eps.dtype == np.complex128 and eps.flags.c_contiguous \
+                and (self.nzl, self.N[1], self.N[0]) != (3, 3, 3):
+            buf = eps
+        elif eps.shape != (self.N[0], self.N[1], self.nzl, 3, 3):
             raise ValueError(f"eps must have shape (Nx,Ny,nzl,3,3) = {(self.N[0], self.N[1], self.nzl, 3, 3)}")
-        buf = self._julia_layout(eps)
+        else:
+            buf = self._julia_layout(eps)
         if has_offdiag is None:
             has_offdiag = True  # the library scans and drops the flag if every off-diagonal entry is 0
         L.check(L.lib().fdfd_set_eps(self._h, buf.ctypes.data, 1 if has_offdiag else 0), self._h)

@@ -69,3 +69,8 @@ if __name__ == "__main__":
     print(json.dumps(measure("C2 Si waveguide 200^3, full eps (sparse off-diagonals)", workloads.c2_waveguide())))
     print(json.dumps(measure("C3 PhC slab 256x256x128, Bloch x/y, PML z", workloads.c3_phc_slab())))
     print(json.dumps(c1_solve()))
+    if "--c4" in sys.argv:
+        t0 = time.perf_counter()
+        w4 = workloads.c4_scatterer()
+        sys.stderr.write(f"C4 eps built in {time.perf_counter() - t0:.1f} s\n")
+        print(json.dumps(measure("C4 dielectric sphere 512^3 (1 GPU)", w4, steps=20, kry=5)))

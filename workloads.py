@@ -171,6 +171,41 @@ def c3_rhs(w):
     return fb.create_srcs(mdl)
 
 
+def c4_scatterer(N=(512, 512, 512), k0=0, k1=None, seed=20261017, delta=20.0, radius_cells=100):
+    """C4: dielectric sphere (eps 4, radius 100 cells) in vacuum, 10-cell PML on all sides.  Smoothing stand-in:
+    linear fill ramp across the surface for the diagonal entries + the seeded symmetric off-diagonal perturbation
+    on the surface shell.  The eps array is built directly in Julia memory order ([u,v,k,j,i], C-contiguous) so
+    that no transposing copy of the 19 GB array is needed."""
+    Nx, Ny, Nz = N
+    w = _common(N, delta, (False, False, False), ((10,) * 3, (10,) * 3))
+    k1 = Nz if k1 is None else k1
+    g = w["grid"]
+    R = radius_cells * delta
+    eps = np.zeros((3, 3, k1 - k0, Ny, Nx), np.complex128)
+    xp, xd = g.l[fb.PRIM][0], g.l[fb.DUAL][0]
+    yp, yd = g.l[fb.PRIM][1], g.l[fb.DUAL][1]
+    zp, zd = g.l[fb.PRIM][2][k0:k1], g.l[fb.DUAL][2][k0:k1]
+
+    def fill(x, y, z):
+        d = np.sqrt(z[:, None, None] ** 2 + y[None, :, None] ** 2 + x[None, None, :] ** 2)
+        return np.clip((R - d) / delta + 0.5, 0.0, 1.0)
+
+    for v, (xx, yy, zz) in enumerate(((xd, yp, zp), (xp, yd, zp), (xp, yp, zd))):
+        eps[v, v] = 1.0 + 3.0 * fill(xx, yy, zz)
+    d = np.sqrt(zp[:, None, None] ** 2 + yp[None, :, None] ** 2 + xp[None, None, :] ** 2)
+    shell = np.abs(d - R) < delta
+    del d
+    rng = np.random.default_rng(seed + 1000 * k0)
+    for (v, u) in ((0, 1), (0, 2), (1, 2)):
+        pert = np.zeros(shell.shape)
+        pert[shell] = 0.2 * (rng.random(int(shell.sum())) - 0.5)
+        eps[u, v] = pert
+        eps[v, u] = pert
+    w.update(eps=eps, k0=k0, k1=k1, full_eps=True,
+             name=f"C4 dielectric sphere {Nx}x{Ny}x{Nz}, full 3x3 eps on the surface, 10-cell PML")
+    return w
+
+
 def make_operator(w, device=-1, rank=0, nranks=1, kernel=0, **kw):
     return fb.FdfdOperator(w["N"], w["isbloch"], w["sdl_e"], w["sdl_m"], w["omega"], w["eps"], None, w["e_mikL"],
                            device=device, rank=rank, nranks=nranks, kernel=kernel,
