@@ -107,6 +107,22 @@ function h_from_e_gpu(A::GpuOperator, e::Vector{ComplexF64}, jₘ::Vector{Comple
     return h
 end
 
+"""e_from_h (model.jl:281-284) -> fdfd_e_from_h (diagonal Pε only, like the reference's `Pε \\`)."""
+function e_from_h_gpu(A::GpuOperator, h::Vector{ComplexF64}, jₑ::Vector{ComplexF64})
+    e = similar(h)
+    check(ccall((:fdfd_e_from_h, LIB), Cint, (Ptr{Cvoid}, Ptr{ComplexF64}, Ptr{ComplexF64}, Ptr{ComplexF64}, Cint),
+                A.h, h, iszero(jₑ) ? C_NULL : pointer(jₑ), e, 0), A.h)
+    return e
+end
+
+"""create_Mcs (model.jl:287-306) applied to a field: `Mcₑ * e` (ft = EE) or `Mcₘ * h` (ft = HH) -> fdfd_interp_corners."""
+function interp_corners_gpu(A::GpuOperator, ft::FieldType, f::Vector{ComplexF64})
+    out = similar(f)
+    check(ccall((:fdfd_interp_corners, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{ComplexF64}, Ptr{ComplexF64}, Cint),
+                A.h, ft == EE ? 0 : 1, f, out, 0), A.h)
+    return out
+end
+
 """Debug: the assembled A as a SparseMatrixCSC (same colptr/rowval Julia's create_A produces)."""
 function sparse_export(A::GpuOperator)
     nnz = Ref{Int64}(0)

@@ -6,14 +6,18 @@
 // create_A (src/model/model.jl:225-246); stencil per SURVEY.md App. A.4-A.6.
 //
 // Structure (2.5-D blocking, B200):
-//   * a CTA owns an x-y tile of TX x TY cells (thread (tx,ty) <-> one cell, all 3 components) and marches
-//     over a chunk of z-planes;
-//   * x planes are staged global -> shared by the TMA unit with 1-D bulk copies (cp.async.bulk, one per
-//     tile row [+ wrap pieces for Bloch boundaries]) completing on an mbarrier per ring stage; NST planes
-//     are in flight, so HBM latency is hidden by the copy engine, not by occupancy;
-//   * the intermediate field H = q .* C1 x never leaves the SM: own-cell values stay in registers, the
-//     3 neighbour values travel through a double-buffered shared tile (one __syncthreads per plane);
-//   * boundary conditions are pure data (1-D coefficient tables, coeffs.cpp): no divergent branches;
+//   * a CTA owns an x-y tile of TX x TY cells (thread (tx,ty) <-> one cell, all 3 components) and marches over a
+//     chunk of z-planes; 32x8 tiles with two CTAs per SM for diagonal material, 32x16 for the fused full tensor;
+//   * x planes are staged global -> shared by the TMA unit with 1-D bulk copies (cp.async.bulk, one per tile row
+//     [+ 1-cell wrap pieces at Bloch boundaries]) completing on an mbarrier per ring stage; 3-4 planes are in
+//     flight, so HBM latency is hidden by the copy engine, not by occupancy; the producer duty rotates over warps;
+//   * the intermediate field H = q .* C1 x never leaves the SM: own-cell values stay in registers, the neighbour
+//     values travel through a double-buffered shared tile (one __syncthreads per plane);
+//   * outputs are staged in shared memory and leave through TMA bulk stores (cp.async.bulk.global.shared::cta);
+//   * boundary conditions are pure data (1-D coefficient tables in shared memory, coeffs.cpp): no divergent
+//     branches; material is prefetched to L2 two planes ahead and loaded one phase before use;
+//   * off-diagonal material: per-(tile, plane) occupancy mask; sparse case = this kernel's diagonal variant + the
+//     marching correction kernel (apply_naive.cu) on flagged runs; dense case = the fused HAS_OFF variant;
 //   * each x element is read from HBM once (+ halo re-reads that hit L2), y written once, material read once.
 // Tile: thread tile TX x TY covers cells [ox, ox+TX) x [oy, oy+TY); outputs are the inner (TX-2) x (TY-2).
 #include <algorithm>
