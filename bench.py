@@ -311,8 +311,8 @@ def main():
                     "note": "fdfd_apply(FDFD_HOST) with pinned host buffers"},
             "gpu_launches": launches, "clocks": clocks,
             "krylov": {"method": "bicgstab", "iters": args.krylov_iters, "iter_per_s": it_per_s,
-                       "bytes_per_dof_model": 2 * bpd + 288,
-                       "hbm_frac": (2 * bpd + 288) * (n_tot / world) * it_per_s / 1e9 / peak},
+                       "bytes_per_dof_model": 2 * bpd + 256,
+                       "hbm_frac": (2 * bpd + 256) * (n_tot / world) * it_per_s / 1e9 / peak},
         }
         if world == 1 and not args.no_cpu:
             try:

@@ -50,7 +50,7 @@ static inline int nblocks(int64_t n) {
 static void free_device(Ctx *c) {
     auto F = [](auto *&p) { if (p) cudaFree((void *)p); p = nullptr; };
     F(c->coef_dev); F(c->mat_dev); F(c->halo_lo); F(c->halo_hi); F(c->work); F(c->scal); F(c->partial);
-    F(c->stage_x); F(c->stage_y); F(c->flush_buf); F(c->offmask); F(c->corr_list);
+    F(c->stage_x); F(c->stage_y); F(c->flush_buf); F(c->offmask); F(c->corr_list); F(c->dot_partial); F(c->dot_ticket);
     if (c->scal_host) cudaFreeHost(c->scal_host);
     c->scal_host = nullptr;
 }
@@ -239,6 +239,10 @@ void fill_params(Ctx *c, ApplyParams &p, const double2 *x, double2 *y, bool tran
     p.y = y; p.y_pstride = p.x.pstride; p.y_cs = p.x.cs; p.y_es = p.x.es;
     p.offmask = c->offmask; p.offmask_ty = c->offmask_ty;
     p.corr_list = c->corr_list; p.corr_count = c->corr_count;
+    if (c->dot_req) {
+        p.dot_mode = 2; p.dot_out = c->dot_req; p.dot_partial = c->dot_partial; p.dot_ticket = c->dot_ticket;
+        p.dot_cap = c->dot_cap;
+    }
 }
 
 int apply_device(Ctx *c, const double2 *x, double2 *y, bool transpose) {
@@ -308,6 +312,33 @@ int apply_device(Ctx *c, const double2 *x, double2 *y, bool transpose) {
         c->launches += 1;
     }
     return FDFD_OK;
+}
+
+int ensure_dot_buffers(Ctx *c) {   // outside any stream capture
+    if (c->dot_partial) return FDFD_OK;
+    c->dot_cap = 1 << 20;
+    FDFD_CUDA(c, cudaMalloc((void **)&c->dot_partial, (size_t)c->dot_cap * 4 * sizeof(double)));
+    FDFD_CUDA(c, cudaMalloc((void **)&c->dot_ticket, sizeof(unsigned int)));
+    FDFD_CUDA(c, cudaMemset(c->dot_ticket, 0, sizeof(unsigned int)));
+    return FDFD_OK;
+}
+
+int apply_device_dots(Ctx *c, const double2 *x, double2 *y, double *dot_out, bool *fused) {
+    *fused = false;
+    int r = ensure_ready(c);
+    if (r != FDFD_OK) return r;
+    static const bool no_fuse = getenv("FDFD_NO_DOT_FUSION") != nullptr;
+    static const bool split_overlap = getenv("FDFD_SPLIT_OVERLAP") != nullptr;
+    ApplyParams p0;
+    fill_params(c, p0, x, y, false);
+    const bool tiled = c->d.kernel != FDFD_KERNEL_NAIVE && tiled_supported(p0);
+    if (no_fuse || !tiled || (c->d.nranks > 1 && split_overlap)) return apply_device(c, x, y, false);
+    if (!c->dot_partial) return apply_device(c, x, y, false);   // ensure_dot_buffers() was not called
+    c->dot_req = dot_out;
+    r = apply_device(c, x, y, false);
+    c->dot_req = nullptr;
+    *fused = (r == FDFD_OK);
+    return r;
 }
 
 bool halo_prefetch_usable(const Ctx *c) {

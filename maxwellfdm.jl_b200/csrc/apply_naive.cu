@@ -215,8 +215,10 @@ __global__ void __launch_bounds__(256) offdiag_march_kernel(const __grid_constan
     const int txp = min(tx + 1, 31), typ = min(ty + 1, 7);
 
     // corner quantity G(kk) at this thread's cell; ezm = E_z of plane kk-1 at this cell (in), E_z(kk) (out)
+    // own-cell field of the plane handled last by corner() (needed as `s` by the fused-dot deltas)
+    double2 ex = c_zero(), ey = c_zero(), ez = c_zero();
     auto corner = [&](int kk, double2 &ezm, double2 &Gx, double2 &Gy, double2 &Gz) {
-        const double2 ex = g.E(0, ci, cj, kk), ey = g.E(1, ci, cj, kk), ez = g.E(2, ci, cj, kk);
+        ex = g.E(0, ci, cj, kk); ey = g.E(1, ci, cj, kk); ez = g.E(2, ci, cj, kk);
         const int kg = g.kglob(kk);
         const double2 Ax = c_fma(mi1x, g.E(0, cim, cj, kk), c_mul(mi0x, ex));
         const double2 Ay = c_fma(mi1y, g.E(1, ci, cjm, kk), c_mul(mi0y, ey));
@@ -234,7 +236,9 @@ __global__ void __launch_bounds__(256) offdiag_march_kernel(const __grid_constan
     gs[ks & 1][0][tid] = Gcx;
     gs[ks & 1][1][tid] = Gcy;
     __syncthreads();
+    double d_re = 0.0, d_im = 0.0, d_tt = 0.0;   // fused Krylov dots: exact change of (y,x), (y,y) caused by this pass
     for (int k = ks; k < ke; ++k) {
+        const double2 sx = ex, sy = ey, sz = ez;      // x at this cell, plane k
         // neighbours of G(k): written one step ago, visible since the last barrier; read BEFORE this step's barrier
         const double2 Gx_xp = gs[k & 1][0][ty * 32 + txp], Gy_yp = gs[k & 1][1][typ * 32 + tx];
         double2 Gnx, Gny, Gnz;
@@ -244,17 +248,42 @@ __global__ void __launch_bounds__(256) offdiag_march_kernel(const __grid_constan
         if (out_ok) {
             const int kg = g.kglob(k);
             double2 *yo = &p.y[(int64_t)k * p.y_pstride + ((int64_t)gj * p.Nx + gi) * p.y_es];
-            double2 t = c_fma(p.c.mo1[0][ci], Gx_xp, c_mul(p.c.mo0[0][ci], Gcx));
-            yo[0] = c_add(yo[0], t);
-            t = c_fma(p.c.mo1[1][cj], Gy_yp, c_mul(p.c.mo0[1][cj], Gcy));
-            yo[p.y_cs] = c_add(yo[p.y_cs], t);
-            t = c_fma(p.c.mo1[2][kg], Gnz, c_mul(p.c.mo0[2][kg], Gcz));
-            yo[2 * p.y_cs] = c_add(yo[2 * p.y_cs], t);
+            const double2 tx_ = c_fma(p.c.mo1[0][ci], Gx_xp, c_mul(p.c.mo0[0][ci], Gcx));
+            const double2 ty_ = c_fma(p.c.mo1[1][cj], Gy_yp, c_mul(p.c.mo0[1][cj], Gcy));
+            const double2 tz_ = c_fma(p.c.mo1[2][kg], Gnz, c_mul(p.c.mo0[2][kg], Gcz));
+            const double2 o0 = yo[0], o1 = yo[p.y_cs], o2 = yo[2 * p.y_cs];
+            const double2 n0 = c_add(o0, tx_), n1 = c_add(o1, ty_), n2 = c_add(o2, tz_);
+            yo[0] = n0;
+            yo[p.y_cs] = n1;
+            yo[2 * p.y_cs] = n2;
+            if (p.dot_mode == 2) {
+                d_re += tx_.x * sx.x + tx_.y * sx.y + ty_.x * sy.x + ty_.y * sy.y + tz_.x * sz.x + tz_.y * sz.y;
+                d_im += tx_.x * sx.y - tx_.y * sx.x + ty_.x * sy.y - ty_.y * sy.x + tz_.x * sz.y - tz_.y * sz.x;
+                d_tt += (n0.x * n0.x + n0.y * n0.y - o0.x * o0.x - o0.y * o0.y) +
+                        (n1.x * n1.x + n1.y * n1.y - o1.x * o1.x - o1.y * o1.y) +
+                        (n2.x * n2.x + n2.y * n2.y - o2.x * o2.x - o2.y * o2.y);
+            }
         }
         Gcx = Gnx;
         Gcy = Gny;
         Gcz = Gnz;
         __syncthreads();
+    }
+    if (p.dot_mode == 2) {   // add this CTA's deltas to the sums the main kernel's last CTA has already published
+        __shared__ double red[8][3];
+        double v3[3] = {d_re, d_im, d_tt};
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v3[q] += __shfl_xor_sync(0xffffffffu, v3[q], o);
+            if ((tid & 31) == 0) red[tid >> 5][q] = v3[q];
+        }
+        __syncthreads();
+        if (tid < 3) {
+            double a = 0.0;
+            for (int w = 0; w < 8; ++w) a += red[w][tid];
+            if (a != 0.0) atomicAdd(&p.dot_out[tid], a);
+        }
     }
 }
 

@@ -97,7 +97,7 @@ struct TileIdx {
     __device__ __forceinline__ static int h(int c, int tx, int ty) { return (c * TY + ty) * TX + tx; }
 };
 
-template <bool CMPFIRST, bool HAS_OFF, bool HAS_Q, int TX, int TY>
+template <bool CMPFIRST, bool HAS_OFF, bool HAS_Q, int TX, int TY, bool DOT>
 __global__ void __launch_bounds__(TX *TY, (TX * TY <= 256 ? 2 : 1)) apply_tiled_kernel(const __grid_constant__ TiledParams tp) {
     using TI = TileIdx<CMPFIRST, TX, TY>;
     constexpr int NT = TX * TY;
@@ -288,6 +288,7 @@ __global__ void __launch_bounds__(TX *TY, (TX * TY <= 256 ? 2 : 1)) apply_tiled_
     double2 Hpx = c_zero(), Hpy = c_zero();
     double2 Gcz = c_zero();                                   // G_z(k) own
     bool hasc = false;                                        // does plane k of this tile hold off-diagonal material?
+    double ts_re = 0.0, ts_im = 0.0, tt = 0.0;                // DOT: (y,x) and (y,y) over this thread's outputs
     // q of the plane whose H comes next is kept one phase ahead in registers
     double2 qc0 = c_zero(), qc1 = c_zero(), qc2 = c_zero();
     if (HAS_Q) {
@@ -450,6 +451,11 @@ __global__ void __launch_bounds__(TX *TY, (TX * TY <= 256 ? 2 : 1)) apply_tiled_
                     yz = c_fma(czs[7 * LZP + n], Gz1, yz);
                 }
             }
+            if (DOT) {   // fused Krylov inner products: t = y, s = x (own cell, in registers)
+                ts_re += yx.x * Eo0.x + yx.y * Eo0.y + yy.x * Eo1.x + yy.y * Eo1.y + yz.x * Eo2.x + yz.y * Eo2.y;
+                ts_im += yx.x * Eo0.y - yx.y * Eo0.x + yy.x * Eo1.y - yy.y * Eo1.x + yz.x * Eo2.y - yz.y * Eo2.x;
+                tt += yx.x * yx.x + yx.y * yx.y + yy.x * yy.x + yy.y * yy.y + yz.x * yz.x + yz.y * yz.y;
+            }
             double2 *yb = ybuf + (n & 1) * STAGE;
             yb[eo] = yx;
             yb[eo + EC] = yy;
@@ -466,6 +472,50 @@ __global__ void __launch_bounds__(TX *TY, (TX * TY <= 256 ? 2 : 1)) apply_tiled_
     // outputs of the last iteration
     __syncthreads();
     if (nplanes >= 3 && wid == 0) issue_store(nplanes - 2);
+    if (DOT) {
+        // block reduction of the three sums (the coefficient tables are dead now: reuse them as scratch), one partial
+        // per CTA, and the last CTA (atomic ticket) adds the partials in a fixed order -> deterministic result
+        double *scratch = reinterpret_cast<double *>(cxs);
+        double v3[3] = {ts_re, ts_im, tt};
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v3[q] += __shfl_xor_sync(0xffffffffu, v3[q], o);
+            if (lane == 0) scratch[wid * 3 + q] = v3[q];
+        }
+        __syncthreads();
+        __shared__ bool last_cta;
+        if (tid == 0) {
+            double a = 0, b2 = 0, c3 = 0;
+            for (int w = 0; w < NW; ++w) { a += scratch[w * 3]; b2 += scratch[w * 3 + 1]; c3 += scratch[w * 3 + 2]; }
+            double *pp = p.dot_partial + (size_t)blockIdx.x * 4;
+            pp[0] = a; pp[1] = b2; pp[2] = c3;
+            __threadfence();
+            last_cta = atomicAdd(p.dot_ticket, 1u) == gridDim.x - 1;
+        }
+        __syncthreads();
+        if (last_cta) {
+            __threadfence();
+            double s3[3] = {0.0, 0.0, 0.0};
+            for (int bI = tid; bI < (int)gridDim.x; bI += NT) {
+                const double *pp = p.dot_partial + (size_t)bI * 4;
+                s3[0] += __ldcg(pp); s3[1] += __ldcg(pp + 1); s3[2] += __ldcg(pp + 2);
+            }
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) s3[q] += __shfl_xor_sync(0xffffffffu, s3[q], o);
+                if (lane == 0) scratch[64 + wid * 3 + q] = s3[q];
+            }
+            __syncthreads();
+            if (tid == 0) {
+                double a = 0, b2 = 0, c3 = 0;
+                for (int w = 0; w < NW; ++w) { a += scratch[64 + w * 3]; b2 += scratch[64 + w * 3 + 1]; c3 += scratch[64 + w * 3 + 2]; }
+                p.dot_out[0] = a; p.dot_out[1] = b2; p.dot_out[2] = c3; p.dot_out[3] = 0.0;
+                *p.dot_ticket = 0;
+            }
+        }
+    }
     bulk_wait0();   // every outstanding bulk store of this thread has completed before the CTA exits
 }
 
@@ -497,9 +547,9 @@ size_t tiled_smem_bytes() {
                sizeof(double2) + NST * 8 + 128;
 }
 
-template <bool CMPFIRST, bool HAS_OFF, bool HAS_Q, int TX, int TY>
+template <bool CMPFIRST, bool HAS_OFF, bool HAS_Q, int TX, int TY, bool DOT>
 cudaError_t launch_variant(const TiledParams &tp, cudaStream_t s) {
-    auto kern = apply_tiled_kernel<CMPFIRST, HAS_OFF, HAS_Q, TX, TY>;
+    auto kern = apply_tiled_kernel<CMPFIRST, HAS_OFF, HAS_Q, TX, TY, DOT>;
     const size_t smem = tiled_smem_bytes<CMPFIRST, HAS_OFF, HAS_Q, TX, TY>();
     static bool attr_set = false;
     if (!attr_set) {
@@ -508,6 +558,7 @@ cudaError_t launch_variant(const TiledParams &tp, cudaStream_t s) {
         attr_set = true;
     }
     const int grid = tp.ntx * tp.nty * tp.nchunk;
+    if (DOT && grid > tp.a.dot_cap) return cudaErrorInvalidConfiguration;
     kern<<<grid, TX * TY, smem, s>>>(tp);
     return cudaGetLastError();
 }
@@ -555,7 +606,7 @@ static cudaError_t launch_tile(const ApplyParams &p, int kl_begin, int kl_end, c
     tp.offmask = (p.offmask && p.offmask_ty == TY) ? p.offmask : nullptr;
     const bool cf = tp.a.cmpfirst != 0, off = p.has_off != 0 && p.has_mass != 0 && !diag_only, q = p.has_q != 0;
     cudaError_t e;
-#define V(CF, OFF, Q) e = launch_variant<CF, OFF, Q, TX, TY>(tp, s)
+#define V(CF, OFF, Q) e = (p.dot_mode == 2) ? launch_variant<CF, OFF, Q, TX, TY, true>(tp, s) : launch_variant<CF, OFF, Q, TX, TY, false>(tp, s)
     if (cf) {
         if (off) { if (q) V(true, true, true); else V(true, true, false); }
         else     { if (q) V(true, false, true); else V(true, false, false); }

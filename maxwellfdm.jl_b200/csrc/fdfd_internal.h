@@ -63,6 +63,11 @@ struct ApplyParams {
     int32_t offmask_ty;            // tile height the mask was built for
     const int4 *corr_list;         // sparse off-diagonals: work items (tile, ks, ke) of the correction pass
     int32_t corr_count;
+    // fused Krylov inner products (tiled kernel epilogue): dot_mode 2 = accumulate (y,x) and (y,y) over the outputs
+    int32_t dot_mode, dot_cap;
+    double *dot_out;               // 4 doubles: Re (y,x), Im (y,x), (y,y), 0
+    double *dot_partial;           // per-CTA partials (4 doubles each), capacity dot_cap CTAs
+    unsigned int *dot_ticket;
     double2 *y;             // output slab, same layout as x.base
     int64_t y_pstride, y_cs;
     int32_t y_es;
@@ -124,6 +129,10 @@ struct Ctx {
     // Krylov workspace
     double2 *work = nullptr;
     size_t work_bytes = 0;
+    double *dot_partial = nullptr;   // per-CTA partials of the fused apply-epilogue dots
+    unsigned int *dot_ticket = nullptr;
+    int dot_cap = 0;
+    double *dot_req = nullptr;       // set while apply_device runs on behalf of apply_device_dots
     double *scal = nullptr;          // device scalars
     double *partial = nullptr;       // per-block partial sums
     double *scal_host = nullptr;     // pinned
@@ -200,6 +209,10 @@ int allreduce_sum(Ctx *c, double *dev, int count, cudaStream_t s);
 // api.cu -------------------------------------------------------------------------------------------
 int ensure_ready(Ctx *c);
 int apply_device(Ctx *c, const double2 *x, double2 *y, bool transpose);
+// y = A x and, fused into the kernel epilogue when the tiled single-launch path is taken, (y,x) -> dot_out[0..1],
+// (y,y) -> dot_out[2]; *fused tells the caller whether it still has to run its own dot kernel.
+int apply_device_dots(Ctx *c, const double2 *x, double2 *y, double *dot_out, bool *fused);
+int ensure_dot_buffers(Ctx *c);
 // Start the halo exchange of slab vector v on the comm stream (v's boundary planes must already be enqueued on the
 // main stream); the next apply_device(v) then only waits for it.  No-op unless nranks > 1 and cmp-first layout.
 int halo_prefetch(Ctx *c, const double2 *v);

@@ -120,6 +120,7 @@ static int bicgstab(Ctx *c, const double2 *b, double2 *x, double rtol, int maxit
     int rc = ensure_ready(c);
     if (rc != FDFD_OK) return rc;
     if ((rc = kry::workspace(c, 6)) != FDFD_OK) return rc;
+    if ((rc = ensure_dot_buffers(c)) != FDFD_OK) return rc;
     const int64_t n = c->nloc;
     double2 *r = c->work, *rhat = r + n, *p = rhat + n, *v = p + n, *s = v + n, *t = s + n;
     Red rd = kry::make_red(c);
@@ -191,8 +192,10 @@ static int bicgstab(Ctx *c, const double2 *b, double2 *x, double rtol, int maxit
         } else {
             k_s<<<g, RB, 0, st>>>(n, r, v, s, rd, rho_old);
         }
-        if ((r1 = apply_device(c, s, t, false)) != FDFD_OK) return r1;
-        k_dot2<<<g, RB, 0, st>>>(n, t, s, rd);
+        // t = A s with (t,s) and (t,t) accumulated in the kernel epilogue when the tiled path is taken
+        bool fused = false;
+        if ((r1 = apply_device_dots(c, s, t, sc + 2 * S_TS, &fused)) != FDFD_OK) return r1;
+        if (!fused) { k_dot2<<<g, RB, 0, st>>>(n, t, s, rd); c->launches += 1; }
         if ((r1 = allreduce_sum(c, sc + 2 * S_TS, 4, st)) != FDFD_OK) return r1;
         k_xr<<<g, RB, 0, st>>>(n, x, p, s, t, rhat, r, rd, rho_new);
         if ((r1 = allreduce_sum(c, sc + 2 * rho_new, 4, st)) != FDFD_OK) return r1;
@@ -207,7 +210,7 @@ static int bicgstab(Ctx *c, const double2 *b, double2 *x, double rtol, int maxit
         }
         cudaError_t e1 = cudaGetLastError();
         if (e1 != cudaSuccess) return set_err(c, FDFD_ECUDA, cudaGetErrorString(e1));
-        c->launches += 5;
+        c->launches += 4;
         return FDFD_OK;
     };
     // Small grids are launch-bound (40^3: ~50 us of launches per iteration): replay two iterations (both scalar
