@@ -33,7 +33,7 @@ namespace fdfd {
 namespace {
 
 constexpr int nst_for(int nthreads) { return nthreads <= 256 ? 4 : 3; }   // ring stages (planes in flight)
-constexpr int lzmax_for(int nthreads) { return nthreads <= 256 ? 32 : 64; }     // max planes per z-chunk
+constexpr int lzmax_for(int nthreads) { return nthreads <= 256 ? 40 : 64; }     // max planes per z-chunk
 
 struct TiledParams {
     ApplyParams a;
