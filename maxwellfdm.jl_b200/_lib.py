@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libfdfd_b200.so")
+LIB_PATH = os.environ.get("FDFD_B200_LIB", os.path.join(HERE, "libfdfd_b200.so"))   # override: tuning experiments
 
 OK, EINVAL, ECUDA, ENCCL, ENOMEM, ENOCONV, ESTATE = range(7)
 HOST, DEVICE = 0, 1

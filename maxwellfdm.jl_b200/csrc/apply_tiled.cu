@@ -28,6 +28,7 @@
 #include "cplx.cuh"
 #include "fdfd_internal.h"
 
+
 namespace fdfd {
 
 namespace {
@@ -298,6 +299,9 @@ __global__ void __launch_bounds__(TX *TY, (TX * TY <= 256 ? 2 : 1)) apply_tiled_
         qc2 = ldg2(&p.q[2][mk]);
     }
 
+    // unrolling by 2 lets the compiler rename away the register rotation and fold the double-buffer offsets
+    // (-20 % instructions per plane; measured +3 % for the diagonal kernel, -2 % for the register-bound full tensor)
+#pragma unroll(HAS_OFF ? 1 : 2)
     for (int n = 0; n + 1 < nplanes; ++n) {
         const int k = kc0 - 1 + n;                              // local plane whose H is computed (and y, if n >= 1)
         const double2 *es = ering + (n % NST) * STAGE;          // plane k
