@@ -142,6 +142,7 @@ def run_reference(args):
         return
     import numpy as np
     from oracle import cbaseline as cb
+    cb.use_all_cores()                       # torchrun pins OMP_NUM_THREADS=1; the reference arm uses every core
     A, desc = oracle_sample_matrix()
     R = cb.CsrOmp(A)
     n = A.shape[0]

@@ -555,11 +555,13 @@ template <bool CMPFIRST, bool HAS_OFF, bool HAS_Q, int TX, int TY, bool DOT>
 cudaError_t launch_variant(const TiledParams &tp, cudaStream_t s) {
     auto kern = apply_tiled_kernel<CMPFIRST, HAS_OFF, HAS_Q, TX, TY, DOT>;
     const size_t smem = tiled_smem_bytes<CMPFIRST, HAS_OFF, HAS_Q, TX, TY>();
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};   // per device: the opt-in to > 48 KB dynamic shared memory is a per-device attribute
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        attr_set = true;
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
     const int grid = tp.ntx * tp.nty * tp.nchunk;
     if (DOT && grid > tp.a.dot_cap) return cudaErrorInvalidConfiguration;

@@ -24,6 +24,7 @@ def lib():
         l.csc_mul_serial.argtypes = [C.c_int64, P, P, P, P, P]
         l.csr_mul_omp.argtypes = [C.c_int64, P, P, P, P, P]
         l.oracle_num_threads.restype = C.c_int
+        l.oracle_set_threads.argtypes = [C.c_int]
         _lib = l
     return _lib
 
@@ -59,3 +60,12 @@ class CsrOmp:
 
 def num_threads():
     return int(lib().oracle_num_threads())
+
+
+def use_all_cores():
+    """Size the OpenMP team to the cores this process may run on, whatever OMP_NUM_THREADS says (torchrun sets
+    it to 1 for its workers).  Returns the team size."""
+    import os
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lib().oracle_set_threads(int(n))
+    return num_threads()

@@ -33,6 +33,15 @@ void csr_mul_omp(int64_t n, const int64_t *rowptr, const int64_t *colval, const 
     }
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to its workers; the all-cores baseline sets its team size explicitly. */
+void oracle_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int oracle_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -305,6 +305,24 @@ def test_e_from_h_and_corner_interpolation():
     A.close()
 
 
+def test_tfsf_rhs_reproduces_the_incident_wave():
+    """TF/SF stand-in for C4 (workloads.tfsf_rhs): b = A (M E_inc) - M (A E_inc) lives on the surface of the
+    total-field box only, and in vacuum the solve returns exactly M E_inc (the discrete plane wave inside the box,
+    nothing outside)."""
+    import workloads
+    w = workloads.c4_scatterer((40, 40, 40), radius_cells=-5)       # negative radius: vacuum everywhere
+    A = workloads.make_operator(w, device=0)
+    b, e_ref = workloads.tfsf_rhs(A, w, box_cells=16)
+    B = np.abs(_fb().field_vec2arr(b, w["N"])).max(axis=-1)
+    assert B[20, 20, 20] == 0 and B[2, 2, 2] == 0                   # deep inside / far outside: exactly zero
+    assert B[20, 20, 28] > 0 and B[20, 20, 12] > 0                  # the two z faces of the box
+    assert np.count_nonzero(B) < 0.05 * B.size
+    e, info = A.solve(b, rtol=1e-10, maxit=20000, check_every=50)
+    assert info["converged"]
+    assert np.abs(e - e_ref).max() < 1e-5                            # |E_inc| = 1
+    A.close()
+
+
 def test_model_api_end_to_end():
     """reference-shaped host API: ModelFull -> add_srce -> create_linsys -> solve -> h_from_e."""
     fb = _fb()

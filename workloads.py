@@ -206,6 +206,30 @@ def c4_scatterer(N=(512, 512, 512), k0=0, k1=None, seed=20261017, delta=20.0, ra
     return w
 
 
+def tfsf_rhs(A, w, box_cells=140, axis=2, pol=0):
+    """TF/SF plane-wave source stand-in for C4 (the reference has no TF/SF source, README.md:40), built from the
+    operator itself:  b = A (M E_inc) - M (A E_inc),  with M the mask of the total-field region (a centred box of
+    `box_cells` cells) and E_inc a plane wave travelling along +`axis`, polarised along `pol`, with the DISCRETE
+    vacuum wavenumber (2/d) asin(w d / 2) so that A E_inc = 0 on the uniform part of the grid.  A is local, so b
+    lives on the box surface only, and the solution of A e = b is E_inc + E_scat inside the box and E_scat
+    outside.  `A` is anything with a matvec (`A @ x`) in the reference's DOF ordering."""
+    assert axis != pol
+    g = w["grid"]
+    d = float(g.lg_prim[axis][1] - g.lg_prim[axis][0])
+    k = 2.0 / d * np.arcsin(w["omega"] * d / 2.0)
+    E = np.zeros(tuple(w["N"]) + (3,), np.complex128)
+    inside = np.zeros(E.shape, bool)
+    for v in range(3):
+        pos = np.meshgrid(*[g.l[fb.DUAL if a == v else fb.PRIM][a] for a in range(3)], indexing="ij")
+        if v == pol:
+            E[..., v] = np.exp(-1j * k * pos[axis])
+        half = box_cells / 2.0 * d
+        inside[..., v] = (np.abs(pos[0]) < half) & (np.abs(pos[1]) < half) & (np.abs(pos[2]) < half)
+    e_inc = fb.field_arr2vec(E)
+    m = fb.field_arr2vec(inside.astype(np.complex128))
+    return A @ (m * e_inc) - m * (A @ e_inc), m * e_inc
+
+
 def make_operator(w, device=-1, rank=0, nranks=1, kernel=0, **kw):
     return fb.FdfdOperator(w["N"], w["isbloch"], w["sdl_e"], w["sdl_m"], w["omega"], w["eps"], None, w["e_mikL"],
                            device=device, rank=rank, nranks=nranks, kernel=kernel,
