@@ -105,7 +105,7 @@ static int upload_materials(Ctx *c) {
     const std::vector<cplx> &mid = ee ? c->mu_host : c->eps_host;
     const bool mass_given = !mass.empty(), mid_given = !mid.empty();
     const bool has_mass = c->omega != cplx(0.0);
-    const bool has_off = has_mass && mass_given && (ee ? c->eps_off : c->have_mu && false);
+    const bool has_off = has_mass && mass_given && (ee ? c->eps_off : c->mu_off);
     const int narr = (has_mass ? 3 : 0) + (has_off ? 6 : 0) + (mid_given ? 3 : 0);
     const size_t bytes = (size_t)narr * Mg * sizeof(double2);
     if (bytes != c->mat_bytes) {
@@ -253,7 +253,7 @@ int apply_device(Ctx *c, const double2 *x, double2 *y, bool transpose) {
     fill_params(c, p, x, y, transpose);
     const bool can_tile = tiled_supported(p);
     if (c->d.kernel == FDFD_KERNEL_TILED && !can_tile)
-        return set_err(c, FDFD_EINVAL, "tiled kernel requires the first curl to be forward on every axis");
+        return set_err(c, FDFD_EINVAL, "tiled kernel requires a uniform Yee arrangement (boundft all-EE or all-HH)");
     const bool use_tiled = c->d.kernel != FDFD_KERNEL_NAIVE && can_tile;
     // timing experiments only (results are wrong with FDFD_DEBUG_SKIP_HALO): where does the multi-slab overhead go?
     static const bool dbg_skip_halo = getenv("FDFD_DEBUG_SKIP_HALO") != nullptr;
@@ -370,8 +370,8 @@ static int stage_buffers(Ctx *c) {
 // direction's transfer time instead of H2D + kernel + D2H.  Needs a single slab, the cmp-first layout (a
 // z sub-slab is contiguous) and the tiled kernel; other configurations use the plain staged path.
 static bool can_pipeline(Ctx *c) {
-    return c->d.nranks == 1 && c->d.order_cmpfirst && c->d.kernel != FDFD_KERNEL_NAIVE && c->s1[0] == 1 &&
-           c->s1[1] == 1 && c->s1[2] == 1 && (c->k1 - c->k0) >= 16;
+    return c->d.nranks == 1 && c->d.order_cmpfirst && c->d.kernel != FDFD_KERNEL_NAIVE &&
+           c->s1[0] == c->s1[1] && c->s1[1] == c->s1[2] && (c->k1 - c->k0) >= 16;
 }
 
 static int apply_host_pipelined(Ctx *c, const double2 *xh, double2 *yh, bool transpose) {
@@ -639,6 +639,7 @@ int fdfd_set_mu(fdfd_handle h, const fdfd_c128 *mu) {
         c->mu_host.clear();
         c->mu_host.shrink_to_fit();
         c->have_mu = false;
+        c->mu_off = false;
     } else {
         const cplx *p = reinterpret_cast<const cplx *>(mu);
         try {
@@ -646,11 +647,13 @@ int fdfd_set_mu(fdfd_handle h, const fdfd_c128 *mu) {
         } catch (const std::bad_alloc &) {
             return set_err(c, FDFD_ENOMEM, "fdfd_set_mu: out of host memory");
         }
-        if (offdiag_nonzero(c->mu_host, M)) {
+        c->mu_off = offdiag_nonzero(c->mu_host, M);
+        if (c->mu_off && c->d.field_type == FDFD_FT_EE) {
             c->mu_host.clear();
-            // reference: `Pmu \ Ce` (model.jl:236) is unsupported for non-diagonal Pmu; for FT_HH the mass
-            // operator with off-diagonal mu is not built yet either.
-            return set_err(c, FDFD_EINVAL, "mu must be diagonal (reference model.jl:236)");
+            c->mu_off = false;
+            // reference: `Pmu \ Ce` (model.jl:236) is unsupported for non-diagonal Pmu.  (For FT_HH mu is the mass
+            // parameter, A = Ce (Peps \ Cm) - w^2 Pmu, model.jl:238-240, and may be a full tensor.)
+            return set_err(c, FDFD_EINVAL, "mu must be diagonal for FT_EE (reference model.jl:236)");
         }
         c->have_mu = true;
     }

@@ -13,6 +13,8 @@ namespace fdfd {
 
 namespace {
 
+__device__ __forceinline__ int g_wrap(int i, int N) { return i < 0 ? i + N : (i >= N ? i - N : i); }
+
 struct Gather {
     const ApplyParams &p;
     __device__ __forceinline__ int wrapx(int i) const { return i < 0 ? i + p.Nx : (i >= p.Nx ? i - p.Nx : i); }
@@ -196,8 +198,10 @@ __global__ void __launch_bounds__(128) interp_kernel(const __grid_constant__ App
 // kernel when off-diagonal entries are sparse (material interfaces only).  Work item = (tile, [ks,ke)): a run of
 // consecutive z-planes of one 32x8 thread tile (outputs: inner 30x6) whose corner terms can be non-zero.  The CTA
 // marches the run: the corner quantity G(k+1) is computed once per plane (11 loads per thread) and reused as
-// G(k) in the next step; x/y neighbours of G travel through a double-buffered shared tile.  Default Yee
-// arrangement only (first curl forward: in-average looks back, out-average looks forward).
+// G(k) in the next step; x/y neighbours of G travel through a double-buffered shared tile.  REV = false: default
+// Yee arrangement (first curl forward: in-average looks back, out-average looks forward, upward march);
+// REV = true: the mirror image (first curl backward on every axis, downward march).
+template <bool REV>
 __global__ void __launch_bounds__(256) offdiag_march_kernel(const __grid_constant__ ApplyParams p,
                                                              const int4 *__restrict__ items, int ntx, int kl_begin,
                                                              int kl_end) {
@@ -208,13 +212,14 @@ __global__ void __launch_bounds__(256) offdiag_march_kernel(const __grid_constan
     const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
     const int gi = (item.x % ntx) * 30 - 1 + tx, gj = (item.x / ntx) * 6 - 1 + ty;
     const int ci = ((gi % p.Nx) + p.Nx) % p.Nx, cj = ((gj % p.Ny) + p.Ny) % p.Ny;
-    const int cim = ci == 0 ? p.Nx - 1 : ci - 1, cjm = cj == 0 ? p.Ny - 1 : cj - 1;
+    constexpr int SG = REV ? -1 : 1;
+    const int cim = g_wrap(ci - SG, p.Nx), cjm = g_wrap(cj - SG, p.Ny);   // in-average neighbour (shift -s1)
     const bool out_ok = tx >= 1 && tx <= 30 && ty >= 1 && ty <= 6 && gi < p.Nx && gj < p.Ny;
     Gather g{p};
     const double2 mi0x = p.c.mi0[0][ci], mi1x = p.c.mi1[0][ci], mi0y = p.c.mi0[1][cj], mi1y = p.c.mi1[1][cj];
-    const int txp = min(tx + 1, 31), typ = min(ty + 1, 7);
+    const int txp = min(max(tx + SG, 0), 31), typ = min(max(ty + SG, 0), 7);   // out-average neighbour (shift +s1)
 
-    // corner quantity G(kk) at this thread's cell; ezm = E_z of plane kk-1 at this cell (in), E_z(kk) (out)
+    // corner quantity G(kk) at this thread's cell; ezm = E_z of plane kk-SG at this cell (in), E_z(kk) (out)
     // own-cell field of the plane handled last by corner() (needed as `s` by the fused-dot deltas)
     double2 ex = c_zero(), ey = c_zero(), ez = c_zero();
     auto corner = [&](int kk, double2 &ezm, double2 &Gx, double2 &Gy, double2 &Gz) {
@@ -230,21 +235,23 @@ __global__ void __launch_bounds__(256) offdiag_march_kernel(const __grid_constan
         ezm = ez;
     };
 
-    double2 ezm = g.E(2, ci, cj, ks - 1);
+    const int kfirst = REV ? ke - 1 : ks;
+    double2 ezm = g.E(2, ci, cj, kfirst - SG);
     double2 Gcx, Gcy, Gcz;
-    corner(ks, ezm, Gcx, Gcy, Gcz);
-    gs[ks & 1][0][tid] = Gcx;
-    gs[ks & 1][1][tid] = Gcy;
+    corner(kfirst, ezm, Gcx, Gcy, Gcz);
+    gs[0][0][tid] = Gcx;
+    gs[0][1][tid] = Gcy;
     __syncthreads();
     double d_re = 0.0, d_im = 0.0, d_tt = 0.0;   // fused Krylov dots: exact change of (y,x), (y,y) caused by this pass
-    for (int k = ks; k < ke; ++k) {
+    for (int st = 0; st < ke - ks; ++st) {
+        const int k = kfirst + SG * st;
         const double2 sx = ex, sy = ey, sz = ez;      // x at this cell, plane k
         // neighbours of G(k): written one step ago, visible since the last barrier; read BEFORE this step's barrier
-        const double2 Gx_xp = gs[k & 1][0][ty * 32 + txp], Gy_yp = gs[k & 1][1][typ * 32 + tx];
+        const double2 Gx_xp = gs[st & 1][0][ty * 32 + txp], Gy_yp = gs[st & 1][1][typ * 32 + tx];
         double2 Gnx, Gny, Gnz;
-        corner(k + 1, ezm, Gnx, Gny, Gnz);
-        gs[(k + 1) & 1][0][tid] = Gnx;
-        gs[(k + 1) & 1][1][tid] = Gny;
+        corner(k + SG, ezm, Gnx, Gny, Gnz);
+        gs[(st + 1) & 1][0][tid] = Gnx;
+        gs[(st + 1) & 1][1][tid] = Gny;
         if (out_ok) {
             const int kg = g.kglob(k);
             double2 *yo = &p.y[(int64_t)k * p.y_pstride + ((int64_t)gj * p.Nx + gi) * p.y_es];
@@ -299,7 +306,8 @@ cudaError_t launch_apply_naive(const ApplyParams &p, cudaStream_t s) {
 cudaError_t launch_offdiag_correction(const ApplyParams &p, const int4 *items, int count, int ntx, int kl_begin,
                                       int kl_end, cudaStream_t s) {
     if (count <= 0) return cudaSuccess;
-    offdiag_march_kernel<<<count, 256, 0, s>>>(p, items, ntx, kl_begin, kl_end);
+    if (p.s1[0] < 0) offdiag_march_kernel<true><<<count, 256, 0, s>>>(p, items, ntx, kl_begin, kl_end);
+    else             offdiag_march_kernel<false><<<count, 256, 0, s>>>(p, items, ntx, kl_begin, kl_end);
     return cudaGetLastError();
 }
 

@@ -1,6 +1,8 @@
-// K1 - the roofline kernel: matrix-free y = C2 (q .* C1 x) + mass(x) for the default Yee arrangement
-// (first curl forward on every axis, i.e. boundft = (EE,EE,EE) for FT_EE), any boundary condition,
-// both DOF layouts, diagonal or full 3x3 material tensor.
+// K1 - the roofline kernel: matrix-free y = C2 (q .* C1 x) + mass(x) for the two uniform Yee arrangements
+// (first curl forward on every axis: boundft = (EE,EE,EE) with FT_EE, the reference default, model.jl:46; or
+// backward on every axis [REV]: FT_HH with the default boundft, model.jl:238-240, or FT_EE with boundft all-HH),
+// any boundary condition, both DOF layouts, diagonal or full 3x3 material tensor.  REV is the mirror image of
+// the forward kernel: neighbour offsets change sign and the z-march runs downwards.
 //
 // Replaces the per-iteration CSC SpMV `mul!(y, A, x)` on the matrix assembled by the reference's
 // create_A (src/model/model.jl:225-246); stencil per SURVEY.md App. A.4-A.6.
@@ -98,9 +100,10 @@ struct TileIdx {
     __device__ __forceinline__ static int h(int c, int tx, int ty) { return (c * TY + ty) * TX + tx; }
 };
 
-template <bool CMPFIRST, bool HAS_OFF, bool HAS_Q, int TX, int TY, bool DOT>
+template <bool CMPFIRST, bool HAS_OFF, bool HAS_Q, int TX, int TY, bool DOT, bool REV>
 __global__ void __launch_bounds__(TX *TY, (TX * TY <= 256 ? 2 : 1)) apply_tiled_kernel(const __grid_constant__ TiledParams tp) {
     using TI = TileIdx<CMPFIRST, TX, TY>;
+    constexpr int SG = REV ? -1 : 1;   // direction of the first curl's neighbour (and of the z-march)
     constexpr int NT = TX * TY;
     constexpr int NST = nst_for(NT);
     constexpr int LZP = lzmax_for(NT) + 2;
@@ -133,6 +136,7 @@ __global__ void __launch_bounds__(TX *TY, (TX * TY <= 256 ? 2 : 1)) apply_tiled_
     const int kc0 = tp.kl_begin + chunk * tp.lz;
     const int kc1 = min(kc0 + tp.lz, tp.kl_end);
     const int nplanes = kc1 - kc0 + 2;  // planes kc0-1 .. kc1
+    auto kof = [&](int n) { return REV ? kc1 - n : kc0 - 1 + n; };   // local plane of march step n
 
     const int Nx = p.Nx, Ny = p.Ny;
     const int gi = ox + tx, gj = oy + ty;
@@ -174,12 +178,12 @@ __global__ void __launch_bounds__(TX *TY, (TX * TY <= 256 ? 2 : 1)) apply_tiled_
         const bool inr = CMPFIRST ? (idx < TY) : (idx < 3 * TY);
         cp_j[q] = inr ? row_src(cp_r[q]) : -1;
     }
-    // issue the copies of load #n (plane kc0-1+n) into ring stage n % NST; executed by ONE warp (any)
+    // issue the copies of load #n (plane kof(n)) into ring stage n % NST; executed by ONE warp (any)
     auto issue_load = [&](int n) {
         uint64_t *bar = &bars[n % NST];
         double2 *dst = ering + (n % NST) * STAGE;
         int64_t cs;
-        const double2 *src = plane_ptr(kc0 - 1 + n, cs);
+        const double2 *src = plane_ptr(kof(n), cs);
         if (lane == 0) mbar_arrive_expect_tx(bar, stage_bytes);
         __syncwarp();
 #pragma unroll
@@ -202,11 +206,11 @@ __global__ void __launch_bounds__(TX *TY, (TX * TY <= 256 ? 2 : 1)) apply_tiled_
         }
     };
 
-    // bulk-store the outputs written at iteration m (plane kc0-1+m) from ybuf[m & 1]: one copy per tile row
+    // bulk-store the outputs written at iteration m (plane kof(m)) from ybuf[m & 1]: one copy per tile row
     // (x range = the tile's output columns inside the domain); executed by ONE warp, one async-group per lane
     auto issue_store = [&](int m) {
         const double2 *src = ybuf + (m & 1) * STAGE;
-        double2 *dstp = p.y + (int64_t)(kc0 - 1 + m) * p.y_pstride;
+        double2 *dstp = p.y + (int64_t)kof(m) * p.y_pstride;
         const int c0 = ox + 1, c1 = min(ox + TX - 1, Nx);
         if (CMPFIRST) {
             for (int r = 1 + lane; r <= TY - 2; r += 32) {
@@ -254,10 +258,10 @@ __global__ void __launch_bounds__(TX *TY, (TX * TY <= 256 ? 2 : 1)) apply_tiled_
                                : a == 4 ? p.c.mi0[1] : a == 5 ? p.c.mi1[1] : a == 6 ? p.c.mo0[1] : p.c.mo1[1];
             cys[t] = src[j];
         }
-        // z tables: entry n <-> local plane kc0-1+n (global index wrapped)
+        // z tables: entry n <-> local plane kof(n) (global index wrapped)
         for (int t = tid; t < 8 * nplanes; t += NT) {
             const int a = t / nplanes, n = t % nplanes;
-            int kg = p.kz0 + kc0 - 1 + n;
+            int kg = p.kz0 + kof(n);
             kg = ((kg % p.Nz) + p.Nz) % p.Nz;
             const double2 *src = a == 0 ? p.c.a0[2] : a == 1 ? p.c.a1[2] : a == 2 ? p.c.b0[2] : a == 3 ? p.c.b1[2]
                                : a == 4 ? p.c.mi0[2] : a == 5 ? p.c.mi1[2] : a == 6 ? p.c.mo0[2] : p.c.mo1[2];
@@ -277,10 +281,13 @@ __global__ void __launch_bounds__(TX *TY, (TX * TY <= 256 ? 2 : 1)) apply_tiled_
     const int ho = ty * TX + tx;                 // H / G tiles: component stride NT, x stride 1, y stride TX
     // y-neighbour offsets collapse to 0 on the first / last tile row and x-neighbour reads of the first / last tile
     // position land in the gaps between buffers, so no read ever touches memory another agent may be writing.
-    const int eyp = ty == TY - 1 ? 0 : EY, eym = ty == 0 ? 0 : EY;
-    const int hyp = ty == TY - 1 ? 0 : TX, hym = ty == 0 ? 0 : TX;
+    // ..f: towards the first curl's neighbour (y + SG), ..b: the opposite side (signed offsets)
+    const int tyf = REV ? 0 : TY - 1, tyb = REV ? TY - 1 : 0;
+    const int eyf = ty == tyf ? 0 : SG * EY, eyb = ty == tyb ? 0 : -SG * EY;
+    const int hyf = ty == tyf ? 0 : SG * TX, hyb = ty == tyb ? 0 : -SG * TX;
 
     const int64_t Nxy = (int64_t)Nx * Ny;
+    const int64_t dN = SG * Nxy;                  // material stride to the next plane of the march
     const int64_t mcell = (int64_t)cj * Nx + ci;  // in-plane index into the ghosted material arrays
 
     // E(k) own, H(k-1) own, G state
@@ -293,7 +300,7 @@ __global__ void __launch_bounds__(TX *TY, (TX * TY <= 256 ? 2 : 1)) apply_tiled_
     // q of the plane whose H comes next is kept one phase ahead in registers
     double2 qc0 = c_zero(), qc1 = c_zero(), qc2 = c_zero();
     if (HAS_Q) {
-        const int64_t mk = (int64_t)kc0 * Nxy + mcell;          // ghosted index of plane kc0-1
+        const int64_t mk = (int64_t)(kof(0) + 1) * Nxy + mcell;   // ghosted index of the first plane of the march
         qc0 = ldg2(&p.q[0][mk]);
         qc1 = ldg2(&p.q[1][mk]);
         qc2 = ldg2(&p.q[2][mk]);
@@ -303,9 +310,9 @@ __global__ void __launch_bounds__(TX *TY, (TX * TY <= 256 ? 2 : 1)) apply_tiled_
     // (-20 % instructions per plane; measured +3 % for the diagonal kernel, -2 % for the register-bound full tensor)
 #pragma unroll(HAS_OFF ? 1 : 2)
     for (int n = 0; n + 1 < nplanes; ++n) {
-        const int k = kc0 - 1 + n;                              // local plane whose H is computed (and y, if n >= 1)
+        const int k = kof(n);                                   // local plane whose H is computed (and y, if n >= 1)
         const double2 *es = ering + (n % NST) * STAGE;          // plane k
-        const double2 *en = ering + ((n + 1) % NST) * STAGE;    // plane k+1
+        const double2 *en = ering + ((n + 1) % NST) * STAGE;    // plane k+SG
         const bool do_out = out_ok && (n >= 1);
         const int64_t mk = (int64_t)(k + 1) * Nxy + mcell;      // ghosted material index of plane k
 
@@ -320,28 +327,29 @@ __global__ void __launch_bounds__(TX *TY, (TX * TY <= 256 ? 2 : 1)) apply_tiled_
         }
         // L2 prefetch of the material two iterations ahead, bounded by what this chunk will consume
         if (p.has_mass && n + 3 < nplanes) {
-            prefetch_l2(&p.md[0][mk + 2 * Nxy]);
-            prefetch_l2(&p.md[1][mk + 2 * Nxy]);
-            prefetch_l2(&p.md[2][mk + 2 * Nxy]);
+            prefetch_l2(&p.md[0][mk + 2 * dN]);
+            prefetch_l2(&p.md[1][mk + 2 * dN]);
+            prefetch_l2(&p.md[2][mk + 2 * dN]);
         }
         // Off-diagonal material exists only at material interfaces: a per-(tile, plane) occupancy mask (CTA-uniform)
         // lets the kernel skip the six off-diagonal streams and the corner terms on empty blocks (exact zeros).
-        const bool hasn = HAS_OFF && (tp.offmask == nullptr || __ldg(&tp.offmask[(int64_t)(k + 2) * ntile + tile]) != 0);
+        const bool hasn =
+            HAS_OFF && (tp.offmask == nullptr || __ldg(&tp.offmask[(int64_t)(k + SG + 1) * ntile + tile]) != 0);
         if (HAS_OFF && n + 3 < nplanes &&
-            (tp.offmask == nullptr || __ldg(&tp.offmask[(int64_t)(k + 4) * ntile + tile]) != 0)) {
+            (tp.offmask == nullptr || __ldg(&tp.offmask[(int64_t)(k + 3 * SG + 1) * ntile + tile]) != 0)) {
 #pragma unroll
-            for (int e = 0; e < 6; ++e) prefetch_l2(&p.mo[e][mk + 3 * Nxy]);
+            for (int e = 0; e < 6; ++e) prefetch_l2(&p.mo[e][mk + 3 * dN]);
         }
         if (HAS_Q && n + 4 < nplanes) {
-            prefetch_l2(&p.q[0][mk + 3 * Nxy]);
-            prefetch_l2(&p.q[1][mk + 3 * Nxy]);
-            prefetch_l2(&p.q[2][mk + 3 * Nxy]);
+            prefetch_l2(&p.q[0][mk + 3 * dN]);
+            prefetch_l2(&p.q[1][mk + 3 * dN]);
+            prefetch_l2(&p.q[2][mk + 3 * dN]);
         }
 
         mbar_wait(&bars[(n + 1) % NST], ((n + 1) / NST) & 1);
         const double2 En0 = en[eo], En1 = en[eo + EC], En2 = en[eo + 2 * EC];
-        const double2 Exp1 = es[eo + EC + EX], Exp2 = es[eo + 2 * EC + EX];       // E_y, E_z at x+1
-        const double2 Eyp0 = es[eo + eyp], Eyp2 = es[eo + 2 * EC + eyp];            // E_x, E_z at y+1
+        const double2 Exp1 = es[eo + EC + SG * EX], Exp2 = es[eo + 2 * EC + SG * EX];   // E_y, E_z at x+SG
+        const double2 Eyp0 = es[eo + eyf], Eyp2 = es[eo + 2 * EC + eyf];                // E_x, E_z at y+SG
         const double2 a0x = cxs[0 * TX + tx], a1x = cxs[1 * TX + tx];
         const double2 a0y = cys[0 * TY + ty], a1y = cys[1 * TY + ty];
         const double2 a0z = czs[0 * LZP + n], a1z = czs[1 * LZP + n];
@@ -380,9 +388,9 @@ __global__ void __launch_bounds__(TX *TY, (TX * TY <= 256 ? 2 : 1)) apply_tiled_
         if (n >= 2 && wid == store_warp(n - 1)) issue_store(n - 1);
 
         if (HAS_Q && n + 2 < nplanes) {
-            qc0 = ldg2(&p.q[0][mk + Nxy]);
-            qc1 = ldg2(&p.q[1][mk + Nxy]);
-            qc2 = ldg2(&p.q[2][mk + Nxy]);
+            qc0 = ldg2(&p.q[0][mk + dN]);
+            qc1 = ldg2(&p.q[1][mk + dN]);
+            qc2 = ldg2(&p.q[2][mk + dN]);
         }
 
         // full-tensor kernel: issue this phase's material loads first (L2 hits), then do work that does not
@@ -390,7 +398,7 @@ __global__ void __launch_bounds__(TX *TY, (TX * TY <= 256 ? 2 : 1)) apply_tiled_
         double2 o01 = c_zero(), o02 = c_zero(), o10 = c_zero(), o12 = c_zero(), o20 = c_zero(), o21 = c_zero();
         if (HAS_OFF) {
             if (hasn) {
-                const int64_t mk1 = mk + Nxy;                   // plane k+1
+                const int64_t mk1 = mk + dN;                    // plane k+SG
                 o01 = ldg2(&p.mo[0][mk1]); o02 = ldg2(&p.mo[1][mk1]);
                 o10 = ldg2(&p.mo[2][mk1]); o12 = ldg2(&p.mo[3][mk1]);
                 o20 = ldg2(&p.mo[4][mk1]); o21 = ldg2(&p.mo[5][mk1]);
@@ -407,9 +415,9 @@ __global__ void __launch_bounds__(TX *TY, (TX * TY <= 256 ? 2 : 1)) apply_tiled_
             const double2 b0x = cxs[2 * TX + tx], b1x = cxs[3 * TX + tx];
             const double2 b0y = cys[2 * TY + ty], b1y = cys[3 * TY + ty];
             const double2 b0z = czs[2 * LZP + n], b1z = czs[3 * LZP + n];
-            const double2 Hy_xm = hb[ho + NT - 1], Hz_xm = hb[ho + 2 * NT - 1];       // H_y, H_z at x-1
-            const double2 Hx_ym = hb[ho - hym], Hz_ym = hb[ho + 2 * NT - hym];          // H_x, H_z at y-1
-            // y = C2 H :  yx = Dy Hz - Dz Hy,  yy = Dz Hx - Dx Hz,  yz = Dx Hy - Dy Hx   (backward differences)
+            const double2 Hy_xm = hb[ho + NT - SG], Hz_xm = hb[ho + 2 * NT - SG];     // H_y, H_z at x-SG
+            const double2 Hx_ym = hb[ho + hyb], Hz_ym = hb[ho + 2 * NT + hyb];          // H_x, H_z at y-SG
+            // y = C2 H :  yx = Dy Hz - Dz Hy,  yy = Dz Hx - Dx Hz,  yz = Dx Hy - Dy Hx   (differences towards -SG)
             yx = c_mul(b0y, Hz);
             yx = c_fma(b1y, Hz_ym, yx);
             yx = c_fms(b0z, Hy, yx);
@@ -424,12 +432,12 @@ __global__ void __launch_bounds__(TX *TY, (TX * TY <= 256 ? 2 : 1)) apply_tiled_
             yz = c_fms(b1y, Hx_ym, yz);
         }
 
-        double2 Gz1 = c_zero();                                 // G_z(k+1) own
+        double2 Gz1 = c_zero();                                 // G_z(k+SG) own
         if (HAS_OFF && hasn) {
-            // G(k+1) at this corner: in-averages of plane k+1 (still resident in the ring), then the off-diagonal
+            // G(k+SG) at this corner: in-averages of plane k+SG (still resident in the ring), then the off-diagonal
             // material entries; G_x, G_y go to the buffer the NEXT iteration reads after its barrier
-            const double2 Ax = c_fma(cxs[5 * TX + tx], en[eo - EX], c_mul(cxs[4 * TX + tx], En0));
-            const double2 Ay = c_fma(cys[5 * TY + ty], en[eo + EC - eym], c_mul(cys[4 * TY + ty], En1));
+            const double2 Ax = c_fma(cxs[5 * TX + tx], en[eo - SG * EX], c_mul(cxs[4 * TX + tx], En0));
+            const double2 Ay = c_fma(cys[5 * TY + ty], en[eo + EC + eyb], c_mul(cys[4 * TY + ty], En1));
             const double2 Az = c_fma(czs[5 * LZP + n + 1], Eo2, c_mul(czs[4 * LZP + n + 1], En2));
             double2 *gn = gbuf + ((n + 1) & 1) * GST;
             gn[ho] = c_fma(o02, Az, c_mul(o01, Ay));
@@ -446,9 +454,9 @@ __global__ void __launch_bounds__(TX *TY, (TX * TY <= 256 ? 2 : 1)) apply_tiled_
                     // G(k): own values and neighbours were written in the previous iteration
                     const double2 *gc = gbuf + (n & 1) * GST;
                     yx = c_fma(cxs[6 * TX + tx], gc[ho], yx);
-                    yx = c_fma(cxs[7 * TX + tx], gc[ho + 1], yx);
+                    yx = c_fma(cxs[7 * TX + tx], gc[ho + SG], yx);
                     yy = c_fma(cys[6 * TY + ty], gc[ho + NT], yy);
-                    yy = c_fma(cys[7 * TY + ty], gc[ho + NT + hyp], yy);
+                    yy = c_fma(cys[7 * TY + ty], gc[ho + NT + hyf], yy);
                 }
                 if (HAS_OFF && (hasc || hasn)) {
                     yz = c_fma(czs[6 * LZP + n], Gcz, yz);
@@ -551,9 +559,9 @@ size_t tiled_smem_bytes() {
                sizeof(double2) + NST * 8 + 128;
 }
 
-template <bool CMPFIRST, bool HAS_OFF, bool HAS_Q, int TX, int TY, bool DOT>
+template <bool CMPFIRST, bool HAS_OFF, bool HAS_Q, int TX, int TY, bool DOT, bool REV>
 cudaError_t launch_variant(const TiledParams &tp, cudaStream_t s) {
-    auto kern = apply_tiled_kernel<CMPFIRST, HAS_OFF, HAS_Q, TX, TY, DOT>;
+    auto kern = apply_tiled_kernel<CMPFIRST, HAS_OFF, HAS_Q, TX, TY, DOT, REV>;
     const size_t smem = tiled_smem_bytes<CMPFIRST, HAS_OFF, HAS_Q, TX, TY>();
     static bool attr_set[64] = {};   // per device: the opt-in to > 48 KB dynamic shared memory is a per-device attribute
     int dev = 0;
@@ -571,8 +579,9 @@ cudaError_t launch_variant(const TiledParams &tp, cudaStream_t s) {
 
 }  // namespace
 
+// the two uniform arrangements; mixed boundft (first curl forward on some axes only) runs on the general kernel
 bool tiled_supported(const ApplyParams &p) {
-    return p.s1[0] == 1 && p.s1[1] == 1 && p.s1[2] == 1 && p.nzl >= 1;
+    return p.s1[0] == p.s1[1] && p.s1[1] == p.s1[2] && (p.s1[0] == 1 || p.s1[0] == -1) && p.nzl >= 1;
 }
 
 // Pick the z-chunk length: enough CTAs to fill 148 SMs for several waves, little ring-prologue overhead.
@@ -612,7 +621,12 @@ static cudaError_t launch_tile(const ApplyParams &p, int kl_begin, int kl_end, c
     tp.offmask = (p.offmask && p.offmask_ty == TY) ? p.offmask : nullptr;
     const bool cf = tp.a.cmpfirst != 0, off = p.has_off != 0 && p.has_mass != 0 && !diag_only, q = p.has_q != 0;
     cudaError_t e;
-#define V(CF, OFF, Q) e = (p.dot_mode == 2) ? launch_variant<CF, OFF, Q, TX, TY, true>(tp, s) : launch_variant<CF, OFF, Q, TX, TY, false>(tp, s)
+    const bool rev = p.s1[0] < 0;
+#define V(CF, OFF, Q)                                                                                          \
+    e = (p.dot_mode == 2) ? (rev ? launch_variant<CF, OFF, Q, TX, TY, true, true>(tp, s)                       \
+                                 : launch_variant<CF, OFF, Q, TX, TY, true, false>(tp, s))                     \
+                          : (rev ? launch_variant<CF, OFF, Q, TX, TY, false, true>(tp, s)                      \
+                                 : launch_variant<CF, OFF, Q, TX, TY, false, false>(tp, s))
     if (cf) {
         if (off) { if (q) V(true, true, true); else V(true, true, false); }
         else     { if (q) V(true, false, true); else V(true, false, false); }
@@ -667,6 +681,7 @@ cudaError_t tiled_build_offmask(const ApplyParams &p, unsigned char **mask, int 
     *corr_list = nullptr;
     *corr_count = 0;
     if (!tiled_supported(p) || !p.has_off || !p.has_mass) return cudaSuccess;
+    const int sg = p.s1[0] < 0 ? -1 : 1;
     int TY = env_ty() ? env_ty() : 8;
     std::vector<unsigned char> h;
     cudaError_t e = build_mask_for(p, TY, mask, frac, s, &h);
@@ -680,12 +695,12 @@ cudaError_t tiled_build_offmask(const ApplyParams &p, unsigned char **mask, int 
     *ty_used = TY;
     if (TY == 8) {
         // work items of the correction pass: per tile, runs [ks,ke) of consecutive output planes whose corner terms
-        // G(k) / G(k+1) can be non-zero.  A run of L planes costs L+1 corner evaluations but is a serial march, so
+        // G(k) / G(k+s1) can be non-zero.  A run of L planes costs L+1 corner evaluations but is a serial march, so
         // the cut length adapts to the amount of flagged work: enough CTAs for several waves first, longer runs
         // (less redundancy) only when there is plenty of work.
         const int ntx = (p.Nx + 29) / 30, nty = (p.Ny + 5) / 6;
         const size_t nt = (size_t)ntx * nty;
-        auto flagged = [&](size_t t, int k) { return (h[(size_t)(k + 1) * nt + t] | h[(size_t)(k + 2) * nt + t]) != 0; };
+        auto flagged = [&](size_t t, int k) { return (h[(size_t)(k + 1) * nt + t] | h[(size_t)(k + 1 + sg) * nt + t]) != 0; };
         size_t nblocks = 0;
         for (size_t t = 0; t < nt; ++t)
             for (int k = 0; k < p.nzl; ++k) nblocks += flagged(t, k);

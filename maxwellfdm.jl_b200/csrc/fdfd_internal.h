@@ -98,7 +98,7 @@ struct Ctx {
     cplx phase[3] = {1.0, 1.0, 1.0};
     cplx omega = 0.0;
     bool have_coeffs = false, have_eps = false, have_omega = false;
-    bool eps_off = false, have_mu = false;
+    bool eps_off = false, have_mu = false, mu_off = false;
     std::vector<cplx> eps_host;  // local slab, Julia layout (kept for re-scaling by omega and export)
     std::vector<cplx> mu_host;
 

@@ -126,7 +126,7 @@ int export_pattern(Ctx *c, int64_t *colptr, int64_t *rowval, fdfd_c128 *nzval, i
     ex.mid = ee ? &c->mu_host : &c->eps_host;
     if (ex.has_mass && ee && !c->have_eps) return set_err(c, FDFD_ESTATE, "fdfd_set_eps has not been called");
     if (!ee && !c->have_eps) return set_err(c, FDFD_ESTATE, "FT_HH needs fdfd_set_eps");
-    ex.has_off = ex.has_mass && ee && c->eps_off;
+    ex.has_off = ex.has_mass && (ee ? c->eps_off : c->mu_off);
     const int64_t n = 3 * ex.M;
     const bool fill = colptr && rowval;
     std::vector<int64_t> counts;

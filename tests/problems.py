@@ -23,7 +23,7 @@ class Problem:
 
     def __init__(self, N, isbloch=(True, True, True), boundft=(EE, EE, EE), full_eps=False, with_mu=False,
                  ft=EE, omega=1.1 - 0.05j, npml=1, uniform=False, seed=SEED, cmpfirst=True, weighted_out=False,
-                 kb_scale=1.0):
+                 kb_scale=1.0, full_mu=False):
         rng = np.random.default_rng(seed)
         self.N = tuple(int(n) for n in N)
         self.isbloch = tuple(bool(b) for b in isbloch)
@@ -46,7 +46,10 @@ class Problem:
         if full_eps:
             for v, u in itertools.permutations(range(3), 2):
                 self.eps[..., v, u] = 0.3 * crandn(rng, *self.N)
-        self.with_mu, self.full_eps = with_mu, full_eps
+        if full_mu:   # only meaningful for ft == HH (mu is the mass parameter there, model.jl:238-240)
+            for v, u in itertools.permutations(range(3), 2):
+                self.mu[..., v, u] = 0.25 * crandn(rng, *self.N)
+        self.with_mu, self.full_eps = with_mu or full_mu, full_eps
         self.n = 3 * int(np.prod(self.N))
         self.rng = rng
 

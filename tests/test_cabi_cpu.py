@@ -108,6 +108,9 @@ def test_export_pattern_variants():
     _check_export(Problem((4, 3, 5), (False, True, True), full_eps=True, weighted_out=True))
     _check_export(Problem((4, 3, 5), (True, False, True), with_mu=True, ft=HH))
     _check_export(Problem((4, 3, 5), (True, True, False), (HH, EE, HH), with_mu=True, ft=HH, cmpfirst=False))
+    # HH formulation with a full 3x3 mu tensor as the mass parameter (model.jl:238-240)
+    _check_export(Problem((4, 3, 5), (False, True, True), ft=HH, full_mu=True))
+    _check_export(Problem((3, 4, 2), (True, False, False), (HH, HH, EE), ft=HH, full_mu=True, weighted_out=True))
     # exact zeros are dropped when w != 0 (symmetry boundaries on a uniform grid)
     p = Problem((5, 6, 7), (False,) * 3, uniform=True, npml=0, omega=1.0)
     A, _ = p.oracle_csc()

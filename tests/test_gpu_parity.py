@@ -68,16 +68,94 @@ def test_apply_all_boundary_conditions(kernel, N):
 
 @pytest.mark.parametrize("boundft", list(itertools.product([EE, HH], repeat=3)))
 def test_apply_all_boundft(boundft):
-    """all 2^3 boundft choices (general kernel; the tiled kernel covers the default all-EE arrangement)."""
+    """all 2^3 boundft choices (tiled kernel for the two uniform arrangements, general kernel for mixed ones)."""
     for isbloch in ((True, False, True), (False, True, False)):
         for ft in (EE, HH):
-            p = Problem((9, 6, 7), isbloch, boundft, full_eps=(ft == EE), with_mu=True, ft=ft)
+            p = Problem((9, 6, 7), isbloch, boundft, full_eps=(ft == EE), with_mu=True, ft=ft, full_mu=(ft == HH))
             A_ref, _ = p.oracle_csc()
             A = p.operator(device=0)
             x = p.random_x()
             err = rel(_apply_dev(A, x), A_ref.matvec(x))
             A.close()
             assert err < TOL, (boundft, isbloch, ft, err)
+
+
+MIRRORED = (  # (ft, boundft, full_eps, with_mu): first curl backward on every axis
+    (HH, (EE, EE, EE), False, True),     # A = Ce eps^-1 Cm - w^2 mu (model.jl:238-240), default boundft
+    (HH, (EE, EE, EE), False, "full"),   # ... with a full 3x3 mu tensor as the mass parameter
+    (EE, (HH, HH, HH), True, True),      # EE formulation on the dual arrangement, full tensor
+    (EE, (HH, HH, HH), False, False),
+)
+
+
+@pytest.mark.parametrize("N", [(1, 1, 1), (2, 1, 3), (5, 3, 2), (31, 15, 4), (33, 17, 9), (70, 45, 6)])
+def test_mirrored_arrangement_on_tiled_kernel(N):
+    """N3 row: the HH formulation / boundft all-HH run on the mirrored variant of the tiled kernel (REV): every
+    Bloch/symmetry combination, both layouts, forward and transposed."""
+    for isbloch in itertools.product([True, False], repeat=3):
+        for ft, boundft, full_eps, with_mu in MIRRORED:
+            cmpfirst = not (isbloch[0] ^ isbloch[2])      # alternate the layout over the combinations
+            p = Problem(N, isbloch, boundft, full_eps=full_eps, with_mu=bool(with_mu), ft=ft, cmpfirst=cmpfirst,
+                        full_mu=(with_mu == "full"))
+            A_ref, _ = p.oracle_csc()
+            A = p.operator(device=0, kernel=KERNELS["tiled"])
+            x = p.random_x()
+            err = rel(_apply_dev(A, x), A_ref.matvec(x))
+            errT = rel(_apply_dev(A, x, transpose=True), A_ref.to_scipy().T.tocsc() @ x)
+            A.close()
+            assert err < TOL and errT < TOL, (N, isbloch, ft, boundft, full_eps, cmpfirst, err, errT)
+
+
+def test_mirrored_arrangement_deep_grid_and_sparse_offdiag():
+    """several z-chunks per tile column (downward march), off-diagonal eps on part of the grid only (occupancy-mask
+    path of the fused kernel), against the matrix-free oracle; tiled == general kernel."""
+    torch = _torch()
+    # z1 = 47: > 25 % of the (tile, plane) blocks flagged -> fused full-tensor kernel with the mask;
+    # z1 = 33: sparse -> diagonal kernel + mirrored marching correction kernel
+    for isbloch, z1, lo, hi in (((False, False, False), 47, 0.25, 0.6), ((True, False, True), 33, 0.0, 0.25)):
+        p = Problem((70, 45, 90), isbloch, (HH, HH, HH), full_eps=True, with_mu=True)
+        for v, u in itertools.permutations(range(3), 2):
+            p.eps[:, :, :20, v, u] = 0
+            p.eps[:, :, z1:, v, u] = 0
+            p.eps[:25, :, :, v, u] = 0
+        mf = p.oracle_matfree()
+        x = p.random_x()
+        At = p.operator(device=0, kernel=KERNELS["tiled"])
+        An = p.operator(device=0, kernel=KERNELS["naive"])
+        assert lo < At.offdiag_fraction < hi
+        yt, yn = _apply_dev(At, x), _apply_dev(An, x)
+        assert rel(yt, yn) < 1e-13
+        assert rel(yt, mf(x)) < TOL
+        At.close()
+        An.close()
+    p = Problem((40, 33, 70), (False, True, False), ft=HH, with_mu=True)
+    A = p.operator(device=0, kernel=KERNELS["tiled"])
+    x = p.random_x()
+    assert rel(_apply_dev(A, x), p.oracle_matfree()(x)) < TOL
+    A.close()
+
+
+@pytest.mark.parametrize("method", ["bicgstab", "qmr"])
+def test_solve_hh_formulation(method):
+    """HH formulation end to end (fused-dot epilogue of the mirrored kernel inside BiCGSTAB): PML box, magnetic
+    dipole; field vs sparse direct solve of the oracle matrix."""
+    import scipy.sparse.linalg as spla
+    fb = _fb()
+    grid, (sdl_e, sdl_m, sei, smi), omega, eps, mu = _pml_box()
+    ph = np.ones(3, complex)
+    Ce, Cm = op.create_curls(sei, smi, (EE,) * 3, grid.isbloch, ph)
+    Pe, Pm = op.create_paramops(eps, mu, sdl_e, sdl_m, sei, smi, (EE,) * 3, grid.isbloch, ph)
+    A_ref = op.create_A(HH, omega, Pe, Pm, Ce, Cm)
+    b = np.zeros(A_ref.shape[0], complex)
+    n = grid.N[0]
+    b[2 + 3 * ((n // 2) + n * ((n // 2) + n * (n // 2)))] = 1.0    # z-directed magnetic dipole at the centre
+    h_ref = spla.splu(A_ref.to_scipy().tocsc()).solve(b)
+    A = fb.FdfdOperator(grid.N, grid.isbloch, sdl_e, sdl_m, omega, eps, None, ph, ft="H", device=0, kernel=KERNELS["tiled"])
+    x, info = A.solve(b, method=method, rtol=1e-10, maxit=20000, check_every=25)
+    assert info["converged"], info
+    assert rel(A_ref.matvec(x), b) < 1e-8
+    assert rel(x, h_ref) < 1e-8 * 50
+    A.close()
 
 
 @pytest.mark.parametrize("kernel", ["tiled", "naive"])
