@@ -106,7 +106,8 @@ static int upload_materials(Ctx *c) {
     const bool mass_given = !mass.empty(), mid_given = !mid.empty();
     const bool has_mass = c->omega != cplx(0.0);
     const bool has_off = has_mass && mass_given && (ee ? c->eps_off : c->mu_off);
-    const int narr = (has_mass ? 3 : 0) + (has_off ? 6 : 0) + (mid_given ? 3 : 0);
+    // an identity mass parameter (mu == 1 of the HH formulation) is a scalar, not three arrays
+    const int narr = (has_mass && mass_given ? 3 : 0) + (has_off ? 6 : 0) + (mid_given ? 3 : 0);
     const size_t bytes = (size_t)narr * Mg * sizeof(double2);
     if (bytes != c->mat_bytes) {
         if (c->mat_dev) cudaFree(c->mat_dev);
@@ -116,6 +117,11 @@ static int upload_materials(Ctx *c) {
     }
     for (int i = 0; i < 3; ++i) c->md[i] = c->q[i] = nullptr;
     for (int i = 0; i < 6; ++i) c->mo[i] = c->mo_t[i] = nullptr;
+    c->has_mass = has_mass;
+    {
+        const cplx w2u = -(c->omega * c->omega);
+        c->md_uniform = make_double2(w2u.real(), w2u.imag());
+    }
     if (!narr) return FDFD_OK;
     double2 *tmp = nullptr;
     FDFD_CUDA(c, cudaMalloc((void **)&tmp, (size_t)M * sizeof(double2)));
@@ -141,8 +147,8 @@ static int upload_materials(Ctx *c) {
         return FDFD_OK;
     };
     int rc = FDFD_OK;
-    if (has_mass)
-        for (int v = 0; v < 3 && rc == FDFD_OK; ++v) rc = build(mass_given ? &mass : nullptr, v, v, 0, c->md[v]);
+    if (has_mass && mass_given)
+        for (int v = 0; v < 3 && rc == FDFD_OK; ++v) rc = build(&mass, v, v, 0, c->md[v]);
     if (has_off && rc == FDFD_OK) {
         int e = 0;
         for (int v = 0; v < 3; ++v)
@@ -218,7 +224,8 @@ void fill_params(Ctx *c, ApplyParams &p, const double2 *x, double2 *y, bool tran
     p.Nx = (int)Nx; p.Ny = (int)Ny; p.nzl = (int)nzl; p.Nz = (int)c->d.N[2]; p.kz0 = (int)c->k0;
     for (int w = 0; w < 3; ++w) { p.s1[w] = c->s1[w]; p.wrap[w] = c->d.isbloch[w] ? 1 : 0; }
     p.cmpfirst = c->d.order_cmpfirst ? 1 : 0;
-    p.has_mass = c->md[0] != nullptr;
+    p.has_mass = c->has_mass ? 1 : 0;
+    p.md_uniform = c->md_uniform;
     p.has_off = c->mo[0] != nullptr;
     p.has_q = c->q[0] != nullptr;
     p.c = transpose ? c->ct : c->cf;

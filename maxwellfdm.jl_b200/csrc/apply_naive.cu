@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(128) apply_naive_kernel(const __grid_constant_
         y = c_fms(p.c.b0[w2][i2], g.H(u2, i, j, kl), y);
         y = c_fms(p.c.b1[w2][i2], g.Hsh(u2, i, j, kl, w2, -p.s1[w2]), y);
         if (p.has_mass) {
-            y = c_fma(p.md[v][g.gidx(i, j, kl)], g.E(v, i, j, kl), y);
+            y = c_fma(p.md[v] ? p.md[v][g.gidx(i, j, kl)] : p.md_uniform, g.E(v, i, j, kl), y);
             if (p.has_off) {
                 const int iv = g.cidx(v, i, j, kl);
                 y = c_fma(p.c.mo0[v][iv], g.G(v, i, j, kl), y);
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(128) curl2_kernel(const __grid_constant__ Appl
             y = c_mul(beta, t);
         }
         if (je) y = c_fma(gamma, je[o], y);
-        if (divide_by_md) y = c_div(y, p.md[v][g.gidx(i, j, kl)]);   // e_from_h: divide by -w^2 eps_vv
+        if (divide_by_md) y = c_div(y, p.md[v] ? p.md[v][g.gidx(i, j, kl)] : p.md_uniform);   // e_from_h: divide by -w^2 eps_vv
         p.y[o] = y;
     }
 }

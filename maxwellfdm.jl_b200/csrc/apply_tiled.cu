@@ -320,13 +320,20 @@ __global__ void __launch_bounds__(TX *TY, (TX * TY <= 256 ? 2 : 1)) apply_tiled_
         // into L2 two iterations ago by the prefetch below).  The full-tensor kernel is register-bound, so it
         // loads its material after the barrier instead (see below).
         double2 mdc0 = c_zero(), mdc1 = c_zero(), mdc2 = c_zero();
+        // identity mass parameter (md = -w^2, no arrays): only the HH formulation with mu == 1 has it, and that always
+        // carries q = 1/eps, so the other instantiations keep their branch-free code
+        const bool md_arrays = !(HAS_Q && !HAS_OFF) || p.md[0] != nullptr;
         if (!HAS_OFF && p.has_mass && do_out) {
-            mdc0 = ldg2(&p.md[0][mk]);
-            mdc1 = ldg2(&p.md[1][mk]);
-            mdc2 = ldg2(&p.md[2][mk]);
+            if (md_arrays) {
+                mdc0 = ldg2(&p.md[0][mk]);
+                mdc1 = ldg2(&p.md[1][mk]);
+                mdc2 = ldg2(&p.md[2][mk]);
+            } else {
+                mdc0 = mdc1 = mdc2 = p.md_uniform;
+            }
         }
         // L2 prefetch of the material two iterations ahead, bounded by what this chunk will consume
-        if (p.has_mass && n + 3 < nplanes) {
+        if (p.has_mass && md_arrays && n + 3 < nplanes) {
             prefetch_l2(&p.md[0][mk + 2 * dN]);
             prefetch_l2(&p.md[1][mk + 2 * dN]);
             prefetch_l2(&p.md[2][mk + 2 * dN]);
@@ -730,6 +737,7 @@ cudaError_t tiled_build_offmask(const ApplyParams &p, unsigned char **mask, int 
 
 cudaError_t launch_apply_tiled(const ApplyParams &p, int kl_begin, int kl_end, cudaStream_t s, int *nlaunch) {
     if (!tiled_supported(p)) return cudaErrorNotSupported;
+    if (p.has_mass && !p.md[0] && !p.has_q) return cudaErrorInvalidValue;   // scalar mass is compiled into the q variants only
     if (kl_end <= kl_begin) return cudaSuccess;
     const bool full = p.has_off != 0 && p.has_mass != 0;
     cudaError_t e;

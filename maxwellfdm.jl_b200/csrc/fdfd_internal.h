@@ -55,7 +55,8 @@ struct ApplyParams {
     CoefDev c;
     // material arrays, SoA, ghosted in z: plane index kl+1, i.e. element (kl,j,i) at
     // [(kl+1)*Nx*Ny + j*Nx + i]
-    const double2 *md[3];   // -w^2 * P_vv
+    const double2 *md[3];   // -w^2 * P_vv (null when the mass parameter is the identity: md_uniform = -w^2)
+    double2 md_uniform;
     const double2 *mo[6];   // -w^2 * P_vu, order (0,1),(0,2),(1,0),(1,2),(2,0),(2,1)
     const double2 *q[3];    // inverse of the middle diagonal parameter (mu^-1 for FT_EE)
     PlaneSet x;
@@ -110,6 +111,8 @@ struct Ctx {
     double2 *mat_dev = nullptr;      // md[3], mo[6], q[3] ghosted slabs
     size_t mat_bytes = 0;
     const double2 *md[3]{}, *mo[6]{}, *mo_t[6]{}, *q[3]{};
+    bool has_mass = false;           // omega != 0
+    double2 md_uniform{};            // -w^2, used when the mass parameter was not supplied (identity)
     unsigned char *offmask = nullptr;  // device, (nzl+2) x ntiles
     int offmask_ty = 0;
     int4 *corr_list = nullptr;         // device list of (tile, ks, ke) runs for the correction pass
