@@ -230,13 +230,17 @@ def test_export_pattern_on_gpu_handle_is_bit_exact():
 
 
 def test_config_shapes_against_oracle():
-    """BASELINE configs: C1 (40^3, CSC oracle) and reduced C2 / C3 (matrix-free oracle), real inputs."""
+    """BASELINE configs: C1 (40^3, CSC oracle) and reduced C2 / C3 / C4 / C5 (matrix-free oracle), real inputs."""
     import workloads
     from oracle.matfree import MatFreeOperator
     rng = np.random.default_rng(SEED)
-    for w in (workloads.c1_vacuum_box(), workloads.c2_waveguide((72, 60, 40)), workloads.c3_phc_slab((64, 64, 40))):
+    for w in (workloads.c1_vacuum_box(), workloads.c2_waveguide((72, 60, 40)), workloads.c3_phc_slab((64, 64, 40)),
+              workloads.c4_scatterer((48, 48, 48), radius_cells=12), workloads.c5_metalens((64, 64, 96))):
         A = workloads.make_operator(w, device=0)
-        mf = MatFreeOperator(EE, w["omega"], w["eps"], None, w["sdl_e"], w["sdl_m"], (EE,) * 3, w["isbloch"], w["e_mikL"])
+        eps = w["eps"]
+        if w.get("julia_layout"):       # [u,v,k,j,i] (the memory of Julia's (Nx,Ny,Nz,3,3) array) -> [i,j,k,v,u]
+            eps = np.ascontiguousarray(np.transpose(eps, (4, 3, 2, 1, 0)))
+        mf = MatFreeOperator(EE, w["omega"], eps, None, w["sdl_e"], w["sdl_m"], (EE,) * 3, w["isbloch"], w["e_mikL"])
         x = crandn(rng, A.n)
         err = rel(_apply_dev(A, x), mf(x))
         A.close()

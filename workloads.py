@@ -201,8 +201,60 @@ def c4_scatterer(N=(512, 512, 512), k0=0, k1=None, seed=20261017, delta=20.0, ra
         pert[shell] = 0.2 * (rng.random(int(shell.sum())) - 0.5)
         eps[u, v] = pert
         eps[v, u] = pert
-    w.update(eps=eps, k0=k0, k1=k1, full_eps=True,
+    w.update(eps=eps, k0=k0, k1=k1, full_eps=True, julia_layout=True,
              name=f"C4 dielectric sphere {Nx}x{Ny}x{Nz}, full 3x3 eps on the surface, 10-cell PML")
+    return w
+
+
+def c5_metalens(N=(1024, 1024, 96), k0=0, k1=None, seed=7, delta=20.0, pitch_cells=32):
+    """C5 (weak-scaling unit: 96 z-planes per GPU, global Nz = 96 * n_gpus): metalens - eps 6.0 pillars with random
+    radii (seed 7) on an eps 2.1 substrate, Bloch-periodic in x,y with k = 0, 10-cell PML in z.  Substrate = lower
+    third of the global z range, pillars = the next 32 cells, air above.  Planar interfaces smooth to diagonal
+    tensors; the pillar walls carry the seeded symmetric off-diagonal perturbation (Kottke stand-in).  Built in
+    Julia memory order ([u,v,k,j,i]) so the 14.5 GB slab array needs no transposing copy."""
+    Nx, Ny, Nz = N
+    w = _common(N, delta, (True, True, False), ((0, 0, 10), (0, 0, 10)))
+    k1 = Nz if k1 is None else k1
+    g = w["grid"]
+    a = pitch_cells * delta
+    npx, npy = Nx // pitch_cells, Ny // pitch_cells
+    radii = (6.0 + 7.0 * np.random.default_rng(seed).random((npx, npy))) * delta      # 6..13 cells
+    Lx, Ly = Nx * delta, Ny * delta
+    z0 = g.lg_prim[2][0]
+    z_sub = z0 + (Nz // 3) * delta                    # substrate top
+    z_top = z_sub + 32 * delta                        # pillar top
+
+    def pillar(x, y):                                 # (signed distance to the wall, in-plane), shape (Ny, Nx)
+        ix = np.minimum(((x + Lx / 2) // a).astype(int), npx - 1)
+        iy = np.minimum(((y + Ly / 2) // a).astype(int), npy - 1)
+        X = (x + Lx / 2) % a - a / 2
+        Y = (y + Ly / 2) % a - a / 2
+        return radii[ix[None, :], iy[:, None]] - np.sqrt(X[None, :] ** 2 + Y[:, None] ** 2)
+
+    def slab_fill(z, lo, hi):                         # fraction of the cell [z-d/2, z+d/2] inside [lo, hi]
+        return np.clip(np.minimum(z + delta / 2, hi) - np.maximum(z - delta / 2, lo), 0.0, delta) / delta
+
+    eps = np.zeros((3, 3, k1 - k0, Ny, Nx), np.complex128)
+    xp, xd = g.l[fb.PRIM][0], g.l[fb.DUAL][0]
+    yp, yd = g.l[fb.PRIM][1], g.l[fb.DUAL][1]
+    zp, zd = g.l[fb.PRIM][2][k0:k1], g.l[fb.DUAL][2][k0:k1]
+    for v, (xx, yy, zz) in enumerate(((xd, yp, zp), (xp, yd, zp), (xp, yp, zd))):
+        fxy = np.clip(pillar(xx, yy) / delta + 0.5, 0.0, 1.0)
+        fsub = slab_fill(zz, -1e30, z_sub)
+        fpil = slab_fill(zz, z_sub, z_top)
+        eps[v, v] = 1.0 + 1.1 * fsub[:, None, None] + 5.0 * fpil[:, None, None] * fxy[None, :, :]
+    wall_xy = np.abs(pillar(xp, yp)) < delta
+    in_z = slab_fill(zp, z_sub, z_top) > 0
+    rng = np.random.default_rng(seed + 1000 * k0 + 1)
+    nwall = int(wall_xy.sum())
+    for (v, u) in ((0, 1), (0, 2), (1, 2)):
+        for kk in np.nonzero(in_z)[0]:
+            pert = np.zeros((Ny, Nx))
+            pert[wall_xy] = 0.2 * (rng.random(nwall) - 0.5)
+            eps[u, v, kk] = pert
+            eps[v, u, kk] = pert
+    w.update(eps=eps, k0=k0, k1=k1, full_eps=True, julia_layout=True,
+             name=f"C5 metalens {Nx}x{Ny}x{Nz} (96 planes per GPU), Bloch x/y, PML z, full 3x3 eps on pillar walls")
     return w
 
 
