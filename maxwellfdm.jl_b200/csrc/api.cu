@@ -383,7 +383,8 @@ static bool can_pipeline(Ctx *c) {
 
 static int apply_host_pipelined(Ctx *c, const double2 *xh, double2 *yh, bool transpose) {
     const int64_t nzl = c->k1 - c->k0, pl = c->plane;
-    const int S = (int)std::min<int64_t>(16, nzl / 4);
+    static const int s_env = [] { const char *e = getenv("FDFD_PIPE_SLABS"); return e ? atoi(e) : 0; }();
+    const int S = (int)std::max<int64_t>(1, std::min<int64_t>(s_env > 0 ? s_env : 16, nzl / 2));
     if (!c->stream_d2h) FDFD_CUDA(c, cudaStreamCreateWithFlags(&c->stream_d2h, cudaStreamNonBlocking));
     while ((int)c->ev_h2d.size() < S + 1) {
         cudaEvent_t e;
