@@ -261,6 +261,13 @@ def main():
     if world > 1:
         dist.all_reduce(tk, op=dist.ReduceOp.MAX)
     it_per_s = args.krylov_iters / (float(tk.item()) * 1e-3)
+    xs.zero_()
+    barrier()
+    ms_q = A.bench_solve(b, xs, "qmr", warmup=2, iters=args.krylov_iters)
+    tq = torch.tensor([ms_q], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tq, op=dist.ReduceOp.MAX)
+    qmr_it_per_s = args.krylov_iters / (float(tq.item()) * 1e-3)
     del b, xs
 
     # ---- end to end through the C ABI with host buffers ------------------------------------------
@@ -313,7 +320,8 @@ def main():
             "gpu_launches": launches, "clocks": clocks,
             "krylov": {"method": "bicgstab", "iters": args.krylov_iters, "iter_per_s": it_per_s,
                        "bytes_per_dof_model": 2 * bpd + 256,
-                       "hbm_frac": (2 * bpd + 256) * (n_tot / world) * it_per_s / 1e9 / peak},
+                       "hbm_frac": (2 * bpd + 256) * (n_tot / world) * it_per_s / 1e9 / peak,
+                       "qmr_iter_per_s": qmr_it_per_s, "qmr_bytes_per_dof_model": 2 * bpd + 304},
         }
         if world == 1 and not args.no_cpu:
             try:

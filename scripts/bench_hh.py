@@ -33,7 +33,10 @@ def main():
         ("EE on boundft all-HH (mirrored kernel), full eps", dict(ft="E", boundft=["H"] * 3), eps_full, True, 0),
         ("EE on boundft all-HH, general kernel", dict(ft="E", boundft=["H"] * 3), eps_full, True, 1),
     )
-    for name, kw, eps, off, kernel in variants:
+    only = int(sys.argv[sys.argv.index("--variant") + 1]) if "--variant" in sys.argv else None
+    for iv, (name, kw, eps, off, kernel) in enumerate(variants):
+        if only is not None and iv != only:
+            continue
         A = fb.FdfdOperator(w["N"], w["isbloch"], w["sdl_e"], w["sdl_m"], w["omega"], eps, None, w["e_mikL"],
                             device=0, kernel=kernel, eps_has_offdiag=off, **kw)
         tot, mn = A.bench_apply(x, y, warmup=5, iters=50)
@@ -42,7 +45,7 @@ def main():
         bpd = 48 + 32 * f
         line = {"variant": name, "gdof_s": n / t / 1e9, "us": t * 1e6, "bytes_per_dof": bpd,
                 "hbm_frac": n * bpd / t / 1e9 / PEAK}
-        if kernel == 0:
+        if kernel == 0 and only is None:
             b = torch.randn(n, 2, device="cuda", dtype=torch.float64, generator=g).view(torch.complex128).reshape(-1)
             xs = torch.zeros_like(b)
             ts = A.bench_solve(b, xs, "bicgstab", warmup=2, iters=40)
