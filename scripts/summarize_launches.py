@@ -29,7 +29,8 @@ def short(n, g):
         return "apply_tiled_kernel<" + (m.group(1) if m else "") + "> " + (
             "[whole slab]" if g > 0.5 * gmax else "[1/16 sub-slab, pipelined host path]")
     for k in ("offdiag_march_kernel", "k_xr", "k_p", "k_s", "k_dot2", "k_dot1", "k_init", "scale_copy_kernel",
-              "build_offmask_kernel", "k_store_hist", "recip_copy_kernel", "fill_kernel"):
+              "build_offmask_kernel", "k_store_hist", "recip_copy_kernel", "fill_kernel", "q_pq", "q_vw", "q_xd", "q_xr",
+              "q_eps", "q_init", "q_resid", "q_store_hist"):
         if k in n:
             return k
     return "torch/other: " + n[:40]
@@ -46,7 +47,13 @@ lines = ["# ncu launch list of: python bench.py --steps 10 --warmup 3 --no-cpu -
          f"{'kernel':92s} {'n':>4s} {'total us':>10s} {'avg us':>9s} {'share':>7s}"]
 for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
     lines.append(f"{k:92s} {len(v):4d} {sum(v) / 1e3:10.1f} {sum(v) / len(v) / 1e3:9.1f} {sum(v) / tot:7.1%}")
-whole = [v for k, v in agg.items() if k.startswith("apply_tiled") and "whole" in k and ", 0>" in k]
+def dot_flag(k):   # template arguments: CMPFIRST, HAS_OFF, HAS_Q, TX, TY, DOT, REV
+    m = re.search(r"<([^>]*)>", k)
+    a = [x.strip() for x in m.group(1).split(",")] if m else []
+    return a[5] if len(a) > 5 else "0"
+
+
+whole = [v for k, v in agg.items() if k.startswith("apply_tiled") and "whole" in k and dot_flag(k) == "0"]
 corr = agg.get("offdiag_march_kernel", [])
 if whole:
     a = sum(whole[0]) / len(whole[0]) / 1e3
@@ -58,7 +65,7 @@ if whole:
         lines.append(f"   bench.py measures {ms_step * 1e3:.1f} us per step with CUDA events (warm, back to back): the dominant "
                      f"kernel's share agrees")
     kk = {k: sum(v) / len(v) / 1e3 for k, v in agg.items() if k in ("k_xr", "k_p", "k_s", "k_dot2", "k_dot1")}
-    fused = [v for k, v in agg.items() if k.startswith("apply_tiled") and "whole" in k and ", 1>" in k]
+    fused = [v for k, v in agg.items() if k.startswith("apply_tiled") and "whole" in k and dot_flag(k) == "1"]
     a2 = sum(fused[0]) / len(fused[0]) / 1e3 if fused else a
     it = (a + c) + (a2 + c) + sum(kk.values())
     lines.append("one BiCGSTAB iteration = apply %.1f us + apply with fused (t,s),(t,t) epilogue %.1f us + " % (a + c, a2 + c) +
