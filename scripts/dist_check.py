@@ -29,6 +29,7 @@ def main():
         k0, k1 = fb.partition(p.N[2], world, rank)
         A = fb.FdfdOperator(p.N, p.isbloch, p.sdl_e, p.sdl_m, p.omega, p.eps[:, :, k0:k1],
                             p.mu[:, :, k0:k1] if p.with_mu else None, p.ph, order_cmpfirst=p.cmpfirst,
+                            boundft=["E" if b == 0 else "H" for b in p.boundft], ft="E" if p.ft == 0 else "H",
                             device=local, rank=rank, nranks=world, **kw)
         uid = [fb.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
@@ -60,6 +61,11 @@ def main():
             cases.append(dict(N=(21, 18, 2 * world + 3), isbloch=isbloch, full_eps=full, with_mu=mu, cmpfirst=cf,
                               kernel=kern))
     cases.append(dict(N=(9, 7, world), isbloch=(True, True, True), full_eps=True, with_mu=True, cmpfirst=True, kernel=0))
+    # mirrored arrangement across slabs: HH formulation (full-tensor mu), EE on boundft all-HH (full eps)
+    for isbloch in ((True, True, True), (False, True, False)):
+        cases.append(dict(N=(21, 18, 2 * world + 3), isbloch=isbloch, ft=1, full_mu=True, kernel=0))
+        cases.append(dict(N=(33, 10, 3 * world + 1), isbloch=isbloch, boundft=(1, 1, 1), full_eps=True, with_mu=True,
+                          kernel=0))
     for cs in cases:
         kern = cs.pop("kernel")
         p = Problem(**cs)

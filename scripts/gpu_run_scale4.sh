@@ -1,9 +1,9 @@
 mkdir -p gpurun_out
 N=$(nvidia-smi -L | wc -l)
-python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29611 scripts/dist_check.py > gpurun_out/dist_check_$N.log 2>&1; echo "dist$N rc=$?"; grep -E "DIST_CHECK" gpurun_out/dist_check_$N.log | head -2 | cut -c1-300
+timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29611 scripts/dist_check.py > gpurun_out/dist_check_$N.log 2>&1; echo "dist$N rc=$?"; grep -E "DIST_CHECK" gpurun_out/dist_check_$N.log | head -2 | cut -c1-300
 for n in 1 2 $N; do
  if [ $n -eq 1 ]; then python bench.py --gpus 1 --steps 100 --warmup 5 --no-cpu > gpurun_out/scale_$n.json 2> gpurun_out/scale_$n.err;
- else python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29612 bench.py --gpus $n --steps 100 --warmup 5 > gpurun_out/scale_$n.json 2> gpurun_out/scale_$n.err; fi
+ else timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29612 bench.py --gpus $n --steps 100 --warmup 5 > gpurun_out/scale_$n.json 2> gpurun_out/scale_$n.err; fi
  tail -1 gpurun_out/scale_$n.json | python -c "
 import sys,json; d=json.loads(sys.stdin.read()); print('N', d['n_gpus'], 'GDOF/s', round(d['value'],2), 'ms', round(d['ms_per_step'],4), 'it/s', round(d['krylov']['iter_per_s'],1), 'e2e', round(d['e2e']['value'],2), 'frac', round(d['roofline']['frac'],3))" || tail -5 gpurun_out/scale_$n.err
 done
