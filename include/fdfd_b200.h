@@ -124,16 +124,18 @@ int fdfd_export_pattern(fdfd_handle h, int64_t *colptr, int64_t *rowval, fdfd_c1
                         int64_t *nnz_inout);
 
 /* Post-processing next to the solve: h = (i/w) mu^-1 (Ce e + jm)  (h_from_e, model.jl:276-279).
- * jm_or_null == NULL means jm = 0. */
+ * jm_or_null == NULL means jm = 0.  Works on handles of either formulation (on an FT_HH handle mu is the
+ * mass parameter and must be diagonal, the `Pmu \` restriction). */
 int fdfd_h_from_e(fdfd_handle h, const fdfd_c128 *e, const fdfd_c128 *jm_or_null, fdfd_c128 *hout, int where);
 /* e = (-i/w) eps^-1 (Cm h - je)  (e_from_h, model.jl:281-284); diagonal eps only (`Peps \` restriction),
- * je_or_null == NULL means je = 0. */
+ * je_or_null == NULL means je = 0.  Either formulation. */
 int fdfd_e_from_h(fdfd_handle h, const fdfd_c128 *hfield, const fdfd_c128 *je_or_null, fdfd_c128 *eout, int where);
 /* Interpolate a solution field to the voxel corners: out = Mc_e * f (which = FDFD_FT_EE) or Mc_m * f
  * (which = FDFD_FT_HH), the operators of create_Mcs (model.jl:287-306): component w is averaged along its
  * own axis w with the weighted two-point mean of create_mean. */
 int fdfd_interp_corners(fdfd_handle h, int which, const fdfd_c128 *f, fdfd_c128 *out, int where);
-/* RHS: b = -Cm (mu^-1 jm) - i w je   (create_b, model.jl:251-274, EE branch). */
+/* RHS (create_b, model.jl:251-274): FT_EE handle: b = -Cm (mu^-1 jm) - i w je;
+ * FT_HH handle: b = Ce (eps^-1 je) - i w jm.  The -i w term is skipped for w == 0. */
 int fdfd_create_b(fdfd_handle h, const fdfd_c128 *je, const fdfd_c128 *jm_or_null, fdfd_c128 *b, int where);
 
 /* Multi-GPU plumbing: NCCL communicator over the z-slab ranks (halo send/recv + allreduce).

@@ -725,111 +725,142 @@ int fdfd_export_pattern(fdfd_handle h, int64_t *colptr, int64_t *rowval, fdfd_c1
     return export_pattern(c, colptr, rowval, nzval, nnz_inout);
 }
 
+// The three source / post-processing operators of the reference (model.jl:251-284) are two shapes of the same
+// stencils; which curl and which material each one needs depends on the handle's formulation:
+//   first-curl shape   out = alpha * q .* (C1 f + sj * j)      FT_EE: h_from_e (C1 = Ce, q = 1/mu)
+//                                                              FT_HH: e_from_h (C1 = Cm, q = 1/eps)
+//   second-curl shape  out = (beta * C2 (q? .* f) + gamma * j) [/ md]
+//                                                              FT_EE: create_b (C2 = Cm, with q), e_from_h (no q, / md)
+//                                                              FT_HH: create_b (C2 = Ce, with q), h_from_e (no q, / md)
+// f is required, j optional; `where` selects host or device buffers.
+namespace {
+struct PostArgs {
+    const fdfd_c128 *f, *j;
+    fdfd_c128 *out;
+    int where;
+};
+
+// stages f -> stage_x, j -> tmp (host case); returns device pointers
+int post_stage(Ctx *c, const PostArgs &a, const double2 *&df, const double2 *&dj, double2 *&dout, double2 *&tmp) {
+    const size_t bytes = (size_t)c->nloc * sizeof(double2);
+    df = reinterpret_cast<const double2 *>(a.f);
+    dj = reinterpret_cast<const double2 *>(a.j);
+    dout = reinterpret_cast<double2 *>(a.out);
+    tmp = nullptr;
+    if (a.where == FDFD_HOST) {
+        int r;
+        if ((r = stage_buffers(c)) != FDFD_OK) return r;
+        if (a.f) {
+            FDFD_CUDA(c, cudaMemcpyAsync(c->stage_x, a.f, bytes, cudaMemcpyHostToDevice, c->stream));
+            df = c->stage_x;
+        }
+        if (a.j) {
+            FDFD_CUDA(c, cudaMalloc((void **)&tmp, bytes));
+            FDFD_CUDA(c, cudaMemcpyAsync(tmp, a.j, bytes, cudaMemcpyHostToDevice, c->stream));
+            dj = tmp;
+        }
+        dout = c->stage_y;
+    } else if (a.where != FDFD_DEVICE) {
+        return set_err(c, FDFD_EINVAL, "bad `where`");
+    }
+    return FDFD_OK;
+}
+
+int post_finish(Ctx *c, const PostArgs &a, double2 *tmp, int rc) {
+    const size_t bytes = (size_t)c->nloc * sizeof(double2);
+    cudaError_t e = cudaSuccess;
+    if (rc == FDFD_OK && a.where == FDFD_HOST)
+        e = cudaMemcpyAsync(a.out, c->stage_y, bytes, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (tmp) cudaFree(tmp);
+    if (rc != FDFD_OK) return rc;
+    if (e != cudaSuccess) return set_err(c, FDFD_ECUDA, cudaGetErrorString(e));
+    return FDFD_OK;
+}
+
+int first_curl_post(Ctx *c, const PostArgs &a, cplx alpha, double sj) {
+    const double2 *df, *dj;
+    double2 *dout, *tmp;
+    int r = post_stage(c, a, df, dj, dout, tmp);
+    if (r == FDFD_OK) {
+        ApplyParams p;
+        fill_params(c, p, df, dout, false);
+        if (c->d.nranks > 1) r = halo_exchange(c, df, c->halo_lo, c->halo_hi, c->stream);
+        if (r == FDFD_OK) {
+            cudaError_t e = launch_curl1(p, dj, make_double2(alpha.real(), alpha.imag()), sj, c->stream);
+            if (e != cudaSuccess) r = set_err(c, FDFD_ECUDA, cudaGetErrorString(e));
+            c->launches += 1;
+        }
+    }
+    return post_finish(c, a, tmp, r);
+}
+
+int second_curl_post(Ctx *c, const PostArgs &a, cplx beta, cplx gamma, bool with_q, bool divide_by_md) {
+    const double2 *df, *dj;
+    double2 *dout, *tmp;
+    int r = post_stage(c, a, df, dj, dout, tmp);
+    if (r == FDFD_OK) {
+        ApplyParams p;
+        fill_params(c, p, df ? df : dj, dout, false);
+        if (!with_q) p.has_q = 0;
+        if (df && c->d.nranks > 1) r = halo_exchange(c, df, c->halo_lo, c->halo_hi, c->stream);
+        if (r == FDFD_OK) {
+            cudaError_t e = launch_curl2(p, dj, make_double2(beta.real(), beta.imag()),
+                                         make_double2(gamma.real(), gamma.imag()), df ? 1 : 0, c->stream,
+                                         divide_by_md ? 1 : 0);
+            if (e != cudaSuccess) r = set_err(c, FDFD_ECUDA, cudaGetErrorString(e));
+            c->launches += 1;
+        }
+    }
+    return post_finish(c, a, tmp, r);
+}
+}  // namespace
+
 int fdfd_h_from_e(fdfd_handle h, const fdfd_c128 *e, const fdfd_c128 *jm, fdfd_c128 *hout, int where) {
     CHECK_H(h);
     if (!e || !hout) return set_err(c, FDFD_EINVAL, "fdfd_h_from_e: null argument");
-    if (c->d.field_type != FDFD_FT_EE) return set_err(c, FDFD_EINVAL, "fdfd_h_from_e needs an FT_EE handle");
     if (c->omega == cplx(0.0)) return set_err(c, FDFD_EINVAL, "fdfd_h_from_e: omega == 0");
     int r = ensure_ready(c);
     if (r != FDFD_OK) return r;
-    const size_t bytes = (size_t)c->nloc * sizeof(double2);
-    const double2 *de = reinterpret_cast<const double2 *>(e), *dj = reinterpret_cast<const double2 *>(jm);
-    double2 *dh = reinterpret_cast<double2 *>(hout);
-    double2 *tmpj = nullptr;
-    if (where == FDFD_HOST) {
-        if ((r = stage_buffers(c)) != FDFD_OK) return r;
-        FDFD_CUDA(c, cudaMemcpyAsync(c->stage_x, e, bytes, cudaMemcpyHostToDevice, c->stream));
-        if (jm) {
-            FDFD_CUDA(c, cudaMalloc((void **)&tmpj, bytes));
-            FDFD_CUDA(c, cudaMemcpyAsync(tmpj, jm, bytes, cudaMemcpyHostToDevice, c->stream));
-            dj = tmpj;
-        }
-        de = c->stage_x;
-        dh = c->stage_y;
-    }
-    ApplyParams p;
-    fill_params(c, p, de, dh, false);
-    if (c->d.nranks > 1 && (r = halo_exchange(c, de, c->halo_lo, c->halo_hi, c->stream)) != FDFD_OK) return r;
-    const cplx a = cplx(0.0, 1.0) / c->omega;
-    FDFD_CUDA(c, launch_curl1(p, dj, make_double2(a.real(), a.imag()), c->stream));
-    c->launches += 1;
-    if (where == FDFD_HOST) FDFD_CUDA(c, cudaMemcpyAsync(hout, c->stage_y, bytes, cudaMemcpyDeviceToHost, c->stream));
-    FDFD_CUDA(c, cudaStreamSynchronize(c->stream));
-    if (tmpj) cudaFree(tmpj);
-    return FDFD_OK;
+    const cplx iw = cplx(0.0, 1.0) * c->omega;
+    const PostArgs a{e, jm, hout, where};
+    // h = (i/w) Pmu \ (Ce e + jm)   (model.jl:276-279)
+    if (c->d.field_type == FDFD_FT_EE) return first_curl_post(c, a, cplx(0.0, 1.0) / c->omega, +1.0);
+    // FT_HH handle: Ce is the second curl and mu the mass parameter: (i/w)(..)/mu = (-i w)(..)/(-w^2 mu)
+    if (c->mo[0]) return set_err(c, FDFD_EINVAL, "fdfd_h_from_e: Pmu must be diagonal (reference model.jl:236,279)");
+    return second_curl_post(c, a, -iw, -iw, false, true);
 }
 
 int fdfd_create_b(fdfd_handle h, const fdfd_c128 *je, const fdfd_c128 *jm, fdfd_c128 *b, int where) {
     CHECK_H(h);
     if (!je || !b) return set_err(c, FDFD_EINVAL, "fdfd_create_b: null argument");
-    if (c->d.field_type != FDFD_FT_EE) return set_err(c, FDFD_EINVAL, "fdfd_create_b needs an FT_EE handle");
     int r = ensure_ready(c);
     if (r != FDFD_OK) return r;
-    const size_t bytes = (size_t)c->nloc * sizeof(double2);
-    const double2 *dje = reinterpret_cast<const double2 *>(je), *djm = reinterpret_cast<const double2 *>(jm);
-    double2 *db = reinterpret_cast<double2 *>(b);
-    double2 *tmp = nullptr;
-    if (where == FDFD_HOST) {
-        if ((r = stage_buffers(c)) != FDFD_OK) return r;
-        FDFD_CUDA(c, cudaMemcpyAsync(c->stage_x, je, bytes, cudaMemcpyHostToDevice, c->stream));
-        dje = c->stage_x;
-        if (jm) {
-            FDFD_CUDA(c, cudaMalloc((void **)&tmp, bytes));
-            FDFD_CUDA(c, cudaMemcpyAsync(tmp, jm, bytes, cudaMemcpyHostToDevice, c->stream));
-            djm = tmp;
-        }
-        db = c->stage_y;
+    const cplx gm = -cplx(0.0, 1.0) * c->omega;   // the -i w j term is skipped for w == 0 (model.jl:265,270)
+    const bool w0 = c->omega == cplx(0.0);
+    if (c->d.field_type == FDFD_FT_EE) {
+        // b = -Cm (mu^-1 jm) - i w je   (model.jl:262-265)
+        const PostArgs a{jm, w0 ? nullptr : je, b, where};
+        return second_curl_post(c, a, cplx(-1.0), gm, true, false);
     }
-    ApplyParams p;
-    fill_params(c, p, djm ? djm : dje, db, false);
-    if (djm && c->d.nranks > 1 && (r = halo_exchange(c, djm, c->halo_lo, c->halo_hi, c->stream)) != FDFD_OK) return r;
-    // b = -Cm (mu^-1 jm) - i w je ; the second term is skipped for w == 0 (model.jl:265)
-    const cplx gm = -cplx(0.0, 1.0) * c->omega;
-    FDFD_CUDA(c, launch_curl2(p, c->omega == cplx(0.0) ? nullptr : dje, make_double2(-1.0, 0.0),
-                              make_double2(gm.real(), gm.imag()), djm ? 1 : 0, c->stream));
-    c->launches += 1;
-    if (where == FDFD_HOST) FDFD_CUDA(c, cudaMemcpyAsync(b, c->stage_y, bytes, cudaMemcpyDeviceToHost, c->stream));
-    FDFD_CUDA(c, cudaStreamSynchronize(c->stream));
-    if (tmp) cudaFree(tmp);
-    return FDFD_OK;
+    // b = Ce (eps^-1 je) - i w jm       (model.jl:267-270)
+    const PostArgs a{je, w0 ? nullptr : jm, b, where};
+    return second_curl_post(c, a, cplx(1.0), gm, true, false);
 }
 
 int fdfd_e_from_h(fdfd_handle h, const fdfd_c128 *hf, const fdfd_c128 *je, fdfd_c128 *eout, int where) {
     CHECK_H(h);
     if (!hf || !eout) return set_err(c, FDFD_EINVAL, "fdfd_e_from_h: null argument");
-    if (c->d.field_type != FDFD_FT_EE) return set_err(c, FDFD_EINVAL, "fdfd_e_from_h needs an FT_EE handle");
     if (c->omega == cplx(0.0)) return set_err(c, FDFD_EINVAL, "fdfd_e_from_h: omega == 0");
     int r = ensure_ready(c);
     if (r != FDFD_OK) return r;
+    const cplx iw = cplx(0.0, 1.0) * c->omega;
+    const PostArgs a{hf, je, eout, where};
+    // e = (-i/w) Peps \ (Cm h - je)   (model.jl:281-284)
+    if (c->d.field_type == FDFD_FT_HH) return first_curl_post(c, a, -cplx(0.0, 1.0) / c->omega, -1.0);
+    // FT_EE handle: Cm is the second curl and eps the mass parameter: (-i/w)(..)/eps = (i w)(..)/(-w^2 eps)
     if (c->mo[0]) return set_err(c, FDFD_EINVAL, "fdfd_e_from_h: Peps must be diagonal (reference model.jl:239,283)");
-    const size_t bytes = (size_t)c->nloc * sizeof(double2);
-    const double2 *dh = reinterpret_cast<const double2 *>(hf), *dj = reinterpret_cast<const double2 *>(je);
-    double2 *de = reinterpret_cast<double2 *>(eout);
-    double2 *tmp = nullptr;
-    if (where == FDFD_HOST) {
-        if ((r = stage_buffers(c)) != FDFD_OK) return r;
-        FDFD_CUDA(c, cudaMemcpyAsync(c->stage_x, hf, bytes, cudaMemcpyHostToDevice, c->stream));
-        dh = c->stage_x;
-        if (je) {
-            FDFD_CUDA(c, cudaMalloc((void **)&tmp, bytes));
-            FDFD_CUDA(c, cudaMemcpyAsync(tmp, je, bytes, cudaMemcpyHostToDevice, c->stream));
-            dj = tmp;
-        }
-        de = c->stage_y;
-    }
-    ApplyParams p;
-    fill_params(c, p, dh, de, false);
-    p.has_q = 0;   // Cm acts on h itself here, not on mu^-1 h
-    if (c->d.nranks > 1 && (r = halo_exchange(c, dh, c->halo_lo, c->halo_hi, c->stream)) != FDFD_OK) return r;
-    // e = (-i/w) (Cm h - je) / eps = (i w) (Cm h - je) / (-w^2 eps) = (i w) (Cm h - je) / md
-    const cplx f = cplx(0.0, 1.0) * c->omega;
-    FDFD_CUDA(c, launch_curl2(p, dj, make_double2(f.real(), f.imag()), make_double2(-f.real(), -f.imag()), 1,
-                              c->stream, 1));
-    c->launches += 1;
-    if (where == FDFD_HOST) FDFD_CUDA(c, cudaMemcpyAsync(eout, c->stage_y, bytes, cudaMemcpyDeviceToHost, c->stream));
-    FDFD_CUDA(c, cudaStreamSynchronize(c->stream));
-    if (tmp) cudaFree(tmp);
-    return FDFD_OK;
+    return second_curl_post(c, a, iw, -iw, false, true);
 }
 
 int fdfd_interp_corners(fdfd_handle h, int which, const fdfd_c128 *f, fdfd_c128 *out, int where) {

@@ -111,9 +111,9 @@ __global__ void __launch_bounds__(128) apply_naive_kernel(const __grid_constant_
     }
 }
 
-// h = alpha * q .* (C1 e + jm)       (h_from_e, reference model.jl:276-279)
+// h = alpha * q .* (C1 e + sj * jm)  (h_from_e on an FT_EE handle, e_from_h on an FT_HH handle; model.jl:276-284)
 __global__ void __launch_bounds__(128) curl1_kernel(const __grid_constant__ ApplyParams p, const double2 *jm,
-                                                     double2 alpha) {
+                                                     double2 alpha, double sj) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y;
     const int kl = blockIdx.z;
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(128) curl1_kernel(const __grid_constant__ Appl
         t = c_fms(p.c.a0[wb][ib], g.E(cb, i, j, kl), t);
         t = c_fms(p.c.a1[wb][ib], g.Esh(cb, i, j, kl, wb, p.s1[wb]), t);
         const int64_t o = (int64_t)kl * p.y_pstride + (int64_t)u * p.y_cs + ((int64_t)j * p.Nx + i) * p.y_es;
-        if (jm) t = c_add(t, jm[o]);
+        if (jm) t = c_add(t, c_scale(sj, jm[o]));
         if (p.has_q) t = c_mul(p.q[u][g.gidx(i, j, kl)], t);
         p.y[o] = c_mul(alpha, t);
     }
@@ -318,10 +318,10 @@ cudaError_t launch_interp(const ApplyParams &p, int which_other, cudaStream_t s)
     return cudaGetLastError();
 }
 
-cudaError_t launch_curl1(const ApplyParams &p, const double2 *jm, double2 alpha, cudaStream_t s) {
+cudaError_t launch_curl1(const ApplyParams &p, const double2 *jm, double2 alpha, double sj, cudaStream_t s) {
     dim3 block(128, 1, 1);
     dim3 grid((p.Nx + 127) / 128, p.Ny, p.nzl);
-    curl1_kernel<<<grid, block, 0, s>>>(p, jm, alpha);
+    curl1_kernel<<<grid, block, 0, s>>>(p, jm, alpha, sj);
     return cudaGetLastError();
 }
 

@@ -188,7 +188,7 @@ cudaError_t tiled_build_offmask(const ApplyParams &p, unsigned char **mask, int 
 cudaError_t launch_offdiag_correction(const ApplyParams &p, const int4 *items, int count, int ntx, int kl_begin,
                                       int kl_end, cudaStream_t s);
 // first-curl only: h = scale * q .* (C1 e + jm)   (h_from_e), naive kernel
-cudaError_t launch_curl1(const ApplyParams &p, const double2 *jm, double2 alpha, cudaStream_t s);
+cudaError_t launch_curl1(const ApplyParams &p, const double2 *jm, double2 alpha, double sj, cudaStream_t s);
 // second-curl only: y = beta * C2 (q .* h) + gamma * je   (create_b), naive kernel
 cudaError_t launch_curl2(const ApplyParams &p, const double2 *je, double2 beta, double2 gamma, int has_h,
                          cudaStream_t s, int divide_by_md = 0);

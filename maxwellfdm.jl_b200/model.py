@@ -6,11 +6,14 @@ Same names and argument meaning as the reference (ASCII spellings: ω→w, ε→
     create_e_mikL                       model.jl:91
     clear_srcs / add_srce / add_srcm / create_srcs      model.jl:177-207
     create_stretched_dls                model.jl:122-139
+    create_paramops / create_curls      model.jl:141-175   (descriptions, not sparse matrices)
     create_A / create_b / create_linsys model.jl:209-274   (GPU: returns an FdfdOperator, not a CSC)
-    h_from_e                            model.jl:276-279
+    h_from_e / e_from_h / create_Mcs    model.jl:276-306
     solve                               (absent in the reference: `A \\ b` left to the user)
-What changes for the user: `Ps = create_paramops(mdl); Cs = create_curls(mdl); A,b = create_linsys(EE,ω,Ps,Cs,js);
-e = A\\b` becomes `A,b = create_linsys(EE, ω, mdl); e,info = solve(A,b)`; the operator is never assembled.
+The reference call sequence carries over: `Ps = create_paramops(mdl); Cs = create_curls(mdl); js = create_srcs(mdl);
+A, b = create_linsys(EE, ω, Ps, Cs, js)`, then `e, info = solve(A, b)` instead of `e = A \\ b`, then
+`h = h_from_e(e, ω, Ps, Cs, js)`.  The operator is never assembled.  Shortcuts taking the model are kept:
+`create_linsys(EE, ω, mdl)`.
 Geometry rasterisation (calc_matparams!, full.jl:16-70) is out of scope: fill mdl.eps_arr / mdl.mu_arr directly.
 """
 import numpy as np
@@ -117,8 +120,7 @@ def create_stretched_dls(mdl):
     return sdl_e, sdl_m, tuple(1 / a for a in sdl_e), tuple(1 / a for a in sdl_m)
 
 
-def _mu_or_none(mdl):
-    mu = mdl.mu_arr
+def _mu_or_none(mu):
     ident = np.zeros((3, 3))
     np.fill_diagonal(ident, 1.0)
     if not mu.any() or np.array_equal(mu, np.broadcast_to(ident, mu.shape)):
@@ -126,45 +128,156 @@ def _mu_or_none(mdl):
     return mu
 
 
-def create_A(ft, w, mdl, device=-1, rank=0, nranks=1, kernel=0, weighted_out_avg=False):
-    """GPU stand-in for create_A(ft, ω, create_paramops(mdl), create_curls(mdl)) (model.jl:141-175,225-246).
-    With nranks > 1 this rank's z-slab of eps/mu is taken from the full model arrays."""
+class ParamOp:
+    """What the reference's create_paramop turns into a sparse matrix (model.jl:152-155): the material array plus the
+    averaging inputs.  Here it stays a description - the GPU kernels apply it matrix-free.  Holds a REFERENCE to the
+    model's array (no copy of a multi-GB tensor), so build the operator before editing the model again."""
+
+    def __init__(self, kind, arr, geom):
+        self.kind, self.arr, self.geom = kind, arr, geom
+
+
+class CurlOp:
+    """What the reference's create_curl turns into a sparse matrix (model.jl:171-172): which curl (Ce: E->H, Cm: H->E)
+    and the 1-D inputs (stretched dl's, Bloch flags and phases, boundft, DOF order)."""
+
+    def __init__(self, kind, geom):
+        self.kind, self.geom = kind, geom
+
+
+class _Geom:
+    """the model settings both create_paramops and create_curls read (model.jl:141-175), taken at call time"""
+
+    def __init__(self, mdl):
+        self.N, self.isbloch = mdl.grid.N, mdl.grid.isbloch
+        self.sdl_e, self.sdl_m, _, _ = create_stretched_dls(mdl)
+        self.e_mikL = create_e_mikL(mdl)
+        self.boundft, self.order_cmpfirst = tuple(mdl.boundft), mdl.order_cmpfirst
+        self.ops = {}            # operators built from this description, keyed by (ft, w, options)
+
+    def same(self, o):
+        return (self.N == o.N and self.isbloch == o.isbloch and self.boundft == o.boundft
+                and self.order_cmpfirst == o.order_cmpfirst and np.array_equal(self.e_mikL, o.e_mikL)
+                and all(np.array_equal(a, b) for a, b in zip(self.sdl_e + self.sdl_m, o.sdl_e + o.sdl_m)))
+
+
+def create_paramops(mdl):
+    """(Peps, Pmu) - model.jl:141-158 (calc_matparams!, the rasterisation at :143, is out of scope: fill
+    mdl.eps_arr / mdl.mu_arr directly)."""
+    g = _Geom(mdl)
+    return ParamOp("eps", mdl.eps_arr, g), ParamOp("mu", mdl.mu_arr, g)
+
+
+def create_curls(mdl):
+    """(Ce, Cm) - model.jl:160-175."""
+    g = _Geom(mdl)
+    return CurlOp("Ce", g), CurlOp("Cm", g)
+
+
+def _build(ft, w, Ps, Cs, device=-1, rank=0, nranks=1, kernel=0, weighted_out_avg=False):
+    if ft not in (EE, HH):
+        raise ValueError(f"ft = {ft} is unsupported.")          # model.jl:242
+    Pe, Pm = Ps
+    Ce, Cm = Cs
+    if not (isinstance(Pe, ParamOp) and isinstance(Pm, ParamOp) and isinstance(Ce, CurlOp) and isinstance(Cm, CurlOp)):
+        raise TypeError("Ps / Cs must come from create_paramops / create_curls")
+    g = Ce.geom
+    if not g.same(Pe.geom):
+        raise ValueError("create_paramops and create_curls were called on different model settings")
+    key = (ft, complex(w), device, rank, nranks, kernel, weighted_out_avg)
+    A = g.ops.get(key)
+    if A is not None and not A.closed:
+        return A
+    from .operator import partition
+    k0, k1 = partition(g.N[2], nranks, rank)
+    mu = _mu_or_none(Pm.arr)
+    A = FdfdOperator(g.N, g.isbloch, g.sdl_e, g.sdl_m, w, Pe.arr[:, :, k0:k1],
+                     None if mu is None else mu[:, :, k0:k1], g.e_mikL, boundft=g.boundft, ft=ft,
+                     order_cmpfirst=g.order_cmpfirst, device=device, rank=rank, nranks=nranks, kernel=kernel,
+                     weighted_out_avg=weighted_out_avg)
+    g.ops[key] = A
+    return A
+
+
+def _as_ops(third, fourth):
+    """accept both call shapes: (..., mdl) and the reference's (..., Ps, Cs)"""
+    if isinstance(third, Model):
+        return create_paramops(third), create_curls(third)
+    return third, fourth
+
+
+def create_A(ft, w, Ps, Cs=None, **kw):
+    """create_A(ft, ω, Ps, Cs) (model.jl:222-246) - or create_A(ft, ω, mdl).  Returns the GPU operator (an
+    FdfdOperator: supports `A @ x`, `A.solve(b)`), not a SparseMatrixCSC; nothing is assembled.  Keyword options:
+    device, rank, nranks (z-slabs: this rank's slab of eps/mu is taken from the full model arrays), kernel,
+    weighted_out_avg."""
+    Ps, Cs = _as_ops(Ps, Cs)
+    return _build(ft, w, Ps, Cs, **kw)
+
+
+def create_b(ft, w, Ps, Cs=None, js=None, **kw):
+    """create_b(ft, ω, Ps, Cs, js) (model.jl:248-274), evaluated on the GPU (fdfd_create_b): EE: b = -Cm(Pmu\\jm) - iω je,
+    HH: b = Ce(Peps\\je) - iω jm.  Also accepts create_b(ft, ω, A, js) with an operator built by create_A."""
+    if isinstance(Ps, FdfdOperator):
+        A, js = Ps, (Cs if js is None else js)
+    else:
+        Ps, Cs = _as_ops(Ps, Cs)
+        A = _build(ft, w, Ps, Cs, **kw)
     if ft not in (EE, HH):
         raise ValueError(f"ft = {ft} is unsupported.")
-    sdl_e, sdl_m, _, _ = create_stretched_dls(mdl)
-    from .operator import partition
-    k0, k1 = partition(mdl.grid.N[2], nranks, rank)
-    mu = _mu_or_none(mdl)
-    return FdfdOperator(mdl.grid.N, mdl.grid.isbloch, sdl_e, sdl_m, w, mdl.eps_arr[:, :, k0:k1],
-                        None if mu is None else mu[:, :, k0:k1], create_e_mikL(mdl),
-                        boundft=mdl.boundft, ft=ft, order_cmpfirst=mdl.order_cmpfirst, device=device,
-                        rank=rank, nranks=nranks, kernel=kernel, weighted_out_avg=weighted_out_avg)
-
-
-def create_b(ft, w, A, js):
-    """create_b (model.jl:251-274), EE branch, evaluated on the GPU through fdfd_create_b."""
-    if ft != EE:
-        raise ValueError(f"ft = {ft} is unsupported.")
+    if A.ft != ft:
+        raise ValueError("create_b: operator was built for the other formulation")
     je, jm = js
-    return A.create_b(je, jm if np.any(jm) else None)
+    other = jm if ft == EE else je        # the current that goes through the curl; skipped when identically zero
+    if ft == EE:
+        return A.create_b(je, jm if np.any(other) else None)
+    return A.create_b(je, jm)
 
 
-def create_linsys(ft, w, mdl, **kw):
-    A = create_A(ft, w, mdl, **kw)
-    return A, create_b(ft, w, A, create_srcs(mdl))
+def create_linsys(ft, w, Ps, Cs=None, js=None, **kw):
+    """create_linsys(ft, ω, Ps, Cs, js) (model.jl:209-220) - or create_linsys(ft, ω, mdl) (sources from the model)."""
+    if isinstance(Ps, Model):
+        js = create_srcs(Ps) if js is None else js
+    Ps, Cs = _as_ops(Ps, Cs)
+    A = _build(ft, w, Ps, Cs, **kw)
+    return A, create_b(ft, w, A, js)
 
 
-def h_from_e(e, w, A, jm=None):
-    return A.h_from_e(e, jm)
+def _post_operator(w, third, fourth, **kw):
+    if isinstance(third, FdfdOperator):
+        return third
+    Ps, Cs = _as_ops(third, fourth)
+    g = Cs[0].geom
+    for key, A in g.ops.items():           # reuse the operator create_A built for this ω (either formulation works)
+        if key[1] == complex(w) and not A.closed:
+            return A
+    return _build(EE, w, Ps, Cs, **kw)
 
 
-def e_from_h(h, w, A, je=None):
-    """e_from_h (model.jl:281-284)"""
-    return A.e_from_h(h, je)
+def h_from_e(e, w, Ps, Cs=None, js=None, **kw):
+    """h_from_e(e, ω, Ps, Cs, js) (model.jl:276-279) = (i/ω) Pmu \\ (Ce e + jm); also h_from_e(e, ω, A, jm)."""
+    if isinstance(Ps, FdfdOperator):
+        jm = Cs if js is None else js
+    else:
+        jm = None if js is None else js[1]
+    A = _post_operator(w, Ps, Cs, **kw)
+    return A.h_from_e(e, jm if (jm is not None and np.any(jm)) else None)
 
 
-def create_Mcs(A):
-    """create_Mcs (model.jl:287-306): returns two callables (Mc_e, Mc_m) interpolating E / H to the voxel corners."""
+def e_from_h(h, w, Ps, Cs=None, js=None, **kw):
+    """e_from_h(h, ω, Ps, Cs, js) (model.jl:281-284) = (-i/ω) Peps \\ (Cm h - je); also e_from_h(h, ω, A, je)."""
+    if isinstance(Ps, FdfdOperator):
+        je = Cs if js is None else js
+    else:
+        je = None if js is None else js[0]
+    A = _post_operator(w, Ps, Cs, **kw)
+    return A.e_from_h(h, je if (je is not None and np.any(je)) else None)
+
+
+def create_Mcs(mdl_or_A, **kw):
+    """create_Mcs(mdl) (model.jl:287-306): two callables (Mc_e, Mc_m) interpolating E / H to the voxel corners
+    (the reference returns two sparse matrices; apply these like `Mc_e(e)`).  Also accepts an operator."""
+    A = mdl_or_A if isinstance(mdl_or_A, FdfdOperator) else _build(EE, 0.0, *(_as_ops(mdl_or_A, None)), **kw)
     return (lambda e: A.interp_corners(e, "E")), (lambda h: A.interp_corners(h, "H"))
 
 

@@ -51,6 +51,7 @@ class FdfdOperator:
         h = C.c_void_p()
         L.check(lib.fdfd_create(C.byref(h), C.byref(d)))
         self._h = h
+        self.ft = 0 if d.field_type == L.FT_EE else 1        # EE / HH as in grid.py
         self.N = tuple(int(n) for n in N)
         self.order_cmpfirst = bool(order_cmpfirst)
         k0, k1 = C.c_int64(), C.c_int64()
@@ -71,6 +72,10 @@ class FdfdOperator:
         if self._h is not None:
             L.lib().fdfd_destroy(self._h)
             self._h = None
+
+    @property
+    def closed(self):
+        return self._h is None
 
     def __del__(self):
         try:

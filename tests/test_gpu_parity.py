@@ -405,6 +405,68 @@ def test_tfsf_rhs_reproduces_the_incident_wave():
     A.close()
 
 
+def test_rhs_and_postprocessing_on_hh_handles():
+    """create_b (HH branch, model.jl:267-270), h_from_e and e_from_h evaluated on an FT_HH handle vs the oracle."""
+    for isbloch, boundft in (((True, False, True), (EE, EE, EE)), ((False, True, False), (HH, EE, HH))):
+        p = Problem((9, 8, 7), isbloch, boundft, with_mu=True, ft=HH)
+        A_ref, (Pe, Pm, Ce, Cm) = p.oracle_csc()
+        A = p.operator(device=0)
+        je, jm, e, h = p.random_x(31), p.random_x(32), p.random_x(33), p.random_x(34)
+        assert rel(A.create_b(je, jm), op.create_b(HH, p.omega, Pe, Pm, Ce, Cm, je, jm)) < TOL
+        assert rel(A.create_b(je), op.create_b(HH, p.omega, Pe, Pm, Ce, Cm, je, np.zeros_like(je))) < TOL
+        assert rel(A.e_from_h(h, je), op.e_from_h(h, p.omega, Pe, Cm, je)) < TOL
+        assert rel(A.h_from_e(e, jm), op.h_from_e(e, p.omega, Pm, Ce, jm)) < TOL
+        assert rel(A.h_from_e(e), op.h_from_e(e, p.omega, Pm, Ce, np.zeros_like(e))) < TOL
+        A.close()
+    # identity mu (scalar mass parameter) on the HH handle
+    p = Problem((8, 7, 6), (True, True, False), ft=HH)
+    A_ref, (Pe, Pm, Ce, Cm) = p.oracle_csc()
+    A = p.operator(device=0)
+    e, jm = p.random_x(41), p.random_x(42)
+    assert rel(A.h_from_e(e, jm), op.h_from_e(e, p.omega, Pm, Ce, jm)) < TOL
+    A.close()
+
+
+@pytest.mark.parametrize("ft", [EE, HH])
+def test_reference_call_sequence(ft):
+    """The reference's own sequence (model.jl:141-284): Ps = create_paramops(mdl); Cs = create_curls(mdl);
+    js = create_srcs(mdl); A, b = create_linsys(ft, w, Ps, Cs, js); solve; h_from_e / e_from_h(.., w, Ps, Cs, js) -
+    every piece against the oracle built from the same model inputs."""
+    from oracle.grid import Grid as OGrid, create_stretched_dls as o_sdls
+    fb = _fb()
+    n = 14
+    lp = (np.arange(n + 1) - n / 2) * 1.0
+    mdl = fb.ModelFull(fb.Grid((lp, lp, lp), (False, False, False)))
+    w = 2 * np.pi / 8.0
+    fb.set_wpml(mdl, w)
+    fb.set_Npml(mdl, ((3,) * 3, (3,) * 3))
+    rng = np.random.default_rng(SEED)
+    for v in range(3):
+        mdl.eps_arr[..., v, v] = 1.0 + 0.5 * rng.random(mdl.grid.N)
+        mdl.mu_arr[..., v, v] = 1.0 + 0.2 * rng.random(mdl.grid.N)
+    fb.add_srce(mdl, fb.PointSrc([0.3, 0.2, 0.1], [0, 0, 1]))
+    fb.add_srcm(mdl, fb.PointSrc([-1.2, 0.4, 0.6], [1, 0, 0]))
+    Ps, Cs, js = fb.create_paramops(mdl), fb.create_curls(mdl), fb.create_srcs(mdl)
+    A, b = fb.create_linsys(ft, w, Ps, Cs, js, device=0)
+    assert fb.create_A(ft, w, Ps, Cs, device=0) is A                  # one operator per (formulation, w)
+    # oracle from the same inputs
+    og = OGrid((lp, lp, lp), (False, False, False))
+    sdl_e, sdl_m, sei, smi = o_sdls(w, og, ((3,) * 3, (3,) * 3))
+    ph = np.ones(3, complex)
+    Ce, Cm = op.create_curls(sei, smi, (EE,) * 3, og.isbloch, ph)
+    Pe, Pm = op.create_paramops(mdl.eps_arr, mdl.mu_arr, sdl_e, sdl_m, sei, smi, (EE,) * 3, og.isbloch, ph)
+    A_ref = op.create_A(ft, w, Pe, Pm, Ce, Cm)
+    assert rel(b, op.create_b(ft, w, Pe, Pm, Ce, Cm, js[0], js[1])) < TOL
+    assert rel(fb.create_b(ft, w, Ps, Cs, js, device=0), b) == 0.0
+    x, info = fb.solve(A, b, rtol=1e-10, maxit=20000)
+    assert info["converged"] and rel(A_ref.matvec(x), b) < 1e-8
+    if ft == EE:
+        assert rel(fb.h_from_e(x, w, Ps, Cs, js, device=0), op.h_from_e(x, w, Pm, Ce, js[1])) < TOL
+    else:
+        assert rel(fb.e_from_h(x, w, Ps, Cs, js, device=0), op.e_from_h(x, w, Pe, Cm, js[0])) < TOL
+    A.close()
+
+
 def test_model_api_end_to_end():
     """reference-shaped host API: ModelFull -> add_srce -> create_linsys -> solve -> h_from_e."""
     fb = _fb()

@@ -108,3 +108,42 @@ def test_dof_ordering_rule():
     assert mdl.size(fb.EE) == (3,) + N and mdl.length(fb.EE) == 3 * 60
     with pytest.raises(ValueError):
         fb.create_A(7, 1.0, mdl)      # reference: @error "ft = ... is unsupported." (model.jl:242)
+    with pytest.raises(ValueError):
+        fb.create_A(7, 1.0, fb.create_paramops(mdl), fb.create_curls(mdl))
+
+
+def test_reference_call_sequence_descriptors():
+    """create_paramops / create_curls (model.jl:141-175) return descriptions the reference-shaped create_A consumes;
+    on a host-only handle (device = -2) the assembled pattern equals the oracle's create_A for both formulations."""
+    from oracle.grid import Grid as OGrid, create_stretched_dls as o_sdls, EE as OEE, HH as OHH
+    from oracle import operators as op
+    N = (5, 4, 6)
+    lp = tuple(np.arange(n + 1.0) for n in N)
+    mdl = fb.ModelFull(fb.Grid(lp, (True, False, True)))
+    fb.set_wpml(mdl, 0.9)
+    fb.set_Npml(mdl, ((0, 1, 0), (0, 2, 0)))
+    fb.set_kbloch(mdl, (0.3, 0.0, 0.2))
+    rng = np.random.default_rng(5)
+    for v in range(3):
+        mdl.eps_arr[..., v, v] = 2 + rng.random(N)
+        mdl.mu_arr[..., v, v] = 1 + rng.random(N)
+    Ps, Cs = fb.create_paramops(mdl), fb.create_curls(mdl)
+    assert isinstance(Ps[0], fb.ParamOp) and Ps[0].kind == "eps" and Ps[1].kind == "mu"
+    assert isinstance(Cs[0], fb.CurlOp) and (Cs[0].kind, Cs[1].kind) == ("Ce", "Cm")
+    og = OGrid(lp, (True, False, True))
+    sdl_e, sdl_m, sei, smi = o_sdls(0.9, og, ((0, 1, 0), (0, 2, 0)))
+    ph = fb.create_e_mikL(mdl)
+    Ce, Cm = op.create_curls(sei, smi, (OEE,) * 3, og.isbloch, ph)
+    Pe, Pm = op.create_paramops(mdl.eps_arr, mdl.mu_arr, sdl_e, sdl_m, sei, smi, (OEE,) * 3, og.isbloch, ph)
+    for ft, oft in ((fb.EE, OEE), (fb.HH, OHH)):
+        A = fb.create_A(ft, 1.3, Ps, Cs, device=-2)
+        assert fb.create_A(ft, 1.3, Ps, Cs, device=-2) is A
+        cp, rv, nz = A.export_pattern()
+        ref = op.create_A(oft, 1.3, Pe, Pm, Ce, Cm)
+        assert np.array_equal(cp, ref.julia_pattern()[0]) and np.array_equal(rv, ref.julia_pattern()[1])
+        assert np.abs(nz - ref.nzval).max() <= 1e-13 * np.abs(ref.nzval).max()
+        A.close()
+    # descriptions taken from different model settings do not mix
+    fb.set_kbloch(mdl, (0.1, 0.0, 0.2))
+    with pytest.raises(ValueError):
+        fb.create_A(fb.EE, 1.3, Ps, fb.create_curls(mdl), device=-2)
