@@ -646,10 +646,10 @@ static cudaError_t launch_tile(const ApplyParams &p, int kl_begin, int kl_end, c
 }
 
 // Tile choice.  Diagonal material: 32x8 tiles, two independent CTAs per SM (more concurrency beats the better halo
-// ratio of the large tile).  Full tensor: if most (tile, plane) blocks hold off-diagonal material, one launch of the
-// 32x16 full-tensor kernel; otherwise (the usual case: subpixel smoothing touches only material interfaces) a SPLIT
-// launch on 32x8 tiles - the diagonal kernel takes every work item without off-diagonal material, the full-tensor
-// kernel only the flagged ones.
+// ratio of the large tile).  Full tensor: if more than a quarter of the (tile, plane) blocks hold off-diagonal
+// material, one launch of the fused 32x16 full-tensor kernel (which skips empty planes through the mask); otherwise
+// (the usual case: subpixel smoothing touches only material interfaces) the diagonal kernel on 32x8 tiles followed
+// by the marching correction kernel on the flagged runs (apply_naive.cu).  Measured choices: DESIGN.md section 5.
 static int env_ty() {
     static const int ty_env = [] { const char *e = getenv("FDFD_TY"); return e ? atoi(e) : 0; }();
     return (ty_env == 8 || ty_env == 16) ? ty_env : 0;

@@ -19,8 +19,6 @@ namespace {
 
 using namespace kry;
 
-// complex scalar slots
-
 // complex scalar slots (index into double2 array)
 enum { S_RHO0 = 0, S_RR0 = 1, S_RHO1 = 2, S_RR1 = 3, S_SIGMA = 4, S_TS = 5, S_TT = 6, S_ALPHA = 7, S_OMEGA = 8,
        S_BNORM = 9, S_TMP0 = 10, S_TMP1 = 11, S_TMP2 = 12 };
@@ -140,9 +138,6 @@ static int bicgstab(Ctx *c, const double2 *b, double2 *x, double rtol, int maxit
     c->launches += 1;
     KCHK(allreduce_sum(c, sc + 2 * S_RHO0, 4, st));
     KCHK(allreduce_sum(c, sc + 2 * S_BNORM, 2, st));
-    if (c->d.nranks > 1) {
-        // RHO0 and RR0 were reduced as one pair; nothing else to fix up
-    }
     if (hist_dev) { k_store_hist<<<1, 1, 0, st>>>(hist_dev, 0, rd.scal, S_RR0); c->launches += 1; }
 
     auto read_relres = [&](int rr_slot, double &out) -> int {
