@@ -260,7 +260,7 @@ int apply_device(Ctx *c, const double2 *x, double2 *y, bool transpose) {
     fill_params(c, p, x, y, transpose);
     const bool can_tile = tiled_supported(p);
     if (c->d.kernel == FDFD_KERNEL_TILED && !can_tile)
-        return set_err(c, FDFD_EINVAL, "tiled kernel requires a uniform Yee arrangement (boundft all-EE or all-HH)");
+        return set_err(c, FDFD_EINVAL, "tiled kernel: unsupported arrangement");
     const bool use_tiled = c->d.kernel != FDFD_KERNEL_NAIVE && can_tile;
     // timing experiments only (results are wrong with FDFD_DEBUG_SKIP_HALO): where does the multi-slab overhead go?
     static const bool dbg_skip_halo = getenv("FDFD_DEBUG_SKIP_HALO") != nullptr;
@@ -377,8 +377,7 @@ static int stage_buffers(Ctx *c) {
 // direction's transfer time instead of H2D + kernel + D2H.  Needs a single slab, the cmp-first layout (a
 // z sub-slab is contiguous) and the tiled kernel; other configurations use the plain staged path.
 static bool can_pipeline(Ctx *c) {
-    return c->d.nranks == 1 && c->d.order_cmpfirst && c->d.kernel != FDFD_KERNEL_NAIVE &&
-           c->s1[0] == c->s1[1] && c->s1[1] == c->s1[2] && (c->k1 - c->k0) >= 16;
+    return c->d.nranks == 1 && c->d.order_cmpfirst && c->d.kernel != FDFD_KERNEL_NAIVE && (c->k1 - c->k0) >= 16;
 }
 
 static int apply_host_pipelined(Ctx *c, const double2 *xh, double2 *yh, bool transpose) {

@@ -198,10 +198,8 @@ __global__ void __launch_bounds__(128) interp_kernel(const __grid_constant__ App
 // kernel when off-diagonal entries are sparse (material interfaces only).  Work item = (tile, [ks,ke)): a run of
 // consecutive z-planes of one 32x8 thread tile (outputs: inner 30x6) whose corner terms can be non-zero.  The CTA
 // marches the run: the corner quantity G(k+1) is computed once per plane (11 loads per thread) and reused as
-// G(k) in the next step; x/y neighbours of G travel through a double-buffered shared tile.  REV = false: default
-// Yee arrangement (first curl forward: in-average looks back, out-average looks forward, upward march);
-// REV = true: the mirror image (first curl backward on every axis, downward march).
-template <bool REV>
+// G(k) in the next step; x/y neighbours of G travel through a double-buffered shared tile.  Per axis the in-average
+// looks towards -s1 and the out-average towards +s1 (s1 = direction of the first curl); the march follows s1_z.
 __global__ void __launch_bounds__(256) offdiag_march_kernel(const __grid_constant__ ApplyParams p,
                                                              const int4 *__restrict__ items, int ntx, int kl_begin,
                                                              int kl_end) {
@@ -212,12 +210,12 @@ __global__ void __launch_bounds__(256) offdiag_march_kernel(const __grid_constan
     const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
     const int gi = (item.x % ntx) * 30 - 1 + tx, gj = (item.x / ntx) * 6 - 1 + ty;
     const int ci = ((gi % p.Nx) + p.Nx) % p.Nx, cj = ((gj % p.Ny) + p.Ny) % p.Ny;
-    constexpr int SG = REV ? -1 : 1;
-    const int cim = g_wrap(ci - SG, p.Nx), cjm = g_wrap(cj - SG, p.Ny);   // in-average neighbour (shift -s1)
+    const int SGX = p.s1[0], SGY = p.s1[1], SG = p.s1[2];
+    const int cim = g_wrap(ci - SGX, p.Nx), cjm = g_wrap(cj - SGY, p.Ny);   // in-average neighbour (shift -s1)
     const bool out_ok = tx >= 1 && tx <= 30 && ty >= 1 && ty <= 6 && gi < p.Nx && gj < p.Ny;
     Gather g{p};
     const double2 mi0x = p.c.mi0[0][ci], mi1x = p.c.mi1[0][ci], mi0y = p.c.mi0[1][cj], mi1y = p.c.mi1[1][cj];
-    const int txp = min(max(tx + SG, 0), 31), typ = min(max(ty + SG, 0), 7);   // out-average neighbour (shift +s1)
+    const int txp = min(max(tx + SGX, 0), 31), typ = min(max(ty + SGY, 0), 7);   // out-average neighbour (shift +s1)
 
     // corner quantity G(kk) at this thread's cell; ezm = E_z of plane kk-SG at this cell (in), E_z(kk) (out)
     // own-cell field of the plane handled last by corner() (needed as `s` by the fused-dot deltas)
@@ -235,7 +233,7 @@ __global__ void __launch_bounds__(256) offdiag_march_kernel(const __grid_constan
         ezm = ez;
     };
 
-    const int kfirst = REV ? ke - 1 : ks;
+    const int kfirst = SG < 0 ? ke - 1 : ks;
     double2 ezm = g.E(2, ci, cj, kfirst - SG);
     double2 Gcx, Gcy, Gcz;
     corner(kfirst, ezm, Gcx, Gcy, Gcz);
@@ -306,8 +304,7 @@ cudaError_t launch_apply_naive(const ApplyParams &p, cudaStream_t s) {
 cudaError_t launch_offdiag_correction(const ApplyParams &p, const int4 *items, int count, int ntx, int kl_begin,
                                       int kl_end, cudaStream_t s) {
     if (count <= 0) return cudaSuccess;
-    if (p.s1[0] < 0) offdiag_march_kernel<true><<<count, 256, 0, s>>>(p, items, ntx, kl_begin, kl_end);
-    else             offdiag_march_kernel<false><<<count, 256, 0, s>>>(p, items, ntx, kl_begin, kl_end);
+    offdiag_march_kernel<<<count, 256, 0, s>>>(p, items, ntx, kl_begin, kl_end);
     return cudaGetLastError();
 }
 

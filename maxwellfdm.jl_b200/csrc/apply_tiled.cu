@@ -1,8 +1,9 @@
-// K1 - the roofline kernel: matrix-free y = C2 (q .* C1 x) + mass(x) for the two uniform Yee arrangements
-// (first curl forward on every axis: boundft = (EE,EE,EE) with FT_EE, the reference default, model.jl:46; or
-// backward on every axis [REV]: FT_HH with the default boundft, model.jl:238-240, or FT_EE with boundft all-HH),
-// any boundary condition, both DOF layouts, diagonal or full 3x3 material tensor.  REV is the mirror image of
-// the forward kernel: neighbour offsets change sign and the z-march runs downwards.
+// K1 - the roofline kernel: matrix-free y = C2 (q .* C1 x) + mass(x) for every Yee arrangement (boundft), any
+// boundary condition, both DOF layouts, diagonal or full 3x3 material tensor.  Template argument ARR:
+//   0  first curl forward on every axis: boundft = (EE,EE,EE) with FT_EE, the reference default (model.jl:46);
+//   1  backward on every axis: FT_HH with the default boundft (model.jl:238-240), or FT_EE with boundft all-HH -
+//      the mirror image: neighbour offsets change sign (still immediates), the z-march runs downwards;
+//   2  mixed: per-axis directions read from the parameters (offsets in registers instead of immediates).
 //
 // Replaces the per-iteration CSC SpMV `mul!(y, A, x)` on the matrix assembled by the reference's
 // create_A (src/model/model.jl:225-246); stencil per SURVEY.md App. A.4-A.6.
@@ -100,10 +101,14 @@ struct TileIdx {
     __device__ __forceinline__ static int h(int c, int tx, int ty) { return (c * TY + ty) * TX + tx; }
 };
 
-template <bool CMPFIRST, bool HAS_OFF, bool HAS_Q, int TX, int TY, bool DOT, bool REV>
+template <bool CMPFIRST, bool HAS_OFF, bool HAS_Q, int TX, int TY, bool DOT, int ARR>
 __global__ void __launch_bounds__(TX *TY, (TX * TY <= 256 ? 2 : 1)) apply_tiled_kernel(const __grid_constant__ TiledParams tp) {
     using TI = TileIdx<CMPFIRST, TX, TY>;
-    constexpr int SG = REV ? -1 : 1;   // direction of the first curl's neighbour (and of the z-march)
+    // direction of the first curl's neighbour per axis (z: also the direction of the march); compile-time for the
+    // two uniform arrangements
+    const int SGX = ARR == 0 ? 1 : ARR == 1 ? -1 : tp.a.s1[0];
+    const int SGY = ARR == 0 ? 1 : ARR == 1 ? -1 : tp.a.s1[1];
+    const int SGZ = ARR == 0 ? 1 : ARR == 1 ? -1 : tp.a.s1[2];
     constexpr int NT = TX * TY;
     constexpr int NST = nst_for(NT);
     constexpr int LZP = lzmax_for(NT) + 2;
@@ -136,7 +141,7 @@ __global__ void __launch_bounds__(TX *TY, (TX * TY <= 256 ? 2 : 1)) apply_tiled_
     const int kc0 = tp.kl_begin + chunk * tp.lz;
     const int kc1 = min(kc0 + tp.lz, tp.kl_end);
     const int nplanes = kc1 - kc0 + 2;  // planes kc0-1 .. kc1
-    auto kof = [&](int n) { return REV ? kc1 - n : kc0 - 1 + n; };   // local plane of march step n
+    auto kof = [&](int n) { return SGZ < 0 ? kc1 - n : kc0 - 1 + n; };   // local plane of march step n
 
     const int Nx = p.Nx, Ny = p.Ny;
     const int gi = ox + tx, gj = oy + ty;
@@ -281,13 +286,13 @@ __global__ void __launch_bounds__(TX *TY, (TX * TY <= 256 ? 2 : 1)) apply_tiled_
     const int ho = ty * TX + tx;                 // H / G tiles: component stride NT, x stride 1, y stride TX
     // y-neighbour offsets collapse to 0 on the first / last tile row and x-neighbour reads of the first / last tile
     // position land in the gaps between buffers, so no read ever touches memory another agent may be writing.
-    // ..f: towards the first curl's neighbour (y + SG), ..b: the opposite side (signed offsets)
-    const int tyf = REV ? 0 : TY - 1, tyb = REV ? TY - 1 : 0;
-    const int eyf = ty == tyf ? 0 : SG * EY, eyb = ty == tyb ? 0 : -SG * EY;
-    const int hyf = ty == tyf ? 0 : SG * TX, hyb = ty == tyb ? 0 : -SG * TX;
+    // ..f: towards the first curl's neighbour (y + SGY), ..b: the opposite side (signed offsets)
+    const int tyf = SGY < 0 ? 0 : TY - 1, tyb = SGY < 0 ? TY - 1 : 0;
+    const int eyf = ty == tyf ? 0 : SGY * EY, eyb = ty == tyb ? 0 : -SGY * EY;
+    const int hyf = ty == tyf ? 0 : SGY * TX, hyb = ty == tyb ? 0 : -SGY * TX;
 
     const int64_t Nxy = (int64_t)Nx * Ny;
-    const int64_t dN = SG * Nxy;                  // material stride to the next plane of the march
+    const int64_t dN = SGZ * Nxy;                 // material stride to the next plane of the march
     const int64_t mcell = (int64_t)cj * Nx + ci;  // in-plane index into the ghosted material arrays
 
     // E(k) own, H(k-1) own, G state
@@ -312,7 +317,7 @@ __global__ void __launch_bounds__(TX *TY, (TX * TY <= 256 ? 2 : 1)) apply_tiled_
     for (int n = 0; n + 1 < nplanes; ++n) {
         const int k = kof(n);                                   // local plane whose H is computed (and y, if n >= 1)
         const double2 *es = ering + (n % NST) * STAGE;          // plane k
-        const double2 *en = ering + ((n + 1) % NST) * STAGE;    // plane k+SG
+        const double2 *en = ering + ((n + 1) % NST) * STAGE;    // plane k+SGZ
         const bool do_out = out_ok && (n >= 1);
         const int64_t mk = (int64_t)(k + 1) * Nxy + mcell;      // ghosted material index of plane k
 
@@ -341,9 +346,9 @@ __global__ void __launch_bounds__(TX *TY, (TX * TY <= 256 ? 2 : 1)) apply_tiled_
         // Off-diagonal material exists only at material interfaces: a per-(tile, plane) occupancy mask (CTA-uniform)
         // lets the kernel skip the six off-diagonal streams and the corner terms on empty blocks (exact zeros).
         const bool hasn =
-            HAS_OFF && (tp.offmask == nullptr || __ldg(&tp.offmask[(int64_t)(k + SG + 1) * ntile + tile]) != 0);
+            HAS_OFF && (tp.offmask == nullptr || __ldg(&tp.offmask[(int64_t)(k + SGZ + 1) * ntile + tile]) != 0);
         if (HAS_OFF && n + 3 < nplanes &&
-            (tp.offmask == nullptr || __ldg(&tp.offmask[(int64_t)(k + 3 * SG + 1) * ntile + tile]) != 0)) {
+            (tp.offmask == nullptr || __ldg(&tp.offmask[(int64_t)(k + 3 * SGZ + 1) * ntile + tile]) != 0)) {
 #pragma unroll
             for (int e = 0; e < 6; ++e) prefetch_l2(&p.mo[e][mk + 3 * dN]);
         }
@@ -355,8 +360,8 @@ __global__ void __launch_bounds__(TX *TY, (TX * TY <= 256 ? 2 : 1)) apply_tiled_
 
         mbar_wait(&bars[(n + 1) % NST], ((n + 1) / NST) & 1);
         const double2 En0 = en[eo], En1 = en[eo + EC], En2 = en[eo + 2 * EC];
-        const double2 Exp1 = es[eo + EC + SG * EX], Exp2 = es[eo + 2 * EC + SG * EX];   // E_y, E_z at x+SG
-        const double2 Eyp0 = es[eo + eyf], Eyp2 = es[eo + 2 * EC + eyf];                // E_x, E_z at y+SG
+        const double2 Exp1 = es[eo + EC + SGX * EX], Exp2 = es[eo + 2 * EC + SGX * EX];   // E_y, E_z at x+SGX
+        const double2 Eyp0 = es[eo + eyf], Eyp2 = es[eo + 2 * EC + eyf];                  // E_x, E_z at y+SGY
         const double2 a0x = cxs[0 * TX + tx], a1x = cxs[1 * TX + tx];
         const double2 a0y = cys[0 * TY + ty], a1y = cys[1 * TY + ty];
         const double2 a0z = czs[0 * LZP + n], a1z = czs[1 * LZP + n];
@@ -405,7 +410,7 @@ __global__ void __launch_bounds__(TX *TY, (TX * TY <= 256 ? 2 : 1)) apply_tiled_
         double2 o01 = c_zero(), o02 = c_zero(), o10 = c_zero(), o12 = c_zero(), o20 = c_zero(), o21 = c_zero();
         if (HAS_OFF) {
             if (hasn) {
-                const int64_t mk1 = mk + dN;                    // plane k+SG
+                const int64_t mk1 = mk + dN;                    // plane k+SGZ
                 o01 = ldg2(&p.mo[0][mk1]); o02 = ldg2(&p.mo[1][mk1]);
                 o10 = ldg2(&p.mo[2][mk1]); o12 = ldg2(&p.mo[3][mk1]);
                 o20 = ldg2(&p.mo[4][mk1]); o21 = ldg2(&p.mo[5][mk1]);
@@ -422,9 +427,9 @@ __global__ void __launch_bounds__(TX *TY, (TX * TY <= 256 ? 2 : 1)) apply_tiled_
             const double2 b0x = cxs[2 * TX + tx], b1x = cxs[3 * TX + tx];
             const double2 b0y = cys[2 * TY + ty], b1y = cys[3 * TY + ty];
             const double2 b0z = czs[2 * LZP + n], b1z = czs[3 * LZP + n];
-            const double2 Hy_xm = hb[ho + NT - SG], Hz_xm = hb[ho + 2 * NT - SG];     // H_y, H_z at x-SG
-            const double2 Hx_ym = hb[ho + hyb], Hz_ym = hb[ho + 2 * NT + hyb];          // H_x, H_z at y-SG
-            // y = C2 H :  yx = Dy Hz - Dz Hy,  yy = Dz Hx - Dx Hz,  yz = Dx Hy - Dy Hx   (differences towards -SG)
+            const double2 Hy_xm = hb[ho + NT - SGX], Hz_xm = hb[ho + 2 * NT - SGX];   // H_y, H_z at x-SGX
+            const double2 Hx_ym = hb[ho + hyb], Hz_ym = hb[ho + 2 * NT + hyb];          // H_x, H_z at y-SGY
+            // y = C2 H :  yx = Dy Hz - Dz Hy,  yy = Dz Hx - Dx Hz,  yz = Dx Hy - Dy Hx   (differences towards -SG.)
             yx = c_mul(b0y, Hz);
             yx = c_fma(b1y, Hz_ym, yx);
             yx = c_fms(b0z, Hy, yx);
@@ -439,11 +444,11 @@ __global__ void __launch_bounds__(TX *TY, (TX * TY <= 256 ? 2 : 1)) apply_tiled_
             yz = c_fms(b1y, Hx_ym, yz);
         }
 
-        double2 Gz1 = c_zero();                                 // G_z(k+SG) own
+        double2 Gz1 = c_zero();                                 // G_z(k+SGZ) own
         if (HAS_OFF && hasn) {
-            // G(k+SG) at this corner: in-averages of plane k+SG (still resident in the ring), then the off-diagonal
+            // G(k+SGZ) at this corner: in-averages of plane k+SGZ (still resident in the ring), then the off-diagonal
             // material entries; G_x, G_y go to the buffer the NEXT iteration reads after its barrier
-            const double2 Ax = c_fma(cxs[5 * TX + tx], en[eo - SG * EX], c_mul(cxs[4 * TX + tx], En0));
+            const double2 Ax = c_fma(cxs[5 * TX + tx], en[eo - SGX * EX], c_mul(cxs[4 * TX + tx], En0));
             const double2 Ay = c_fma(cys[5 * TY + ty], en[eo + EC + eyb], c_mul(cys[4 * TY + ty], En1));
             const double2 Az = c_fma(czs[5 * LZP + n + 1], Eo2, c_mul(czs[4 * LZP + n + 1], En2));
             double2 *gn = gbuf + ((n + 1) & 1) * GST;
@@ -461,7 +466,7 @@ __global__ void __launch_bounds__(TX *TY, (TX * TY <= 256 ? 2 : 1)) apply_tiled_
                     // G(k): own values and neighbours were written in the previous iteration
                     const double2 *gc = gbuf + (n & 1) * GST;
                     yx = c_fma(cxs[6 * TX + tx], gc[ho], yx);
-                    yx = c_fma(cxs[7 * TX + tx], gc[ho + SG], yx);
+                    yx = c_fma(cxs[7 * TX + tx], gc[ho + SGX], yx);
                     yy = c_fma(cys[6 * TY + ty], gc[ho + NT], yy);
                     yy = c_fma(cys[7 * TY + ty], gc[ho + NT + hyf], yy);
                 }
@@ -566,9 +571,9 @@ size_t tiled_smem_bytes() {
                sizeof(double2) + NST * 8 + 128;
 }
 
-template <bool CMPFIRST, bool HAS_OFF, bool HAS_Q, int TX, int TY, bool DOT, bool REV>
+template <bool CMPFIRST, bool HAS_OFF, bool HAS_Q, int TX, int TY, bool DOT, int ARR>
 cudaError_t launch_variant(const TiledParams &tp, cudaStream_t s) {
-    auto kern = apply_tiled_kernel<CMPFIRST, HAS_OFF, HAS_Q, TX, TY, DOT, REV>;
+    auto kern = apply_tiled_kernel<CMPFIRST, HAS_OFF, HAS_Q, TX, TY, DOT, ARR>;
     const size_t smem = tiled_smem_bytes<CMPFIRST, HAS_OFF, HAS_Q, TX, TY>();
     static bool attr_set[64] = {};   // per device: the opt-in to > 48 KB dynamic shared memory is a per-device attribute
     int dev = 0;
@@ -586,9 +591,10 @@ cudaError_t launch_variant(const TiledParams &tp, cudaStream_t s) {
 
 }  // namespace
 
-// the two uniform arrangements; mixed boundft (first curl forward on some axes only) runs on the general kernel
 bool tiled_supported(const ApplyParams &p) {
-    return p.s1[0] == p.s1[1] && p.s1[1] == p.s1[2] && (p.s1[0] == 1 || p.s1[0] == -1) && p.nzl >= 1;
+    for (int w = 0; w < 3; ++w)
+        if (p.s1[w] != 1 && p.s1[w] != -1) return false;
+    return p.nzl >= 1;
 }
 
 // Pick the z-chunk length: enough CTAs to fill 148 SMs for several waves, little ring-prologue overhead.
@@ -628,12 +634,15 @@ static cudaError_t launch_tile(const ApplyParams &p, int kl_begin, int kl_end, c
     tp.offmask = (p.offmask && p.offmask_ty == TY) ? p.offmask : nullptr;
     const bool cf = tp.a.cmpfirst != 0, off = p.has_off != 0 && p.has_mass != 0 && !diag_only, q = p.has_q != 0;
     cudaError_t e;
-    const bool rev = p.s1[0] < 0;
+    const int nfwd = (p.s1[0] > 0) + (p.s1[1] > 0) + (p.s1[2] > 0);
+    const int arr = nfwd == 3 ? 0 : nfwd == 0 ? 1 : 2;
 #define V(CF, OFF, Q)                                                                                          \
-    e = (p.dot_mode == 2) ? (rev ? launch_variant<CF, OFF, Q, TX, TY, true, true>(tp, s)                       \
-                                 : launch_variant<CF, OFF, Q, TX, TY, true, false>(tp, s))                     \
-                          : (rev ? launch_variant<CF, OFF, Q, TX, TY, false, true>(tp, s)                      \
-                                 : launch_variant<CF, OFF, Q, TX, TY, false, false>(tp, s))
+    e = (p.dot_mode == 2) ? (arr == 0   ? launch_variant<CF, OFF, Q, TX, TY, true, 0>(tp, s)                   \
+                             : arr == 1 ? launch_variant<CF, OFF, Q, TX, TY, true, 1>(tp, s)                   \
+                                        : launch_variant<CF, OFF, Q, TX, TY, true, 2>(tp, s))                  \
+                          : (arr == 0   ? launch_variant<CF, OFF, Q, TX, TY, false, 0>(tp, s)                  \
+                             : arr == 1 ? launch_variant<CF, OFF, Q, TX, TY, false, 1>(tp, s)                  \
+                                        : launch_variant<CF, OFF, Q, TX, TY, false, 2>(tp, s))
     if (cf) {
         if (off) { if (q) V(true, true, true); else V(true, true, false); }
         else     { if (q) V(true, false, true); else V(true, false, false); }
@@ -688,7 +697,7 @@ cudaError_t tiled_build_offmask(const ApplyParams &p, unsigned char **mask, int 
     *corr_list = nullptr;
     *corr_count = 0;
     if (!tiled_supported(p) || !p.has_off || !p.has_mass) return cudaSuccess;
-    const int sg = p.s1[0] < 0 ? -1 : 1;
+    const int sg = p.s1[2] < 0 ? -1 : 1;    // the corner terms of plane k need G(k) and G(k + s1_z)
     int TY = env_ty() ? env_ty() : 8;
     std::vector<unsigned char> h;
     cudaError_t e = build_mask_for(p, TY, mask, frac, s, &h);

@@ -68,16 +68,17 @@ def test_apply_all_boundary_conditions(kernel, N):
 
 @pytest.mark.parametrize("boundft", list(itertools.product([EE, HH], repeat=3)))
 def test_apply_all_boundft(boundft):
-    """all 2^3 boundft choices (tiled kernel for the two uniform arrangements, general kernel for mixed ones)."""
+    """all 2^3 boundft choices, both formulations, on the tiled kernel (ARR = 0 / 1 / 2 instantiations)."""
     for isbloch in ((True, False, True), (False, True, False)):
         for ft in (EE, HH):
             p = Problem((9, 6, 7), isbloch, boundft, full_eps=(ft == EE), with_mu=True, ft=ft, full_mu=(ft == HH))
             A_ref, _ = p.oracle_csc()
-            A = p.operator(device=0)
+            A = p.operator(device=0, kernel=KERNELS["tiled"])
             x = p.random_x()
             err = rel(_apply_dev(A, x), A_ref.matvec(x))
+            errT = rel(_apply_dev(A, x, transpose=True), A_ref.to_scipy().T.tocsc() @ x)
             A.close()
-            assert err < TOL, (boundft, isbloch, ft, err)
+            assert err < TOL and errT < TOL, (boundft, isbloch, ft, err, errT)
 
 
 MIRRORED = (  # (ft, boundft, full_eps, with_mu): first curl backward on every axis
@@ -129,6 +130,32 @@ def test_mirrored_arrangement_deep_grid_and_sparse_offdiag():
         At.close()
         An.close()
     p = Problem((40, 33, 70), (False, True, False), ft=HH, with_mu=True)
+    A = p.operator(device=0, kernel=KERNELS["tiled"])
+    x = p.random_x()
+    assert rel(_apply_dev(A, x), p.oracle_matfree()(x)) < TOL
+    A.close()
+
+
+@pytest.mark.parametrize("boundft", [(EE, HH, EE), (HH, EE, EE), (HH, HH, EE), (EE, EE, HH), (EE, HH, HH), (HH, EE, HH)])
+def test_mixed_boundft_on_tiled_kernel(boundft):
+    """first curl forward on some axes only (ARR = 2: per-axis directions at run time): several z-chunks and tiles,
+    sparse off-diagonal eps (diagonal kernel + marching correction) and dense (fused kernel), both layouts, HH
+    formulation; against the matrix-free oracle and the general kernel."""
+    for isbloch, z1, cmpfirst in (((True, False, True), 33, True), ((False, True, False), 60, False)):
+        p = Problem((70, 45, 90), isbloch, boundft, full_eps=True, with_mu=True, cmpfirst=cmpfirst)
+        for v, u in itertools.permutations(range(3), 2):
+            p.eps[:, :, :20, v, u] = 0
+            p.eps[:, :, z1:, v, u] = 0
+            p.eps[:25, :, :, v, u] = 0
+        x = p.random_x()
+        At = p.operator(device=0, kernel=KERNELS["tiled"])
+        An = p.operator(device=0, kernel=KERNELS["naive"])
+        yt, yn = _apply_dev(At, x), _apply_dev(An, x)
+        assert rel(yt, yn) < 1e-13, (boundft, isbloch)
+        assert rel(yt, p.oracle_matfree()(x)) < TOL, (boundft, isbloch)
+        At.close()
+        An.close()
+    p = Problem((40, 33, 50), (True, True, False), boundft, ft=HH, full_mu=True)
     A = p.operator(device=0, kernel=KERNELS["tiled"])
     x = p.random_x()
     assert rel(_apply_dev(A, x), p.oracle_matfree()(x)) < TOL
