@@ -51,6 +51,7 @@ static void free_device(Ctx *c) {
     auto F = [](auto *&p) { if (p) cudaFree((void *)p); p = nullptr; };
     F(c->coef_dev); F(c->mat_dev); F(c->halo_lo); F(c->halo_hi); F(c->work); F(c->scal); F(c->partial);
     F(c->stage_x); F(c->stage_y); F(c->flush_buf); F(c->offmask); F(c->corr_list); F(c->dot_partial); F(c->dot_ticket);
+    F(c->halo_flag);
     if (c->scal_host) cudaFreeHost(c->scal_host);
     c->scal_host = nullptr;
 }
@@ -288,6 +289,36 @@ int apply_device(Ctx *c, const double2 *x, double2 *y, bool transpose) {
         FDFD_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_halo, 0));
         c->comm_pending = false;
     }
+    // EXPERIMENTAL, opt-in, not validated for back-to-back applies: ONE launch that does not wait for the exchange.
+    // The kernel schedules the two z-chunks that touch a neighbour's plane last and gates them on a flag word that
+    // a stream memory operation sets behind the NCCL exchange, so the transfer runs under the interior chunks.
+    // Needs at least two interior chunks per tile column (several waves of CTAs ahead of the gated ones).  Status
+    // (2x B200): results equal the single-slab operator when every apply is followed by a host sync; a stream of
+    // back-to-back applies (bench.py) did not finish - the NCCL kernel of apply i+1 and the apply kernel i+1
+    // become runnable together and, if the apply kernel is dispatched first, its gated CTAs can occupy every SM
+    // before the NCCL kernel gets one.  The gated spin is bounded (traps after ~4 s) so this shows as an error,
+    // not a hang.  See DESIGN.md section 10 for the fix that is planned (copy-engine / peer-memory transfer).
+    static const bool inkernel_wait = getenv("FDFD_INKERNEL_HALO_WAIT") != nullptr;
+    if (c->d.nranks > 1 && use_tiled && inkernel_wait && c->d.order_cmpfirst && !dbg_skip_halo && stream_write_u32_available() &&
+        tiled_plan_nchunk(p) >= 4) {
+        if (!c->halo_flag) {
+            FDFD_CUDA(c, cudaMalloc((void **)&c->halo_flag, sizeof(uint32_t)));
+            FDFD_CUDA(c, cudaMemset(c->halo_flag, 0, sizeof(uint32_t)));
+        }
+        const uint32_t epoch = ++c->halo_epoch;
+        FDFD_CUDA(c, cudaEventRecord(c->ev_x, c->stream));
+        FDFD_CUDA(c, cudaStreamWaitEvent(c->stream_comm, c->ev_x, 0));
+        if ((r = halo_exchange(c, x, c->halo_lo, c->halo_hi, c->stream_comm)) != FDFD_OK) return r;
+        if ((r = stream_write_u32(c, c->stream_comm, c->halo_flag, epoch)) != FDFD_OK) return r;
+        FDFD_CUDA(c, cudaEventRecord(c->ev_halo, c->stream_comm));
+        c->comm_pending = true;     // later NCCL operations order themselves after this exchange through ev_halo
+        p.halo_flag = c->halo_flag;
+        p.halo_expect = epoch;
+        int nl = 0;
+        FDFD_CUDA(c, launch_apply_tiled(p, 0, p.nzl, c->stream, &nl));
+        c->launches += nl;
+        return FDFD_OK;
+    }
     if (c->d.nranks > 1 && use_tiled && p.nzl >= 4 && split_overlap) {
         // z-slabs: the halo exchange (NCCL, own stream) overlaps the interior planes, which only need this rank's
         // own planes; the two boundary planes run on a high-priority stream as soon as the halos have landed,
@@ -524,7 +555,16 @@ int fdfd_create(fdfd_handle *out, const fdfd_desc *d) {
         if ((e = cudaMalloc((void **)&c->halo_hi, pb)) != cudaSuccess) return fail(e, "cudaMalloc(halo)");
         cudaMemset(c->halo_lo, 0, pb);
         cudaMemset(c->halo_hi, 0, pb);
-        if ((e = cudaStreamCreateWithFlags(&c->stream_comm, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
+        if (getenv("FDFD_INKERNEL_HALO_WAIT")) {
+            // experimental path only: the NCCL kernels must win the work distributor against an apply kernel whose
+            // last CTAs spin on them, so their stream gets the highest priority (the default paths are unchanged)
+            int lo_pri = 0, hi_pri = 0;
+            cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri);
+            e = cudaStreamCreateWithPriority(&c->stream_comm, cudaStreamNonBlocking, hi_pri);
+        } else {
+            e = cudaStreamCreateWithFlags(&c->stream_comm, cudaStreamNonBlocking);
+        }
+        if (e != cudaSuccess) return fail(e, "cudaStreamCreate");
         if ((e = cudaEventCreateWithFlags(&c->ev_x, cudaEventDisableTiming)) != cudaSuccess) return fail(e, "cudaEventCreate");
         if ((e = cudaEventCreateWithFlags(&c->ev_halo, cudaEventDisableTiming)) != cudaSuccess) return fail(e, "cudaEventCreate");
         if ((e = cudaEventCreateWithFlags(&c->ev_bnd, cudaEventDisableTiming)) != cudaSuccess) return fail(e, "cudaEventCreate");

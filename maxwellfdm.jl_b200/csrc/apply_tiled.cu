@@ -46,6 +46,8 @@ struct TiledParams {
     int32_t lz;               // planes per chunk
     int32_t kl_begin, kl_end; // local plane range of this launch
     const unsigned char *offmask;  // [ghosted plane][tile]: 1 if any off-diagonal material entry is non-zero there
+    const uint32_t *halo_flag;     // z-slabs, in-kernel halo wait: boundary chunks run last and spin on this word
+    uint32_t halo_expect;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -90,6 +92,12 @@ __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 
 template <bool CMPFIRST, int TX, int TY>
 struct TileIdx {
@@ -101,7 +109,7 @@ struct TileIdx {
     __device__ __forceinline__ static int h(int c, int tx, int ty) { return (c * TY + ty) * TX + tx; }
 };
 
-template <bool CMPFIRST, bool HAS_OFF, bool HAS_Q, int TX, int TY, bool DOT, int ARR>
+template <bool CMPFIRST, bool HAS_OFF, bool HAS_Q, int TX, int TY, bool DOT, int ARR, bool HWAIT>
 __global__ void __launch_bounds__(TX *TY, (TX * TY <= 256 ? 2 : 1)) apply_tiled_kernel(const __grid_constant__ TiledParams tp) {
     using TI = TileIdx<CMPFIRST, TX, TY>;
     // direction of the first curl's neighbour per axis (z: also the direction of the march); compile-time for the
@@ -135,7 +143,11 @@ __global__ void __launch_bounds__(TX *TY, (TX * TY <= 256 ? 2 : 1)) apply_tiled_
     const int tile_x = b % tp.ntx;
     b /= tp.ntx;
     const int tile_y = b % tp.nty;
-    const int chunk = b / tp.nty;
+    int chunk = b / tp.nty;
+    // in-kernel halo wait: the two chunks that touch a neighbour's plane are scheduled last (CTAs start in index
+    // order), so the exchange runs behind the interior chunks and the spin below normally falls straight through
+    const bool halo_wait = HWAIT && tp.halo_flag != nullptr;   // HWAIT = false: compiled out
+    if (halo_wait) chunk = chunk < tp.nchunk - 2 ? chunk + 1 : (chunk == tp.nchunk - 2 ? 0 : tp.nchunk - 1);
     const int ox = tile_x * (TX - 2) - 1, oy = tile_y * (TY - 2) - 1;
     const int tile = tile_y * tp.ntx + tile_x, ntile = tp.ntx * tp.nty;
     const int kc0 = tp.kl_begin + chunk * tp.lz;
@@ -239,6 +251,13 @@ __global__ void __launch_bounds__(TX *TY, (TX * TY <= 256 ? 2 : 1)) apply_tiled_
     if (tid == 0) {
         for (int s = 0; s < NST; ++s) mbar_init(&bars[s], 1);
         fence_barrier_init();
+        if (halo_wait && (chunk == 0 || chunk == tp.nchunk - 1)) {
+            uint32_t spins = 0;
+            while (ld_acquire_sys(tp.halo_flag) != tp.halo_expect) {
+                __nanosleep(200);
+                if (++spins > 20000000u) __trap();   // ~4 s: the exchange never arrived - fail loudly, do not hang
+            }
+        }
     }
     {   // zero the tile positions no copy ever writes (symmetry-boundary halos, overhang): their values are
         // multiplied by zero coefficients or feed masked outputs, but must be finite
@@ -274,6 +293,7 @@ __global__ void __launch_bounds__(TX *TY, (TX * TY <= 256 ? 2 : 1)) apply_tiled_
         }
     }
     __syncthreads();
+    if (halo_wait) fence_proxy_async_all();   // the bulk copies below must not read the halo planes ahead of the flag
     if (wid < min(NST, nplanes)) issue_load(wid);   // warp m issues the initial load #m
 
     // Shared-memory addressing: ONE per-thread base index per tile; every neighbour / component offset is a
@@ -571,9 +591,9 @@ size_t tiled_smem_bytes() {
                sizeof(double2) + NST * 8 + 128;
 }
 
-template <bool CMPFIRST, bool HAS_OFF, bool HAS_Q, int TX, int TY, bool DOT, int ARR>
+template <bool CMPFIRST, bool HAS_OFF, bool HAS_Q, int TX, int TY, bool DOT, int ARR, bool HWAIT>
 cudaError_t launch_variant(const TiledParams &tp, cudaStream_t s) {
-    auto kern = apply_tiled_kernel<CMPFIRST, HAS_OFF, HAS_Q, TX, TY, DOT, ARR>;
+    auto kern = apply_tiled_kernel<CMPFIRST, HAS_OFF, HAS_Q, TX, TY, DOT, ARR, HWAIT>;
     const size_t smem = tiled_smem_bytes<CMPFIRST, HAS_OFF, HAS_Q, TX, TY>();
     static bool attr_set[64] = {};   // per device: the opt-in to > 48 KB dynamic shared memory is a per-device attribute
     int dev = 0;
@@ -614,6 +634,37 @@ static int pick_lz(int ncols, int nplanes, int cta_per_sm, int LZMAX) {
     return best_lz;
 }
 
+// run-time -> compile-time dispatch of the remaining template arguments; the halo-wait instantiations exist for the
+// cmp-first layout only (the z-slab fast paths require it)
+template <bool CF, bool OFF, bool Q, int TX, int TY, bool DOT, int ARR>
+static cudaError_t launch_hw(const TiledParams &tp, cudaStream_t s) {
+    if (tp.halo_flag == nullptr) return launch_variant<CF, OFF, Q, TX, TY, DOT, ARR, false>(tp, s);
+    if constexpr (CF) return launch_variant<CF, OFF, Q, TX, TY, DOT, ARR, true>(tp, s);
+    else return cudaErrorInvalidConfiguration;
+}
+
+template <bool CF, bool OFF, bool Q, int TX, int TY>
+static cudaError_t launch_select(const TiledParams &tp, cudaStream_t s, bool dot, int arr) {
+    if (dot) return arr == 0 ? launch_hw<CF, OFF, Q, TX, TY, true, 0>(tp, s)
+                  : arr == 1 ? launch_hw<CF, OFF, Q, TX, TY, true, 1>(tp, s)
+                             : launch_hw<CF, OFF, Q, TX, TY, true, 2>(tp, s);
+    return arr == 0 ? launch_hw<CF, OFF, Q, TX, TY, false, 0>(tp, s)
+         : arr == 1 ? launch_hw<CF, OFF, Q, TX, TY, false, 1>(tp, s)
+                    : launch_hw<CF, OFF, Q, TX, TY, false, 2>(tp, s);
+}
+
+template <int TX, int TY>
+static int plan_lz(const ApplyParams &p, int kl_begin, int kl_end) {
+    const int ntx = (p.Nx + (TX - 2) - 1) / (TX - 2), nty = (p.Ny + (TY - 2) - 1) / (TY - 2);
+    constexpr int LZMAX = lzmax_for(TX * TY);
+    int lz = pick_lz(ntx * nty, kl_end - kl_begin, TX * TY <= 256 ? 2 : 1, LZMAX);
+    if (const char *e = getenv("FDFD_LZ")) {   // tuning/debug override of the z-chunk length
+        const int v = atoi(e);
+        if (v >= 1 && v <= LZMAX) lz = v < kl_end - kl_begin ? v : kl_end - kl_begin;
+    }
+    return lz;
+}
+
 template <int TX, int TY>
 static cudaError_t launch_tile(const ApplyParams &p, int kl_begin, int kl_end, cudaStream_t s, bool diag_only = false) {
     TiledParams tp;
@@ -622,27 +673,21 @@ static cudaError_t launch_tile(const ApplyParams &p, int kl_begin, int kl_end, c
     tp.wrapy = p.wrap[1];
     tp.ntx = (p.Nx + (TX - 2) - 1) / (TX - 2);
     tp.nty = (p.Ny + (TY - 2) - 1) / (TY - 2);
-    constexpr int LZMAX = lzmax_for(TX * TY);
-    tp.lz = pick_lz(tp.ntx * tp.nty, kl_end - kl_begin, TX * TY <= 256 ? 2 : 1, LZMAX);
-    if (const char *e = getenv("FDFD_LZ")) {   // tuning/debug override of the z-chunk length
-        const int v = atoi(e);
-        if (v >= 1 && v <= LZMAX) tp.lz = v < kl_end - kl_begin ? v : kl_end - kl_begin;
-    }
+    tp.lz = plan_lz<TX, TY>(p, kl_begin, kl_end);
     tp.nchunk = (kl_end - kl_begin + tp.lz - 1) / tp.lz;
     tp.kl_begin = kl_begin;
     tp.kl_end = kl_end;
+    // in-kernel halo wait: whole-slab launches with at least one interior chunk ahead of the two boundary chunks
+    const bool gate = p.halo_flag != nullptr && kl_begin == 0 && kl_end == p.nzl && tp.nchunk >= 3;
+    if (p.halo_flag != nullptr && !gate) return cudaErrorInvalidConfiguration;   // the host must not have skipped its wait
+    tp.halo_flag = gate ? p.halo_flag : nullptr;
+    tp.halo_expect = p.halo_expect;
     tp.offmask = (p.offmask && p.offmask_ty == TY) ? p.offmask : nullptr;
     const bool cf = tp.a.cmpfirst != 0, off = p.has_off != 0 && p.has_mass != 0 && !diag_only, q = p.has_q != 0;
     cudaError_t e;
     const int nfwd = (p.s1[0] > 0) + (p.s1[1] > 0) + (p.s1[2] > 0);
     const int arr = nfwd == 3 ? 0 : nfwd == 0 ? 1 : 2;
-#define V(CF, OFF, Q)                                                                                          \
-    e = (p.dot_mode == 2) ? (arr == 0   ? launch_variant<CF, OFF, Q, TX, TY, true, 0>(tp, s)                   \
-                             : arr == 1 ? launch_variant<CF, OFF, Q, TX, TY, true, 1>(tp, s)                   \
-                                        : launch_variant<CF, OFF, Q, TX, TY, true, 2>(tp, s))                  \
-                          : (arr == 0   ? launch_variant<CF, OFF, Q, TX, TY, false, 0>(tp, s)                  \
-                             : arr == 1 ? launch_variant<CF, OFF, Q, TX, TY, false, 1>(tp, s)                  \
-                                        : launch_variant<CF, OFF, Q, TX, TY, false, 2>(tp, s))
+#define V(CF, OFF, Q) e = launch_select<CF, OFF, Q, TX, TY>(tp, s, p.dot_mode == 2, arr)
     if (cf) {
         if (off) { if (q) V(true, true, true); else V(true, true, false); }
         else     { if (q) V(true, false, true); else V(true, false, false); }
@@ -742,6 +787,19 @@ cudaError_t tiled_build_offmask(const ApplyParams &p, unsigned char **mask, int 
         }
     }
     return cudaSuccess;
+}
+
+// tile height of the (first) kernel launch_apply_tiled will launch for p
+static int main_kernel_ty(const ApplyParams &p) {
+    const bool full = p.has_off != 0 && p.has_mass != 0;
+    if (!full) return env_ty() == 16 ? 16 : 8;
+    return (p.offmask && p.offmask_ty == 8) ? 8 : 16;
+}
+
+int tiled_plan_nchunk(const ApplyParams &p) {
+    if (!tiled_supported(p)) return 0;
+    const int lz = main_kernel_ty(p) == 8 ? plan_lz<32, 8>(p, 0, p.nzl) : plan_lz<32, 16>(p, 0, p.nzl);
+    return (p.nzl + lz - 1) / lz;
 }
 
 cudaError_t launch_apply_tiled(const ApplyParams &p, int kl_begin, int kl_end, cudaStream_t s, int *nlaunch) {

@@ -157,6 +157,29 @@ int halo_exchange_ghosted(Ctx *c, double2 *arr, cudaStream_t s) {
     return exchange_planes(c, arr + Nxy, arr + nzl * Nxy, 0, arr, arr + (nzl + 1) * Nxy, 0, 1, Nxy, s);
 }
 
+// cuStreamWriteValue32 resolved from the driver library at run time (the library links cudart statically only)
+typedef int (*cuStreamWriteValue32_t)(cudaStream_t, unsigned long long, uint32_t, unsigned int);
+static cuStreamWriteValue32_t load_write_value() {
+    static cuStreamWriteValue32_t fn = [] {
+        void *lib = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) return (cuStreamWriteValue32_t) nullptr;
+        void *f = dlsym(lib, "cuStreamWriteValue32_v2");
+        if (!f) f = dlsym(lib, "cuStreamWriteValue32");
+        return reinterpret_cast<cuStreamWriteValue32_t>(f);
+    }();
+    return fn;
+}
+
+bool stream_write_u32_available() { return load_write_value() != nullptr; }
+
+int stream_write_u32(Ctx *c, cudaStream_t s, uint32_t *dev_word, uint32_t value) {
+    cuStreamWriteValue32_t fn = load_write_value();
+    if (!fn) return set_err(c, FDFD_ESTATE, "cuStreamWriteValue32 not available");
+    const int r = fn(s, (unsigned long long)(uintptr_t)dev_word, value, 0u);
+    if (r != 0) return set_err(c, FDFD_ECUDA, "cuStreamWriteValue32 failed (" + std::to_string(r) + ")");
+    return FDFD_OK;
+}
+
 int allreduce_sum(Ctx *c, double *dev, int count, cudaStream_t s) {
     if (c->d.nranks == 1) return FDFD_OK;
     if (c->comm_pending) {   // keep NCCL operations on this communicator totally ordered

@@ -60,6 +60,10 @@ struct ApplyParams {
     const double2 *mo[6];   // -w^2 * P_vu, order (0,1),(0,2),(1,0),(1,2),(2,0),(2,1)
     const double2 *q[3];    // inverse of the middle diagonal parameter (mu^-1 for FT_EE)
     PlaneSet x;
+    // z-slabs, in-kernel halo wait (opt-in): the CTAs of the first / last z-chunk spin until *halo_flag ==
+    // halo_expect (written by a stream memory operation behind the NCCL exchange); null = halos already in place
+    const uint32_t *halo_flag;
+    uint32_t halo_expect;
     const unsigned char *offmask;  // occupancy mask of the off-diagonal material (tiled kernel), or null
     int32_t offmask_ty;            // tile height the mask was built for
     const int4 *corr_list;         // sparse off-diagonals: work items (tile, ks, ke) of the correction pass
@@ -128,6 +132,8 @@ struct Ctx {
     // halo buffers (device): 2 receive planes, 2 send staging not needed (planes are contiguous
     // or 3 contiguous pieces)
     double2 *halo_lo = nullptr, *halo_hi = nullptr;
+    uint32_t *halo_flag = nullptr;      // device word the exchange stream sets to halo_epoch when the planes have landed
+    uint32_t halo_epoch = 0;
 
     // Krylov workspace
     double2 *work = nullptr;
@@ -183,6 +189,8 @@ cudaError_t launch_apply_naive(const ApplyParams &p, cudaStream_t s);
 // returns cudaErrorNotSupported when the tiled kernel does not cover this configuration
 cudaError_t launch_apply_tiled(const ApplyParams &p, int kl_begin, int kl_end, cudaStream_t s, int *nlaunch);
 bool tiled_supported(const ApplyParams &p);
+// number of z-chunks per tile column the main kernel of launch_apply_tiled(p, 0, nzl) will use
+int tiled_plan_nchunk(const ApplyParams &p);
 cudaError_t tiled_build_offmask(const ApplyParams &p, unsigned char **mask, int *ty_used, double *frac, int4 **corr_list,
                                 int *corr_count, cudaStream_t s);
 cudaError_t launch_offdiag_correction(const ApplyParams &p, const int4 *items, int count, int ntx, int kl_begin,
@@ -208,6 +216,10 @@ void comm_destroy(Ctx *c);
 int halo_exchange(Ctx *c, const double2 *v, double2 *lo, double2 *hi, cudaStream_t s);
 int halo_exchange_ghosted(Ctx *c, double2 *arr, cudaStream_t s);
 int allreduce_sum(Ctx *c, double *dev, int count, cudaStream_t s);
+// stream memory operation (no SM needed): *dev_word = value once everything enqueued before it on s has completed;
+// returns FDFD_ESTATE when the driver entry point is unavailable
+int stream_write_u32(Ctx *c, cudaStream_t s, uint32_t *dev_word, uint32_t value);
+bool stream_write_u32_available();
 
 // api.cu -------------------------------------------------------------------------------------------
 int ensure_ready(Ctx *c);
