@@ -5,6 +5,7 @@
 // NCCL is resolved at run time with dlopen so that single-GPU use has no NCCL dependency and so that
 // a process which already loaded torch's bundled libnccl.so.2 shares that copy.
 #include <dlfcn.h>
+#include <cstdlib>
 #include <cstring>
 
 #include "fdfd_internal.h"
@@ -103,10 +104,12 @@ int comm_init(Ctx *c, const char id[128]) {
     FDFD_NCCL(c, api->CommInitRank(&comm, c->d.nranks, uid, c->d.rank));
     c->comm = comm;
     c->dirty = true;  // material ghost planes must be exchanged
+    if (getenv("FDFD_PEER_HALO")) return peer_halo_init(c);   // experimental, see PeerHalo
     return FDFD_OK;
 }
 
 void comm_destroy(Ctx *c) {
+    peer_halo_destroy(c);
     if (c->comm && c->nccl) c->nccl->CommDestroy((ncclComm_t)c->comm);
     c->comm = nullptr;
 }
@@ -144,6 +147,7 @@ int halo_exchange(Ctx *c, const double2 *v, double2 *lo, double2 *hi, cudaStream
     const int64_t nzl = c->k1 - c->k0;
     if (c->d.order_cmpfirst) {
         const int64_t pl = 3 * Nxy;
+        if (c->peer.ready && lo == c->halo_lo && hi == c->halo_hi) return peer_halo_exchange(c, v, v + (nzl - 1) * pl, s);
         return exchange_planes(c, v, v + (nzl - 1) * pl, 0, lo, hi, 0, 1, pl, s);
     }
     // component-major: 3 pieces of Nx*Ny, component stride Nxy*nzl in the slab, Nxy in the halo buffer
@@ -171,6 +175,37 @@ static cuStreamWriteValue32_t load_write_value() {
 }
 
 bool stream_write_u32_available() { return load_write_value() != nullptr; }
+
+typedef int (*cuStreamWaitValue32_t)(cudaStream_t, unsigned long long, uint32_t, unsigned int);
+int stream_wait_geq_u32(Ctx *c, cudaStream_t s, uint32_t *dev_word, uint32_t value) {
+    static cuStreamWaitValue32_t fn = [] {
+        void *lib = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) return (cuStreamWaitValue32_t) nullptr;
+        void *f = dlsym(lib, "cuStreamWaitValue32_v2");
+        if (!f) f = dlsym(lib, "cuStreamWaitValue32");
+        return reinterpret_cast<cuStreamWaitValue32_t>(f);
+    }();
+    if (!fn) return set_err(c, FDFD_ESTATE, "cuStreamWaitValue32 not available");
+    const int r = fn(s, (unsigned long long)(uintptr_t)dev_word, value, 0u /* CU_STREAM_WAIT_VALUE_GEQ */);
+    if (r != 0) return set_err(c, FDFD_ECUDA, "cuStreamWaitValue32 failed (" + std::to_string(r) + ")");
+    return FDFD_OK;
+}
+
+// Setup-time byte exchange with the z-neighbours (IPC handles): same pairing and order as exchange_planes.
+int comm_exchange_bytes(Ctx *c, const void *dev_mine, void *dev_from_up, void *dev_from_dn, size_t bytes, cudaStream_t s) {
+    if (!c->comm) return set_err(c, FDFD_ESTATE, "comm_exchange_bytes: no communicator");
+    int up, dn;
+    halo_neighbours(c->d.nranks, c->d.rank, c->d.isbloch[2] != 0, &up, &dn);
+    ncclComm_t comm = (ncclComm_t)c->comm;
+    NcclApi *n = c->nccl;
+    FDFD_NCCL(c, n->GroupStart());
+    if (up >= 0) FDFD_NCCL(c, n->Send(dev_mine, bytes, ncclInt8, up, comm, s));
+    if (dn >= 0) FDFD_NCCL(c, n->Recv(dev_from_dn, bytes, ncclInt8, dn, comm, s));
+    if (dn >= 0) FDFD_NCCL(c, n->Send(dev_mine, bytes, ncclInt8, dn, comm, s));
+    if (up >= 0) FDFD_NCCL(c, n->Recv(dev_from_up, bytes, ncclInt8, up, comm, s));
+    FDFD_NCCL(c, n->GroupEnd());
+    return FDFD_OK;
+}
 
 int stream_write_u32(Ctx *c, cudaStream_t s, uint32_t *dev_word, uint32_t value) {
     cuStreamWriteValue32_t fn = load_write_value();

@@ -84,6 +84,19 @@ struct ApplyParams {
 // ---------------------------------------------------------------------------------------------
 struct NcclApi;  // comm.cpp
 
+// Halo exchange over NVLink peer memory without any SM-resident collective (EXPERIMENTAL, FDFD_PEER_HALO, written in
+// round 1 and NOT yet run on hardware): neighbours' halo buffers and flag words are mapped with CUDA IPC; a plane
+// travels by a copy-engine cudaMemcpyAsync into the neighbour's buffer, ordering is by stream memory operations.
+struct PeerHalo {
+    bool ready = false;
+    uint32_t *flags = nullptr;       // local, written by the neighbours: [DATA_LO, DATA_HI, FREE_UP, FREE_DN]
+    double2 *up_halo_lo = nullptr;   // the up neighbour's halo_lo   (receives my last plane)
+    double2 *dn_halo_hi = nullptr;   // the down neighbour's halo_hi (receives my first plane)
+    uint32_t *up_flags = nullptr, *dn_flags = nullptr;
+    void *mapped[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // bases to cudaIpcCloseMemHandle
+    uint32_t epoch = 0;
+};
+
 struct Ctx {
     fdfd_desc d{};
     int dev = 0;
@@ -153,6 +166,7 @@ struct Ctx {
     // NCCL
     void *comm = nullptr;
     NcclApi *nccl = nullptr;
+    PeerHalo peer;
 };
 
 int set_err(Ctx *c, int code, const std::string &msg);
@@ -219,6 +233,14 @@ int allreduce_sum(Ctx *c, double *dev, int count, cudaStream_t s);
 // stream memory operation (no SM needed): *dev_word = value once everything enqueued before it on s has completed;
 // returns FDFD_ESTATE when the driver entry point is unavailable
 int stream_write_u32(Ctx *c, cudaStream_t s, uint32_t *dev_word, uint32_t value);
+// stream s proceeds once (int32)(*dev_word - value) >= 0
+int stream_wait_geq_u32(Ctx *c, cudaStream_t s, uint32_t *dev_word, uint32_t value);
+// peer.cpp: set up / tear down the IPC mappings (collective over the neighbours), and the exchange itself
+int peer_halo_init(Ctx *c);
+void peer_halo_destroy(Ctx *c);
+int peer_halo_exchange(Ctx *c, const double2 *first_plane, const double2 *last_plane, cudaStream_t s);
+// raw byte exchange with the two z-neighbours over the NCCL communicator (setup only)
+int comm_exchange_bytes(Ctx *c, const void *dev_mine, void *dev_from_up, void *dev_from_dn, size_t bytes, cudaStream_t s);
 bool stream_write_u32_available();
 
 // api.cu -------------------------------------------------------------------------------------------

@@ -1,0 +1,107 @@
+// EXPERIMENTAL (FDFD_PEER_HALO=1), written in round 1 and NOT YET RUN ON HARDWARE - off by default.
+//
+// z-halo exchange over NVLink peer memory with no SM-resident collective: every rank maps its two neighbours' halo
+// buffers and flag words with CUDA IPC (handles travel once over the NCCL communicator).  Per exchange a plane moves
+// by ONE copy-engine cudaMemcpyAsync straight into the neighbour's receive buffer; ordering uses stream memory
+// operations (cuStreamWriteValue32 / cuStreamWaitValue32) on flag words that live in the RECEIVER's memory:
+//     DATA_LO / DATA_HI   "your halo_lo / halo_hi holds the planes of epoch e"      (written by the sender)
+//     FREE_UP / FREE_DN   "I have consumed what you sent me in epoch e"             (written by the receiver)
+// Exchange e on stream s:   release(e-1) to both neighbours            [s is ordered after the consumer of e-1]
+//                           wait FREE >= e-1, copy, write DATA = e     [towards each neighbour]
+//                           wait DATA >= e                             [from each neighbour]
+// Nothing here needs an SM, which is what the in-kernel halo wait (apply_tiled.cu, HWAIT) requires of its transfer.
+// Replaces the ncclSend/ncclRecv pair of comm.cpp; the reference has no distributed code.
+#include <cstring>
+
+#include "fdfd_internal.h"
+
+namespace fdfd {
+
+namespace {
+enum { DATA_LO = 0, DATA_HI = 1, FREE_UP = 2, FREE_DN = 3, NFLAGS = 4 };
+
+struct Handles {
+    cudaIpcMemHandle_t halo_lo, halo_hi, flags;
+};
+}  // namespace
+
+int peer_halo_init(Ctx *c) {
+    PeerHalo &ph = c->peer;
+    if (ph.ready || c->d.nranks == 1) return FDFD_OK;
+    if (!c->d.order_cmpfirst) return FDFD_OK;                 // component-major planes are not contiguous: NCCL path
+    int up, dn;
+    halo_neighbours(c->d.nranks, c->d.rank, c->d.isbloch[2] != 0, &up, &dn);
+    FDFD_CUDA(c, cudaMalloc((void **)&ph.flags, NFLAGS * sizeof(uint32_t)));
+    FDFD_CUDA(c, cudaMemset(ph.flags, 0, NFLAGS * sizeof(uint32_t)));
+    Handles mine;
+    FDFD_CUDA(c, cudaIpcGetMemHandle(&mine.halo_lo, c->halo_lo));
+    FDFD_CUDA(c, cudaIpcGetMemHandle(&mine.halo_hi, c->halo_hi));
+    FDFD_CUDA(c, cudaIpcGetMemHandle(&mine.flags, ph.flags));
+    // ship the handles to both neighbours (device staging: NCCL moves device memory)
+    unsigned char *stage = nullptr;
+    FDFD_CUDA(c, cudaMalloc((void **)&stage, 3 * sizeof(Handles)));
+    FDFD_CUDA(c, cudaMemcpy(stage, &mine, sizeof(Handles), cudaMemcpyHostToDevice));
+    int r = comm_exchange_bytes(c, stage, stage + sizeof(Handles), stage + 2 * sizeof(Handles), sizeof(Handles), c->stream);
+    if (r != FDFD_OK) { cudaFree(stage); return r; }
+    FDFD_CUDA(c, cudaStreamSynchronize(c->stream));
+    Handles from_up, from_dn;
+    FDFD_CUDA(c, cudaMemcpy(&from_up, stage + sizeof(Handles), sizeof(Handles), cudaMemcpyDeviceToHost));
+    FDFD_CUDA(c, cudaMemcpy(&from_dn, stage + 2 * sizeof(Handles), sizeof(Handles), cudaMemcpyDeviceToHost));
+    cudaFree(stage);
+    int nm = 0;
+    auto open = [&](const cudaIpcMemHandle_t &h, void **out) -> cudaError_t {
+        cudaError_t e = cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e == cudaSuccess) ph.mapped[nm++] = *out;
+        return e;
+    };
+    if (up >= 0) {
+        FDFD_CUDA(c, open(from_up.halo_lo, (void **)&ph.up_halo_lo));
+        FDFD_CUDA(c, open(from_up.flags, (void **)&ph.up_flags));
+    }
+    if (dn >= 0) {
+        FDFD_CUDA(c, open(from_dn.halo_hi, (void **)&ph.dn_halo_hi));
+        if (dn == up) ph.dn_flags = ph.up_flags;              // two ranks with a periodic z axis: one peer, map once
+        else FDFD_CUDA(c, open(from_dn.flags, (void **)&ph.dn_flags));
+    }
+    ph.epoch = 0;
+    ph.ready = true;
+    return FDFD_OK;
+}
+
+void peer_halo_destroy(Ctx *c) {
+    PeerHalo &ph = c->peer;
+    for (void *&m : ph.mapped) {
+        if (m) cudaIpcCloseMemHandle(m);
+        m = nullptr;
+    }
+    if (ph.flags) cudaFree(ph.flags);
+    ph = PeerHalo();
+}
+
+int peer_halo_exchange(Ctx *c, const double2 *first_plane, const double2 *last_plane, cudaStream_t s) {
+    PeerHalo &ph = c->peer;
+    int up, dn, r;
+    halo_neighbours(c->d.nranks, c->d.rank, c->d.isbloch[2] != 0, &up, &dn);
+    const size_t bytes = (size_t)c->plane * sizeof(double2);
+    const uint32_t e = ++ph.epoch;
+    // 1. the consumer of epoch e-1 is behind us on this stream: tell the senders their planes are consumed
+    if (dn >= 0 && (r = stream_write_u32(c, s, &ph.dn_flags[FREE_UP], e - 1)) != FDFD_OK) return r;
+    if (up >= 0 && (r = stream_write_u32(c, s, &ph.up_flags[FREE_DN], e - 1)) != FDFD_OK) return r;
+    // 2. send: my last plane -> up's halo_lo, my first plane -> down's halo_hi
+    if (up >= 0) {
+        if ((r = stream_wait_geq_u32(c, s, &ph.flags[FREE_UP], e - 1)) != FDFD_OK) return r;
+        FDFD_CUDA(c, cudaMemcpyAsync(ph.up_halo_lo, last_plane, bytes, cudaMemcpyDeviceToDevice, s));
+        if ((r = stream_write_u32(c, s, &ph.up_flags[DATA_LO], e)) != FDFD_OK) return r;
+    }
+    if (dn >= 0) {
+        if ((r = stream_wait_geq_u32(c, s, &ph.flags[FREE_DN], e - 1)) != FDFD_OK) return r;
+        FDFD_CUDA(c, cudaMemcpyAsync(ph.dn_halo_hi, first_plane, bytes, cudaMemcpyDeviceToDevice, s));
+        if ((r = stream_write_u32(c, s, &ph.dn_flags[DATA_HI], e)) != FDFD_OK) return r;
+    }
+    // 3. receive
+    if (dn >= 0 && (r = stream_wait_geq_u32(c, s, &ph.flags[DATA_LO], e)) != FDFD_OK) return r;
+    if (up >= 0 && (r = stream_wait_geq_u32(c, s, &ph.flags[DATA_HI], e)) != FDFD_OK) return r;
+    return FDFD_OK;
+}
+
+}  // namespace fdfd
