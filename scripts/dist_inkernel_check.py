@@ -1,9 +1,16 @@
-"""2+ GPU check of the opt-in single-launch apply with the in-kernel halo wait (FDFD_INKERNEL_HALO_WAIT): slab results
-must equal the single-slab GPU operator; then the apply is timed with and without nothing else changed."""
+"""2+ GPU check of the experimental z-slab paths: slab results must equal the single-slab GPU operator, first with a
+host sync after every apply, then (--stress) as a back-to-back stream of applies.
+    default        FDFD_INKERNEL_HALO_WAIT=1  (single launch, boundary z-chunks gated on a flag)
+    --peer         + FDFD_PEER_HALO=1         (SM-free exchange over IPC-mapped peer memory, csrc/peer.cpp)
+    --peer-only    FDFD_PEER_HALO=1 alone     (exchange, then launch)
+Run under `timeout`: round 1 saw the default mode stall in the back-to-back stream."""
 import os
 import sys
 
-os.environ["FDFD_INKERNEL_HALO_WAIT"] = "1"
+if "--peer-only" not in sys.argv:
+    os.environ["FDFD_INKERNEL_HALO_WAIT"] = "1"
+if "--peer" in sys.argv or "--peer-only" in sys.argv:
+    os.environ["FDFD_PEER_HALO"] = "1"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -49,6 +56,15 @@ def main():
             if not (e1 < 1e-13 and e2 < 1e-13):
                 fails.append((isbloch, e1, e2))
             A1.close()
+        if "--stress" in sys.argv:
+            if rank == 0:
+                print("stress: 50 back-to-back applies ...", flush=True)
+            ys2 = torch.empty_like(xs)
+            tot, _ = A.bench_apply(xs, ys2, warmup=3, iters=50)
+            if not torch.equal(ys2, ys[2]):
+                fails.append(("back-to-back result differs", isbloch))
+            if rank == 0:
+                print(f"stress ok: {tot / 50 * 1e3:.1f} us per apply", flush=True)
         A.close()
     flag = torch.tensor([len(fails)], device="cuda")
     dist.all_reduce(flag)
