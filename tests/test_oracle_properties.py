@@ -321,3 +321,39 @@ def test_P7_dipole_in_pml_box_direct_solve():
     # field decays into the PML: amplitude at the outer wall << amplitude at the PML entrance
     assert Ez[c, c - 1, 1] < 0.05 * Ez[c, c - 1, npml]
     assert Ez[1, c - 1, c] < 0.05 * Ez[npml, c - 1, c]
+
+
+# ---- P8 -------------------------------------------------------------------------------
+@pytest.mark.parametrize("boundft", [(EE, EE, EE), (HH, HH, HH), (EE, HH, EE)])
+def test_P8_cavity_spectrum_pins_the_symmetry_boundaries(boundft):
+    """Closed box with symmetry boundaries on all six faces, uniform grid, no PML, w = 0: A = Cm Ce is the discrete
+    curl-curl of a cavity.  Whatever the wall type per axis (boundft = EE: electric wall, HH: magnetic wall), the 1-D
+    Laplacians D- D+ / D+ D- have eigenvalues k_w(m)^2 = (2/d_w sin(m pi / 2N_w))^2, m = 0..N_w-1, so every non-zero
+    eigenvalue of A must be a sum kx^2 + ky^2 + kz^2 of such values, and every sum with all three mode numbers
+    >= 1 must occur at least twice (two polarisations).  (Sums with two zero mode numbers occur as well: the
+    tangential unknowns ON a wall stay in the system - boundary rules zero values, never positions - and couple
+    among themselves within the wall plane.)  This pins what the boundary rows of create_d do at both ends, which
+    the adjointness / nilpotency identities P1-P2 leave open."""
+    N, d = (3, 4, 5), (1.0, 0.8, 1.25)
+    lprim = tuple(np.arange(n + 1) * dw for n, dw in zip(N, d))
+    grid = Grid(lprim, (False, False, False))
+    sdl_e, sdl_m, sei, smi = create_stretched_dls(0.0, grid, ((0, 0, 0), (0, 0, 0)), boundft)
+    ph = np.ones(3, complex)
+    Ce, Cm = op.create_curls(sei, smi, boundft, grid.isbloch, ph)
+    A = (Cm.to_scipy() @ Ce.to_scipy()).toarray()
+    lam = np.linalg.eigvals(A)
+    assert np.abs(lam.imag).max() < 1e-10                      # real spectrum
+    lam = np.sort(lam.real)
+    assert lam.min() > -1e-10                                  # positive semi-definite
+    nz = lam[lam > 1e-8]
+    k2 = [np.array([(2 / dw * np.sin(m * np.pi / (2 * n))) ** 2 for m in range(n)]) for n, dw in zip(N, d)]
+    allowed = np.array([k2[0][a] + k2[1][b] + k2[2][c] for a in range(N[0]) for b in range(N[1]) for c in range(N[2])
+                        if a + b + c > 0])
+    dist = np.abs(nz[:, None] - allowed[None, :]).min(axis=1)
+    assert dist.max() < 1e-9, dist.max()                       # nothing outside the separable spectrum
+    full = np.array([k2[0][a] + k2[1][b] + k2[2][c] for a in range(1, N[0]) for b in range(1, N[1])
+                     for c in range(1, N[2])])
+    for v in full:
+        assert np.sum(np.abs(nz - v) < 1e-9) >= 2, v           # both polarisations of every volume mode
+    # the null space is exactly the discrete gradients + the decoupled wall unknowns: rank = #non-zero eigenvalues
+    assert np.linalg.matrix_rank(A, tol=1e-9) == nz.size
