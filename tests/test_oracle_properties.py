@@ -357,3 +357,33 @@ def test_P8_cavity_spectrum_pins_the_symmetry_boundaries(boundft):
         assert np.sum(np.abs(nz - v) < 1e-9) >= 2, v           # both polarisations of every volume mode
     # the null space is exactly the discrete gradients + the decoupled wall unknowns: rank = #non-zero eigenvalues
     assert np.linalg.matrix_rank(A, tol=1e-9) == nz.size
+
+
+# ---- P9 -------------------------------------------------------------------------------
+def test_P9_paramop_preserves_uniform_fields_on_nonuniform_grids():
+    """Default arrangement (boundft all-EE, unweighted output mean), non-uniform periodic grid (k = 0), one constant
+    full 3x3 tensor everywhere, uniform field E0: the two averaging steps of create_paramop must reproduce eps * E0
+    exactly.  The input mean takes E_w from the dual points i-1, i to the primal corner i with weights
+    dl_dual[i-1], dl_dual[i] over 2 dl_prim[i]; these sum to one only because a primal cell is made of the two
+    adjacent half dual cells - the identity fails if a cell size is paired with the wrong neighbour or taken from the
+    wrong (primal/dual) array.  (The mirror-image statement for primal -> dual means is NOT an identity on a
+    non-uniform grid - primal points are not midpoints of dual points - so it is not asserted for boundft = HH or for
+    the weighted output mean.)"""
+    N = (4, 5, 3)
+    rng = np.random.default_rng(9)
+    lprim = tuple(np.concatenate(([0.0], np.cumsum(0.5 + rng.random(n)))) for n in N)
+    grid = Grid(lprim, (True, True, True))
+    boundft = (EE, EE, EE)
+    sdl_e, sdl_m, sei, smi = create_stretched_dls(0.0, grid, ((0, 0, 0), (0, 0, 0)), boundft)
+    T = rng.standard_normal((3, 3)) + 1j * rng.standard_normal((3, 3))
+    eps = np.broadcast_to(T, N + (3, 3)).copy()
+    mu = np.broadcast_to(np.eye(3), N + (3, 3))
+    ph = np.ones(3, complex)
+    Pe, _ = op.create_paramops(eps, mu, sdl_e, sdl_m, sei, smi, boundft, grid.isbloch, ph, True, False)
+    E0 = np.array([0.7 - 0.2j, -1.1 + 0.4j, 0.3 + 0.9j])
+    e = op.field_arr2vec(np.broadcast_to(E0, N + (3,)).copy())
+    want = op.field_arr2vec(np.broadcast_to(T @ E0, N + (3,)).copy())
+    assert rel(Pe.matvec(e), want) < 1e-13
+    # the same inputs through the matrix-free oracle
+    mf = MatFreeOperator(EE, 1.0, eps, None, sdl_e, sdl_m, boundft, grid.isbloch, ph)
+    assert rel(mf.arr2vec(mf.Peps(mf.vec2arr(e))), want) < 1e-13
