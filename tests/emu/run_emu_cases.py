@@ -1,0 +1,202 @@
+"""TEST INFRASTRUCTURE ONLY - runs groups of parity cases against build/emu/libfdfd_emu.so (the CUDA sources
+compiled for the CPU, tests/emu/README.md) and checks every result against the oracle.
+
+    FDFD_B200_LIB=build/emu/libfdfd_emu.so python tests/emu/run_emu_cases.py GROUP [GROUP ...] [--full]
+
+Must run in its own process: the ctypes binding loads whatever FDFD_B200_LIB names, once.  "Device" buffers are host
+memory here, so the FDFD_DEVICE entry points are called with numpy arrays.  Started by tests/test_emu_kernels_cpu.py
+with FDFD_EMU_ASYNC / FDFD_EMU_SHUFFLE set to the scheduling mode under test."""
+import itertools
+import os
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+
+from oracle.grid import EE, HH                      # noqa: E402
+from oracle import operators as op                  # noqa: E402
+from problems import Problem, rel                   # noqa: E402
+import maxwellfdm_jl_b200 as fb                     # noqa: E402
+
+L = fb._lib
+TOL = 1e-12
+NAIVE, TILED = 1, 2
+FULL = "--full" in sys.argv
+
+
+def apply_dev(A, x, transpose=False):
+    x = np.ascontiguousarray(x, dtype=np.complex128)
+    y = np.full(A.n, np.nan + 1j * np.nan)
+    f = L.lib().fdfd_apply_transpose if transpose else L.lib().fdfd_apply
+    L.check(f(A._h, x.ctypes.data, y.ctypes.data, L.DEVICE), A._h)
+    return y
+
+
+def check(err, what, tol=TOL):
+    if not (err < tol):
+        raise AssertionError(f"{what}: rel. error {err:.3e} (tol {tol:.0e})")
+
+
+def g_apply():
+    """every Bloch/symmetry combination, diagonal / full eps / +mu, odd shapes, N_w = 1..3 (tiled kernel vs CSC oracle)"""
+    shapes = [(1, 1, 1), (2, 1, 3), (3, 2, 1), (5, 3, 2), (3, 5, 8), (31, 15, 4), (33, 17, 9), (70, 45, 6)]
+    combos = list(itertools.product([True, False], repeat=3))
+    n = 0
+    for N in shapes:
+        for i, isbloch in enumerate(combos):
+            for j, (full_eps, with_mu) in enumerate(((False, False), (True, False), (True, True))):
+                if not FULL and (i + j + sum(N)) % 4 != 0:      # default: a quarter of the combinations per shape
+                    continue
+                p = Problem(N, isbloch, full_eps=full_eps, with_mu=with_mu)
+                A_ref, _ = p.oracle_csc()
+                A = p.operator(device=0, kernel=TILED)
+                x = p.random_x()
+                check(rel(apply_dev(A, x), A_ref.matvec(x)), f"apply {N} {isbloch} full={full_eps} mu={with_mu}")
+                A.close()
+                n += 1
+    return n
+
+
+def g_boundft():
+    """all 2^3 boundft choices, both formulations, forward and transposed (ARR = 0 / 1 / 2 instantiations)"""
+    n = 0
+    for boundft in itertools.product([EE, HH], repeat=3):
+        for isbloch in ((True, False, True), (False, True, False)):
+            for ft in (EE, HH):
+                p = Problem((9, 6, 7), isbloch, boundft, full_eps=(ft == EE), with_mu=True, ft=ft, full_mu=(ft == HH))
+                A_ref, _ = p.oracle_csc()
+                A = p.operator(device=0, kernel=TILED)
+                x = p.random_x()
+                check(rel(apply_dev(A, x), A_ref.matvec(x)), f"boundft {boundft} {isbloch} ft={ft}")
+                check(rel(apply_dev(A, x, True), A_ref.to_scipy().T.tocsc() @ x), f"boundft^T {boundft} {isbloch} ft={ft}")
+                A.close()
+                n += 2
+    return n
+
+
+def g_layouts():
+    """component-major layout, weighted output average, omega = 0, host path == device path"""
+    n = 0
+    for cmpfirst, wo in ((False, False), (True, True), (False, True)):
+        p = Problem((37, 20, 11), (True, False, True), full_eps=True, with_mu=True, cmpfirst=cmpfirst, weighted_out=wo)
+        A_ref, _ = p.oracle_csc()
+        for k in (TILED, NAIVE):
+            A = p.operator(device=0, kernel=k)
+            x = p.random_x()
+            check(rel(apply_dev(A, x), A_ref.matvec(x)), f"layout cmpfirst={cmpfirst} wo={wo} kernel={k}")
+            A.close()
+            n += 1
+    p = Problem((10, 9, 8), (True, False, True), omega=0.0)
+    A_ref, _ = p.oracle_csc()
+    A = p.operator(device=0, kernel=TILED)
+    x = p.random_x()
+    check(rel(apply_dev(A, x), A_ref.matvec(x)), "omega = 0")
+    A.close()
+    p = Problem((20, 18, 10), (False, True, False), full_eps=True)
+    A = p.operator(device=0)
+    x = p.random_x()
+    assert np.array_equal(A @ x, apply_dev(A, x)), "host-buffer path differs from the device path"
+    A.close()
+    return n + 2
+
+
+def g_deep():
+    """several tiles and z-chunks per column, sparse / dense / absent off-diagonal blocks (occupancy mask, marching
+    correction kernel, fused kernel), uniform and mixed arrangements, both layouts; vs the matrix-free oracle and
+    the general kernel"""
+    n = 0
+    cases = [((EE, EE, EE), (True, False, True), 33, True), ((EE, EE, EE), (False, False, False), 60, True),
+             ((HH, HH, HH), (False, True, False), 33, True), ((HH, HH, HH), (True, True, True), 60, False),
+             ((EE, HH, EE), (True, False, True), 33, True), ((HH, EE, HH), (False, True, False), 60, False)]
+    if not FULL:
+        cases = cases[:1] + cases[3:5]
+    for boundft, isbloch, z1, cmpfirst in cases:
+        p = Problem((70, 45, 90), isbloch, boundft, full_eps=True, with_mu=True, cmpfirst=cmpfirst)
+        for v, u in itertools.permutations(range(3), 2):
+            p.eps[:, :, :20, v, u] = 0
+            p.eps[:, :, z1:, v, u] = 0
+            p.eps[:25, :, :, v, u] = 0
+        x = p.random_x()
+        At = p.operator(device=0, kernel=TILED)
+        An = p.operator(device=0, kernel=NAIVE)
+        yt, yn = apply_dev(At, x), apply_dev(An, x)
+        check(rel(yt, yn), f"deep tiled vs general {boundft} {isbloch}", 1e-13)
+        check(rel(yt, p.oracle_matfree()(x)), f"deep vs matrix-free oracle {boundft} {isbloch}")
+        At.close()
+        An.close()
+        n += 1
+    p = Problem((40, 33, 70), (False, True, False), ft=HH, with_mu=True)
+    A = p.operator(device=0, kernel=TILED)
+    x = p.random_x()
+    check(rel(apply_dev(A, x), p.oracle_matfree()(x)), "deep HH formulation")
+    A.close()
+    return n + 1
+
+
+def g_solve():
+    """BiCGSTAB (with the fused apply-epilogue dots) and QMR on the emulated device vs a sparse direct solve"""
+    import scipy.sparse.linalg as spla
+    n = 0
+    for ft, kw in ((EE, dict(full_eps=True)), (HH, dict(with_mu=True))):
+        p = Problem((12, 10, 9), (True, False, True), ft=ft, omega=1.3 - 0.4j, **kw)
+        A_ref, _ = p.oracle_csc()
+        b = A_ref.matvec(p.random_x(5))
+        x_ref = spla.splu(A_ref.to_scipy().tocsc()).solve(b)
+        A = p.operator(device=0, kernel=TILED)
+        for method in ("bicgstab", "qmr"):
+            x = np.zeros(A.n, complex)
+            import ctypes as C
+            iters, relres = C.c_int(), C.c_double()
+            m = L.BICGSTAB if method == "bicgstab" else L.QMR
+            code = L.lib().fdfd_solve(A._h, m, b.ctypes.data, x.ctypes.data, L.DEVICE, 1e-10, 400, 10, C.byref(iters),
+                                      C.byref(relres), None)
+            L.check(code, A._h)
+            check(rel(A_ref.matvec(x), b), f"{method} true residual ft={ft}", 1e-8)
+            check(rel(x, x_ref), f"{method} field vs direct solve ft={ft}", 1e-7)
+            n += 1
+        A.close()
+    return n
+
+
+def g_aux():
+    """create_b, h_from_e, e_from_h, corner interpolation on EE and HH handles vs the oracle"""
+    n = 0
+    for isbloch, boundft, ft in (((True, False, True), (EE, EE, EE), EE), ((True, True, False), (HH, EE, HH), EE),
+                                 ((False, True, False), (HH, EE, HH), HH)):
+        p = Problem((9, 8, 7), isbloch, boundft, with_mu=True, ft=ft)
+        A_ref, (Pe, Pm, Ce, Cm) = p.oracle_csc()
+        A = p.operator(device=0)
+        je, jm, e, h = p.random_x(31), p.random_x(32), p.random_x(33), p.random_x(34)
+        check(rel(A.create_b(je, jm), op.create_b(ft, p.omega, Pe, Pm, Ce, Cm, je, jm)), "create_b")
+        check(rel(A.e_from_h(h, je), op.e_from_h(h, p.omega, Pe, Cm, je)), "e_from_h")
+        check(rel(A.h_from_e(e, jm), op.h_from_e(e, p.omega, Pm, Ce, jm)), "h_from_e")
+        Mce, Mcm = op.create_Mcs(p.sdl_e, p.sdl_m, p.sei, p.smi, boundft, isbloch, p.ph)
+        check(rel(A.interp_corners(e, "E"), Mce.matvec(e)), "interp_corners E")
+        check(rel(A.interp_corners(h, "H"), Mcm.matvec(h)), "interp_corners H")
+        A.close()
+        n += 5
+    return n
+
+
+GROUPS = {"apply": g_apply, "boundft": g_boundft, "layouts": g_layouts, "deep": g_deep, "solve": g_solve, "aux": g_aux}
+
+
+def main():
+    ver = L.lib().fdfd_version().decode()
+    if "EMULATED" not in ver:
+        sys.exit("run_emu_cases.py must be pointed at the emulation build (FDFD_B200_LIB=build/emu/libfdfd_emu.so); "
+                 f"loaded: {ver}")
+    names = [a for a in sys.argv[1:] if not a.startswith("--")] or list(GROUPS)
+    for name in names:
+        t = time.time()
+        n = GROUPS[name]()
+        print(f"emu[{os.environ.get('FDFD_EMU_ASYNC', 'eager')},shuffle={os.environ.get('FDFD_EMU_SHUFFLE', '0')}] "
+              f"{name}: {n} checks ok in {time.time() - t:.1f}s", flush=True)
+
+
+if __name__ == "__main__":
+    main()
