@@ -138,6 +138,38 @@ int fdfd_interp_corners(fdfd_handle h, int which, const fdfd_c128 *f, fdfd_c128 
  * FT_HH handle: b = Ce (eps^-1 je) - i w jm.  The -i w term is skipped for w == 0. */
 int fdfd_create_b(fdfd_handle h, const fdfd_c128 *je, const fdfd_c128 *jm_or_null, fdfd_c128 *b, int where);
 
+/* Material-parameter pipeline: calc_matparams!(mdl) of the reference (src/model/full.jl:16-70:
+ * assign_param! + smooth_param! of MaxwellBase over the shapes added with add_obj!, model.jl:107-120) as one GPU
+ * kernel - object assignment at the Yee locations and Kottke subpixel smoothing of every voxel an interface cuts.
+ * Shapes are listed in the order they were added (later shapes lie on top); every voxel corner must be covered by at
+ * least one shape (reference users add a background Box first).  out: the eps (field_type FDFD_FT_EE) or mu
+ * (FDFD_FT_HH) array in the layout fdfd_set_eps / fdfd_set_mu take - Julia column-major (Nx,Ny,k1-k0,3,3): diagonal
+ * entries at the field-component locations, off-diagonal entries at the voxel corners - for planes [k0,k1) of the
+ * global grid (a z-slab), host or device buffer.  Errors are reported through fdfd_last_error(NULL). */
+enum { FDFD_SHAPE_BOX = 0, FDFD_SHAPE_BALL = 1, FDFD_SHAPE_CYLINDER = 2 };
+typedef struct {
+    int32_t kind;      /* FDFD_SHAPE_* */
+    int32_t axis;      /* cylinder: coordinate axis 0..2 */
+    int32_t pind;      /* index of the object's material in params */
+    int32_t reserved;
+    double c[3];       /* centre */
+    double r[3];       /* box: half-widths; ball: r[0] = radius; cylinder: r[0] = radius, r[1] = half-height */
+} fdfd_shape;
+typedef struct {
+    int64_t N[3];
+    int32_t isbloch[3];
+    int32_t boundft_is_E[3];
+    int32_t field_type;          /* FDFD_FT_EE: eps at the E locations; FDFD_FT_HH: mu at the H locations */
+    int32_t field_ortho_shape;   /* ise-perp-shp / ish-perp-shp of the model (model.jl:65-69); 0 for full 3-D models */
+    const double *lprim[3];      /* N[w]+1 primal plane positions incl. the +end ghost point (Grid ctor argument) */
+    int64_t k0, k1;              /* z-planes to compute */
+    int32_t nshape, nparam;
+    const fdfd_shape *shapes;    /* host pointer */
+    const fdfd_c128 *params;     /* host pointer, nparam x 9: row-major 3x3 tensors */
+    int32_t device;              /* CUDA device ordinal; -1 = current device */
+} fdfd_matparams_desc;
+int fdfd_calc_matparams(const fdfd_matparams_desc *desc, fdfd_c128 *out, int where);
+
 /* Multi-GPU plumbing: NCCL communicator over the z-slab ranks (halo send/recv + allreduce).
  * Rank 0 calls fdfd_comm_unique_id, ships the 128 bytes to the other ranks by any means
  * (torch.distributed broadcast, MPI, a file), then every rank calls fdfd_comm_init. */

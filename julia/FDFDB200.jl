@@ -123,6 +123,42 @@ function interp_corners_gpu(A::GpuOperator, ft::FieldType, f::Vector{ComplexF64}
     return out
 end
 
+# mirrors `fdfd_shape` / `fdfd_matparams_desc` (include/fdfd_b200.h)
+struct CShape
+    kind::Int32; axis::Int32; pind::Int32; reserved::Int32
+    c::NTuple{3,Float64}
+    r::NTuple{3,Float64}
+end
+struct MatParamsDesc
+    N::NTuple{3,Int64}
+    isbloch::NTuple{3,Int32}
+    boundft_is_E::NTuple{3,Int32}
+    field_type::Int32
+    field_ortho_shape::Int32
+    lprim::NTuple{3,Ptr{Float64}}
+    k0::Int64; k1::Int64
+    nshape::Int32; nparam::Int32
+    shapes::Ptr{CShape}
+    params::Ptr{ComplexF64}
+    device::Int32
+end
+
+"""GPU stand-in for `calc_matparams!(mdl)` (full.jl:16-70): fills `mdl.εarr` (and `mdl.μarr` with `ft = HH`) from
+the objects added with `add_obj!`.  `cshapes` / `pinds` / `params` are the model's `oind2shp`, `oind2εind`, `εind2ε`
+converted by the caller (Box -> kind 0 with half-widths, Ball -> 1, axis-aligned Cylinder -> 2; row-major 3x3 tensors)."""
+function calc_matparams_gpu!(arr::Array{ComplexF64,5}, ft::FieldType, mdl::MaxwellFDFD.Model,
+                             cshapes::Vector{CShape}, params::Matrix{ComplexF64}; device::Integer=-1)
+    g = mdl.grid
+    lprim = ntuple(w -> collect(Float64, g.ghosted.l[1][w]), 3)          # N+1 primal planes incl. the +end ghost point
+    GC.@preserve lprim cshapes params begin
+        d = MatParamsDesc(Tuple(Int64.(g.N)), Tuple(Int32.(g.isbloch)), Tuple(Int32.(mdl.boundft .== EE)),
+                          ft == EE ? 0 : 1, 0, ntuple(w -> pointer(lprim[w]), 3), 0, g.N[3],
+                          length(cshapes), size(params, 2), pointer(cshapes), pointer(params), device)
+        check(ccall((:fdfd_calc_matparams, LIB), Cint, (Ref{MatParamsDesc}, Ptr{ComplexF64}, Cint), d, arr, 0))
+    end
+    return arr
+end
+
 """Debug: the assembled A as a SparseMatrixCSC (same colptr/rowval Julia's create_A produces)."""
 function sparse_export(A::GpuOperator)
     nnz = Ref{Int64}(0)

@@ -11,6 +11,7 @@ from .model import (Model, ModelFull, set_wpml, set_boundft, set_Npml, set_kbloc
                     create_A, create_b, create_linsys,
                     h_from_e, e_from_h, create_Mcs, solve, field_arr2vec, field_vec2arr)
 from .operator import FdfdOperator, comm_unique_id, partition, halo_plan
+from .shapes import Box, Ball, Sphere, Cylinder, add_obj, clear_objs, calc_matparams, calc_matparams_array
 from . import _lib
 
 __all__ = [n for n in dir() if not n.startswith("_")]

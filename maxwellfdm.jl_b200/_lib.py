@@ -14,6 +14,7 @@ HOST, DEVICE = 0, 1
 BICGSTAB, QMR = 0, 1
 FT_EE, FT_HH = 0, 1
 KERNEL_AUTO, KERNEL_NAIVE, KERNEL_TILED = 0, 1, 2
+SHAPE_BOX, SHAPE_BALL, SHAPE_CYLINDER = 0, 1, 2
 
 
 class c128(C.Structure):
@@ -25,6 +26,18 @@ class Desc(C.Structure):
                 ("order_cmpfirst", C.c_int32), ("field_type", C.c_int32), ("device", C.c_int32),
                 ("rank", C.c_int32), ("nranks", C.c_int32), ("weighted_out_avg", C.c_int32),
                 ("kernel", C.c_int32)]
+
+
+class Shape(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("axis", C.c_int32), ("pind", C.c_int32), ("reserved", C.c_int32),
+                ("c", C.c_double * 3), ("r", C.c_double * 3)]
+
+
+class MatParamsDesc(C.Structure):
+    _fields_ = [("N", C.c_int64 * 3), ("isbloch", C.c_int32 * 3), ("boundft_is_E", C.c_int32 * 3),
+                ("field_type", C.c_int32), ("field_ortho_shape", C.c_int32), ("lprim", C.c_void_p * 3),
+                ("k0", C.c_int64), ("k1", C.c_int64), ("nshape", C.c_int32), ("nparam", C.c_int32),
+                ("shapes", C.c_void_p), ("params", C.c_void_p), ("device", C.c_int32)]
 
 
 class FdfdError(RuntimeError):
@@ -59,6 +72,7 @@ SYMBOLS = {
     "fdfd_e_from_h": (C.c_int, [P, P, P, P, C.c_int]),
     "fdfd_interp_corners": (C.c_int, [P, C.c_int, P, P, C.c_int]),
     "fdfd_create_b": (C.c_int, [P, P, P, P, C.c_int]),
+    "fdfd_calc_matparams": (C.c_int, [P, P, C.c_int]),
     "fdfd_comm_unique_id": (C.c_int, [C.c_char_p]),
     "fdfd_comm_init": (C.c_int, [P, C.c_char_p]),
     "fdfd_bench_apply": (C.c_int, [P, P, P, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),

@@ -484,6 +484,19 @@ using namespace fdfd;
 
 extern "C" {
 
+int fdfd_calc_matparams(const fdfd_matparams_desc *desc, fdfd_c128 *out, int where) {
+    std::string err;
+    int r;
+    try {
+        r = fdfd::calc_matparams(desc, out, where, err);
+    } catch (const std::exception &e) {
+        r = FDFD_ENOMEM;
+        err = e.what();
+    }
+    if (r != FDFD_OK) fdfd::set_err(nullptr, r, err);
+    return r;
+}
+
 const char *fdfd_version(void) { return "fdfd_b200 0.1.0 (sm_100a)"; }
 
 const char *fdfd_last_error(fdfd_handle h) { return h ? static_cast<Ctx *>(h)->err.c_str() : g_create_err.c_str(); }

@@ -243,6 +243,9 @@ int peer_halo_exchange(Ctx *c, const double2 *first_plane, const double2 *last_p
 int comm_exchange_bytes(Ctx *c, const void *dev_mine, void *dev_from_up, void *dev_from_dn, size_t bytes, cudaStream_t s);
 bool stream_write_u32_available();
 
+// matparams.cu -------------------------------------------------------------------------------------
+int calc_matparams(const fdfd_matparams_desc *d, fdfd_c128 *out, int where, std::string &err);
+
 // api.cu -------------------------------------------------------------------------------------------
 int ensure_ready(Ctx *c);
 int apply_device(Ctx *c, const double2 *x, double2 *y, bool transpose);

@@ -14,7 +14,8 @@ The reference call sequence carries over: `Ps = create_paramops(mdl); Cs = creat
 A, b = create_linsys(EE, ω, Ps, Cs, js)`, then `e, info = solve(A, b)` instead of `e = A \\ b`, then
 `h = h_from_e(e, ω, Ps, Cs, js)`.  The operator is never assembled.  Shortcuts taking the model are kept:
 `create_linsys(EE, ω, mdl)`.
-Geometry rasterisation (calc_matparams!, full.jl:16-70) is out of scope: fill mdl.eps_arr / mdl.mu_arr directly.
+Geometry rasterisation + subpixel smoothing (calc_matparams!, full.jl:16-70): shapes.py / csrc/matparams.cu; models
+without objects may fill mdl.eps_arr / mdl.mu_arr directly.
 """
 import numpy as np
 
@@ -161,9 +162,12 @@ class _Geom:
                 and all(np.array_equal(a, b) for a, b in zip(self.sdl_e + self.sdl_m, o.sdl_e + o.sdl_m)))
 
 
-def create_paramops(mdl):
-    """(Peps, Pmu) - model.jl:141-158 (calc_matparams!, the rasterisation at :143, is out of scope: fill
-    mdl.eps_arr / mdl.mu_arr directly)."""
+def create_paramops(mdl, device=-1):
+    """(Peps, Pmu) - model.jl:141-158.  As in the reference (:143) the material arrays are first computed from the
+    objects added with add_obj (calc_matparams, GPU); a model without objects keeps arrays that were filled directly."""
+    if getattr(mdl, "oind2shp", None):
+        from .shapes import calc_matparams
+        calc_matparams(mdl, device=device)
     g = _Geom(mdl)
     return ParamOp("eps", mdl.eps_arr, g), ParamOp("mu", mdl.mu_arr, g)
 

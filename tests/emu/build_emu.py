@@ -19,7 +19,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "maxwellfdm.jl_b200", "csrc")
 OUT_DIR = os.path.join(ROOT, "build", "emu")
 OUT_LIB = os.path.join(OUT_DIR, "libfdfd_emu.so")
-SOURCES = ["api.cu", "apply_naive.cu", "apply_tiled.cu", "krylov.cu", "qmr.cu", "coeffs.cpp", "pattern.cpp", "comm.cpp",
+SOURCES = ["api.cu", "apply_naive.cu", "apply_tiled.cu", "krylov.cu", "qmr.cu", "matparams.cu", "coeffs.cpp", "pattern.cpp", "comm.cpp",
            "peer.cpp"]
 
 

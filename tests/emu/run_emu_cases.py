@@ -182,7 +182,34 @@ def g_aux():
     return n
 
 
-GROUPS = {"apply": g_apply, "boundft": g_boundft, "layouts": g_layouts, "deep": g_deep, "solve": g_solve, "aux": g_aux}
+def g_matparams():
+    """N4: object assignment + Kottke smoothing kernel vs the oracle (boxes, balls, cylinders; Bloch / symmetry ghost
+    corners; non-uniform grids; full-tensor materials; mu locations; z-slabs)"""
+    from oracle import matparams as omp
+    from oracle.grid import Grid as OGrid
+    from problems import matparams_scene, MATPARAMS_CASES
+    n = 0
+    for N, isbloch, boundft, ft, uniform, nshape, aniso in MATPARAMS_CASES:
+        lp, o_sh, f_sh, pinds, params = matparams_scene(N, isbloch, uniform, nshape, aniso)
+        ref = omp.calc_matparams(OGrid(lp, isbloch), boundft, ft, o_sh, pinds, params)
+        g = fb.Grid(lp, isbloch)
+        got = fb.calc_matparams_array(g, boundft, ft, f_sh, pinds, params, device=0)
+        check(rel(got, ref), f"matparams {N} {isbloch} {boundft} ft={ft}")
+        k0, k1 = 2, N[2] - 1                                       # a z-slab is the same planes of the same array
+        slab = fb.calc_matparams_array(g, boundft, ft, f_sh, pinds, params, k0=k0, k1=k1, device=0)
+        assert np.array_equal(slab, got[:, :, k0:k1]), "slab differs from the full-grid result"
+        n += 2
+    try:
+        fb.calc_matparams_array(g, boundft, ft, f_sh[1:2], [0], params[:1], device=0)
+    except L.FdfdError as e:
+        assert e.code == L.EINVAL and "covered by no shape" in str(e)
+        n += 1
+    else:
+        raise AssertionError("an uncovered grid must be rejected")
+    return n
+
+
+GROUPS = {"matparams": g_matparams, "apply": g_apply, "boundft": g_boundft, "layouts": g_layouts, "deep": g_deep, "solve": g_solve, "aux": g_aux}
 
 
 def main():

@@ -93,6 +93,8 @@ inline T __shfl_xor_sync(unsigned, T v, int lane_mask) {
 template <class T> inline T __ldg(const T *p) { return *p; }
 template <class T> inline T __ldcg(const T *p) { return *p; }
 inline unsigned atomicAdd(unsigned *p, unsigned v) { unsigned o = *p; *p = o + v; return o; }
+inline int atomicAdd(int *p, int v) { int o = *p; *p = o + v; return o; }
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline double atomicAdd(double *p, double v) { double o = *p; *p = o + v; return o; }
 inline void __threadfence() {}
 inline void __nanosleep(unsigned) { emu::yield(); }

@@ -75,3 +75,42 @@ class Problem:
                                boundft=["E" if b == EE else "H" for b in self.boundft],
                                ft="E" if self.ft == EE else "H", order_cmpfirst=self.cmpfirst,
                                weighted_out_avg=self.weighted_out, **kw)
+
+
+def matparams_scene(N, isbloch, uniform=False, nshape=6, aniso=False, seed=SEED):
+    """Seeded random scene for the material pipeline (N4): a background box plus boxes / balls / cylinders with
+    scalar or full-tensor materials; two consecutive objects share one material.  Returns (lprim, oracle shapes,
+    product shapes, pinds, params)."""
+    from oracle import matparams as omp
+    import maxwellfdm_jl_b200 as fb
+    rng = np.random.default_rng(seed)
+    lp = [np.arange(n + 1.0) if uniform else np.concatenate(([0.0], np.cumsum(0.6 + 0.8 * rng.random(n)))) for n in N]
+    Ls = [a[-1] for a in lp]
+    o_sh, f_sh = [omp.Box([l / 2 for l in Ls], Ls)], [fb.Box([l / 2 for l in Ls], Ls)]
+    params, pinds = [np.eye(3, dtype=complex)], [0]
+    for s in range(nshape):
+        c = [rng.random() * l for l in Ls]
+        if s % 3 == 0:
+            r = [0.5 + 2.5 * rng.random() for _ in range(3)]
+            o_sh.append(omp.Box(c, r)); f_sh.append(fb.Box(c, r))
+        elif s % 3 == 1:
+            R = 1 + 2.5 * rng.random()
+            o_sh.append(omp.Ball(c, R)); f_sh.append(fb.Ball(c, R))
+        else:
+            R, h, ax = 0.8 + 2 * rng.random(), 0.5 + 2 * rng.random(), int(rng.integers(3))
+            o_sh.append(omp.Cylinder(c, R, h, ax)); f_sh.append(fb.Cylinder(c, R, h, ax))
+        if s == 3:
+            pinds.append(pinds[-1])
+        else:
+            P = np.eye(3) * (2 + 10 * rng.random()) + (0.3 * crandn(rng, 3, 3) if aniso else 0)
+            params.append(P.astype(complex))
+            pinds.append(len(params) - 1)
+    return lp, o_sh, f_sh, pinds, params
+
+
+MATPARAMS_CASES = [  # (N, isbloch, boundft, ft, uniform grid, number of shapes, anisotropic materials)
+    ((12, 10, 9), (True, False, True), (EE, EE, EE), EE, True, 6, False),
+    ((12, 10, 9), (False, True, False), (EE, HH, EE), EE, False, 6, True),
+    ((13, 9, 11), (True, True, True), (EE, EE, EE), HH, False, 6, True),
+    ((9, 17, 6), (False, False, False), (HH, HH, HH), EE, False, 9, False),
+]

@@ -54,6 +54,13 @@ def test_no_cpu_fallback_without_gpu():
     with pytest.raises(L.FdfdError) as ei:
         p.operator()
     assert ei.value.code == L.ECUDA and "no CPU fallback" in str(ei.value)
+    # the material pipeline is a GPU kernel too: no device, no result
+    import maxwellfdm_jl_b200 as fb
+    lp = np.arange(5.0)
+    with pytest.raises(L.FdfdError) as ei2:
+        fb.calc_matparams_array(fb.Grid((lp, lp, lp), (True,) * 3), (EE,) * 3, EE, [fb.Box([2, 2, 2], [4, 4, 4])], [0],
+                                [np.eye(3)])
+    assert ei2.value.code == L.ECUDA
     # a host-only handle exports patterns but refuses every compute call
     A = p.operator(device=-2)
     with pytest.raises(L.FdfdError) as ei:

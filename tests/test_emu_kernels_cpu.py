@@ -41,6 +41,11 @@ def test_emulated_apply_kernels_match_oracle(emu_lib, mode):
     assert out.count("checks ok") == 4, out
 
 
+def test_emulated_material_pipeline_matches_oracle(emu_lib):
+    out = _run(emu_lib, ["matparams"], "eager", 7)
+    assert "checks ok" in out, out
+
+
 def test_emulated_multi_chunk_grids_and_offdiag_paths(emu_lib):
     out = _run(emu_lib, ["deep"], "lazy", 3)
     assert "checks ok" in out, out

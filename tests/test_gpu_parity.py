@@ -513,3 +513,60 @@ def test_model_api_end_to_end():
     h = fb.h_from_e(e, w, A)
     assert np.isfinite(h).all() and np.abs(h).max() > 0
     A.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# N4: material pipeline (kept last in this file: the newest kernel)
+# ---------------------------------------------------------------------------------------------------
+def test_calc_matparams_matches_oracle():
+    """fdfd_calc_matparams (object assignment + Kottke smoothing, one kernel) vs oracle/matparams.py: boxes, balls,
+    cylinders, Bloch / symmetry ghost corners, non-uniform grids, full-tensor materials, mu locations, z-slabs.
+    Tolerance 1e-11 relative: the plane-cut volume formula cancels for nearly axis-parallel normals."""
+    from oracle import matparams as omp
+    from oracle.grid import Grid as OGrid
+    from problems import matparams_scene, MATPARAMS_CASES
+    fb = _fb()
+    for N, isbloch, boundft, ft, uniform, nshape, aniso in MATPARAMS_CASES:
+        lp, o_sh, f_sh, pinds, params = matparams_scene(N, isbloch, uniform, nshape, aniso)
+        ref = omp.calc_matparams(OGrid(lp, isbloch), boundft, ft, o_sh, pinds, params)
+        g = fb.Grid(lp, isbloch)
+        got = fb.calc_matparams_array(g, boundft, ft, f_sh, pinds, params, device=0)
+        assert rel(got, ref) < 1e-11, (N, isbloch, boundft, ft, rel(got, ref))
+        slab = fb.calc_matparams_array(g, boundft, ft, f_sh, pinds, params, k0=2, k1=N[2] - 1, device=0)
+        assert np.array_equal(slab, got[:, :, 2:N[2] - 1])
+    with pytest.raises(fb._lib.FdfdError):
+        fb.calc_matparams_array(g, boundft, ft, f_sh[1:2], [0], params[:1], device=0)
+
+
+def test_model_with_objects_end_to_end():
+    """reference sequence with objects: add_obj! -> create_paramops (calc_matparams!, model.jl:143) -> create_A;
+    the operator built from the GPU-smoothed arrays equals the oracle operator built from the oracle-smoothed arrays."""
+    from oracle import matparams as omp
+    from oracle.grid import Grid as OGrid, create_stretched_dls as o_sdls
+    fb = _fb()
+    n = 12
+    lp = (np.arange(n + 1) - n / 2) * 1.0
+    mdl = fb.ModelFull(fb.Grid((lp, lp, lp), (False, False, False)))
+    w = 2 * np.pi / 8.0
+    fb.set_wpml(mdl, w)
+    fb.set_Npml(mdl, ((2,) * 3, (2,) * 3))
+    fb.add_obj(mdl, "vacuum", fb.Box([0, 0, 0], [10, 10, 10]), eps=1.0)
+    fb.add_obj(mdl, "glass", fb.Ball([0.3, -0.2, 0.1], 3.4), fb.Cylinder([-2, 2, 0], 1.5, 4.0, axis=0), eps=2.25)
+    Ps, Cs = fb.create_paramops(mdl, device=0), fb.create_curls(mdl)
+    o_sh = [omp.Box([0, 0, 0], [10, 10, 10]), omp.Ball([0.3, -0.2, 0.1], 3.4), omp.Cylinder([-2, 2, 0], 1.5, 4.0, 0)]
+    og = OGrid((lp, lp, lp), (False, False, False))
+    eps_ref = omp.calc_matparams(og, (EE,) * 3, EE, o_sh, [0, 1, 1], [np.eye(3), 2.25 * np.eye(3)])
+    assert rel(mdl.eps_arr, eps_ref) < 1e-11
+    assert np.abs(mdl.eps_arr[..., 0, 1]).max() > 1e-3          # the smoothing produced off-diagonal entries
+    A = fb.create_A(fb.EE, w, Ps, Cs, device=0)
+    sdl_e, sdl_m, sei, smi = o_sdls(w, og, ((2,) * 3, (2,) * 3))
+    ph = np.ones(3, complex)
+    mu = np.zeros(og.N + (3, 3), complex)
+    for v in range(3):
+        mu[..., v, v] = 1
+    Ce, Cm = op.create_curls(sei, smi, (EE,) * 3, og.isbloch, ph)
+    Pe, Pm = op.create_paramops(eps_ref, mu, sdl_e, sdl_m, sei, smi, (EE,) * 3, og.isbloch, ph)
+    A_ref = op.create_A(EE, w, Pe, Pm, Ce, Cm)
+    x = crandn(np.random.default_rng(SEED), A.n)
+    assert rel(A @ x, A_ref.matvec(x)) < 1e-11
+    A.close()
