@@ -521,7 +521,8 @@ def test_model_api_end_to_end():
 def test_calc_matparams_matches_oracle():
     """fdfd_calc_matparams (object assignment + Kottke smoothing, one kernel) vs oracle/matparams.py: boxes, balls,
     cylinders, Bloch / symmetry ghost corners, non-uniform grids, full-tensor materials, mu locations, z-slabs.
-    Tolerance 1e-11 relative: the plane-cut volume formula cancels for nearly axis-parallel normals."""
+    Tolerance 1e-10 relative (fp64; measured 1e-13..1e-14 under the CPU logic-check build): the plane-cut volume
+    formula cancels for nearly axis-parallel normals, which amplifies FMA-contraction differences."""
     from oracle import matparams as omp
     from oracle.grid import Grid as OGrid
     from problems import matparams_scene, MATPARAMS_CASES
@@ -531,7 +532,7 @@ def test_calc_matparams_matches_oracle():
         ref = omp.calc_matparams(OGrid(lp, isbloch), boundft, ft, o_sh, pinds, params)
         g = fb.Grid(lp, isbloch)
         got = fb.calc_matparams_array(g, boundft, ft, f_sh, pinds, params, device=0)
-        assert rel(got, ref) < 1e-11, (N, isbloch, boundft, ft, rel(got, ref))
+        assert rel(got, ref) < 1e-10, (N, isbloch, boundft, ft, rel(got, ref))
         slab = fb.calc_matparams_array(g, boundft, ft, f_sh, pinds, params, k0=2, k1=N[2] - 1, device=0)
         assert np.array_equal(slab, got[:, :, 2:N[2] - 1])
     with pytest.raises(fb._lib.FdfdError):
@@ -556,7 +557,7 @@ def test_model_with_objects_end_to_end():
     o_sh = [omp.Box([0, 0, 0], [10, 10, 10]), omp.Ball([0.3, -0.2, 0.1], 3.4), omp.Cylinder([-2, 2, 0], 1.5, 4.0, 0)]
     og = OGrid((lp, lp, lp), (False, False, False))
     eps_ref = omp.calc_matparams(og, (EE,) * 3, EE, o_sh, [0, 1, 1], [np.eye(3), 2.25 * np.eye(3)])
-    assert rel(mdl.eps_arr, eps_ref) < 1e-11
+    assert rel(mdl.eps_arr, eps_ref) < 1e-10
     assert np.abs(mdl.eps_arr[..., 0, 1]).max() > 1e-3          # the smoothing produced off-diagonal entries
     A = fb.create_A(fb.EE, w, Ps, Cs, device=0)
     sdl_e, sdl_m, sei, smi = o_sdls(w, og, ((2,) * 3, (2,) * 3))
@@ -568,5 +569,5 @@ def test_model_with_objects_end_to_end():
     Pe, Pm = op.create_paramops(eps_ref, mu, sdl_e, sdl_m, sei, smi, (EE,) * 3, og.isbloch, ph)
     A_ref = op.create_A(EE, w, Pe, Pm, Ce, Cm)
     x = crandn(np.random.default_rng(SEED), A.n)
-    assert rel(A @ x, A_ref.matvec(x)) < 1e-11
+    assert rel(A @ x, A_ref.matvec(x)) < 1e-10
     A.close()
