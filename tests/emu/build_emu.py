@@ -19,6 +19,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "maxwellfdm.jl_b200", "csrc")
 OUT_DIR = os.path.join(ROOT, "build", "emu")
 OUT_LIB = os.path.join(OUT_DIR, "libfdfd_emu.so")
+FAKE_DIR = os.path.join(OUT_DIR, "fakelibs")
 SOURCES = ["api.cu", "apply_naive.cu", "apply_tiled.cu", "krylov.cu", "qmr.cu", "matparams.cu", "coeffs.cpp", "pattern.cpp", "comm.cpp",
            "peer.cpp"]
 
@@ -114,7 +115,13 @@ def build(verbose=False):
     if failed:
         raise RuntimeError("emulation build failed")
     if procs or not _newer(OUT_LIB, objs):
-        subprocess.run(["g++", "-shared", "-o", OUT_LIB, *objs, "-ldl", "-lpthread", "-lgomp"], check=True)
+        subprocess.run(["g++", "-shared", "-o", OUT_LIB, *objs, "-ldl", "-lpthread", "-lgomp", "-lrt"], check=True)
+    # stand-ins for the libraries csrc/comm.cpp resolves with dlopen, for the multi-rank runs (LD_LIBRARY_PATH=FAKE_DIR)
+    os.makedirs(FAKE_DIR, exist_ok=True)
+    for src, lib in (("fake_nccl.cpp", "libnccl.so.2"), ("fake_cuda_driver.cpp", "libcuda.so.1")):
+        srcp, libp = os.path.join(HERE, "fakelibs", src), os.path.join(FAKE_DIR, lib)
+        if not _newer(libp, [srcp]):
+            subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-o", libp, srcp, "-lpthread"], check=True)
     return OUT_LIB
 
 

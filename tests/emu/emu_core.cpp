@@ -9,8 +9,13 @@
 #include <ucontext.h>
 #endif
 
+#include <fcntl.h>
+#include <unistd.h>
+
 #include <cstdarg>
+#include <map>
 #include <random>
+#include <string>
 #include <vector>
 
 #if defined(__x86_64__)
@@ -432,14 +437,58 @@ const char *cudaGetErrorString(cudaError_t e) {
     }
 }
 cudaError_t cudaGetLastError() { return cudaSuccess; }
+// "Device" memory.  With FDFD_EMU_IPC=1 (multi-rank runs, one process per rank) every allocation is a named POSIX
+// shared-memory object so that cudaIpcGetMemHandle / cudaIpcOpenMemHandle can map it into a neighbour's process.
+namespace {
+struct DevAlloc { size_t bytes; std::string shm_name; };
+std::map<void *, DevAlloc> dev_allocs;
+bool env_ipc() {
+    static const bool v = getenv("FDFD_EMU_IPC") != nullptr;
+    return v;
+}
+struct IpcPayload { char name[48]; uint64_t offset; uint64_t bytes; };
+static_assert(sizeof(IpcPayload) <= sizeof(cudaIpcMemHandle_t), "payload must fit the handle");
+void unlink_all_shm() {
+    for (auto &kv : dev_allocs)
+        if (!kv.second.shm_name.empty()) shm_unlink(kv.second.shm_name.c_str());
+}
+}  // namespace
+
 cudaError_t cudaMalloc(void **p, size_t bytes) {
     const size_t n = ((bytes + 255) / 256) * 256 + 256;
-    *p = aligned_alloc(256, n);
-    if (!*p) return cudaErrorMemoryAllocation;
-    emu::fill_nan(*p, n);
+    if (!env_ipc()) {
+        *p = aligned_alloc(256, n);
+        if (!*p) return cudaErrorMemoryAllocation;
+        emu::fill_nan(*p, n);
+        dev_allocs[*p] = DevAlloc{n, ""};
+        return cudaSuccess;
+    }
+    static int counter = 0;
+    static bool registered = false;
+    if (!registered) { atexit(unlink_all_shm); registered = true; }
+    const std::string name = "/fdfd_emu_" + std::to_string((long)getpid()) + "_" + std::to_string(counter++);
+    const int fd = shm_open(name.c_str(), O_CREAT | O_EXCL | O_RDWR, 0600);
+    if (fd < 0 || ftruncate(fd, (off_t)n) != 0) return cudaErrorMemoryAllocation;
+    void *q = mmap(nullptr, n, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (q == MAP_FAILED) return cudaErrorMemoryAllocation;
+    emu::fill_nan(q, n);
+    dev_allocs[q] = DevAlloc{n, name};
+    *p = q;
     return cudaSuccess;
 }
-cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
+cudaError_t cudaFree(void *p) {
+    if (!p) return cudaSuccess;
+    auto it = dev_allocs.find(p);
+    if (it == dev_allocs.end()) { std::fprintf(stderr, "emu: cudaFree of an unknown pointer\n"); std::abort(); }
+    if (it->second.shm_name.empty()) free(p);
+    else {
+        munmap(p, it->second.bytes);
+        shm_unlink(it->second.shm_name.c_str());
+    }
+    dev_allocs.erase(it);
+    return cudaSuccess;
+}
 cudaError_t cudaMallocHost(void **p, size_t bytes) {
     *p = aligned_alloc(256, ((bytes + 255) / 256) * 256 + 256);
     return *p ? cudaSuccess : cudaErrorMemoryAllocation;
@@ -473,6 +522,37 @@ cudaError_t cudaEventDestroy(cudaEvent_t e) { free(e); return cudaSuccess; }
 cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
 cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t, cudaEvent_t) { *ms = 1.0f; return cudaSuccess; }
-cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *, void *) { return cudaErrorNotSupported; }
-cudaError_t cudaIpcOpenMemHandle(void **, cudaIpcMemHandle_t, unsigned) { return cudaErrorNotSupported; }
-cudaError_t cudaIpcCloseMemHandle(void *) { return cudaErrorNotSupported; }
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p) {
+    auto it = dev_allocs.upper_bound(p);
+    if (it == dev_allocs.begin()) return cudaErrorInvalidValue;
+    --it;
+    const char *base = static_cast<const char *>(it->first);
+    if (static_cast<const char *>(p) >= base + it->second.bytes || it->second.shm_name.empty()) return cudaErrorNotSupported;
+    IpcPayload pl{};
+    std::strncpy(pl.name, it->second.shm_name.c_str(), sizeof(pl.name) - 1);
+    pl.offset = (uint64_t)(static_cast<const char *>(p) - base);
+    pl.bytes = it->second.bytes;
+    std::memset(h, 0, sizeof(*h));
+    std::memcpy(h, &pl, sizeof(pl));
+    return cudaSuccess;
+}
+namespace { std::map<void *, std::pair<void *, size_t>> ipc_maps; }   // returned pointer -> (mapping base, bytes)
+cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned) {
+    IpcPayload pl;
+    std::memcpy(&pl, &h, sizeof(pl));
+    const int fd = shm_open(pl.name, O_RDWR, 0600);
+    if (fd < 0) return cudaErrorInvalidValue;
+    void *q = mmap(nullptr, pl.bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (q == MAP_FAILED) return cudaErrorMemoryAllocation;
+    *p = static_cast<char *>(q) + pl.offset;
+    ipc_maps[*p] = {q, (size_t)pl.bytes};
+    return cudaSuccess;
+}
+cudaError_t cudaIpcCloseMemHandle(void *p) {
+    auto it = ipc_maps.find(p);
+    if (it == ipc_maps.end()) return cudaErrorInvalidValue;
+    munmap(it->second.first, it->second.second);
+    ipc_maps.erase(it);
+    return cudaSuccess;
+}

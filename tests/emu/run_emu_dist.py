@@ -1,0 +1,161 @@
+"""TEST INFRASTRUCTURE ONLY - multi-rank (z-slab) runs of the CPU logic-check build: one PROCESS per rank as on the GPU
+box, the NCCL and driver entry points csrc/comm.cpp resolves with dlopen replaced by tests/emu/fakelibs (FIFOs between
+the rank processes; stream memory operations as stores / bounded spins), "device" memory in named shared memory so
+that the CUDA-IPC peer mapping of csrc/peer.cpp works between the processes.
+
+    python tests/emu/run_emu_dist.py WORLD [apply] [krylov]        (parent: builds nothing, spawns the ranks)
+
+Modes come from the environment the library itself reads (FDFD_PEER_HALO, FDFD_INKERNEL_HALO_WAIT, FDFD_SPLIT_OVERLAP,
+FDFD_NO_HALO_PREFETCH).  Every rank checks its own slab against the oracle on the global problem."""
+import ctypes as C
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import time
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+
+
+def parent(world, groups):
+    emu = os.path.join(ROOT, "build", "emu")
+    tmp = tempfile.mkdtemp(prefix="fdfd_emu_dist_")
+    env = dict(os.environ, FDFD_B200_LIB=os.path.join(emu, "libfdfd_emu.so"), FDFD_EMU_IPC="1",
+               LD_LIBRARY_PATH=os.path.join(emu, "fakelibs") + ":" + os.environ.get("LD_LIBRARY_PATH", ""),
+               EMU_DIST_DIR=tmp, OMP_NUM_THREADS="1")
+    procs = [subprocess.Popen([sys.executable, os.path.abspath(__file__), "--rank", str(r), str(world), *groups], env=env)
+             for r in range(world)]
+    deadline = time.time() + 600
+    rc = 0
+    for p in procs:
+        try:
+            rc |= p.wait(timeout=max(1, deadline - time.time()))
+        except subprocess.TimeoutExpired:
+            rc |= 1
+            print("emu dist: a rank did not finish (dead-lock?)", flush=True)
+            for q in procs:
+                q.kill()
+            break
+    shutil.rmtree(tmp, ignore_errors=True)
+    sys.exit(rc)
+
+
+def wait_file(path, timeout=120):
+    t0 = time.time()
+    while not os.path.exists(path):
+        if time.time() - t0 > timeout:
+            raise TimeoutError(path)
+        time.sleep(0.01)
+
+
+def child(rank, world, groups):
+    import numpy as np
+    from problems import Problem, rel
+    import maxwellfdm_jl_b200 as fb
+    L = fb._lib
+    assert "EMULATED" in L.lib().fdfd_version().decode()
+    tmp = os.environ["EMU_DIST_DIR"]
+    counter = [0]
+
+    def comm_id():
+        """rank 0 creates the unique id, the others read it from a file (the 128 bytes may travel by any means)"""
+        counter[0] += 1
+        path = os.path.join(tmp, f"uid_{counter[0]}")
+        if rank == 0:
+            uid = fb.comm_unique_id()
+            with open(path + ".tmp", "wb") as f:
+                f.write(uid)
+            os.rename(path + ".tmp", path)
+            return uid
+        wait_file(path)
+        return open(path, "rb").read()
+
+    def slab_operator(p, **kw):
+        k0, k1 = fb.partition(p.N[2], world, rank)
+        A = fb.FdfdOperator(p.N, p.isbloch, p.sdl_e, p.sdl_m, p.omega, p.eps[:, :, k0:k1],
+                            p.mu[:, :, k0:k1] if p.with_mu else None, p.ph, order_cmpfirst=p.cmpfirst,
+                            boundft=["E" if b == 0 else "H" for b in p.boundft], ft="E" if p.ft == 0 else "H",
+                            device=0, rank=rank, nranks=world, **kw)
+        A.comm_init(comm_id())
+        return A, k0, k1
+
+    def slab_of(p, v, k0, k1):
+        Nx, Ny, Nz = p.N
+        if p.cmpfirst:
+            return v[3 * Nx * Ny * k0:3 * Nx * Ny * k1].copy()
+        return np.ascontiguousarray(v.reshape(3, Nz, Ny * Nx)[:, k0:k1]).ravel()
+
+    def dev_apply(A, x, transpose=False):
+        y = np.full(A.n, np.nan + 1j * np.nan)
+        f = L.lib().fdfd_apply_transpose if transpose else L.lib().fdfd_apply
+        L.check(f(A._h, x.ctypes.data, y.ctypes.data, L.DEVICE), A._h)
+        return y
+
+    nchecks = 0
+    if "apply" in groups:
+        cases = []
+        for isbloch in ((True, True, True), (False, True, False), (True, False, True)):
+            for full, mu, cf, kern in ((True, True, True, 0), (False, False, True, 0), (True, False, False, 0), (True, True, True, 1)):
+                cases.append(dict(N=(21, 18, 2 * world + 3), isbloch=isbloch, full_eps=full, with_mu=mu, cmpfirst=cf, kernel=kern))
+        cases.append(dict(N=(9, 7, world), isbloch=(True, True, True), full_eps=True, with_mu=True, cmpfirst=True, kernel=0))
+        for isbloch in ((True, True, True), (False, True, False)):
+            cases.append(dict(N=(21, 18, 2 * world + 3), isbloch=isbloch, ft=1, full_mu=True, kernel=0))
+            cases.append(dict(N=(33, 10, 3 * world + 1), isbloch=isbloch, boundft=(1, 1, 1), full_eps=True, with_mu=True, kernel=0))
+        # slabs deep enough for >= 3 z-chunks (the in-kernel halo wait gates the first and last chunk) and several tiles
+        cases.append(dict(N=(40, 14, 14 * world), isbloch=(True, False, True), full_eps=False, with_mu=False, kernel=0, lz=4))
+        cases.append(dict(N=(40, 14, 14 * world), isbloch=(False, True, False), full_eps=True, with_mu=True, kernel=0, lz=3))
+        for cs in cases:
+            kern = cs.pop("kernel")
+            lz = cs.pop("lz", 0)
+            if lz:
+                os.environ["FDFD_LZ"] = str(lz)
+            else:
+                os.environ.pop("FDFD_LZ", None)
+            p = Problem(**cs)
+            mf = p.oracle_matfree()
+            x = p.random_x()
+            A, k0, k1 = slab_operator(p, kernel=kern)
+            xs = slab_of(p, x, k0, k1)
+            for rep in range(3):             # back-to-back applies: epochs of the halo protocol advance
+                y = dev_apply(A, xs)
+            e1 = rel(y, slab_of(p, mf(x), k0, k1))
+            yh = A @ xs                      # host-buffer path
+            e2 = rel(yh, slab_of(p, mf(x), k0, k1))
+            yt = dev_apply(A, xs, True)
+            A_ref, _ = p.oracle_csc()
+            e3 = rel(yt, slab_of(p, A_ref.to_scipy().T @ x, k0, k1))
+            A.close()
+            assert e1 < 1e-12 and e2 < 1e-12 and e3 < 1e-12, (rank, cs, kern, e1, e2, e3)
+            nchecks += 3
+    if "krylov" in groups:
+        os.environ.pop("FDFD_LZ", None)
+        import scipy.sparse.linalg as spla
+        for ft, kw in ((0, dict(full_eps=True)), (1, dict(with_mu=True))):
+            p = Problem((12, 10, 4 * world + 1), (True, False, True), ft=ft, omega=1.3 - 0.4j, **kw)
+            A_ref, _ = p.oracle_csc()
+            b = A_ref.matvec(p.random_x(5))
+            x_ref = spla.splu(A_ref.to_scipy().tocsc()).solve(b)
+            A, k0, k1 = slab_operator(p, kernel=2)
+            bs = slab_of(p, b, k0, k1)
+            for method in (L.BICGSTAB, L.QMR):
+                x = np.zeros(A.n, complex)
+                iters, relres = C.c_int(), C.c_double()
+                code = L.lib().fdfd_solve(A._h, method, bs.ctypes.data, x.ctypes.data, L.DEVICE, 1e-10, 400, 10,
+                                          C.byref(iters), C.byref(relres), None)
+                L.check(code, A._h)
+                e = rel(x, slab_of(p, x_ref, k0, k1))
+                assert e < 1e-7, (rank, ft, method, e, iters.value, relres.value)
+                nchecks += 1
+            A.close()
+    modes = [k for k in ("FDFD_PEER_HALO", "FDFD_INKERNEL_HALO_WAIT", "FDFD_SPLIT_OVERLAP", "FDFD_NO_HALO_PREFETCH") if os.environ.get(k)]
+    print(f"emu dist rank {rank}/{world} [{','.join(modes) or 'default'}]: {nchecks} checks ok", flush=True)
+
+
+if __name__ == "__main__":
+    if sys.argv[1] == "--rank":
+        child(int(sys.argv[2]), int(sys.argv[3]), sys.argv[4:] or ["apply", "krylov"])
+    else:
+        parent(int(sys.argv[1]), sys.argv[2:] or ["apply", "krylov"])

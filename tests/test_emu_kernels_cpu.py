@@ -56,6 +56,25 @@ def test_emulated_krylov_solvers(emu_lib):
     assert "checks ok" in out, out
 
 
+def _run_dist(world, groups, **modes):
+    env = dict(os.environ, **{k: "1" for k in modes})
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emu", "run_emu_dist.py"), str(world), *groups],
+                       env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and r.stdout.count("checks ok") == world, f"{world} {groups} {modes}\n{r.stdout[-2000:]}\n{r.stderr[-4000:]}"
+
+
+@pytest.mark.parametrize("world,groups,modes", [(3, ["apply", "krylov"], {}), (2, ["apply", "krylov"], {"FDFD_PEER_HALO": 1}),
+                                                (2, ["apply"], {"FDFD_SPLIT_OVERLAP": 1}),
+                                                (2, ["apply"], {"FDFD_INKERNEL_HALO_WAIT": 1})],
+                         ids=["nccl-3", "peer-halo-2", "split-overlap-2", "inkernel-wait-2"])
+def test_emulated_z_slab_ranks(emu_lib, world, groups, modes):
+    """one process per rank as on the GPU box; NCCL / driver entry points replaced by tests/emu/fakelibs, device memory
+    in named shared memory so that the CUDA-IPC peer-halo path maps between the processes: halo exchange on every
+    arrangement and layout, Bloch wrap between the first and last rank, back-to-back applies (protocol epochs), host
+    and device paths, transposed apply, BiCGSTAB / QMR with allreduced dots"""
+    _run_dist(world, groups, **modes)
+
+
 def test_product_binding_never_points_at_the_emulation_build():
     """the default library path of the product binding is the CUDA build; the emulation library is only reachable
     through the explicit FDFD_B200_LIB override used above"""
