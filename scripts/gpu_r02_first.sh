@@ -1,0 +1,28 @@
+# Round-2 first GPU calls (nothing below has run on hardware yet - it was written after the round-1 GPU budget was spent
+# and checked only under the CPU logic-check build, tests/emu/).
+#   1 GPU :  gpurun --timeout 1200 -- 'bash scripts/gpu_r02_first.sh single'
+#   2 GPUs:  gpurun --gpus 2 --timeout 900 -- 'bash scripts/gpu_r02_first.sh peer'
+mkdir -p gpurun_out
+case "$1" in
+single)
+  # new GPU tests first (material pipeline), then the whole suite, the bench line, the material-pipeline timing + ncu
+  timeout 600 python -m pytest tests -m gpu -x -q -k "matparams or objects" > gpurun_out/r02_matparams_tests.log 2>&1; echo "matparams tests rc=$?"; tail -3 gpurun_out/r02_matparams_tests.log
+  timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r02_gpu_tests.log 2>&1; echo "gpu tests rc=$?"; tail -3 gpurun_out/r02_gpu_tests.log
+  python bench.py > gpurun_out/r02_bench_line.json 2> gpurun_out/r02_bench.err; echo "bench rc=$?"; cut -c1-400 gpurun_out/r02_bench_line.json
+  timeout 600 python scripts/bench_matparams.py > gpurun_out/r02_matparams_bench.jsonl 2>&1; echo "matparams bench rc=$?"; cat gpurun_out/r02_matparams_bench.jsonl | cut -c1-300
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:matparams --csv --log-file gpurun_out/r02_matparams_launches.csv python scripts/bench_matparams.py > /dev/null 2>&1; echo "ncu rc=$?"
+  ;;
+peer)
+  N=$(nvidia-smi -L | wc -l)
+  # correctness of the SM-free peer-memory halo exchange (csrc/peer.cpp), then apply / BiCGSTAB throughput with and without it
+  for mode in "" "FDFD_PEER_HALO=1"; do
+    env $mode timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29621 scripts/dist_check.py > gpurun_out/r02_dist_check_${N}_${mode%%=*}.log 2>&1; echo "dist_check [$mode] rc=$?"; grep -E "DIST_CHECK" gpurun_out/r02_dist_check_${N}_${mode%%=*}.log | cut -c1-300
+    env $mode timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29622 bench.py --gpus $N --steps 100 --warmup 5 > gpurun_out/r02_scale_${N}_${mode%%=*}.json 2> gpurun_out/r02_scale_${N}_${mode%%=*}.err; echo "bench [$mode] rc=$?"
+    tail -1 gpurun_out/r02_scale_${N}_${mode%%=*}.json | python -c "
+import sys,json; d=json.loads(sys.stdin.read()); print('N', d['n_gpus'], 'GDOF/s', round(d['value'],2), 'ms', round(d['ms_per_step'],4), 'it/s', round(d['krylov']['iter_per_s'],1))" || tail -5 gpurun_out/r02_scale_${N}_${mode%%=*}.err
+  done
+  # the in-kernel halo wait on top of the SM-free exchange (the combination the round-1 experiment was missing)
+  env FDFD_PEER_HALO=1 FDFD_INKERNEL_HALO_WAIT=1 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29623 scripts/dist_inkernel_check.py > gpurun_out/r02_inkernel_peer_$N.log 2>&1; echo "inkernel+peer rc=$?"; tail -3 gpurun_out/r02_inkernel_peer_$N.log | cut -c1-300
+  ;;
+*) echo "usage: $0 single|peer";;
+esac
