@@ -290,8 +290,10 @@ def main():
         peak, peak_src = peaks()
         # bytes an apply must move per DOF: x 16 + y 16 + eps_diag 16, + 32 for the six off-diagonal entries on the
         # (tile, plane) blocks that hold any (the kernel skips empty blocks; dense off-diagonals -> 80)
+        # a pointwise symmetric tensor is stored once (three arrays): 16 instead of 32
         off_frac = A.offdiag_fraction if w["full_eps"] else 0.0
-        bpd = 48 + 32 * off_frac
+        off_sym = bool(w["full_eps"] and A.offdiag_symmetric)
+        bpd = 48 + (16 if off_sym else 32) * off_frac
         achieved = bpd * (n_tot / world) / (ms_step * 1e-3) / 1e9      # per GPU
         traffic = None
         try:
@@ -305,7 +307,8 @@ def main():
             "vs_baseline": None, "dtype": "c128 (complex fp64)", "data": "synthetic",
             "config": {"workload": w["name"] + (" [diagonal-eps variant]" if args.diag else "") +
                        (" [dense off-diagonal variant]" if args.dense_off else ""),
-                       "offdiag_block_fraction": off_frac, "bytes_per_dof_if_dense": 80 if w["full_eps"] else 48,
+                       "offdiag_block_fraction": off_frac, "offdiag_symmetric": off_sym,
+                       "bytes_per_dof_if_dense": (64 if off_sym else 80) if w["full_eps"] else 48,
                        "grid": list(N), "per_gpu_grid": list(per), "dof": n_tot, "parallelism": f"z-slab x{world}",
                        "l2": "inputs (x, y, eps: > 1 GB per GPU) larger than the 126 MB L2; no flush needed",
                        "bytes_per_dof": bpd},

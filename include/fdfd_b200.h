@@ -189,6 +189,10 @@ int fdfd_bench_solve(fdfd_handle h, int method, const fdfd_c128 *b_dev, fdfd_c12
  * tiled kernel skips the six off-diagonal streams on empty blocks (subpixel smoothing puts off-diagonal
  * entries only at material interfaces), so the bytes an apply must move are (48 + 32*frac) B/DOF. */
 int fdfd_offdiag_fraction(fdfd_handle h, double *frac);
+/* 1 if the off-diagonal entries of the mass tensor are pointwise symmetric (P_vu == P_uv exactly - what subpixel
+ * smoothing of reciprocal media produces): the library then keeps three off-diagonal arrays instead of six and an apply
+ * moves (48 + 16*frac) B/DOF.  0 otherwise (and when there are no off-diagonal entries). */
+int fdfd_offdiag_symmetric(fdfd_handle h, int *symmetric);
 /* Number of kernels this handle has launched since creation (for bench.py's gpu_launches). */
 int64_t fdfd_launch_count(fdfd_handle h);
 

@@ -78,6 +78,7 @@ SYMBOLS = {
     "fdfd_bench_apply": (C.c_int, [P, P, P, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "fdfd_bench_solve": (C.c_int, [P, C.c_int, P, P, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "fdfd_offdiag_fraction": (C.c_int, [P, C.POINTER(C.c_double)]),
+    "fdfd_offdiag_symmetric": (C.c_int, [P, C.POINTER(C.c_int)]),
     "fdfd_launch_count": (C.c_int64, [P]),
     "fdfd_host_alloc": (C.c_int, [C.POINTER(P), C.c_uint64]),
     "fdfd_host_free": (C.c_int, [P]),

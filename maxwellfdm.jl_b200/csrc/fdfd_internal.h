@@ -140,6 +140,7 @@ struct Ctx {
     const double2 *halo_for = nullptr;  // vector whose halo planes are (being) exchanged ahead of its apply
     bool comm_pending = false;          // an NCCL op may still be running on stream_comm (ordered by ev_halo)
     double off_frac = 1.0;             // fraction of (tile, plane) blocks holding off-diagonal material
+    bool off_sym = false;              // off-diagonal mass entries pointwise symmetric: three arrays, three aliases
     int s1[3]{+1, +1, +1};
 
     // halo buffers (device): 2 receive planes, 2 send staging not needed (planes are contiguous

@@ -260,6 +260,13 @@ class FdfdOperator:
         return f.value
 
     @property
+    def offdiag_symmetric(self):
+        """True when the off-diagonal mass entries are pointwise symmetric (stored once: 16 instead of 32 B/DOF)."""
+        f = C.c_int()
+        L.check(L.lib().fdfd_offdiag_symmetric(self._h, C.byref(f)), self._h)
+        return bool(f.value)
+
+    @property
     def launch_count(self):
         return int(L.lib().fdfd_launch_count(self._h))
 

@@ -90,6 +90,20 @@ def g_layouts():
             check(rel(apply_dev(A, x), A_ref.matvec(x)), f"layout cmpfirst={cmpfirst} wo={wo} kernel={k}")
             A.close()
             n += 1
+    for sym in (True, False):                # pointwise symmetric off-diagonals are stored once (aliased slots)
+        p = Problem((37, 20, 11), (True, False, True), full_eps=True, with_mu=True)
+        if sym:
+            for v, u in itertools.combinations(range(3), 2):
+                p.eps[..., u, v] = p.eps[..., v, u]
+        A_ref, _ = p.oracle_csc()
+        for k in (TILED, NAIVE):
+            A = p.operator(device=0, kernel=k)
+            assert A.offdiag_symmetric == sym
+            x = p.random_x()
+            check(rel(apply_dev(A, x), A_ref.matvec(x)), f"symmetric={sym} kernel={k}")
+            check(rel(apply_dev(A, x, True), A_ref.to_scipy().T.tocsc() @ x), f"symmetric={sym} kernel={k} transposed")
+            A.close()
+            n += 2
     p = Problem((10, 9, 8), (True, False, True), omega=0.0)
     A_ref, _ = p.oracle_csc()
     A = p.operator(device=0, kernel=TILED)

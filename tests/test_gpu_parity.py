@@ -515,6 +515,32 @@ def test_model_api_end_to_end():
     A.close()
 
 
+def test_symmetric_offdiagonal_tensor_is_stored_once():
+    """P_vu == P_uv pointwise (what subpixel smoothing of reciprocal media gives): three off-diagonal arrays, the
+    other three slots alias them - same results from every kernel path, forward and transposed, both formulations."""
+    for N, isbloch, cmpfirst, ft in (((37, 20, 11), (True, False, True), True, EE), ((33, 9, 40), (False, True, False), False, EE),
+                                     ((20, 13, 9), (True, True, True), True, HH)):
+        for sym in (True, False):
+            p = Problem(N, isbloch, full_eps=(ft == EE), full_mu=(ft == HH), with_mu=True, cmpfirst=cmpfirst, ft=ft)
+            m = p.eps if ft == EE else p.mu
+            if sym:
+                for v, u in itertools.combinations(range(3), 2):
+                    m[..., u, v] = m[..., v, u]
+            A_ref, _ = p.oracle_csc()
+            x = p.random_x()
+            for k in (2, 1):
+                A = p.operator(device=0, kernel=k)
+                assert A.offdiag_symmetric == sym
+                assert rel(_apply_dev(A, x), A_ref.matvec(x)) < TOL
+                assert rel(_apply_dev(A, x, transpose=True), A_ref.to_scipy().T.tocsc() @ x) < TOL
+                A.close()
+            for v, u in itertools.permutations(range(3), 2):      # sparse pattern: diagonal kernel + correction pass
+                m[:, :, 2:, v, u] = 0
+            A = p.operator(device=0, kernel=2)
+            assert rel(_apply_dev(A, x), p.oracle_csc()[0].matvec(x)) < TOL
+            A.close()
+
+
 # ---------------------------------------------------------------------------------------------------
 # N4: material pipeline (kept last in this file: the newest kernel)
 # ---------------------------------------------------------------------------------------------------
