@@ -6,6 +6,8 @@
 //   y = C2 ( q .* (C1 x) ) + massd .* x + Mout[ masso .* (Min x) ]
 // where C1/C2/Min/Mout are given by 1-D coefficient arrays (coeffs.cpp) and massd/masso are the
 // material entries pre-multiplied by -w^2.
+#include <cstdlib>
+
 #include "cplx.cuh"
 #include "fdfd_internal.h"
 
@@ -200,6 +202,12 @@ __global__ void __launch_bounds__(128) interp_kernel(const __grid_constant__ App
 // marches the run: the corner quantity G(k+1) is computed once per plane (11 loads per thread) and reused as
 // G(k) in the next step; x/y neighbours of G travel through a double-buffered shared tile.  Per axis the in-average
 // looks towards -s1 and the out-average towards +s1 (s1 = direction of the first curl); the march follows s1_z.
+// SKIPZ (opt-in, FDFD_CORR_SKIP_ZERO): inside a flagged block most cells still carry no off-diagonal entry (an
+// interface is a surface).  A thread whose six entries are exactly zero loads no field values (its G is zero), and an
+// output cell whose three corner terms are exactly zero is not read-modified-written: the pass then moves the material
+// streams plus x / y only around the interface cells instead of 64-80 B per DOF of the whole block.  Results are
+// identical (only additions of exact zeros are dropped).
+template <bool SKIPZ>
 __global__ void __launch_bounds__(256) offdiag_march_kernel(const __grid_constant__ ApplyParams p,
                                                              const int4 *__restrict__ items, int ntx, int kl_begin,
                                                              int kl_end) {
@@ -216,17 +224,39 @@ __global__ void __launch_bounds__(256) offdiag_march_kernel(const __grid_constan
     Gather g{p};
     const double2 mi0x = p.c.mi0[0][ci], mi1x = p.c.mi1[0][ci], mi0y = p.c.mi0[1][cj], mi1y = p.c.mi1[1][cj];
     const int txp = min(max(tx + SGX, 0), 31), typ = min(max(ty + SGY, 0), 7);   // out-average neighbour (shift +s1)
+    auto nonzero = [](double2 a) { return (a.x != 0.0) | (a.y != 0.0); };
 
     // corner quantity G(kk) at this thread's cell; ezm = E_z of plane kk-SG at this cell (in), E_z(kk) (out)
-    // own-cell field of the plane handled last by corner() (needed as `s` by the fused-dot deltas)
+    // own-cell field of the plane handled last by corner() (needed as `s` by the fused-dot deltas); have_e tells
+    // whether corner() loaded it (SKIPZ: only where the cell carries off-diagonal material)
     double2 ex = c_zero(), ey = c_zero(), ez = c_zero();
+    bool have_e = false;
     auto corner = [&](int kk, double2 &ezm, double2 &Gx, double2 &Gy, double2 &Gz) {
+        const int64_t m = g.gidx(ci, cj, kk);
+        if (SKIPZ) {
+            const double2 o01 = p.mo[0][m], o02 = p.mo[1][m], o10 = p.mo[2][m], o12 = p.mo[3][m], o20 = p.mo[4][m],
+                          o21 = p.mo[5][m];
+            have_e = nonzero(o01) | nonzero(o02) | nonzero(o10) | nonzero(o12) | nonzero(o20) | nonzero(o21);
+            if (!have_e) {
+                Gx = Gy = Gz = c_zero();
+                return;
+            }
+            ex = g.E(0, ci, cj, kk); ey = g.E(1, ci, cj, kk); ez = g.E(2, ci, cj, kk);
+            const int kg = g.kglob(kk);
+            const double2 Ax = c_fma(mi1x, g.E(0, cim, cj, kk), c_mul(mi0x, ex));
+            const double2 Ay = c_fma(mi1y, g.E(1, ci, cjm, kk), c_mul(mi0y, ey));
+            const double2 Az = c_fma(p.c.mi1[2][kg], g.E(2, ci, cj, kk - SG), c_mul(p.c.mi0[2][kg], ez));
+            Gx = c_fma(o02, Az, c_mul(o01, Ay));
+            Gy = c_fma(o12, Az, c_mul(o10, Ax));
+            Gz = c_fma(o21, Ay, c_mul(o20, Ax));
+            return;
+        }
         ex = g.E(0, ci, cj, kk); ey = g.E(1, ci, cj, kk); ez = g.E(2, ci, cj, kk);
+        have_e = true;
         const int kg = g.kglob(kk);
         const double2 Ax = c_fma(mi1x, g.E(0, cim, cj, kk), c_mul(mi0x, ex));
         const double2 Ay = c_fma(mi1y, g.E(1, ci, cjm, kk), c_mul(mi0y, ey));
         const double2 Az = c_fma(p.c.mi1[2][kg], ezm, c_mul(p.c.mi0[2][kg], ez));
-        const int64_t m = g.gidx(ci, cj, kk);
         Gx = c_fma(p.mo[1][m], Az, c_mul(p.mo[0][m], Ay));
         Gy = c_fma(p.mo[3][m], Az, c_mul(p.mo[2][m], Ax));
         Gz = c_fma(p.mo[5][m], Ay, c_mul(p.mo[4][m], Ax));
@@ -234,7 +264,7 @@ __global__ void __launch_bounds__(256) offdiag_march_kernel(const __grid_constan
     };
 
     const int kfirst = SG < 0 ? ke - 1 : ks;
-    double2 ezm = g.E(2, ci, cj, kfirst - SG);
+    double2 ezm = SKIPZ ? c_zero() : g.E(2, ci, cj, kfirst - SG);
     double2 Gcx, Gcy, Gcz;
     corner(kfirst, ezm, Gcx, Gcy, Gcz);
     gs[0][0][tid] = Gcx;
@@ -243,7 +273,8 @@ __global__ void __launch_bounds__(256) offdiag_march_kernel(const __grid_constan
     double d_re = 0.0, d_im = 0.0, d_tt = 0.0;   // fused Krylov dots: exact change of (y,x), (y,y) caused by this pass
     for (int st = 0; st < ke - ks; ++st) {
         const int k = kfirst + SG * st;
-        const double2 sx = ex, sy = ey, sz = ez;      // x at this cell, plane k
+        double2 sx = ex, sy = ey, sz = ez;            // x at this cell, plane k (valid if have_s)
+        const bool have_s = have_e;
         // neighbours of G(k): written one step ago, visible since the last barrier; read BEFORE this step's barrier
         const double2 Gx_xp = gs[st & 1][0][ty * 32 + txp], Gy_yp = gs[st & 1][1][typ * 32 + tx];
         double2 Gnx, Gny, Gnz;
@@ -252,21 +283,24 @@ __global__ void __launch_bounds__(256) offdiag_march_kernel(const __grid_constan
         gs[(st + 1) & 1][1][tid] = Gny;
         if (out_ok) {
             const int kg = g.kglob(k);
-            double2 *yo = &p.y[(int64_t)k * p.y_pstride + ((int64_t)gj * p.Nx + gi) * p.y_es];
             const double2 tx_ = c_fma(p.c.mo1[0][ci], Gx_xp, c_mul(p.c.mo0[0][ci], Gcx));
             const double2 ty_ = c_fma(p.c.mo1[1][cj], Gy_yp, c_mul(p.c.mo0[1][cj], Gcy));
             const double2 tz_ = c_fma(p.c.mo1[2][kg], Gnz, c_mul(p.c.mo0[2][kg], Gcz));
-            const double2 o0 = yo[0], o1 = yo[p.y_cs], o2 = yo[2 * p.y_cs];
-            const double2 n0 = c_add(o0, tx_), n1 = c_add(o1, ty_), n2 = c_add(o2, tz_);
-            yo[0] = n0;
-            yo[p.y_cs] = n1;
-            yo[2 * p.y_cs] = n2;
-            if (p.dot_mode == 2) {
-                d_re += tx_.x * sx.x + tx_.y * sx.y + ty_.x * sy.x + ty_.y * sy.y + tz_.x * sz.x + tz_.y * sz.y;
-                d_im += tx_.x * sx.y - tx_.y * sx.x + ty_.x * sy.y - ty_.y * sy.x + tz_.x * sz.y - tz_.y * sz.x;
-                d_tt += (n0.x * n0.x + n0.y * n0.y - o0.x * o0.x - o0.y * o0.y) +
-                        (n1.x * n1.x + n1.y * n1.y - o1.x * o1.x - o1.y * o1.y) +
-                        (n2.x * n2.x + n2.y * n2.y - o2.x * o2.x - o2.y * o2.y);
+            if (!SKIPZ || (nonzero(tx_) | nonzero(ty_) | nonzero(tz_))) {
+                double2 *yo = &p.y[(int64_t)k * p.y_pstride + ((int64_t)gj * p.Nx + gi) * p.y_es];
+                const double2 o0 = yo[0], o1 = yo[p.y_cs], o2 = yo[2 * p.y_cs];
+                const double2 n0 = c_add(o0, tx_), n1 = c_add(o1, ty_), n2 = c_add(o2, tz_);
+                yo[0] = n0;
+                yo[p.y_cs] = n1;
+                yo[2 * p.y_cs] = n2;
+                if (p.dot_mode == 2) {
+                    if (SKIPZ && !have_s) { sx = g.E(0, ci, cj, k); sy = g.E(1, ci, cj, k); sz = g.E(2, ci, cj, k); }
+                    d_re += tx_.x * sx.x + tx_.y * sx.y + ty_.x * sy.x + ty_.y * sy.y + tz_.x * sz.x + tz_.y * sz.y;
+                    d_im += tx_.x * sx.y - tx_.y * sx.x + ty_.x * sy.y - ty_.y * sy.x + tz_.x * sz.y - tz_.y * sz.x;
+                    d_tt += (n0.x * n0.x + n0.y * n0.y - o0.x * o0.x - o0.y * o0.y) +
+                            (n1.x * n1.x + n1.y * n1.y - o1.x * o1.x - o1.y * o1.y) +
+                            (n2.x * n2.x + n2.y * n2.y - o2.x * o2.x - o2.y * o2.y);
+                }
             }
         }
         Gcx = Gnx;
@@ -304,7 +338,9 @@ cudaError_t launch_apply_naive(const ApplyParams &p, cudaStream_t s) {
 cudaError_t launch_offdiag_correction(const ApplyParams &p, const int4 *items, int count, int ntx, int kl_begin,
                                       int kl_end, cudaStream_t s) {
     if (count <= 0) return cudaSuccess;
-    offdiag_march_kernel<<<count, 256, 0, s>>>(p, items, ntx, kl_begin, kl_end);
+    static const bool skipz = getenv("FDFD_CORR_SKIP_ZERO") != nullptr;   // opt-in until it has been timed on hardware
+    if (skipz) offdiag_march_kernel<true><<<count, 256, 0, s>>>(p, items, ntx, kl_begin, kl_end);
+    else       offdiag_march_kernel<false><<<count, 256, 0, s>>>(p, items, ntx, kl_begin, kl_end);
     return cudaGetLastError();
 }
 

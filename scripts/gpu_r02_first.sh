@@ -9,6 +9,11 @@ single)
   timeout 600 python -m pytest tests -m gpu -x -q -k "matparams or objects" > gpurun_out/r02_matparams_tests.log 2>&1; echo "matparams tests rc=$?"; tail -3 gpurun_out/r02_matparams_tests.log
   timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r02_gpu_tests.log 2>&1; echo "gpu tests rc=$?"; tail -3 gpurun_out/r02_gpu_tests.log
   python bench.py > gpurun_out/r02_bench_line.json 2> gpurun_out/r02_bench.err; echo "bench rc=$?"; cut -c1-400 gpurun_out/r02_bench_line.json
+  # correction pass that skips exact zeros (opt-in): parity of the whole suite with it on, then C2-C5 with / without
+  FDFD_CORR_SKIP_ZERO=1 timeout 900 python -m pytest tests -m gpu -x -q -k "not matparams and not objects" > gpurun_out/r02_gpu_tests_skipz.log 2>&1; echo "gpu tests (skip-zero) rc=$?"; tail -2 gpurun_out/r02_gpu_tests_skipz.log
+  timeout 900 python scripts/bench_configs.py > gpurun_out/r02_configs_default.jsonl 2>&1; echo "configs rc=$?"
+  FDFD_CORR_SKIP_ZERO=1 timeout 900 python scripts/bench_configs.py > gpurun_out/r02_configs_skipz.jsonl 2>&1; echo "configs (skip-zero) rc=$?"
+  for f in gpurun_out/r02_configs_default.jsonl gpurun_out/r02_configs_skipz.jsonl; do echo $f; cut -c1-200 $f | grep gdof_s; done
   timeout 600 python scripts/bench_matparams.py > gpurun_out/r02_matparams_bench.jsonl 2>&1; echo "matparams bench rc=$?"; cat gpurun_out/r02_matparams_bench.jsonl | cut -c1-300
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:matparams --csv --log-file gpurun_out/r02_matparams_launches.csv python scripts/bench_matparams.py > /dev/null 2>&1; echo "ncu rc=$?"
   ;;

@@ -21,8 +21,8 @@ def emu_lib():
     return build_emu.build()
 
 
-def _run(lib, groups, async_mode, shuffle):
-    env = dict(os.environ, FDFD_B200_LIB=lib, FDFD_EMU_ASYNC=async_mode, FDFD_EMU_SHUFFLE=str(shuffle))
+def _run(lib, groups, async_mode, shuffle, **extra_env):
+    env = dict(os.environ, FDFD_B200_LIB=lib, FDFD_EMU_ASYNC=async_mode, FDFD_EMU_SHUFFLE=str(shuffle), **extra_env)
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emu", "run_emu_cases.py"), *groups], env=env,
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, f"{groups} [{async_mode}, shuffle={shuffle}]\n{r.stdout[-2000:]}\n{r.stderr[-4000:]}"
@@ -49,6 +49,13 @@ def test_emulated_material_pipeline_matches_oracle(emu_lib):
 def test_emulated_multi_chunk_grids_and_offdiag_paths(emu_lib):
     out = _run(emu_lib, ["deep"], "lazy", 3)
     assert "checks ok" in out, out
+
+
+def test_emulated_correction_pass_skipping_exact_zeros(emu_lib):
+    """FDFD_CORR_SKIP_ZERO (opt-in until timed on hardware): threads without off-diagonal material load no field
+    values, output cells with zero corner terms are not read-modified-written - same results"""
+    out = _run(emu_lib, ["deep", "layouts"], "eager", 4, FDFD_CORR_SKIP_ZERO="1")
+    assert out.count("checks ok") == 2, out
 
 
 def test_emulated_krylov_solvers(emu_lib):
