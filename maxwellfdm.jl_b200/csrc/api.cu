@@ -285,6 +285,24 @@ int apply_device(Ctx *c, const double2 *x, double2 *y, bool transpose) {
     // then one launch - and inside the Krylov loops the exchange is started early by the kernel that produces the
     // vector (halo_prefetch), so the apply only waits on an event.
     static const bool split_overlap = getenv("FDFD_SPLIT_OVERLAP") != nullptr;
+    if (c->d.nranks > 1 && c->halo_for == x && x != nullptr && c->peer.direct_pending) {
+        // peer-direct (opt-in): the neighbours announced their boundary planes of this workspace vector; the kernel
+        // reads them in place over NVLink - no halo copy
+        c->halo_for = nullptr;
+        if (!peer_direct_planes(c, x, &p.x.lo, &p.x.hi)) return set_err(c, FDFD_ESTATE, "peer-direct: vector is not in the workspace");
+        if ((r = peer_direct_wait(c, c->stream)) != FDFD_OK) return r;
+        static const bool verbose = getenv("FDFD_VERBOSE") != nullptr;
+        if (verbose && c->peer.depoch == 1) fprintf(stderr, "fdfd rank %d: peer-direct halo reads active\n", c->d.rank);
+        if (use_tiled) {
+            int nl = 0;
+            FDFD_CUDA(c, launch_apply_tiled(p, 0, p.nzl, c->stream, &nl));
+            c->launches += nl;
+        } else {
+            FDFD_CUDA(c, launch_apply_naive(p, c->stream));
+            c->launches += 1;
+        }
+        return FDFD_OK;
+    }
     if (c->d.nranks > 1 && c->halo_for == x && x != nullptr) {
         c->halo_for = nullptr;
         c->comm_pending = false;
@@ -403,6 +421,14 @@ int halo_prefetch(Ctx *c, const double2 *v) {
     if (!halo_prefetch_usable(c)) return FDFD_OK;
     FDFD_CUDA(c, cudaEventRecord(c->ev_x, c->stream));
     FDFD_CUDA(c, cudaStreamWaitEvent(c->stream_comm, c->ev_x, 0));
+    const double2 *plo = nullptr, *phi = nullptr;
+    if (c->peer.direct && peer_direct_planes(c, v, &plo, &phi)) {
+        // peer-direct (opt-in): nothing is copied - only tell the neighbours that the planes they will read are final
+        int rs = peer_direct_signal(c, c->stream_comm);
+        if (rs != FDFD_OK) return rs;
+        c->halo_for = v;
+        return FDFD_OK;
+    }
     int r = halo_exchange(c, v, c->halo_lo, c->halo_hi, c->stream_comm);
     if (r != FDFD_OK) return r;
     FDFD_CUDA(c, cudaEventRecord(c->ev_halo, c->stream_comm));

@@ -104,7 +104,7 @@ int comm_init(Ctx *c, const char id[128]) {
     FDFD_NCCL(c, api->CommInitRank(&comm, c->d.nranks, uid, c->d.rank));
     c->comm = comm;
     c->dirty = true;  // material ghost planes must be exchanged
-    if (getenv("FDFD_PEER_HALO")) return peer_halo_init(c);   // experimental, see PeerHalo
+    if (getenv("FDFD_PEER_HALO") || getenv("FDFD_PEER_DIRECT")) return peer_halo_init(c);   // experimental, see PeerHalo
     return FDFD_OK;
 }
 

@@ -95,6 +95,16 @@ struct PeerHalo {
     uint32_t *up_flags = nullptr, *dn_flags = nullptr;
     void *mapped[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // bases to cudaIpcCloseMemHandle
     uint32_t epoch = 0;
+    // Peer-direct reads (EXPERIMENTAL, FDFD_PEER_DIRECT, not yet run on hardware): inside BiCGSTAB the neighbours'
+    // Krylov workspaces are mapped too and the apply kernel reads their boundary planes IN PLACE over NVLink (its
+    // bulk copies of the first / last z-chunk address peer memory) - no halo copy at all, only a flag per direction.
+    bool direct = false;                 // workspaces mapped
+    bool direct_pending = false;         // halo_for's planes were announced with peer_direct_signal
+    double2 *up_work = nullptr, *dn_work = nullptr;
+    int64_t up_nloc = 0, dn_nloc = 0, dn_nzl = 0;
+    void *work_mapped[2] = {nullptr, nullptr};
+    unsigned char up_handle[64] = {}, dn_handle[64] = {};   // handles the current mappings were opened from
+    uint32_t depoch = 0;
 };
 
 struct Ctx {
@@ -240,6 +250,15 @@ int stream_wait_geq_u32(Ctx *c, cudaStream_t s, uint32_t *dev_word, uint32_t val
 int peer_halo_init(Ctx *c);
 void peer_halo_destroy(Ctx *c);
 int peer_halo_exchange(Ctx *c, const double2 *first_plane, const double2 *last_plane, cudaStream_t s);
+// peer-direct reads: map the neighbours' workspaces (collective; call once the workspace exists), announce that the
+// boundary planes of a workspace vector are final (stream s), wait for the neighbours' announcement, and the peer
+// addresses of the planes below / above this slab of workspace vector x
+bool peer_direct_enabled(const Ctx *c);
+int peer_direct_map(Ctx *c);
+void peer_direct_unmap(Ctx *c);
+int peer_direct_signal(Ctx *c, cudaStream_t s);
+int peer_direct_wait(Ctx *c, cudaStream_t s);
+bool peer_direct_planes(const Ctx *c, const double2 *x, const double2 **lo, const double2 **hi);
 // raw byte exchange with the two z-neighbours over the NCCL communicator (setup only)
 int comm_exchange_bytes(Ctx *c, const void *dev_mine, void *dev_from_up, void *dev_from_dn, size_t bytes, cudaStream_t s);
 bool stream_write_u32_available();

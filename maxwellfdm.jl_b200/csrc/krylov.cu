@@ -118,6 +118,7 @@ static int bicgstab(Ctx *c, const double2 *b, double2 *x, double rtol, int maxit
     int rc = ensure_ready(c);
     if (rc != FDFD_OK) return rc;
     if ((rc = kry::workspace(c, 6)) != FDFD_OK) return rc;
+    if ((rc = peer_direct_map(c)) != FDFD_OK) return rc;   // opt-in (FDFD_PEER_DIRECT): neighbours' workspaces, read in place
     if ((rc = ensure_dot_buffers(c)) != FDFD_OK) return rc;
     const int64_t n = c->nloc;
     double2 *r = c->work, *rhat = r + n, *p = rhat + n, *v = p + n, *s = v + n, *t = s + n;

@@ -11,6 +11,7 @@
 //                           wait DATA >= e                             [from each neighbour]
 // Nothing here needs an SM, which is what the in-kernel halo wait (apply_tiled.cu, HWAIT) requires of its transfer.
 // Replaces the ncclSend/ncclRecv pair of comm.cpp; the reference has no distributed code.
+#include <cstdlib>
 #include <cstring>
 
 #include "fdfd_internal.h"
@@ -18,7 +19,7 @@
 namespace fdfd {
 
 namespace {
-enum { DATA_LO = 0, DATA_HI = 1, FREE_UP = 2, FREE_DN = 3, NFLAGS = 4 };
+enum { DATA_LO = 0, DATA_HI = 1, FREE_UP = 2, FREE_DN = 3, DIRECT_LO = 4, DIRECT_HI = 5, NFLAGS = 6 };
 
 struct Handles {
     cudaIpcMemHandle_t halo_lo, halo_hi, flags;
@@ -70,6 +71,7 @@ int peer_halo_init(Ctx *c) {
 
 void peer_halo_destroy(Ctx *c) {
     PeerHalo &ph = c->peer;
+    peer_direct_unmap(c);
     for (void *&m : ph.mapped) {
         if (m) cudaIpcCloseMemHandle(m);
         m = nullptr;
@@ -102,6 +104,114 @@ int peer_halo_exchange(Ctx *c, const double2 *first_plane, const double2 *last_p
     if (dn >= 0 && (r = stream_wait_geq_u32(c, s, &ph.flags[DATA_LO], e)) != FDFD_OK) return r;
     if (up >= 0 && (r = stream_wait_geq_u32(c, s, &ph.flags[DATA_HI], e)) != FDFD_OK) return r;
     return FDFD_OK;
+}
+
+// ---- peer-direct reads ---------------------------------------------------------------------------------------------
+// Inside BiCGSTAB the vectors that are applied (p, s) live in the library's own workspace, so a neighbour can read their
+// boundary planes in place.  Ordering: the producer announces "my boundary planes of epoch e are final" with a stream
+// memory operation into the consumer's flag word (behind the kernel that wrote the planes); the consumer's stream
+// waits for that word before the apply kernel.  The reverse hazard (a producer overwriting planes a neighbour still
+// reads) cannot occur: between an apply of a vector and the next kernel that writes it lies an allreduce of every
+// rank (sigma after A p, (t,s),(t,t) after A s), which completes only after every rank's apply.
+namespace {
+struct WorkInfo {
+    cudaIpcMemHandle_t handle;
+    int64_t nloc, nzl;
+};
+}  // namespace
+
+bool peer_direct_enabled(const Ctx *c) {
+    static const bool env = getenv("FDFD_PEER_DIRECT") != nullptr;
+    return env && c->peer.ready && c->d.nranks > 1 && c->d.order_cmpfirst;
+}
+
+void peer_direct_unmap(Ctx *c) {
+    PeerHalo &ph = c->peer;
+    for (void *&m : ph.work_mapped) {
+        if (m) cudaIpcCloseMemHandle(m);
+        m = nullptr;
+    }
+    ph.up_work = ph.dn_work = nullptr;
+    ph.direct = ph.direct_pending = false;
+}
+
+int peer_direct_map(Ctx *c) {
+    PeerHalo &ph = c->peer;
+    if (!peer_direct_enabled(c) || !c->work) return FDFD_OK;
+    int up, dn;
+    halo_neighbours(c->d.nranks, c->d.rank, c->d.isbloch[2] != 0, &up, &dn);
+    WorkInfo mine{}, from_up{}, from_dn{};
+    FDFD_CUDA(c, cudaIpcGetMemHandle(&mine.handle, c->work));
+    mine.nloc = c->nloc;
+    mine.nzl = c->k1 - c->k0;
+    unsigned char *stage = nullptr;
+    FDFD_CUDA(c, cudaMalloc((void **)&stage, 3 * sizeof(WorkInfo)));
+    FDFD_CUDA(c, cudaMemcpy(stage, &mine, sizeof(WorkInfo), cudaMemcpyHostToDevice));
+    int r = comm_exchange_bytes(c, stage, stage + sizeof(WorkInfo), stage + 2 * sizeof(WorkInfo), sizeof(WorkInfo), c->stream);
+    if (r != FDFD_OK) { cudaFree(stage); return r; }
+    FDFD_CUDA(c, cudaStreamSynchronize(c->stream));
+    FDFD_CUDA(c, cudaMemcpy(&from_up, stage + sizeof(WorkInfo), sizeof(WorkInfo), cudaMemcpyDeviceToHost));
+    FDFD_CUDA(c, cudaMemcpy(&from_dn, stage + 2 * sizeof(WorkInfo), sizeof(WorkInfo), cudaMemcpyDeviceToHost));
+    cudaFree(stage);
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle cache size");
+    const bool same_up = up < 0 || (ph.up_work && std::memcmp(ph.up_handle, &from_up.handle, 64) == 0);
+    const bool same_dn = dn < 0 || (ph.dn_work && std::memcmp(ph.dn_handle, &from_dn.handle, 64) == 0);
+    if (!(ph.direct && same_up && same_dn)) {     // first solve, or a neighbour re-allocated its workspace
+        peer_direct_unmap(c);
+        if (up >= 0) {
+            FDFD_CUDA(c, cudaIpcOpenMemHandle(&ph.work_mapped[0], from_up.handle, cudaIpcMemLazyEnablePeerAccess));
+            ph.up_work = static_cast<double2 *>(ph.work_mapped[0]);
+            std::memcpy(ph.up_handle, &from_up.handle, 64);
+        }
+        if (dn >= 0) {
+            if (dn == up) ph.dn_work = ph.up_work;            // one peer on both sides: map once
+            else {
+                FDFD_CUDA(c, cudaIpcOpenMemHandle(&ph.work_mapped[1], from_dn.handle, cudaIpcMemLazyEnablePeerAccess));
+                ph.dn_work = static_cast<double2 *>(ph.work_mapped[1]);
+            }
+            std::memcpy(ph.dn_handle, &from_dn.handle, 64);
+        }
+    }
+    ph.up_nloc = from_up.nloc;
+    ph.dn_nloc = from_dn.nloc;
+    ph.dn_nzl = from_dn.nzl;
+    ph.direct = true;
+    ph.direct_pending = false;
+    return FDFD_OK;
+}
+
+int peer_direct_signal(Ctx *c, cudaStream_t s) {
+    PeerHalo &ph = c->peer;
+    int up, dn, r;
+    halo_neighbours(c->d.nranks, c->d.rank, c->d.isbloch[2] != 0, &up, &dn);
+    const uint32_t e = ++ph.depoch;
+    // my last plane is the plane below the up neighbour's slab, my first plane the one above the down neighbour's
+    if (up >= 0 && (r = stream_write_u32(c, s, &ph.up_flags[DIRECT_LO], e)) != FDFD_OK) return r;
+    if (dn >= 0 && (r = stream_write_u32(c, s, &ph.dn_flags[DIRECT_HI], e)) != FDFD_OK) return r;
+    ph.direct_pending = true;
+    return FDFD_OK;
+}
+
+int peer_direct_wait(Ctx *c, cudaStream_t s) {
+    PeerHalo &ph = c->peer;
+    int up, dn, r;
+    halo_neighbours(c->d.nranks, c->d.rank, c->d.isbloch[2] != 0, &up, &dn);
+    if (dn >= 0 && (r = stream_wait_geq_u32(c, s, &ph.flags[DIRECT_LO], ph.depoch)) != FDFD_OK) return r;
+    if (up >= 0 && (r = stream_wait_geq_u32(c, s, &ph.flags[DIRECT_HI], ph.depoch)) != FDFD_OK) return r;
+    ph.direct_pending = false;
+    return FDFD_OK;
+}
+
+bool peer_direct_planes(const Ctx *c, const double2 *x, const double2 **lo, const double2 **hi) {
+    const PeerHalo &ph = c->peer;
+    if (!ph.direct || !c->work || x < c->work || c->nloc <= 0) return false;
+    const int64_t off = x - c->work;
+    if (off % c->nloc != 0 || (size_t)(off + c->nloc) * sizeof(double2) > c->work_bytes) return false;
+    const int64_t idx = off / c->nloc;
+    // same vector of the neighbour's workspace: its last plane lies below my slab, its first plane above it
+    if (ph.dn_work) *lo = ph.dn_work + idx * ph.dn_nloc + (ph.dn_nzl - 1) * c->plane;
+    if (ph.up_work) *hi = ph.up_work + idx * ph.up_nloc;
+    return true;
 }
 
 }  // namespace fdfd

@@ -20,7 +20,7 @@ single)
 peer)
   N=$(nvidia-smi -L | wc -l)
   # correctness of the SM-free peer-memory halo exchange (csrc/peer.cpp), then apply / BiCGSTAB throughput with and without it
-  for mode in "" "FDFD_PEER_HALO=1"; do
+  for mode in "" "FDFD_PEER_HALO=1" "FDFD_PEER_DIRECT=1"; do
     env $mode timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29621 scripts/dist_check.py > gpurun_out/r02_dist_check_${N}_${mode%%=*}.log 2>&1; echo "dist_check [$mode] rc=$?"; grep -E "DIST_CHECK" gpurun_out/r02_dist_check_${N}_${mode%%=*}.log | cut -c1-300
     env $mode timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29622 bench.py --gpus $N --steps 100 --warmup 5 > gpurun_out/r02_scale_${N}_${mode%%=*}.json 2> gpurun_out/r02_scale_${N}_${mode%%=*}.err; echo "bench [$mode] rc=$?"
     tail -1 gpurun_out/r02_scale_${N}_${mode%%=*}.json | python -c "

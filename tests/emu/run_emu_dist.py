@@ -5,7 +5,7 @@ that the CUDA-IPC peer mapping of csrc/peer.cpp works between the processes.
 
     python tests/emu/run_emu_dist.py WORLD [apply] [krylov]        (parent: builds nothing, spawns the ranks)
 
-Modes come from the environment the library itself reads (FDFD_PEER_HALO, FDFD_INKERNEL_HALO_WAIT, FDFD_SPLIT_OVERLAP,
+Modes come from the environment the library itself reads (FDFD_PEER_DIRECT, FDFD_PEER_HALO, FDFD_INKERNEL_HALO_WAIT, FDFD_SPLIT_OVERLAP,
 FDFD_NO_HALO_PREFETCH).  Every rank checks its own slab against the oracle on the global problem."""
 import ctypes as C
 import os
@@ -150,7 +150,7 @@ def child(rank, world, groups):
                 assert e < 1e-7, (rank, ft, method, e, iters.value, relres.value)
                 nchecks += 1
             A.close()
-    modes = [k for k in ("FDFD_PEER_HALO", "FDFD_INKERNEL_HALO_WAIT", "FDFD_SPLIT_OVERLAP", "FDFD_NO_HALO_PREFETCH") if os.environ.get(k)]
+    modes = [k for k in ("FDFD_PEER_DIRECT", "FDFD_PEER_HALO", "FDFD_INKERNEL_HALO_WAIT", "FDFD_SPLIT_OVERLAP", "FDFD_NO_HALO_PREFETCH") if os.environ.get(k)]
     print(f"emu dist rank {rank}/{world} [{','.join(modes) or 'default'}]: {nchecks} checks ok", flush=True)
 
 

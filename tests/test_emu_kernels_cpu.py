@@ -71,9 +71,10 @@ def _run_dist(world, groups, **modes):
 
 
 @pytest.mark.parametrize("world,groups,modes", [(3, ["apply", "krylov"], {}), (2, ["apply", "krylov"], {"FDFD_PEER_HALO": 1}),
+                                                (3, ["krylov"], {"FDFD_PEER_DIRECT": 1}),
                                                 (2, ["apply"], {"FDFD_SPLIT_OVERLAP": 1}),
                                                 (2, ["apply"], {"FDFD_INKERNEL_HALO_WAIT": 1})],
-                         ids=["nccl-3", "peer-halo-2", "split-overlap-2", "inkernel-wait-2"])
+                         ids=["nccl-3", "peer-halo-2", "peer-direct-3", "split-overlap-2", "inkernel-wait-2"])
 def test_emulated_z_slab_ranks(emu_lib, world, groups, modes):
     """one process per rank as on the GPU box; NCCL / driver entry points replaced by tests/emu/fakelibs, device memory
     in named shared memory so that the CUDA-IPC peer-halo path maps between the processes: halo exchange on every
