@@ -106,7 +106,7 @@ static int upload_materials(Ctx *c) {
     const std::vector<cplx> &mid = ee ? c->mu_host : c->eps_host;
     const bool mass_given = !mass.empty(), mid_given = !mid.empty();
     const bool has_mass = c->omega != cplx(0.0);
-    const bool has_off = has_mass && mass_given && (ee ? c->eps_off : c->mu_off);
+    bool has_off = has_mass && mass_given && (ee ? c->eps_off : c->mu_off);
     // A pointwise symmetric mass tensor (P_vu == P_uv exactly, the usual outcome of subpixel smoothing of reciprocal
     // media) is stored as three off-diagonal arrays; the other three slots alias them, so every kernel reads the same
     // values through the same code while the off-diagonal streams cost 16 instead of 32 B/DOF of HBM traffic.
@@ -119,6 +119,26 @@ static int upload_materials(Ctx *c) {
                 for (int u = v + 1; u < 3; ++u)
                     nonsym |= mass[(size_t)M * (v + 3 * u) + i] != mass[(size_t)M * (u + 3 * v) + i];
         off_sym = nonsym == 0;
+    }
+    if (c->d.nranks > 1 && has_mass && mass_given) {
+        // z-slabs: every rank must build (and exchange the ghost planes of) the same set of arrays - a slab without
+        // any off-diagonal entry next to one that has them (the C4 sphere) builds zero-filled arrays, and the tensor
+        // counts as symmetric only if it is on every slab
+        if (!c->comm) return set_err(c, FDFD_ESTATE, "nranks > 1: call fdfd_comm_init before the first apply");
+        double *flags = nullptr;
+        const double h2[2] = {has_off ? 1.0 : 0.0, (has_off && !off_sym) ? 1.0 : 0.0};
+        FDFD_CUDA(c, cudaMalloc((void **)&flags, 2 * sizeof(double)));
+        FDFD_CUDA(c, cudaMemcpyAsync(flags, h2, sizeof(h2), cudaMemcpyHostToDevice, c->stream));
+        int ra = allreduce_sum(c, flags, 2, c->stream);
+        double g2[2] = {0.0, 0.0};
+        if (ra == FDFD_OK) {
+            FDFD_CUDA(c, cudaMemcpyAsync(g2, flags, sizeof(g2), cudaMemcpyDeviceToHost, c->stream));
+            FDFD_CUDA(c, cudaStreamSynchronize(c->stream));
+        }
+        cudaFree(flags);
+        if (ra != FDFD_OK) return ra;
+        has_off = g2[0] > 0.0;
+        off_sym = has_off && g2[1] == 0.0;
     }
     c->off_sym = off_sym;
     // an identity mass parameter (mu == 1 of the HH formulation) is a scalar, not three arrays
@@ -732,6 +752,11 @@ int fdfd_set_eps(fdfd_handle h, const fdfd_c128 *eps, int has_offdiag) {
     }
     if (!has_offdiag) {
         c->eps_off = false;
+        // the caller promised zeros and they are normally never read; a neighbouring z-slab WITH off-diagonal entries
+        // makes this rank build (zero) arrays too, so make the promise true in the copy
+        for (int v = 0; v < 3; ++v)
+            for (int u = 0; u < 3; ++u)
+                if (u != v) std::fill(c->eps_host.begin() + (size_t)M * (v + 3 * u), c->eps_host.begin() + (size_t)M * (v + 3 * u + 1), cplx(0.0));
     } else {
         c->eps_off = offdiag_nonzero(c->eps_host, M);
     }

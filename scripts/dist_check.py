@@ -66,12 +66,28 @@ def main():
         cases.append(dict(N=(21, 18, 2 * world + 3), isbloch=isbloch, ft=1, full_mu=True, kernel=0))
         cases.append(dict(N=(33, 10, 3 * world + 1), isbloch=isbloch, boundft=(1, 1, 1), full_eps=True, with_mu=True,
                           kernel=0))
+    # off-diagonal material on ONE slab only (every rank must still build and exchange the same arrays), once
+    # pointwise symmetric on that slab and once not
+    cases.append(dict(N=(21, 18, 4 * world), isbloch=(True, True, True), full_eps=True, with_mu=False, kernel=0, only_slab=1, sym=True))
+    cases.append(dict(N=(21, 18, 4 * world), isbloch=(False, True, False), full_eps=True, with_mu=True, kernel=0, only_slab=0, sym=False))
     for cs in cases:
         kern = cs.pop("kernel")
+        only_slab, sym = cs.pop("only_slab", None), cs.pop("sym", False)
         p = Problem(**cs)
+        if only_slab is not None:
+            import itertools
+            a0, a1 = fb.partition(p.N[2], world, only_slab % world)
+            for v, u in itertools.permutations(range(3), 2):
+                p.eps[:, :, :a0, v, u] = 0
+                p.eps[:, :, a1:, v, u] = 0
+            if sym:
+                for v, u in itertools.combinations(range(3), 2):
+                    p.eps[..., u, v] = p.eps[..., v, u]
         A_ref, _ = p.oracle_csc()
         x = p.random_x()
         A, k0, k1 = slab_operator(p, kernel=kern)
+        if only_slab is not None and A.offdiag_symmetric != sym:
+            fails.append(("offdiag_symmetric", cs, sym))
         y = gather(p, A @ slab_of(p, x, k0, k1), k0, k1)
         e1 = rel(y, A_ref.matvec(x))
         yt = gather(p, A.rmatvec_T(slab_of(p, x, k0, k1)), k0, k1)

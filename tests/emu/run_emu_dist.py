@@ -107,17 +107,33 @@ def child(rank, world, groups):
         # slabs deep enough for >= 3 z-chunks (the in-kernel halo wait gates the first and last chunk) and several tiles
         cases.append(dict(N=(40, 14, 14 * world), isbloch=(True, False, True), full_eps=False, with_mu=False, kernel=0, lz=4))
         cases.append(dict(N=(40, 14, 14 * world), isbloch=(False, True, False), full_eps=True, with_mu=True, kernel=0, lz=3))
+        # off-diagonal material on ONE slab only (every rank must still build and exchange the same arrays), once
+        # pointwise symmetric on that slab and once not
+        cases.append(dict(N=(21, 18, 4 * world), isbloch=(True, True, True), full_eps=True, with_mu=False, kernel=0, only_slab=1, sym=True))
+        cases.append(dict(N=(21, 18, 4 * world), isbloch=(False, True, False), full_eps=True, with_mu=True, kernel=0, only_slab=0, sym=False))
         for cs in cases:
             kern = cs.pop("kernel")
             lz = cs.pop("lz", 0)
+            only_slab, sym = cs.pop("only_slab", None), cs.pop("sym", False)
             if lz:
                 os.environ["FDFD_LZ"] = str(lz)
             else:
                 os.environ.pop("FDFD_LZ", None)
             p = Problem(**cs)
+            if only_slab is not None:
+                import itertools
+                a0, a1 = fb.partition(p.N[2], world, only_slab % world)
+                for v, u in itertools.permutations(range(3), 2):
+                    p.eps[:, :, :a0, v, u] = 0
+                    p.eps[:, :, a1:, v, u] = 0
+                if sym:
+                    for v, u in itertools.combinations(range(3), 2):
+                        p.eps[..., u, v] = p.eps[..., v, u]
             mf = p.oracle_matfree()
             x = p.random_x()
             A, k0, k1 = slab_operator(p, kernel=kern)
+            if only_slab is not None:
+                assert A.offdiag_symmetric == sym, (rank, sym)
             xs = slab_of(p, x, k0, k1)
             for rep in range(3):             # back-to-back applies: epochs of the halo protocol advance
                 y = dev_apply(A, xs)
