@@ -169,6 +169,12 @@ typedef struct {
     int32_t device;              /* CUDA device ordinal; -1 = current device */
 } fdfd_matparams_desc;
 int fdfd_calc_matparams(const fdfd_matparams_desc *desc, fdfd_c128 *out, int where);
+/* eps of an FT_EE handle straight from objects: instead of filling mdl.eps_arr on the host (calc_matparams!) and passing it
+ * to fdfd_set_eps, the library rasterises and smooths this rank's z-slab on the device, directly into the operator's
+ * material arrays - no (Nx,Ny,Nz,3,3) host array exists (it would be 116 GB for the 1024x1024x768 configuration).
+ * desc->N / isbloch / boundft_is_E must equal the handle's; k0, k1, device and field_type are taken from the handle.
+ * fdfd_export_pattern is not available on such a handle (it needs the host array). */
+int fdfd_set_eps_objects(fdfd_handle h, const fdfd_matparams_desc *desc);
 
 /* Multi-GPU plumbing: NCCL communicator over the z-slab ranks (halo send/recv + allreduce).
  * Rank 0 calls fdfd_comm_unique_id, ships the 128 bytes to the other ranks by any means

@@ -73,6 +73,7 @@ SYMBOLS = {
     "fdfd_interp_corners": (C.c_int, [P, C.c_int, P, P, C.c_int]),
     "fdfd_create_b": (C.c_int, [P, P, P, P, C.c_int]),
     "fdfd_calc_matparams": (C.c_int, [P, P, C.c_int]),
+    "fdfd_set_eps_objects": (C.c_int, [P, P]),
     "fdfd_comm_unique_id": (C.c_int, [C.c_char_p]),
     "fdfd_comm_init": (C.c_int, [P, C.c_char_p]),
     "fdfd_bench_apply": (C.c_int, [P, P, P, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),

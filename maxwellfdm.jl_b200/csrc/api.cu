@@ -104,14 +104,17 @@ static int upload_materials(Ctx *c) {
     // mass parameter / middle parameter in reference terms
     const std::vector<cplx> &mass = ee ? c->eps_host : c->mu_host;
     const std::vector<cplx> &mid = ee ? c->mu_host : c->eps_host;
-    const bool mass_given = !mass.empty(), mid_given = !mid.empty();
+    const bool obj = ee && c->eps_obj.set;      // eps from objects: rasterised on the device below, no host array
+    const bool mass_given = !mass.empty() || obj, mid_given = !mid.empty();
     const bool has_mass = c->omega != cplx(0.0);
     bool has_off = has_mass && mass_given && (ee ? c->eps_off : c->mu_off);
     // A pointwise symmetric mass tensor (P_vu == P_uv exactly, the usual outcome of subpixel smoothing of reciprocal
     // media) is stored as three off-diagonal arrays; the other three slots alias them, so every kernel reads the same
     // values through the same code while the off-diagonal streams cost 16 instead of 32 B/DOF of HBM traffic.
     bool off_sym = has_off;
-    if (has_off) {
+    if (has_off && obj) {
+        off_sym = c->eps_obj.symmetric;         // the kernel writes the upper triangle to both places
+    } else if (has_off) {
         int nonsym = 0;
 #pragma omp parallel for reduction(| : nonsym) schedule(static)
         for (int64_t i = 0; i < M; ++i)
@@ -158,6 +161,30 @@ static int upload_materials(Ctx *c) {
         c->md_uniform = make_double2(w2u.real(), w2u.imag());
     }
     if (!narr) return FDFD_OK;
+    double2 *objbuf = nullptr;                  // objects: the smoothed slab in Julia layout, on the device
+    if (obj && has_mass) {
+        fdfd_matparams_desc md{};
+        for (int w = 0; w < 3; ++w) {
+            md.N[w] = c->d.N[w];
+            md.isbloch[w] = c->d.isbloch[w];
+            md.boundft_is_E[w] = c->d.boundft_is_E[w];
+            md.lprim[w] = c->eps_obj.lprim[w].data();
+        }
+        md.field_type = FDFD_FT_EE;
+        md.field_ortho_shape = c->eps_obj.ortho;
+        md.k0 = c->k0;
+        md.k1 = c->k1;
+        md.nshape = (int32_t)c->eps_obj.shapes.size();
+        md.nparam = (int32_t)(c->eps_obj.params.size() / 9);
+        md.shapes = c->eps_obj.shapes.data();
+        md.params = reinterpret_cast<const fdfd_c128 *>(c->eps_obj.params.data());
+        md.device = -1;
+        FDFD_CUDA(c, cudaMalloc((void **)&objbuf, (size_t)9 * M * sizeof(double2)));
+        std::string merr;
+        const int rm = calc_matparams(&md, reinterpret_cast<fdfd_c128 *>(objbuf), FDFD_DEVICE, merr);
+        c->launches += 1;
+        if (rm != FDFD_OK) { cudaFree(objbuf); return set_err(c, rm, "fdfd_set_eps_objects: " + merr); }
+    }
     double2 *tmp = nullptr;
     FDFD_CUDA(c, cudaMalloc((void **)&tmp, (size_t)M * sizeof(double2)));
     double2 *cur = c->mat_dev;
@@ -167,10 +194,15 @@ static int upload_materials(Ctx *c) {
     auto build = [&](const std::vector<cplx> *src, int v, int u, int mode, const double2 *&slot) -> int {
         // mode 0: f * src, mode 1: 1/src; src == nullptr: identity parameter (1 on the diagonal)
         if (src) {
-            FDFD_CUDA(c, cudaMemcpyAsync(tmp, src->data() + (size_t)M * (v + 3 * u), (size_t)M * sizeof(double2),
-                                         cudaMemcpyHostToDevice, c->stream));
-            if (mode == 0) scale_copy_kernel<<<nblocks(M), 256, 0, c->stream>>>(cur + Nxy, tmp, M, f);
-            else           recip_copy_kernel<<<nblocks(M), 256, 0, c->stream>>>(cur + Nxy, tmp, M);
+            const double2 *from = tmp;
+            if (objbuf && src == &mass) {
+                from = objbuf + (size_t)M * (v + 3 * u);      // already on the device
+            } else {
+                FDFD_CUDA(c, cudaMemcpyAsync(tmp, src->data() + (size_t)M * (v + 3 * u), (size_t)M * sizeof(double2),
+                                             cudaMemcpyHostToDevice, c->stream));
+            }
+            if (mode == 0) scale_copy_kernel<<<nblocks(M), 256, 0, c->stream>>>(cur + Nxy, from, M, f);
+            else           recip_copy_kernel<<<nblocks(M), 256, 0, c->stream>>>(cur + Nxy, from, M);
         } else {
             fill_kernel<<<nblocks(M), 256, 0, c->stream>>>(cur + Nxy, M, mode == 0 ? f : make_double2(1.0, 0.0));
         }
@@ -203,6 +235,7 @@ static int upload_materials(Ctx *c) {
     if (mid_given && rc == FDFD_OK)
         for (int v = 0; v < 3 && rc == FDFD_OK; ++v) rc = build(&mid, v, v, 1, c->q[v]);
     cudaFree(tmp);
+    if (objbuf) cudaFree(objbuf);
     if (rc != FDFD_OK) return rc;
     // ghost planes: periodic wrap (single slab), neighbour exchange (multi slab), zero at symmetry ends
     for (double2 *g : ghosted) {
@@ -745,6 +778,7 @@ int fdfd_set_eps(fdfd_handle h, const fdfd_c128 *eps, int has_offdiag) {
     if (!eps) return set_err(c, FDFD_EINVAL, "fdfd_set_eps: null argument");
     const int64_t M = c->d.N[0] * c->d.N[1] * (c->k1 - c->k0);
     const cplx *p = reinterpret_cast<const cplx *>(eps);
+    c->eps_obj = ObjMaterial();
     try {
         c->eps_host.assign(p, p + 9 * M);
     } catch (const std::bad_alloc &) {
@@ -762,6 +796,43 @@ int fdfd_set_eps(fdfd_handle h, const fdfd_c128 *eps, int has_offdiag) {
     }
     if (c->d.field_type == FDFD_FT_HH && c->eps_off)
         return set_err(c, FDFD_EINVAL, "FT_HH: Peps must be diagonal (reference model.jl:239)");
+    c->have_eps = true;
+    c->dirty = true;
+    return FDFD_OK;
+}
+
+int fdfd_set_eps_objects(fdfd_handle h, const fdfd_matparams_desc *d) {
+    CHECK_H(h);
+    if (!d || !d->shapes || !d->params || d->nshape < 1 || d->nparam < 1)
+        return set_err(c, FDFD_EINVAL, "fdfd_set_eps_objects: null argument / no shapes");
+    if (c->d.field_type != FDFD_FT_EE)
+        return set_err(c, FDFD_EINVAL, "fdfd_set_eps_objects: FT_HH needs a diagonal Peps (reference model.jl:239); smoothed objects are not");
+    for (int w = 0; w < 3; ++w)
+        if (d->N[w] != c->d.N[w] || !d->lprim[w] || (d->isbloch[w] != 0) != (c->d.isbloch[w] != 0) ||
+            (d->boundft_is_E[w] != 0) != (c->d.boundft_is_E[w] != 0))
+            return set_err(c, FDFD_EINVAL, "fdfd_set_eps_objects: grid / boundary description differs from the handle's");
+    for (int o = 0; o < d->nshape; ++o)
+        if (d->shapes[o].pind < 0 || d->shapes[o].pind >= d->nparam)
+            return set_err(c, FDFD_EINVAL, "fdfd_set_eps_objects: bad material index");
+    ObjMaterial &m = c->eps_obj;
+    try {
+        m.shapes.assign(d->shapes, d->shapes + d->nshape);
+        const cplx *pp = reinterpret_cast<const cplx *>(d->params);
+        m.params.assign(pp, pp + 9 * (size_t)d->nparam);
+        for (int w = 0; w < 3; ++w) m.lprim[w].assign(d->lprim[w], d->lprim[w] + d->N[w] + 1);
+    } catch (const std::bad_alloc &) {
+        return set_err(c, FDFD_ENOMEM, "fdfd_set_eps_objects: out of host memory");
+    }
+    m.ortho = d->field_ortho_shape != 0;
+    m.symmetric = true;
+    for (int q = 0; q < d->nparam; ++q)
+        for (int a = 0; a < 3; ++a)
+            for (int b = a + 1; b < 3; ++b)
+                if (m.params[9 * q + 3 * a + b] != m.params[9 * q + 3 * b + a]) m.symmetric = false;
+    m.set = true;
+    c->eps_host.clear();
+    c->eps_host.shrink_to_fit();
+    c->eps_off = d->nshape > 1;        // an interface may be cut obliquely; an all-zero result is skipped through the occupancy mask
     c->have_eps = true;
     c->dirty = true;
     return FDFD_OK;
@@ -849,6 +920,8 @@ int fdfd_solve(fdfd_handle h, int method, const fdfd_c128 *b, fdfd_c128 *x, int 
 
 int fdfd_export_pattern(fdfd_handle h, int64_t *colptr, int64_t *rowval, fdfd_c128 *nzval, int64_t *nnz_inout) {
     CHECK_H(h);
+    if (c->eps_obj.set)
+        return set_err(c, FDFD_ESTATE, "fdfd_export_pattern needs eps as a host array (fdfd_set_eps); this handle's eps was rasterised on the device from objects");
     return export_pattern(c, colptr, rowval, nzval, nnz_inout);
 }
 

@@ -107,6 +107,17 @@ struct PeerHalo {
     uint32_t depoch = 0;
 };
 
+// eps given as objects (fdfd_set_eps_objects): the material arrays are rasterised and smoothed on the device straight
+// into the operator's arrays - no host array exists
+struct ObjMaterial {
+    bool set = false;
+    std::vector<fdfd_shape> shapes;
+    std::vector<cplx> params;          // nparam x 9
+    std::vector<double> lprim[3];
+    int ortho = 0;
+    bool symmetric = false;            // every tensor symmetric: the smoothed array is too (stored once)
+};
+
 struct Ctx {
     fdfd_desc d{};
     int dev = 0;
@@ -129,6 +140,7 @@ struct Ctx {
     bool eps_off = false, have_mu = false, mu_off = false;
     std::vector<cplx> eps_host;  // local slab, Julia layout (kept for re-scaling by omega and export)
     std::vector<cplx> mu_host;
+    ObjMaterial eps_obj;
 
     // device state
     bool dirty = true;               // coefficient / material device arrays need rebuilding

@@ -34,6 +34,7 @@ struct MatParams {
     int32_t isbloch[3];
     int32_t g[3];                 // grid type of the field planes per axis (0 PRIM, 1 DUAL): ft2gt(ft, boundft[w])
     int32_t ortho;                // field orthogonal to the shape dimensions: arithmetic averages (model.jl:65-69)
+    int32_t symmetric;            // every material tensor is symmetric: write P_ab (a < b) into both (a,b) and (b,a)
     int32_t k0, k1;               // planes of this slab
     int32_t nshape, nparam;
     const double *H[3];           // half-step lattice per axis: H[2i] = ghosted dual i, H[2i+1] = primal i (2N+2 entries)
@@ -411,9 +412,12 @@ __global__ void __launch_bounds__(MNT) matparams_kernel(const __grid_constant__ 
         if (v < 3) {
             p.out[(int64_t)(v * 3 + v) * nzl * Nxy + cell] = P.m[v * 3 + v];
         } else {
+            // symmetric materials give a symmetric average; rounding in the frame rotation breaks that by an ulp, so
+            // the upper triangle is written to both places - the operator then stores the off-diagonals once
             for (int a = 0; a < 3; ++a)
                 for (int b = 0; b < 3; ++b)
-                    if (a != b) p.out[(int64_t)(b * 3 + a) * nzl * Nxy + cell] = P.m[a * 3 + b];
+                    if (a != b)
+                        p.out[(int64_t)(b * 3 + a) * nzl * Nxy + cell] = (p.symmetric && a > b) ? P.m[b * 3 + a] : P.m[a * 3 + b];
         }
     }
 }
@@ -476,6 +480,11 @@ int calc_matparams(const fdfd_matparams_desc *d, fdfd_c128 *out, int where, std:
     std::vector<cplx> prm(9 * (size_t)d->nparam), prm_inv(9 * (size_t)d->nparam);
     std::memcpy(prm.data(), d->params, prm.size() * sizeof(cplx));
     for (int q = 0; q < d->nparam; ++q) host_inverse3(&prm[9 * q], &prm_inv[9 * q]);
+    p.symmetric = 1;
+    for (int q = 0; q < d->nparam; ++q)
+        for (int a = 0; a < 3; ++a)
+            for (int b = a + 1; b < 3; ++b)
+                if (prm[9 * q + 3 * a + b] != prm[9 * q + 3 * b + a]) p.symmetric = 0;
 
     const int64_t nzl = d->k1 - d->k0;
     const size_t out_bytes = (size_t)9 * nzl * d->N[0] * d->N[1] * sizeof(double2);

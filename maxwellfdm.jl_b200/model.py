@@ -162,13 +162,26 @@ class _Geom:
                 and all(np.array_equal(a, b) for a, b in zip(self.sdl_e + self.sdl_m, o.sdl_e + o.sdl_m)))
 
 
-def create_paramops(mdl, device=-1):
+def create_paramops(mdl, device=-1, device_materials=False):
     """(Peps, Pmu) - model.jl:141-158.  As in the reference (:143) the material arrays are first computed from the
-    objects added with add_obj (calc_matparams, GPU); a model without objects keeps arrays that were filled directly."""
-    if getattr(mdl, "oind2shp", None):
+    objects added with add_obj (calc_matparams, GPU); a model without objects keeps arrays that were filled directly.
+    device_materials=True (models whose objects all have mu = 1): mdl.eps_arr is NOT filled - Peps carries the objects
+    and the operator rasterises and smooths its own z-slab on the device (fdfd_set_eps_objects), so no (Nx,Ny,Nz,3,3)
+    host array is ever built."""
+    objs = getattr(mdl, "oind2shp", None)
+    g = _Geom(mdl)
+    if objs and device_materials:
+        if not (len(mdl.muind2mu) == 1 and np.array_equal(mdl.muind2mu[0], np.eye(3))):
+            raise ValueError("device_materials needs mu = 1 for every object")
+        Pe = ParamOp("eps", None, g)
+        Pe.objects = (mdl.grid.lg_prim, list(mdl.oind2shp), list(mdl.oind2epsind), list(mdl.epsind2eps))
+        mu = np.zeros(mdl.grid.N + (3, 3), np.complex128)
+        for v in range(3):
+            mu[..., v, v] = 1.0
+        return Pe, ParamOp("mu", mu, g)
+    if objs:
         from .shapes import calc_matparams
         calc_matparams(mdl, device=device)
-    g = _Geom(mdl)
     return ParamOp("eps", mdl.eps_arr, g), ParamOp("mu", mdl.mu_arr, g)
 
 
@@ -195,10 +208,14 @@ def _build(ft, w, Ps, Cs, device=-1, rank=0, nranks=1, kernel=0, weighted_out_av
     from .operator import partition
     k0, k1 = partition(g.N[2], nranks, rank)
     mu = _mu_or_none(Pm.arr)
-    A = FdfdOperator(g.N, g.isbloch, g.sdl_e, g.sdl_m, w, Pe.arr[:, :, k0:k1],
+    objects = getattr(Pe, "objects", None)
+    A = FdfdOperator(g.N, g.isbloch, g.sdl_e, g.sdl_m, w, None if objects else Pe.arr[:, :, k0:k1],
                      None if mu is None else mu[:, :, k0:k1], g.e_mikL, boundft=g.boundft, ft=ft,
                      order_cmpfirst=g.order_cmpfirst, device=device, rank=rank, nranks=nranks, kernel=kernel,
                      weighted_out_avg=weighted_out_avg)
+    if objects:
+        lprim, shapes, pinds, params = objects
+        A.set_eps_objects(lprim, shapes, pinds, params, boundft=g.boundft)
     g.ops[key] = A
     return A
 

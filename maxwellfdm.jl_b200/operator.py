@@ -53,6 +53,7 @@ class FdfdOperator:
         self._h = h
         self.ft = 0 if d.field_type == L.FT_EE else 1        # EE / HH as in grid.py
         self.N = tuple(int(n) for n in N)
+        self._isbloch = tuple(bool(b) for b in isbloch)
         self.order_cmpfirst = bool(order_cmpfirst)
         k0, k1 = C.c_int64(), C.c_int64()
         L.check(lib.fdfd_slab_range(h, C.byref(k0), C.byref(k1)), h)
@@ -122,6 +123,30 @@ class FdfdOperator:
         if has_offdiag is None:
             has_offdiag = True  # the library scans and drops the flag if every off-diagonal entry is 0
         L.check(L.lib().fdfd_set_eps(self._h, buf.ctypes.data, 1 if has_offdiag else 0), self._h)
+
+    def set_eps_objects(self, lprim, shapes, pinds, params, boundft=("E", "E", "E"), isbloch=None, field_ortho_shape=False):
+        """eps straight from objects (shapes.py): this rank's slab is rasterised and subpixel-smoothed on the device,
+        directly into the operator's material arrays - no (Nx,Ny,Nz,3,3) host array.  lprim: the Grid's ghosted primal
+        planes; shapes / pinds / params as for calc_matparams_array; boundft / isbloch must be the handle's."""
+        from .shapes import _as_tensor
+        sh = (L.Shape * len(shapes))()
+        for s, shp, pi in zip(sh, shapes, pinds):
+            s.kind, s.axis, s.pind = shp.kind, shp.axis, int(pi)
+            s.c[:] = shp.c
+            s.r[:] = shp.r
+        prm = np.ascontiguousarray(np.stack([_as_tensor(P) for P in params]).reshape(-1, 9))
+        lp = [np.ascontiguousarray(a, dtype=np.float64) for a in lprim]
+        d = L.MatParamsDesc()
+        d.N[:] = self.N
+        d.isbloch[:] = [1 if b else 0 for b in (self._isbloch if isbloch is None else isbloch)]
+        d.boundft_is_E[:] = [1 if str(b).upper().startswith("E") or b == 0 else 0 for b in boundft]
+        d.field_type = L.FT_EE
+        d.field_ortho_shape = 1 if field_ortho_shape else 0
+        d.lprim[:] = [a.ctypes.data for a in lp]
+        d.nshape, d.nparam = len(shapes), prm.shape[0]
+        d.shapes = C.cast(sh, C.c_void_p).value
+        d.params = prm.ctypes.data
+        L.check(L.lib().fdfd_set_eps_objects(self._h, C.byref(d)), self._h)
 
     def set_mu(self, mu):
         if mu is None:

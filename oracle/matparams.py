@@ -210,6 +210,7 @@ def calc_matparams(grid: Grid, boundft, ft, shapes, pinds, params, field_ortho_s
     N = grid.N
     gl = _ghosted(grid)
     params = [np.asarray(P, complex).reshape(3, 3) for P in params]
+    symmetric = all(np.array_equal(P, P.T) for P in params)   # then the average is symmetric: upper triangle to both places
     out = np.zeros(N + (3, 3), complex)
     for v in range(4):
         gts = location_gt(ft, boundft, v)
@@ -224,7 +225,7 @@ def calc_matparams(grid: Grid, boundft, ft, shapes, pinds, params, field_ortho_s
                 out[i, j, k, v, v] = P[v, v]
             else:
                 for a, b in itertools.permutations(range(3), 2):
-                    out[i, j, k, a, b] = P[a, b]
+                    out[i, j, k, a, b] = P[b, a] if (symmetric and a > b) else P[a, b]
     return out
 
 

@@ -213,6 +213,31 @@ def g_matparams():
         slab = fb.calc_matparams_array(g, boundft, ft, f_sh, pinds, params, k0=k0, k1=k1, device=0)
         assert np.array_equal(slab, got[:, :, k0:k1]), "slab differs from the full-grid result"
         n += 2
+    # eps straight from objects (no host array): same operator as the one fed with the array calc_matparams_array returns
+    for N, isbloch, boundft_o, sym in (((12, 10, 9), (True, False, True), (EE, EE, EE), True), ((13, 9, 11), (False, True, False), (EE, HH, EE), False)):
+        lp, o_sh, f_sh2, pinds2, params2 = matparams_scene(N, isbloch, False, 6, not sym)
+        p = Problem(N, isbloch, boundft_o)
+        p.grid_lp = lp
+        g2 = fb.Grid(lp, isbloch)
+        eps = fb.calc_matparams_array(g2, boundft_o, EE, f_sh2, pinds2, params2, device=0)
+        bf = ["E" if b == EE else "H" for b in boundft_o]
+        A1 = fb.FdfdOperator(N, isbloch, p.sdl_e, p.sdl_m, p.omega, eps, None, p.ph, boundft=bf, device=0, kernel=TILED)
+        A2 = fb.FdfdOperator(N, isbloch, p.sdl_e, p.sdl_m, p.omega, None, None, p.ph, boundft=bf, device=0, kernel=TILED)
+        A2.set_eps_objects(lp, f_sh2, pinds2, params2, boundft=bf)
+        x = p.random_x()
+        y1, y2 = apply_dev(A1, x), apply_dev(A2, x)
+        assert np.array_equal(y1, y2), f"objects path differs from the array path: {rel(y2, y1):.2e}"
+        assert A1.offdiag_symmetric == sym and A2.offdiag_symmetric == sym, (A1.offdiag_symmetric, A2.offdiag_symmetric, sym)
+        assert np.isfinite(y1).all() and A2.offdiag_fraction > 0
+        try:
+            A2.export_pattern()
+        except L.FdfdError as e:
+            assert e.code == L.ESTATE
+        else:
+            raise AssertionError("export_pattern must refuse a handle without a host eps array")
+        A1.close()
+        A2.close()
+        n += 2
     try:
         fb.calc_matparams_array(g, boundft, ft, f_sh[1:2], [0], params[:1], device=0)
     except L.FdfdError as e:

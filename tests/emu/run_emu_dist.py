@@ -146,6 +146,27 @@ def child(rank, world, groups):
             A.close()
             assert e1 < 1e-12 and e2 < 1e-12 and e3 < 1e-12, (rank, cs, kern, e1, e2, e3)
             nchecks += 3
+    if "apply" in groups:
+        # eps from objects on z-slabs: every rank rasterises its own planes; the slabs together are the single-slab operator
+        from problems import matparams_scene
+        from oracle.grid import EE
+        os.environ.pop("FDFD_LZ", None)
+        N, isbloch = (14, 11, 3 * world + 2), (True, False, True)
+        lp, _, f_sh, pinds, params = matparams_scene(N, isbloch, False, 6, False)
+        p = Problem(N, isbloch)
+        eps = np.zeros(N + (3, 3), complex)
+        k0, k1 = fb.partition(N[2], world, rank)
+        A = fb.FdfdOperator(N, isbloch, p.sdl_e, p.sdl_m, p.omega, None, None, p.ph, device=0, rank=rank, nranks=world)
+        A.set_eps_objects(lp, f_sh, pinds, params)
+        A.comm_init(comm_id())
+        # reference: the array of the whole grid (same kernel, so the comparison is exact up to the operator's own rounding)
+        p.eps = fb.calc_matparams_array(fb.Grid(lp, isbloch), (EE,) * 3, EE, f_sh, pinds, params, device=0)
+        p.full_eps = True
+        x = p.random_x()
+        e = rel(dev_apply(A, slab_of(p, x, k0, k1)), slab_of(p, p.oracle_matfree()(x), k0, k1))
+        assert e < 1e-12 and A.offdiag_symmetric, (rank, e)
+        A.close()
+        nchecks += 1
     if "krylov" in groups:
         os.environ.pop("FDFD_LZ", None)
         import scipy.sparse.linalg as spla

@@ -597,3 +597,42 @@ def test_model_with_objects_end_to_end():
     x = crandn(np.random.default_rng(SEED), A.n)
     assert rel(A @ x, A_ref.matvec(x)) < 1e-10
     A.close()
+
+
+def test_eps_from_objects_on_the_device():
+    """fdfd_set_eps_objects: the operator rasterises and smooths its own slab on the device (no host eps array); it is
+    bit-for-bit the operator that is fed the array fdfd_calc_matparams returns, and symmetric materials are stored once"""
+    from problems import matparams_scene
+    fb = _fb()
+    for N, isbloch, boundft, sym in (((12, 10, 9), (True, False, True), (EE, EE, EE), True),
+                                     ((13, 9, 11), (False, True, False), (EE, HH, EE), False)):
+        lp, _, f_sh, pinds, params = matparams_scene(N, isbloch, False, 6, not sym)
+        p = Problem(N, isbloch, boundft)
+        eps = fb.calc_matparams_array(fb.Grid(lp, isbloch), boundft, EE, f_sh, pinds, params, device=0)
+        bf = ["E" if b == EE else "H" for b in boundft]
+        A1 = fb.FdfdOperator(N, isbloch, p.sdl_e, p.sdl_m, p.omega, eps, None, p.ph, boundft=bf, device=0)
+        A2 = fb.FdfdOperator(N, isbloch, p.sdl_e, p.sdl_m, p.omega, None, None, p.ph, boundft=bf, device=0)
+        A2.set_eps_objects(lp, f_sh, pinds, params, boundft=bf)
+        x = p.random_x()
+        assert np.array_equal(_apply_dev(A1, x), _apply_dev(A2, x))
+        assert A1.offdiag_symmetric == sym and A2.offdiag_symmetric == sym
+        with pytest.raises(fb._lib.FdfdError):
+            A2.export_pattern()
+        A1.close()
+        A2.close()
+    # model API: objects -> operator without mdl.eps_arr ever being filled
+    n = 12
+    lpm = (np.arange(n + 1) - n / 2) * 1.0
+    mdl = fb.ModelFull(fb.Grid((lpm, lpm, lpm), (False, False, False)))
+    w = 2 * np.pi / 8.0
+    fb.set_wpml(mdl, w)
+    fb.set_Npml(mdl, ((2,) * 3, (2,) * 3))
+    fb.add_obj(mdl, "vacuum", fb.Box([0, 0, 0], [10, 10, 10]), eps=1.0)
+    fb.add_obj(mdl, "glass", fb.Ball([0.3, -0.2, 0.1], 3.4), eps=2.25)
+    Ad = fb.create_A(fb.EE, w, fb.create_paramops(mdl, device=0, device_materials=True), fb.create_curls(mdl), device=0)
+    assert not mdl.eps_arr.any()
+    Ah = fb.create_A(fb.EE, w, fb.create_paramops(mdl, device=0), fb.create_curls(mdl), device=0)
+    x = crandn(np.random.default_rng(SEED), Ad.n)
+    assert np.array_equal(Ad @ x, Ah @ x)
+    Ad.close()
+    Ah.close()
