@@ -234,8 +234,10 @@ __global__ void __launch_bounds__(256) offdiag_march_kernel(const __grid_constan
     auto corner = [&](int kk, double2 &ezm, double2 &Gx, double2 &Gy, double2 &Gz) {
         const int64_t m = g.gidx(ci, cj, kk);
         if (SKIPZ) {
-            const double2 o01 = p.mo[0][m], o02 = p.mo[1][m], o10 = p.mo[2][m], o12 = p.mo[3][m], o20 = p.mo[4][m],
-                          o21 = p.mo[5][m];
+            // a tensor stored once (aliased slots, api.cu) needs three loads, not six
+            const bool sym = p.mo[2] == p.mo[0] && p.mo[4] == p.mo[1] && p.mo[5] == p.mo[3];
+            const double2 o01 = p.mo[0][m], o02 = p.mo[1][m], o12 = p.mo[3][m];
+            const double2 o10 = sym ? o01 : p.mo[2][m], o20 = sym ? o02 : p.mo[4][m], o21 = sym ? o12 : p.mo[5][m];
             have_e = nonzero(o01) | nonzero(o02) | nonzero(o10) | nonzero(o12) | nonzero(o20) | nonzero(o21);
             if (!have_e) {
                 Gx = Gy = Gz = c_zero();

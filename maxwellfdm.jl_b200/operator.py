@@ -113,8 +113,9 @@ class FdfdOperator:
         C-contiguous complex128 array of shape (3,3,nzl,Ny,Nx) indexed [u,v,k,j,i], which IS the memory of the Julia
         column-major (Nx,Ny,nzl,3,3) array."""
         eps = np.asarray(eps)
+        # (a 3x3 grid in x-y makes the two shapes coincide: such an array is read as [i,j,k,v,u])
         if eps.shape == (3, 3, self.nzl, self.N[1], self.N[0]) and eps.dtype == np.complex128 and eps.flags.c_contiguous \
-                and (self.nzl, self.N[1], self.N[0]) != (3, 3, 3):
+                and (self.N[1], self.N[0]) != (3, 3):
             buf = eps
         elif eps.shape != (self.N[0], self.N[1], self.nzl, 3, 3):
             raise ValueError(f"eps must have shape (Nx,Ny,nzl,3,3) = {(self.N[0], self.N[1], self.nzl, 3, 3)}")

@@ -43,7 +43,7 @@ def check(err, what, tol=TOL):
 
 def g_apply():
     """every Bloch/symmetry combination, diagonal / full eps / +mu, odd shapes, N_w = 1..3 (tiled kernel vs CSC oracle)"""
-    shapes = [(1, 1, 1), (2, 1, 3), (3, 2, 1), (5, 3, 2), (3, 5, 8), (31, 15, 4), (33, 17, 9), (70, 45, 6)]
+    shapes = [(1, 1, 1), (2, 1, 3), (3, 2, 1), (3, 3, 2), (5, 3, 2), (3, 5, 8), (31, 15, 4), (33, 17, 9), (70, 45, 6)]
     combos = list(itertools.product([True, False], repeat=3))
     n = 0
     for N in shapes:

@@ -47,7 +47,7 @@ def _apply_dev(A, x, transpose=False):
 
 KERNELS = {"naive": 1, "tiled": 2}
 
-SMALL = [(1, 1, 1), (2, 1, 3), (3, 2, 1), (5, 3, 2), (3, 5, 8), (31, 15, 4), (33, 17, 9), (70, 45, 6)]
+SMALL = [(1, 1, 1), (2, 1, 3), (3, 2, 1), (3, 3, 2), (5, 3, 2), (3, 5, 8), (31, 15, 4), (33, 17, 9), (70, 45, 6)]
 
 
 @pytest.mark.parametrize("kernel", ["tiled", "naive"])
