@@ -21,3 +21,15 @@ def test_oracle_reproduces_golden():
         assert np.array_equal(cp, g[f"{tag}_colptr"]) and np.array_equal(rv, g[f"{tag}_rowval"])
         cp2, rv2, _ = p.operator(device=-2).export_pattern(values=False)
         assert np.array_equal(cp2, g[f"{tag}_colptr"]) and np.array_equal(rv2, g[f"{tag}_rowval"])
+
+
+def test_oracle_reproduces_matparams_golden():
+    """material pipeline (N4): the committed arrays (tests/golden/make_golden_matparams.py) equal today's oracle"""
+    from oracle import matparams as omp
+    from oracle.grid import Grid
+    from problems import matparams_scene, MATPARAMS_CASES
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "matparams_golden.npz"))
+    for i in (1, 2):
+        N, isbloch, boundft, ft, uniform, nshape, aniso = MATPARAMS_CASES[i]
+        lp, o_sh, _, pinds, params = matparams_scene(N, isbloch, uniform, nshape, aniso)
+        assert rel(omp.calc_matparams(Grid(lp, isbloch), boundft, ft, o_sh, pinds, params), g[f"case{i}"]) < 1e-14

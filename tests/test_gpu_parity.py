@@ -553,12 +553,15 @@ def test_calc_matparams_matches_oracle():
     from oracle.grid import Grid as OGrid
     from problems import matparams_scene, MATPARAMS_CASES
     fb = _fb()
-    for N, isbloch, boundft, ft, uniform, nshape, aniso in MATPARAMS_CASES:
+    golden = np.load(os.path.join(os.path.dirname(__file__), "golden", "matparams_golden.npz"))
+    for case_no, (N, isbloch, boundft, ft, uniform, nshape, aniso) in enumerate(MATPARAMS_CASES):
         lp, o_sh, f_sh, pinds, params = matparams_scene(N, isbloch, uniform, nshape, aniso)
         ref = omp.calc_matparams(OGrid(lp, isbloch), boundft, ft, o_sh, pinds, params)
         g = fb.Grid(lp, isbloch)
         got = fb.calc_matparams_array(g, boundft, ft, f_sh, pinds, params, device=0)
         assert rel(got, ref) < 1e-10, (N, isbloch, boundft, ft, rel(got, ref))
+        if f"case{case_no}" in golden:                       # committed fixture (tests/golden/make_golden_matparams.py)
+            assert rel(got, golden[f"case{case_no}"]) < 1e-10
         slab = fb.calc_matparams_array(g, boundft, ft, f_sh, pinds, params, k0=2, k1=N[2] - 1, device=0)
         assert np.array_equal(slab, got[:, :, 2:N[2] - 1])
     with pytest.raises(fb._lib.FdfdError):
