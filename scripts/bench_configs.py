@@ -20,19 +20,23 @@ PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if 
 
 
 def measure(name, w, steps=100, kry=20):
-    A = workloads.make_operator(w, device=0)
+    t_setup = time.perf_counter()
+    A = workloads.make_operator_from_objects(w, device=0) if "shapes" in w else workloads.make_operator(w, device=0)
     n = A.n
     g = torch.Generator(device="cuda").manual_seed(1)
     x = torch.randn(n, 2, device="cuda", dtype=torch.float64, generator=g).view(torch.complex128).reshape(-1)
     y = torch.empty_like(x)
     A.bench_apply(x, y, warmup=5, iters=1)
+    t_setup = time.perf_counter() - t_setup       # operator set-up incl. the first applies (objects: rasterisation on the device)
     ms, _ = A.bench_apply(x, y, warmup=0, iters=steps)
     ms /= steps
     off = A.offdiag_fraction if w["full_eps"] else 0.0
     bpd = 48 + (16 if (w["full_eps"] and A.offdiag_symmetric) else 32) * off
     b = torch.randn(n, 2, device="cuda", dtype=torch.float64, generator=g).view(torch.complex128).reshape(-1)
     out = {"config": name, "grid": list(w["N"]), "dof": n, "ms_per_apply": ms, "gdof_s": n / ms / 1e6,
-           "bytes_per_dof": bpd, "hbm_frac": bpd * n / (ms * 1e-3) / 1e9 / PEAK, "offdiag_block_fraction": off}
+           "bytes_per_dof": bpd, "hbm_frac": bpd * n / (ms * 1e-3) / 1e9 / PEAK, "offdiag_block_fraction": off,
+           "offdiag_symmetric": bool(w["full_eps"] and A.offdiag_symmetric), "setup_s": t_setup,
+           "corr_skip_zero": bool(os.environ.get("FDFD_CORR_SKIP_ZERO"))}
     for method in ("bicgstab", "qmr"):
         xs = torch.zeros_like(b)
         t = A.bench_solve(b, xs, method, warmup=2, iters=kry)
@@ -70,6 +74,9 @@ if __name__ == "__main__":
         print(json.dumps(measure("C2 Si waveguide 200^3, full eps (sparse off-diagonals)", workloads.c2_waveguide())))
         print(json.dumps(measure("C3 PhC slab 256x256x128, Bloch x/y, PML z", workloads.c3_phc_slab())))
         print(json.dumps(c1_solve()))
+    if "--objects" in sys.argv:        # C4 / C5 described by objects: Kottke-smoothed on the device, no host eps array
+        print(json.dumps(measure("C4 sphere 512^3 from objects (1 GPU)", workloads.c4_objects(), steps=20, kry=5)))
+        print(json.dumps(measure("C5 metalens 1024x1024x96 from objects (1 GPU)", workloads.c5_objects(), steps=20, kry=5)))
     if "--c4" in sys.argv:
         t0 = time.perf_counter()
         w4 = workloads.c4_scatterer()

@@ -14,6 +14,8 @@ single)
   timeout 900 python scripts/bench_configs.py > gpurun_out/r02_configs_default.jsonl 2>&1; echo "configs rc=$?"
   FDFD_CORR_SKIP_ZERO=1 timeout 900 python scripts/bench_configs.py > gpurun_out/r02_configs_skipz.jsonl 2>&1; echo "configs (skip-zero) rc=$?"
   for f in gpurun_out/r02_configs_default.jsonl gpurun_out/r02_configs_skipz.jsonl; do echo $f; cut -c1-200 $f | grep gdof_s; done
+  timeout 900 python scripts/bench_configs.py --skip-small --objects > gpurun_out/r02_configs_objects.jsonl 2>&1; echo "configs (objects) rc=$?"; cut -c1-260 gpurun_out/r02_configs_objects.jsonl
+  FDFD_CORR_SKIP_ZERO=1 timeout 900 python scripts/bench_configs.py --skip-small --objects > gpurun_out/r02_configs_objects_skipz.jsonl 2>&1; echo "configs (objects, skip-zero) rc=$?"; cut -c1-260 gpurun_out/r02_configs_objects_skipz.jsonl
   timeout 600 python scripts/bench_matparams.py > gpurun_out/r02_matparams_bench.jsonl 2>&1; echo "matparams bench rc=$?"; cat gpurun_out/r02_matparams_bench.jsonl | cut -c1-300
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:matparams --csv --log-file gpurun_out/r02_matparams_launches.csv python scripts/bench_matparams.py > /dev/null 2>&1; echo "ncu rc=$?"
   ;;

@@ -286,3 +286,48 @@ def make_operator(w, device=-1, rank=0, nranks=1, kernel=0, **kw):
     return fb.FdfdOperator(w["N"], w["isbloch"], w["sdl_e"], w["sdl_m"], w["omega"], w["eps"], None, w["e_mikL"],
                            device=device, rank=rank, nranks=nranks, kernel=kernel,
                            eps_has_offdiag=w["full_eps"], **kw)
+
+
+# ---------------------------------------------------------------------------------------------------
+# The same configurations described by OBJECTS (material pipeline): eps is rasterised and subpixel-
+# smoothed on the device by the operator itself (fdfd_set_eps_objects) - no (Nx,Ny,Nz,3,3) host array.  These replace
+# the analytic stand-ins above once the pipeline has been timed on hardware (round 2).
+# ---------------------------------------------------------------------------------------------------
+def c4_objects(N=(512, 512, 512), delta=20.0, radius_cells=100):
+    """C4 from objects: vacuum box + one ball (eps 4, radius 100 cells) centred in the domain."""
+    w = _common(N, delta, (False, False, False), ((10,) * 3, (10,) * 3))
+    g = w["grid"]
+    c = [0.5 * (g.bounds[0][a] + g.bounds[1][a]) for a in range(3)]
+    shapes = [fb.Box(c, [2 * L for L in g.L]), fb.Ball(c, radius_cells * delta)]
+    w.update(shapes=shapes, pinds=[0, 1], params=[np.eye(3), 4.0 * np.eye(3)], full_eps=True,
+             name=f"C4 dielectric sphere {N[0]}x{N[1]}x{N[2]} from objects (Kottke-smoothed on the device), 10-cell PML")
+    return w
+
+
+def c5_objects(N=(1024, 1024, 96), seed=7, delta=20.0, pitch_cells=32):
+    """C5 weak-scaling unit from objects: substrate slab (eps 2.1) + one cylinder (eps 6.0, seeded radius) per pitch cell."""
+    w = _common(N, delta, (True, True, False), ((0, 0, 10), (0, 0, 10)))
+    g = w["grid"]
+    lo, L = g.bounds[0], g.L
+    c = [lo[a] + 0.5 * L[a] for a in range(3)]
+    zsub = lo[2] + 0.25 * L[2]
+    shapes = [fb.Box(c, [2 * l for l in L]), fb.Box([c[0], c[1], lo[2] + 0.5 * (zsub - lo[2])], [2 * L[0], 2 * L[1], 0.5 * (zsub - lo[2])])]
+    pinds = [0, 1]
+    rng = np.random.default_rng(seed)
+    pitch = pitch_cells * delta
+    h = 0.2 * L[2]
+    for j in range(N[1] // pitch_cells):
+        for i in range(N[0] // pitch_cells):
+            r = (0.15 + 0.25 * rng.random()) * pitch
+            shapes.append(fb.Cylinder([lo[0] + (i + 0.5) * pitch, lo[1] + (j + 0.5) * pitch, zsub + h], r, h, axis=2))
+            pinds.append(2)
+    w.update(shapes=shapes, pinds=pinds, params=[np.eye(3), 2.1 * np.eye(3), 6.0 * np.eye(3)], full_eps=True,
+             name=f"C5 metalens {N[0]}x{N[1]}x{N[2]} from objects ({len(shapes) - 2} pillars, Kottke-smoothed on the device)")
+    return w
+
+
+def make_operator_from_objects(w, device=-1, rank=0, nranks=1, kernel=0, **kw):
+    A = fb.FdfdOperator(w["N"], w["isbloch"], w["sdl_e"], w["sdl_m"], w["omega"], None, None, w["e_mikL"],
+                        device=device, rank=rank, nranks=nranks, kernel=kernel, **kw)
+    A.set_eps_objects(w["grid"].lg_prim, w["shapes"], w["pinds"], w["params"])
+    return A
