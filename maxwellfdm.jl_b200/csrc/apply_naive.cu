@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(128) interp_kernel(const __grid_constant__ App
 // streams plus x / y only around the interface cells instead of 64-80 B per DOF of the whole block.  Results are
 // identical (only additions of exact zeros are dropped).
 template <bool SKIPZ>
-__global__ void __launch_bounds__(256, SKIPZ ? 2 : 1) offdiag_march_kernel(const __grid_constant__ ApplyParams p,
+__global__ void __launch_bounds__(256, SKIPZ ? 2 : 0) offdiag_march_kernel(const __grid_constant__ ApplyParams p,
                                                              const int4 *__restrict__ items, int ntx, int kl_begin,
                                                              int kl_end) {
     const int4 item = items[blockIdx.x];
