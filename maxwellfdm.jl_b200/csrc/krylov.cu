@@ -21,11 +21,12 @@ using namespace kry;
 
 // complex scalar slots (index into double2 array)
 enum { S_RHO0 = 0, S_RR0 = 1, S_RHO1 = 2, S_RR1 = 3, S_SIGMA = 4, S_TS = 5, S_TT = 6, S_ALPHA = 7, S_OMEGA = 8,
-       S_BNORM = 9, S_TMP0 = 10, S_TMP1 = 11, S_TMP2 = 12 };
+       S_BNORM = 9, S_TMP0 = 10, S_TMP1 = 11, S_TMP2 = 12, S_SIG0 = 13, S_SIG1 = 14, S_SIG2 = 15 };
 
-// r = b - r ; rhat = r ; p = r ;  RHO0 = RR0 = (r,r) ; BNORM = (b,b)
+// r = b - r ; rhat = r ; p = r ;  RHO0 = RR0 = (r,r) ; BNORM = (b,b) ; cj = conj(rhat) when asked for
 __global__ void __launch_bounds__(RB) k_init(int64_t n, const double2 *__restrict__ b, double2 *__restrict__ r,
-                                             double2 *__restrict__ rhat, double2 *__restrict__ p, Red rd) {
+                                             double2 *__restrict__ rhat, double2 *__restrict__ p,
+                                             double2 *__restrict__ cj, Red rd) {
     double2 acc[2] = {c_zero(), c_zero()};
     double2 accb[1] = {c_zero()};
     GRID_STRIDE(i, n) {
@@ -34,6 +35,7 @@ __global__ void __launch_bounds__(RB) k_init(int64_t n, const double2 *__restric
         r[i] = rr;
         rhat[i] = rr;
         p[i] = rr;
+        if (cj) cj[i] = make_double2(rr.x, -rr.y);
         dot_acc(acc[0], rr, rr);
         dot_acc(accb[0], bb, bb);
     }
@@ -50,10 +52,25 @@ __global__ void __launch_bounds__(RB) k_dot1(int64_t n, const double2 *__restric
     reduce_publish<1>(acc, rd, slot);
 }
 
+// sum_i u_i p_i (no conjugation) -> slot
+__global__ void __launch_bounds__(RB) k_dotu1(int64_t n, const double2 *__restrict__ u, const double2 *__restrict__ p,
+                                              Red rd, int slot) {
+    double2 acc[1] = {c_zero()};
+    GRID_STRIDE(i, n) dotu_acc(acc[0], u[i], p[i]);
+    reduce_publish<1>(acc, rd, slot);
+}
+
+// sigma = (rhat, v): slot SIGMA, or - when it was accumulated by the kernels that produced p - the sum of SIG0..2
+__device__ __forceinline__ double2 load_sigma(const Red &rd, int sig3) {
+    if (!sig3) return rd.scal[S_SIGMA];
+    const double2 a = rd.scal[S_SIG0], b = rd.scal[S_SIG1], c = rd.scal[S_SIG2];
+    return make_double2(a.x + b.x + c.x, a.y + b.y + c.y);
+}
+
 // alpha = rho/sigma ; s = r - alpha v
 __global__ void __launch_bounds__(RB) k_s(int64_t n, const double2 *__restrict__ r, const double2 *__restrict__ v,
-                                          double2 *__restrict__ s, Red rd, int rho_slot) {
-    const double2 alpha = c_div(rd.scal[rho_slot], rd.scal[S_SIGMA]);
+                                          double2 *__restrict__ s, Red rd, int rho_slot, int sig3) {
+    const double2 alpha = c_div(rd.scal[rho_slot], load_sigma(rd, sig3));
     GRID_STRIDE(i, n) s[i] = c_fms(alpha, v[i], r[i]);
     if (blockIdx.x == 0 && threadIdx.x == 0) rd.scal[S_ALPHA] = alpha;
 }
@@ -93,14 +110,22 @@ __global__ void __launch_bounds__(RB) k_xr(int64_t n, double2 *__restrict__ x, c
 }
 
 // beta = (rho'/rho)(alpha/omega) ; p = r + beta (p - omega v)
+// SIG: also the next iteration's sigma = (rhat, A p) = sum_i u_i p_i with u = A^T conj(rhat) fixed for the whole solve,
+// accumulated while p is in registers -> sig_slot (the separate pass over rhat and v after the apply disappears)
+template <bool SIG>
 __global__ void __launch_bounds__(RB) k_p(int64_t n, const double2 *__restrict__ r, const double2 *__restrict__ v,
-                                          double2 *__restrict__ p, Red rd, int rho_old_slot, int rho_new_slot) {
+                                          double2 *__restrict__ p, const double2 *__restrict__ u, Red rd,
+                                          int rho_old_slot, int rho_new_slot, int sig_slot) {
     const double2 omega = rd.scal[S_OMEGA];
     const double2 beta = c_mul(c_div(rd.scal[rho_new_slot], rd.scal[rho_old_slot]), c_div(rd.scal[S_ALPHA], omega));
+    double2 acc[1] = {c_zero()};
     GRID_STRIDE(i, n) {
         const double2 q = c_fms(omega, v[i], p[i]);
-        p[i] = c_fma(beta, q, r[i]);
+        const double2 pn = c_fma(beta, q, r[i]);
+        p[i] = pn;
+        if (SIG) dotu_acc(acc[0], u[i], pn);
     }
+    if (SIG) reduce_publish<1>(acc, rd, sig_slot);
 }
 
 __global__ void k_store_hist(double *hist, int idx, const double2 *scal, int rr_slot) {
@@ -117,11 +142,16 @@ static int bicgstab(Ctx *c, const double2 *b, double2 *x, double rtol, int maxit
                     int *iters, double *relres, double *hist) {
     int rc = ensure_ready(c);
     if (rc != FDFD_OK) return rc;
-    if ((rc = kry::workspace(c, 6)) != FDFD_OK) return rc;
+    // sigma = (rhat, A p) is taken as (A^H rhat, p): u = A^T conj(rhat) is computed once (one transposed apply, one more
+    // workspace vector) and the sum rides on the kernel that writes p, so an iteration has one vector pass (32 B/DOF
+    // read, one launch, one reduction tail) less and the allreduce of sigma no longer sits behind the apply.
+    // FDFD_BICGSTAB_CLASSIC restores the separate (rhat, v) pass.
+    const bool sigf = getenv("FDFD_BICGSTAB_CLASSIC") == nullptr;
+    if ((rc = kry::workspace(c, sigf ? 7 : 6)) != FDFD_OK) return rc;
     if ((rc = peer_direct_map(c)) != FDFD_OK) return rc;   // opt-in (FDFD_PEER_DIRECT): neighbours' workspaces, read in place
     if ((rc = ensure_dot_buffers(c)) != FDFD_OK) return rc;
     const int64_t n = c->nloc;
-    double2 *r = c->work, *rhat = r + n, *p = rhat + n, *v = p + n, *s = v + n, *t = s + n;
+    double2 *r = c->work, *rhat = r + n, *p = rhat + n, *v = p + n, *s = v + n, *t = s + n, *u = sigf ? t + n : nullptr;
     Red rd = kry::make_red(c);
     double *sc = c->scal;
     const int g = kry::grid_for(n);
@@ -134,7 +164,7 @@ static int bicgstab(Ctx *c, const double2 *b, double2 *x, double rtol, int maxit
 
     // r = b - A x0
     KCHK(apply_device(c, x, r, false));
-    k_init<<<g, RB, 0, st>>>(n, b, r, rhat, p, rd);
+    k_init<<<g, RB, 0, st>>>(n, b, r, rhat, p, sigf ? v : nullptr, rd);
     LCHK();
     c->launches += 1;
     KCHK(allreduce_sum(c, sc + 2 * S_RHO0, 4, st));
@@ -166,6 +196,15 @@ static int bicgstab(Ctx *c, const double2 *b, double2 *x, double rtol, int maxit
         }
         converged = rel <= rtol;
     }
+    if (sigf && !converged && maxit > 0) {
+        // u = A^T conj(rhat) (conj(rhat) was left in v by k_init), sigma of the first iteration = sum u_i p_i
+        FDFD_CUDA(c, cudaMemsetAsync(sc + 2 * S_SIG0, 0, 3 * sizeof(double2), st));
+        KCHK(apply_device(c, v, u, true));
+        k_dotu1<<<g, RB, 0, st>>>(n, u, p, rd, S_SIG0);
+        LCHK();
+        c->launches += 1;
+        KCHK(allreduce_sum(c, sc + 2 * S_SIG0, 6, st));
+    }
     // z-slabs: the kernels that produce s and p handle the two boundary planes first so that the NCCL halo exchange
     // of the next apply runs behind their interior part (halo_prefetch)
     const bool pre = halo_prefetch_usable(c);
@@ -177,16 +216,20 @@ static int bicgstab(Ctx *c, const double2 *b, double2 *x, double rtol, int maxit
         const int rho_old = par ? S_RHO1 : S_RHO0, rho_new = par ? S_RHO0 : S_RHO1;
         int r1 = apply_device(c, p, v, false);
         if (r1 != FDFD_OK) return r1;
-        k_dot1<<<g, RB, 0, st>>>(n, rhat, v, rd, S_SIGMA);
-        if ((r1 = allreduce_sum(c, sc + 2 * S_SIGMA, 2, st)) != FDFD_OK) return r1;
+        if (!sigf) {
+            k_dot1<<<g, RB, 0, st>>>(n, rhat, v, rd, S_SIGMA);
+            if ((r1 = allreduce_sum(c, sc + 2 * S_SIGMA, 2, st)) != FDFD_OK) return r1;
+            c->launches += 1;
+        }
+        const int sig3 = sigf ? 1 : 0;
         if (pre) {   // boundary planes first, start their halo exchange, then the interior behind which it hides
-            k_s<<<gb, RB, 0, st>>>(pl, r, v, s, rd, rho_old);
-            k_s<<<gb, RB, 0, st>>>(pl, r + n - pl, v + n - pl, s + n - pl, rd, rho_old);
+            k_s<<<gb, RB, 0, st>>>(pl, r, v, s, rd, rho_old, sig3);
+            k_s<<<gb, RB, 0, st>>>(pl, r + n - pl, v + n - pl, s + n - pl, rd, rho_old, sig3);
             if ((r1 = halo_prefetch(c, s)) != FDFD_OK) return r1;
-            k_s<<<g, RB, 0, st>>>(n - 2 * pl, r + pl, v + pl, s + pl, rd, rho_old);
+            k_s<<<g, RB, 0, st>>>(n - 2 * pl, r + pl, v + pl, s + pl, rd, rho_old, sig3);
             c->launches += 2;
         } else {
-            k_s<<<g, RB, 0, st>>>(n, r, v, s, rd, rho_old);
+            k_s<<<g, RB, 0, st>>>(n, r, v, s, rd, rho_old, sig3);
         }
         // t = A s with (t,s) and (t,t) accumulated in the kernel epilogue when the tiled path is taken
         bool fused = false;
@@ -195,18 +238,27 @@ static int bicgstab(Ctx *c, const double2 *b, double2 *x, double rtol, int maxit
         if ((r1 = allreduce_sum(c, sc + 2 * S_TS, 4, st)) != FDFD_OK) return r1;
         k_xr<<<g, RB, 0, st>>>(n, x, p, s, t, rhat, r, rd, rho_new);
         if ((r1 = allreduce_sum(c, sc + 2 * rho_new, 4, st)) != FDFD_OK) return r1;
-        if (pre) {
-            k_p<<<gb, RB, 0, st>>>(pl, r, v, p, rd, rho_old, rho_new);
-            k_p<<<gb, RB, 0, st>>>(pl, r + n - pl, v + n - pl, p + n - pl, rd, rho_old, rho_new);
+        if (pre && sigf) {   // the three parts of p publish their share of the next sigma into SIG1, SIG2, SIG0
+            k_p<true><<<gb, RB, 0, st>>>(pl, r, v, p, u, rd, rho_old, rho_new, S_SIG1);
+            k_p<true><<<gb, RB, 0, st>>>(pl, r + n - pl, v + n - pl, p + n - pl, u + n - pl, rd, rho_old, rho_new, S_SIG2);
             if ((r1 = halo_prefetch(c, p)) != FDFD_OK) return r1;
-            k_p<<<g, RB, 0, st>>>(n - 2 * pl, r + pl, v + pl, p + pl, rd, rho_old, rho_new);
+            k_p<true><<<g, RB, 0, st>>>(n - 2 * pl, r + pl, v + pl, p + pl, u + pl, rd, rho_old, rho_new, S_SIG0);
             c->launches += 2;
+        } else if (pre) {
+            k_p<false><<<gb, RB, 0, st>>>(pl, r, v, p, nullptr, rd, rho_old, rho_new, 0);
+            k_p<false><<<gb, RB, 0, st>>>(pl, r + n - pl, v + n - pl, p + n - pl, nullptr, rd, rho_old, rho_new, 0);
+            if ((r1 = halo_prefetch(c, p)) != FDFD_OK) return r1;
+            k_p<false><<<g, RB, 0, st>>>(n - 2 * pl, r + pl, v + pl, p + pl, nullptr, rd, rho_old, rho_new, 0);
+            c->launches += 2;
+        } else if (sigf) {
+            k_p<true><<<g, RB, 0, st>>>(n, r, v, p, u, rd, rho_old, rho_new, S_SIG0);
         } else {
-            k_p<<<g, RB, 0, st>>>(n, r, v, p, rd, rho_old, rho_new);
+            k_p<false><<<g, RB, 0, st>>>(n, r, v, p, nullptr, rd, rho_old, rho_new, 0);
         }
         cudaError_t e1 = cudaGetLastError();
         if (e1 != cudaSuccess) return set_err(c, FDFD_ECUDA, cudaGetErrorString(e1));
-        c->launches += 4;
+        if (sigf && (r1 = allreduce_sum(c, sc + 2 * S_SIG0, 6, st)) != FDFD_OK) return r1;
+        c->launches += 3;
         return FDFD_OK;
     };
     // Small grids are launch-bound (40^3: ~50 us of launches per iteration): replay two iterations (both scalar

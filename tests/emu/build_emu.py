@@ -17,7 +17,10 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "maxwellfdm.jl_b200", "csrc")
-OUT_DIR = os.path.join(ROOT, "build", "emu")
+# FDFD_EMU_FMA=1: a second build with fused multiply-adds contracted as nvcc does (-mfma -ffp-contract=fast), to see
+# whether a parity tolerance survives the different rounding of the device code (build/emu_fma/)
+FMA = bool(os.environ.get("FDFD_EMU_FMA"))
+OUT_DIR = os.path.join(ROOT, "build", "emu_fma" if FMA else "emu")
 OUT_LIB = os.path.join(OUT_DIR, "libfdfd_emu.so")
 FAKE_DIR = os.path.join(OUT_DIR, "fakelibs")
 SOURCES = ["api.cu", "apply_naive.cu", "apply_tiled.cu", "krylov.cu", "qmr.cu", "matparams.cu", "coeffs.cpp", "pattern.cpp", "comm.cpp",
@@ -86,7 +89,7 @@ def build(verbose=False):
     shim = os.path.join(HERE, "shim")
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))] + \
               [os.path.join(shim, f) for f in os.listdir(shim)] + [os.path.join(ROOT, "include", "fdfd_b200.h"), __file__]
-    flags = ["-O1", *(["-g"] if os.environ.get("FDFD_EMU_DEBUG") else []), "-std=c++17", "-fPIC", "-fopenmp",
+    flags = ["-O1", *(["-g"] if os.environ.get("FDFD_EMU_DEBUG") else []), *(["-O2", "-mfma", "-ffp-contract=fast"] if FMA else []), "-std=c++17", "-fPIC", "-fopenmp",
              "-Wno-unknown-pragmas", "-Wno-unused-variable", "-Wno-unused-but-set-variable", "-Wno-attributes",
              "-I", shim, "-I", CSRC, "-I", os.path.join(ROOT, "include")]
     objs, procs = [], []

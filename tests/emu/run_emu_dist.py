@@ -17,7 +17,7 @@ import time
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests"), HERE]
 
 
 def parent(world, groups):
@@ -186,6 +186,17 @@ def child(rank, world, groups):
                 e = rel(x, slab_of(p, x_ref, k0, k1))
                 assert e < 1e-7, (rank, ft, method, e, iters.value, relres.value)
                 nchecks += 1
+            # five BiCGSTAB iterations against the textbook iteration on the global operator: inner products that miss a
+            # slab's share (sigma is accumulated by the three launches that write p) keep r = b - A x consistent and
+            # may still converge, so only the trajectory shows them
+            from fuzz_krylov_emu import bicgstab_ref
+            x = np.zeros(A.n, complex)
+            code = L.lib().fdfd_solve(A._h, L.BICGSTAB, bs.ctypes.data, x.ctypes.data, L.DEVICE, 1e-300, 5, 1,
+                                      C.byref(iters), C.byref(relres), None)
+            assert code in (L.OK, L.ENOCONV), (rank, code)
+            e = rel(x, slab_of(p, bicgstab_ref(p.oracle_matfree(), b, 5), k0, k1))
+            assert e < 1e-9, (rank, ft, "trajectory", e)
+            nchecks += 1
             A.close()
     modes = [k for k in ("FDFD_PEER_DIRECT", "FDFD_PEER_HALO", "FDFD_INKERNEL_HALO_WAIT", "FDFD_SPLIT_OVERLAP", "FDFD_NO_HALO_PREFETCH") if os.environ.get(k)]
     print(f"emu dist rank {rank}/{world} [{','.join(modes) or 'default'}]: {nchecks} checks ok", flush=True)
