@@ -9,6 +9,10 @@ single)
   timeout 600 python -m pytest tests -m gpu -x -q -k "matparams or objects" > gpurun_out/r02_matparams_tests.log 2>&1; echo "matparams tests rc=$?"; tail -3 gpurun_out/r02_matparams_tests.log
   timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r02_gpu_tests.log 2>&1; echo "gpu tests rc=$?"; tail -3 gpurun_out/r02_gpu_tests.log
   python bench.py > gpurun_out/r02_bench_line.json 2> gpurun_out/r02_bench.err; echo "bench rc=$?"; cut -c1-400 gpurun_out/r02_bench_line.json
+  # BiCGSTAB with sigma accumulated by the p update (default since the end of round 1) vs the separate (rhat, v) pass
+  FDFD_BICGSTAB_CLASSIC=1 python bench.py --no-cpu > gpurun_out/r02_bench_line_classic_bicgstab.json 2>> gpurun_out/r02_bench.err; echo "bench (classic BiCGSTAB) rc=$?"
+  for f in gpurun_out/r02_bench_line.json gpurun_out/r02_bench_line_classic_bicgstab.json; do python -c "
+import sys,json; d=json.loads(open('$f').read().strip().splitlines()[-1]); print('$f', 'BiCGSTAB it/s', round(d['krylov']['iter_per_s'],1), 'hbm_frac', round(d['krylov']['hbm_frac'],3))"; done
   # correction pass that skips exact zeros (opt-in): parity of the whole suite with it on, then C2-C5 with / without
   FDFD_CORR_SKIP_ZERO=1 timeout 900 python -m pytest tests -m gpu -x -q -k "not matparams and not objects" > gpurun_out/r02_gpu_tests_skipz.log 2>&1; echo "gpu tests (skip-zero) rc=$?"; tail -2 gpurun_out/r02_gpu_tests_skipz.log
   timeout 900 python scripts/bench_configs.py > gpurun_out/r02_configs_default.jsonl 2>&1; echo "configs rc=$?"

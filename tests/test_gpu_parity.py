@@ -369,6 +369,45 @@ def test_solve_matches_direct_solve(method):
     A.close()
 
 
+@pytest.mark.parametrize("classic", [False, True])
+@pytest.mark.parametrize("ft,full", [(EE, True), (EE, False), (HH, False)])
+def test_bicgstab_trajectory_matches_textbook_iteration(ft, full, classic):
+    """Inner products that are wrong (sigma accumulated by the p update from u = A^T conj(rhat), (t,s) / (t,t) from the
+    apply epilogue and the correction-pass deltas) keep r = b - A x consistent and may still converge: only the
+    iterates themselves show them.  Five iterations against the textbook BiCGSTAB on the oracle operator, both with
+    the default schedule and with the separate (rhat, v) pass (FDFD_BICGSTAB_CLASSIC)."""
+    p = Problem((33, 20, 11), (True, False, True), ft=ft, omega=1.2 - 0.3j, full_eps=full and ft == EE, with_mu=ft == HH)
+    mf = p.oracle_matfree()
+    b = p.random_x(3)
+    x_ref = np.zeros_like(b)                                    # textbook iteration (van der Vorst), numpy
+    r = b.copy(); rh = r.copy(); pv = r.copy(); rho = np.vdot(rh, r)
+    for _ in range(5):
+        v = mf(pv)
+        alpha = rho / np.vdot(rh, v)
+        sv = r - alpha * v
+        t = mf(sv)
+        omega = np.vdot(t, sv) / np.vdot(t, t)
+        x_ref = x_ref + alpha * pv + omega * sv
+        r = sv - omega * t
+        rho_new = np.vdot(rh, r)
+        pv = r + (rho_new / rho) * (alpha / omega) * (pv - omega * v)
+        rho = rho_new
+    A = p.operator(device=0, kernel=KERNELS["tiled"])
+    old = os.environ.pop("FDFD_BICGSTAB_CLASSIC", None)
+    try:
+        if classic:
+            os.environ["FDFD_BICGSTAB_CLASSIC"] = "1"
+        x, info = A.solve(b, method="bicgstab", rtol=1e-300, maxit=5, check_every=1)
+    finally:
+        os.environ.pop("FDFD_BICGSTAB_CLASSIC", None)
+        if old is not None:
+            os.environ["FDFD_BICGSTAB_CLASSIC"] = old
+    assert info["iters"] == 5
+    assert rel(x, x_ref) < 1e-9
+    assert abs(rel(mf(x), b) - info["relres"]) < 1e-9
+    A.close()
+
+
 def test_solve_edge_cases():
     fb = _fb()
     p = Problem((8, 7, 6), (True, True, True))
