@@ -2,6 +2,7 @@
 
 Same names and argument meaning as the reference (ASCII spellings: ω→w, ε→eps, μ→mu, ∆→d, ₑ→e, ₘ→m):
     ModelFull(grid)                     full.jl:7-13
+    ModelTE / ModelTM / ModelTEM        te.jl:4-14, tm.jl:4-14, tem.jl:4-13   (K < 3 grids: reduced.py)
     set_wpml / set_boundft / set_Npml / set_kbloch      model.jl:86-89
     create_e_mikL                       model.jl:91
     clear_srcs / add_srce / add_srcm / create_srcs      model.jl:177-207
@@ -22,25 +23,34 @@ import numpy as np
 from .grid import EE, HH, PRIM, DUAL, Grid, PMLParam, create_stretched_dl, ft2gt
 from .operator import FdfdOperator
 from .sources import Source
+from .reduced import ReducedOperator
+
+_OPS = (FdfdOperator, ReducedOperator)      # what create_A returns (3-D model / ModelTE, ModelTM, ModelTEM)
 
 
 class Model:
-    def __init__(self, grid):
+    def __init__(self, grid, cmp_s=(0, 1, 2), cmp_e=(0, 1, 2), cmp_m=(0, 1, 2)):
         K = len(grid)
+        if len(cmp_s) != K:
+            raise ValueError("cmp_s must name one Cartesian axis per grid axis")
+        # Cartesian components (0-based) of the shape dimensions, of E and of H (model.jl:41-43)
+        self.cmp_s, self.cmp_e, self.cmp_m = tuple(cmp_s), tuple(cmp_e), tuple(cmp_m)
+        Ke, Km = len(cmp_e), len(cmp_m)
         self.wpml = 0.0                                   # ωpml (model.jl:37)
         self.grid = grid
         self.boundft = (EE,) * K                          # model.jl:46
         self.Npml = ((0,) * K, (0,) * K)                  # model.jl:47
         self.kbloch = (0.0,) * K                          # model.jl:48
-        self.eps_arr = np.zeros(grid.N + (3, 3), np.complex128)   # create_param_array (model.jl:51-52)
-        self.mu_arr = np.zeros(grid.N + (3, 3), np.complex128)
-        self.je_arr = np.zeros(grid.N + (3,), np.complex128)      # create_field_array (model.jl:55-56)
-        self.jm_arr = np.zeros(grid.N + (3,), np.complex128)
+        self.eps_arr = np.zeros(grid.N + (Ke, Ke), np.complex128)   # create_param_array (model.jl:51-52)
+        self.mu_arr = np.zeros(grid.N + (Km, Km), np.complex128)
+        self.je_arr = np.zeros(grid.N + (Ke,), np.complex128)      # create_field_array (model.jl:55-56)
+        self.jm_arr = np.zeros(grid.N + (Km,), np.complex128)
         self.order_cmpfirst = True                        # model.jl:72
         self.pml = PMLParam()
 
     def size(self, ft):
-        return ((3,) + self.grid.N) if self.order_cmpfirst else (self.grid.N + (3,))   # model.jl:75-81
+        Kf = len(self.cmp_e) if ft == EE else len(self.cmp_m)
+        return ((Kf,) + self.grid.N) if self.order_cmpfirst else (self.grid.N + (Kf,))   # model.jl:75-81
 
     def length(self, ft):
         return int(np.prod(self.size(ft)))
@@ -50,6 +60,27 @@ def ModelFull(grid):
     if len(grid) != 3:
         raise ValueError("ModelFull needs a 3-D grid")
     return Model(grid)
+
+
+def ModelTE(grid):
+    """2-D TE (te.jl:4-14): shapes in the x-y plane, E = (Ex, Ey), H = (Hz)."""
+    if len(grid) != 2:
+        raise ValueError("ModelTE needs a 2-D grid")
+    return Model(grid, cmp_s=(0, 1), cmp_e=(0, 1), cmp_m=(2,))
+
+
+def ModelTM(grid):
+    """2-D TM (tm.jl:4-14): shapes in the x-y plane, E = (Ez), H = (Hx, Hy)."""
+    if len(grid) != 2:
+        raise ValueError("ModelTM needs a 2-D grid")
+    return Model(grid, cmp_s=(0, 1), cmp_e=(2,), cmp_m=(0, 1))
+
+
+def ModelTEM(grid):
+    """1-D TEM (tem.jl:4-13): shapes along z, E = (Ex), H = (Hy)."""
+    if len(grid) != 1:
+        raise ValueError("ModelTEM needs a 1-D grid")
+    return Model(grid, cmp_s=(2,), cmp_e=(0,), cmp_m=(1,))
 
 
 def set_wpml(mdl, wpml):
@@ -95,16 +126,23 @@ def add_srcm(mdl, src):
 
 
 def field_arr2vec(F, order_cmpfirst=True):
+    """(N..., Kf) array -> DOF vector in the reference's order (model.jl:75-83; first grid axis fastest)."""
     F = np.asarray(F)
-    axes = (2, 1, 0, 3) if order_cmpfirst else (3, 2, 1, 0)
+    K = F.ndim - 1
+    rev = tuple(range(K - 1, -1, -1))
+    axes = rev + (K,) if order_cmpfirst else (K,) + rev
     return np.ascontiguousarray(F.transpose(axes)).reshape(-1)
 
 
 def field_vec2arr(v, N, order_cmpfirst=True):
-    Nx, Ny, Nz = N
+    N = tuple(int(n) for n in N)
+    K = len(N)
+    v = np.asarray(v)
+    Kf = v.size // int(np.prod(N))
+    rev = tuple(range(K - 1, -1, -1))
     if order_cmpfirst:
-        return np.asarray(v).reshape(Nz, Ny, Nx, 3).transpose(2, 1, 0, 3)
-    return np.asarray(v).reshape(3, Nz, Ny, Nx).transpose(3, 2, 1, 0)
+        return v.reshape(N[::-1] + (Kf,)).transpose(rev + (K,))
+    return v.reshape((Kf,) + N[::-1]).transpose(tuple(range(K, 0, -1)) + (0,))
 
 
 def create_srcs(mdl):
@@ -154,11 +192,13 @@ class _Geom:
         self.sdl_e, self.sdl_m, _, _ = create_stretched_dls(mdl)
         self.e_mikL = create_e_mikL(mdl)
         self.boundft, self.order_cmpfirst = tuple(mdl.boundft), mdl.order_cmpfirst
+        self.cmp_s, self.cmp_e, self.cmp_m = mdl.cmp_s, mdl.cmp_e, mdl.cmp_m
         self.ops = {}            # operators built from this description, keyed by (ft, w, options)
 
     def same(self, o):
         return (self.N == o.N and self.isbloch == o.isbloch and self.boundft == o.boundft
                 and self.order_cmpfirst == o.order_cmpfirst and np.array_equal(self.e_mikL, o.e_mikL)
+                and (self.cmp_s, self.cmp_e, self.cmp_m) == (o.cmp_s, o.cmp_e, o.cmp_m)
                 and all(np.array_equal(a, b) for a, b in zip(self.sdl_e + self.sdl_m, o.sdl_e + o.sdl_m)))
 
 
@@ -170,6 +210,8 @@ def create_paramops(mdl, device=-1, device_materials=False):
     host array is ever built."""
     objs = getattr(mdl, "oind2shp", None)
     g = _Geom(mdl)
+    if objs and len(mdl.grid) < 3:
+        raise NotImplementedError("objects on 2-D / 1-D models: fill mdl.eps_arr / mdl.mu_arr directly (reduced.py)")
     if objs and device_materials:
         if not (len(mdl.muind2mu) == 1 and np.array_equal(mdl.muind2mu[0], np.eye(3))):
             raise ValueError("device_materials needs mu = 1 for every object")
@@ -205,6 +247,20 @@ def _build(ft, w, Ps, Cs, device=-1, rank=0, nranks=1, kernel=0, weighted_out_av
     A = g.ops.get(key)
     if A is not None and not A.closed:
         return A
+    if len(g.N) < 3:
+        # ModelTE / ModelTM / ModelTEM: the 3-D handle that is one periodic cell thick along the missing axes
+        from .reduced import ReducedOperator, embed_geometry, embed_param
+        if nranks != 1:
+            raise ValueError("z-slabs need a 3-D model")
+        N3, bl3, se3, sm3, ph3, bft3 = embed_geometry(g)
+        eps3 = embed_param(Pe.arr, N3, g.cmp_e)
+        if eps3 is None:
+            eps3 = np.broadcast_to(np.eye(3, dtype=np.complex128), N3 + (3, 3)).copy()
+        A3 = FdfdOperator(N3, bl3, se3, sm3, w, eps3, embed_param(Pm.arr, N3, g.cmp_m), ph3, boundft=bft3, ft=ft,
+                          order_cmpfirst=True, device=device, kernel=kernel, weighted_out_avg=weighted_out_avg)
+        A = ReducedOperator(A3, int(np.prod(g.N)), g.cmp_e, g.cmp_m, ft, g.order_cmpfirst)
+        g.ops[key] = A
+        return A
     from .operator import partition
     k0, k1 = partition(g.N[2], nranks, rank)
     mu = _mu_or_none(Pm.arr)
@@ -239,7 +295,7 @@ def create_A(ft, w, Ps, Cs=None, **kw):
 def create_b(ft, w, Ps, Cs=None, js=None, **kw):
     """create_b(ft, ω, Ps, Cs, js) (model.jl:248-274), evaluated on the GPU (fdfd_create_b): EE: b = -Cm(Pmu\\jm) - iω je,
     HH: b = Ce(Peps\\je) - iω jm.  Also accepts create_b(ft, ω, A, js) with an operator built by create_A."""
-    if isinstance(Ps, FdfdOperator):
+    if isinstance(Ps, _OPS):
         A, js = Ps, (Cs if js is None else js)
     else:
         Ps, Cs = _as_ops(Ps, Cs)
@@ -265,7 +321,7 @@ def create_linsys(ft, w, Ps, Cs=None, js=None, **kw):
 
 
 def _post_operator(w, third, fourth, **kw):
-    if isinstance(third, FdfdOperator):
+    if isinstance(third, _OPS):
         return third
     Ps, Cs = _as_ops(third, fourth)
     g = Cs[0].geom
@@ -277,7 +333,7 @@ def _post_operator(w, third, fourth, **kw):
 
 def h_from_e(e, w, Ps, Cs=None, js=None, **kw):
     """h_from_e(e, ω, Ps, Cs, js) (model.jl:276-279) = (i/ω) Pmu \\ (Ce e + jm); also h_from_e(e, ω, A, jm)."""
-    if isinstance(Ps, FdfdOperator):
+    if isinstance(Ps, _OPS):
         jm = Cs if js is None else js
     else:
         jm = None if js is None else js[1]
@@ -287,7 +343,7 @@ def h_from_e(e, w, Ps, Cs=None, js=None, **kw):
 
 def e_from_h(h, w, Ps, Cs=None, js=None, **kw):
     """e_from_h(h, ω, Ps, Cs, js) (model.jl:281-284) = (-i/ω) Peps \\ (Cm h - je); also e_from_h(h, ω, A, je)."""
-    if isinstance(Ps, FdfdOperator):
+    if isinstance(Ps, _OPS):
         je = Cs if js is None else js
     else:
         je = None if js is None else js[0]
@@ -298,7 +354,7 @@ def e_from_h(h, w, Ps, Cs=None, js=None, **kw):
 def create_Mcs(mdl_or_A, **kw):
     """create_Mcs(mdl) (model.jl:287-306): two callables (Mc_e, Mc_m) interpolating E / H to the voxel corners
     (the reference returns two sparse matrices; apply these like `Mc_e(e)`).  Also accepts an operator."""
-    A = mdl_or_A if isinstance(mdl_or_A, FdfdOperator) else _build(EE, 0.0, *(_as_ops(mdl_or_A, None)), **kw)
+    A = mdl_or_A if isinstance(mdl_or_A, _OPS) else _build(EE, 0.0, *(_as_ops(mdl_or_A, None)), **kw)
     return (lambda e: A.interp_corners(e, "E")), (lambda h: A.interp_corners(h, "H"))
 
 

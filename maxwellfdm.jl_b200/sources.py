@@ -67,11 +67,19 @@ class Source:
     pass
 
 
+def isfield_ortho_shape(Kf, K):
+    """MaxwellBase's default for `isfield˔shp` (pointsrc.jl:56,61; planesrc.jl:20,25; not in the reference tree): true
+    when the field components span the orthogonal complement of the shape axes (TM: E_z over x-y; TE: H_z), false
+    when they are the same space (3-D, TE's E, TM's H).  Override per source where this default does not fit."""
+    return Kf + K == 3
+
+
 class PointSrc(Source):
     """PointSrc(c, p, I∆r=1) - pointsrc.jl:51-62."""
 
-    def __init__(self, c, p, Idr=1.0, isfield_ortho_shp=False):
-        self.c, self.p, self.Idr, self.isfield_ortho_shp = np.asarray(c, float), _unit(p), complex(Idr), isfield_ortho_shp
+    def __init__(self, c, p, Idr=1.0, isfield_ortho_shp=None):
+        self.c, self.p, self.Idr = np.atleast_1d(np.asarray(c, float)), _unit(np.atleast_1d(p)), complex(Idr)
+        self.isfield_ortho_shp = isfield_ortho_shape(self.p.size, self.c.size) if isfield_ortho_shp is None else bool(isfield_ortho_shp)
 
     def add(self, jarr, gt0, bounds, l, dl, isbloch):
         K = self.c.size
@@ -88,11 +96,12 @@ class PointSrc(Source):
 class PlaneSrc(Source):
     """PlaneSrc(n, c, p, J∆n=1) - planesrc.jl:14-32."""
 
-    def __init__(self, n, c, p, Jdn=1.0, isfield_ortho_shp=False):
-        n = np.asarray(n, float)
+    def __init__(self, n, c, p, Jdn=1.0, isfield_ortho_shp=None):
+        n = np.atleast_1d(np.asarray(n, float))
         if np.count_nonzero(n) != 1:
             raise ValueError(f"n = {n} must be along Cartesian direction.")
-        self.n, self.c, self.p, self.Jdn, self.isfield_ortho_shp = _unit(n), float(c), _unit(p), complex(Jdn), isfield_ortho_shp
+        self.n, self.c, self.p, self.Jdn = _unit(n), float(c), _unit(np.atleast_1d(p)), complex(Jdn)
+        self.isfield_ortho_shp = isfield_ortho_shape(self.p.size, self.n.size) if isfield_ortho_shp is None else bool(isfield_ortho_shp)
 
     def add(self, jarr, gt0, bounds, l, dl, isbloch):
         nn = int(np.argmax(self.n == 1))

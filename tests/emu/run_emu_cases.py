@@ -248,7 +248,19 @@ def g_matparams():
     return n
 
 
-GROUPS = {"matparams": g_matparams, "apply": g_apply, "boundft": g_boundft, "layouts": g_layouts, "deep": g_deep, "solve": g_solve, "aux": g_aux}
+def g_reduced():
+    """ModelTE / ModelTM / ModelTEM (maxwellfdm.jl_b200/reduced.py: 3-D handle one periodic cell thick) against the
+    K-dimensional oracle"""
+    from problems import REDUCED_CASES, reduced_model_check
+    n = 0
+    for case in REDUCED_CASES:
+        errs = reduced_model_check(fb, *case)
+        assert max(errs[k] for k in ("apply", "transpose", "b", "post")) < 1e-12 and errs["solve"] < 1e-7, (case, errs)
+        n += len(errs)
+    return n
+
+
+GROUPS = {"reduced": g_reduced, "matparams": g_matparams, "apply": g_apply, "boundft": g_boundft, "layouts": g_layouts, "deep": g_deep, "solve": g_solve, "aux": g_aux}
 
 
 def main():

@@ -114,3 +114,69 @@ MATPARAMS_CASES = [  # (N, isbloch, boundft, ft, uniform grid, number of shapes,
     ((13, 9, 11), (True, True, True), (EE, EE, EE), HH, False, 6, True),
     ((9, 17, 6), (False, False, False), (HH, HH, HH), EE, False, 9, False),
 ]
+
+
+# ---- 2-D / 1-D models (ModelTE, ModelTM, ModelTEM) -----------------------------------------------------------------
+REDUCED_CASES = [   # kind, N, isbloch, boundft, ft, order_cmpfirst
+    ("TE", (9, 7), (True, False), (EE, EE), EE, True),
+    ("TE", (12, 5), (False, True), (HH, EE), EE, False),
+    ("TE", (8, 8), (True, True), (EE, HH), HH, True),
+    ("TE", (70, 33), (False, False), (EE, EE), EE, True),
+    ("TM", (9, 7), (True, False), (EE, EE), EE, True),
+    ("TM", (6, 11), (False, False), (HH, HH), HH, False),
+    ("TM", (35, 10), (True, True), (EE, HH), HH, True),
+    ("TEM", (17,), (False,), (EE,), EE, True),
+    ("TEM", (9,), (True,), (HH,), HH, True),
+]
+
+
+def reduced_model_check(fb, kind, N, isbloch, boundft, ft, cmpfirst, device=0, seed=5):
+    """Reference call sequence on a ModelTE / ModelTM / ModelTEM (random non-uniform grid, PML on the non-periodic
+    axes, Bloch phases, full 2x2 tensors where the formulation allows them, point source + random currents) against
+    the K-dimensional oracle (oracle/reduced.py).  Returns the relative errors of A x, A^T x, b, the post-processed
+    field and the solved field."""
+    import scipy.sparse.linalg as spla
+    from oracle import reduced as ored
+    rng = np.random.default_rng(seed)
+    kd = getattr(ored, kind)
+    lprim = [np.concatenate(([0.0], np.cumsum(0.5 + rng.random(n)))) for n in N]
+    mdl = {"TE": fb.ModelTE, "TM": fb.ModelTM, "TEM": fb.ModelTEM}[kind](fb.Grid(lprim, isbloch))
+    fb.set_boundft(mdl, boundft)
+    fb.set_wpml(mdl, 1.3)
+    fb.set_Npml(mdl, ([1 if not b and n > 4 else 0 for b, n in zip(isbloch, N)],) * 2)
+    fb.set_kbloch(mdl, [0.3 * b for b in isbloch])
+    mdl.order_cmpfirst = cmpfirst
+
+    def rand_param(Kf, diag):
+        P = np.zeros(tuple(N) + (Kf, Kf), complex)
+        for i in range(Kf):
+            P[..., i, i] = 1.5 + rng.random(N) + 0.1j * rng.random(N)
+        if not diag:
+            for i, j in itertools.permutations(range(Kf), 2):
+                P[..., i, j] = 0.2 * (rng.random(N) - 0.5) + 0.05j * rng.random(N)
+        return P
+
+    mdl.eps_arr[...] = rand_param(len(kd["cmp_e"]), diag=ft == HH)     # the divided tensor must be diagonal (model.jl:236,239)
+    mdl.mu_arr[...] = rand_param(len(kd["cmp_m"]), diag=ft == EE)
+    mdl.je_arr[...] = crandn(rng, *mdl.je_arr.shape)
+    mdl.jm_arr[...] = crandn(rng, *mdl.jm_arr.shape)
+    centre = [0.5 * (a[0] + a[-1]) + 0.1 for a in lprim]
+    fb.add_srce(mdl, fb.PointSrc(centre, [1.0] * len(kd["cmp_e"])))
+    w = 1.1 - 0.2j
+    Ps, Cs, js = fb.create_paramops(mdl), fb.create_curls(mdl), fb.create_srcs(mdl)
+    A, b = fb.create_linsys(ft, w, Ps, Cs, js, device=device)
+    sdl_e, sdl_m, _, _ = fb.create_stretched_dls(mdl)
+    S = ored.ReducedSystem(kd, mdl.eps_arr, mdl.mu_arr, sdl_e, sdl_m, boundft, isbloch, fb.create_e_mikL(mdl), cmpfirst)
+    Ar = S.A(ft, w)
+    assert A.n == Ar.shape[0] == mdl.length(ft)
+    x = crandn(rng, A.n)
+    errs = {"apply": rel(A @ x, Ar @ x), "transpose": rel(A.rmatvec_T(x), Ar.T @ x), "b": rel(b, S.b(ft, w, *js))}
+    if ft == EE:
+        errs["post"] = rel(fb.h_from_e(x, w, Ps, Cs, js), S.h_from_e(x, w, js[1]))
+    else:
+        errs["post"] = rel(fb.e_from_h(x, w, Ps, Cs, js), S.e_from_h(x, w, js[0]))
+    xs, info = fb.solve(A, b, rtol=1e-11, maxit=5000)
+    assert info["converged"], info
+    errs["solve"] = rel(xs, spla.splu(Ar).solve(b))
+    A.close()
+    return errs

@@ -46,6 +46,13 @@ def test_emulated_material_pipeline_matches_oracle(emu_lib):
     assert "checks ok" in out, out
 
 
+def test_emulated_reduced_models_match_k_dimensional_oracle(emu_lib):
+    """ModelTE / ModelTM / ModelTEM through the reference call sequence (operator, transpose, right-hand side,
+    post-processing, solve) against oracle/reduced.py"""
+    out = _run(emu_lib, ["reduced"], "lazy", 2)
+    assert "checks ok" in out, out
+
+
 def test_emulated_multi_chunk_grids_and_offdiag_paths(emu_lib):
     out = _run(emu_lib, ["deep"], "lazy", 3)
     assert "checks ok" in out, out

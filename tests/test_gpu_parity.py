@@ -408,6 +408,22 @@ def test_bicgstab_trajectory_matches_textbook_iteration(ft, full, classic):
     A.close()
 
 
+def _reduced_cases():
+    from problems import REDUCED_CASES
+    return REDUCED_CASES
+
+
+@pytest.mark.parametrize("case", _reduced_cases(), ids=lambda c: f"{c[0]}-{'x'.join(map(str, c[1]))}-ft{c[4]}")
+def test_reduced_models_match_k_dimensional_oracle(case):
+    """ModelTE / ModelTM / ModelTEM (te.jl, tm.jl, tem.jl) run on the 3-D kernels (one periodic cell along the missing
+    axes); the reference call sequence against the operators assembled on the K-dimensional grid (oracle/reduced.py):
+    A x, A^T x, b, h_from_e / e_from_h within 1e-12, solved field within 1e-8 * cond. slack"""
+    from problems import reduced_model_check
+    errs = reduced_model_check(_fb(), *case)
+    assert max(errs[k] for k in ("apply", "transpose", "b", "post")) < TOL, errs
+    assert errs["solve"] < 1e-8 * 50, errs
+
+
 def test_solve_edge_cases():
     fb = _fb()
     p = Problem((8, 7, 6), (True, True, True))

@@ -147,3 +147,51 @@ def test_reference_call_sequence_descriptors():
     fb.set_kbloch(mdl, (0.1, 0.0, 0.2))
     with pytest.raises(ValueError):
         fb.create_A(fb.EE, 1.3, Ps, fb.create_curls(mdl), device=-2)
+
+
+def test_reduced_models_layout_and_sources():
+    """ModelTE / ModelTM / ModelTEM (te.jl:4-14, tm.jl:4-14, tem.jl:4-13): array shapes, DOF order with Kf components
+    (model.jl:75-83), sources on K-dimensional grids (isfield˔shp default: orthogonal complement -> true) against the
+    oracle's K-generic add_src."""
+    rng = np.random.default_rng(3)
+    g2, o2 = _rand_grid(rng, (7, 5), (True, False))
+    te, tm = fb.ModelTE(g2), fb.ModelTM(g2)
+    assert te.eps_arr.shape == (7, 5, 2, 2) and te.mu_arr.shape == (7, 5, 1, 1) and te.je_arr.shape == (7, 5, 2)
+    assert tm.eps_arr.shape == (7, 5, 1, 1) and tm.mu_arr.shape == (7, 5, 2, 2) and tm.jm_arr.shape == (7, 5, 2)
+    assert te.size(fb.EE) == (2, 7, 5) and te.size(fb.HH) == (1, 7, 5) and tm.length(fb.HH) == 70
+    g1, _ = _rand_grid(rng, (9,), (False,))
+    tem = fb.ModelTEM(g1)
+    assert tem.eps_arr.shape == (9, 1, 1) and tem.cmp_s == (2,) and tem.cmp_e == (0,) and tem.cmp_m == (1,)
+    for bad in (lambda: fb.ModelTE(g1), lambda: fb.ModelTEM(g2), lambda: fb.ModelFull(g2)):
+        with pytest.raises(ValueError):
+            bad()
+    # DOF order: r = c + Kf (i + Nx j) (cmp-first) / i + Nx (j + Ny c)
+    F = rng.standard_normal((7, 5, 2))
+    v = fb.field_arr2vec(F)
+    assert v[1 + 2 * (3 + 7 * 4)] == F[3, 4, 1] and np.array_equal(fb.field_vec2arr(v, (7, 5)), F)
+    v = fb.field_arr2vec(F, order_cmpfirst=False)
+    assert v[3 + 7 * (4 + 5 * 1)] == F[3, 4, 1] and np.array_equal(fb.field_vec2arr(v, (7, 5), False), F)
+    # sources
+    c = [rng.uniform(g2.bounds[0][w], g2.bounds[1][w]) for w in range(2)]
+    assert not fb.PointSrc(c, [1, 1]).isfield_ortho_shp and fb.PointSrc(c, [1]).isfield_ortho_shp
+    assert not fb.PointSrc([0, 0, 0], [0, 0, 1]).isfield_ortho_shp and fb.PlaneSrc([1, 0], 0.0, [1]).isfield_ortho_shp
+    bft = (fb.EE, fb.HH)
+    for mdl, Ke, Km in ((te, 2, 1), (tm, 1, 2)):
+        fb.set_boundft(mdl, bft)
+        pe, pm = [1.0, -2.0][:Ke], [0.5, 1.0][:Km]
+        fb.add_srce(mdl, fb.PointSrc(c, pe, 0.3 + 0.1j))
+        fb.add_srce(mdl, fb.PlaneSrc([0, 1], c[1], pe, 2.0))
+        fb.add_srcm(mdl, fb.PointSrc(c, pm))
+        je, jm = osrc.create_field_array(o2.N, Ke), osrc.create_field_array(o2.N, Km)
+        osrc.add_src(je, og.EE, bft, o2, osrc.PointSrc(c, pe, 0.3 + 0.1j, isfield_ortho_shp=Ke == 1))
+        osrc.add_src(je, og.EE, bft, o2, osrc.PlaneSrc([0, 1], c[1], pe, 2.0, isfield_ortho_shp=Ke == 1))
+        osrc.add_src(jm, og.HH, bft, o2, osrc.PointSrc(c, pm, isfield_ortho_shp=Km == 1))
+        assert je.any() and jm.any()
+        assert np.allclose(mdl.je_arr, je, rtol=1e-14, atol=0) and np.allclose(mdl.jm_arr, jm, rtol=1e-14, atol=0)
+        vje, vjm = fb.create_srcs(mdl)
+        assert vje.shape == (mdl.length(fb.EE),) and vjm.shape == (mdl.length(fb.HH),)
+    # descriptors: objects on reduced models are refused loudly, z-slabs too
+    Ps, Cs = fb.create_paramops(te), fb.create_curls(te)
+    assert Ps[0].arr is te.eps_arr and Cs[0].geom.cmp_m == (2,)
+    with pytest.raises(ValueError):
+        fb.create_A(fb.EE, 1.0, Ps, Cs, nranks=2, rank=0)
