@@ -210,8 +210,8 @@ def create_paramops(mdl, device=-1, device_materials=False):
     host array is ever built."""
     objs = getattr(mdl, "oind2shp", None)
     g = _Geom(mdl)
-    if objs and len(mdl.grid) < 3:
-        raise NotImplementedError("objects on 2-D / 1-D models: fill mdl.eps_arr / mdl.mu_arr directly (reduced.py)")
+    if objs and device_materials and len(mdl.grid) < 3:
+        raise ValueError("device_materials needs a 3-D model")
     if objs and device_materials:
         if not (len(mdl.muind2mu) == 1 and np.array_equal(mdl.muind2mu[0], np.eye(3))):
             raise ValueError("device_materials needs mu = 1 for every object")

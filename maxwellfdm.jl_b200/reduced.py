@@ -9,7 +9,8 @@ blocks, and the block of the model's components IS the reference's K-dimensional
 runs on the same kernels (libfdfd_b200, 3-D handle with N = 1 along the missing axes); this module only embeds the
 K-dimensional vectors into the 3-component layout and extracts the result.  Krylov iterates started in one block stay
 in it exactly (the other block's entries are exact zeros), so `solve` is the K-dimensional solve.
-Not covered: objects / calc_matparams for K < 3 (fill mdl.eps_arr / mdl.mu_arr directly), z-slabs, pattern export.
+Objects: shapes.calc_matparams extrudes the K-dimensional shapes the same way (material kernel on the 3-D scene).
+Not covered: z-slabs and the CSC pattern export of a reduced model.
 """
 import numpy as np
 

@@ -28,10 +28,10 @@ class Box(Shape):
     kind = L.SHAPE_BOX
 
     def __init__(self, c, r):
-        self.c = tuple(float(v) for v in c)
-        self.r = tuple(float(v) for v in r)
-        if len(self.c) != 3 or len(self.r) != 3 or min(self.r) < 0:
-            raise ValueError("Box(c, r): three centre coordinates and three non-negative half-widths")
+        self.c = tuple(float(v) for v in np.atleast_1d(c))
+        self.r = tuple(float(v) for v in np.atleast_1d(r))
+        if not 1 <= len(self.c) <= 3 or len(self.r) != len(self.c) or min(self.r) < 0:
+            raise ValueError("Box(c, r): K centre coordinates and K non-negative half-widths (K = 3; 2 / 1 on 2-D / 1-D models)")
         self.axis = 0
 
 
@@ -40,8 +40,8 @@ class Ball(Shape):
     kind = L.SHAPE_BALL
 
     def __init__(self, c, radius):
-        self.c = tuple(float(v) for v in c)
-        if len(self.c) != 3 or radius < 0:
+        self.c = tuple(float(v) for v in np.atleast_1d(c))
+        if not 1 <= len(self.c) <= 3 or radius < 0:
             raise ValueError("Ball(c, radius)")
         self.r = (float(radius), 0.0, 0.0)
         self.axis = 0
@@ -60,6 +60,27 @@ class Cylinder(Shape):
             raise ValueError("Cylinder(c, radius, h, axis)")
         self.r = (float(radius), float(h), 0.0)
         self.axis = int(axis)
+
+
+def extrude(shp, cmp_s, big):
+    """The 3-D shape a K-dimensional shape of a 2-D / 1-D model stands for: invariant along the missing axes (half-width
+    `big` there, centred on the unit cell [0, 1] of the embedding grid, reduced.py).  A disc becomes a cylinder along
+    the missing axis, an interval a slab."""
+    K = len(cmp_s)
+    if len(shp.c) != K:
+        raise ValueError(f"a {K}-D model takes {K}-D shapes")
+    if isinstance(shp, Cylinder):
+        raise ValueError("Cylinder is a 3-D shape")
+    c = [0.5, 0.5, 0.5]
+    for k, a in enumerate(cmp_s):
+        c[a] = shp.c[k]
+    if isinstance(shp, Ball) and K == 2:
+        axis = ({0, 1, 2} - set(cmp_s)).pop()
+        return Cylinder(c, shp.r[0], big, axis)
+    r = [big, big, big]
+    for k, a in enumerate(cmp_s):
+        r[a] = shp.r[k] if isinstance(shp, Box) else shp.r[0]
+    return Box(c, r)
 
 
 def _as_tensor(p):
@@ -137,10 +158,51 @@ def calc_matparams_array(grid, boundft, ft, shapes, pinds, params, k0=0, k1=None
     return out if julia_layout else np.ascontiguousarray(out.transpose(4, 3, 2, 1, 0))
 
 
+def _calc_matparams_reduced(mdl, device):
+    """calc_matparams!(mdl::ModelTE / ModelTM / ModelTEM) (te.jl:17-64, tm.jl:17-64, tem.jl:16-59) on the 3-D kernel:
+    the K-dimensional shapes are extruded along the missing axes, the grid is one periodic unit cell thick there, each
+    material tensor is reduced to the block of the field's components first (sub_pind2matprm, te.jl:43-44) and
+    embedded with 1 on the rest of the diagonal, and the fields that are orthogonal to the shape dimensions (E_z of
+    TM, H_z of TE, both fields of TEM) are averaged arithmetically (ise˔shp / ish˔shp, model.jl:65-69).  The block of
+    the result is the K-dimensional array: an interface that is invariant along an axis has its normal in the shape
+    dimensions, so the 3-D smoothing of the embedded tensor does not mix the block with the rest."""
+    from .grid import Grid
+    g, cs = mdl.grid, mdl.cmp_s
+    K = len(cs)
+    big = 1e6 * max(1.0, max(g.L))
+    lprim = [np.array([0.0, 1.0])] * 3
+    isbloch, boundft = [True] * 3, [EE] * 3
+    for k, a in enumerate(cs):
+        lprim[a], isbloch[a], boundft[a] = g.lg_prim[k], g.isbloch[k], mdl.boundft[k]
+    g3 = Grid(lprim, isbloch)
+    shapes3 = [extrude(s, cs, big) for s in mdl.oind2shp]
+    for arr, ft, cmps, pinds, table in ((mdl.eps_arr, EE, mdl.cmp_e, mdl.oind2epsind, mdl.epsind2eps),
+                                        (mdl.mu_arr, HH, mdl.cmp_m, mdl.oind2muind, mdl.muind2mu)):
+        Kf = len(cmps)
+        params3 = []
+        for P in table:
+            Q = np.eye(3, dtype=np.complex128)
+            for i, ci in enumerate(cmps):
+                for j, cj in enumerate(cmps):
+                    Q[ci, cj] = P[ci, cj]
+            params3.append(Q)
+        if len(table) == 1:                                   # one material: nothing to rasterise
+            for i, ci in enumerate(cmps):
+                for j, cj in enumerate(cmps):
+                    arr[..., i, j] = params3[0][ci, cj]
+            continue
+        a3 = calc_matparams_array(g3, boundft, ft, shapes3, pinds, params3, device=device, field_ortho_shape=(Kf + K == 3))
+        for i, ci in enumerate(cmps):
+            for j, cj in enumerate(cmps):
+                arr[..., i, j] = a3[..., ci, cj].reshape(g.N)
+
+
 def calc_matparams(mdl, device=-1):
     """calc_matparams!(mdl) (full.jl:16-70): assignment + subpixel smoothing of eps and mu from the added objects."""
     if not getattr(mdl, "oind2shp", None):
         raise ValueError("calc_matparams: no objects (add_obj) in the model")
+    if len(mdl.grid) < 3:
+        return _calc_matparams_reduced(mdl, device)
     mdl.eps_arr[...] = calc_matparams_array(mdl.grid, mdl.boundft, EE, mdl.oind2shp, mdl.oind2epsind, mdl.epsind2eps,
                                             device=device)
     if len(mdl.muind2mu) == 1 and np.array_equal(mdl.muind2mu[0], np.eye(3)):

@@ -251,8 +251,8 @@ def g_matparams():
 def g_reduced():
     """ModelTE / ModelTM / ModelTEM (maxwellfdm.jl_b200/reduced.py: 3-D handle one periodic cell thick) against the
     K-dimensional oracle"""
-    from problems import REDUCED_CASES, reduced_model_check
-    n = 0
+    from problems import REDUCED_CASES, reduced_model_check, reduced_objects_check
+    n = reduced_objects_check(fb)
     for case in REDUCED_CASES:
         errs = reduced_model_check(fb, *case)
         assert max(errs[k] for k in ("apply", "transpose", "b", "post")) < 1e-12 and errs["solve"] < 1e-7, (case, errs)

@@ -180,3 +180,90 @@ def reduced_model_check(fb, kind, N, isbloch, boundft, ft, cmpfirst, device=0, s
     errs["solve"] = rel(xs, spla.splu(Ar).solve(b))
     A.close()
     return errs
+
+
+def reduced_objects_check(fb, device=0):
+    """add_obj / calc_matparams on ModelTE, ModelTM, ModelTEM.  (a) against the (numpy, 3-D) oracle on the scene the
+    K-dimensional one stands for (shapes invariant along the missing axes, one periodic cell there); (b) analytic,
+    independent of any 3-D code: across a planar x-normal interface on a uniform grid the tangential entries are the
+    arithmetic mean and the normal entry the harmonic mean over the voxel's own x-extent.  Returns the number of checks."""
+    from oracle import matparams as omp
+    n = 0
+    lx, ly = np.arange(13.0) - 2.0, np.arange(9.0) - 1.5
+    e1, e2, x0 = 2.0, 9.0, 4.3          # eps = e2 for x < x0, e1 elsewhere
+    for isbloch in ((False, False), (True, True)):
+        res = {}
+        for name, ctor in (("TE", fb.ModelTE), ("TM", fb.ModelTM)):
+            mdl = ctor(fb.Grid([lx, ly], isbloch))
+            fb.add_obj(mdl, "bg", fb.Box([4.0, 2.5], [50.0, 50.0]), eps=e1)
+            fb.add_obj(mdl, "slab", fb.Box([x0 - 20.0, 2.5], [20.0, 50.0]), eps=e2)
+            fb.create_paramops(mdl, device=device)             # runs calc_matparams (model.jl:143)
+            res[name] = mdl
+            assert np.array_equal(mdl.mu_arr[..., 0, 0], np.ones(mdl.grid.N))
+        te, tm = res["TE"], res["TM"]
+        xp = lx[:-1]                                             # primal planes; dual points sit half a cell further
+        f_ex = np.clip((x0 - xp) / 1.0, 0, 1)                    # E_x: x-dual location, voxel [xp_i, xp_i + 1]
+        f_ey = np.clip((x0 - (xp - 0.5)) / 1.0, 0, 1)            # E_y, E_z: x-primal location, voxel [xp_i - 1/2, xp_i + 1/2]
+        # (the voxel around the first primal plane reaches across the boundary: its ghost half follows the pipeline's
+        # boundary rule, which (a) below covers; the analytic statement is made for the voxels inside the domain)
+        assert np.allclose(te.eps_arr[:, :, 0, 0], (1 / (f_ex / e2 + (1 - f_ex) / e1))[:, None], rtol=1e-12, atol=0)   # normal: harmonic
+        assert np.allclose(te.eps_arr[1:, :, 1, 1], (f_ey * e2 + (1 - f_ey) * e1)[1:, None], rtol=1e-12, atol=0)        # tangential
+        assert np.allclose(tm.eps_arr[:, :, 0, 0], te.eps_arr[:, :, 1, 1], rtol=1e-12, atol=0)     # E_z: tangential, same extent
+        assert not te.eps_arr[:, :, 0, 1].any() and not te.eps_arr[:, :, 1, 0].any()
+        n += 4
+    # (a) disc + rotated-tensor rectangle on a non-uniform grid, every boundft, against the 3-D oracle
+    rng = np.random.default_rng(9)
+    lp = [np.concatenate(([0.0], np.cumsum(0.6 + 0.8 * rng.random(m)))) - 2.0 for m in (11, 9)]
+    Q = np.array([[5.0, 0.7, 0.0], [0.7, 3.0, 0.0], [0.0, 0.0, 7.0]])
+    for boundft in ((EE, EE), (HH, EE), (EE, HH)):
+        for name, ctor, cmp_e, cmp_m in (("TE", fb.ModelTE, (0, 1), (2,)), ("TM", fb.ModelTM, (2,), (0, 1))):
+            mdl = ctor(fb.Grid(lp, (True, False)))
+            fb.set_boundft(mdl, boundft)
+            fb.add_obj(mdl, "bg", fb.Box([2.0, 2.0], [40.0, 40.0]), eps=1.0, mu=1.0)
+            fb.add_obj(mdl, "disc", fb.Ball([1.7, 2.2], 2.1), eps=Q, mu=2.0)
+            fb.add_obj(mdl, "bar", fb.Box([4.1, 0.4], [1.3, 0.9]), eps=11.0, mu=[1.0, 3.0, 2.0])
+            fb.calc_matparams(mdl, device=device)
+            g3 = Grid([lp[0], lp[1], np.array([0.0, 1.0])], (True, False, True))
+            big = 1e6 * max(1.0, max(mdl.grid.L))
+            o_sh = [omp.Box([2.0, 2.0, 0.5], [40.0, 40.0, big]), omp.Cylinder([1.7, 2.2, 0.5], 2.1, big, 2),
+                    omp.Box([4.1, 0.4, 0.5], [1.3, 0.9, big])]
+            for arr, ft, cmps, prm in ((mdl.eps_arr, EE, cmp_e, [np.eye(3), Q, 11.0 * np.eye(3)]),
+                                       (mdl.mu_arr, HH, cmp_m, [np.eye(3), 2.0 * np.eye(3), np.diag([1.0, 3.0, 2.0])])):
+                prm3 = []
+                for P in prm:
+                    R = np.eye(3, dtype=complex)
+                    R[np.ix_(cmps, cmps)] = np.asarray(P)[np.ix_(cmps, cmps)]
+                    prm3.append(R)
+                ref = omp.calc_matparams(g3, boundft + (EE,), ft, o_sh, [0, 1, 2], prm3, field_ortho_shape=len(cmps) == 1)
+                ref = ref[:, :, 0][..., list(cmps), :][..., list(cmps)]
+                assert rel(arr, ref) < 1e-10, (name, boundft, ft, rel(arr, ref))
+                n += 1
+    # 1-D: interval of eps 4 in vacuum, arithmetic averages (E_x, H_y orthogonal to z)
+    lz = np.arange(11.0)
+    tem = fb.ModelTEM(fb.Grid([lz], (False,)))
+    fb.add_obj(tem, "bg", fb.Box([5.0], [50.0]), eps=1.0)
+    fb.add_obj(tem, "film", fb.Box([5.15], [2.0]), eps=4.0)       # [3.15, 7.15]
+    fb.calc_matparams(tem, device=device)
+    zc = lz[:-1]                                                   # E_x on primal z: voxel [z - 1/2, z + 1/2]
+    f = np.clip(np.minimum(zc + 0.5, 7.15) - np.maximum(zc - 0.5, 3.15), 0, 1)
+    assert np.allclose(tem.eps_arr[:, 0, 0], 1.0 + 3.0 * f, rtol=1e-12, atol=0)
+    n += 1
+    with pytest_raises(ValueError):
+        fb.add_obj(tem, "bad", fb.Box([1.0, 2.0], [1.0, 1.0]), eps=2.0)
+        fb.calc_matparams(tem, device=device)
+    return n + 1
+
+
+class pytest_raises:
+    """minimal stand-in for pytest.raises (this module is also imported by the stand-alone runners of tests/emu)"""
+
+    def __init__(self, exc):
+        self.exc = exc
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, et, ev, tb):
+        if et is None:
+            raise AssertionError(f"{self.exc.__name__} not raised")
+        return issubclass(et, self.exc)

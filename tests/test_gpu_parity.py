@@ -424,6 +424,14 @@ def test_reduced_models_match_k_dimensional_oracle(case):
     assert errs["solve"] < 1e-8 * 50, errs
 
 
+def test_objects_on_reduced_models():
+    """add_obj / calc_matparams on ModelTE, ModelTM, ModelTEM (te.jl:17-64, tm.jl:17-64, tem.jl:16-59): the material
+    kernel on the extruded scene; analytic harmonic / arithmetic means across a planar interface, and the oracle's
+    smoothing of the scene the K-dimensional one stands for (1e-10, as for the 3-D pipeline)"""
+    from problems import reduced_objects_check
+    assert reduced_objects_check(_fb()) == 22
+
+
 def test_solve_edge_cases():
     fb = _fb()
     p = Problem((8, 7, 6), (True, True, True))
