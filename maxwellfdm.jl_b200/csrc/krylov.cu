@@ -67,10 +67,18 @@ __device__ __forceinline__ double2 load_sigma(const Red &rd, int sig3) {
     return make_double2(a.x + b.x + c.x, a.y + b.y + c.y);
 }
 
+// Convergence far below any tolerance between two residual checks (tiny systems converge exactly within a few
+// iterations; b in an invariant subspace) would drive rho, sigma, (t,t) to 0 / underflow and fill x with NaN before the
+// host looks.  Once ||r|| <= 1e-30 ||b|| the iteration therefore idles: alpha = omega = beta = 0, x and r stay.  A
+// genuine breakdown (sigma or rho = 0 with a residual above that) still shows as NaN / ENOCONV.
+__device__ __forceinline__ bool idle(const Red &rd, int rr_slot) {
+    return rd.scal[rr_slot].x <= 1e-60 * rd.scal[S_BNORM].x;
+}
+
 // alpha = rho/sigma ; s = r - alpha v
 __global__ void __launch_bounds__(RB) k_s(int64_t n, const double2 *__restrict__ r, const double2 *__restrict__ v,
                                           double2 *__restrict__ s, Red rd, int rho_slot, int sig3) {
-    const double2 alpha = c_div(rd.scal[rho_slot], load_sigma(rd, sig3));
+    const double2 alpha = idle(rd, rho_slot + 1) ? c_zero() : c_div(rd.scal[rho_slot], load_sigma(rd, sig3));
     GRID_STRIDE(i, n) s[i] = c_fms(alpha, v[i], r[i]);
     if (blockIdx.x == 0 && threadIdx.x == 0) rd.scal[S_ALPHA] = alpha;
 }
@@ -93,7 +101,8 @@ __global__ void __launch_bounds__(RB) k_xr(int64_t n, double2 *__restrict__ x, c
                                            const double2 *__restrict__ rhat, double2 *__restrict__ r, Red rd,
                                            int rho_new_slot) {
     const double2 alpha = rd.scal[S_ALPHA];
-    const double2 omega = c_div(rd.scal[S_TS], rd.scal[S_TT]);
+    const int rho_old_slot = rho_new_slot == S_RHO0 ? S_RHO1 : S_RHO0;    // RR of the residual this iteration started from
+    const double2 omega = idle(rd, rho_old_slot + 1) ? c_zero() : c_div(rd.scal[S_TS], rd.scal[S_TT]);
     double2 acc[2] = {c_zero(), c_zero()};
     GRID_STRIDE(i, n) {
         const double2 ss = s[i];
@@ -117,7 +126,9 @@ __global__ void __launch_bounds__(RB) k_p(int64_t n, const double2 *__restrict__
                                           double2 *__restrict__ p, const double2 *__restrict__ u, Red rd,
                                           int rho_old_slot, int rho_new_slot, int sig_slot) {
     const double2 omega = rd.scal[S_OMEGA];
-    const double2 beta = c_mul(c_div(rd.scal[rho_new_slot], rd.scal[rho_old_slot]), c_div(rd.scal[S_ALPHA], omega));
+    const double2 beta = idle(rd, rho_new_slot + 1) || idle(rd, rho_old_slot + 1)
+                             ? c_zero()
+                             : c_mul(c_div(rd.scal[rho_new_slot], rd.scal[rho_old_slot]), c_div(rd.scal[S_ALPHA], omega));
     double2 acc[1] = {c_zero()};
     GRID_STRIDE(i, n) {
         const double2 q = c_fms(omega, v[i], p[i]);

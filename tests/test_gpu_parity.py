@@ -442,6 +442,15 @@ def test_solve_edge_cases():
     x, info = A.solve(b, maxit=3, rtol=1e-14)                    # maxit hit: ENOCONV, x still valid
     assert not info["converged"] and info["iters"] == 3 and np.isfinite(x).all()
     A.close()
+    # exact convergence between two residual checks (3 unknowns, check every 10 iterations): the iteration idles on
+    # the solution instead of dividing 0 by 0
+    p1 = Problem((1, 1, 1), (True, True, True), kb_scale=3.0)
+    A = p1.operator(device=0)
+    A_ref = p1.oracle_csc()[0]
+    b = A_ref.matvec(p1.random_x(2))
+    x, info = A.solve(b, rtol=1e-12, maxit=50, check_every=10)
+    assert info["converged"] and np.isfinite(x).all() and rel(A_ref.matvec(x), b) < 1e-12, info
+    A.close()
 
 
 def test_create_b_with_magnetic_current_and_h_from_e_with_mu():
