@@ -29,7 +29,7 @@ def main():
         boundft = tuple(int(b) for b in rng.integers(0, 2, K))
         args = (kind, N, isbloch, boundft, int(rng.integers(0, 2)), bool(rng.integers(0, 2)))
         errs = reduced_model_check(fb, *args, seed=int(rng.integers(1 << 30)))
-        if not (max(errs[k] for k in ("apply", "transpose", "b", "post")) < 1e-12 and errs["solve"] < 1e-6):
+        if not (max(v for k, v in errs.items() if k != "solve") < 1e-12 and errs["solve"] < 1e-6):
             print("FAIL", args, errs, flush=True)
             sys.exit(1)
     print(f"reduced-model fuzz seed {seed}: {ncases} cases ok")

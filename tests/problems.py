@@ -175,6 +175,21 @@ def reduced_model_check(fb, kind, N, isbloch, boundft, ft, cmpfirst, device=0, s
         errs["post"] = rel(fb.h_from_e(x, w, Ps, Cs, js), S.h_from_e(x, w, js[1]))
     else:
         errs["post"] = rel(fb.e_from_h(x, w, Ps, Cs, js), S.e_from_h(x, w, js[0]))
+    # create_Mcs (model.jl:287-306) where it is defined for a reduced model: the field whose components are the grid axes
+    # (E of TE, H of TM) - component w averaged along its own axis w with the weights of model.jl:302-303
+    Mce, Mcm = fb.create_Mcs(A)
+    for cmps, Mc, isfwd, dl, dlo in ((kd["cmp_e"], Mce, [b_ != EE for b_ in boundft], sdl_m, sdl_e),
+                                     (kd["cmp_m"], Mcm, [b_ != HH for b_ in boundft], sdl_e, sdl_m)):
+        if tuple(cmps) != tuple(kd["cmp_s"]):
+            continue
+        ph = fb.create_e_mikL(mdl)
+        f = crandn(rng, len(cmps) * int(np.prod(N)))
+        F = op.field_vec2arr(f, N, len(cmps), cmpfirst) if len(N) == 3 else fb.field_vec2arr(f, N, cmpfirst)
+        G = np.empty_like(F)
+        for k in range(len(cmps)):
+            M1 = op.create_m(k, bool(isfwd[k]), N, dl[k], 1 / np.asarray(dlo[k]), bool(isbloch[k]), ph[k]).to_scipy()
+            G[..., k] = (M1 @ F[..., k].ravel(order="F")).reshape(N, order="F")
+        errs["corners"] = rel(Mc(f), fb.field_arr2vec(G, cmpfirst))
     xs, info = fb.solve(A, b, rtol=1e-11, maxit=5000)
     assert info["converged"], info
     errs["solve"] = rel(xs, spla.splu(Ar).solve(b))

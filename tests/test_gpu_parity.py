@@ -420,7 +420,7 @@ def test_reduced_models_match_k_dimensional_oracle(case):
     A x, A^T x, b, h_from_e / e_from_h within 1e-12, solved field within 1e-8 * cond. slack"""
     from problems import reduced_model_check
     errs = reduced_model_check(_fb(), *case)
-    assert max(errs[k] for k in ("apply", "transpose", "b", "post")) < TOL, errs
+    assert max(v for k, v in errs.items() if k != "solve") < TOL, errs
     assert errs["solve"] < 1e-8 * 50, errs
 
 
