@@ -10,7 +10,7 @@ runs on the same kernels (libfdfd_b200, 3-D handle with N = 1 along the missing 
 K-dimensional vectors into the 3-component layout and extracts the result.  Krylov iterates started in one block stay
 in it exactly (the other block's entries are exact zeros), so `solve` is the K-dimensional solve.
 Objects: shapes.calc_matparams extrudes the K-dimensional shapes the same way (material kernel on the 3-D scene).
-Not covered: z-slabs and the CSC pattern export of a reduced model.
+Not covered: z-slabs.
 """
 import numpy as np
 
@@ -125,6 +125,29 @@ class ReducedOperator:
     def interp_corners(self, f, ft="E"):
         cm = self.cmp_e if (str(ft).upper().startswith("E") or ft == 0) else self.cmp_m
         return self._extract(self.A3.interp_corners(self._embed(f, cm, "f"), ft), cm)
+
+    def export_pattern(self, values=True):
+        """(colptr, rowval, nzval) of the K-dimensional A as Julia stores it (1-based Int64): the block of the 3-D
+        export (fdfd_export_pattern) that belongs to the model's components, renumbered to the K-dimensional DOF
+        order.  The couplings through the missing axes fall on entries the K-dimensional operator stores anyway
+        (they are differences of a cell with itself), so the block has the K-dimensional structure."""
+        colptr3, rowval3, nz3 = self.A3.export_pattern(values)
+        nc, Kf, cm = self.ncell, len(self.cmp_f), list(self.cmp_f)
+        col3 = np.repeat(np.arange(3 * nc, dtype=np.int64), np.diff(colptr3))
+        row3 = rowval3 - 1
+        slot = np.full(3, -1, np.int64)
+        slot[cm] = np.arange(Kf)
+        kr, kc = slot[row3 % 3], slot[col3 % 3]
+        keep = (kr >= 0) & (kc >= 0)
+        cell_r, cell_c, kr, kc = row3[keep] // 3, col3[keep] // 3, kr[keep], kc[keep]
+        if self.order_cmpfirst:
+            r, c = kr + Kf * cell_r, kc + Kf * cell_c
+        else:
+            r, c = kr * nc + cell_r, kc * nc + cell_c
+        order = np.lexsort((r, c))                      # columns ascending, rows ascending inside a column
+        colptr = np.zeros(self.n + 1, np.int64)
+        np.add.at(colptr, c + 1, 1)
+        return np.cumsum(colptr) + 1, r[order] + 1, (nz3[keep][order] if values else None)
 
     # -- life cycle / bookkeeping ---------------------------------------------------------------------
     def close(self):

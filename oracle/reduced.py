@@ -101,3 +101,58 @@ class ReducedSystem:
 
     def e_from_h(self, h, omega, je):
         return (-1j / omega) * ((self.Cm @ h - je) / self.Pe.diagonal())
+
+
+# ---- the same operators with the storage structure Julia would give them (for the index-pattern export) ----------------
+def julia_csc(kind, ft, omega, eps, mu, sdl_e, sdl_m, boundft, isbloch, e_mikL, order_cmpfirst=True):
+    """A of a K-dimensional model as a Csc with Julia's structure: every factor from `sparse(I,J,V)` triplets
+    (duplicates summed, explicit zeros kept), products and the mass term with the structural rules of
+    oracle/operators.py (spgemm, diag_ldiv, sub_scaled) - the composition of model.jl:225-246."""
+    from .operators import (create_d_info, create_m, coo_to_csc, dof_index, spgemm, Csc, create_A as compose)
+    cs, ce, cm = kind["cmp_s"], kind["cmp_e"], kind["cmp_m"]
+    N = tuple(len(a) for a in sdl_e)
+    M = int(np.prod(N))
+    sei, smi = [1 / np.asarray(a) for a in sdl_e], [1 / np.asarray(a) for a in sdl_m]
+
+    def curl(isfwd, dl_inv, cout, cin):
+        Is, Js, Vs = [np.zeros(0, np.int64)], [np.zeros(0, np.int64)], [np.zeros(0, complex)]
+        for iv, v in enumerate(cout):
+            for iu, u in enumerate(cin):
+                w = 3 - u - v
+                if u == v or w not in cs:
+                    continue
+                k = cs.index(w)
+                I, J, V = create_d_info(k, bool(isfwd[k]), N, dl_inv[k], bool(isbloch[k]), e_mikL[k])
+                Is.append(dof_index(I, iv, M, len(cout), order_cmpfirst))
+                Js.append(dof_index(J, iu, M, len(cin), order_cmpfirst))
+                Vs.append(_levi_civita(v, w, u) * V)
+        return coo_to_csc(np.concatenate(Is), np.concatenate(Js), np.concatenate(Vs), (len(cout) * M, len(cin) * M))
+
+    def paramop(param, cmps, isfwd_in, dl, dlo_inv):
+        param = np.asarray(param, np.complex128)
+        Kf = len(cmps)
+        cell = np.arange(M, dtype=np.int64)
+        Is, Js, Vs = [], [], []
+        for i in range(Kf):
+            Is.append(dof_index(cell, i, M, Kf, order_cmpfirst)); Js.append(Is[-1]); Vs.append(param[..., i, i].ravel(order="F"))
+        off = any(param[..., i, j].any() for i in range(Kf) for j in range(Kf) if i != j)
+        if off:
+            for i, v in enumerate(cmps):
+                for j, u in enumerate(cmps):
+                    if i == j:
+                        continue
+                    ku, kv = cs.index(u), cs.index(v)
+                    Min = create_m(ku, bool(isfwd_in[ku]), N, dl[ku], dlo_inv[ku], bool(isbloch[ku]), e_mikL[ku])
+                    Mout = create_m(kv, not bool(isfwd_in[kv]), N, None, None, bool(isbloch[kv]), e_mikL[kv])
+                    pvu = param[..., i, j].ravel(order="F")
+                    blk = spgemm(Mout, Csc(Min.shape, Min.colptr, Min.rowval, Min.nzval * pvu[Min.rowval]))
+                    Is.append(dof_index(blk.rowval, i, M, Kf, order_cmpfirst))
+                    Js.append(dof_index(blk.cols(), j, M, Kf, order_cmpfirst))
+                    Vs.append(blk.nzval)
+        return coo_to_csc(np.concatenate(Is), np.concatenate(Js), np.concatenate(Vs), (Kf * M, Kf * M))
+
+    Ce = curl([b == EE for b in boundft], smi, cm, ce)
+    Cm = curl([b == HH for b in boundft], sei, ce, cm)
+    Pe = paramop(eps, ce, [b != EE for b in boundft], sdl_m, sei)
+    Pm = paramop(mu, cm, [b != HH for b in boundft], sdl_e, smi)
+    return compose(ft, omega, Pe, Pm, Ce, Cm)

@@ -282,3 +282,49 @@ class pytest_raises:
         if et is None:
             raise AssertionError(f"{self.exc.__name__} not raised")
         return issubclass(et, self.exc)
+
+
+REDUCED_PATTERN_CASES = REDUCED_CASES + [("TE", (1, 3), (True, True), (EE, EE), EE, True),
+                                         ("TM", (2, 2), (True, False), (HH, EE), EE, True),
+                                         ("TEM", (1,), (True,), (EE,), EE, True), ("TEM", (2,), (True,), (EE,), HH, False)]
+
+
+def reduced_pattern_check(fb, kind, N, isbloch, boundft, ft, cmpfirst, device=-2, seed=3):
+    """CSC index pattern of a 2-D / 1-D model's A (ReducedOperator.export_pattern: the block of the 3-D debug export)
+    against the Julia-structure K-dimensional oracle (oracle/reduced.julia_csc): colptr / rowval bit-exact, values
+    relative to the largest entry.  Also ties julia_csc to the scipy assembly of the same oracle."""
+    from oracle import reduced as ored
+    rng = np.random.default_rng(seed)
+    kd = getattr(ored, kind)
+    lprim = [np.concatenate(([0.0], np.cumsum(0.5 + rng.random(n)))) for n in N]
+    mdl = {"TE": fb.ModelTE, "TM": fb.ModelTM, "TEM": fb.ModelTEM}[kind](fb.Grid(lprim, isbloch))
+    fb.set_boundft(mdl, boundft)
+    fb.set_wpml(mdl, 1.3)
+    fb.set_Npml(mdl, ([1 if not b and n > 4 else 0 for b, n in zip(isbloch, N)],) * 2)
+    fb.set_kbloch(mdl, [0.3 * b for b in isbloch])
+    mdl.order_cmpfirst = cmpfirst
+
+    def rand_param(Kf, diag):
+        P = np.zeros(tuple(N) + (Kf, Kf), complex)
+        for i in range(Kf):
+            P[..., i, i] = 1.5 + rng.random(N) + 0.1j * rng.random(N)
+        if not diag:
+            for i, j in itertools.permutations(range(Kf), 2):
+                P[..., i, j] = 0.2 * (rng.random(N) - 0.5)
+        return P
+
+    mdl.eps_arr[...] = rand_param(len(kd["cmp_e"]), ft == HH)
+    mdl.mu_arr[...] = rand_param(len(kd["cmp_m"]), ft == EE)
+    w = 1.1 - 0.2j
+    A = fb.create_A(ft, w, mdl, device=device)
+    colptr, rowval, nz = A.export_pattern()
+    A.close()
+    sdl_e, sdl_m, _, _ = fb.create_stretched_dls(mdl)
+    args = (mdl.eps_arr, mdl.mu_arr, sdl_e, sdl_m, boundft, isbloch, fb.create_e_mikL(mdl), cmpfirst)
+    J = ored.julia_csc(kd, ft, w, *args)
+    cp, rv = J.julia_pattern()
+    assert colptr.dtype == np.int64 and rowval.dtype == np.int64
+    assert np.array_equal(colptr, cp) and np.array_equal(rowval, rv), (kind, N, isbloch, boundft, ft, cmpfirst)
+    S = ored.ReducedSystem(kd, *args).A(ft, w)
+    assert abs(J.to_scipy() - S).max() <= 1e-13 * abs(S).max()
+    return float(np.abs(nz - J.nzval).max() / np.abs(J.nzval).max())

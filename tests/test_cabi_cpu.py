@@ -142,3 +142,12 @@ def test_export_capacity_and_errors():
         mu = p.mu.copy()
         mu[..., 0, 1] = 0.1
         A.set_mu(mu)
+
+
+def test_export_pattern_of_reduced_models():
+    """ModelTE / ModelTM / ModelTEM: the index pattern of A (1-based Int64, Julia CSC order) is the block of the 3-D
+    export and equals the K-dimensional operator's structure bit for bit (host-only handle: no GPU needed)."""
+    import maxwellfdm_jl_b200 as fb
+    from problems import REDUCED_PATTERN_CASES, reduced_pattern_check
+    for case in REDUCED_PATTERN_CASES:
+        assert reduced_pattern_check(fb, *case) < 1e-14, case
