@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 case "$1" in
 single)
   # new GPU tests first (material pipeline), then the whole suite, the bench line, the material-pipeline timing + ncu
-  timeout 600 python -m pytest tests -m gpu -x -q -k "matparams or objects" > gpurun_out/r02_matparams_tests.log 2>&1; echo "matparams tests rc=$?"; tail -3 gpurun_out/r02_matparams_tests.log
+  timeout 600 python -m pytest tests -m gpu -x -q -k "matparams or objects or reduced or trajectory or edge_cases" > gpurun_out/r02_matparams_tests.log 2>&1; echo "matparams tests rc=$?"; tail -3 gpurun_out/r02_matparams_tests.log
   timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r02_gpu_tests.log 2>&1; echo "gpu tests rc=$?"; tail -3 gpurun_out/r02_gpu_tests.log
   python bench.py > gpurun_out/r02_bench_line.json 2> gpurun_out/r02_bench.err; echo "bench rc=$?"; cut -c1-400 gpurun_out/r02_bench_line.json
   # BiCGSTAB with sigma accumulated by the p update (default since the end of round 1) vs the separate (rhat, v) pass
