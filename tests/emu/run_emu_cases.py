@@ -253,6 +253,27 @@ def g_reduced():
     K-dimensional oracle"""
     from problems import REDUCED_CASES, reduced_model_check, reduced_objects_check
     n = reduced_objects_check(fb)
+    # the torch branch of ReducedOperator (embedding / extraction with tensor indexing) on CPU tensors: the emulation
+    # build takes host pointers, the GPU box runs the same code on CUDA tensors (test_reduced_operator_on_device_tensors)
+    import torch
+    rng = np.random.default_rng(1)
+    for cmpfirst in (True, False):
+        mdl = fb.ModelTE(fb.Grid([np.arange(8.0), np.arange(6.0)], (True, False)))
+        mdl.order_cmpfirst = cmpfirst
+        mdl.eps_arr[..., 0, 0], mdl.eps_arr[..., 1, 1] = 2.0, 3.0
+        mdl.eps_arr[..., 0, 1] = mdl.eps_arr[..., 1, 0] = 0.1
+        A = fb.create_A(0, 1.0, mdl, device=0)
+        x = rng.standard_normal(A.n) + 1j * rng.standard_normal(A.n)
+        y = A @ x
+        yt = A @ torch.from_numpy(x)
+        assert isinstance(yt, torch.Tensor) and rel(yt.numpy(), y) == 0.0
+        out = torch.empty(A.n, dtype=torch.complex128)
+        A.mul(out, torch.from_numpy(x))
+        assert rel(out.numpy(), y) == 0.0
+        xs, info = A.solve(torch.from_numpy(y), rtol=1e-12)
+        assert info["converged"] and rel(xs.numpy(), x) < 1e-9
+        A.close()
+        n += 3
     for case in REDUCED_CASES:
         errs = reduced_model_check(fb, *case)
         assert max(v for k, v in errs.items() if k != "solve") < 1e-12 and errs["solve"] < 1e-7, (case, errs)

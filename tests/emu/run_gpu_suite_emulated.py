@@ -65,7 +65,9 @@ import maxwellfdm_jl_b200 as fb                     # noqa: E402
 assert "EMULATED" in fb._lib.lib().fdfd_version().decode(), "point FDFD_B200_LIB at build/emu/libfdfd_emu.so"
 import test_gpu_parity as T                          # noqa: E402
 
-SKIP = {"test_large_grid_properties": "draws its inputs with torch.randn on the device"}
+SKIP = {"test_large_grid_properties": "draws its inputs with torch.randn on the device",
+        "test_reduced_operator_on_device_tensors": "indexes torch tensors on the device (the same code runs on CPU tensors "
+                                                   "against the emulation build: run_emu_cases.py reduced)"}
 SLOW = {"test_tfsf_rhs_reproduces_the_incident_wave": "a 40^3 solve to 1e-10: half an hour of emulation (run with --slow)"}
 
 
