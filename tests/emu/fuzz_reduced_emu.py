@@ -1,6 +1,7 @@
 """TEST INFRASTRUCTURE ONLY - randomised 2-D / 1-D models (ModelTE, ModelTM, ModelTEM on the 3-D kernels,
 maxwellfdm.jl_b200/reduced.py) against the K-dimensional oracle: sizes around the tile edges, every boundft, Bloch /
-symmetry mixes, both formulations and DOF orders.
+symmetry mixes, both formulations and DOF orders; operator, right-hand side, post-processing, solve and the exported
+index pattern.
 
     FDFD_B200_LIB=build/emu/libfdfd_emu.so python tests/emu/fuzz_reduced_emu.py SEED NCASES
 """
@@ -13,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
 
-from problems import reduced_model_check            # noqa: E402
+from problems import reduced_model_check, reduced_pattern_check   # noqa: E402
 import maxwellfdm_jl_b200 as fb                     # noqa: E402
 
 
@@ -31,6 +32,10 @@ def main():
         errs = reduced_model_check(fb, *args, seed=int(rng.integers(1 << 30)))
         if not (max(v for k, v in errs.items() if k != "solve") < 1e-12 and errs["solve"] < 1e-6):
             print("FAIL", args, errs, flush=True)
+            sys.exit(1)
+        ev = reduced_pattern_check(fb, *args, seed=int(rng.integers(1 << 30)))     # index pattern bit-exact (asserts inside)
+        if not ev < 1e-13:
+            print("FAIL pattern values", args, ev, flush=True)
             sys.exit(1)
     print(f"reduced-model fuzz seed {seed}: {ncases} cases ok")
 
