@@ -37,6 +37,15 @@ __global__ void fill_kernel(double2 *dst, int64_t n, double2 v) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         dst[i] = v;
 }
+// dst[i*3 + c] = src_c[i]: the diagonal mass entries interleaved like a cmp-first DOF vector, so that the row-pair
+// kernel's TMA row copies fetch them with the geometry of the x rows
+__global__ void interleave3_kernel(double2 *dst, const double2 *s0, const double2 *s1, const double2 *s2, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        dst[3 * i] = s0[i];
+        dst[3 * i + 1] = s1[i];
+        dst[3 * i + 2] = s2[i];
+    }
+}
 __global__ void flush_kernel(float4 *p, int64_t n, float v) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         p[i] = make_float4(v, v, v, v);
@@ -49,7 +58,7 @@ static inline int nblocks(int64_t n) {
 
 static void free_device(Ctx *c) {
     auto F = [](auto *&p) { if (p) cudaFree((void *)p); p = nullptr; };
-    F(c->coef_dev); F(c->mat_dev); F(c->halo_lo); F(c->halo_hi); F(c->work); F(c->scal); F(c->partial);
+    F(c->coef_dev); F(c->mat_dev); F(c->md_aos); F(c->halo_lo); F(c->halo_hi); F(c->work); F(c->scal); F(c->partial);
     F(c->stage_x); F(c->stage_y); F(c->flush_buf); F(c->offmask); F(c->corr_list); F(c->dot_partial); F(c->dot_ticket);
     F(c->halo_flag);
     if (c->scal_host) cudaFreeHost(c->scal_host);
@@ -160,6 +169,7 @@ static int upload_materials(Ctx *c) {
         const cplx w2u = -(c->omega * c->omega);
         c->md_uniform = make_double2(w2u.real(), w2u.imag());
     }
+    if (c->md_aos) { cudaFree(c->md_aos); c->md_aos = nullptr; }
     if (!narr) return FDFD_OK;
     double2 *objbuf = nullptr;                  // objects: the smoothed slab in Julia layout, on the device
     if (obj && has_mass) {
@@ -254,6 +264,13 @@ static int upload_materials(Ctx *c) {
             if (r != FDFD_OK) return r;
         }
     }
+    // cmp-first DOF layout: a second, interleaved copy of the (ghosted) diagonal mass arrays for the row-pair kernel,
+    // which stages material through the same TMA ring as x (apply_rowpair.cu); +16 B/DOF of HBM capacity
+    if (c->md[0] && c->d.order_cmpfirst && c->d.kernel != FDFD_KERNEL_NAIVE) {
+        FDFD_CUDA(c, cudaMalloc((void **)&c->md_aos, (size_t)3 * Mg * sizeof(double2)));
+        interleave3_kernel<<<nblocks(Mg), 256, 0, c->stream>>>(c->md_aos, c->md[0], c->md[1], c->md[2], Mg);
+        FDFD_CUDA(c, cudaGetLastError());
+    }
     FDFD_CUDA(c, cudaStreamSynchronize(c->stream));
     return FDFD_OK;
 }
@@ -299,6 +316,7 @@ void fill_params(Ctx *c, ApplyParams &p, const double2 *x, double2 *y, bool tran
     p.has_q = c->q[0] != nullptr;
     p.c = transpose ? c->ct : c->cf;
     for (int i = 0; i < 3; ++i) { p.md[i] = c->md[i]; p.q[i] = c->q[i]; }
+    p.md_aos = c->md_aos;
     for (int i = 0; i < 6; ++i) p.mo[i] = transpose ? c->mo_t[i] : c->mo[i];
     const int64_t Nxy = Nx * Ny;
     p.x.base = x;

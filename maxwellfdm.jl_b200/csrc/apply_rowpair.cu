@@ -1,0 +1,745 @@
+// K1, second generation - the "row-pair" kernel: matrix-free y = C2 (q .* C1 x) + md .* x for a diagonal mass
+// parameter (the common case: off-diagonal material, where present, is added by the correction pass on the flagged
+// blocks only), any Yee arrangement (boundft), any boundary condition, both DOF layouts.
+//
+// Replaces the per-iteration CSC SpMV `mul!(y, A, x)` on the matrix assembled by the reference's create_A
+// (src/model/model.jl:225-246); stencil per SURVEY.md App. A.4-A.6.  Same arithmetic as apply_tiled.cu (K1, first
+// generation, kept for the fused full tensor and as the on-device cross-check) - what changes is who waits for whom:
+//
+//   * PERSISTENT grid, one CTA per SM (148 on B200); a CTA walks a static round-robin list of work items
+//     (x-y tile of 30 x 2*NWC output cells, z-chunk), so nothing is lost to wave quantisation and the TMA ring of
+//     the next item fills while the current one drains;
+//   * WARP SPECIALISATION: warp NWC is the producer - it owns the TMA unit (1-D bulk copies global -> shared, one
+//     per tile row, completing on a `full` mbarrier per ring stage) and the per-item coefficient tables; warps
+//     0..NWC-1 compute.  There is NO CTA-wide barrier in the plane loop: a compute warp waits on `full`, and when it
+//     is done with a stage it arrives on that stage's `empty` mbarrier (count NWC), which is all the producer waits on;
+//   * a compute warp owns TWO adjacent tile rows (one thread = two cells, 6 complex outputs): the y-neighbour of one
+//     of its cells is its own other cell (registers), the H values of the row below are RECOMPUTED from the ring
+//     (2 of 8 H components, +15 % flops) instead of being exchanged between warps, and the x-neighbour H values move
+//     by warp shuffle - the intermediate field H never touches shared memory, warps never wait for each other;
+//   * outputs are staged in a private per-warp buffer and leave through TMA bulk stores issued by the warp itself;
+//   * x / y / z coefficient tables: x in registers (per lane), y and z in shared memory (warp-uniform -> broadcast);
+//   * thread efficiency 30/32 (x halo lanes) instead of 30*6/256: 2.3x fewer instructions per output cell, and the
+//     shared-memory traffic per cell drops by ~45 %.
+//
+// Directions: the first curl's neighbour is at +s1[w] on axis w.  Lanes and rows are numbered along that direction
+// (physical column = s1x > 0 ? lane : 31 - lane, likewise rows), the z-march runs along s1z, so every arrangement
+// (default, mirrored, mixed) runs the same code with run-time index maps - no per-arrangement instantiation.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "cplx.cuh"
+#include "fdfd_internal.h"
+#include "ptx_sm100.cuh"
+
+namespace fdfd {
+
+namespace {
+
+#ifdef FDFD_RP_ABLATION   // timing experiments only (make abl): FDFD_RP_DEBUG bit 8 replaces the curl arithmetic by adds
+constexpr bool RP_ABL = true;
+#else
+constexpr bool RP_ABL = false;
+#endif
+constexpr int RP_TX = 32;          // data columns per tile (30 outputs)
+constexpr int RP_LZMAX = 62;       // max planes per z-chunk
+constexpr int RP_LZP = RP_LZMAX + 2;
+
+struct RowPairParams {
+    ApplyParams a;
+    int32_t wrapx, wrapy;
+    int32_t ntx, nty, nchunk;
+    int32_t kl_begin, kl_end;
+    int32_t nitems;
+    // tensor-map TMA path (cmp-first layout): x planes [0,nzl), the plane below / above the slab, interleaved material,
+    // and y (store boxes of 30 cells x 2 rows); tmap = 0: 1-D bulk row copies instead
+    TmaMap mx, mlo, mhi, mmd, my;
+    int32_t tmap;
+    int32_t dbg;   // timing experiments only (FDFD_RP_DEBUG bit mask; results are wrong): 1 no material loads,
+                   // 2 no y stores, 4 no x loads, 8 no arithmetic
+};
+
+template <int NWC, int NST>
+struct RPCfg {
+    static constexpr int NR = 2 * NWC + 2;            // E rows per ring stage
+    static constexpr int NM = 2 * NWC;                // material rows per ring stage (output rows only)
+    static constexpr int NT = 32 * (NWC + 1);
+    static constexpr int MD0 = NR * RP_TX * 3;        // offset of the material rows inside a stage
+    static constexpr int STAGE = (NR + NM) * RP_TX * 3;   // double2 per ring stage
+    static constexpr int FPAD = 8;                    // slack below stage 0 / above the last stage (halo-lane over-reads)
+    static constexpr int YW = 2 * RP_TX * 3;          // per-warp y staging (two rows)
+    static constexpr int TABS = 4 * NR + 4 * RP_LZP;  // per-item tables: a0,a1,b0,b1 for y (NR rows) and z (planes)
+    static constexpr size_t smem_bytes() {
+        return (size_t)(FPAD + NST * STAGE + FPAD + NWC * YW + 2 * TABS) * sizeof(double2) + 3 * NST * 8 + 128;
+    }
+};
+
+// chunk c of nch over [kb, ke): sizes differ by at most one plane
+__host__ __device__ __forceinline__ int chunk_begin(int kb, int ke, int nch, int c) {
+    return kb + (int)(((int64_t)(ke - kb) * c) / nch);
+}
+
+template <bool CMPFIRST, bool HAS_Q, bool DOT, int ARR, int NWC, int NST>
+__global__ void __launch_bounds__(32 * (NWC + 1), 1) apply_rowpair_kernel(const __grid_constant__ RowPairParams tp) {
+    using C = RPCfg<NWC, NST>;
+    constexpr int NR = C::NR, NM = C::NM, NT = C::NT, STAGE = C::STAGE, MD0 = C::MD0, TX = RP_TX, LZP = RP_LZP;
+    const ApplyParams &p = tp.a;
+    // direction of the first curl's neighbour per axis: compile-time for the two uniform arrangements (ARR 0: the
+    // reference default boundft = (EE,EE,EE) with FT_EE; ARR 1: its mirror image), run-time values for the mixed ones
+    const int SGX = ARR == 0 ? 1 : ARR == 1 ? -1 : p.s1[0];
+    const int SGY = ARR == 0 ? 1 : ARR == 1 ? -1 : p.s1[1];
+    const int SGZ = ARR == 0 ? 1 : ARR == 1 ? -1 : p.s1[2];
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double2 *ring = reinterpret_cast<double2 *>(smem_raw) + C::FPAD;   // NST * STAGE
+    double2 *ybase = ring + NST * STAGE + C::FPAD;                     // NWC * YW
+    double2 *tabs = ybase + NWC * C::YW;                               // 2 * TABS
+    uint64_t *full = reinterpret_cast<uint64_t *>(tabs + 2 * C::TABS);  // NST
+    uint64_t *empty = full + NST;                                      // NST
+    uint64_t *aux = empty + NST;                                       // NST  (tensor-map boxes of tiles with Bloch wrap)
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int Nx = p.Nx, Ny = p.Ny;
+    const int64_t Nxy = (int64_t)Nx * Ny;
+    const bool md_tile = p.has_mass && p.md[0] != nullptr && !(tp.dbg & 1);   // material rows travel through the ring
+
+    // ---- one-time prologue: barriers, finite ring contents --------------------------------------------------
+    if (tid == 0) {
+        for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NWC); mbar_init(&aux[s], 1); }
+        fence_barrier_init();
+    }
+    // tile positions no copy writes (symmetry-boundary halos, overhang) only ever meet zero coefficients or masked
+    // lanes, but must hold finite values: zero everything once (later items may leave stale - finite - data there)
+    for (int t = tid; t < NST * STAGE + 2 * C::FPAD; t += NT) (ring - C::FPAD)[t] = c_zero();
+    __syncthreads();
+
+    // element offsets inside a ring stage / the y staging rows
+    constexpr int EC = CMPFIRST ? 1 : NR * TX;        // E rows: component stride
+    constexpr int EX = CMPFIRST ? 3 : 1;              //         x-neighbour stride
+    constexpr int ER = CMPFIRST ? 3 * TX : TX;        //         row stride
+    constexpr int MC = CMPFIRST ? 1 : NM * TX;        // material rows: component stride (row / x strides as for E)
+    constexpr int YC = CMPFIRST ? 1 : 2 * TX;         // y staging: component stride (two rows per warp)
+    constexpr int YR = CMPFIRST ? 3 * TX : TX;
+
+    uint32_t g = 0;   // running index of plane loads of this CTA (ring stage g % NST, phase (g / NST) & 1)
+
+    if (wid == NWC) {
+        // =============================== producer warp ======================================================
+        int itc = 0;
+        uint32_t aux_phase = 0;   // bit s: parity of the phase of aux[s] that the next box sent there completes
+        for (int item = blockIdx.x; item < tp.nitems; item += gridDim.x, ++itc) {
+            int b = item;
+            const int tile_x = b % tp.ntx; b /= tp.ntx;
+            const int tile_y = b % tp.nty;
+            const int chunk = b / tp.nty;
+            const int ox = tile_x * (TX - 2) - 1, oy = tile_y * (2 * NWC) - 1;
+            const int kc0 = chunk_begin(tp.kl_begin, tp.kl_end, tp.nchunk, chunk);
+            const int kc1 = chunk_begin(tp.kl_begin, tp.kl_end, tp.nchunk, chunk + 1);
+            const int nplanes = kc1 - kc0 + 2;   // planes kc0-1 .. kc1
+            auto kof = [&](int n) { return SGZ < 0 ? kc1 - n : kc0 - 1 + n; };
+            // geometry of the bulk copies of one plane
+            const int xlo = max(ox, 0), xhi = min(ox + TX, Nx);
+            const bool lwrap = (ox < 0) && tp.wrapx;          // cell Nx-1 -> tile column 0
+            const bool rwrap = (ox + TX > Nx) && tp.wrapx;    // cell 0    -> tile column Nx-ox
+            auto row_src = [&](int r) -> int {
+                const int j = oy + r;
+                if (j >= 0 && j < Ny) return j;
+                if (tp.wrapy && (j == -1 || j == Ny)) return j < 0 ? Ny - 1 : 0;
+                return -1;
+            };
+            int nrows = 0;
+            for (int r = 0; r < NR; ++r) nrows += (row_src(r) >= 0);
+            const int nmrows = max(0, min(NM, Ny - (oy + 1)));   // material rows inside the domain
+            const uint32_t e_bytes = (uint32_t)nrows * (uint32_t)((xhi - xlo) + (lwrap ? 1 : 0) + (rwrap ? 1 : 0)) * 48u;
+            const uint32_t m_bytes = md_tile ? (uint32_t)nmrows * (uint32_t)(xhi - xlo) * 48u : 0u;
+            // per-lane copy descriptors: pair index < NE -> an E row (or (component,row)), else a material row
+            constexpr int NE = CMPFIRST ? NR : 3 * NR, NMP = CMPFIRST ? NM : 3 * NM;
+            constexpr int NPAIR = (NE + NMP + 31) / 32;
+            int cp_j[NPAIR], cp_c[NPAIR], cp_r[NPAIR];
+#pragma unroll
+            for (int q = 0; q < NPAIR; ++q) {
+                const int idx = lane + 32 * q;
+                if (idx < NE) {
+                    cp_c[q] = CMPFIRST ? 0 : idx / NR;
+                    cp_r[q] = CMPFIRST ? idx : idx % NR;
+                    cp_j[q] = row_src(cp_r[q]);
+                } else if (idx < NE + NMP) {
+                    const int m = idx - NE;
+                    cp_c[q] = CMPFIRST ? 0 : m / NM;
+                    cp_r[q] = CMPFIRST ? m : m % NM;
+                    const int j = oy + 1 + cp_r[q];
+                    cp_j[q] = (md_tile && j < Ny) ? j : -1;
+                } else {
+                    cp_c[q] = cp_r[q] = 0;
+                    cp_j[q] = -1;
+                }
+            }
+            // tensor-map path: does this tile need wrapped cells (Bloch boundary inside the tile)?
+            bool ywrap_rows = false;
+            for (int r = 0; r < NR; ++r) {
+                const int j = oy + r;
+                ywrap_rows |= (j < 0 || j >= Ny) && row_src(r) >= 0;
+            }
+            const bool has_wrap = (lwrap || rwrap || ywrap_rows) && !(tp.dbg & 4);
+            const uint32_t g_item = g;
+            // bytes of the 1-D wrap pieces of one plane: in-domain rows contribute their wrapped cells, wrapped rows
+            // their whole run
+            uint32_t wrap_bytes = 0;
+            for (int r = 0; r < NR; ++r) {
+                const int j = oy + r;
+                if (row_src(r) < 0) continue;
+                const bool wrapped_row = j < 0 || j >= Ny;
+                wrap_bytes += ((wrapped_row ? (uint32_t)(xhi - xlo) : 0u) + (lwrap ? 1u : 0u) + (rwrap ? 1u : 0u)) * 48u;
+            }
+            auto finish_wrap = [&](int m) {
+                const uint32_t gm = g_item + (uint32_t)m;
+                const int sm = gm % NST;
+                mbar_wait(&aux[sm], (aux_phase >> sm) & 1u);     // the box of load m has landed
+                aux_phase ^= 1u << sm;
+                const int km = kof(m);
+                const double2 *src = km < 0 ? p.x.lo : km >= p.nzl ? p.x.hi : p.x.base + (int64_t)km * p.x.pstride;
+                double2 *dstm = ring + sm * STAGE;
+                if (lane == 0) mbar_arrive_expect_tx(&full[sm], wrap_bytes);
+                __syncwarp();
+                if (CMPFIRST && lane < NR) {
+                    const int j = row_src(lane);
+                    if (j >= 0) {
+                        const bool wrapped_row = (oy + lane) < 0 || (oy + lane) >= Ny;
+                        const double2 *srow = src + (int64_t)j * Nx * 3;
+                        double2 *drow = dstm + lane * TX * 3;
+                        if (wrapped_row)
+                            bulk_g2s(drow + (xlo - ox) * 3, srow + (int64_t)xlo * 3, (uint32_t)(xhi - xlo) * 48u, &full[sm]);
+                        if (lwrap) bulk_g2s(drow, srow + (int64_t)(Nx - 1) * 3, 48u, &full[sm]);
+                        if (rwrap) bulk_g2s(drow + (Nx - ox) * 3, srow, 48u, &full[sm]);
+                    }
+                }
+            };
+            for (int n = 0; n < nplanes; ++n, ++g) {
+                const int s = g % NST;
+                if (g >= NST) mbar_wait(&empty[s], ((g / NST) - 1) & 1);
+                if (n == 0) {
+                    // tables of this item (double-buffered by item parity): every compute warp has left the item
+                    // before the previous one, because the stage just waited for was filled during the previous item
+                    double2 *tb = tabs + (itc & 1) * C::TABS;
+                    for (int t = lane; t < 4 * NR; t += 32) {
+                        const int a = t / NR, r = t % NR;
+                        const int j = (((oy + r) % Ny) + Ny) % Ny;
+                        const double2 *src = a == 0 ? p.c.a0[1] : a == 1 ? p.c.a1[1] : a == 2 ? p.c.b0[1] : p.c.b1[1];
+                        tb[t] = src[j];
+                    }
+                    for (int t = lane; t < 4 * nplanes; t += 32) {
+                        const int a = t / nplanes, m = t % nplanes;
+                        int kg = p.kz0 + kof(m);
+                        kg = ((kg % p.Nz) + p.Nz) % p.Nz;
+                        const double2 *src = a == 0 ? p.c.a0[2] : a == 1 ? p.c.a1[2] : a == 2 ? p.c.b0[2] : p.c.b1[2];
+                        tb[4 * NR + a * LZP + m] = src[kg];
+                    }
+                    __syncwarp();
+                }
+                const int kk = kof(n);
+                const bool want_m = md_tile && n >= 1 && n + 1 < nplanes;    // output planes only
+                const bool skip_x = (tp.dbg & 4) != 0;
+                double2 *dst = ring + s * STAGE;
+                if (CMPFIRST && tp.tmap) {
+                    // ---- tensor-map path: ONE box per array and plane; parts outside the domain read as zero
+                    const uint32_t box_bytes = (skip_x ? 0u : (uint32_t)(NR * TX * 48)) + (want_m ? (uint32_t)(NM * TX * 48) : 0u);
+                    uint64_t *bar = has_wrap ? &aux[s] : &full[s];
+                    if (lane == 0) {
+                        mbar_arrive_expect_tx(bar, box_bytes);
+                        if (!skip_x) {
+                            if (kk < 0) tma_load_3d(dst, &tp.mlo, 6 * ox, oy, 0, bar);
+                            else if (kk >= p.nzl) tma_load_3d(dst, &tp.mhi, 6 * ox, oy, 0, bar);
+                            else tma_load_3d(dst, &tp.mx, 6 * ox, oy, kk, bar);
+                        }
+                        if (want_m) tma_load_3d(dst + MD0, &tp.mmd, 6 * ox, oy + 1, kk + 1, bar);
+                    }
+                    // tiles with Bloch wrap: the wrapped cells / rows of the PREVIOUS plane follow as 1-D pieces once
+                    // its box (which zero-filled those places) has landed - it has had a whole step to do so
+                    if (has_wrap && n >= 1) finish_wrap(n - 1);
+                    continue;
+                }
+                int64_t cs;
+                const double2 *src;
+                if (kk < 0) { cs = p.x.cs_lo; src = p.x.lo; }
+                else if (kk >= p.nzl) { cs = p.x.cs_hi; src = p.x.hi; }
+                else { cs = p.x.cs; src = p.x.base + (int64_t)kk * p.x.pstride; }
+                uint64_t *bar = &full[s];
+                if (lane == 0) mbar_arrive_expect_tx(bar, (skip_x ? 0u : e_bytes) + (want_m ? m_bytes : 0u));
+                __syncwarp();
+#pragma unroll
+                for (int q = 0; q < NPAIR; ++q) {
+                    const int j = cp_j[q];
+                    if (j < 0) continue;
+                    const int idx = lane + 32 * q;
+                    if (idx < NE) {
+                        if (skip_x) continue;
+                        if (CMPFIRST) {
+                            const double2 *srow = src + (int64_t)j * Nx * 3;
+                            double2 *drow = dst + cp_r[q] * TX * 3;
+                            bulk_g2s(drow + (xlo - ox) * 3, srow + (int64_t)xlo * 3, (uint32_t)(xhi - xlo) * 48u, bar);
+                            if (lwrap) bulk_g2s(drow, srow + (int64_t)(Nx - 1) * 3, 48u, bar);
+                            if (rwrap) bulk_g2s(drow + (Nx - ox) * 3, srow, 48u, bar);
+                        } else {
+                            const double2 *srow = src + (int64_t)cp_c[q] * cs + (int64_t)j * Nx;
+                            double2 *drow = dst + (cp_c[q] * NR + cp_r[q]) * TX;
+                            bulk_g2s(drow + (xlo - ox), srow + xlo, (uint32_t)(xhi - xlo) * 16u, bar);
+                            if (lwrap) bulk_g2s(drow, srow + (Nx - 1), 16u, bar);
+                            if (rwrap) bulk_g2s(drow + (Nx - ox), srow, 16u, bar);
+                        }
+                    } else if (want_m) {
+                        const int64_t mo = (int64_t)(kk + 1) * Nxy + (int64_t)j * Nx + xlo;   // ghosted material index
+                        if (CMPFIRST)
+                            bulk_g2s(dst + MD0 + (cp_r[q] * TX + (xlo - ox)) * 3, p.md_aos + mo * 3,
+                                     (uint32_t)(xhi - xlo) * 48u, bar);
+                        else
+                            bulk_g2s(dst + MD0 + (cp_c[q] * NM + cp_r[q]) * TX + (xlo - ox), p.md[cp_c[q]] + mo,
+                                     (uint32_t)(xhi - xlo) * 16u, bar);
+                    }
+                }
+            }
+            if (CMPFIRST && tp.tmap && has_wrap) finish_wrap(nplanes - 1);
+        }
+    } else {
+        // =============================== compute warps ======================================================
+        // logical (along the first curl's direction) -> physical tile coordinates
+        const int ptx = SGX > 0 ? lane : TX - 1 - lane;
+        const int rA = SGY > 0 ? 2 * wid + 1 : NR - 2 - 2 * wid;      // physical tile row of cell A; B = A + s1y
+        const int rB = rA + SGY;
+        const int eA = rA * ER + ptx * EX;                // E element of cell A, component 0, inside a stage
+        const int dB = SGY * ER;                          // A -> B; R (row below the pair) = A - dB, F = A + 2 dB
+        const int exf = SGX * EX;                         // offset to the x-neighbour of the first curl
+        const int mdo = MD0 - ER;                         // E element of an output cell -> its material element (c = 0)
+        // y staging: row slot 0 <-> the physically lower row of the pair
+        double2 *yw = ybase + wid * C::YW;
+        const int ysA = SGY > 0 ? 0 : 1;
+        const bool tmap = CMPFIRST && tp.tmap != 0;
+        // tensor-map stores take a dense box: 30 output cells per row (no halo columns in the staging rows)
+        const int yA = tmap ? (ysA * (TX - 2) + ptx - 1) * 3 : ysA * YR + ptx * EX;
+        const int yB = tmap ? ((1 - ysA) * (TX - 2) + ptx - 1) * 3 : (1 - ysA) * YR + ptx * EX;
+        const int rlo = SGY > 0 ? rA : rB;                // physical tile row of staging slot 0
+        const bool lane_out = (lane >= 1) && (lane <= TX - 2);
+        constexpr int NSTORE1D = CMPFIRST ? 2 : 6;
+        const int NSTORE = tmap ? 1 : NSTORE1D;           // lanes that issue this warp's bulk stores
+
+        double ts_re = 0.0, ts_im = 0.0, tt = 0.0;
+        int itc = 0;
+        for (int item = blockIdx.x; item < tp.nitems; item += gridDim.x, ++itc) {
+            int b = item;
+            const int tile_x = b % tp.ntx; b /= tp.ntx;
+            const int tile_y = b % tp.nty;
+            const int chunk = b / tp.nty;
+            const int ox = tile_x * (TX - 2) - 1, oy = tile_y * (2 * NWC) - 1;
+            const int kc0 = chunk_begin(tp.kl_begin, tp.kl_end, tp.nchunk, chunk);
+            const int kc1 = chunk_begin(tp.kl_begin, tp.kl_end, tp.nchunk, chunk + 1);
+            const int nplanes = kc1 - kc0 + 2;
+            const int kfirst = SGZ < 0 ? kc1 : kc0 - 1;   // local plane of march step 0
+
+            const int gi = ox + ptx, gjA = oy + rA, gjB = oy + rB;
+            const int ci = ((gi % Nx) + Nx) % Nx;
+            const bool okA = lane_out && gi < Nx && gjA < Ny, okB = lane_out && gi < Nx && gjB < Ny;
+            // x tables in registers
+            const double2 a0x = ldg2(&p.c.a0[0][ci]), a1x = ldg2(&p.c.a1[0][ci]);
+            const double2 b0x = ldg2(&p.c.b0[0][ci]), b1x = ldg2(&p.c.b1[0][ci]);
+            // q (inverse middle parameter): per-thread global loads (only FT_HH and models with a mu array carry it)
+            int64_t qA = 0, qB = 0, qR = 0;
+            if (HAS_Q) {
+                const int gjR = gjA - SGY;
+                const int cjA = ((gjA % Ny) + Ny) % Ny, cjB = ((gjB % Ny) + Ny) % Ny, cjR = ((gjR % Ny) + Ny) % Ny;
+                const int64_t k1 = (int64_t)(kfirst + 1) * Nxy;
+                qA = k1 + (int64_t)cjA * Nx + ci; qB = k1 + (int64_t)cjB * Nx + ci; qR = k1 + (int64_t)cjR * Nx + ci;
+            }
+            const int64_t dN = SGZ * Nxy;
+            // store geometry of this item (lanes < NSTORE): row / component handled by this lane, in-domain columns
+            const int c0 = ox + 1, c1 = min(ox + TX - 1, Nx);
+            const int st_slot = CMPFIRST ? lane : lane % 2, st_c = CMPFIRST ? 0 : lane / 2;
+            const int st_j = oy + rlo + st_slot;
+            const bool st_on = lane < NSTORE && (tmap || (st_j < Ny && c1 > c0)) && !(tp.dbg & 2);
+            const int st_x = 6 * (ox + 1), st_y = oy + rlo;   // tensor-map store: box origin (clipped by the hardware)
+            double2 *st_dst = p.y + (int64_t)kfirst * p.y_pstride +
+                              (CMPFIRST ? ((int64_t)st_j * Nx + c0) * 3 : (int64_t)st_c * p.y_cs + (int64_t)st_j * Nx + c0);
+            const int64_t st_step = SGZ * p.y_pstride;
+            const double2 *st_src = CMPFIRST ? yw + (st_slot * TX + 1) * 3 : yw + st_c * YC + st_slot * YR + 1;
+            const uint32_t st_bytes = (uint32_t)(c1 - c0) * (CMPFIRST ? 48u : 16u);
+
+            const double2 *tb = tabs + (itc & 1) * C::TABS;
+            const double2 *ty = tb + rA;                  // y tables of row A: + a * NR; rows B / R at +- s1y
+            const double2 *tz = tb + 4 * NR;              // + a * LZP + n
+
+            // first plane of the item
+            int s_cur = g % NST;
+            mbar_wait(&full[s_cur], (g / NST) & 1);
+            const double2 *es = ring + s_cur * STAGE + eA;
+            double2 EA0 = es[0], EA1 = es[EC], EA2 = es[2 * EC];
+            double2 EB0 = es[dB], EB1 = es[dB + EC], EB2 = es[dB + 2 * EC];
+            double2 ER1 = es[EC - dB];
+            double2 HpxA = c_zero(), HpyA = c_zero(), HpxB = c_zero(), HpyB = c_zero();
+
+#pragma unroll 2
+            for (int n = 0; n + 1 < nplanes; ++n, ++g) {
+                const bool do_out = n >= 1;
+                double2 qA0, qA1, qA2, qB0, qB1, qB2, qR0, qR2;
+                if (HAS_Q) {
+                    const int64_t o = (int64_t)n * dN;
+                    qA0 = ldg2(&p.q[0][qA + o]); qA1 = ldg2(&p.q[1][qA + o]); qA2 = ldg2(&p.q[2][qA + o]);
+                    qB0 = ldg2(&p.q[0][qB + o]); qB1 = ldg2(&p.q[1][qB + o]); qB2 = ldg2(&p.q[2][qB + o]);
+                    qR0 = ldg2(&p.q[0][qR + o]); qR2 = ldg2(&p.q[2][qR + o]);
+                    if (n + 4 < nplanes) {
+                        prefetch_l2(&p.q[0][qA + o + 3 * dN]); prefetch_l2(&p.q[1][qA + o + 3 * dN]);
+                        prefetch_l2(&p.q[2][qA + o + 3 * dN]);
+                        prefetch_l2(&p.q[0][qB + o + 3 * dN]); prefetch_l2(&p.q[1][qB + o + 3 * dN]);
+                        prefetch_l2(&p.q[2][qB + o + 3 * dN]);
+                    }
+                }
+
+                // plane k (stage es, complete since the previous step): the neighbours the first curl needs
+                const double2 EA1x = es[EC + exf], EA2x = es[2 * EC + exf];
+                const double2 EB1x = es[dB + EC + exf], EB2x = es[dB + 2 * EC + exf];
+                const double2 ER1x = es[EC - dB + exf];
+                const double2 EF0 = es[2 * dB], EF2 = es[2 * dB + 2 * EC];
+                const double2 ER0 = es[-dB], ER2 = es[2 * EC - dB];
+                const double2 a0yA = ty[0], a1yA = ty[NR], a0yB = ty[SGY], a1yB = ty[NR + SGY];
+                const double2 a0yR = ty[-SGY], a1yR = ty[NR - SGY];
+                const double2 a0z = tz[n], a1z = tz[LZP + n];
+
+                // plane k + s1z
+                const int s_nxt = (s_cur + 1 == NST) ? 0 : s_cur + 1;
+                mbar_wait(&full[s_nxt], ((g + 1) / NST) & 1);
+                const double2 *en = ring + s_nxt * STAGE + eA;
+                const double2 NA0 = en[0], NA1 = en[EC], NA2 = en[2 * EC];
+                const double2 NB0 = en[dB], NB1 = en[dB + EC], NB2 = en[dB + 2 * EC];
+                const double2 NR1 = en[EC - dB];
+
+                double2 HxA, HyA, HzA, HxB, HyB, HzB, HxR, HzR;
+                if (!RP_ABL || !(tp.dbg & 8)) {
+                    // H(k) = C1 E :  Hx = Dy Ez - Dz Ey,  Hy = Dz Ex - Dx Ez,  Hz = Dx Ey - Dy Ex
+                    HxA = c_mul(a0yA, EA2); HxA = c_fma(a1yA, EB2, HxA); HxA = c_fms(a0z, EA1, HxA); HxA = c_fms(a1z, NA1, HxA);
+                    HyA = c_mul(a0z, EA0);  HyA = c_fma(a1z, NA0, HyA);  HyA = c_fms(a0x, EA2, HyA); HyA = c_fms(a1x, EA2x, HyA);
+                    HzA = c_mul(a0x, EA1);  HzA = c_fma(a1x, EA1x, HzA); HzA = c_fms(a0yA, EA0, HzA); HzA = c_fms(a1yA, EB0, HzA);
+                    HxB = c_mul(a0yB, EB2); HxB = c_fma(a1yB, EF2, HxB); HxB = c_fms(a0z, EB1, HxB); HxB = c_fms(a1z, NB1, HxB);
+                    HyB = c_mul(a0z, EB0);  HyB = c_fma(a1z, NB0, HyB);  HyB = c_fms(a0x, EB2, HyB); HyB = c_fms(a1x, EB2x, HyB);
+                    HzB = c_mul(a0x, EB1);  HzB = c_fma(a1x, EB1x, HzB); HzB = c_fms(a0yB, EB0, HzB); HzB = c_fms(a1yB, EF0, HzB);
+                    // the two components of the row below that this pair's second curl needs (recomputed, not exchanged)
+                    HxR = c_mul(a0yR, ER2); HxR = c_fma(a1yR, EA2, HxR); HxR = c_fms(a0z, ER1, HxR); HxR = c_fms(a1z, NR1, HxR);
+                    HzR = c_mul(a0x, ER1);  HzR = c_fma(a1x, ER1x, HzR); HzR = c_fms(a0yR, ER0, HzR); HzR = c_fms(a1yR, EA0, HzR);
+                } else {   // timing experiment: touch every operand, no curl arithmetic
+                    HxA = c_add(EA2, EB2); HyA = c_add(NA0, EA2x); HzA = c_add(EA1x, EB0);
+                    HxB = c_add(EF2, NB1); HyB = c_add(NB0, EB2x); HzB = c_add(EB1x, EF0);
+                    HxR = c_add(ER2, NR1); HzR = c_add(ER1x, ER0);
+                    HxA = c_add(HxA, a0yA); HyA = c_add(HyA, a1yA); HzA = c_add(HzA, a0yB); HxB = c_add(HxB, a1yB);
+                    HyB = c_add(HyB, a0yR); HzB = c_add(HzB, a1yR); HxR = c_add(HxR, a0z); HzR = c_add(HzR, a1z);
+                    HxA = c_add(HxA, NA1); HxB = c_add(HxB, NA2); HyB = c_add(HyB, NB2);
+                }
+                if (HAS_Q) {
+                    HxA = c_mul(qA0, HxA); HyA = c_mul(qA1, HyA); HzA = c_mul(qA2, HzA);
+                    HxB = c_mul(qB0, HxB); HyB = c_mul(qB1, HyB); HzB = c_mul(qB2, HzB);
+                    HxR = c_mul(qR0, HxR); HzR = c_mul(qR2, HzR);
+                }
+
+                if (do_out) {
+                    // H_y, H_z of the x-neighbour opposite to the first curl's direction: from the previous lane
+                    double2 HyAm, HzAm, HyBm, HzBm;
+                    HyAm.x = __shfl_up_sync(0xffffffffu, HyA.x, 1); HyAm.y = __shfl_up_sync(0xffffffffu, HyA.y, 1);
+                    HzAm.x = __shfl_up_sync(0xffffffffu, HzA.x, 1); HzAm.y = __shfl_up_sync(0xffffffffu, HzA.y, 1);
+                    HyBm.x = __shfl_up_sync(0xffffffffu, HyB.x, 1); HyBm.y = __shfl_up_sync(0xffffffffu, HyB.y, 1);
+                    HzBm.x = __shfl_up_sync(0xffffffffu, HzB.x, 1); HzBm.y = __shfl_up_sync(0xffffffffu, HzB.y, 1);
+                    const double2 b0yA = ty[2 * NR], b1yA = ty[3 * NR], b0yB = ty[2 * NR + SGY], b1yB = ty[3 * NR + SGY];
+                    const double2 b0z = tz[2 * LZP + n], b1z = tz[3 * LZP + n];
+                    // material of plane k: same ring stage as E(k)
+                    double2 mdA0 = p.md_uniform, mdA1 = p.md_uniform, mdA2 = p.md_uniform;
+                    double2 mdB0 = p.md_uniform, mdB1 = p.md_uniform, mdB2 = p.md_uniform;
+                    if (md_tile) {
+                        mdA0 = es[mdo]; mdA1 = es[mdo + MC]; mdA2 = es[mdo + 2 * MC];
+                        mdB0 = es[mdo + dB]; mdB1 = es[mdo + dB + MC]; mdB2 = es[mdo + dB + 2 * MC];
+                    }
+                    double2 yxA, yyA, yzA, yxB, yyB, yzB;
+                    if (!RP_ABL || !(tp.dbg & 8)) {
+                        // y = C2 H :  yx = Dy Hz - Dz Hy,  yy = Dz Hx - Dx Hz,  yz = Dx Hy - Dy Hx
+                        yxA = c_mul(b0yA, HzA); yxA = c_fma(b1yA, HzR, yxA);  yxA = c_fms(b0z, HyA, yxA); yxA = c_fms(b1z, HpyA, yxA);
+                        yyA = c_mul(b0z, HxA);  yyA = c_fma(b1z, HpxA, yyA);  yyA = c_fms(b0x, HzA, yyA); yyA = c_fms(b1x, HzAm, yyA);
+                        yzA = c_mul(b0x, HyA);  yzA = c_fma(b1x, HyAm, yzA);  yzA = c_fms(b0yA, HxA, yzA); yzA = c_fms(b1yA, HxR, yzA);
+                        yxB = c_mul(b0yB, HzB); yxB = c_fma(b1yB, HzA, yxB);  yxB = c_fms(b0z, HyB, yxB); yxB = c_fms(b1z, HpyB, yxB);
+                        yyB = c_mul(b0z, HxB);  yyB = c_fma(b1z, HpxB, yyB);  yyB = c_fms(b0x, HzB, yyB); yyB = c_fms(b1x, HzBm, yyB);
+                        yzB = c_mul(b0x, HyB);  yzB = c_fma(b1x, HyBm, yzB);  yzB = c_fms(b0yB, HxB, yzB); yzB = c_fms(b1yB, HxA, yzB);
+                        if (p.has_mass) {
+                            yxA = c_fma(mdA0, EA0, yxA); yyA = c_fma(mdA1, EA1, yyA); yzA = c_fma(mdA2, EA2, yzA);
+                            yxB = c_fma(mdB0, EB0, yxB); yyB = c_fma(mdB1, EB1, yyB); yzB = c_fma(mdB2, EB2, yzB);
+                        }
+                    } else {
+                        yxA = c_add(c_add(HzA, HzR), c_add(HpyA, mdA0)); yyA = c_add(c_add(HxA, HpxA), c_add(HzAm, mdA1));
+                        yzA = c_add(c_add(HyA, HyAm), c_add(HxR, mdA2)); yxB = c_add(c_add(HzB, HyB), c_add(HpyB, mdB0));
+                        yyB = c_add(c_add(HxB, HpxB), c_add(HzBm, mdB1)); yzB = c_add(c_add(HyBm, b0yA), c_add(b1yB, mdB2));
+                        yxA = c_add(yxA, b0z); yyA = c_add(yyA, b1z); yzA = c_add(yzA, b1yA); yxB = c_add(yxB, b0yB);
+                    }
+                    if (DOT) {   // fused Krylov inner products: t = y, s = x (own cells, in registers)
+                        if (okA) {
+                            ts_re += yxA.x * EA0.x + yxA.y * EA0.y + yyA.x * EA1.x + yyA.y * EA1.y + yzA.x * EA2.x + yzA.y * EA2.y;
+                            ts_im += yxA.x * EA0.y - yxA.y * EA0.x + yyA.x * EA1.y - yyA.y * EA1.x + yzA.x * EA2.y - yzA.y * EA2.x;
+                            tt += yxA.x * yxA.x + yxA.y * yxA.y + yyA.x * yyA.x + yyA.y * yyA.y + yzA.x * yzA.x + yzA.y * yzA.y;
+                        }
+                        if (okB) {
+                            ts_re += yxB.x * EB0.x + yxB.y * EB0.y + yyB.x * EB1.x + yyB.y * EB1.y + yzB.x * EB2.x + yzB.y * EB2.y;
+                            ts_im += yxB.x * EB0.y - yxB.y * EB0.x + yyB.x * EB1.y - yyB.y * EB1.x + yzB.x * EB2.y - yzB.y * EB2.x;
+                            tt += yxB.x * yxB.x + yxB.y * yxB.y + yyB.x * yyB.x + yyB.y * yyB.y + yzB.x * yzB.x + yzB.y * yzB.y;
+                        }
+                    }
+                    // the copy engine must have finished READING the staging rows of the previous plane
+                    if (lane < NSTORE) bulk_wait_read0();
+                    __syncwarp();
+                    if (!tmap || lane_out) {
+                        yw[yA] = yxA; yw[yA + YC] = yyA; yw[yA + 2 * YC] = yzA;
+                        yw[yB] = yxB; yw[yB + YC] = yyB; yw[yB + 2 * YC] = yzB;
+                    }
+                    fence_proxy_async();   // generic-proxy writes -> visible to the bulk-copy (async) proxy
+                }
+                // stage es (plane k: E and material) is no longer needed by this warp; the same warp-wide
+                // synchronisation orders the staging writes above before the bulk store below
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(&empty[s_cur]);
+                    if (n + 2 == nplanes) mbar_arrive(&empty[s_nxt]);   // last step: plane k + s1z is not revisited
+                }
+                if (do_out && st_on) {
+                    if (tmap) tma_store_3d(&tp.my, st_x, st_y, kfirst + SGZ * n, yw);
+                    else bulk_s2g(st_dst + (int64_t)n * st_step, st_src, st_bytes);
+                    bulk_commit();
+                }
+                HpxA = HxA; HpyA = HyA; HpxB = HxB; HpyB = HyB;
+                EA0 = NA0; EA1 = NA1; EA2 = NA2;
+                EB0 = NB0; EB1 = NB1; EB2 = NB2;
+                ER1 = NR1;
+                es = en;
+                s_cur = s_nxt;
+            }
+            ++g;   // the last plane of the item was consumed as `en` of the final step
+        }
+        if (lane < NSTORE) bulk_wait0();   // outstanding bulk stores complete before the CTA exits
+
+        if (DOT) {
+            // warp partials -> shared scratch (the y staging of this warp is idle now)
+            double v3[3] = {ts_re, ts_im, tt};
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v3[q] += __shfl_xor_sync(0xffffffffu, v3[q], o);
+            }
+            if (lane == 0) {
+                double *sc = reinterpret_cast<double *>(yw);
+                sc[0] = v3[0]; sc[1] = v3[1]; sc[2] = v3[2];
+            }
+        }
+    }
+    if (DOT) {
+        // one partial per CTA; the last CTA (atomic ticket) adds the partials in a fixed order -> deterministic result
+        __syncthreads();
+        __shared__ bool last_cta;
+        if (tid == 0) {
+            double a = 0, b2 = 0, c3 = 0;
+            for (int w = 0; w < NWC; ++w) {
+                const double *sc = reinterpret_cast<const double *>(ybase + w * C::YW);
+                a += sc[0]; b2 += sc[1]; c3 += sc[2];
+            }
+            double *pp = p.dot_partial + (size_t)blockIdx.x * 4;
+            pp[0] = a; pp[1] = b2; pp[2] = c3;
+            __threadfence();
+            last_cta = atomicAdd(p.dot_ticket, 1u) == gridDim.x - 1;
+        }
+        __syncthreads();
+        if (last_cta) {
+            __threadfence();
+            double s3[3] = {0.0, 0.0, 0.0};
+            for (int bI = tid; bI < (int)gridDim.x; bI += NT) {
+                const double *pp = p.dot_partial + (size_t)bI * 4;
+                s3[0] += __ldcg(pp); s3[1] += __ldcg(pp + 1); s3[2] += __ldcg(pp + 2);
+            }
+            double *sc = reinterpret_cast<double *>(tabs);   // tables are dead now
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) s3[q] += __shfl_xor_sync(0xffffffffu, s3[q], o);
+                if (lane == 0) sc[wid * 3 + q] = s3[q];
+            }
+            __syncthreads();
+            if (tid == 0) {
+                double a = 0, b2 = 0, c3 = 0;
+                for (int w = 0; w < NWC + 1; ++w) { a += sc[w * 3]; b2 += sc[w * 3 + 1]; c3 += sc[w * 3 + 2]; }
+                p.dot_out[0] = a; p.dot_out[1] = b2; p.dot_out[2] = c3; p.dot_out[3] = 0.0;
+                *p.dot_ticket = 0;
+            }
+        }
+    }
+}
+
+int sm_count() {
+    static int n[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return 148;
+    if (!n[dev]) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        n[dev] = v;
+    }
+    return n[dev];
+}
+
+template <bool CMPFIRST, bool HAS_Q, bool DOT, int ARR, int NWC, int NST>
+cudaError_t launch_rp(const RowPairParams &tp, int grid, cudaStream_t s) {
+    auto kern = apply_rowpair_kernel<CMPFIRST, HAS_Q, DOT, ARR, NWC, NST>;
+    const size_t smem = RPCfg<NWC, NST>::smem_bytes();
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
+    kern<<<grid, 32 * (NWC + 1), smem, s>>>(tp);
+    return cudaGetLastError();
+}
+
+// Compiled tile heights / ring depths.  Warps are spread over the four SM sub-partitions, so the register budget per
+// thread steps with ceil(warps / 4): 8 warps (7 compute + producer) may use 255 registers, 12 warps (11 + 1) 168.
+struct RpShape { int nwc, nst; };
+constexpr RpShape RP_SHAPES[] = {{7, 4}, {7, 3}, {5, 5}};
+constexpr int RP_NSHAPES = sizeof(RP_SHAPES) / sizeof(RP_SHAPES[0]);
+
+}  // namespace
+
+// Plan: number of z-chunks per tile column so that the per-CTA sum of (planes + 1 extra first-curl step) is smallest.
+static int rp_pick_nchunk(int ncols, int nplanes, int nsm, int nst, double *cost_out) {
+    const int lzmin = std::max(1, nst - 2);   // an item must span at least NST plane loads (table double-buffering)
+    int best = 0;
+    double best_cost = 1e300;
+    const int nch_min = (nplanes + RP_LZMAX - 1) / RP_LZMAX;
+    for (int nch = std::max(1, nch_min); nch <= nplanes; ++nch) {
+        const int lz_lo = nplanes / nch, lz_hi = (nplanes + nch - 1) / nch;
+        if (lz_lo < lzmin) break;
+        if (lz_hi > RP_LZMAX) continue;
+        const long items = (long)ncols * nch;
+        const long per_cta = (items + nsm - 1) / nsm;
+        const double cost = (double)per_cta * (0.5 * (lz_lo + lz_hi) + 1.6);
+        if (cost < best_cost) { best_cost = cost; best = nch; }
+    }
+    if (cost_out) *cost_out = best_cost;
+    return best;
+}
+
+static int env_int(const char *name) {
+    const char *e = getenv(name);
+    return e ? atoi(e) : 0;
+}
+
+// tile shape for this problem: the one whose plan costs least (plane-steps per CTA x rows per step), unless
+// FDFD_RP_NWC / FDFD_RP_NST pin it (tuning)
+static int rp_pick_shape(const ApplyParams &p, int kl_begin, int kl_end, int *nchunk) {
+    static const int want_nwc = env_int("FDFD_RP_NWC"), want_nst = env_int("FDFD_RP_NST"), want_nch = env_int("FDFD_RP_NCHUNK");
+    int best = -1;
+    double best_cost = 1e300;
+    const int n = kl_end - kl_begin;
+    for (int i = 0; i < RP_NSHAPES; ++i) {
+        const int nwc = RP_SHAPES[i].nwc, nst = RP_SHAPES[i].nst;
+        if (want_nwc && nwc != want_nwc) continue;
+        if (want_nst && nst != want_nst) continue;
+        if (!want_nst && i > 0 && RP_SHAPES[i].nwc == RP_SHAPES[i - 1].nwc) continue;   // first listed ring depth is the default
+        const int ntx = (p.Nx + RP_TX - 3) / (RP_TX - 2), nty = (p.Ny + 2 * nwc - 1) / (2 * nwc);
+        double cost;
+        int nch = rp_pick_nchunk(ntx * nty, n, sm_count(), nst, &cost);
+        if (want_nch >= 1 && n / want_nch >= std::max(1, nst - 2) && (n + want_nch - 1) / want_nch <= RP_LZMAX) nch = want_nch;
+        if (nch < 1) continue;
+        cost *= 2.0 * nwc;   // cells per plane-step scale with the tile height; throughput per CTA roughly does too
+        if (cost < best_cost) { best_cost = cost; best = i; *nchunk = nch; }
+    }
+    return best;
+}
+
+bool rowpair_supported(const ApplyParams &p, int kl_begin, int kl_end) {
+    for (int w = 0; w < 3; ++w)
+        if (p.s1[w] != 1 && p.s1[w] != -1) return false;
+    if (p.halo_flag != nullptr) return false;               // in-kernel halo wait: first-generation kernel only
+    int nch = 0;
+    return kl_end > kl_begin && rp_pick_shape(p, kl_begin, kl_end, &nch) >= 0;
+}
+
+// Tensor maps are cached by (address, geometry): a Krylov solve applies the operator to a handful of workspace
+// vectors over and over, so the driver's encode call (~1 us) is paid once per vector, not once per apply.
+static bool cached_map(TmaMap *out, const void *base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0, uint32_t b1) {
+    struct Entry { const void *base; uint64_t d0, d1, d2; uint32_t b0, b1; TmaMap m; };
+    static thread_local std::vector<Entry> cache;
+    for (size_t i = 0; i < cache.size(); ++i) {
+        const Entry &e = cache[i];
+        if (e.base == base && e.d0 == d0 && e.d1 == d1 && e.d2 == d2 && e.b0 == b0 && e.b1 == b1) {
+            *out = e.m;
+            return true;
+        }
+    }
+    const uint64_t dims[3] = {d0, d1, d2}, strides[2] = {d0 * 8, d0 * d1 * 8};
+    const uint32_t box[3] = {b0, b1, 1};
+    Entry e{base, d0, d1, d2, b0, b1, {}};
+    if (!tmap_encode_f64_3d(&e.m, base, dims, strides, box)) return false;
+    if (cache.size() >= 64) cache.erase(cache.begin());
+    cache.push_back(e);
+    *out = e.m;
+    return true;
+}
+
+template <int NWC, int NST>
+static cudaError_t launch_rp_shape(RowPairParams &tp, const ApplyParams &p, cudaStream_t s) {
+    // tensor-map TMA path (cmp-first layout): boxes of 32 cells x (E rows | material rows), y boxes of 30 cells x 2 rows
+    static const bool want_tmap = [] { const char *e = getenv("FDFD_RP_TMAP"); return !e || atoi(e) != 0; }();
+    tp.tmap = 0;
+    if (want_tmap && p.cmpfirst && p.x.base && p.y) {
+        const uint64_t d0 = 6ull * p.Nx, d1 = (uint64_t)p.Ny;
+        const bool md_tile = p.has_mass && p.md[0] != nullptr;
+        bool ok = cached_map(&tp.mx, p.x.base, d0, d1, (uint64_t)p.nzl, 6 * RP_TX, 2 * NWC + 2) &&
+                  cached_map(&tp.mlo, p.x.lo, d0, d1, 1, 6 * RP_TX, 2 * NWC + 2) &&
+                  cached_map(&tp.mhi, p.x.hi, d0, d1, 1, 6 * RP_TX, 2 * NWC + 2) &&
+                  cached_map(&tp.my, p.y, d0, d1, (uint64_t)p.nzl, 6 * (RP_TX - 2), 2);
+        if (ok && md_tile) ok = p.md_aos != nullptr && cached_map(&tp.mmd, p.md_aos, d0, d1, (uint64_t)p.nzl + 2, 6 * RP_TX, 2 * NWC);
+        tp.tmap = ok ? 1 : 0;
+    }
+    tp.ntx = (p.Nx + RP_TX - 3) / (RP_TX - 2);
+    tp.nty = (p.Ny + 2 * NWC - 1) / (2 * NWC);
+    tp.nitems = tp.ntx * tp.nty * tp.nchunk;
+    int grid = std::min(tp.nitems, sm_count());
+    static const int want_grid = env_int("FDFD_RP_GRID");   // tuning / test override of the persistent grid size
+    if (want_grid >= 1) grid = std::min(tp.nitems, want_grid);
+    const bool dot = p.dot_mode == 2;
+    if (dot && grid > p.dot_cap) return cudaErrorInvalidConfiguration;
+    const bool cf = p.cmpfirst != 0, q = p.has_q != 0;
+    const int nfwd = (p.s1[0] > 0) + (p.s1[1] > 0) + (p.s1[2] > 0);
+    const int arr = nfwd == 3 ? 0 : nfwd == 0 ? 1 : 2;
+#define W(CF, Q, D)                                                                                  \
+    (arr == 0 ? launch_rp<CF, Q, D, 0, NWC, NST>(tp, grid, s)                                        \
+              : arr == 1 ? launch_rp<CF, Q, D, 1, NWC, NST>(tp, grid, s) : launch_rp<CF, Q, D, 2, NWC, NST>(tp, grid, s))
+#define V(CF, Q) (dot ? W(CF, Q, true) : W(CF, Q, false))
+    if (cf) return q ? V(true, true) : V(true, false);
+    return q ? V(false, true) : V(false, false);
+#undef W
+#undef V
+}
+
+// diagonal-mass apply over local planes [kl_begin, kl_end) with the row-pair kernel
+cudaError_t launch_apply_rowpair(const ApplyParams &p, int kl_begin, int kl_end, cudaStream_t s) {
+    if (kl_end <= kl_begin) return cudaSuccess;
+    RowPairParams tp;
+    tp.a = p;
+    tp.wrapx = p.wrap[0];
+    tp.wrapy = p.wrap[1];
+    tp.kl_begin = kl_begin;
+    tp.kl_end = kl_end;
+    static const int dbg = env_int("FDFD_RP_DEBUG");
+    tp.dbg = dbg;
+    const int shape = (p.s1[0] * p.s1[0] == 1 && p.s1[1] * p.s1[1] == 1 && p.s1[2] * p.s1[2] == 1 && !p.halo_flag)
+                          ? rp_pick_shape(p, kl_begin, kl_end, &tp.nchunk) : -1;
+    switch (shape) {
+        case 0: return launch_rp_shape<RP_SHAPES[0].nwc, RP_SHAPES[0].nst>(tp, p, s);
+        case 1: return launch_rp_shape<RP_SHAPES[1].nwc, RP_SHAPES[1].nst>(tp, p, s);
+        case 2: return launch_rp_shape<RP_SHAPES[2].nwc, RP_SHAPES[2].nst>(tp, p, s);
+        default: return cudaErrorNotSupported;
+    }
+}
+
+}  // namespace fdfd

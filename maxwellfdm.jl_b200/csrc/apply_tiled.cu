@@ -760,13 +760,24 @@ cudaError_t launch_apply_tiled(const ApplyParams &p, int kl_begin, int kl_end, c
     if (kl_end <= kl_begin) return cudaSuccess;
     const bool full = p.has_off != 0 && p.has_mass != 0;
     cudaError_t e;
+    // diagonal mass parameter: the second-generation (persistent, warp-specialised) kernel unless FDFD_K1_GEN=1 asks
+    // for the first-generation tiled kernel (A/B timing, on-device cross-check)
+    static const bool gen1 = [] { const char *g = getenv("FDFD_K1_GEN"); return g && atoi(g) == 1; }();
+    const bool rowpair = !gen1 && !env_ty() && rowpair_supported(p, kl_begin, kl_end);
     if (!full) {
-        e = (env_ty() == 16) ? launch_tile<32, 16>(p, kl_begin, kl_end, s) : launch_tile<32, 8>(p, kl_begin, kl_end, s);
+        if (rowpair) e = launch_apply_rowpair(p, kl_begin, kl_end, s);
+        else e = (env_ty() == 16) ? launch_tile<32, 16>(p, kl_begin, kl_end, s) : launch_tile<32, 8>(p, kl_begin, kl_end, s);
         if (nlaunch) *nlaunch += 1;
     } else if (p.offmask && p.offmask_ty == 8) {
         // sparse off-diagonals (material interfaces only): diagonal kernel everywhere, then the off-diagonal part
         // of the mass operator is added on the flagged runs of this plane range (the operator is linear)
-        e = launch_tile<32, 8>(p, kl_begin, kl_end, s, true);
+        if (rowpair) {
+            ApplyParams pd = p;
+            pd.has_off = 0;
+            e = launch_apply_rowpair(pd, kl_begin, kl_end, s);
+        } else {
+            e = launch_tile<32, 8>(p, kl_begin, kl_end, s, true);
+        }
         if (e == cudaSuccess)
             e = launch_offdiag_correction(p, p.corr_list, p.corr_count, (p.Nx + 29) / 30, kl_begin, kl_end, s);
         if (nlaunch) *nlaunch += p.corr_count > 0 ? 2 : 1;

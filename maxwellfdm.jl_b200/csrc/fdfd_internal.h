@@ -57,6 +57,7 @@ struct ApplyParams {
     // [(kl+1)*Nx*Ny + j*Nx + i]
     const double2 *md[3];   // -w^2 * P_vv (null when the mass parameter is the identity: md_uniform = -w^2)
     double2 md_uniform;
+    const double2 *md_aos;  // cmp-first layout only: the three md arrays interleaved, element ((kl+1)*Nx*Ny + j*Nx + i)*3 + v
     const double2 *mo[6];   // -w^2 * P_vu, order (0,1),(0,2),(1,0),(1,2),(2,0),(2,1)
     const double2 *q[3];    // inverse of the middle diagonal parameter (mu^-1 for FT_EE)
     PlaneSet x;
@@ -148,6 +149,7 @@ struct Ctx {
     size_t coef_bytes = 0;
     CoefDev cf{}, ct{};              // forward operator / transposed operator
     double2 *mat_dev = nullptr;      // md[3], mo[6], q[3] ghosted slabs
+    double2 *md_aos = nullptr;       // interleaved copy of md[3] (cmp-first layout; row-pair kernel)
     size_t mat_bytes = 0;
     const double2 *md[3]{}, *mo[6]{}, *mo_t[6]{}, *q[3]{};
     bool has_mass = false;           // omega != 0
@@ -226,6 +228,10 @@ cudaError_t launch_apply_naive(const ApplyParams &p, cudaStream_t s);
 // returns cudaErrorNotSupported when the tiled kernel does not cover this configuration
 cudaError_t launch_apply_tiled(const ApplyParams &p, int kl_begin, int kl_end, cudaStream_t s, int *nlaunch);
 bool tiled_supported(const ApplyParams &p);
+// apply_rowpair.cu: second-generation K1 (persistent, warp-specialised; diagonal mass parameter) over local planes
+// [kl_begin, kl_end); cudaErrorNotSupported when the configuration is outside its range
+bool rowpair_supported(const ApplyParams &p, int kl_begin, int kl_end);
+cudaError_t launch_apply_rowpair(const ApplyParams &p, int kl_begin, int kl_end, cudaStream_t s);
 // number of z-chunks per tile column the main kernel of launch_apply_tiled(p, 0, nzl) will use
 int tiled_plan_nchunk(const ApplyParams &p);
 cudaError_t tiled_build_offmask(const ApplyParams &p, unsigned char **mask, int *ty_used, double *frac, int4 **corr_list,
@@ -239,6 +245,13 @@ cudaError_t launch_curl2(const ApplyParams &p, const double2 *je, double2 beta, 
                          cudaStream_t s, int divide_by_md = 0);
 // out_w = mean along w of component w (create_Mcs); which_other = 0: in-average tables (mi), 1: mh tables
 cudaError_t launch_interp(const ApplyParams &p, int which_other, cudaStream_t s);
+
+// tmap.cpp -----------------------------------------------------------------------------------------
+// 3-D tiled tensor map over 8-byte elements (cuTensorMapEncodeTiled through the runtime's driver entry point);
+// false when the driver does not offer it or rejects the geometry - callers then use 1-D bulk copies
+struct TmaMap;
+bool tmap_encode_f64_3d(TmaMap *out, const void *base, const uint64_t dims[3], const uint64_t strides_bytes[2],
+                        const uint32_t box[3]);
 
 // krylov.cu ----------------------------------------------------------------------------------------
 int krylov_solve(Ctx *c, int method, const double2 *b, double2 *x, double rtol, int maxit, int check_every,

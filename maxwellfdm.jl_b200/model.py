@@ -18,6 +18,8 @@ A, b = create_linsys(EE, ω, Ps, Cs, js)`, then `e, info = solve(A, b)` instead 
 Geometry rasterisation + subpixel smoothing (calc_matparams!, full.jl:16-70): shapes.py / csrc/matparams.cu; models
 without objects may fill mdl.eps_arr / mdl.mu_arr directly.
 """
+import itertools
+
 import numpy as np
 
 from .grid import EE, HH, PRIM, DUAL, Grid, PMLParam, create_stretched_dl, ft2gt
@@ -172,8 +174,14 @@ class ParamOp:
     averaging inputs.  Here it stays a description - the GPU kernels apply it matrix-free.  Holds a REFERENCE to the
     model's array (no copy of a multi-GB tensor), so build the operator before editing the model again."""
 
+    _tokens = itertools.count(1)
+
     def __init__(self, kind, arr, geom):
         self.kind, self.arr, self.geom = kind, arr, geom
+        # every create_paramops call yields new material operators (the reference builds new sparse matrices,
+        # model.jl:152-155): operators cached on a shared Cs are keyed by this token, so Ps from a later call - after
+        # the objects or the arrays changed - never resolve to a GPU operator that still holds the old material
+        self.token = next(ParamOp._tokens)
 
 
 class CurlOp:
@@ -243,10 +251,12 @@ def _build(ft, w, Ps, Cs, device=-1, rank=0, nranks=1, kernel=0, weighted_out_av
     g = Ce.geom
     if not g.same(Pe.geom):
         raise ValueError("create_paramops and create_curls were called on different model settings")
-    key = (ft, complex(w), device, rank, nranks, kernel, weighted_out_avg)
+    key = (ft, complex(w), device, rank, nranks, kernel, weighted_out_avg, Pe.token, Pm.token)
     A = g.ops.get(key)
     if A is not None and not A.closed:
         return A
+    for k in [k for k in g.ops if k[:7] == key[:7]]:     # same settings, older material: no longer reachable through
+        del g.ops[k]                                     # the cache (the caller's own reference keeps it alive)
     if len(g.N) < 3:
         # ModelTE / ModelTM / ModelTEM: the 3-D handle that is one periodic cell thick along the missing axes
         from .reduced import ReducedOperator, embed_geometry, embed_param
@@ -326,7 +336,7 @@ def _post_operator(w, third, fourth, **kw):
     Ps, Cs = _as_ops(third, fourth)
     g = Cs[0].geom
     for key, A in g.ops.items():           # reuse the operator create_A built for this ω (either formulation works)
-        if key[1] == complex(w) and not A.closed:
+        if key[1] == complex(w) and key[7:] == (Ps[0].token, Ps[1].token) and not A.closed:
             return A
     return _build(EE, w, Ps, Cs, **kw)
 

@@ -72,7 +72,7 @@ void fill_nan(void *p, size_t bytes) {
 
 struct BulkOp {
     void *dst;
-    const void *src;
+    const void *src;   // nullptr: zero fill (out-of-range part of a tensor-map box)
     uint32_t bytes;
     uint64_t *bar;   // g2s only
 };
@@ -153,7 +153,8 @@ void mbar_try_complete(MBar *m) {
 }
 
 void perform_load(const BulkOp &op) {
-    std::memcpy(op.dst, op.src, op.bytes);
+    if (op.src) std::memcpy(op.dst, op.src, op.bytes);
+    else std::memset(op.dst, 0, op.bytes);
     MBar *m = reinterpret_cast<MBar *>(op.bar);
     m->tx -= (int32_t)op.bytes;
     mbar_try_complete(m);
@@ -383,6 +384,18 @@ uint64_t shfl_xor_bits(uint64_t v, int lane_mask) {
     return r;
 }
 
+uint64_t shfl_idx_bits(uint64_t v, int src) {
+    Block *b = blk;
+    const int lin = self()->linear, wid = lin >> 5, lane = lin & 31;
+    const int nl = std::min(32, b->nthreads - wid * 32);
+    Warp &w = b->warps[wid];
+    w.slot[lane] = v;
+    warp_barrier(w, nl);
+    const uint64_t r = (src >= 0 && src < nl) ? w.slot[src] : v;
+    warp_barrier(w, nl);
+    return r;
+}
+
 // ---- mbarrier / bulk copies --------------------------------------------------------------------------------------
 void mbar_init(uint64_t *bar, uint32_t count) {
     check_smem_range(bar, 8, "mbarrier.init");
@@ -409,6 +422,56 @@ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
     const BulkOp op{dst, src, bytes, bar};
     if (env_lazy()) blk->pending_loads.push_back(op);
     else perform_load(op);
+}
+// tensor-map box load: row by row, the in-range run copied, the rest zero-filled; every piece counts on the mbarrier
+void tma_load_3d(void *dst, const unsigned long long *map, int c0, int c1, int c2, uint64_t *bar) {
+    const unsigned char *base = reinterpret_cast<const unsigned char *>(map[0]);
+    const long d0 = (long)map[1], d1 = (long)map[2], d2 = (long)map[3];
+    const long s1 = (long)map[4], s2 = (long)map[5];
+    const long b0 = (long)map[6], b1 = (long)map[7], b2 = (long)map[8];
+    if (!base || b0 <= 0) die("tensor-map load through an unencoded map");
+    if (((uintptr_t)dst & 127) != 0) die("tensor-map load: shared destination not 128-byte aligned");
+    check_smem_range(dst, (uint32_t)(b0 * b1 * b2 * 8), "cp.async.bulk.tensor global->shared");
+    unsigned char *out = static_cast<unsigned char *>(dst);
+    auto push = [&](void *d, const void *s, long n) {
+        if (n <= 0) return;
+        const BulkOp op{d, s, (uint32_t)n, bar};
+        if (env_lazy()) blk->pending_loads.push_back(op);
+        else perform_load(op);
+    };
+    for (long z = 0; z < b2; ++z)
+        for (long y = 0; y < b1; ++y) {
+            unsigned char *row = out + ((z * b1 + y) * b0) * 8;
+            const long gz = c2 + z, gy = c1 + y;
+            if (gz < 0 || gz >= d2 || gy < 0 || gy >= d1) { push(row, nullptr, b0 * 8); continue; }
+            const long lo = std::max<long>(c0, 0), hi = std::min<long>(c0 + b0, d0);
+            if (hi <= lo) { push(row, nullptr, b0 * 8); continue; }
+            push(row, nullptr, (lo - c0) * 8);
+            push(row + (lo - c0) * 8, base + gz * s2 + gy * s1 + lo * 8, (hi - lo) * 8);
+            push(row + (hi - c0) * 8, nullptr, (c0 + b0 - hi) * 8);
+        }
+}
+// tensor-map box store: the in-range part of every row, as one bulk-group member per piece
+void tma_store_3d(const unsigned long long *map, int c0, int c1, int c2, const void *src) {
+    unsigned char *base = reinterpret_cast<unsigned char *>(map[0]);
+    const long d0 = (long)map[1], d1 = (long)map[2], d2 = (long)map[3];
+    const long s1 = (long)map[4], s2 = (long)map[5];
+    const long b0 = (long)map[6], b1 = (long)map[7], b2 = (long)map[8];
+    if (!base || b0 <= 0) die("tensor-map store through an unencoded map");
+    if (((uintptr_t)src & 127) != 0) die("tensor-map store: shared source not 128-byte aligned");
+    check_smem_range(src, (uint32_t)(b0 * b1 * b2 * 8), "cp.async.bulk.tensor shared->global");
+    const unsigned char *in = static_cast<const unsigned char *>(src);
+    for (long z = 0; z < b2; ++z)
+        for (long y = 0; y < b1; ++y) {
+            const long gz = c2 + z, gy = c1 + y;
+            if (gz < 0 || gz >= d2 || gy < 0 || gy >= d1) continue;
+            const long lo = std::max<long>(c0, 0), hi = std::min<long>(c0 + b0, d0);
+            if (hi <= lo) continue;
+            void *d = base + gz * s2 + gy * s1 + lo * 8;
+            const void *s = in + ((z * b1 + y) * b0 + (lo - c0)) * 8;
+            if (env_lazy()) self()->open_stores.push_back(BulkOp{d, s, (uint32_t)((hi - lo) * 8), nullptr});
+            else std::memcpy(d, s, (hi - lo) * 8);
+        }
 }
 void bulk_s2g(void *dst, const void *src, uint32_t bytes) {
     check_bulk_args(src, dst, bytes, "cp.async.bulk shared->global");
@@ -501,6 +564,11 @@ cudaError_t cudaMemsetAsync(void *p, int v, size_t n, cudaStream_t) { std::memse
 cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
 cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 cudaError_t cudaGetDevice(int *d) { *d = 0; return cudaSuccess; }
+cudaError_t cudaDeviceGetAttribute(int *v, cudaDeviceAttr, int) {   // FDFD_EMU_SMS: persistent grids of a few CTAs
+    const char *e = getenv("FDFD_EMU_SMS");
+    *v = e ? atoi(e) : 148;
+    return cudaSuccess;
+}
 cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
 cudaError_t cudaDeviceGetStreamPriorityRange(int *lo, int *hi) { *lo = 0; *hi = 0; return cudaSuccess; }
 static cudaError_t new_stream(cudaStream_t *s) { *s = reinterpret_cast<cudaStream_t>(malloc(8)); return cudaSuccess; }

@@ -57,6 +57,7 @@ void syncthreads();
 int syncthreads_or(int v);
 void syncwarp();
 uint64_t shfl_xor_bits(uint64_t v, int lane_mask);
+uint64_t shfl_idx_bits(uint64_t v, int src_lane);   // src_lane outside the warp: own value
 int lane_id();
 bool lazy_async();            // FDFD_EMU_ASYNC=lazy: bulk copies complete at the latest legal moment
 // bulk-copy engine stand-in (ptx_sm100.cuh of the shim)
@@ -65,6 +66,9 @@ void bulk_s2g(void *dst, const void *src, uint32_t bytes);
 void bulk_commit();
 void bulk_wait_read0();
 void bulk_wait0();
+// tensor-map stand-in (3-D, 8-byte elements): image = {base, dim0..2, stride1..2 (bytes), box0..2}
+void tma_load_3d(void *dst, const unsigned long long *map, int c0, int c1, int c2, uint64_t *bar);
+void tma_store_3d(const unsigned long long *map, int c0, int c1, int c2, const void *src);
 void mbar_init(uint64_t *bar, uint32_t count);
 void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes);
 void mbar_wait(uint64_t *bar, uint32_t parity);
@@ -90,6 +94,19 @@ inline T __shfl_xor_sync(unsigned, T v, int lane_mask) {
     std::memcpy(&r, &b, sizeof(T));
     return r;
 }
+template <class T>
+inline T emu_shfl_idx(T v, int src) {
+    static_assert(sizeof(T) <= 8, "shuffle of at most 64 bits");
+    uint64_t b = 0;
+    std::memcpy(&b, &v, sizeof(T));
+    b = emu::shfl_idx_bits(b, src);
+    T r;
+    std::memcpy(&r, &b, sizeof(T));
+    return r;
+}
+template <class T> inline T __shfl_up_sync(unsigned, T v, unsigned d) { const int l = emu::lane_id(); return emu_shfl_idx(v, l - (int)d < 0 ? l : l - (int)d); }
+template <class T> inline T __shfl_down_sync(unsigned, T v, unsigned d) { const int l = emu::lane_id(); return emu_shfl_idx(v, l + (int)d > 31 ? l : l + (int)d); }
+template <class T> inline T __shfl_sync(unsigned, T v, int src) { return emu_shfl_idx(v, src & 31); }
 template <class T> inline T __ldg(const T *p) { return *p; }
 template <class T> inline T __ldcg(const T *p) { return *p; }
 inline unsigned atomicAdd(unsigned *p, unsigned v) { unsigned o = *p; *p = o + v; return o; }
@@ -135,6 +152,8 @@ cudaError_t cudaMemsetAsync(void *p, int v, size_t n, cudaStream_t s = nullptr);
 cudaError_t cudaGetDeviceCount(int *n);
 cudaError_t cudaSetDevice(int d);
 cudaError_t cudaGetDevice(int *d);
+enum cudaDeviceAttr { cudaDevAttrMultiProcessorCount = 16 };
+cudaError_t cudaDeviceGetAttribute(int *v, cudaDeviceAttr a, int dev);
 cudaError_t cudaDeviceSynchronize();
 cudaError_t cudaDeviceGetStreamPriorityRange(int *lo, int *hi);
 cudaError_t cudaStreamCreate(cudaStream_t *s);

@@ -16,8 +16,13 @@ namespace fdfd {
 inline uint32_t smem_u32(const void *p) { return (uint32_t)(uintptr_t)p; }
 inline void mbar_init(uint64_t *bar, uint32_t count) { emu::mbar_init(bar, count); }
 inline void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) { emu::mbar_arrive_expect_tx(bar, bytes); }
+inline void mbar_arrive(uint64_t *bar) { emu::mbar_arrive_expect_tx(bar, 0); }
 inline void mbar_wait(uint64_t *bar, uint32_t parity) { emu::mbar_wait(bar, parity); }
 inline void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) { emu::bulk_g2s(dst, src, bytes, bar); }
+// tensor-map stand-in: the encode helper of csrc/tmap.cpp fills the image with plain fields under FDFD_EMU
+struct alignas(64) TmaMap { unsigned long long opaque[16]; };
+inline void tma_load_3d(void *dst, const TmaMap *m, int c0, int c1, int c2, uint64_t *bar) { emu::tma_load_3d(dst, m->opaque, c0, c1, c2, bar); }
+inline void tma_store_3d(const TmaMap *m, int c0, int c1, int c2, const void *src) { emu::tma_store_3d(m->opaque, c0, c1, c2, src); }
 inline void fence_barrier_init() {}
 inline void bulk_s2g(void *dst, const void *src, uint32_t bytes) { emu::bulk_s2g(dst, src, bytes); }
 inline void bulk_commit() { emu::bulk_commit(); }

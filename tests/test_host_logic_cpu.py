@@ -149,6 +149,41 @@ def test_reference_call_sequence_descriptors():
         fb.create_A(fb.EE, 1.3, Ps, fb.create_curls(mdl), device=-2)
 
 
+def test_create_A_follows_new_paramops_on_shared_curls():
+    """The reference keeps create_paramops and create_curls apart so that Cs can be reused when only the material
+    changes (model.jl:141-175).  Ps from a later create_paramops call must give an operator with the NEW material,
+    never the operator cached for the earlier Ps (the cache was keyed on geometry only)."""
+    from oracle.grid import Grid as OGrid, create_stretched_dls as o_sdls, EE as OEE
+    from oracle import operators as op
+    N = (4, 5, 3)
+    lp = tuple(np.arange(n + 1.0) for n in N)
+    mdl = fb.ModelFull(fb.Grid(lp, (True, True, True)))
+    for v in range(3):
+        mdl.eps_arr[..., v, v] = 2.0
+        mdl.mu_arr[..., v, v] = 1.0
+    Cs = fb.create_curls(mdl)
+    Ps1 = fb.create_paramops(mdl)
+    A1 = fb.create_A(fb.EE, 1.1, Ps1, Cs, device=-2)
+    assert fb.create_A(fb.EE, 1.1, Ps1, Cs, device=-2) is A1
+    nz1 = A1.export_pattern()[2]
+    for v in range(3):
+        mdl.eps_arr[..., v, v] = 5.0                      # the material changes, the curls do not
+    Ps2 = fb.create_paramops(mdl)
+    A2 = fb.create_A(fb.EE, 1.1, Ps2, Cs, device=-2)
+    assert A2 is not A1
+    nz2 = A2.export_pattern()[2]
+    og = OGrid(lp, (True, True, True))
+    sdl_e, sdl_m, sei, smi = o_sdls(0.0, og, ((0, 0, 0), (0, 0, 0)))
+    ph = fb.create_e_mikL(mdl)
+    Ce, Cm = op.create_curls(sei, smi, (OEE,) * 3, og.isbloch, ph)
+    Pe, Pm = op.create_paramops(mdl.eps_arr, mdl.mu_arr, sdl_e, sdl_m, sei, smi, (OEE,) * 3, og.isbloch, ph)
+    ref = op.create_A(OEE, 1.1, Pe, Pm, Ce, Cm)
+    assert np.abs(nz2 - ref.nzval).max() <= 1e-13 * np.abs(ref.nzval).max()
+    assert np.abs(nz1 - nz2).max() > 1.0                  # the first operator really held the old material
+    assert fb.create_A(fb.EE, 1.1, Ps2, Cs, device=-2) is A2
+    A1.close(); A2.close()
+
+
 def test_reduced_models_layout_and_sources():
     """ModelTE / ModelTM / ModelTEM (te.jl:4-14, tm.jl:4-14, tem.jl:4-13): array shapes, DOF order with Kf components
     (model.jl:75-83), sources on K-dimensional grids (isfield˔shp default: orthogonal complement -> true) against the
