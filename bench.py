@@ -1,23 +1,28 @@
 #!/usr/bin/env python
-"""bench.py - FDFD operator throughput (GDOF/s) on B200, BASELINE.json metric.
+"""bench.py - FDFD operator throughput (GDOF/s) and Krylov iterations/s on B200, BASELINE.json metric.
 
-A "step" is ONE application y = A x of the matrix-free operator A = curl mu^-1 curl - w^2 eps on the
-workload of BASELINE.json configs[1] (200^3 Si strip waveguide, full 3x3 eps, 10-cell PML); with N GPUs
-the grid is 200 x 200 x (200 N) split into N z-slabs (weak scaling, one NCCL halo exchange per apply).
-    value     GDOF/s, x / eps resident in HBM, CUDA events on the library's stream, max over ranks
-    e2e       the same metric through the C-ABI call with HOST (pinned) buffers: H2D of x and D2H of y
-              inside the timed region
-    roofline  algorithmic bytes (80 B/DOF full-tensor, 48 B/DOF diagonal) / apply time
-              against the measured HBM copy bandwidth (MEASURED_PEAKS.json)
-    cpu_baseline   the oracle's Julia-style single-thread CSC mul! on a bounded sample of the workload
---impl reference times the reference's CPU path stand-in (CSC assembled by the oracle restatement,
-product on all host cores) - the reference itself is Julia and cannot run here.
+A "step" is ONE application y = A x of the matrix-free operator A = curl mu^-1 curl - w^2 eps on the workload of
+BASELINE.json configs[1] (C2: 200^3 Si strip waveguide, full 3x3 eps, 10-cell PML); with N GPUs the grid is
+200 x 200 x (200 N) split into N z-slabs (weak scaling, one NCCL halo exchange per apply).
+    value        GDOF/s, x / eps resident in HBM, CUDA events on the library's stream, max over ranks
+    e2e          the same metric through the C-ABI call with HOST (pinned) buffers: H2D of x and D2H of y inside the
+                 timed region;  e2e_solve: fdfd_solve(FDFD_HOST), b in / x out, fixed 200 BiCGSTAB iterations
+    roofline     algorithmic bytes per DOF (x 16 + y 16 + eps_diag 16, or 8 when the diagonal mass entries are real and
+                 travel as doubles; + the off-diagonal streams on the blocks that hold any) / apply time against the
+                 measured HBM copy bandwidth (MEASURED_PEAKS.json)
+    parity       UNTIMED check before the timed region, at every N: the N-slab operator and 5 BiCGSTAB iterations on
+                 a reduced copy of the workload against the CPU oracle (oracle/ is the checker, never the thing timed)
+    configs      (N = 1) the other BASELINE configurations: C1, C3, C4 512^3, C5 unit slab, dense off-diagonals, HH
+    scale_c5 / scale_c4   C5 weak scaling (1024 x 1024 x 96 per GPU) and C4 strong scaling (512^3 / N) at this N
+    halo         (N > 1) the halo exchange by itself: bytes, microseconds, fraction of the NVLink peer bandwidth
+    cpu_baseline the oracle's Julia-style single-thread CSC mul! on a bounded sample of the workload
+--impl reference times the reference's CPU path stand-in (CSC assembled by the oracle restatement; product and an
+unpreconditioned BiCGSTAB on all host cores) - the reference itself is Julia and cannot run here.
 """
 import argparse
 import json
 import os
 import statistics
-import subprocess
 import sys
 import threading
 import time
@@ -29,6 +34,7 @@ METRIC = "fdfd_operator_apply_throughput"
 UNIT = "GDOF/s"
 PER_GPU_N = (200, 200, 200)
 SAMPLE_PLANES = 8
+NVLINK_PEER_GBS = 770.0        # measured peer copy per direction on this pool (B200_PROFILING.md); nominal 900
 
 
 def peaks():
@@ -40,44 +46,67 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """SM clock and throttle reasons sampled through NVML every ~2 ms while the timed region runs
-    (an nvidia-smi subprocess is too slow for a region of a few tens of ms)."""
+    """SM clock and throttle reasons sampled through NVML every ~2 ms while the timed region runs (an nvidia-smi
+    subprocess is too slow for a region of a few ms).  start_and_wait() returns once the first sample exists, and a
+    sample is taken synchronously at stop, so even a 5 ms region is bracketed."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.stop_flag, self.err = index, [], False, None
         self.max_mhz = None
+        self.ready = threading.Event()
+        self._h = self._nv = self._reasons = None
+
+    def _open(self):
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(self.index)
+        try:       # honour CUDA_VISIBLE_DEVICES-style remapping by matching the torch device's UUID when possible
+            import torch
+            uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            for i in range(nv.nvmlDeviceGetCount()):
+                hh = nv.nvmlDeviceGetHandleByIndex(i)
+                u = nv.nvmlDeviceGetUUID(hh)
+                u = u.decode() if isinstance(u, bytes) else u
+                if uuid in u:
+                    h = hh
+                    break
+        except Exception:
+            pass
+        self._nv, self._h = nv, h
+        self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        self._reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            nv.nvmlDeviceGetCurrentClocksThrottleReasons
+
+    def _sample(self):
+        nv, h = self._nv, self._h
+        self.samples.append((float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), int(self._reasons(h))))
 
     def run(self):
         try:
-            import pynvml as nv
-            nv.nvmlInit()
-            # honour CUDA_VISIBLE_DEVICES-style remapping by matching the torch device's UUID when possible
-            h = nv.nvmlDeviceGetHandleByIndex(self.index)
-            try:
-                import torch
-                uuid = str(torch.cuda.get_device_properties(self.index).uuid)
-                for i in range(nv.nvmlDeviceGetCount()):
-                    hh = nv.nvmlDeviceGetHandleByIndex(i)
-                    u = nv.nvmlDeviceGetUUID(hh)
-                    u = u.decode() if isinstance(u, bytes) else u
-                    if uuid in u:
-                        h = hh
-                        break
-            except Exception:
-                pass
-            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
-            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
-                nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            self._open()
+            self._sample()
+            self.ready.set()
             while not self.stop_flag:
-                self.samples.append((float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), int(get_reasons(h))))
+                self._sample()
                 time.sleep(0.002)
         except Exception as e:  # noqa: BLE001
             self.err = repr(e)
+            self.ready.set()
+
+    def start_and_wait(self):
+        self.start()
+        self.ready.wait(timeout=10)
+        return self
 
     def summary(self):
         self.stop_flag = True
         self.join(timeout=2)
+        try:
+            if self._h is not None:
+                self._sample()
+        except Exception:
+            pass
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable: " + str(self.err)]}
         bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
@@ -89,6 +118,9 @@ class ClockSampler(threading.Thread):
                 "reasons": [n for n, b in bits.items() if allr & b], "samples": len(self.samples)}
 
 
+# ---------------------------------------------------------------------------------------------------
+# CPU legs (oracle = checker / reported baseline; never part of the product path)
+# ---------------------------------------------------------------------------------------------------
 def sample_workload():
     """Bounded sample of the C2 workload for the CPU legs: the SAMPLE_PLANES z-planes through the core."""
     import workloads
@@ -150,23 +182,188 @@ def run_reference(args):
     y = np.empty_like(x)
     for _ in range(max(args.warmup, 1)):
         R.mul(x, y)
-    t0 = time.perf_counter()
+    ts = []
     for _ in range(args.steps):
+        t0 = time.perf_counter()
         R.mul(x, y)
-    dt = (time.perf_counter() - t0) / args.steps
+        ts.append(time.perf_counter() - t0)
+    dt = sum(ts) / len(ts)
     cores = cb.num_threads()
     val = n / dt / 1e9
+    # the solve half of the metric: unpreconditioned BiCGSTAB on the same CSC matrix, all
+    # host cores, fixed iteration count (no convergence exit), as the GPU arm's krylov block
+    kit = max(10, min(args.krylov_iters, 50))
+    b = R.mul(x, np.empty_like(x)).copy()
+    xs = np.zeros(n, np.complex128)
+    R.bicgstab(b, xs, 3)                      # warm-up
+    xs[:] = 0
+    t0 = time.perf_counter()
+    relres = R.bicgstab(b, xs, kit)
+    tk = time.perf_counter() - t0
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "ms_per_step_min": min(ts) * 1e3,
+            "ms_per_step_median": statistics.median(ts) * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "c128 (complex fp64)", "data": "synthetic",
             "config": {"workload": "C2 Si strip waveguide 200x200x200, full 3x3 eps, 10-cell PML",
                        "sample": desc, "l2": "matrix stream larger than LLC"},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": desc + "; OpenMP CSR product of the oracle-assembled matrix (stand-in for the "
                                               "Julia SparseMatrixCSC mul!, which cannot run here: no julia binary)"},
+            "krylov": {"method": "bicgstab", "iters": kit, "iter_per_s": kit / tk, "relres_after": relres,
+                       "dof": n, "gdof_iter_per_s": n * kit / tk / 1e9,
+                       "note": "unpreconditioned BiCGSTAB on the sampled CSC matrix, OpenMP on all host cores; compare "
+                               "per DOF: iterations/s scale inversely with the DOF count"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------
+# GPU legs
+# ---------------------------------------------------------------------------------------------------
+class Ctx:
+    pass
+
+
+def rand_vec(n, gen):
+    import torch
+    return torch.randn(n, 2, device="cuda", dtype=torch.float64, generator=gen).view(torch.complex128).reshape(-1)
+
+
+def max_over_ranks(v, world):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([float(v)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def barrier(world):
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def build_operator(w, local, rank, world, **kw):
+    import torch.distributed as dist
+    import workloads
+    import maxwellfdm_jl_b200 as fb
+    if "shapes" in w:
+        A = None
+        if world > 1:
+            # objects are rasterised on the first use, which needs the communicator (ghost planes): create, connect, set
+            A = fb.FdfdOperator(w["N"], w["isbloch"], w["sdl_e"], w["sdl_m"], w["omega"], None, None, w["e_mikL"],
+                                device=local, rank=rank, nranks=world, **kw)
+            uid = [fb.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            A.comm_init(uid[0])
+            A.set_eps_objects(w["grid"].lg_prim, w["shapes"], w["pinds"], w["params"])
+            return A
+        return workloads.make_operator_from_objects(w, device=local, **kw)
+    A = workloads.make_operator(w, device=local, rank=rank, nranks=world, **kw)
+    if world > 1:
+        uid = [fb.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        A.comm_init(uid[0])
+    return A
+
+
+def bytes_per_dof(A, w):
+    """bytes one apply must move per DOF on this handle (x 16 + y 16 + diagonal mass 16 or 8 + off-diagonal streams on
+    the (tile, plane) blocks that hold any: 32, or 16 when the tensor is symmetric and stored once)"""
+    off = A.offdiag_fraction if w.get("full_eps") else 0.0
+    sym = bool(w.get("full_eps") and A.offdiag_symmetric)
+    return 32.0 + A.mass_bytes_per_dof + (16 if sym else 32) * off, off, sym
+
+
+def measure_config(name, w, local, rank, world, steps, kry_iters, gen, extra=None, **opkw):
+    """device-resident apply throughput (+ min / median over batches), BiCGSTAB iterations/s for one workload"""
+    import torch
+    t0 = time.perf_counter()
+    A = build_operator(w, local, rank, world, **opkw)
+    n = A.n
+    x = rand_vec(n, gen)
+    y = torch.empty_like(x)
+    A.bench_apply(x, y, warmup=10 if steps >= 50 else 3, iters=1)
+    setup_s = time.perf_counter() - t0
+    barrier(world)
+    nb = 10
+    per = max(1, steps // nb)
+    batch = []
+    for _ in range(nb):
+        ms, _ = A.bench_apply(x, y, warmup=0, iters=per)
+        batch.append(max_over_ranks(ms / per, world))
+    ms_med, ms_min = statistics.median(batch), min(batch)
+    bpd, off, sym = bytes_per_dof(A, w)
+    peak, _ = peaks()
+    n_tot = 3 * w["N"][0] * w["N"][1] * w["N"][2]
+    out = {"config": name, "grid": list(w["N"]), "dof": n_tot, "n_gpus": world, "applies_timed": nb * per,
+           "ms_per_apply": ms_med, "ms_per_apply_min": ms_min, "gdof_s": n_tot / ms_med / 1e6,
+           "gdof_s_best": n_tot / ms_min / 1e6, "bytes_per_dof": bpd, "offdiag_block_fraction": off,
+           "offdiag_symmetric": sym, "hbm_frac": bpd * (n_tot / world) / (ms_med * 1e-3) / 1e9 / peak, "setup_s": setup_s}
+    if kry_iters:
+        try:
+            b = rand_vec(n, gen)
+            xs = torch.zeros_like(b)
+            barrier(world)
+            ms_k = max_over_ranks(A.bench_solve(b, xs, "bicgstab", warmup=2, iters=kry_iters), world)
+            out["bicgstab_it_s"] = kry_iters / (ms_k * 1e-3)
+            out["bicgstab_hbm_frac"] = (2 * bpd + 240) * (n_tot / world) * out["bicgstab_it_s"] / 1e9 / peak
+            del b, xs
+        except Exception as e:  # noqa: BLE001
+            out["bicgstab_error"] = f"{type(e).__name__}: {e}"
+    if extra:
+        out.update(extra(A, x))
+    A.close()
+    del x, y
+    torch.cuda.empty_cache()
+    return out
+
+
+def parity_block(local, rank, world):
+    """UNTIMED correctness check at this N (oracle = checker): a reduced copy of the C2 workload (full 3x3 eps with
+    off-diagonals, PML) on world z-slabs - (a) y = A x on this rank's planes against the oracle's matrix-free numpy
+    apply on the global grid, (b) five BiCGSTAB iterations against a textbook iteration on the oracle operator."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import workloads
+    import maxwellfdm_jl_b200 as fb
+    from oracle.matfree import MatFreeOperator
+    N = (46, 40, 12 * world)
+    wg = workloads.c2_waveguide(N, 0, N[2], npml=4)                     # global arrays for the oracle
+    k0, k1 = fb.partition(N[2], world, rank)
+    w = dict(wg, eps=np.ascontiguousarray(wg["eps"][:, :, k0:k1]), k0=k0, k1=k1)
+    A = build_operator(w, local, rank, world)
+    rng = np.random.default_rng(20261018)
+    nz = N[0] * N[1] * 3
+    xg = rng.standard_normal(nz * N[2]) + 1j * rng.standard_normal(nz * N[2])
+    O = MatFreeOperator(0, wg["omega"], wg["eps"], None, wg["sdl_e"], wg["sdl_m"], (0, 0, 0), wg["isbloch"], wg["e_mikL"])
+    yg = O.apply(xg)
+    sl = slice(nz * k0, nz * k1)
+    yl = (A @ torch.from_numpy(xg[sl].copy()).cuda()).cpu().numpy()
+    num, den = np.linalg.norm(yl - yg[sl]) ** 2, np.linalg.norm(yg[sl]) ** 2
+    # textbook BiCGSTAB (5 iterations, x0 = 0) on the oracle operator
+    bg = O.apply(rng.standard_normal(xg.size) + 1j * rng.standard_normal(xg.size))
+    xr = np.zeros_like(bg); r = bg.copy(); rh = r.copy(); rho = alpha = om = 1.0 + 0j; v = np.zeros_like(bg); p = np.zeros_like(bg)
+    for _ in range(5):
+        rho1 = np.vdot(rh, r); beta = (rho1 / rho) * (alpha / om); rho = rho1
+        p = r + beta * (p - om * v); v = O.apply(p); alpha = rho / np.vdot(rh, v)
+        s = r - alpha * v; t = O.apply(s); om = np.vdot(t, s) / np.vdot(t, t)
+        xr = xr + alpha * p + om * s; r = s - om * t
+    xs, _ = A.solve(torch.from_numpy(bg[sl].copy()).cuda(), rtol=1e-300, maxit=5, check_every=1)
+    xs = xs.cpu().numpy()
+    num2, den2 = np.linalg.norm(xs - xr[sl]) ** 2, np.linalg.norm(xr[sl]) ** 2
+    A.close()
+    t = torch.tensor([num, den, num2, den2], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t)
+    num, den, num2, den2 = (float(v) for v in t.tolist())
+    return {"grid": list(N), "n_slabs": world, "apply_rel_err": (num / den) ** 0.5, "traj_rel_err": (num2 / den2) ** 0.5,
+            "checker": "oracle/matfree.py on the global grid (untimed)", "tolerance": {"apply": 1e-12, "trajectory": 1e-9}}
 
 
 def main():
@@ -177,9 +374,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--krylov-iters", type=int, default=200)   # fixed 200 iterations, set-up included
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-configs", action="store_true", help="skip the per-configuration block (N = 1)")
+    ap.add_argument("--no-scale", action="store_true", help="skip the C5 weak / C4 strong scaling blocks")
     ap.add_argument("--diag", action="store_true", help="diagonal-eps variant of the workload (48 B/DOF)")
     ap.add_argument("--dense-off", action="store_true",
-                    help="variant with non-zero off-diagonal eps in EVERY cell (80 B/DOF: dense full-tensor kernel path)")
+                    help="variant with non-zero off-diagonal eps in EVERY cell (dense full-tensor kernel path)")
     ap.add_argument("--n", type=int, nargs=3, default=None, help="override the per-GPU grid (debug)")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -202,6 +401,14 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    gen = torch.Generator(device="cuda").manual_seed(20261017 + rank)
+    peak, peak_src = peaks()
+
+    # ---- untimed parity check at this N (oracle as the checker) ---------------------------------------------
+    try:
+        parity = parity_block(local, rank, world)
+    except Exception as e:  # noqa: BLE001   (reported, never hidden; the timed numbers below still stand on their own)
+        parity = {"error": f"{type(e).__name__}: {e}"}
 
     per = tuple(args.n) if args.n else PER_GPU_N
     N = (per[0], per[1], per[2] * world)
@@ -214,43 +421,46 @@ def main():
                     w["eps"][..., v, u] = 0
         w["full_eps"] = False
     if args.dense_off:
-        rng = np.random.default_rng(7 + rank)
-        for (v, u) in ((0, 1), (0, 2), (1, 2)):
-            pert = 0.05 * (rng.random(w["eps"].shape[:3]) - 0.5)
-            w["eps"][..., v, u] = pert
-            w["eps"][..., u, v] = pert
-    A = workloads.make_operator(w, device=local, rank=rank, nranks=world)
-    if world > 1:
-        uid = [fb.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        A.comm_init(uid[0])
+        workloads.make_dense_offdiag(w, seed=7 + rank)
+    A = build_operator(w, local, rank, world)
     n_loc = A.n
     n_tot = 3 * N[0] * N[1] * N[2]
-    g = torch.Generator(device="cuda").manual_seed(20261017 + rank)
-    x = torch.randn(n_loc, 2, device="cuda", dtype=torch.float64, generator=g).view(torch.complex128).reshape(-1)
+    x = rand_vec(n_loc, gen)
     y = torch.empty_like(x)
     torch.cuda.synchronize()
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     # ---- device-resident operator throughput ------------------------------------------------
-    A.bench_apply(x, y, warmup=args.warmup, iters=1)
-    sampler = ClockSampler(local)
-    sampler.start()
-    barrier()
+    A.bench_apply(x, y, warmup=max(args.warmup, 10), iters=1)
+    sampler = ClockSampler(local).start_and_wait()
+    barrier(world)
     l0 = A.launch_count
     ms_total, _ = A.bench_apply(x, y, warmup=0, iters=args.steps)
-    barrier()
+    barrier(world)
     launches = A.launch_count - l0
     clocks = sampler.summary()
-    t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t.item()) / args.steps
+    ms_step = max_over_ranks(ms_total, world) / args.steps
     gdofs = n_tot / (ms_step * 1e-3) / 1e9
+    # BASELINE.md section 4 protocol: >= 100 further applies in 10 batches, median and min per apply
+    batch = []
+    for _ in range(10):
+        ms_b, _ = A.bench_apply(x, y, warmup=0, iters=10)
+        batch.append(max_over_ranks(ms_b / 10, world))
+    ms_med, ms_min = statistics.median(batch), min(batch)
+
+    # ---- halo exchange by itself (N > 1) ----------------------------------------------------------------------
+    halo = None
+    if world > 1:
+        try:
+            ms_h, nb = A.bench_halo(x, warmup=5, iters=50)
+            us = max_over_ranks(ms_h / 50 * 1e3, world)
+            nbm = int(max_over_ranks(nb, world))
+            halo = {"bytes_sent_per_rank": nbm, "us": us, "gbs_per_direction": nbm / 2 / (us * 1e-6) / 1e9 if us > 0 else None,
+                    "nvlink_frac": (nbm / 2 / (us * 1e-6) / 1e9 / NVLINK_PEER_GBS) if us > 0 else None,
+                    "nvlink_peak_gbs": NVLINK_PEER_GBS, "share_of_apply": us / (ms_step * 1e3),
+                    "note": "grouped ncclSend/ncclRecv of the two boundary planes, timed alone (serialised in front of "
+                            "a plain apply; started early and hidden behind the vector kernels inside BiCGSTAB)"}
+        except Exception as e:  # noqa: BLE001
+            halo = {"error": f"{type(e).__name__}: {e}"}
 
     # ---- end to end through the C ABI with host buffers ------------------------------------------
     xh = torch.empty(n_loc, dtype=torch.complex128).pin_memory()
@@ -258,49 +468,83 @@ def main():
     xh.copy_(x.cpu())
     e2e_steps = max(3, min(args.steps, 5))
     A.mul(yh.numpy(), xh.numpy())
-    barrier()
+    barrier(world)
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         A.mul(yh.numpy(), xh.numpy())
-    barrier()
-    te = torch.tensor([(time.perf_counter() - t0) / e2e_steps], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e = n_tot / float(te.item()) / 1e9
+    barrier(world)
+    e2e = n_tot / max_over_ranks((time.perf_counter() - t0) / e2e_steps, world) / 1e9
 
     # ---- Krylov iterations / s (2 applies + fused vector updates per BiCGSTAB iteration) ---------
     kry_vec = 256 if os.environ.get("FDFD_BICGSTAB_CLASSIC") else 240
-    # (a failure here must not lose the operator numbers measured above: it is reported in the line instead)
     it_per_s = qmr_it_per_s = krylov_error = None
+    e2e_solve = None
     try:
-        b = torch.randn(n_loc, 2, device="cuda", dtype=torch.float64, generator=g).view(torch.complex128).reshape(-1)
+        b = rand_vec(n_loc, gen)
         xs = torch.zeros_like(b)
-        barrier()
-        ms_k = A.bench_solve(b, xs, "bicgstab", warmup=2, iters=args.krylov_iters)
-        tk = torch.tensor([ms_k], device="cuda", dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(tk, op=dist.ReduceOp.MAX)
-        it_per_s = args.krylov_iters / (float(tk.item()) * 1e-3)
+        barrier(world)
+        ms_k = max_over_ranks(A.bench_solve(b, xs, "bicgstab", warmup=2, iters=args.krylov_iters), world)
+        it_per_s = args.krylov_iters / (ms_k * 1e-3)
         xs.zero_()
-        barrier()
-        ms_q = A.bench_solve(b, xs, "qmr", warmup=2, iters=args.krylov_iters)
-        tq = torch.tensor([ms_q], device="cuda", dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(tq, op=dist.ReduceOp.MAX)
-        qmr_it_per_s = args.krylov_iters / (float(tq.item()) * 1e-3)
+        barrier(world)
+        ms_q = max_over_ranks(A.bench_solve(b, xs, "qmr", warmup=2, iters=args.krylov_iters), world)
+        qmr_it_per_s = args.krylov_iters / (ms_q * 1e-3)
+        # the path's real end-to-end unit: A \ b with host buffers - b in, x out, fixed iteration count
+        xh.copy_(b.cpu())
+        A.solve(xh.numpy(), rtol=1e-300, maxit=3, check_every=1 << 30)
+        barrier(world)
+        t0 = time.perf_counter()
+        _, info = A.solve(xh.numpy(), rtol=1e-300, maxit=args.krylov_iters, check_every=1 << 30)
+        barrier(world)
+        ts = max_over_ranks(time.perf_counter() - t0, world)
+        e2e_solve = {"iters": info["iters"], "seconds": ts, "iter_per_s": info["iters"] / ts,
+                     "gdof_iter_per_s": n_tot * info["iters"] / ts / 1e9,
+                     "h2d_bytes": 16 * n_loc * world, "d2h_bytes": 16 * n_loc * world,
+                     "note": "fdfd_solve(FDFD_HOST): b copied in, x copied out, BiCGSTAB without convergence exit"}
         del b, xs
     except Exception as e:  # noqa: BLE001
         krylov_error = f"{type(e).__name__}: {e}"
         print(f"bench.py: Krylov timing failed: {krylov_error}", file=sys.stderr)
 
+    bpd, off_frac, off_sym = bytes_per_dof(A, w)
+    mass_b = A.mass_bytes_per_dof
+    A.close()
+    del x, y, xh, yh
+    torch.cuda.empty_cache()
+
+    # ---- the other BASELINE configurations (N = 1) and the north_star scaling configurations (every N) ----------
+    configs, scale_c5, scale_c4 = None, None, None
+
+    def guarded(fn):
+        try:
+            return fn()
+        except Exception as e:  # noqa: BLE001
+            torch.cuda.empty_cache()
+            return {"error": f"{type(e).__name__}: {e}"}
+
+    if world == 1 and not args.no_configs:
+        configs = []
+        configs.append(guarded(lambda: measure_config("C1 vacuum box 40^3 + PML", workloads.c1_vacuum_box(), local, 0, 1,
+                                                       300, 50, gen)))
+        configs.append(guarded(lambda: measure_config("C3 PhC slab 256x256x128, Bloch x/y, PML z", workloads.c3_phc_slab(),
+                                                       local, 0, 1, 100, 40, gen)))
+        wd = workloads.c2_waveguide(PER_GPU_N)
+        workloads.make_dense_offdiag(wd, seed=7)
+        configs.append(guarded(lambda: measure_config("C2 grid, dense off-diagonal eps (fused full-tensor kernel)", wd, local,
+                                                       0, 1, 100, 40, gen)))
+        del wd
+        configs.append(guarded(lambda: measure_config("C2 grid, HH formulation A = Ce eps^-1 Cm - w^2 mu (model.jl:238-240)",
+                                                       workloads.c2_hh(), local, 0, 1, 100, 40, gen, ft="H")))
+    if not args.no_scale and not args.n:
+        # C4: 512^3 scatterer from objects (Kottke-smoothed on the device), STRONG scaling over the N slabs
+        scale_c4 = guarded(lambda: measure_config("C4 dielectric sphere 512^3 (strong scaling: 512/N planes per GPU)",
+                                                  workloads.c4_objects(), local, rank, world, 20, 10, gen))
+        # C5: metalens, WEAK scaling unit 1024 x 1024 x 96 planes per GPU (N = 8: 1024 x 1024 x 768)
+        scale_c5 = guarded(lambda: measure_config("C5 metalens 1024x1024x(96 N) (weak scaling: 96 planes per GPU)",
+                                                  workloads.c5_objects(N=(1024, 1024, 96 * world)), local, rank, world,
+                                                  20, 10, gen))
+
     if rank == 0:
-        peak, peak_src = peaks()
-        # bytes an apply must move per DOF: x 16 + y 16 + eps_diag 16, + 32 for the six off-diagonal entries on the
-        # (tile, plane) blocks that hold any (the kernel skips empty blocks; dense off-diagonals -> 80)
-        # a pointwise symmetric tensor is stored once (three arrays): 16 instead of 32
-        off_frac = A.offdiag_fraction if w["full_eps"] else 0.0
-        off_sym = bool(w["full_eps"] and A.offdiag_symmetric)
-        bpd = 48 + (16 if off_sym else 32) * off_frac
         achieved = bpd * (n_tot / world) / (ms_step * 1e-3) / 1e9      # per GPU
         traffic = None
         try:
@@ -310,32 +554,44 @@ def main():
             pass
         line = {
             "metric": METRIC, "value": gdofs, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms_step, "ms_per_step_median": ms_med, "ms_per_step_min": ms_min,
+            "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "c128 (complex fp64)", "data": "synthetic",
             "config": {"workload": w["name"] + (" [diagonal-eps variant]" if args.diag else "") +
                        (" [dense off-diagonal variant]" if args.dense_off else ""),
                        "offdiag_block_fraction": off_frac, "offdiag_symmetric": off_sym,
-                       "bytes_per_dof_if_dense": (64 if off_sym else 80) if w["full_eps"] else 48,
+                       "diagonal_mass_bytes_per_dof": mass_b,
                        "grid": list(N), "per_gpu_grid": list(per), "dof": n_tot, "parallelism": f"z-slab x{world}",
-                       "l2": "inputs (x, y, eps: > 1 GB per GPU) larger than the 126 MB L2; no flush needed",
+                       "l2": "inputs (x, y, eps: ~1 GB per GPU) larger than the 126 MB L2; no flush needed",
                        "bytes_per_dof": bpd},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "apply_tiled_kernel (+ offdiag_correction_kernel on flagged blocks when off-diagonal "
+                         "kernel": "apply_rowpair_kernel (+ offdiag_march_kernel on the flagged blocks when off-diagonal "
                                    "eps is sparse); traffic from the ncu --set full capture in profiles/",
-                         "bytes_per_dof": bpd},
+                         "bytes_per_dof": bpd,
+                         "bytes_model": "x 16 + y 16 + diagonal mass %g (real entries travel as doubles) + off-diagonal "
+                                        "streams on the flagged blocks" % mass_b},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 16 * n_loc * world,
                     "d2h_bytes_per_step": 16 * n_loc * world, "steps": e2e_steps,
                     "note": "fdfd_apply(FDFD_HOST) with pinned host buffers"},
-            "gpu_launches": launches, "clocks": clocks,
+            "e2e_solve": e2e_solve,
+            "gpu_launches": launches, "clocks": clocks, "parity": parity,
             "krylov": {"method": "bicgstab", "iters": args.krylov_iters, "iter_per_s": it_per_s,
-                       # 15 vector passes of 16 B (s: 3, x/r update with both dots: 7, p with the next sigma: 5);
-                       # 16 with FDFD_BICGSTAB_CLASSIC (separate (rhat, v) pass)
+                       "gdof_iter_per_s": None if it_per_s is None else n_tot * it_per_s / 1e9,
+                       # 15 vector passes of 16 B (s: 3, x/r update with both dots: 7, p with the next sigma: 5)
                        "bytes_per_dof_model": 2 * bpd + kry_vec,
                        "hbm_frac": None if it_per_s is None else (2 * bpd + kry_vec) * (n_tot / world) * it_per_s / 1e9 / peak,
                        "error": krylov_error,
                        "qmr_iter_per_s": qmr_it_per_s, "qmr_bytes_per_dof_model": 2 * bpd + 304},
         }
+        if halo is not None:
+            line["halo"] = halo
+        if configs is not None:
+            line["configs"] = configs
+        if scale_c4 is not None:
+            line["scale_c4"] = scale_c4
+        if scale_c5 is not None:
+            line["scale_c5"] = scale_c5
         if world == 1 and not args.no_cpu:
             try:
                 line["cpu_baseline"] = cpu_baseline_port()
@@ -343,7 +599,6 @@ def main():
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "port",
                                         "sample": f"failed: {e}"}
         print(json.dumps(line))
-    A.close()
     if world > 1:
         dist.destroy_process_group()
 

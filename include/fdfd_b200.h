@@ -191,6 +191,9 @@ int fdfd_bench_apply(fdfd_handle h, const fdfd_c128 *x_dev, fdfd_c128 *y_dev, in
 /* Fixed-iteration Krylov run without convergence exit (iterations/s): *ms_total for `iters`. */
 int fdfd_bench_solve(fdfd_handle h, int method, const fdfd_c128 *b_dev, fdfd_c128 *x_dev,
                      int warmup, int iters, double *ms_total);
+/* z-slabs: the halo exchange of one apply by itself (the two boundary planes of x_dev to / from the z-neighbours),
+ * `iters` times back to back; *bytes_sent = bytes this rank sends per exchange (0 on a single slab). */
+int fdfd_bench_halo(fdfd_handle h, const fdfd_c128 *x_dev, int warmup, int iters, double *ms_total, uint64_t *bytes_sent);
 /* Fraction of the (x-y tile, z-plane) blocks of this slab that hold a non-zero off-diagonal eps entry.  The
  * tiled kernel skips the six off-diagonal streams on empty blocks (subpixel smoothing puts off-diagonal
  * entries only at material interfaces), so the bytes an apply must move are (48 + 32*frac) B/DOF. */
@@ -199,6 +202,11 @@ int fdfd_offdiag_fraction(fdfd_handle h, double *frac);
  * smoothing of reciprocal media produces): the library then keeps three off-diagonal arrays instead of six and an apply
  * moves (48 + 16*frac) B/DOF.  0 otherwise (and when there are no off-diagonal entries). */
 int fdfd_offdiag_symmetric(fdfd_handle h, int *symmetric);
+/* Bytes per DOF the operator kernel streams for the diagonal material terms of this handle: the mass entries (16, or 8
+ * when every entry -w^2 P_vv is real - lossless media at a real frequency - and they travel as doubles; 0 when w = 0
+ * or the parameter is the identity) plus 16 for the inverse middle parameter when one was supplied.  With the 32 B of
+ * x and y and the off-diagonal streams (fdfd_offdiag_fraction) this is the algorithmic traffic of one apply. */
+int fdfd_mass_bytes_per_dof(fdfd_handle h, double *bytes);
 /* Number of kernels this handle has launched since creation (for bench.py's gpu_launches). */
 int64_t fdfd_launch_count(fdfd_handle h);
 

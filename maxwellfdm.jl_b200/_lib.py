@@ -78,6 +78,8 @@ SYMBOLS = {
     "fdfd_comm_init": (C.c_int, [P, C.c_char_p]),
     "fdfd_bench_apply": (C.c_int, [P, P, P, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "fdfd_bench_solve": (C.c_int, [P, C.c_int, P, P, C.c_int, C.c_int, C.POINTER(C.c_double)]),
+    "fdfd_mass_bytes_per_dof": (C.c_int, [P, C.POINTER(C.c_double)]),
+    "fdfd_bench_halo": (C.c_int, [P, P, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "fdfd_offdiag_fraction": (C.c_int, [P, C.POINTER(C.c_double)]),
     "fdfd_offdiag_symmetric": (C.c_int, [P, C.POINTER(C.c_int)]),
     "fdfd_launch_count": (C.c_int64, [P]),

@@ -46,6 +46,20 @@ __global__ void interleave3_kernel(double2 *dst, const double2 *s0, const double
         dst[3 * i + 2] = s2[i];
     }
 }
+// real-valued variant (dst doubles); *any_imag is raised when an entry has a non-zero imaginary part
+__global__ void interleave3_real_kernel(double *dst, const double2 *s0, const double2 *s1, const double2 *s2, int64_t n,
+                                        int Nx, int64_t pitch, int *any_imag) {
+    bool bad = false;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double2 a = s0[i], b = s1[i], c = s2[i];
+        double *d = dst + (i / Nx) * pitch + (i % Nx) * 3;     // rows padded to a whole number of 16-byte units
+        d[0] = a.x;
+        d[1] = b.x;
+        d[2] = c.x;
+        bad |= (a.y != 0.0) | (b.y != 0.0) | (c.y != 0.0);
+    }
+    if (bad) *any_imag = 1;
+}
 __global__ void flush_kernel(float4 *p, int64_t n, float v) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         p[i] = make_float4(v, v, v, v);
@@ -58,7 +72,7 @@ static inline int nblocks(int64_t n) {
 
 static void free_device(Ctx *c) {
     auto F = [](auto *&p) { if (p) cudaFree((void *)p); p = nullptr; };
-    F(c->coef_dev); F(c->mat_dev); F(c->md_aos); F(c->halo_lo); F(c->halo_hi); F(c->work); F(c->scal); F(c->partial);
+    F(c->coef_dev); F(c->mat_dev); F(c->md_aos); F(c->md_aos_r); F(c->halo_lo); F(c->halo_hi); F(c->work); F(c->scal); F(c->partial);
     F(c->stage_x); F(c->stage_y); F(c->flush_buf); F(c->offmask); F(c->corr_list); F(c->dot_partial); F(c->dot_ticket);
     F(c->halo_flag);
     if (c->scal_host) cudaFreeHost(c->scal_host);
@@ -170,6 +184,7 @@ static int upload_materials(Ctx *c) {
         c->md_uniform = make_double2(w2u.real(), w2u.imag());
     }
     if (c->md_aos) { cudaFree(c->md_aos); c->md_aos = nullptr; }
+    if (c->md_aos_r) { cudaFree(c->md_aos_r); c->md_aos_r = nullptr; }
     if (!narr) return FDFD_OK;
     double2 *objbuf = nullptr;                  // objects: the smoothed slab in Julia layout, on the device
     if (obj && has_mass) {
@@ -267,9 +282,52 @@ static int upload_materials(Ctx *c) {
     // cmp-first DOF layout: a second, interleaved copy of the (ghosted) diagonal mass arrays for the row-pair kernel,
     // which stages material through the same TMA ring as x (apply_rowpair.cu); +16 B/DOF of HBM capacity
     if (c->md[0] && c->d.order_cmpfirst && c->d.kernel != FDFD_KERNEL_NAIVE) {
-        FDFD_CUDA(c, cudaMalloc((void **)&c->md_aos, (size_t)3 * Mg * sizeof(double2)));
-        interleave3_kernel<<<nblocks(Mg), 256, 0, c->stream>>>(c->md_aos, c->md[0], c->md[1], c->md[2], Mg);
-        FDFD_CUDA(c, cudaGetLastError());
+        // Real diagonal entries (real omega, real eps_vv - every lossless dielectric) are kept as doubles: the kernel's
+        // tensor-map boxes then move 8 instead of 16 bytes per entry (40 instead of 48 B/DOF per apply).  Needs the
+        // tensor-map path; FDFD_RP_MDR=0 / FDFD_RP_TMAP=0 keep the complex rows (A/B timing).
+        static const bool allow_real = [] {
+            const char *a = getenv("FDFD_RP_MDR"), *t = getenv("FDFD_RP_TMAP");
+            return !(a && atoi(a) == 0) && !(t && atoi(t) == 0);
+        }();
+        bool real_rows = false;
+        if (allow_real && tmap_probe(c->md[0])) {
+            int *flag = nullptr;
+            FDFD_CUDA(c, cudaMalloc((void **)&flag, sizeof(int)));
+            FDFD_CUDA(c, cudaMemsetAsync(flag, 0, sizeof(int), c->stream));
+            const int64_t pitch = mdr_row_pitch((int)c->d.N[0]), nrow = c->d.N[1] * (nzl + 2);
+            FDFD_CUDA(c, cudaMalloc((void **)&c->md_aos_r, (size_t)(pitch * nrow) * sizeof(double)));
+            FDFD_CUDA(c, cudaMemsetAsync(c->md_aos_r, 0, (size_t)(pitch * nrow) * sizeof(double), c->stream));
+            interleave3_real_kernel<<<nblocks(Mg), 256, 0, c->stream>>>(c->md_aos_r, c->md[0], c->md[1], c->md[2], Mg,
+                                                                        (int)c->d.N[0], pitch, flag);
+            FDFD_CUDA(c, cudaGetLastError());
+            int any_imag = 1;
+            FDFD_CUDA(c, cudaMemcpyAsync(&any_imag, flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+            FDFD_CUDA(c, cudaStreamSynchronize(c->stream));
+            cudaFree(flag);
+            if (c->d.nranks > 1) {
+                // z-slabs: every rank takes the same kernel variant (the fused dots and the graphs assume one plan)
+                double *f = nullptr;
+                const double hv = any_imag ? 1.0 : 0.0;
+                FDFD_CUDA(c, cudaMalloc((void **)&f, sizeof(double)));
+                FDFD_CUDA(c, cudaMemcpyAsync(f, &hv, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+                int ra = allreduce_sum(c, f, 1, c->stream);
+                double gv = 1.0;
+                if (ra == FDFD_OK) {
+                    FDFD_CUDA(c, cudaMemcpyAsync(&gv, f, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+                    FDFD_CUDA(c, cudaStreamSynchronize(c->stream));
+                }
+                cudaFree(f);
+                if (ra != FDFD_OK) return ra;
+                any_imag = gv > 0.0;
+            }
+            real_rows = !any_imag;
+            if (!real_rows) { cudaFree(c->md_aos_r); c->md_aos_r = nullptr; }
+        }
+        if (!real_rows) {
+            FDFD_CUDA(c, cudaMalloc((void **)&c->md_aos, (size_t)3 * Mg * sizeof(double2)));
+            interleave3_kernel<<<nblocks(Mg), 256, 0, c->stream>>>(c->md_aos, c->md[0], c->md[1], c->md[2], Mg);
+            FDFD_CUDA(c, cudaGetLastError());
+        }
     }
     FDFD_CUDA(c, cudaStreamSynchronize(c->stream));
     return FDFD_OK;
@@ -317,6 +375,7 @@ void fill_params(Ctx *c, ApplyParams &p, const double2 *x, double2 *y, bool tran
     p.c = transpose ? c->ct : c->cf;
     for (int i = 0; i < 3; ++i) { p.md[i] = c->md[i]; p.q[i] = c->q[i]; }
     p.md_aos = c->md_aos;
+    p.md_aos_r = c->md_aos_r;
     for (int i = 0; i < 6; ++i) p.mo[i] = transpose ? c->mo_t[i] : c->mo[i];
     const int64_t Nxy = Nx * Ny;
     p.x.base = x;
@@ -1200,12 +1259,62 @@ int fdfd_bench_solve(fdfd_handle h, int method, const fdfd_c128 *b, fdfd_c128 *x
     return r;
 }
 
+int fdfd_bench_halo(fdfd_handle h, const fdfd_c128 *x, int warmup, int iters, double *ms_total, uint64_t *bytes_sent) {
+    CHECK_H(h);
+    if (!x || iters < 1 || warmup < 0) return set_err(c, FDFD_EINVAL, "fdfd_bench_halo: bad argument");
+    { int r0 = ensure_ready(c); if (r0 != FDFD_OK) return r0; }
+    if (ms_total) *ms_total = 0.0;
+    if (bytes_sent) *bytes_sent = 0;
+    if (c->d.nranks == 1) return FDFD_OK;     // a single slab exchanges nothing
+    const double2 *dx = reinterpret_cast<const double2 *>(x);
+    int up, dn, r;
+    halo_neighbours(c->d.nranks, c->d.rank, c->d.isbloch[2] != 0, &up, &dn);
+    if (c->comm_pending) {
+        FDFD_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_halo, 0));
+        c->comm_pending = false;
+    }
+    for (int i = 0; i < warmup; ++i)
+        if ((r = halo_exchange(c, dx, c->halo_lo, c->halo_hi, c->stream)) != FDFD_OK) return r;
+    cudaEvent_t e0, e1;
+    FDFD_CUDA(c, cudaEventCreate(&e0));
+    FDFD_CUDA(c, cudaEventCreate(&e1));
+    FDFD_CUDA(c, cudaStreamSynchronize(c->stream));
+    FDFD_CUDA(c, cudaEventRecord(e0, c->stream));
+    for (int i = 0; i < iters; ++i)
+        if ((r = halo_exchange(c, dx, c->halo_lo, c->halo_hi, c->stream)) != FDFD_OK) {
+            cudaEventDestroy(e0); cudaEventDestroy(e1);
+            return r;
+        }
+    FDFD_CUDA(c, cudaEventRecord(e1, c->stream));
+    FDFD_CUDA(c, cudaEventSynchronize(e1));
+    float ms = 0;
+    FDFD_CUDA(c, cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (ms_total) *ms_total = ms;
+    if (bytes_sent) *bytes_sent = (uint64_t)((up >= 0) + (dn >= 0)) * (uint64_t)c->plane * sizeof(double2);
+    return FDFD_OK;
+}
+
 int fdfd_offdiag_fraction(fdfd_handle h, double *frac) {
     CHECK_H(h);
     if (!frac) return set_err(c, FDFD_EINVAL, "null argument");
     int r = ensure_ready(c);
     if (r != FDFD_OK) return r;
     *frac = c->off_frac;
+    return FDFD_OK;
+}
+
+int fdfd_mass_bytes_per_dof(fdfd_handle h, double *bytes) {
+    CHECK_H(h);
+    if (!bytes) return set_err(c, FDFD_EINVAL, "null argument");
+    int r = ensure_ready(c);
+    if (r != FDFD_OK) return r;
+    // what the operator kernel streams for the diagonal mass term: nothing (omega = 0 or an identity parameter held as
+    // a scalar), complex entries, or doubles when every entry is real
+    double b = (c->has_mass && c->md[0]) ? (c->md_aos_r ? 8.0 : 16.0) : 0.0;
+    if (c->q[0]) b += 16.0;   // inverse middle parameter (mu^-1 for FT_EE with a mu array, eps^-1 for FT_HH)
+    *bytes = b;
     return FDFD_OK;
 }
 

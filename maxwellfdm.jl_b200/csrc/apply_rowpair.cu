@@ -61,13 +61,17 @@ struct RowPairParams {
                    // 2 no y stores, 4 no x loads, 8 no arithmetic
 };
 
-template <int NWC, int NST>
+template <int NWC, int NST, bool MDR>
 struct RPCfg {
     static constexpr int NR = 2 * NWC + 2;            // E rows per ring stage
     static constexpr int NM = 2 * NWC;                // material rows per ring stage (output rows only)
     static constexpr int NT = 32 * (NWC + 1);
     static constexpr int MD0 = NR * RP_TX * 3;        // offset of the material rows inside a stage
-    static constexpr int STAGE = (NR + NM) * RP_TX * 3;   // double2 per ring stage
+    // real material rows: 3 doubles per cell; a tensor-map box must start on a 16-byte boundary of the global array,
+    // i.e. at an even cell, so the box is 34 cells wide and starts at the even cell at or below the tile origin
+    static constexpr int MDCELLS = MDR ? RP_TX + 2 : RP_TX;
+    static constexpr int MDROW = MDR ? MDCELLS * 3 / 2 : RP_TX * 3;          // double2 per material row
+    static constexpr int STAGE = (NR * RP_TX * 3 + NM * MDROW + 7) / 8 * 8;  // double2 per ring stage (128-byte multiple)
     static constexpr int FPAD = 8;                    // slack below stage 0 / above the last stage (halo-lane over-reads)
     static constexpr int YW = 2 * RP_TX * 3;          // per-warp y staging (two rows)
     static constexpr int TABS = 4 * NR + 4 * RP_LZP;  // per-item tables: a0,a1,b0,b1 for y (NR rows) and z (planes)
@@ -81,9 +85,13 @@ __host__ __device__ __forceinline__ int chunk_begin(int kb, int ke, int nch, int
     return kb + (int)(((int64_t)(ke - kb) * c) / nch);
 }
 
-template <bool CMPFIRST, bool HAS_Q, bool DOT, int ARR, int NWC, int NST>
+// MDR: the diagonal mass entries are REAL (real omega and real eps_vv - every lossless dielectric): the ring carries
+// 8 instead of 16 bytes per entry (40 instead of 48 B/DOF of HBM traffic) and the mass term costs half the flops.
+// Tensor-map path only (the rows are 24 B per cell, which 1-D bulk copies cannot always address in 16-B units).
+template <bool CMPFIRST, bool HAS_Q, bool DOT, int ARR, bool MDR, int NWC, int NST>
 __global__ void __launch_bounds__(32 * (NWC + 1), 1) apply_rowpair_kernel(const __grid_constant__ RowPairParams tp) {
-    using C = RPCfg<NWC, NST>;
+    static_assert(!MDR || CMPFIRST, "real material rows exist for the cmp-first layout only");
+    using C = RPCfg<NWC, NST, MDR>;
     constexpr int NR = C::NR, NM = C::NM, NT = C::NT, STAGE = C::STAGE, MD0 = C::MD0, TX = RP_TX, LZP = RP_LZP;
     const ApplyParams &p = tp.a;
     // direction of the first curl's neighbour per axis: compile-time for the two uniform arrangements (ARR 0: the
@@ -244,7 +252,7 @@ __global__ void __launch_bounds__(32 * (NWC + 1), 1) apply_rowpair_kernel(const 
                 double2 *dst = ring + s * STAGE;
                 if (CMPFIRST && tp.tmap) {
                     // ---- tensor-map path: ONE box per array and plane; parts outside the domain read as zero
-                    const uint32_t box_bytes = (skip_x ? 0u : (uint32_t)(NR * TX * 48)) + (want_m ? (uint32_t)(NM * TX * 48) : 0u);
+                    const uint32_t box_bytes = (skip_x ? 0u : (uint32_t)(NR * TX * 48)) + (want_m ? (uint32_t)(NM * C::MDROW * 16) : 0u);
                     uint64_t *bar = has_wrap ? &aux[s] : &full[s];
                     if (lane == 0) {
                         mbar_arrive_expect_tx(bar, box_bytes);
@@ -253,7 +261,7 @@ __global__ void __launch_bounds__(32 * (NWC + 1), 1) apply_rowpair_kernel(const 
                             else if (kk >= p.nzl) tma_load_3d(dst, &tp.mhi, 6 * ox, oy, 0, bar);
                             else tma_load_3d(dst, &tp.mx, 6 * ox, oy, kk, bar);
                         }
-                        if (want_m) tma_load_3d(dst + MD0, &tp.mmd, 6 * ox, oy + 1, kk + 1, bar);
+                        if (want_m) tma_load_3d(dst + MD0, &tp.mmd, MDR ? 3 * (ox - (ox & 1)) : 6 * ox, oy + 1, kk + 1, bar);
                     }
                     // tiles with Bloch wrap: the wrapped cells / rows of the PREVIOUS plane follow as 1-D pieces once
                     // its box (which zero-filled those places) has landed - it has had a whole step to do so
@@ -311,6 +319,7 @@ __global__ void __launch_bounds__(32 * (NWC + 1), 1) apply_rowpair_kernel(const 
         const int dB = SGY * ER;                          // A -> B; R (row below the pair) = A - dB, F = A + 2 dB
         const int exf = SGX * EX;                         // offset to the x-neighbour of the first curl
         const int mdo = MD0 - ER;                         // E element of an output cell -> its material element (c = 0)
+        const int mdr_dB = SGY * C::MDCELLS * 3;          // real material rows (doubles): cell A -> cell B
         // y staging: row slot 0 <-> the physically lower row of the pair
         double2 *yw = ybase + wid * C::YW;
         const int ysA = SGY > 0 ? 0 : 1;
@@ -337,6 +346,7 @@ __global__ void __launch_bounds__(32 * (NWC + 1), 1) apply_rowpair_kernel(const 
             const int kfirst = SGZ < 0 ? kc1 : kc0 - 1;   // local plane of march step 0
 
             const int gi = ox + ptx, gjA = oy + rA, gjB = oy + rB;
+            const int mdr_o = ((rA - 1) * C::MDCELLS + ptx + (ox & 1)) * 3;   // real material rows: cell A, component 0
             const int ci = ((gi % Nx) + Nx) % Nx;
             const bool okA = lane_out && gi < Nx && gjA < Ny, okB = lane_out && gi < Nx && gjB < Ny;
             // x tables in registers
@@ -450,8 +460,15 @@ __global__ void __launch_bounds__(32 * (NWC + 1), 1) apply_rowpair_kernel(const 
                     double2 mdA0 = p.md_uniform, mdA1 = p.md_uniform, mdA2 = p.md_uniform;
                     double2 mdB0 = p.md_uniform, mdB1 = p.md_uniform, mdB2 = p.md_uniform;
                     if (md_tile) {
-                        mdA0 = es[mdo]; mdA1 = es[mdo + MC]; mdA2 = es[mdo + 2 * MC];
-                        mdB0 = es[mdo + dB]; mdB1 = es[mdo + dB + MC]; mdB2 = es[mdo + dB + 2 * MC];
+                        if (MDR) {   // 3 doubles per cell, rows of 32 cells
+                            const double *mr = reinterpret_cast<const double *>(ring + s_cur * STAGE + MD0) + mdr_o;
+                            mdA0 = make_double2(mr[0], 0.0); mdA1 = make_double2(mr[1], 0.0); mdA2 = make_double2(mr[2], 0.0);
+                            mdB0 = make_double2(mr[mdr_dB], 0.0); mdB1 = make_double2(mr[mdr_dB + 1], 0.0);
+                            mdB2 = make_double2(mr[mdr_dB + 2], 0.0);
+                        } else {
+                            mdA0 = es[mdo]; mdA1 = es[mdo + MC]; mdA2 = es[mdo + 2 * MC];
+                            mdB0 = es[mdo + dB]; mdB1 = es[mdo + dB + MC]; mdB2 = es[mdo + dB + 2 * MC];
+                        }
                     }
                     double2 yxA, yyA, yzA, yxB, yyB, yzB;
                     if (!RP_ABL || !(tp.dbg & 8)) {
@@ -463,8 +480,17 @@ __global__ void __launch_bounds__(32 * (NWC + 1), 1) apply_rowpair_kernel(const 
                         yyB = c_mul(b0z, HxB);  yyB = c_fma(b1z, HpxB, yyB);  yyB = c_fms(b0x, HzB, yyB); yyB = c_fms(b1x, HzBm, yyB);
                         yzB = c_mul(b0x, HyB);  yzB = c_fma(b1x, HyBm, yzB);  yzB = c_fms(b0yB, HxB, yzB); yzB = c_fms(b1yB, HxA, yzB);
                         if (p.has_mass) {
-                            yxA = c_fma(mdA0, EA0, yxA); yyA = c_fma(mdA1, EA1, yyA); yzA = c_fma(mdA2, EA2, yzA);
-                            yxB = c_fma(mdB0, EB0, yxB); yyB = c_fma(mdB1, EB1, yyB); yzB = c_fma(mdB2, EB2, yzB);
+                            if (MDR && md_tile) {   // real coefficient: two fused multiply-adds per component
+                                yxA.x = fma(mdA0.x, EA0.x, yxA.x); yxA.y = fma(mdA0.x, EA0.y, yxA.y);
+                                yyA.x = fma(mdA1.x, EA1.x, yyA.x); yyA.y = fma(mdA1.x, EA1.y, yyA.y);
+                                yzA.x = fma(mdA2.x, EA2.x, yzA.x); yzA.y = fma(mdA2.x, EA2.y, yzA.y);
+                                yxB.x = fma(mdB0.x, EB0.x, yxB.x); yxB.y = fma(mdB0.x, EB0.y, yxB.y);
+                                yyB.x = fma(mdB1.x, EB1.x, yyB.x); yyB.y = fma(mdB1.x, EB1.y, yyB.y);
+                                yzB.x = fma(mdB2.x, EB2.x, yzB.x); yzB.y = fma(mdB2.x, EB2.y, yzB.y);
+                            } else {
+                                yxA = c_fma(mdA0, EA0, yxA); yyA = c_fma(mdA1, EA1, yyA); yzA = c_fma(mdA2, EA2, yzA);
+                                yxB = c_fma(mdB0, EB0, yxB); yyB = c_fma(mdB1, EB1, yyB); yzB = c_fma(mdB2, EB2, yzB);
+                            }
                         }
                     } else {
                         yxA = c_add(c_add(HzA, HzR), c_add(HpyA, mdA0)); yyA = c_add(c_add(HxA, HpxA), c_add(HzAm, mdA1));
@@ -571,6 +597,11 @@ __global__ void __launch_bounds__(32 * (NWC + 1), 1) apply_rowpair_kernel(const 
     }
 }
 
+// real material rows: 3 doubles per cell, row pitch padded to a whole number of 16-byte units (tensor-map strides)
+}  // namespace
+int64_t mdr_row_pitch(int Nx) { return ((int64_t)3 * Nx + 1) & ~(int64_t)1; }
+namespace {
+
 int sm_count() {
     static int n[64] = {};
     int dev = 0;
@@ -584,26 +615,31 @@ int sm_count() {
     return n[dev];
 }
 
-template <bool CMPFIRST, bool HAS_Q, bool DOT, int ARR, int NWC, int NST>
+template <bool CMPFIRST, bool HAS_Q, bool DOT, int ARR, bool MDR, int NWC, int NST>
 cudaError_t launch_rp(const RowPairParams &tp, int grid, cudaStream_t s) {
-    auto kern = apply_rowpair_kernel<CMPFIRST, HAS_Q, DOT, ARR, NWC, NST>;
-    const size_t smem = RPCfg<NWC, NST>::smem_bytes();
-    static bool attr_set[64] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    if constexpr (MDR && !CMPFIRST) {
+        return cudaErrorInvalidConfiguration;
+    } else {
+        auto kern = apply_rowpair_kernel<CMPFIRST, HAS_Q, DOT, ARR, MDR, NWC, NST>;
+        const size_t smem = RPCfg<NWC, NST, MDR>::smem_bytes();
+        static bool attr_set[64] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            if (dev >= 0 && dev < 64) attr_set[dev] = true;
+        }
+        kern<<<grid, 32 * (NWC + 1), smem, s>>>(tp);
+        return cudaGetLastError();
     }
-    kern<<<grid, 32 * (NWC + 1), smem, s>>>(tp);
-    return cudaGetLastError();
 }
 
-// Compiled tile heights / ring depths.  Warps are spread over the four SM sub-partitions, so the register budget per
-// thread steps with ceil(warps / 4): 8 warps (7 compute + producer) may use 255 registers, 12 warps (11 + 1) 168.
-struct RpShape { int nwc, nst; };
-constexpr RpShape RP_SHAPES[] = {{7, 4}, {7, 3}, {5, 5}};
+// Compiled shapes.  Warps are spread over the four SM sub-partitions, so the register budget per thread steps with
+// ceil(warps / 4): 8 warps (7 compute + producer) may use 255 registers.  Shape 0: complex material rows, 4 ring
+// stages of 46 KB; shape 1: real material rows (MDR), 5 stages of 35 KB.
+struct RpShape { int nwc, nst; bool mdr; };
+constexpr RpShape RP_SHAPES[] = {{7, 4, false}, {7, 5, true}};
 constexpr int RP_NSHAPES = sizeof(RP_SHAPES) / sizeof(RP_SHAPES[0]);
 
 }  // namespace
@@ -632,27 +668,24 @@ static int env_int(const char *name) {
     return e ? atoi(e) : 0;
 }
 
-// tile shape for this problem: the one whose plan costs least (plane-steps per CTA x rows per step), unless
-// FDFD_RP_NWC / FDFD_RP_NST pin it (tuning)
+static bool want_tmap() {
+    static const bool v = [] { const char *e = getenv("FDFD_RP_TMAP"); return !e || atoi(e) != 0; }();
+    return v;
+}
+
+// shape for this launch: real material rows when the handle built them (tensor-map path, cmp-first layout)
 static int rp_pick_shape(const ApplyParams &p, int kl_begin, int kl_end, int *nchunk) {
-    static const int want_nwc = env_int("FDFD_RP_NWC"), want_nst = env_int("FDFD_RP_NST"), want_nch = env_int("FDFD_RP_NCHUNK");
-    int best = -1;
-    double best_cost = 1e300;
+    static const int want_nch = env_int("FDFD_RP_NCHUNK");
     const int n = kl_end - kl_begin;
-    for (int i = 0; i < RP_NSHAPES; ++i) {
-        const int nwc = RP_SHAPES[i].nwc, nst = RP_SHAPES[i].nst;
-        if (want_nwc && nwc != want_nwc) continue;
-        if (want_nst && nst != want_nst) continue;
-        if (!want_nst && i > 0 && RP_SHAPES[i].nwc == RP_SHAPES[i - 1].nwc) continue;   // first listed ring depth is the default
-        const int ntx = (p.Nx + RP_TX - 3) / (RP_TX - 2), nty = (p.Ny + 2 * nwc - 1) / (2 * nwc);
-        double cost;
-        int nch = rp_pick_nchunk(ntx * nty, n, sm_count(), nst, &cost);
-        if (want_nch >= 1 && n / want_nch >= std::max(1, nst - 2) && (n + want_nch - 1) / want_nch <= RP_LZMAX) nch = want_nch;
-        if (nch < 1) continue;
-        cost *= 2.0 * nwc;   // cells per plane-step scale with the tile height; throughput per CTA roughly does too
-        if (cost < best_cost) { best_cost = cost; best = i; *nchunk = nch; }
-    }
-    return best;
+    const bool mdr = p.cmpfirst && p.has_mass && p.md[0] != nullptr && p.md_aos_r != nullptr && want_tmap();
+    const int i = mdr ? 1 : 0;
+    const int nwc = RP_SHAPES[i].nwc, nst = RP_SHAPES[i].nst;
+    const int ntx = (p.Nx + RP_TX - 3) / (RP_TX - 2), nty = (p.Ny + 2 * nwc - 1) / (2 * nwc);
+    int nch = rp_pick_nchunk(ntx * nty, n, sm_count(), nst, nullptr);
+    if (want_nch >= 1 && n / want_nch >= std::max(1, nst - 2) && (n + want_nch - 1) / want_nch <= RP_LZMAX) nch = want_nch;
+    if (nch < 1) return -1;
+    *nchunk = nch;
+    return i;
 }
 
 bool rowpair_supported(const ApplyParams &p, int kl_begin, int kl_end) {
@@ -665,19 +698,21 @@ bool rowpair_supported(const ApplyParams &p, int kl_begin, int kl_end) {
 
 // Tensor maps are cached by (address, geometry): a Krylov solve applies the operator to a handful of workspace
 // vectors over and over, so the driver's encode call (~1 us) is paid once per vector, not once per apply.
-static bool cached_map(TmaMap *out, const void *base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0, uint32_t b1) {
-    struct Entry { const void *base; uint64_t d0, d1, d2; uint32_t b0, b1; TmaMap m; };
+static bool cached_map(TmaMap *out, const void *base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0, uint32_t b1,
+                       uint64_t pitch0 = 0) {
+    struct Entry { const void *base; uint64_t d0, d1, d2, pitch; uint32_t b0, b1; TmaMap m; };
     static thread_local std::vector<Entry> cache;
+    const uint64_t pitch = pitch0 ? pitch0 : d0;      // elements between consecutive rows
     for (size_t i = 0; i < cache.size(); ++i) {
         const Entry &e = cache[i];
-        if (e.base == base && e.d0 == d0 && e.d1 == d1 && e.d2 == d2 && e.b0 == b0 && e.b1 == b1) {
+        if (e.base == base && e.d0 == d0 && e.d1 == d1 && e.d2 == d2 && e.pitch == pitch && e.b0 == b0 && e.b1 == b1) {
             *out = e.m;
             return true;
         }
     }
-    const uint64_t dims[3] = {d0, d1, d2}, strides[2] = {d0 * 8, d0 * d1 * 8};
+    const uint64_t dims[3] = {d0, d1, d2}, strides[2] = {pitch * 8, pitch * d1 * 8};
     const uint32_t box[3] = {b0, b1, 1};
-    Entry e{base, d0, d1, d2, b0, b1, {}};
+    Entry e{base, d0, d1, d2, pitch, b0, b1, {}};
     if (!tmap_encode_f64_3d(&e.m, base, dims, strides, box)) return false;
     if (cache.size() >= 64) cache.erase(cache.begin());
     cache.push_back(e);
@@ -685,21 +720,25 @@ static bool cached_map(TmaMap *out, const void *base, uint64_t d0, uint64_t d1, 
     return true;
 }
 
-template <int NWC, int NST>
+template <int NWC, int NST, bool MDR>
 static cudaError_t launch_rp_shape(RowPairParams &tp, const ApplyParams &p, cudaStream_t s) {
     // tensor-map TMA path (cmp-first layout): boxes of 32 cells x (E rows | material rows), y boxes of 30 cells x 2 rows
-    static const bool want_tmap = [] { const char *e = getenv("FDFD_RP_TMAP"); return !e || atoi(e) != 0; }();
     tp.tmap = 0;
-    if (want_tmap && p.cmpfirst && p.x.base && p.y) {
+    if (want_tmap() && p.cmpfirst && p.x.base && p.y) {
         const uint64_t d0 = 6ull * p.Nx, d1 = (uint64_t)p.Ny;
         const bool md_tile = p.has_mass && p.md[0] != nullptr;
         bool ok = cached_map(&tp.mx, p.x.base, d0, d1, (uint64_t)p.nzl, 6 * RP_TX, 2 * NWC + 2) &&
                   cached_map(&tp.mlo, p.x.lo, d0, d1, 1, 6 * RP_TX, 2 * NWC + 2) &&
                   cached_map(&tp.mhi, p.x.hi, d0, d1, 1, 6 * RP_TX, 2 * NWC + 2) &&
                   cached_map(&tp.my, p.y, d0, d1, (uint64_t)p.nzl, 6 * (RP_TX - 2), 2);
-        if (ok && md_tile) ok = p.md_aos != nullptr && cached_map(&tp.mmd, p.md_aos, d0, d1, (uint64_t)p.nzl + 2, 6 * RP_TX, 2 * NWC);
+        if (ok && md_tile) {
+            if (MDR) ok = p.md_aos_r != nullptr && cached_map(&tp.mmd, p.md_aos_r, d0 / 2, d1, (uint64_t)p.nzl + 2, 3 * (RP_TX + 2), 2 * NWC,
+                                                                 mdr_row_pitch(p.Nx));
+            else ok = p.md_aos != nullptr && cached_map(&tp.mmd, p.md_aos, d0, d1, (uint64_t)p.nzl + 2, 6 * RP_TX, 2 * NWC);
+        }
         tp.tmap = ok ? 1 : 0;
     }
+    if (MDR && !tp.tmap) return cudaErrorNotSupported;   // the handle keeps complex rows whenever tensor maps are unavailable
     tp.ntx = (p.Nx + RP_TX - 3) / (RP_TX - 2);
     tp.nty = (p.Ny + 2 * NWC - 1) / (2 * NWC);
     tp.nitems = tp.ntx * tp.nty * tp.nchunk;
@@ -711,9 +750,9 @@ static cudaError_t launch_rp_shape(RowPairParams &tp, const ApplyParams &p, cuda
     const bool cf = p.cmpfirst != 0, q = p.has_q != 0;
     const int nfwd = (p.s1[0] > 0) + (p.s1[1] > 0) + (p.s1[2] > 0);
     const int arr = nfwd == 3 ? 0 : nfwd == 0 ? 1 : 2;
-#define W(CF, Q, D)                                                                                  \
-    (arr == 0 ? launch_rp<CF, Q, D, 0, NWC, NST>(tp, grid, s)                                        \
-              : arr == 1 ? launch_rp<CF, Q, D, 1, NWC, NST>(tp, grid, s) : launch_rp<CF, Q, D, 2, NWC, NST>(tp, grid, s))
+#define W(CF, Q, D)                                                                                          \
+    (arr == 0 ? launch_rp<CF, Q, D, 0, MDR, NWC, NST>(tp, grid, s)                                           \
+              : arr == 1 ? launch_rp<CF, Q, D, 1, MDR, NWC, NST>(tp, grid, s) : launch_rp<CF, Q, D, 2, MDR, NWC, NST>(tp, grid, s))
 #define V(CF, Q) (dot ? W(CF, Q, true) : W(CF, Q, false))
     if (cf) return q ? V(true, true) : V(true, false);
     return q ? V(false, true) : V(false, false);
@@ -735,9 +774,8 @@ cudaError_t launch_apply_rowpair(const ApplyParams &p, int kl_begin, int kl_end,
     const int shape = (p.s1[0] * p.s1[0] == 1 && p.s1[1] * p.s1[1] == 1 && p.s1[2] * p.s1[2] == 1 && !p.halo_flag)
                           ? rp_pick_shape(p, kl_begin, kl_end, &tp.nchunk) : -1;
     switch (shape) {
-        case 0: return launch_rp_shape<RP_SHAPES[0].nwc, RP_SHAPES[0].nst>(tp, p, s);
-        case 1: return launch_rp_shape<RP_SHAPES[1].nwc, RP_SHAPES[1].nst>(tp, p, s);
-        case 2: return launch_rp_shape<RP_SHAPES[2].nwc, RP_SHAPES[2].nst>(tp, p, s);
+        case 0: return launch_rp_shape<RP_SHAPES[0].nwc, RP_SHAPES[0].nst, RP_SHAPES[0].mdr>(tp, p, s);
+        case 1: return launch_rp_shape<RP_SHAPES[1].nwc, RP_SHAPES[1].nst, RP_SHAPES[1].mdr>(tp, p, s);
         default: return cudaErrorNotSupported;
     }
 }

@@ -58,6 +58,7 @@ struct ApplyParams {
     const double2 *md[3];   // -w^2 * P_vv (null when the mass parameter is the identity: md_uniform = -w^2)
     double2 md_uniform;
     const double2 *md_aos;  // cmp-first layout only: the three md arrays interleaved, element ((kl+1)*Nx*Ny + j*Nx + i)*3 + v
+    const double *md_aos_r; // the same, real parts only, rows of mdr_row_pitch(Nx) doubles: [(kl+1)*Ny + j][3*i + v] - present when every diagonal mass entry is real (then md_aos is null)
     const double2 *mo[6];   // -w^2 * P_vu, order (0,1),(0,2),(1,0),(1,2),(2,0),(2,1)
     const double2 *q[3];    // inverse of the middle diagonal parameter (mu^-1 for FT_EE)
     PlaneSet x;
@@ -150,6 +151,7 @@ struct Ctx {
     CoefDev cf{}, ct{};              // forward operator / transposed operator
     double2 *mat_dev = nullptr;      // md[3], mo[6], q[3] ghosted slabs
     double2 *md_aos = nullptr;       // interleaved copy of md[3] (cmp-first layout; row-pair kernel)
+    double *md_aos_r = nullptr;      // real-valued interleaved copy (instead of md_aos) when every entry is real
     size_t mat_bytes = 0;
     const double2 *md[3]{}, *mo[6]{}, *mo_t[6]{}, *q[3]{};
     bool has_mass = false;           // omega != 0
@@ -231,6 +233,7 @@ bool tiled_supported(const ApplyParams &p);
 // apply_rowpair.cu: second-generation K1 (persistent, warp-specialised; diagonal mass parameter) over local planes
 // [kl_begin, kl_end); cudaErrorNotSupported when the configuration is outside its range
 bool rowpair_supported(const ApplyParams &p, int kl_begin, int kl_end);
+int64_t mdr_row_pitch(int Nx);   // doubles per row of ApplyParams::md_aos_r
 cudaError_t launch_apply_rowpair(const ApplyParams &p, int kl_begin, int kl_end, cudaStream_t s);
 // number of z-chunks per tile column the main kernel of launch_apply_tiled(p, 0, nzl) will use
 int tiled_plan_nchunk(const ApplyParams &p);
@@ -250,6 +253,7 @@ cudaError_t launch_interp(const ApplyParams &p, int which_other, cudaStream_t s)
 // 3-D tiled tensor map over 8-byte elements (cuTensorMapEncodeTiled through the runtime's driver entry point);
 // false when the driver does not offer it or rejects the geometry - callers then use 1-D bulk copies
 struct TmaMap;
+bool tmap_probe(const void *dev_ptr);   // can tensor maps be encoded on this driver at all?
 bool tmap_encode_f64_3d(TmaMap *out, const void *base, const uint64_t dims[3], const uint64_t strides_bytes[2],
                         const uint32_t box[3]);
 

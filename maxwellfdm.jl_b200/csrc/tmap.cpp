@@ -54,4 +54,11 @@ bool tmap_encode_f64_3d(TmaMap *out, const void *base, const uint64_t dims[3], c
 }
 #endif
 
+bool tmap_probe(const void *dev_ptr) {
+    TmaMap m;
+    const uint64_t dims[3] = {64, 4, 1}, strides[2] = {512, 2048};
+    const uint32_t box[3] = {64, 2, 1};
+    return dev_ptr != nullptr && tmap_encode_f64_3d(&m, dev_ptr, dims, strides, box);
+}
+
 }  // namespace fdfd

@@ -182,9 +182,26 @@ class FdfdOperator:
             raise ValueError(f"{name} must have {self.n} elements")
         return x
 
+    def _chk_out(self, y, like, name):
+        """an OUTPUT buffer is written in place by the library: it must already be what the C ABI expects, and live
+        where the input lives (the `where` argument covers both)"""
+        if hasattr(like, "is_cuda"):
+            import torch
+            if not hasattr(y, "is_cuda") or y.dtype != torch.complex128 or y.numel() != self.n or not y.is_contiguous():
+                raise ValueError(f"{name} must be a contiguous complex128 tensor of {self.n} elements")
+            if y.is_cuda != like.is_cuda:
+                raise ValueError(f"{name} and its input must both be host or both be device buffers")
+            return y
+        if hasattr(y, "is_cuda") or not isinstance(y, np.ndarray) or y.dtype != np.complex128 or y.shape != (self.n,) \
+                or not y.flags.c_contiguous or not y.flags.writeable:
+            raise ValueError(f"{name} must be a writeable contiguous complex128 numpy array of {self.n} elements "
+                             f"(a host buffer, like its input)")
+        return y
+
     def mul(self, y, x, transpose=False):
         """mul!(y, A, x)"""
         x = self._chk_vec(x, "x")
+        y = self._chk_out(y, x, "y")
         f = L.lib().fdfd_apply_transpose if transpose else L.lib().fdfd_apply
         L.check(f(self._h, _ptr(x), _ptr(y), _where(x)), self._h)
         return y
@@ -210,6 +227,8 @@ class FdfdOperator:
                 x = np.zeros(self.n, dtype=np.complex128)
         else:
             x = self._chk_vec(x0, "x0")
+            if hasattr(x, "is_cuda") != hasattr(b, "is_cuda") or (hasattr(x, "is_cuda") and x.is_cuda != b.is_cuda):
+                raise ValueError("x0 and b must both be host or both be device buffers")
             x = x.clone() if hasattr(x, "clone") else x.copy()
         m = L.BICGSTAB if str(method).lower().startswith("bi") else L.QMR
         iters, relres = C.c_int(), C.c_double()
@@ -279,10 +298,23 @@ class FdfdOperator:
         L.check(L.lib().fdfd_bench_solve(self._h, m, _ptr(b_dev), _ptr(x_dev), warmup, iters, C.byref(tot)), self._h)
         return tot.value
 
+    def bench_halo(self, x_dev, warmup=3, iters=20):
+        """(ms for `iters` halo exchanges of x_dev by themselves, bytes this rank sends per exchange)"""
+        tot, nb = C.c_double(), C.c_uint64()
+        L.check(L.lib().fdfd_bench_halo(self._h, _ptr(x_dev), warmup, iters, C.byref(tot), C.byref(nb)), self._h)
+        return tot.value, int(nb.value)
+
     @property
     def offdiag_fraction(self):
         f = C.c_double()
         L.check(L.lib().fdfd_offdiag_fraction(self._h, C.byref(f)), self._h)
+        return f.value
+
+    @property
+    def mass_bytes_per_dof(self):
+        """bytes per DOF the kernel streams for the diagonal material terms (16; 8 when the mass entries are real)"""
+        f = C.c_double()
+        L.check(L.lib().fdfd_mass_bytes_per_dof(self._h, C.byref(f)), self._h)
         return f.value
 
     @property

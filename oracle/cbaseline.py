@@ -23,6 +23,8 @@ def lib():
         P = C.c_void_p
         l.csc_mul_serial.argtypes = [C.c_int64, P, P, P, P, P]
         l.csr_mul_omp.argtypes = [C.c_int64, P, P, P, P, P]
+        l.bicgstab_csr_omp.argtypes = [C.c_int64, P, P, P, P, P, C.c_int, P]
+        l.bicgstab_csr_omp.restype = C.c_double
         l.oracle_num_threads.restype = C.c_int
         l.oracle_set_threads.argtypes = [C.c_int]
         _lib = l
@@ -56,6 +58,17 @@ class CsrOmp:
         lib().csr_mul_omp(self.n, self.rowptr.ctypes.data, self.colval.ctypes.data, self.nzval.ctypes.data,
                           x.ctypes.data, y.ctypes.data)
         return y
+
+
+def _bicgstab(self, b, x, iters):
+    """x <- BiCGSTAB iterate after exactly `iters` iterations from x (no convergence exit); returns ||r|| / ||b||"""
+    b = np.ascontiguousarray(b, np.complex128)
+    work = np.empty(6 * self.n, np.complex128)
+    return float(lib().bicgstab_csr_omp(self.n, self.rowptr.ctypes.data, self.colval.ctypes.data, self.nzval.ctypes.data,
+                                        b.ctypes.data, x.ctypes.data, int(iters), work.ctypes.data))
+
+
+CsrOmp.bicgstab = _bicgstab
 
 
 def num_threads():

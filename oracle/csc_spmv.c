@@ -8,6 +8,7 @@
  * bench.py --impl reference times.  Indices are 0-based int64; values are C99 double complex.
  */
 #include <complex.h>
+#include <math.h>
 #include <stdint.h>
 #include <string.h>
 #ifdef _OPENMP
@@ -31,6 +32,47 @@ void csr_mul_omp(int64_t n, const int64_t *rowptr, const int64_t *colval, const 
         for (int64_t k = rowptr[i]; k < rowptr[i + 1]; ++k) acc += nzval[k] * x[colval[k]];
         y[i] = acc;
     }
+}
+
+/* Unpreconditioned BiCGSTAB on the CSR copy, all host cores - the stand-in for "the reference's solve" (the reference
+ * stops at create_linsys, src/model/model.jl:209-220; its README leaves the solve to the user, README.md:27-33).
+ * Runs exactly `iters` iterations without a convergence exit (iterations/s measurement, like fdfd_bench_solve) and
+ * returns ||b - A x|| / ||b|| from the recurrence.  work: 6 n complex.  x holds x0 on entry. */
+static double complex zdot(int64_t n, const double complex *a, const double complex *b) {   /* conj(a) . b */
+    double re = 0, im = 0;
+#pragma omp parallel for schedule(static) reduction(+ : re, im)
+    for (int64_t i = 0; i < n; ++i) {
+        const double complex t = conj(a[i]) * b[i];
+        re += creal(t);
+        im += cimag(t);
+    }
+    return re + im * I;
+}
+
+double bicgstab_csr_omp(int64_t n, const int64_t *rowptr, const int64_t *colval, const double complex *nzval,
+                        const double complex *b, double complex *x, int iters, double complex *work) {
+    double complex *r = work, *rh = work + n, *p = work + 2 * n, *v = work + 3 * n, *s = work + 4 * n, *t = work + 5 * n;
+    csr_mul_omp(n, rowptr, colval, nzval, x, r);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) { r[i] = b[i] - r[i]; rh[i] = r[i]; p[i] = 0; v[i] = 0; }
+    double complex rho = 1, alpha = 1, om = 1;
+    const double bn = sqrt(creal(zdot(n, b, b)));
+    for (int it = 0; it < iters; ++it) {
+        const double complex rho1 = zdot(n, rh, r);
+        const double complex beta = (rho1 / rho) * (alpha / om);
+        rho = rho1;
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < n; ++i) p[i] = r[i] + beta * (p[i] - om * v[i]);
+        csr_mul_omp(n, rowptr, colval, nzval, p, v);
+        alpha = rho / zdot(n, rh, v);
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < n; ++i) s[i] = r[i] - alpha * v[i];
+        csr_mul_omp(n, rowptr, colval, nzval, s, t);
+        om = zdot(n, t, s) / zdot(n, t, t);
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < n; ++i) { x[i] += alpha * p[i] + om * s[i]; r[i] = s[i] - om * t[i]; }
+    }
+    return sqrt(creal(zdot(n, r, r))) / (bn > 0 ? bn : 1.0);
 }
 
 /* torchrun exports OMP_NUM_THREADS=1 to its workers; the all-cores baseline sets its team size explicitly. */

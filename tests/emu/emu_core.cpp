@@ -431,6 +431,8 @@ void tma_load_3d(void *dst, const unsigned long long *map, int c0, int c1, int c
     const long b0 = (long)map[6], b1 = (long)map[7], b2 = (long)map[8];
     if (!base || b0 <= 0) die("tensor-map load through an unencoded map");
     if (((uintptr_t)dst & 127) != 0) die("tensor-map load: shared destination not 128-byte aligned");
+    if (((long)c0 * 8) % 16 != 0) die("tensor-map load: box starts at element %d - not on a 16-byte boundary of the global array", c0);
+    if ((b0 * 8) % 16 != 0) die("tensor-map load: inner box extent %ld bytes is not a multiple of 16", b0 * 8);
     check_smem_range(dst, (uint32_t)(b0 * b1 * b2 * 8), "cp.async.bulk.tensor global->shared");
     unsigned char *out = static_cast<unsigned char *>(dst);
     auto push = [&](void *d, const void *s, long n) {
@@ -459,6 +461,7 @@ void tma_store_3d(const unsigned long long *map, int c0, int c1, int c2, const v
     const long b0 = (long)map[6], b1 = (long)map[7], b2 = (long)map[8];
     if (!base || b0 <= 0) die("tensor-map store through an unencoded map");
     if (((uintptr_t)src & 127) != 0) die("tensor-map store: shared source not 128-byte aligned");
+    if (((long)c0 * 8) % 16 != 0) die("tensor-map store: box starts at element %d - not on a 16-byte boundary of the global array", c0);
     check_smem_range(src, (uint32_t)(b0 * b1 * b2 * 8), "cp.async.bulk.tensor shared->global");
     const unsigned char *in = static_cast<const unsigned char *>(src);
     for (long z = 0; z < b2; ++z)

@@ -6,6 +6,7 @@ compiled for the CPU, tests/emu/README.md) and checks every result against the o
 Must run in its own process: the ctypes binding loads whatever FDFD_B200_LIB names, once.  "Device" buffers are host
 memory here, so the FDFD_DEVICE entry points are called with numpy arrays.  Started by tests/test_emu_kernels_cpu.py
 with FDFD_EMU_ASYNC / FDFD_EMU_SHUFFLE set to the scheduling mode under test."""
+import ctypes as C
 import itertools
 import os
 import sys
@@ -59,6 +60,47 @@ def g_apply():
                 A.close()
                 n += 1
     return n
+
+
+def g_realmass():
+    """real diagonal mass entries (lossless medium, real omega): material rows travel as doubles (MDR instantiations of
+    the row-pair kernel) - every boundary combination, Bloch wrap tiles, several items per CTA, both uniform
+    arrangements and a mixed one, full eps through the correction pass, transposed apply, fused dots via BiCGSTAB"""
+    n = 0
+    combos = list(itertools.product([True, False], repeat=3))
+    for N in [(3, 3, 2), (33, 17, 9), (70, 45, 6), (31, 40, 5)]:
+        for i, isbloch in enumerate(combos):
+            if not FULL and (i + sum(N)) % 2 != 0:
+                continue
+            for full_eps in (False, True):
+                p = Problem(N, isbloch, full_eps=full_eps, real_mass=True)
+                A_ref, _ = p.oracle_csc()
+                A = p.operator(device=0, kernel=TILED)
+                x = p.random_x()
+                check(rel(apply_dev(A, x), A_ref.matvec(x)), f"real-mass apply {N} {isbloch} full={full_eps}")
+                check(rel(apply_dev(A, x, transpose=True), A_ref.to_scipy().T @ x), f"real-mass transpose {N} {isbloch}")
+                A.close()
+                n += 2
+    for boundft in [(HH, HH, HH), (EE, HH, EE)]:
+        for ft in (EE, HH):
+            p = Problem((34, 19, 7), (True, False, True), boundft=boundft, ft=ft, with_mu=(ft == HH), real_mass=True)
+            A_ref, _ = p.oracle_csc()
+            A = p.operator(device=0, kernel=TILED)
+            x = p.random_x()
+            check(rel(apply_dev(A, x), A_ref.matvec(x)), f"real-mass apply boundft={boundft} ft={ft}")
+            A.close()
+            n += 1
+    p = Problem((12, 9, 6), (True, True, False), real_mass=True, npml=2)
+    A_ref, _ = p.oracle_csc()
+    A = p.operator(device=0, kernel=TILED)
+    b = A_ref.matvec(p.random_x(3))
+    xs = np.zeros(A.n, complex)
+    iters, relres = C.c_int(), C.c_double()
+    L.check(L.lib().fdfd_solve(A._h, L.BICGSTAB, b.ctypes.data, xs.ctypes.data, L.DEVICE, 1e-10, 4000, 5,
+                               C.byref(iters), C.byref(relres), None), A._h, ok=(L.OK, L.ENOCONV))
+    check(rel(A_ref.matvec(xs), b), "real-mass BiCGSTAB true residual", 1e-8)
+    A.close()
+    return n + 1
 
 
 def g_boundft():
@@ -281,7 +323,7 @@ def g_reduced():
     return n
 
 
-GROUPS = {"reduced": g_reduced, "matparams": g_matparams, "apply": g_apply, "boundft": g_boundft, "layouts": g_layouts, "deep": g_deep, "solve": g_solve, "aux": g_aux}
+GROUPS = {"realmass": g_realmass, "reduced": g_reduced, "matparams": g_matparams, "apply": g_apply, "boundft": g_boundft, "layouts": g_layouts, "deep": g_deep, "solve": g_solve, "aux": g_aux}
 
 
 def main():

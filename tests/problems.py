@@ -23,7 +23,7 @@ class Problem:
 
     def __init__(self, N, isbloch=(True, True, True), boundft=(EE, EE, EE), full_eps=False, with_mu=False,
                  ft=EE, omega=1.1 - 0.05j, npml=1, uniform=False, seed=SEED, cmpfirst=True, weighted_out=False,
-                 kb_scale=1.0, full_mu=False):
+                 kb_scale=1.0, full_mu=False, real_mass=False):
         rng = np.random.default_rng(seed)
         self.N = tuple(int(n) for n in N)
         self.isbloch = tuple(bool(b) for b in isbloch)
@@ -49,6 +49,13 @@ class Problem:
         if full_mu:   # only meaningful for ft == HH (mu is the mass parameter there, model.jl:238-240)
             for v, u in itertools.permutations(range(3), 2):
                 self.mu[..., v, u] = 0.25 * crandn(rng, *self.N)
+        if real_mass:
+            # lossless medium at a real frequency: the diagonal mass entries -w^2 eps_vv are real (the kernel then
+            # streams them as doubles, apply_rowpair.cu MDR); PML stretch, Bloch phases and off-diagonals stay complex
+            self.omega = omega = float(np.real(omega))
+            mass = self.eps if ft == EE else self.mu
+            for v in range(3):
+                mass[..., v, v] = np.real(mass[..., v, v])
         self.with_mu, self.full_eps = with_mu or full_mu, full_eps
         self.n = 3 * int(np.prod(self.N))
         self.rng = rng

@@ -70,6 +70,26 @@ def test_no_cpu_fallback_without_gpu():
         A.solve(p.random_x())
 
 
+def test_output_buffers_are_validated_before_the_c_call():
+    """mul!(y, A, x) / solve(b, x0): the library writes y / reads x0 through raw pointers, so the Python mirror rejects
+    a wrong dtype, size, stride or a host / device mix instead of handing it to the C ABI."""
+    import torch
+    L = _lib()
+    p = Problem((4, 3, 2), (True, True, True))
+    A = p.operator(device=-2)          # validation happens before the C call, so no GPU is needed to see it
+    x = p.random_x()
+    for bad in (np.empty(A.n, np.float64), np.empty(A.n - 1, np.complex128), np.empty(2 * A.n, np.complex128)[::2],
+                [0j] * A.n, torch.empty(A.n, dtype=torch.complex128)):
+        with pytest.raises(ValueError):
+            A.mul(bad, x)
+    with pytest.raises(ValueError):
+        A.mul(np.empty(A.n, np.complex128), torch.from_numpy(x))      # torch input, numpy output
+    with pytest.raises(ValueError):
+        A.solve(x, x0=torch.zeros(A.n, dtype=torch.complex128))       # numpy b, torch x0
+    with pytest.raises(L.FdfdError):                                  # a well-formed call reaches the library
+        A.mul(np.empty(A.n, np.complex128), x)
+
+
 def _check_export(p):
     A, _ = p.oracle_csc()
     cp_ref, rv_ref = A.julia_pattern()

@@ -41,6 +41,25 @@ def test_emulated_apply_kernels_match_oracle(emu_lib, mode):
     assert out.count("checks ok") == 4, out
 
 
+def test_emulated_real_mass_rows(emu_lib):
+    """row-pair kernel with real diagonal mass entries streamed as doubles (MDR), a persistent grid of two CTAs so that
+    every CTA walks several work items"""
+    out = _run(emu_lib, ["realmass"], "eager", 2, FDFD_RP_GRID="2")
+    assert "checks ok" in out, out
+
+
+def test_emulated_row_pair_kernel_without_tensor_maps(emu_lib):
+    """the 1-D bulk-copy path of the row-pair kernel (FDFD_RP_TMAP=0; also what the component-major layout takes)"""
+    out = _run(emu_lib, ["apply", "deep"], "lazy", 4, FDFD_RP_TMAP="0", FDFD_RP_GRID="3")
+    assert out.count("checks ok") == 2, out
+
+
+def test_emulated_first_generation_kernel(emu_lib):
+    """FDFD_K1_GEN=1 keeps the first-generation tiled kernel reachable (A/B timing, on-device cross-check)"""
+    out = _run(emu_lib, ["apply", "boundft"], "lazy", 6, FDFD_K1_GEN="1")
+    assert out.count("checks ok") == 2, out
+
+
 def test_emulated_material_pipeline_matches_oracle(emu_lib):
     out = _run(emu_lib, ["matparams"], "eager", 7)
     assert "checks ok" in out, out

@@ -66,6 +66,48 @@ def test_apply_all_boundary_conditions(kernel, N):
             assert err < TOL, (kernel, N, isbloch, full_eps, with_mu, err)
 
 
+@pytest.mark.parametrize("N", [(3, 3, 2), (33, 17, 9), (70, 45, 6), (31, 40, 5), (64, 50, 40)])
+def test_apply_real_mass_rows(N):
+    """lossless medium at a real frequency: the diagonal mass entries are real and the row-pair kernel streams them as
+    doubles (MDR instantiations; odd Nx exercises the padded row pitch of the tensor map) - every boundary combination,
+    diagonal and full eps (correction pass on top), forward and transposed, against the oracle's CSC product."""
+    for isbloch in itertools.product([True, False], repeat=3):
+        for full_eps in (False, True):
+            p = Problem(N, isbloch, full_eps=full_eps, real_mass=True)
+            A_ref, _ = p.oracle_csc()
+            A = p.operator(device=0, kernel=KERNELS["tiled"])
+            x = p.random_x()
+            err = rel(_apply_dev(A, x), A_ref.matvec(x))
+            errT = rel(_apply_dev(A, x, transpose=True), A_ref.to_scipy().T.tocsc() @ x)
+            A.close()
+            assert err < TOL and errT < TOL, (N, isbloch, full_eps, err, errT)
+
+
+def test_real_mass_rows_other_arrangements_and_solve():
+    """MDR on the mirrored and a mixed arrangement, both formulations; BiCGSTAB (fused dots in the apply epilogue) and
+    QMR (transposed operator) on a real-mass problem against a sparse direct solve."""
+    import scipy.sparse.linalg as spla
+    torch = _torch()
+    for boundft in [(HH, HH, HH), (EE, HH, EE)]:
+        for ft in (EE, HH):
+            p = Problem((34, 19, 7), (True, False, True), boundft=boundft, ft=ft, with_mu=(ft == HH), real_mass=True)
+            A_ref, _ = p.oracle_csc()
+            A = p.operator(device=0, kernel=KERNELS["tiled"])
+            x = p.random_x()
+            err = rel(_apply_dev(A, x), A_ref.matvec(x))
+            A.close()
+            assert err < TOL, (boundft, ft, err)
+    p = Problem((14, 11, 9), (True, True, False), real_mass=True, npml=2, omega=1.1)
+    A_ref, _ = p.oracle_csc()
+    b = A_ref.matvec(p.random_x(3))
+    x_ref = spla.splu(A_ref.to_scipy()).solve(b)
+    A = p.operator(device=0, kernel=KERNELS["tiled"])
+    for method in ("bicgstab", "qmr"):
+        xs, info = A.solve(torch.from_numpy(b).cuda(), method=method, rtol=1e-11, maxit=20000, check_every=10)
+        assert rel(xs.cpu().numpy(), x_ref) < 1e-8, (method, info)
+    A.close()
+
+
 @pytest.mark.parametrize("boundft", list(itertools.product([EE, HH], repeat=3)))
 def test_apply_all_boundft(boundft):
     """all 2^3 boundft choices, both formulations, on the tiled kernel (ARR = 0 / 1 / 2 instantiations)."""

@@ -60,14 +60,14 @@ def c1_rhs(w):
     return fb.create_srcs(mdl)
 
 
-def c2_waveguide(N=(200, 200, 200), k0=0, k1=None, period_z=None, seed=20261017, delta=20.0):
+def c2_waveguide(N=(200, 200, 200), k0=0, k1=None, period_z=None, seed=20261017, delta=20.0, npml=10):
     """C2: Si strip (eps 12.085, 500 x 220 nm, along x) in SiO2 (eps 2.085), 10-cell PML on all sides.
     Subpixel-smoothing stand-in: arithmetic/harmonic mixing on cells cut by the (axis-aligned) interfaces
     for the diagonal entries, plus a seeded random SYMMETRIC off-diagonal perturbation 0.2*(U-0.5) on
     the interface cells so the full-tensor path is exercised.  For weak scaling the cross-section repeats
     every `period_z` planes so that every z-slab carries the same work."""
     Nx, Ny, Nz = N
-    w = _common(N, delta, (False, False, False), ((10,) * 3, (10,) * 3))
+    w = _common(N, delta, (False, False, False), ((npml,) * 3, (npml,) * 3))
     k1 = Nz if k1 is None else k1
     period_z = Nz if period_z is None else period_z
     e_si, e_ox = 12.085, 2.085
@@ -106,6 +106,31 @@ def c2_waveguide(N=(200, 200, 200), k0=0, k1=None, period_z=None, seed=20261017,
         eps[..., u, v] = pert
     w.update(eps=eps, k0=k0, k1=k1, full_eps=True,
              name=f"C2 Si strip waveguide in SiO2 {Nx}x{Ny}x{Nz}, full 3x3 eps, 10-cell PML")
+    return w
+
+
+def make_dense_offdiag(w, seed=7):
+    """variant of a workload with a non-zero (symmetric) off-diagonal eps entry in EVERY cell: the fused full-tensor
+    kernel path instead of diagonal kernel + correction pass"""
+    rng = np.random.default_rng(seed)
+    for (v, u) in ((0, 1), (0, 2), (1, 2)):
+        pert = 0.05 * (rng.random(w["eps"].shape[:3]) - 0.5)
+        w["eps"][..., v, u] = pert
+        w["eps"][..., u, v] = pert
+    w["full_eps"] = True
+    w["name"] += " [dense off-diagonal variant]"
+    return w
+
+
+def c2_hh(N=(200, 200, 200)):
+    """the C2 grid for the HH formulation A = Ce eps^-1 Cm - w^2 mu (model.jl:238-240): needs a diagonal eps, mu = 1"""
+    w = c2_waveguide(N)
+    for v in range(3):
+        for u in range(3):
+            if u != v:
+                w["eps"][..., v, u] = 0
+    w["full_eps"] = False
+    w["name"] = f"C2 grid {N[0]}x{N[1]}x{N[2]}, HH formulation, diagonal eps, mu = 1"
     return w
 
 
