@@ -276,7 +276,7 @@ def bytes_per_dof(A, w):
     the (tile, plane) blocks that hold any: 32, or 16 when the tensor is symmetric and stored once)"""
     off = A.offdiag_fraction if w.get("full_eps") else 0.0
     sym = bool(w.get("full_eps") and A.offdiag_symmetric)
-    return 32.0 + A.mass_bytes_per_dof + (16 if sym else 32) * off, off, sym
+    return 32.0 + A.mass_bytes_per_dof + A.offdiag_bytes_per_dof * off, off, sym
 
 
 def measure_config(name, w, local, rank, world, steps, kry_iters, gen, extra=None, **opkw):

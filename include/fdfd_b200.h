@@ -207,6 +207,11 @@ int fdfd_offdiag_symmetric(fdfd_handle h, int *symmetric);
  * or the parameter is the identity) plus 16 for the inverse middle parameter when one was supplied.  With the 32 B of
  * x and y and the off-diagonal streams (fdfd_offdiag_fraction) this is the algorithmic traffic of one apply. */
 int fdfd_mass_bytes_per_dof(fdfd_handle h, double *bytes);
+/* Bytes per DOF the off-diagonal material streams cost on a block that holds any (fdfd_offdiag_fraction of the blocks):
+ * 32 for a general tensor, 16 for a pointwise symmetric one (three arrays), 8 when it is symmetric with real entries and
+ * the fused row-pair kernel streams them as doubles through its TMA ring; 0 when there are none.  Algorithmic traffic
+ * of one apply = 32 + fdfd_mass_bytes_per_dof + fdfd_offdiag_bytes_per_dof * fdfd_offdiag_fraction  [B/DOF]. */
+int fdfd_offdiag_bytes_per_dof(fdfd_handle h, double *bytes);
 /* Number of kernels this handle has launched since creation (for bench.py's gpu_launches). */
 int64_t fdfd_launch_count(fdfd_handle h);
 

@@ -81,6 +81,7 @@ SYMBOLS = {
     "fdfd_mass_bytes_per_dof": (C.c_int, [P, C.POINTER(C.c_double)]),
     "fdfd_bench_halo": (C.c_int, [P, P, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "fdfd_offdiag_fraction": (C.c_int, [P, C.POINTER(C.c_double)]),
+    "fdfd_offdiag_bytes_per_dof": (C.c_int, [P, C.POINTER(C.c_double)]),
     "fdfd_offdiag_symmetric": (C.c_int, [P, C.POINTER(C.c_int)]),
     "fdfd_launch_count": (C.c_int64, [P]),
     "fdfd_host_alloc": (C.c_int, [C.POINTER(P), C.c_uint64]),

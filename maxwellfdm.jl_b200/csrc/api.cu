@@ -60,6 +60,34 @@ __global__ void interleave3_real_kernel(double *dst, const double2 *s0, const do
     }
     if (bad) *any_imag = 1;
 }
+// the three off-diagonal arrays of a symmetric tensor, real parts, interleaved and padded by one cell / row on either side
+// in x and y (wrapped copies on Bloch axes, zeros otherwise): the fused row-pair kernel's tensor-map boxes then deliver
+// the forward neighbours of edge tiles without any patching.  n = padded elements; *any_imag as above.
+__global__ void interleave3_real_pad_kernel(double *dst, const double2 *s0, const double2 *s1, const double2 *s2, int64_t n,
+                                            int Nx, int Ny, int wrapx, int wrapy, int64_t pitch, int *any_imag) {
+    bool bad = false;
+    const int Px = Nx + 2, Py = Ny + 2;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+        const int ip = (int)(t % Px);
+        const int64_t row = t / Px;                  // g * Py + jp
+        const int jp = (int)(row % Py);
+        const int64_t g = row / Py;
+        int i = ip - 1, j = jp - 1;
+        bool in = true;
+        if (i < 0 || i >= Nx) { in = in && wrapx; i = (i + Nx) % Nx; }
+        if (j < 0 || j >= Ny) { in = in && wrapy; j = (j + Ny) % Ny; }
+        double a = 0.0, b = 0.0, c = 0.0;
+        if (in) {
+            const int64_t src = (g * Ny + j) * Nx + i;
+            const double2 va = s0[src], vb = s1[src], vc = s2[src];
+            a = va.x; b = vb.x; c = vc.x;
+            bad |= (va.y != 0.0) | (vb.y != 0.0) | (vc.y != 0.0);
+        }
+        double *d = dst + row * pitch + (int64_t)ip * 3;
+        d[0] = a; d[1] = b; d[2] = c;
+    }
+    if (bad) *any_imag = 1;
+}
 __global__ void flush_kernel(float4 *p, int64_t n, float v) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         p[i] = make_float4(v, v, v, v);
@@ -72,7 +100,7 @@ static inline int nblocks(int64_t n) {
 
 static void free_device(Ctx *c) {
     auto F = [](auto *&p) { if (p) cudaFree((void *)p); p = nullptr; };
-    F(c->coef_dev); F(c->mat_dev); F(c->md_aos); F(c->md_aos_r); F(c->halo_lo); F(c->halo_hi); F(c->work); F(c->scal); F(c->partial);
+    F(c->coef_dev); F(c->mat_dev); F(c->md_aos); F(c->md_aos_r); F(c->mo_aos_r); F(c->halo_lo); F(c->halo_hi); F(c->work); F(c->scal); F(c->partial);
     F(c->stage_x); F(c->stage_y); F(c->flush_buf); F(c->offmask); F(c->corr_list); F(c->dot_partial); F(c->dot_ticket);
     F(c->halo_flag);
     if (c->scal_host) cudaFreeHost(c->scal_host);
@@ -185,6 +213,7 @@ static int upload_materials(Ctx *c) {
     }
     if (c->md_aos) { cudaFree(c->md_aos); c->md_aos = nullptr; }
     if (c->md_aos_r) { cudaFree(c->md_aos_r); c->md_aos_r = nullptr; }
+    if (c->mo_aos_r) { cudaFree(c->mo_aos_r); c->mo_aos_r = nullptr; }
     if (!narr) return FDFD_OK;
     double2 *objbuf = nullptr;                  // objects: the smoothed slab in Julia layout, on the device
     if (obj && has_mass) {
@@ -290,6 +319,25 @@ static int upload_materials(Ctx *c) {
             return !(a && atoi(a) == 0) && !(t && atoi(t) == 0);
         }();
         bool real_rows = false;
+        // z-slabs: every rank takes the same kernel variant (the fused dots and the graphs assume one plan)
+        int r_any = FDFD_OK;
+        auto any_rank = [&](int &flag_io) -> int {
+            if (c->d.nranks <= 1) return FDFD_OK;
+            double *f = nullptr;
+            const double hv = flag_io ? 1.0 : 0.0;
+            FDFD_CUDA(c, cudaMalloc((void **)&f, sizeof(double)));
+            FDFD_CUDA(c, cudaMemcpyAsync(f, &hv, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+            int ra = allreduce_sum(c, f, 1, c->stream);
+            double gv = 1.0;
+            if (ra == FDFD_OK) {
+                FDFD_CUDA(c, cudaMemcpyAsync(&gv, f, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+                FDFD_CUDA(c, cudaStreamSynchronize(c->stream));
+            }
+            cudaFree(f);
+            if (ra != FDFD_OK) return ra;
+            flag_io = gv > 0.0;
+            return FDFD_OK;
+        };
         if (allow_real && tmap_probe(c->md[0])) {
             int *flag = nullptr;
             FDFD_CUDA(c, cudaMalloc((void **)&flag, sizeof(int)));
@@ -304,22 +352,7 @@ static int upload_materials(Ctx *c) {
             FDFD_CUDA(c, cudaMemcpyAsync(&any_imag, flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
             FDFD_CUDA(c, cudaStreamSynchronize(c->stream));
             cudaFree(flag);
-            if (c->d.nranks > 1) {
-                // z-slabs: every rank takes the same kernel variant (the fused dots and the graphs assume one plan)
-                double *f = nullptr;
-                const double hv = any_imag ? 1.0 : 0.0;
-                FDFD_CUDA(c, cudaMalloc((void **)&f, sizeof(double)));
-                FDFD_CUDA(c, cudaMemcpyAsync(f, &hv, sizeof(double), cudaMemcpyHostToDevice, c->stream));
-                int ra = allreduce_sum(c, f, 1, c->stream);
-                double gv = 1.0;
-                if (ra == FDFD_OK) {
-                    FDFD_CUDA(c, cudaMemcpyAsync(&gv, f, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-                    FDFD_CUDA(c, cudaStreamSynchronize(c->stream));
-                }
-                cudaFree(f);
-                if (ra != FDFD_OK) return ra;
-                any_imag = gv > 0.0;
-            }
+            if ((r_any = any_rank(any_imag)) != FDFD_OK) return r_any;
             real_rows = !any_imag;
             if (!real_rows) { cudaFree(c->md_aos_r); c->md_aos_r = nullptr; }
         }
@@ -327,6 +360,30 @@ static int upload_materials(Ctx *c) {
             FDFD_CUDA(c, cudaMalloc((void **)&c->md_aos, (size_t)3 * Mg * sizeof(double2)));
             interleave3_kernel<<<nblocks(Mg), 256, 0, c->stream>>>(c->md_aos, c->md[0], c->md[1], c->md[2], Mg);
             FDFD_CUDA(c, cudaGetLastError());
+        }
+        // Symmetric off-diagonal entries that are real as well (the smoothed tensor of lossless media): a third,
+        // interleaved and padded copy for the fused full-tensor shape of the row-pair kernel (8 B/DOF on the flagged blocks
+        // instead of 16).  FDFD_RP_FUSED=0 keeps the two-pass / first-generation plans (A/B timing).
+        static const bool allow_fused = [] { const char *a = getenv("FDFD_RP_FUSED"); return !(a && atoi(a) == 0); }();
+        if (real_rows && allow_fused && c->mo[0] && c->off_sym) {
+            int *flag = nullptr;
+            FDFD_CUDA(c, cudaMalloc((void **)&flag, sizeof(int)));
+            FDFD_CUDA(c, cudaMemsetAsync(flag, 0, sizeof(int), c->stream));
+            const int Nx = (int)c->d.N[0], Ny = (int)c->d.N[1];
+            const int64_t pitch = mdr_row_pitch(Nx + 2), nrow = (int64_t)(Ny + 2) * (nzl + 2);
+            const int64_t npad = (int64_t)(Nx + 2) * nrow;
+            FDFD_CUDA(c, cudaMalloc((void **)&c->mo_aos_r, (size_t)(pitch * nrow) * sizeof(double)));
+            FDFD_CUDA(c, cudaMemsetAsync(c->mo_aos_r, 0, (size_t)(pitch * nrow) * sizeof(double), c->stream));
+            // order of c->mo: (0,1), (0,2), (1,0), (1,2), (2,0), (2,1)
+            interleave3_real_pad_kernel<<<nblocks(npad), 256, 0, c->stream>>>(c->mo_aos_r, c->mo[0], c->mo[1], c->mo[3], npad, Nx, Ny,
+                                                                             c->d.isbloch[0] ? 1 : 0, c->d.isbloch[1] ? 1 : 0, pitch, flag);
+            FDFD_CUDA(c, cudaGetLastError());
+            int any_imag = 1;
+            FDFD_CUDA(c, cudaMemcpyAsync(&any_imag, flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+            FDFD_CUDA(c, cudaStreamSynchronize(c->stream));
+            cudaFree(flag);
+            if ((r_any = any_rank(any_imag)) != FDFD_OK) return r_any;
+            if (any_imag) { cudaFree(c->mo_aos_r); c->mo_aos_r = nullptr; }
         }
     }
     FDFD_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -355,8 +412,11 @@ int ensure_ready(Ctx *c) {
     if (c->mo[0] && c->d.kernel != FDFD_KERNEL_NAIVE) {
         ApplyParams p;
         fill_params(c, p, nullptr, nullptr, false);
+        // the fused row-pair shape takes the operator from a few per cent of flagged blocks on (FDFD_RP_FUSE_MIN, measured
+        // choice - DESIGN.md section 5); without it the first-generation fused kernel pays off above 25 %
+        static const double fuse_min_rp = [] { const char *e = getenv("FDFD_RP_FUSE_MIN"); return e ? atof(e) : 0.03; }();
         FDFD_CUDA(c, tiled_build_offmask(p, &c->offmask, &c->offmask_ty, &c->off_frac, &c->corr_list, &c->corr_count,
-                                         c->stream));
+                                         c->stream, c->mo_aos_r ? fuse_min_rp : 0.25));
     }
     c->dirty = false;
     return FDFD_OK;
@@ -376,6 +436,7 @@ void fill_params(Ctx *c, ApplyParams &p, const double2 *x, double2 *y, bool tran
     for (int i = 0; i < 3; ++i) { p.md[i] = c->md[i]; p.q[i] = c->q[i]; }
     p.md_aos = c->md_aos;
     p.md_aos_r = c->md_aos_r;
+    p.mo_aos_r = c->mo_aos_r;
     for (int i = 0; i < 6; ++i) p.mo[i] = transpose ? c->mo_t[i] : c->mo[i];
     const int64_t Nxy = Nx * Ny;
     p.x.base = x;
@@ -1315,6 +1376,17 @@ int fdfd_mass_bytes_per_dof(fdfd_handle h, double *bytes) {
     double b = (c->has_mass && c->md[0]) ? (c->md_aos_r ? 8.0 : 16.0) : 0.0;
     if (c->q[0]) b += 16.0;   // inverse middle parameter (mu^-1 for FT_EE with a mu array, eps^-1 for FT_HH)
     *bytes = b;
+    return FDFD_OK;
+}
+
+int fdfd_offdiag_bytes_per_dof(fdfd_handle h, double *bytes) {
+    CHECK_H(h);
+    if (!bytes) return set_err(c, FDFD_EINVAL, "null argument");
+    int r = ensure_ready(c);
+    if (r != FDFD_OK) return r;
+    // the fused row-pair shape runs when its arrays exist and the occupancy mask was built on its tiles
+    const bool fused_real = c->mo_aos_r != nullptr && c->offmask_ty == 16 && c->d.kernel != FDFD_KERNEL_NAIVE;
+    *bytes = !c->mo[0] ? 0.0 : fused_real ? 8.0 : c->off_sym ? 16.0 : 32.0;
     return FDFD_OK;
 }
 

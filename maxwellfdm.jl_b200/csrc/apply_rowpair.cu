@@ -44,8 +44,7 @@ constexpr bool RP_ABL = true;
 constexpr bool RP_ABL = false;
 #endif
 constexpr int RP_TX = 32;          // data columns per tile (30 outputs)
-constexpr int RP_LZMAX = 62;       // max planes per z-chunk
-constexpr int RP_LZP = RP_LZMAX + 2;
+constexpr int RP_LZMAX = 62;       // max planes per z-chunk (30 for the full-tensor variant: its tables are twice as many)
 
 struct RowPairParams {
     ApplyParams a;
@@ -55,30 +54,44 @@ struct RowPairParams {
     int32_t nitems;
     // tensor-map TMA path (cmp-first layout): x planes [0,nzl), the plane below / above the slab, interleaved material,
     // and y (store boxes of 30 cells x 2 rows); tmap = 0: 1-D bulk row copies instead
-    TmaMap mx, mlo, mhi, mmd, my;
+    TmaMap mx, mlo, mhi, mmd, mmo, my;
     int32_t tmap;
     int32_t dbg;   // timing experiments only (FDFD_RP_DEBUG bit mask; results are wrong): 1 no material loads,
                    // 2 no y stores, 4 no x loads, 8 no arithmetic
 };
 
-template <int NWC, int NST, bool MDR>
+template <int NWC, int NST, bool MDR, bool HAS_OFF>
 struct RPCfg {
     static constexpr int NR = 2 * NWC + 2;            // E rows per ring stage
-    static constexpr int NM = 2 * NWC;                // material rows per ring stage (output rows only)
+    static constexpr int NM = 2 * NWC;                // diagonal-material rows per ring stage (output rows only)
+    static constexpr int NO = HAS_OFF ? NM + 1 : 0;   // off-diagonal-material rows (output rows + the row the last G_y needs)
     static constexpr int NT = 32 * (NWC + 1);
     static constexpr int MD0 = NR * RP_TX * 3;        // offset of the material rows inside a stage
     // real material rows: 3 doubles per cell; a tensor-map box must start on a 16-byte boundary of the global array,
     // i.e. at an even cell, so the box is 34 cells wide and starts at the even cell at or below the tile origin
     static constexpr int MDCELLS = MDR ? RP_TX + 2 : RP_TX;
     static constexpr int MDROW = MDR ? MDCELLS * 3 / 2 : RP_TX * 3;          // double2 per material row
-    static constexpr int STAGE = (NR * RP_TX * 3 + NM * MDROW + 7) / 8 * 8;  // double2 per ring stage (128-byte multiple)
+    static constexpr int MO0 = (MD0 + NM * MDROW + 7) / 8 * 8;   // offset of the off-diagonal rows (tensor-map boxes land on 128-byte boundaries)
+    static constexpr int STAGE = (MO0 + NO * MDROW + 7) / 8 * 8;             // double2 per ring stage (128-byte multiple)
     static constexpr int FPAD = 8;                    // slack below stage 0 / above the last stage (halo-lane over-reads)
     static constexpr int YW = 2 * RP_TX * 3;          // per-warp y staging (two rows)
-    static constexpr int TABS = 4 * NR + 4 * RP_LZP;  // per-item tables: a0,a1,b0,b1 for y (NR rows) and z (planes)
+    // per-item tables: a0,a1,b0,b1 (+ mi0,mi1,mo0,mo1 for the full tensor) for y (NR rows) and z (planes); the
+    // full-tensor variant also keeps the x tables of the two averages here (the curl's x tables live in registers)
+    static constexpr int NTAB = HAS_OFF ? 8 : 4;
+    static constexpr int LZP = HAS_OFF ? 32 : RP_LZMAX + 2;
+    static constexpr int LZMAX = LZP - 2;
+    static constexpr int XT0 = NTAB * NR + NTAB * LZP;
+    static constexpr int TABS = XT0 + (HAS_OFF ? 4 * RP_TX : 0);
     static constexpr size_t smem_bytes() {
-        return (size_t)(FPAD + NST * STAGE + FPAD + NWC * YW + 2 * TABS) * sizeof(double2) + 3 * NST * 8 + 128;
+        return (size_t)(FPAD + NST * STAGE + FPAD + NWC * YW + 2 * TABS) * sizeof(double2) + 3 * NST * 8 + NST * 4 + 128;
     }
 };
+
+// real coefficient times complex value (the full-tensor variant's material entries are real)
+__device__ __forceinline__ double2 r_mul(double a, double2 z) { return make_double2(a * z.x, a * z.y); }
+__device__ __forceinline__ double2 r_fma(double a, double2 z, double2 acc) {
+    return make_double2(fma(a, z.x, acc.x), fma(a, z.y, acc.y));
+}
 
 // chunk c of nch over [kb, ke): sizes differ by at most one plane
 __host__ __device__ __forceinline__ int chunk_begin(int kb, int ke, int nch, int c) {
@@ -88,11 +101,16 @@ __host__ __device__ __forceinline__ int chunk_begin(int kb, int ke, int nch, int
 // MDR: the diagonal mass entries are REAL (real omega and real eps_vv - every lossless dielectric): the ring carries
 // 8 instead of 16 bytes per entry (40 instead of 48 B/DOF of HBM traffic) and the mass term costs half the flops.
 // Tensor-map path only (the rows are 24 B per cell, which 1-D bulk copies cannot always address in 16-B units).
-template <bool CMPFIRST, bool HAS_Q, bool DOT, int ARR, bool MDR, int NWC, int NST>
+// HAS_OFF: the fused full 3x3 tensor (symmetric, real entries): the three off-diagonal entries of every corner travel
+// through the ring as a third group of rows; G = P_off (M_in x) is formed one plane ahead, its z component in registers,
+// and planes whose (tile, plane) block holds no off-diagonal material are skipped (occupancy mask, as in apply_tiled.cu).
+template <bool CMPFIRST, bool HAS_Q, bool DOT, int ARR, bool MDR, bool HAS_OFF, int NWC, int NST>
 __global__ void __launch_bounds__(32 * (NWC + 1), 1) apply_rowpair_kernel(const __grid_constant__ RowPairParams tp) {
     static_assert(!MDR || CMPFIRST, "real material rows exist for the cmp-first layout only");
-    using C = RPCfg<NWC, NST, MDR>;
-    constexpr int NR = C::NR, NM = C::NM, NT = C::NT, STAGE = C::STAGE, MD0 = C::MD0, TX = RP_TX, LZP = RP_LZP;
+    static_assert(!HAS_OFF || MDR, "the fused full-tensor variant is built for real, symmetric material");
+    using C = RPCfg<NWC, NST, MDR, HAS_OFF>;
+    constexpr int NR = C::NR, NM = C::NM, NT = C::NT, STAGE = C::STAGE, MD0 = C::MD0, TX = RP_TX, LZP = C::LZP;
+    constexpr int NTAB = C::NTAB;
     const ApplyParams &p = tp.a;
     // direction of the first curl's neighbour per axis: compile-time for the two uniform arrangements (ARR 0: the
     // reference default boundft = (EE,EE,EE) with FT_EE; ARR 1: its mirror image), run-time values for the mixed ones
@@ -107,6 +125,7 @@ __global__ void __launch_bounds__(32 * (NWC + 1), 1) apply_rowpair_kernel(const 
     uint64_t *full = reinterpret_cast<uint64_t *>(tabs + 2 * C::TABS);  // NST
     uint64_t *empty = full + NST;                                      // NST
     uint64_t *aux = empty + NST;                                       // NST  (tensor-map boxes of tiles with Bloch wrap)
+    volatile int *oflag = reinterpret_cast<volatile int *>(aux + NST); // NST  (does the plane in this stage carry off-diagonal rows?)
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int Nx = p.Nx, Ny = p.Ny;
@@ -231,18 +250,24 @@ __global__ void __launch_bounds__(32 * (NWC + 1), 1) apply_rowpair_kernel(const 
                     // tables of this item (double-buffered by item parity): every compute warp has left the item
                     // before the previous one, because the stage just waited for was filled during the previous item
                     double2 *tb = tabs + (itc & 1) * C::TABS;
-                    for (int t = lane; t < 4 * NR; t += 32) {
+                    auto tab = [&](int a, int w) -> const double2 * {
+                        return a == 0 ? p.c.a0[w] : a == 1 ? p.c.a1[w] : a == 2 ? p.c.b0[w] : a == 3 ? p.c.b1[w]
+                             : a == 4 ? p.c.mi0[w] : a == 5 ? p.c.mi1[w] : a == 6 ? p.c.mo0[w] : p.c.mo1[w];
+                    };
+                    for (int t = lane; t < NTAB * NR; t += 32) {
                         const int a = t / NR, r = t % NR;
                         const int j = (((oy + r) % Ny) + Ny) % Ny;
-                        const double2 *src = a == 0 ? p.c.a0[1] : a == 1 ? p.c.a1[1] : a == 2 ? p.c.b0[1] : p.c.b1[1];
-                        tb[t] = src[j];
+                        tb[t] = tab(a, 1)[j];
                     }
-                    for (int t = lane; t < 4 * nplanes; t += 32) {
+                    for (int t = lane; t < NTAB * nplanes; t += 32) {
                         const int a = t / nplanes, m = t % nplanes;
                         int kg = p.kz0 + kof(m);
                         kg = ((kg % p.Nz) + p.Nz) % p.Nz;
-                        const double2 *src = a == 0 ? p.c.a0[2] : a == 1 ? p.c.a1[2] : a == 2 ? p.c.b0[2] : p.c.b1[2];
-                        tb[4 * NR + a * LZP + m] = src[kg];
+                        tb[NTAB * NR + a * LZP + m] = tab(a, 2)[kg];
+                    }
+                    if (HAS_OFF) {
+                        const int i = (((ox + lane) % Nx) + Nx) % Nx;    // x tables of the averages, by tile column
+                        for (int a = 0; a < 4; ++a) tb[C::XT0 + a * TX + lane] = tab(4 + a, 0)[i];
                     }
                     __syncwarp();
                 }
@@ -252,10 +277,23 @@ __global__ void __launch_bounds__(32 * (NWC + 1), 1) apply_rowpair_kernel(const 
                 double2 *dst = ring + s * STAGE;
                 if (CMPFIRST && tp.tmap) {
                     // ---- tensor-map path: ONE box per array and plane; parts outside the domain read as zero
-                    const uint32_t box_bytes = (skip_x ? 0u : (uint32_t)(NR * TX * 48)) + (want_m ? (uint32_t)(NM * C::MDROW * 16) : 0u);
+                    bool want_o = false;
+                    if (HAS_OFF) {
+                        // off-diagonal rows of plane kk feed G(kk): needed from the first output plane on, skipped when the
+                        // (tile, plane) block holds none (occupancy mask of the 30 x 14 tiles, built by tiled_build_offmask)
+                        want_o = n >= 1 && !(tp.dbg & 1) &&
+                                 (p.offmask == nullptr || __ldg(&p.offmask[(int64_t)(kk + 1) * (tp.ntx * tp.nty) + tile_y * tp.ntx + tile_x]) != 0);
+                        if (lane == 0) oflag[s] = want_o ? 1 : 0;
+                    }
+                    const uint32_t box_bytes = (skip_x ? 0u : (uint32_t)(NR * TX * 48)) + (want_m ? (uint32_t)(NM * C::MDROW * 16) : 0u) +
+                                               (want_o ? (uint32_t)(C::NO * C::MDROW * 16) : 0u);
                     uint64_t *bar = has_wrap ? &aux[s] : &full[s];
                     if (lane == 0) {
                         mbar_arrive_expect_tx(bar, box_bytes);
+                        // the off-diagonal array carries one wrapped (or zero) column / row on either side: cell i sits
+                        // in padded column i + 1, row j in padded row j + 1, so the forward neighbours of edge tiles come
+                        // with the same box
+                        if (want_o) tma_load_3d(dst + C::MO0, &tp.mmo, 3 * ((ox + 1) - ((ox + 1) & 1)), oy + 1 + (SGY > 0 ? 1 : 0), kk + 1, bar);
                         if (!skip_x) {
                             if (kk < 0) tma_load_3d(dst, &tp.mlo, 6 * ox, oy, 0, bar);
                             else if (kk >= p.nzl) tma_load_3d(dst, &tp.mhi, 6 * ox, oy, 0, bar);
@@ -375,7 +413,14 @@ __global__ void __launch_bounds__(32 * (NWC + 1), 1) apply_rowpair_kernel(const 
 
             const double2 *tb = tabs + (itc & 1) * C::TABS;
             const double2 *ty = tb + rA;                  // y tables of row A: + a * NR; rows B / R at +- s1y
-            const double2 *tz = tb + 4 * NR;              // + a * LZP + n
+            const double2 *tz = tb + NTAB * NR;           // + a * LZP + n
+            // full tensor: own cells' entries inside the off-diagonal rows of a stage (doubles; 3 per corner: (0,1), (0,2),
+            // (1,2)), x tables of the two averages, and the values carried from plane to plane
+            const int mo_o = ((rA - (SGY > 0 ? 1 : 0)) * C::MDCELLS + ptx + ((ox + 1) & 1)) * 3;
+            const double2 *txo = tb + C::XT0 + ptx;       // + a * TX: mi0, mi1, mo0, mo1
+            double2 GzA = c_zero(), GzB = c_zero();       // G_z of plane k (formed one step earlier)
+            double2 E2pA = c_zero(), E2pB = c_zero(), E2pF = c_zero();   // E_z of the plane before k: rows A, B, F
+            bool fCz = false;
 
             // first plane of the item
             int s_cur = g % NST;
@@ -447,6 +492,26 @@ __global__ void __launch_bounds__(32 * (NWC + 1), 1) apply_rowpair_kernel(const 
                     HxR = c_mul(qR0, HxR); HzR = c_mul(qR2, HzR);
                 }
 
+                // full tensor: G_z of plane k + s1z (needs only that plane's E_x, E_y and entries): the second half of this
+                // plane's z out-average and, carried over, the first half of the next plane's
+                double2 GzAn = c_zero(), GzBn = c_zero();
+                bool fN = false;
+                auto next_gz = [&]() {
+                    if (!oflag[s_nxt]) return;
+                    const double *mo = reinterpret_cast<const double *>(ring + s_nxt * STAGE + C::MO0) + mo_o;
+                    const double o02A = mo[1], o12A = mo[2], o02B = mo[mdr_dB + 1], o12B = mo[mdr_dB + 2];
+                    fN = __any_sync(0xffffffffu, (o02A != 0.0) | (o12A != 0.0) | (o02B != 0.0) | (o12B != 0.0));
+                    if (!fN) return;
+                    const double2 mi0x = txo[0], mi1x = txo[TX];
+                    const double2 AxA = c_fma(mi1x, en[-exf], c_mul(mi0x, NA0));
+                    const double2 AxB = c_fma(mi1x, en[dB - exf], c_mul(mi0x, NB0));
+                    const double2 AyA = c_fma(ty[5 * NR], NR1, c_mul(ty[4 * NR], NA1));
+                    const double2 AyB = c_fma(ty[5 * NR + SGY], NA1, c_mul(ty[4 * NR + SGY], NB1));
+                    GzAn = r_fma(o12A, AyA, r_mul(o02A, AxA));
+                    GzBn = r_fma(o12B, AyB, r_mul(o02B, AxB));
+                };
+                if (HAS_OFF && !do_out) next_gz();
+
                 if (do_out) {
                     // H_y, H_z of the x-neighbour opposite to the first curl's direction: from the previous lane
                     double2 HyAm, HzAm, HyBm, HzBm;
@@ -498,6 +563,54 @@ __global__ void __launch_bounds__(32 * (NWC + 1), 1) apply_rowpair_kernel(const 
                         yyB = c_add(c_add(HxB, HpxB), c_add(HzBm, mdB1)); yzB = c_add(c_add(HyBm, b0yA), c_add(b1yB, mdB2));
                         yxA = c_add(yxA, b0z); yyA = c_add(yyA, b1z); yzA = c_add(yzA, b1yA); yxB = c_add(yxB, b0yB);
                     }
+                    if (HAS_OFF) {
+                        // ---- off-diagonal part of the mass operator: y += Mout [P_off (Min x)] (model.jl:149-153) --------
+                        // corner values of plane k: G_x, G_y at this pair's cells (G_y also at the row above the pair, F -
+                        // recomputed like H of the row below), G_x of the forward x-neighbour by shuffle; G_z(k) was formed
+                        // one step earlier.  A warp whose entries are all zero on this plane skips the block (the
+                        // occupancy mask of the producer is per tile, this test is per row pair).
+                        bool fC = false;
+                        double o01A = 0.0, o02A = 0.0, o12A = 0.0, o01B = 0.0, o02B = 0.0, o12B = 0.0, o01F = 0.0, o12F = 0.0;
+                        if (oflag[s_cur]) {
+                            const double *mo = reinterpret_cast<const double *>(ring + s_cur * STAGE + C::MO0) + mo_o;
+                            o01A = mo[0]; o02A = mo[1]; o12A = mo[2];
+                            o01B = mo[mdr_dB]; o02B = mo[mdr_dB + 1]; o12B = mo[mdr_dB + 2];
+                            o01F = mo[2 * mdr_dB]; o12F = mo[2 * mdr_dB + 2];
+                            fC = __any_sync(0xffffffffu, (o01A != 0.0) | (o02A != 0.0) | (o12A != 0.0) | (o01B != 0.0) |
+                                                             (o02B != 0.0) | (o12B != 0.0) | (o01F != 0.0) | (o12F != 0.0));
+                        }
+                        if (fC) {
+                            const double2 mi0x = txo[0], mi1x = txo[TX];
+                            const double2 mi0z = tz[4 * LZP + n], mi1z = tz[5 * LZP + n];
+                            const double2 AxA = c_fma(mi1x, es[-exf], c_mul(mi0x, EA0));
+                            const double2 AxB = c_fma(mi1x, es[dB - exf], c_mul(mi0x, EB0));
+                            const double2 AxF = c_fma(mi1x, es[2 * dB - exf], c_mul(mi0x, EF0));
+                            const double2 AyA = c_fma(ty[5 * NR], ER1, c_mul(ty[4 * NR], EA1));
+                            const double2 AyB = c_fma(ty[5 * NR + SGY], EA1, c_mul(ty[4 * NR + SGY], EB1));
+                            const double2 AzA = c_fma(mi1z, E2pA, c_mul(mi0z, EA2));
+                            const double2 AzB = c_fma(mi1z, E2pB, c_mul(mi0z, EB2));
+                            const double2 AzF = c_fma(mi1z, E2pF, c_mul(mi0z, EF2));
+                            const double2 GxA = r_fma(o02A, AzA, r_mul(o01A, AyA));
+                            const double2 GxB = r_fma(o02B, AzB, r_mul(o01B, AyB));
+                            const double2 GyA = r_fma(o12A, AzA, r_mul(o01A, AxA));
+                            const double2 GyB = r_fma(o12B, AzB, r_mul(o01B, AxB));
+                            const double2 GyF = r_fma(o12F, AzF, r_mul(o01F, AxF));
+                            double2 GxAp, GxBp;   // G_x of the forward x-neighbour: the next lane
+                            GxAp.x = __shfl_down_sync(0xffffffffu, GxA.x, 1); GxAp.y = __shfl_down_sync(0xffffffffu, GxA.y, 1);
+                            GxBp.x = __shfl_down_sync(0xffffffffu, GxB.x, 1); GxBp.y = __shfl_down_sync(0xffffffffu, GxB.y, 1);
+                            const double2 mo0x = txo[2 * TX], mo1x = txo[3 * TX];
+                            yxA = c_fma(mo0x, GxA, yxA); yxA = c_fma(mo1x, GxAp, yxA);
+                            yxB = c_fma(mo0x, GxB, yxB); yxB = c_fma(mo1x, GxBp, yxB);
+                            yyA = c_fma(ty[6 * NR], GyA, yyA); yyA = c_fma(ty[7 * NR], GyB, yyA);
+                            yyB = c_fma(ty[6 * NR + SGY], GyB, yyB); yyB = c_fma(ty[7 * NR + SGY], GyF, yyB);
+                        }
+                        next_gz();
+                        if (fCz || fN) {
+                            const double2 mo0z = tz[6 * LZP + n], mo1z = tz[7 * LZP + n];
+                            yzA = c_fma(mo0z, GzA, yzA); yzA = c_fma(mo1z, GzAn, yzA);
+                            yzB = c_fma(mo0z, GzB, yzB); yzB = c_fma(mo1z, GzBn, yzB);
+                        }
+                    }
                     if (DOT) {   // fused Krylov inner products: t = y, s = x (own cells, in registers)
                         if (okA) {
                             ts_re += yxA.x * EA0.x + yxA.y * EA0.y + yyA.x * EA1.x + yyA.y * EA1.y + yzA.x * EA2.x + yzA.y * EA2.y;
@@ -530,6 +643,10 @@ __global__ void __launch_bounds__(32 * (NWC + 1), 1) apply_rowpair_kernel(const 
                     if (tmap) tma_store_3d(&tp.my, st_x, st_y, kfirst + SGZ * n, yw);
                     else bulk_s2g(st_dst + (int64_t)n * st_step, st_src, st_bytes);
                     bulk_commit();
+                }
+                if (HAS_OFF) {
+                    GzA = GzAn; GzB = GzBn; fCz = fN;
+                    E2pA = EA2; E2pB = EB2; E2pF = EF2;
                 }
                 HpxA = HxA; HpyA = HyA; HpxB = HxB; HpyB = HyB;
                 EA0 = NA0; EA1 = NA1; EA2 = NA2;
@@ -615,13 +732,13 @@ int sm_count() {
     return n[dev];
 }
 
-template <bool CMPFIRST, bool HAS_Q, bool DOT, int ARR, bool MDR, int NWC, int NST>
+template <bool CMPFIRST, bool HAS_Q, bool DOT, int ARR, bool MDR, bool HAS_OFF, int NWC, int NST>
 cudaError_t launch_rp(const RowPairParams &tp, int grid, cudaStream_t s) {
     if constexpr (MDR && !CMPFIRST) {
         return cudaErrorInvalidConfiguration;
     } else {
-        auto kern = apply_rowpair_kernel<CMPFIRST, HAS_Q, DOT, ARR, MDR, NWC, NST>;
-        const size_t smem = RPCfg<NWC, NST, MDR>::smem_bytes();
+        auto kern = apply_rowpair_kernel<CMPFIRST, HAS_Q, DOT, ARR, MDR, HAS_OFF, NWC, NST>;
+        const size_t smem = RPCfg<NWC, NST, MDR, HAS_OFF>::smem_bytes();
         static bool attr_set[64] = {};
         int dev = 0;
         cudaGetDevice(&dev);
@@ -637,23 +754,24 @@ cudaError_t launch_rp(const RowPairParams &tp, int grid, cudaStream_t s) {
 
 // Compiled shapes.  Warps are spread over the four SM sub-partitions, so the register budget per thread steps with
 // ceil(warps / 4): 8 warps (7 compute + producer) may use 255 registers.  Shape 0: complex material rows, 4 ring
-// stages of 46 KB; shape 1: real material rows (MDR), 5 stages of 35 KB.
-struct RpShape { int nwc, nst; bool mdr; };
-constexpr RpShape RP_SHAPES[] = {{7, 4, false}, {7, 5, true}};
+// stages of 46 KB; shape 1: real material rows (MDR), 5 stages of 35 KB; shape 2: the fused full tensor (real diagonal
+// and off-diagonal rows), 4 stages of 47 KB.
+struct RpShape { int nwc, nst; bool mdr, off; };
+constexpr RpShape RP_SHAPES[] = {{7, 4, false, false}, {7, 5, true, false}, {7, 4, true, true}};
 constexpr int RP_NSHAPES = sizeof(RP_SHAPES) / sizeof(RP_SHAPES[0]);
 
 }  // namespace
 
 // Plan: number of z-chunks per tile column so that the per-CTA sum of (planes + 1 extra first-curl step) is smallest.
-static int rp_pick_nchunk(int ncols, int nplanes, int nsm, int nst, double *cost_out) {
+static int rp_pick_nchunk(int ncols, int nplanes, int nsm, int nst, int lzmax, double *cost_out) {
     const int lzmin = std::max(1, nst - 2);   // an item must span at least NST plane loads (table double-buffering)
     int best = 0;
     double best_cost = 1e300;
-    const int nch_min = (nplanes + RP_LZMAX - 1) / RP_LZMAX;
+    const int nch_min = (nplanes + lzmax - 1) / lzmax;
     for (int nch = std::max(1, nch_min); nch <= nplanes; ++nch) {
         const int lz_lo = nplanes / nch, lz_hi = (nplanes + nch - 1) / nch;
         if (lz_lo < lzmin) break;
-        if (lz_hi > RP_LZMAX) continue;
+        if (lz_hi > lzmax) continue;
         const long items = (long)ncols * nch;
         const long per_cta = (items + nsm - 1) / nsm;
         const double cost = (double)per_cta * (0.5 * (lz_lo + lz_hi) + 1.6);
@@ -673,20 +791,35 @@ static bool want_tmap() {
     return v;
 }
 
+static int rp_lzmax(int shape) { return RP_SHAPES[shape].off ? RPCfg<7, 4, true, true>::LZMAX : RP_LZMAX; }
+
+// can the fused full-tensor shape run p?  (cmp-first layout, tensor maps, real diagonal and real symmetric off-diagonal
+// rows built by the handle, the occupancy mask - if there is one - on this shape's 30 x 14 tiles)
+static bool rp_fused_ok(const ApplyParams &p) {
+    return p.cmpfirst && p.has_mass && p.has_off && p.md[0] != nullptr && p.md_aos_r != nullptr && p.mo_aos_r != nullptr &&
+           (p.offmask == nullptr || p.offmask_ty == 16) && want_tmap();
+}
+
 // shape for this launch: real material rows when the handle built them (tensor-map path, cmp-first layout)
 static int rp_pick_shape(const ApplyParams &p, int kl_begin, int kl_end, int *nchunk) {
     static const int want_nch = env_int("FDFD_RP_NCHUNK");
     const int n = kl_end - kl_begin;
     const bool mdr = p.cmpfirst && p.has_mass && p.md[0] != nullptr && p.md_aos_r != nullptr && want_tmap();
-    const int i = mdr ? 1 : 0;
-    const int nwc = RP_SHAPES[i].nwc, nst = RP_SHAPES[i].nst;
+    int i = mdr ? 1 : 0;
+    if (p.has_off && p.has_mass) {
+        if (!rp_fused_ok(p)) return -1;
+        i = 2;
+    }
+    const int nwc = RP_SHAPES[i].nwc, nst = RP_SHAPES[i].nst, lzmax = rp_lzmax(i);
     const int ntx = (p.Nx + RP_TX - 3) / (RP_TX - 2), nty = (p.Ny + 2 * nwc - 1) / (2 * nwc);
-    int nch = rp_pick_nchunk(ntx * nty, n, sm_count(), nst, nullptr);
-    if (want_nch >= 1 && n / want_nch >= std::max(1, nst - 2) && (n + want_nch - 1) / want_nch <= RP_LZMAX) nch = want_nch;
+    int nch = rp_pick_nchunk(ntx * nty, n, sm_count(), nst, lzmax, nullptr);
+    if (want_nch >= 1 && n / want_nch >= std::max(1, nst - 2) && (n + want_nch - 1) / want_nch <= lzmax) nch = want_nch;
     if (nch < 1) return -1;
     *nchunk = nch;
     return i;
 }
+
+bool rowpair_fused_available(const ApplyParams &p) { return rp_fused_ok(p); }
 
 bool rowpair_supported(const ApplyParams &p, int kl_begin, int kl_end) {
     for (int w = 0; w < 3; ++w)
@@ -720,7 +853,7 @@ static bool cached_map(TmaMap *out, const void *base, uint64_t d0, uint64_t d1, 
     return true;
 }
 
-template <int NWC, int NST, bool MDR>
+template <int NWC, int NST, bool MDR, bool HAS_OFF>
 static cudaError_t launch_rp_shape(RowPairParams &tp, const ApplyParams &p, cudaStream_t s) {
     // tensor-map TMA path (cmp-first layout): boxes of 32 cells x (E rows | material rows), y boxes of 30 cells x 2 rows
     tp.tmap = 0;
@@ -736,9 +869,13 @@ static cudaError_t launch_rp_shape(RowPairParams &tp, const ApplyParams &p, cuda
                                                                  mdr_row_pitch(p.Nx));
             else ok = p.md_aos != nullptr && cached_map(&tp.mmd, p.md_aos, d0, d1, (uint64_t)p.nzl + 2, 6 * RP_TX, 2 * NWC);
         }
+        if (ok && HAS_OFF)   // off-diagonal rows: padded by one cell / row on either side (wrapped copies or zeros)
+            ok = p.mo_aos_r != nullptr && cached_map(&tp.mmo, p.mo_aos_r, 3ull * (p.Nx + 2), (uint64_t)p.Ny + 2, (uint64_t)p.nzl + 2,
+                                                     3 * (RP_TX + 2), 2 * NWC + 1, mdr_row_pitch(p.Nx + 2));
         tp.tmap = ok ? 1 : 0;
     }
     if (MDR && !tp.tmap) return cudaErrorNotSupported;   // the handle keeps complex rows whenever tensor maps are unavailable
+    if (HAS_OFF && p.offmask && p.offmask_ty != 16) return cudaErrorInvalidConfiguration;
     tp.ntx = (p.Nx + RP_TX - 3) / (RP_TX - 2);
     tp.nty = (p.Ny + 2 * NWC - 1) / (2 * NWC);
     tp.nitems = tp.ntx * tp.nty * tp.nchunk;
@@ -751,16 +888,18 @@ static cudaError_t launch_rp_shape(RowPairParams &tp, const ApplyParams &p, cuda
     const int nfwd = (p.s1[0] > 0) + (p.s1[1] > 0) + (p.s1[2] > 0);
     const int arr = nfwd == 3 ? 0 : nfwd == 0 ? 1 : 2;
 #define W(CF, Q, D)                                                                                          \
-    (arr == 0 ? launch_rp<CF, Q, D, 0, MDR, NWC, NST>(tp, grid, s)                                           \
-              : arr == 1 ? launch_rp<CF, Q, D, 1, MDR, NWC, NST>(tp, grid, s) : launch_rp<CF, Q, D, 2, MDR, NWC, NST>(tp, grid, s))
+    (arr == 0 ? launch_rp<CF, Q, D, 0, MDR, HAS_OFF, NWC, NST>(tp, grid, s)                                  \
+              : arr == 1 ? launch_rp<CF, Q, D, 1, MDR, HAS_OFF, NWC, NST>(tp, grid, s)                       \
+                         : launch_rp<CF, Q, D, 2, MDR, HAS_OFF, NWC, NST>(tp, grid, s))
 #define V(CF, Q) (dot ? W(CF, Q, true) : W(CF, Q, false))
     if (cf) return q ? V(true, true) : V(true, false);
-    return q ? V(false, true) : V(false, false);
+    if constexpr (MDR) return cudaErrorInvalidConfiguration;
+    else return q ? V(false, true) : V(false, false);
 #undef W
 #undef V
 }
 
-// diagonal-mass apply over local planes [kl_begin, kl_end) with the row-pair kernel
+// apply over local planes [kl_begin, kl_end) with the row-pair kernel (diagonal mass parameter, or the fused full tensor)
 cudaError_t launch_apply_rowpair(const ApplyParams &p, int kl_begin, int kl_end, cudaStream_t s) {
     if (kl_end <= kl_begin) return cudaSuccess;
     RowPairParams tp;
@@ -773,9 +912,14 @@ cudaError_t launch_apply_rowpair(const ApplyParams &p, int kl_begin, int kl_end,
     tp.dbg = dbg;
     const int shape = (p.s1[0] * p.s1[0] == 1 && p.s1[1] * p.s1[1] == 1 && p.s1[2] * p.s1[2] == 1 && !p.halo_flag)
                           ? rp_pick_shape(p, kl_begin, kl_end, &tp.nchunk) : -1;
+    static const bool verbose = getenv("FDFD_VERBOSE") != nullptr;
+    if (verbose) fprintf(stderr, "fdfd: row-pair kernel shape %d (%s), %d z-chunk(s), planes [%d, %d)\n", shape,
+                         shape == 2 ? "fused full tensor" : shape == 1 ? "real diagonal mass" : shape == 0 ? "complex diagonal mass" : "unsupported",
+                         tp.nchunk, kl_begin, kl_end);
     switch (shape) {
-        case 0: return launch_rp_shape<RP_SHAPES[0].nwc, RP_SHAPES[0].nst, RP_SHAPES[0].mdr>(tp, p, s);
-        case 1: return launch_rp_shape<RP_SHAPES[1].nwc, RP_SHAPES[1].nst, RP_SHAPES[1].mdr>(tp, p, s);
+        case 0: return launch_rp_shape<RP_SHAPES[0].nwc, RP_SHAPES[0].nst, RP_SHAPES[0].mdr, RP_SHAPES[0].off>(tp, p, s);
+        case 1: return launch_rp_shape<RP_SHAPES[1].nwc, RP_SHAPES[1].nst, RP_SHAPES[1].mdr, RP_SHAPES[1].off>(tp, p, s);
+        case 2: return launch_rp_shape<RP_SHAPES[2].nwc, RP_SHAPES[2].nst, RP_SHAPES[2].mdr, RP_SHAPES[2].off>(tp, p, s);
         default: return cudaErrorNotSupported;
     }
 }

@@ -687,7 +687,7 @@ static cudaError_t build_mask_for(const ApplyParams &p, int TY, unsigned char **
 // it is valid for (8: split launch, 16: single full-tensor launch), *frac the fraction of (tile, own plane) blocks
 // that hold off-diagonal material.
 cudaError_t tiled_build_offmask(const ApplyParams &p, unsigned char **mask, int *ty_used, double *frac, int4 **corr_list,
-                                int *corr_count, cudaStream_t s) {
+                                int *corr_count, cudaStream_t s, double fuse_min) {
     *mask = nullptr;
     *ty_used = 0;
     *frac = 1.0;
@@ -699,7 +699,9 @@ cudaError_t tiled_build_offmask(const ApplyParams &p, unsigned char **mask, int 
     std::vector<unsigned char> h;
     cudaError_t e = build_mask_for(p, TY, mask, frac, s, &h);
     if (e != cudaSuccess) return e;
-    if (!env_ty() && *frac > 0.25) {   // dense off-diagonals: the single fused 32x16 launch is the better plan
+    // dense off-diagonals: the single fused launch on 30 x 14 tiles is the better plan (fuse_min: 0.25 for the
+    // first-generation kernel, lower when the fused row-pair kernel can take the operator)
+    if (!env_ty() && *frac > fuse_min) {
         cudaFree(*mask);
         *mask = nullptr;
         TY = 16;
@@ -763,7 +765,9 @@ cudaError_t launch_apply_tiled(const ApplyParams &p, int kl_begin, int kl_end, c
     // diagonal mass parameter: the second-generation (persistent, warp-specialised) kernel unless FDFD_K1_GEN=1 asks
     // for the first-generation tiled kernel (A/B timing, on-device cross-check)
     static const bool gen1 = [] { const char *g = getenv("FDFD_K1_GEN"); return g && atoi(g) == 1; }();
-    const bool rowpair = !gen1 && !env_ty() && rowpair_supported(p, kl_begin, kl_end);
+    ApplyParams pd = p;          // the diagonal part of the operator
+    pd.has_off = 0;
+    const bool rowpair = !gen1 && !env_ty() && rowpair_supported(pd, kl_begin, kl_end);
     if (!full) {
         if (rowpair) e = launch_apply_rowpair(p, kl_begin, kl_end, s);
         else e = (env_ty() == 16) ? launch_tile<32, 16>(p, kl_begin, kl_end, s) : launch_tile<32, 8>(p, kl_begin, kl_end, s);
@@ -771,18 +775,18 @@ cudaError_t launch_apply_tiled(const ApplyParams &p, int kl_begin, int kl_end, c
     } else if (p.offmask && p.offmask_ty == 8) {
         // sparse off-diagonals (material interfaces only): diagonal kernel everywhere, then the off-diagonal part
         // of the mass operator is added on the flagged runs of this plane range (the operator is linear)
-        if (rowpair) {
-            ApplyParams pd = p;
-            pd.has_off = 0;
-            e = launch_apply_rowpair(pd, kl_begin, kl_end, s);
-        } else {
-            e = launch_tile<32, 8>(p, kl_begin, kl_end, s, true);
-        }
+        if (rowpair) e = launch_apply_rowpair(pd, kl_begin, kl_end, s);
+        else e = launch_tile<32, 8>(p, kl_begin, kl_end, s, true);
         if (e == cudaSuccess)
             e = launch_offdiag_correction(p, p.corr_list, p.corr_count, (p.Nx + 29) / 30, kl_begin, kl_end, s);
         if (nlaunch) *nlaunch += p.corr_count > 0 ? 2 : 1;
     } else {
-        e = launch_tile<32, 16>(p, kl_begin, kl_end, s);
+        // off-diagonal material on many blocks: ONE fused launch - the row-pair kernel when the tensor is symmetric with
+        // real entries (its off-diagonal rows travel through the TMA ring), else the first-generation 32 x 16 kernel
+        if (!gen1 && !env_ty() && rowpair_fused_available(p) && rowpair_supported(p, kl_begin, kl_end))
+            e = launch_apply_rowpair(p, kl_begin, kl_end, s);
+        else
+            e = launch_tile<32, 16>(p, kl_begin, kl_end, s);
         if (nlaunch) *nlaunch += 1;
     }
     return e;

@@ -60,6 +60,9 @@ struct ApplyParams {
     const double2 *md_aos;  // cmp-first layout only: the three md arrays interleaved, element ((kl+1)*Nx*Ny + j*Nx + i)*3 + v
     const double *md_aos_r; // the same, real parts only, rows of mdr_row_pitch(Nx) doubles: [(kl+1)*Ny + j][3*i + v] - present when every diagonal mass entry is real (then md_aos is null)
     const double2 *mo[6];   // -w^2 * P_vu, order (0,1),(0,2),(1,0),(1,2),(2,0),(2,1)
+    const double *mo_aos_r; // cmp-first layout, symmetric tensor with real entries only: (0,1),(0,2),(1,2) interleaved, padded by one
+                            // cell / row on either side in x and y (wrapped copies on Bloch axes, zeros otherwise), rows of
+                            // mdr_row_pitch(Nx + 2) doubles: [((kl+1)*(Ny+2) + j+1)][3*(i+1) + e] (fused row-pair kernel)
     const double2 *q[3];    // inverse of the middle diagonal parameter (mu^-1 for FT_EE)
     PlaneSet x;
     // z-slabs, in-kernel halo wait (opt-in): the CTAs of the first / last z-chunk spin until *halo_flag ==
@@ -152,6 +155,7 @@ struct Ctx {
     double2 *mat_dev = nullptr;      // md[3], mo[6], q[3] ghosted slabs
     double2 *md_aos = nullptr;       // interleaved copy of md[3] (cmp-first layout; row-pair kernel)
     double *md_aos_r = nullptr;      // real-valued interleaved copy (instead of md_aos) when every entry is real
+    double *mo_aos_r = nullptr;      // real-valued, padded, interleaved copy of the three symmetric off-diagonal arrays
     size_t mat_bytes = 0;
     const double2 *md[3]{}, *mo[6]{}, *mo_t[6]{}, *q[3]{};
     bool has_mass = false;           // omega != 0
@@ -233,12 +237,13 @@ bool tiled_supported(const ApplyParams &p);
 // apply_rowpair.cu: second-generation K1 (persistent, warp-specialised; diagonal mass parameter) over local planes
 // [kl_begin, kl_end); cudaErrorNotSupported when the configuration is outside its range
 bool rowpair_supported(const ApplyParams &p, int kl_begin, int kl_end);
+bool rowpair_fused_available(const ApplyParams &p);   // fused full-tensor shape: arrays, layout and mask fit
 int64_t mdr_row_pitch(int Nx);   // doubles per row of ApplyParams::md_aos_r
 cudaError_t launch_apply_rowpair(const ApplyParams &p, int kl_begin, int kl_end, cudaStream_t s);
 // number of z-chunks per tile column the main kernel of launch_apply_tiled(p, 0, nzl) will use
 int tiled_plan_nchunk(const ApplyParams &p);
 cudaError_t tiled_build_offmask(const ApplyParams &p, unsigned char **mask, int *ty_used, double *frac, int4 **corr_list,
-                                int *corr_count, cudaStream_t s);
+                                int *corr_count, cudaStream_t s, double fuse_min = 0.25);
 cudaError_t launch_offdiag_correction(const ApplyParams &p, const int4 *items, int count, int ntx, int kl_begin,
                                       int kl_end, cudaStream_t s);
 // first-curl only: h = scale * q .* (C1 e + jm)   (h_from_e), naive kernel

@@ -318,6 +318,14 @@ class FdfdOperator:
         return f.value
 
     @property
+    def offdiag_bytes_per_dof(self):
+        """bytes per DOF of the off-diagonal streams on a flagged block: 32, 16 (symmetric), 8 (symmetric and real, fused
+        row-pair kernel), 0 (none)"""
+        f = C.c_double()
+        L.check(L.lib().fdfd_offdiag_bytes_per_dof(self._h, C.byref(f)), self._h)
+        return f.value
+
+    @property
     def offdiag_symmetric(self):
         """True when the off-diagonal mass entries are pointwise symmetric (stored once: 16 instead of 32 B/DOF)."""
         f = C.c_int()

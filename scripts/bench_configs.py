@@ -31,7 +31,7 @@ def measure(name, w, steps=100, kry=20):
     ms, _ = A.bench_apply(x, y, warmup=0, iters=steps)
     ms /= steps
     off = A.offdiag_fraction if w["full_eps"] else 0.0
-    bpd = 48 + (16 if (w["full_eps"] and A.offdiag_symmetric) else 32) * off
+    bpd = 32 + A.mass_bytes_per_dof + A.offdiag_bytes_per_dof * off
     b = torch.randn(n, 2, device="cuda", dtype=torch.float64, generator=g).view(torch.complex128).reshape(-1)
     out = {"config": name, "grid": list(w["N"]), "dof": n, "ms_per_apply": ms, "gdof_s": n / ms / 1e6,
            "bytes_per_dof": bpd, "hbm_frac": bpd * n / (ms * 1e-3) / 1e9 / PEAK, "offdiag_block_fraction": off,

@@ -29,7 +29,7 @@ def measure(name, w, steps=50, check=True, kry=0):
     ms, _ = A.bench_apply(x, y, warmup=0, iters=steps)
     ms /= steps
     off = A.offdiag_fraction if w["full_eps"] else 0.0
-    bpd = 48 + (16 if (w["full_eps"] and A.offdiag_symmetric) else 32) * off
+    bpd = 32 + A.mass_bytes_per_dof + A.offdiag_bytes_per_dof * off
     out = {"tag": TAG, "config": name, "ms": round(ms, 5), "gdof_s": round(n / ms / 1e6, 2),
            "hbm_frac": round(bpd * n / (ms * 1e-3) / 1e9 / PEAK, 4), "bpd": round(bpd, 2)}
     if kry:

@@ -103,6 +103,60 @@ def g_realmass():
     return n + 1
 
 
+def g_fused():
+    """fused full-tensor shape of the row-pair kernel (real diagonal + real symmetric off-diagonal entries through the TMA
+    ring): every boundary combination incl. Bloch wrap at the forward tile edge, dense / partly empty / empty
+    off-diagonal blocks (tile mask and per-row-pair skip), several z-chunks, uniform and mixed arrangements, both
+    formulations, transposed apply, fused dots through BiCGSTAB"""
+    n = 0
+    combos = list(itertools.product([True, False], repeat=3))
+    os.environ.pop("FDFD_RP_FUSE_MIN", None)
+    for N in [(3, 3, 2), (33, 17, 9), (70, 45, 6), (31, 40, 5), (61, 29, 7)]:
+        for i, isbloch in enumerate(combos):
+            if not FULL and (i + sum(N)) % 2 != 0:
+                continue
+            p = Problem(N, isbloch, full_eps=True, real_mass=True, sym_real_off=True)
+            A_ref, _ = p.oracle_csc()
+            A = p.operator(device=0, kernel=TILED)
+            x = p.random_x()
+            check(rel(apply_dev(A, x), A_ref.matvec(x)), f"fused apply {N} {isbloch}")
+            check(rel(apply_dev(A, x, transpose=True), A_ref.to_scipy().T @ x), f"fused transpose {N} {isbloch}")
+            A.close()
+            n += 2
+    # partly empty off-diagonal blocks: whole planes, a half-space in y (row pairs skip), a half-space in x
+    cases = [((EE, EE, EE), (True, True, True), EE), ((HH, HH, HH), (False, True, False), EE), ((EE, HH, EE), (True, False, True), EE),
+             ((EE, EE, EE), (False, False, True), HH)]
+    for boundft, isbloch, ft in (cases if FULL else cases[:3]):
+        p = Problem((64, 45, 40), isbloch, boundft, full_eps=(ft == EE), full_mu=(ft == HH), with_mu=(ft == HH), ft=ft,
+                    real_mass=True, sym_real_off=True)
+        mass = p.eps if ft == EE else p.mu
+        for v, u in itertools.permutations(range(3), 2):
+            mass[:, :, :9, v, u] = 0
+            mass[:, :, 21:30, v, u] = 0
+            mass[:, 11:30, 30:, v, u] = 0
+            mass[:33, :, 12:18, v, u] = 0
+        x = p.random_x()
+        A = p.operator(device=0, kernel=TILED)
+        An = p.operator(device=0, kernel=NAIVE)
+        y = apply_dev(A, x)
+        check(rel(y, apply_dev(An, x)), f"fused vs general kernel {boundft} {isbloch} ft={ft}", 1e-13)
+        check(rel(y, p.oracle_matfree()(x)), f"fused vs matrix-free oracle {boundft} {isbloch} ft={ft}")
+        A.close()
+        An.close()
+        n += 1
+    p = Problem((12, 9, 6), (True, True, False), full_eps=True, real_mass=True, sym_real_off=True, npml=2)
+    A_ref, _ = p.oracle_csc()
+    A = p.operator(device=0, kernel=TILED)
+    b = A_ref.matvec(p.random_x(3))
+    xs = np.zeros(A.n, complex)
+    iters, relres = C.c_int(), C.c_double()
+    L.check(L.lib().fdfd_solve(A._h, L.BICGSTAB, b.ctypes.data, xs.ctypes.data, L.DEVICE, 1e-10, 4000, 5,
+                               C.byref(iters), C.byref(relres), None), A._h, ok=(L.OK, L.ENOCONV))
+    check(rel(A_ref.matvec(xs), b), "fused BiCGSTAB true residual", 1e-8)
+    A.close()
+    return n + 1
+
+
 def g_boundft():
     """all 2^3 boundft choices, both formulations, forward and transposed (ARR = 0 / 1 / 2 instantiations)"""
     n = 0
@@ -323,7 +377,7 @@ def g_reduced():
     return n
 
 
-GROUPS = {"realmass": g_realmass, "reduced": g_reduced, "matparams": g_matparams, "apply": g_apply, "boundft": g_boundft, "layouts": g_layouts, "deep": g_deep, "solve": g_solve, "aux": g_aux}
+GROUPS = {"fused": g_fused, "realmass": g_realmass, "reduced": g_reduced, "matparams": g_matparams, "apply": g_apply, "boundft": g_boundft, "layouts": g_layouts, "deep": g_deep, "solve": g_solve, "aux": g_aux}
 
 
 def main():

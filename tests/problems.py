@@ -23,7 +23,7 @@ class Problem:
 
     def __init__(self, N, isbloch=(True, True, True), boundft=(EE, EE, EE), full_eps=False, with_mu=False,
                  ft=EE, omega=1.1 - 0.05j, npml=1, uniform=False, seed=SEED, cmpfirst=True, weighted_out=False,
-                 kb_scale=1.0, full_mu=False, real_mass=False):
+                 kb_scale=1.0, full_mu=False, real_mass=False, sym_real_off=False):
         rng = np.random.default_rng(seed)
         self.N = tuple(int(n) for n in N)
         self.isbloch = tuple(bool(b) for b in isbloch)
@@ -56,6 +56,14 @@ class Problem:
             mass = self.eps if ft == EE else self.mu
             for v in range(3):
                 mass[..., v, v] = np.real(mass[..., v, v])
+        if sym_real_off:
+            # symmetric tensor with real off-diagonal entries (what subpixel smoothing of lossless reciprocal media gives);
+            # together with real_mass the operator qualifies for the fused full-tensor shape of the row-pair kernel
+            mass = self.eps if ft == EE else self.mu
+            for v in range(3):
+                for u in range(v + 1, 3):
+                    mass[..., v, u] = np.real(mass[..., v, u])
+                    mass[..., u, v] = mass[..., v, u]
         self.with_mu, self.full_eps = with_mu or full_mu, full_eps
         self.n = 3 * int(np.prod(self.N))
         self.rng = rng

@@ -775,4 +775,62 @@ def test_objects_on_reduced_models():
     kernel on the extruded scene; analytic harmonic / arithmetic means across a planar interface, and the oracle's
     smoothing of the scene the K-dimensional one stands for (1e-10, as for the 3-D pipeline)"""
     from problems import reduced_objects_check
-    assert reduced_objects_check(_fb()) == 22
+    assert reduced_objects_check(_fb()) == 22@pytest.mark.gpu
+@pytest.mark.parametrize("N", [(3, 3, 2), (33, 17, 9), (70, 45, 6), (31, 40, 5), (61, 29, 7)])
+def test_apply_fused_full_tensor_rowpair(N):
+    """Fused full-tensor shape of the row-pair kernel (symmetric tensor, real entries: diagonal and off-diagonal rows travel
+    as doubles through the TMA ring, apply_rowpair.cu HAS_OFF) against the oracle's CSC product, every Bloch / symmetry
+    combination (Bloch wrap of the forward neighbours at tile edges), forward and transposed.  The operator being
+    matched: create_paramops' Mout * P_off * Min, /root/reference/src/model/model.jl:149-153."""
+    for isbloch in itertools.product([True, False], repeat=3):
+        p = Problem(N, isbloch, full_eps=True, real_mass=True, sym_real_off=True)
+        A_ref, _ = p.oracle_csc()
+        A = p.operator(device=0, kernel=KERNELS["tiled"])
+        assert A.offdiag_bytes_per_dof == 8.0, "the fused row-pair shape was not selected"
+        x = p.random_x()
+        err = rel(_apply_dev(A, x), A_ref.matvec(x))
+        errT = rel(_apply_dev(A, x, transpose=True), A_ref.to_scipy().T.tocsc() @ x)
+        A.close()
+        assert err < TOL and errT < TOL, (N, isbloch, err, errT)
+
+
+@pytest.mark.gpu
+def test_fused_full_tensor_partly_empty_blocks_arrangements_and_solve():
+    """Fused row-pair shape on a deeper grid (several z-chunks and items per CTA) whose off-diagonal entries vanish on
+    whole planes / half-spaces (tile occupancy mask, per-row-pair skip), on the default, mirrored and a mixed
+    arrangement and on the HH formulation, against the general kernel (1e-13) and the matrix-free oracle; then BiCGSTAB
+    (fused dots in the apply epilogue) and QMR (transposed operator) against a sparse direct solve."""
+    import scipy.sparse.linalg as spla
+    torch = _torch()
+    cases = [((EE, EE, EE), (True, True, True), EE), ((HH, HH, HH), (False, True, False), EE),
+             ((EE, HH, EE), (True, False, True), EE), ((EE, EE, EE), (False, False, True), HH)]
+    for boundft, isbloch, ft in cases:
+        p = Problem((64, 45, 40), isbloch, boundft, full_eps=(ft == EE), full_mu=(ft == HH), with_mu=(ft == HH), ft=ft,
+                    real_mass=True, sym_real_off=True)
+        mass = p.eps if ft == EE else p.mu
+        for v, u in itertools.permutations(range(3), 2):
+            mass[:, :, :9, v, u] = 0
+            mass[:, :, 21:30, v, u] = 0
+            mass[:, 11:30, 30:, v, u] = 0
+            mass[:33, :, 12:18, v, u] = 0
+        x = p.random_x()
+        A = p.operator(device=0, kernel=KERNELS["tiled"])
+        An = p.operator(device=0, kernel=KERNELS["naive"])
+        assert A.offdiag_bytes_per_dof == 8.0 and 0.0 < A.offdiag_fraction < 1.0
+        y = _apply_dev(A, x)
+        e1, e2 = rel(y, _apply_dev(An, x)), rel(y, p.oracle_matfree()(x))
+        A.close()
+        An.close()
+        assert e1 < 1e-13 and e2 < TOL, (boundft, isbloch, ft, e1, e2)
+    p = Problem((14, 11, 9), (True, True, False), full_eps=True, real_mass=True, sym_real_off=True, npml=2, omega=1.1)
+    A_ref, _ = p.oracle_csc()
+    b = A_ref.matvec(p.random_x(3))
+    x_ref = spla.splu(A_ref.to_scipy()).solve(b)
+    A = p.operator(device=0, kernel=KERNELS["tiled"])
+    for method in ("bicgstab", "qmr"):
+        xs, info = A.solve(torch.from_numpy(b).cuda(), method=method, rtol=1e-11, maxit=20000, check_every=10)
+        assert rel(xs.cpu().numpy(), x_ref) < 1e-8, (method, info)
+    A.close()
+
+
+
