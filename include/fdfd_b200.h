@@ -105,6 +105,13 @@ int fdfd_set_mu(fdfd_handle h, const fdfd_c128 *mu_or_null);
 /* y = A x : the per-iteration `mul!(y, A, x)` of the reference path (SparseMatrixCSC product).
  * x, y: this rank's slab of the DOF vector, `where` = FDFD_HOST or FDFD_DEVICE. x != y. */
 int fdfd_apply(fdfd_handle h, const fdfd_c128 *x, fdfd_c128 *y, int where);
+/* z-slab variant of the host-buffer apply for callers that hold the WHOLE vector in host memory (one process driving
+ * several GPUs, fdfd_multi_* below): x, y = this slab's planes, x_below / x_above = host pointers to plane k0-1 / k1 of
+ * the global vector (the wrapped plane on a Bloch z axis; NULL on a symmetry boundary).  The halo planes ride along
+ * with the H2D copies - no exchange between the GPUs, and the sub-slab pipeline of fdfd_apply(FDFD_HOST) runs per slab.
+ * For the component-major layout the halo planes are three (Nx*Ny)-element pieces, component after component. */
+int fdfd_apply_host_halos(fdfd_handle h, const fdfd_c128 *x, const fdfd_c128 *x_below_or_null, const fdfd_c128 *x_above_or_null,
+                          fdfd_c128 *y, int transpose);
 /* y = A^T x (plain transpose, needed by QMR). */
 int fdfd_apply_transpose(fdfd_handle h, const fdfd_c128 *x, fdfd_c128 *y, int where);
 
@@ -222,6 +229,36 @@ int fdfd_host_free(void *p);
 int fdfd_dev_alloc(fdfd_handle h, void **p, uint64_t bytes);
 int fdfd_dev_free(fdfd_handle h, void *p);
 int fdfd_memcpy(fdfd_handle h, void *dst, const void *src, uint64_t bytes, int dst_where, int src_where);
+
+/* ---------------------------------------------------------------------------------------------------------------------
+ * ONE call, N GPUs.  The reference's seam is a single value in a single process - A = create_A(...), then
+ * A * x / A \ b (model.jl:209-246).  A multi handle gives a single-process host (a Julia session) every GPU of the box
+ * without an MPI launcher: it owns one z-slab handle per device and one host thread per handle, builds the NCCL
+ * communicator across them, takes FULL-GRID host arrays (the layouts documented above with Nz_local = Nz) and splits
+ * them into slabs itself.  fdfd_multi_apply moves each slab, together with the two neighbour planes it needs, over that
+ * GPU's own PCIe link (no exchange between GPUs); fdfd_multi_solve runs the slab Krylov loops with halos and inner
+ * products over NCCL.  desc->device / rank / nranks are ignored; devices_or_null == NULL uses devices 0..ngpu-1.
+ * Every function blocks until all slabs are done; status = the first failing slab's (message: fdfd_multi_last_error). */
+typedef struct fdfd_multi_ctx *fdfd_multi;
+int fdfd_multi_create(fdfd_multi *out, const fdfd_desc *desc, int32_t ngpu, const int32_t *devices_or_null);
+int fdfd_multi_destroy(fdfd_multi m);
+const char *fdfd_multi_last_error(fdfd_multi m);   /* m == NULL: last error of a failed fdfd_multi_create in this thread */
+int fdfd_multi_ngpu(fdfd_multi m);
+/* slab handle `slab` and its plane range (for the measurement / debug entry points of the slab API) */
+int fdfd_multi_slab(fdfd_multi m, int32_t slab, fdfd_handle *h, int64_t *k0, int64_t *k1);
+int fdfd_multi_set_coeffs(fdfd_multi m, const fdfd_c128 *const sdl_e[3], const fdfd_c128 *const sdl_m[3]);
+int fdfd_multi_set_bloch(fdfd_multi m, const fdfd_c128 e_mikL[3]);
+int fdfd_multi_set_omega(fdfd_multi m, fdfd_c128 omega);
+int fdfd_multi_set_eps(fdfd_multi m, const fdfd_c128 *eps, int has_offdiag);   /* (Nx,Ny,Nz,3,3), the whole grid */
+int fdfd_multi_set_mu(fdfd_multi m, const fdfd_c128 *mu_or_null);
+int fdfd_multi_set_eps_objects(fdfd_multi m, const fdfd_matparams_desc *desc);
+int fdfd_multi_apply(fdfd_multi m, const fdfd_c128 *x, fdfd_c128 *y);           /* mul!(y, A, x), full-grid host vectors */
+int fdfd_multi_apply_transpose(fdfd_multi m, const fdfd_c128 *x, fdfd_c128 *y);
+int fdfd_multi_solve(fdfd_multi m, int method, const fdfd_c128 *b, fdfd_c128 *x, double rtol, int maxit, int check_every,
+                     int *iters, double *relres, double *hist_or_null);          /* x = A \ b */
+int fdfd_multi_create_b(fdfd_multi m, const fdfd_c128 *je, const fdfd_c128 *jm_or_null, fdfd_c128 *b);
+int fdfd_multi_h_from_e(fdfd_multi m, const fdfd_c128 *e, const fdfd_c128 *jm_or_null, fdfd_c128 *hout);
+int fdfd_multi_e_from_h(fdfd_multi m, const fdfd_c128 *hfield, const fdfd_c128 *je_or_null, fdfd_c128 *eout);
 
 #ifdef __cplusplus
 }

@@ -10,7 +10,7 @@ from .model import (Model, ModelFull, ModelTE, ModelTM, ModelTEM, set_wpml, set_
                     add_srce, add_srcm, create_srcs, create_stretched_dls, create_paramops, create_curls, ParamOp, CurlOp,
                     create_A, create_b, create_linsys,
                     h_from_e, e_from_h, create_Mcs, solve, field_arr2vec, field_vec2arr)
-from .operator import FdfdOperator, comm_unique_id, partition, halo_plan
+from .operator import FdfdOperator, MultiGpuOperator, comm_unique_id, partition, halo_plan
 from .reduced import ReducedOperator
 from .shapes import Box, Ball, Sphere, Cylinder, add_obj, clear_objs, calc_matparams, calc_matparams_array
 from . import _lib

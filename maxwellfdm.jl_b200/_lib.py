@@ -65,6 +65,7 @@ SYMBOLS = {
     "fdfd_set_mu": (C.c_int, [P, P]),
     "fdfd_apply": (C.c_int, [P, P, P, C.c_int]),
     "fdfd_apply_transpose": (C.c_int, [P, P, P, C.c_int]),
+    "fdfd_apply_host_halos": (C.c_int, [P, P, P, P, P, C.c_int]),
     "fdfd_solve": (C.c_int, [P, C.c_int, P, P, C.c_int, C.c_double, C.c_int, C.c_int,
                              C.POINTER(C.c_int), C.POINTER(C.c_double), P]),
     "fdfd_export_pattern": (C.c_int, [P, P, P, P, C.POINTER(C.c_int64)]),
@@ -89,6 +90,24 @@ SYMBOLS = {
     "fdfd_dev_alloc": (C.c_int, [P, C.POINTER(P), C.c_uint64]),
     "fdfd_dev_free": (C.c_int, [P, P]),
     "fdfd_memcpy": (C.c_int, [P, P, P, C.c_uint64, C.c_int, C.c_int]),
+    # one call, N GPUs (multi.cpp)
+    "fdfd_multi_create": (C.c_int, [C.POINTER(P), C.POINTER(Desc), C.c_int32, C.POINTER(C.c_int32)]),
+    "fdfd_multi_destroy": (C.c_int, [P]),
+    "fdfd_multi_last_error": (C.c_char_p, [P]),
+    "fdfd_multi_ngpu": (C.c_int, [P]),
+    "fdfd_multi_slab": (C.c_int, [P, C.c_int32, C.POINTER(P), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "fdfd_multi_set_coeffs": (C.c_int, [P, C.POINTER(P), C.POINTER(P)]),
+    "fdfd_multi_set_bloch": (C.c_int, [P, P]),
+    "fdfd_multi_set_omega": (C.c_int, [P, c128]),
+    "fdfd_multi_set_eps": (C.c_int, [P, P, C.c_int]),
+    "fdfd_multi_set_mu": (C.c_int, [P, P]),
+    "fdfd_multi_set_eps_objects": (C.c_int, [P, P]),
+    "fdfd_multi_apply": (C.c_int, [P, P, P]),
+    "fdfd_multi_apply_transpose": (C.c_int, [P, P, P]),
+    "fdfd_multi_solve": (C.c_int, [P, C.c_int, P, P, C.c_double, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double), P]),
+    "fdfd_multi_create_b": (C.c_int, [P, P, P, P]),
+    "fdfd_multi_h_from_e": (C.c_int, [P, P, P, P]),
+    "fdfd_multi_e_from_h": (C.c_int, [P, P, P, P]),
 }
 
 
@@ -110,5 +129,11 @@ def lib():
 def check(code, handle=None, ok=(OK,)):
     if code not in ok:
         msg = lib().fdfd_last_error(handle)
+        raise FdfdError(code, msg.decode() if msg else "")
+
+
+def check_multi(code, handle=None, ok=(OK,)):
+    if code not in ok:
+        msg = lib().fdfd_multi_last_error(handle)
         raise FdfdError(code, msg.decode() if msg else "")
     return code

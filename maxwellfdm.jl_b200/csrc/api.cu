@@ -470,7 +470,9 @@ int apply_device(Ctx *c, const double2 *x, double2 *y, bool transpose) {
         return set_err(c, FDFD_EINVAL, "tiled kernel: unsupported arrangement");
     const bool use_tiled = c->d.kernel != FDFD_KERNEL_NAIVE && can_tile;
     // timing experiments only (results are wrong with FDFD_DEBUG_SKIP_HALO): where does the multi-slab overhead go?
-    static const bool dbg_skip_halo = getenv("FDFD_DEBUG_SKIP_HALO") != nullptr;
+    static const bool env_skip_halo = getenv("FDFD_DEBUG_SKIP_HALO") != nullptr;
+    // halo planes already in c->halo_lo / halo_hi: the caller supplied them with the host vector (fdfd_apply_host_halos)
+    const bool dbg_skip_halo = env_skip_halo || c->halo_preloaded;
     // The interior/boundary split (exchange overlapped with the interior planes) costs more than it hides on
     // NVLink (measured: +21 us for the split vs 25 us for the exchange), so it is opt-in; the default is exchange,
     // then one launch - and inside the Krylov loops the exchange is started early by the kernel that produces the
@@ -639,11 +641,14 @@ static int stage_buffers(Ctx *c) {
 // D2H of sub-slab s-1 run concurrently on three streams (PCIe is full duplex), so the call costs about one
 // direction's transfer time instead of H2D + kernel + D2H.  Needs a single slab, the cmp-first layout (a
 // z sub-slab is contiguous) and the tiled kernel; other configurations use the plain staged path.
-static bool can_pipeline(Ctx *c) {
-    return c->d.nranks == 1 && c->d.order_cmpfirst && c->d.kernel != FDFD_KERNEL_NAIVE && (c->k1 - c->k0) >= 16;
+static bool can_pipeline(Ctx *c, bool host_halos) {
+    return (c->d.nranks == 1 || host_halos) && c->d.order_cmpfirst && c->d.kernel != FDFD_KERNEL_NAIVE && (c->k1 - c->k0) >= 16;
 }
 
-static int apply_host_pipelined(Ctx *c, const double2 *xh, double2 *yh, bool transpose) {
+// xlo_h / xhi_h (z-slabs only): host pointers to the plane below / above this slab (null: symmetry boundary, the halo
+// buffer keeps its zeros) - the caller holds the whole vector in host memory, so no exchange between GPUs is needed
+static int apply_host_pipelined(Ctx *c, const double2 *xh, double2 *yh, bool transpose, const double2 *xlo_h = nullptr,
+                                const double2 *xhi_h = nullptr) {
     const int64_t nzl = c->k1 - c->k0, pl = c->plane;
     static const int s_env = [] { const char *e = getenv("FDFD_PIPE_SLABS"); return e ? atoi(e) : 0; }();
     const int S = (int)std::max<int64_t>(1, std::min<int64_t>(s_env > 0 ? s_env : 16, nzl / 2));
@@ -661,9 +666,15 @@ static int apply_host_pipelined(Ctx *c, const double2 *xh, double2 *yh, bool tra
     ApplyParams p;
     fill_params(c, p, c->stage_x, c->stage_y, transpose);
     auto bound = [&](int s) { return (int)((nzl * s) / S); };
-    // the wrap plane (x_lo = plane nzl-1) first, then the sub-slabs in order
-    FDFD_CUDA(c, cudaMemcpyAsync(c->stage_x + (nzl - 1) * pl, xh + (nzl - 1) * pl, (size_t)pl * sizeof(double2),
-                                 cudaMemcpyHostToDevice, c->stream_copy));
+    if (c->d.nranks == 1) {
+        // the wrap plane (x_lo = plane nzl-1) first, then the sub-slabs in order
+        FDFD_CUDA(c, cudaMemcpyAsync(c->stage_x + (nzl - 1) * pl, xh + (nzl - 1) * pl, (size_t)pl * sizeof(double2),
+                                     cudaMemcpyHostToDevice, c->stream_copy));
+    } else {
+        // z-slab: the neighbours' boundary planes come straight from the caller's host vector
+        if (xlo_h) FDFD_CUDA(c, cudaMemcpyAsync(c->halo_lo, xlo_h, (size_t)pl * sizeof(double2), cudaMemcpyHostToDevice, c->stream_copy));
+        if (xhi_h) FDFD_CUDA(c, cudaMemcpyAsync(c->halo_hi, xhi_h, (size_t)pl * sizeof(double2), cudaMemcpyHostToDevice, c->stream_copy));
+    }
     FDFD_CUDA(c, cudaEventRecord(c->ev_h2d[S], c->stream_copy));
     for (int s = 0; s < S; ++s) {
         const int64_t o = (int64_t)bound(s) * pl, n = (int64_t)(bound(s + 1) - bound(s)) * pl;
@@ -692,11 +703,39 @@ static int apply_host(Ctx *c, const fdfd_c128 *x, fdfd_c128 *y, bool transpose) 
     int r;
     if ((r = stage_buffers(c)) != FDFD_OK) return r;
     if ((r = ensure_ready(c)) != FDFD_OK) return r;
-    if (can_pipeline(c))
+    if (can_pipeline(c, false))
         return apply_host_pipelined(c, reinterpret_cast<const double2 *>(x), reinterpret_cast<double2 *>(y), transpose);
     const size_t bytes = (size_t)c->nloc * sizeof(double2);
     FDFD_CUDA(c, cudaMemcpyAsync(c->stage_x, x, bytes, cudaMemcpyHostToDevice, c->stream));
     if ((r = apply_device(c, c->stage_x, c->stage_y, transpose)) != FDFD_OK) return r;
+    FDFD_CUDA(c, cudaMemcpyAsync(y, c->stage_y, bytes, cudaMemcpyDeviceToHost, c->stream));
+    FDFD_CUDA(c, cudaStreamSynchronize(c->stream));
+    return FDFD_OK;
+}
+
+// host-buffer apply of one z-slab whose halo planes the caller supplies from host memory (no exchange between GPUs)
+static int apply_host_halos(Ctx *c, const fdfd_c128 *x, const fdfd_c128 *xlo, const fdfd_c128 *xhi, fdfd_c128 *y, bool transpose) {
+    int r;
+    if (c->d.nranks == 1) return apply_host(c, x, y, transpose);
+    if ((r = stage_buffers(c)) != FDFD_OK) return r;
+    if ((r = ensure_ready(c)) != FDFD_OK) return r;
+    if (c->comm_pending) {
+        FDFD_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_halo, 0));
+        FDFD_CUDA(c, cudaStreamSynchronize(c->stream));
+        c->comm_pending = false;
+    }
+    c->halo_for = nullptr;
+    if (can_pipeline(c, true))
+        return apply_host_pipelined(c, reinterpret_cast<const double2 *>(x), reinterpret_cast<double2 *>(y), transpose,
+                                    reinterpret_cast<const double2 *>(xlo), reinterpret_cast<const double2 *>(xhi));
+    const size_t bytes = (size_t)c->nloc * sizeof(double2), pb = (size_t)c->plane * sizeof(double2);
+    FDFD_CUDA(c, cudaMemcpyAsync(c->stage_x, x, bytes, cudaMemcpyHostToDevice, c->stream));
+    if (xlo) FDFD_CUDA(c, cudaMemcpyAsync(c->halo_lo, xlo, pb, cudaMemcpyHostToDevice, c->stream));
+    if (xhi) FDFD_CUDA(c, cudaMemcpyAsync(c->halo_hi, xhi, pb, cudaMemcpyHostToDevice, c->stream));
+    c->halo_preloaded = true;
+    r = apply_device(c, c->stage_x, c->stage_y, transpose);
+    c->halo_preloaded = false;
+    if (r != FDFD_OK) return r;
     FDFD_CUDA(c, cudaMemcpyAsync(y, c->stage_y, bytes, cudaMemcpyDeviceToHost, c->stream));
     FDFD_CUDA(c, cudaStreamSynchronize(c->stream));
     return FDFD_OK;
@@ -1014,6 +1053,13 @@ int fdfd_apply(fdfd_handle h, const fdfd_c128 *x, fdfd_c128 *y, int where) {
     if (r != FDFD_OK) return r;
     FDFD_CUDA(c, cudaStreamSynchronize(c->stream));
     return FDFD_OK;
+}
+
+int fdfd_apply_host_halos(fdfd_handle h, const fdfd_c128 *x, const fdfd_c128 *x_below_or_null, const fdfd_c128 *x_above_or_null,
+                          fdfd_c128 *y, int transpose) {
+    CHECK_H(h);
+    if (!x || !y) return set_err(c, FDFD_EINVAL, "fdfd_apply_host_halos: null argument");
+    return apply_host_halos(c, x, x_below_or_null, x_above_or_null, y, transpose != 0);
 }
 
 int fdfd_apply_transpose(fdfd_handle h, const fdfd_c128 *x, fdfd_c128 *y, int where) {

@@ -57,7 +57,7 @@ struct RowPairParams {
     TmaMap mx, mlo, mhi, mmd, mmo, my;
     int32_t tmap;
     int32_t dbg;   // timing experiments only (FDFD_RP_DEBUG bit mask; results are wrong): 1 no material loads,
-                   // 2 no y stores, 4 no x loads, 8 no arithmetic
+                   // 2 no y stores, 4 no x loads, 8 no arithmetic; 16, 32 (results stay right): no early stage release, no table fill ahead of the item
 };
 
 template <int NWC, int NST, bool MDR, bool HAS_OFF>
@@ -156,6 +156,43 @@ __global__ void __launch_bounds__(32 * (NWC + 1), 1) apply_rowpair_kernel(const 
         // =============================== producer warp ======================================================
         int itc = 0;
         uint32_t aux_phase = 0;   // bit s: parity of the phase of aux[s] that the next box sent there completes
+        // coefficient tables of one item (double-buffered by item parity).  They are written when the buffer's previous
+        // user - the item before the previous one - has been left by every compute warp: at the first load of the item
+        // (the stage just waited for was filled during the previous item), or AHEAD, behind the last load of the previous
+        // item, when that item is long enough for the same argument (its load NST has been waited for) - then the global
+        // loads below overlap the wait for a free stage instead of delaying the item's first planes.
+        bool tabs_ready = false;
+        auto fill_tables = [&](int it, int itcount) {
+            int b = it;
+            const int tile_x = b % tp.ntx; b /= tp.ntx;
+            const int tile_y = b % tp.nty;
+            const int chunk = b / tp.nty;
+            const int ox = tile_x * (TX - 2) - 1, oy = tile_y * (2 * NWC) - 1;
+            const int kc0 = chunk_begin(tp.kl_begin, tp.kl_end, tp.nchunk, chunk);
+            const int kc1 = chunk_begin(tp.kl_begin, tp.kl_end, tp.nchunk, chunk + 1);
+            const int nplanes = kc1 - kc0 + 2;
+            double2 *tb = tabs + (itcount & 1) * C::TABS;
+            auto tab = [&](int a, int w) -> const double2 * {
+                return a == 0 ? p.c.a0[w] : a == 1 ? p.c.a1[w] : a == 2 ? p.c.b0[w] : a == 3 ? p.c.b1[w]
+                     : a == 4 ? p.c.mi0[w] : a == 5 ? p.c.mi1[w] : a == 6 ? p.c.mo0[w] : p.c.mo1[w];
+            };
+            for (int t = lane; t < NTAB * NR; t += 32) {
+                const int a = t / NR, r = t % NR;
+                const int j = (((oy + r) % Ny) + Ny) % Ny;
+                tb[t] = tab(a, 1)[j];
+            }
+            for (int t = lane; t < NTAB * nplanes; t += 32) {
+                const int a = t / nplanes, m = t % nplanes;
+                int kg = p.kz0 + (SGZ < 0 ? kc1 - m : kc0 - 1 + m);
+                kg = ((kg % p.Nz) + p.Nz) % p.Nz;
+                tb[NTAB * NR + a * LZP + m] = tab(a, 2)[kg];
+            }
+            if (HAS_OFF) {
+                const int i = (((ox + lane) % Nx) + Nx) % Nx;    // x tables of the averages, by tile column
+                for (int a = 0; a < 4; ++a) tb[C::XT0 + a * TX + lane] = tab(4 + a, 0)[i];
+            }
+            __syncwarp();
+        };
         for (int item = blockIdx.x; item < tp.nitems; item += gridDim.x, ++itc) {
             int b = item;
             const int tile_x = b % tp.ntx; b /= tp.ntx;
@@ -246,31 +283,8 @@ __global__ void __launch_bounds__(32 * (NWC + 1), 1) apply_rowpair_kernel(const 
             for (int n = 0; n < nplanes; ++n, ++g) {
                 const int s = g % NST;
                 if (g >= NST) mbar_wait(&empty[s], ((g / NST) - 1) & 1);
-                if (n == 0) {
-                    // tables of this item (double-buffered by item parity): every compute warp has left the item
-                    // before the previous one, because the stage just waited for was filled during the previous item
-                    double2 *tb = tabs + (itc & 1) * C::TABS;
-                    auto tab = [&](int a, int w) -> const double2 * {
-                        return a == 0 ? p.c.a0[w] : a == 1 ? p.c.a1[w] : a == 2 ? p.c.b0[w] : a == 3 ? p.c.b1[w]
-                             : a == 4 ? p.c.mi0[w] : a == 5 ? p.c.mi1[w] : a == 6 ? p.c.mo0[w] : p.c.mo1[w];
-                    };
-                    for (int t = lane; t < NTAB * NR; t += 32) {
-                        const int a = t / NR, r = t % NR;
-                        const int j = (((oy + r) % Ny) + Ny) % Ny;
-                        tb[t] = tab(a, 1)[j];
-                    }
-                    for (int t = lane; t < NTAB * nplanes; t += 32) {
-                        const int a = t / nplanes, m = t % nplanes;
-                        int kg = p.kz0 + kof(m);
-                        kg = ((kg % p.Nz) + p.Nz) % p.Nz;
-                        tb[NTAB * NR + a * LZP + m] = tab(a, 2)[kg];
-                    }
-                    if (HAS_OFF) {
-                        const int i = (((ox + lane) % Nx) + Nx) % Nx;    // x tables of the averages, by tile column
-                        for (int a = 0; a < 4; ++a) tb[C::XT0 + a * TX + lane] = tab(4 + a, 0)[i];
-                    }
-                    __syncwarp();
-                }
+                if (n == 0 && !tabs_ready) fill_tables(item, itc);
+                if (n == 0) tabs_ready = false;
                 const int kk = kof(n);
                 const bool want_m = md_tile && n >= 1 && n + 1 < nplanes;    // output planes only
                 const bool skip_x = (tp.dbg & 4) != 0;
@@ -346,6 +360,10 @@ __global__ void __launch_bounds__(32 * (NWC + 1), 1) apply_rowpair_kernel(const 
                 }
             }
             if (CMPFIRST && tp.tmap && has_wrap) finish_wrap(nplanes - 1);
+            if (nplanes - 1 >= NST && item + (int)gridDim.x < tp.nitems && !(tp.dbg & 32)) {
+                fill_tables(item + gridDim.x, itc + 1);
+                tabs_ready = true;
+            }
         }
     } else {
         // =============================== compute warps ======================================================
@@ -370,6 +388,7 @@ __global__ void __launch_bounds__(32 * (NWC + 1), 1) apply_rowpair_kernel(const 
         constexpr int NSTORE1D = CMPFIRST ? 2 : 6;
         const int NSTORE = tmap ? 1 : NSTORE1D;           // lanes that issue this warp's bulk stores
 
+        const bool no_early = (tp.dbg & 16) != 0;         // A/B timing: hold every stage to the end of its step
         double ts_re = 0.0, ts_im = 0.0, tt = 0.0;
         int itc = 0;
         for (int item = blockIdx.x; item < tp.nitems; item += gridDim.x, ++itc) {
@@ -466,6 +485,32 @@ __global__ void __launch_bounds__(32 * (NWC + 1), 1) apply_rowpair_kernel(const 
                 const double2 NB0 = en[dB], NB1 = en[dB + EC], NB2 = en[dB + 2 * EC];
                 const double2 NR1 = en[EC - dB];
 
+                // material of plane k: same ring stage as E(k)
+                double2 mdA0 = p.md_uniform, mdA1 = p.md_uniform, mdA2 = p.md_uniform;
+                double2 mdB0 = p.md_uniform, mdB1 = p.md_uniform, mdB2 = p.md_uniform;
+                auto load_md = [&]() {
+                    if (!md_tile) return;
+                    if (MDR) {   // 3 doubles per cell, rows of 32 cells
+                        const double *mr = reinterpret_cast<const double *>(ring + s_cur * STAGE + MD0) + mdr_o;
+                        mdA0 = make_double2(mr[0], 0.0); mdA1 = make_double2(mr[1], 0.0); mdA2 = make_double2(mr[2], 0.0);
+                        mdB0 = make_double2(mr[mdr_dB], 0.0); mdB1 = make_double2(mr[mdr_dB + 1], 0.0);
+                        mdB2 = make_double2(mr[mdr_dB + 2], 0.0);
+                    } else {
+                        mdA0 = es[mdo]; mdA1 = es[mdo + MC]; mdA2 = es[mdo + 2 * MC];
+                        mdB0 = es[mdo + dB]; mdB1 = es[mdo + dB + MC]; mdB2 = es[mdo + dB + 2 * MC];
+                    }
+                };
+                // EARLY RELEASE: everything this warp needs from stage es (plane k) now sits in registers, so the producer may
+                // refill the stage while the arithmetic of this step runs - the ring is effectively one stage deeper.  A plane
+                // that carries off-diagonal rows (full tensor) is held to the end of the step, which reads them; so are all
+                // planes of the variants with a q array (their eight extra operands per step leave no registers for it).
+                const bool early = !HAS_Q && !no_early && (!HAS_OFF || !oflag[s_cur]);
+                if (early) {
+                    if (do_out) load_md();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&empty[s_cur]);
+                }
+
                 double2 HxA, HyA, HzA, HxB, HyB, HzB, HxR, HzR;
                 if (!RP_ABL || !(tp.dbg & 8)) {
                     // H(k) = C1 E :  Hx = Dy Ez - Dz Ey,  Hy = Dz Ex - Dx Ez,  Hz = Dx Ey - Dy Ex
@@ -521,20 +566,7 @@ __global__ void __launch_bounds__(32 * (NWC + 1), 1) apply_rowpair_kernel(const 
                     HzBm.x = __shfl_up_sync(0xffffffffu, HzB.x, 1); HzBm.y = __shfl_up_sync(0xffffffffu, HzB.y, 1);
                     const double2 b0yA = ty[2 * NR], b1yA = ty[3 * NR], b0yB = ty[2 * NR + SGY], b1yB = ty[3 * NR + SGY];
                     const double2 b0z = tz[2 * LZP + n], b1z = tz[3 * LZP + n];
-                    // material of plane k: same ring stage as E(k)
-                    double2 mdA0 = p.md_uniform, mdA1 = p.md_uniform, mdA2 = p.md_uniform;
-                    double2 mdB0 = p.md_uniform, mdB1 = p.md_uniform, mdB2 = p.md_uniform;
-                    if (md_tile) {
-                        if (MDR) {   // 3 doubles per cell, rows of 32 cells
-                            const double *mr = reinterpret_cast<const double *>(ring + s_cur * STAGE + MD0) + mdr_o;
-                            mdA0 = make_double2(mr[0], 0.0); mdA1 = make_double2(mr[1], 0.0); mdA2 = make_double2(mr[2], 0.0);
-                            mdB0 = make_double2(mr[mdr_dB], 0.0); mdB1 = make_double2(mr[mdr_dB + 1], 0.0);
-                            mdB2 = make_double2(mr[mdr_dB + 2], 0.0);
-                        } else {
-                            mdA0 = es[mdo]; mdA1 = es[mdo + MC]; mdA2 = es[mdo + 2 * MC];
-                            mdB0 = es[mdo + dB]; mdB1 = es[mdo + dB + MC]; mdB2 = es[mdo + dB + 2 * MC];
-                        }
-                    }
+                    if (!early) load_md();
                     double2 yxA, yyA, yzA, yxB, yyB, yzB;
                     if (!RP_ABL || !(tp.dbg & 8)) {
                         // y = C2 H :  yx = Dy Hz - Dz Hy,  yy = Dz Hx - Dx Hz,  yz = Dx Hy - Dy Hx
@@ -632,11 +664,11 @@ __global__ void __launch_bounds__(32 * (NWC + 1), 1) apply_rowpair_kernel(const 
                     }
                     fence_proxy_async();   // generic-proxy writes -> visible to the bulk-copy (async) proxy
                 }
-                // stage es (plane k: E and material) is no longer needed by this warp; the same warp-wide
-                // synchronisation orders the staging writes above before the bulk store below
+                // a stage held to the end (see EARLY RELEASE) is released here; the same warp-wide synchronisation orders the
+                // staging writes above before the bulk store below
                 __syncwarp();
                 if (lane == 0) {
-                    mbar_arrive(&empty[s_cur]);
+                    if (!early) mbar_arrive(&empty[s_cur]);
                     if (n + 2 == nplanes) mbar_arrive(&empty[s_nxt]);   // last step: plane k + s1z is not revisited
                 }
                 if (do_out && st_on) {

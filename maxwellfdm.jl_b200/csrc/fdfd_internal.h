@@ -169,6 +169,7 @@ struct Ctx {
     cudaEvent_t ev_x = nullptr, ev_halo = nullptr, ev_bnd = nullptr;
     const double2 *halo_for = nullptr;  // vector whose halo planes are (being) exchanged ahead of its apply
     bool comm_pending = false;          // an NCCL op may still be running on stream_comm (ordered by ev_halo)
+    bool halo_preloaded = false;        // halo_lo / halo_hi were filled by the caller (host halos): apply_device skips the exchange
     double off_frac = 1.0;             // fraction of (tile, plane) blocks holding off-diagonal material
     bool off_sym = false;              // off-diagonal mass entries pointwise symmetric: three arrays, three aliases
     int s1[3]{+1, +1, +1};

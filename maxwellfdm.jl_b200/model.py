@@ -23,11 +23,11 @@ import itertools
 import numpy as np
 
 from .grid import EE, HH, PRIM, DUAL, Grid, PMLParam, create_stretched_dl, ft2gt
-from .operator import FdfdOperator
+from .operator import FdfdOperator, MultiGpuOperator
 from .sources import Source
 from .reduced import ReducedOperator
 
-_OPS = (FdfdOperator, ReducedOperator)      # what create_A returns (3-D model / ModelTE, ModelTM, ModelTEM)
+_OPS = (FdfdOperator, ReducedOperator, MultiGpuOperator)   # what create_A returns (3-D model / ModelTE, ModelTM, ModelTEM / ngpu=N)
 
 
 class Model:
@@ -241,7 +241,7 @@ def create_curls(mdl):
     return CurlOp("Ce", g), CurlOp("Cm", g)
 
 
-def _build(ft, w, Ps, Cs, device=-1, rank=0, nranks=1, kernel=0, weighted_out_avg=False):
+def _build(ft, w, Ps, Cs, device=-1, rank=0, nranks=1, kernel=0, weighted_out_avg=False, ngpu=None, devices=None):
     if ft not in (EE, HH):
         raise ValueError(f"ft = {ft} is unsupported.")          # model.jl:242
     Pe, Pm = Ps
@@ -251,6 +251,8 @@ def _build(ft, w, Ps, Cs, device=-1, rank=0, nranks=1, kernel=0, weighted_out_av
     g = Ce.geom
     if not g.same(Pe.geom):
         raise ValueError("create_paramops and create_curls were called on different model settings")
+    if ngpu is not None:
+        device = ("multi", int(ngpu), None if devices is None else tuple(int(v) for v in devices))
     key = (ft, complex(w), device, rank, nranks, kernel, weighted_out_avg, Pe.token, Pm.token)
     A = g.ops.get(key)
     if A is not None and not A.closed:
@@ -271,10 +273,22 @@ def _build(ft, w, Ps, Cs, device=-1, rank=0, nranks=1, kernel=0, weighted_out_av
         A = ReducedOperator(A3, int(np.prod(g.N)), g.cmp_e, g.cmp_m, ft, g.order_cmpfirst)
         g.ops[key] = A
         return A
-    from .operator import partition
-    k0, k1 = partition(g.N[2], nranks, rank)
     mu = _mu_or_none(Pm.arr)
     objects = getattr(Pe, "objects", None)
+    if ngpu is not None:
+        # one value over ngpu devices of this box (fdfd_multi_*): full-grid arrays in, the library cuts the z-slabs
+        from .operator import MultiGpuOperator
+        if nranks != 1 or rank != 0:
+            raise ValueError("ngpu (one process, several GPUs) and rank / nranks (one process per GPU) exclude each other")
+        if objects:
+            raise ValueError("ngpu: device_materials is not available through the single-call handle yet")
+        A = MultiGpuOperator(g.N, g.isbloch, g.sdl_e, g.sdl_m, w, Pe.arr, mu, g.e_mikL, boundft=g.boundft, ft=ft,
+                             order_cmpfirst=g.order_cmpfirst, ngpu=ngpu, devices=devices, kernel=kernel,
+                             weighted_out_avg=weighted_out_avg)
+        g.ops[key] = A
+        return A
+    from .operator import partition
+    k0, k1 = partition(g.N[2], nranks, rank)
     A = FdfdOperator(g.N, g.isbloch, g.sdl_e, g.sdl_m, w, None if objects else Pe.arr[:, :, k0:k1],
                      None if mu is None else mu[:, :, k0:k1], g.e_mikL, boundft=g.boundft, ft=ft,
                      order_cmpfirst=g.order_cmpfirst, device=device, rank=rank, nranks=nranks, kernel=kernel,
@@ -297,7 +311,8 @@ def create_A(ft, w, Ps, Cs=None, **kw):
     """create_A(ft, ω, Ps, Cs) (model.jl:222-246) - or create_A(ft, ω, mdl).  Returns the GPU operator (an
     FdfdOperator: supports `A @ x`, `A.solve(b)`), not a SparseMatrixCSC; nothing is assembled.  Keyword options:
     device, rank, nranks (z-slabs: this rank's slab of eps/mu is taken from the full model arrays), kernel,
-    weighted_out_avg."""
+    weighted_out_avg; ngpu=N (and optionally devices=[...]) returns ONE operator over N GPUs of this box that takes
+    full-grid host vectors (MultiGpuOperator, fdfd_multi_*)."""
     Ps, Cs = _as_ops(Ps, Cs)
     return _build(ft, w, Ps, Cs, **kw)
 

@@ -357,3 +357,144 @@ def halo_plan(nranks, rank, wrapz):
     if L.lib().fdfd_halo_plan(int(nranks), int(rank), 1 if wrapz else 0, C.byref(up), C.byref(dn)) != L.OK:
         raise ValueError("bad halo_plan arguments")
     return up.value, dn.value
+
+
+class MultiGpuOperator:
+    """ONE operator value over N GPUs of the box (fdfd_multi_*, csrc/multi.cpp): what a single-process host -
+    a Julia session holding `A = create_A(...)`, model.jl:225-246 - uses instead of one FdfdOperator per process.  Takes
+    FULL-GRID host arrays; the library splits them into z-slabs, one per device, one host thread each.
+
+    `A @ x` moves every slab (with the two neighbour planes it needs) over that GPU's own PCIe link - no exchange between
+    GPUs; `A.solve(b)` runs the slab Krylov loops with halos and inner products over NCCL."""
+
+    def __init__(self, N, isbloch, sdl_e, sdl_m, omega, eps, mu=None, e_mikL=(1, 1, 1), boundft=("E", "E", "E"), ft="E",
+                 order_cmpfirst=True, ngpu=1, devices=None, weighted_out_avg=False, kernel=L.KERNEL_AUTO, eps_has_offdiag=None):
+        self._m = None
+        lib = L.lib()
+        d = L.Desc()
+        d.N[:] = [int(n) for n in N]
+        d.isbloch[:] = [1 if b else 0 for b in isbloch]
+        d.boundft_is_E[:] = [1 if str(b).upper().startswith("E") or b == 0 else 0 for b in boundft]
+        d.order_cmpfirst = 1 if order_cmpfirst else 0
+        d.field_type = L.FT_EE if (str(ft).upper().startswith("E") or ft == 0) else L.FT_HH
+        d.device, d.rank, d.nranks = -1, 0, 1
+        d.weighted_out_avg = 1 if weighted_out_avg else 0
+        d.kernel = int(kernel)
+        devs = None if devices is None else (C.c_int32 * int(ngpu))(*[int(v) for v in devices])
+        m = C.c_void_p()
+        L.check_multi(lib.fdfd_multi_create(C.byref(m), C.byref(d), int(ngpu), devs))
+        self._m = m
+        self.ft = 0 if d.field_type == L.FT_EE else 1
+        self.N = tuple(int(n) for n in N)
+        self.ngpu = int(ngpu)
+        self.n = 3 * self.N[0] * self.N[1] * self.N[2]
+        self.shape = (self.n, self.n)
+        self.order_cmpfirst = bool(order_cmpfirst)
+        keep = [np.ascontiguousarray(a, dtype=np.complex128) for a in list(sdl_e) + list(sdl_m)]
+        pe = (C.c_void_p * 3)(*[a.ctypes.data for a in keep[:3]])
+        pm = (C.c_void_p * 3)(*[a.ctypes.data for a in keep[3:]])
+        L.check_multi(lib.fdfd_multi_set_coeffs(m, pe, pm), m)
+        ph = np.ascontiguousarray(e_mikL, dtype=np.complex128)
+        L.check_multi(lib.fdfd_multi_set_bloch(m, ph.ctypes.data), m)
+        self.omega = complex(omega)
+        L.check_multi(lib.fdfd_multi_set_omega(m, _c128(omega)), m)
+        if eps is not None:
+            buf = self._material(eps, "eps")
+            L.check_multi(lib.fdfd_multi_set_eps(m, buf.ctypes.data, 0 if eps_has_offdiag is False else 1), m)
+        if mu is not None:
+            buf = self._material(mu, "mu")
+            L.check_multi(lib.fdfd_multi_set_mu(m, buf.ctypes.data), m)
+
+    def _material(self, a, name):
+        a = np.asarray(a)
+        Nx, Ny, Nz = self.N
+        if a.shape == (3, 3, Nz, Ny, Nx) and a.dtype == np.complex128 and a.flags.c_contiguous and (Ny, Nx) != (3, 3):
+            return a                      # already the memory of the Julia column-major (Nx,Ny,Nz,3,3) array
+        if a.shape != (Nx, Ny, Nz, 3, 3):
+            raise ValueError(f"{name} must have shape (Nx,Ny,Nz,3,3) = {(Nx, Ny, Nz, 3, 3)} (the whole grid)")
+        return FdfdOperator._julia_layout(a)
+
+    def close(self):
+        if self._m is not None:
+            L.lib().fdfd_multi_destroy(self._m)
+            self._m = None
+
+    @property
+    def closed(self):
+        return self._m is None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _vec(self, x, name, out=False):
+        if hasattr(x, "is_cuda"):
+            if x.is_cuda:
+                raise ValueError(f"{name}: a multi-GPU operator takes full-grid HOST vectors")
+            x = x.numpy()
+        if out:
+            if not isinstance(x, np.ndarray) or x.dtype != np.complex128 or x.shape != (self.n,) or not x.flags.c_contiguous \
+                    or not x.flags.writeable:
+                raise ValueError(f"{name} must be a writeable contiguous complex128 host array of {self.n} elements")
+            return x
+        x = np.ascontiguousarray(x, dtype=np.complex128)
+        if x.shape != (self.n,):
+            raise ValueError(f"{name} must have {self.n} elements")
+        return x
+
+    def slab(self, r):
+        """(raw slab handle, k0, k1) of slab r - for the measurement entry points of the slab API"""
+        h, k0, k1 = C.c_void_p(), C.c_int64(), C.c_int64()
+        L.check_multi(L.lib().fdfd_multi_slab(self._m, int(r), C.byref(h), C.byref(k0), C.byref(k1)), self._m)
+        return h, k0.value, k1.value
+
+    def mul(self, y, x, transpose=False):
+        """mul!(y, A, x) on full-grid host vectors"""
+        x = self._vec(x, "x")
+        yv = self._vec(y, "y", out=True)
+        f = L.lib().fdfd_multi_apply_transpose if transpose else L.lib().fdfd_multi_apply
+        L.check_multi(f(self._m, x.ctypes.data, yv.ctypes.data), self._m)
+        return y
+
+    def __matmul__(self, x):
+        return self.mul(np.empty(self.n, dtype=np.complex128), x)
+
+    __mul__ = __matmul__
+
+    def solve(self, b, x0=None, method="bicgstab", rtol=1e-8, maxit=10000, check_every=10, history=False, out=None):
+        """x = A \\ b.  Returns (x, info).  `out`: result buffer (e.g. pinned memory); it also carries the initial guess."""
+        b = self._vec(b, "b")
+        if out is not None:
+            x = self._vec(out, "out", out=True)
+            if x0 is not None:
+                x[:] = self._vec(x0, "x0")
+        else:
+            x = np.zeros(self.n, dtype=np.complex128) if x0 is None else self._vec(x0, "x0").copy()
+        m = L.BICGSTAB if str(method).lower().startswith("bi") else L.QMR
+        iters, relres = C.c_int(), C.c_double()
+        hist = np.full(maxit + 1, np.nan) if history else None
+        code = L.lib().fdfd_multi_solve(self._m, m, b.ctypes.data, x.ctypes.data, float(rtol), int(maxit), int(check_every),
+                                        C.byref(iters), C.byref(relres), hist.ctypes.data if history else None)
+        L.check_multi(code, self._m, ok=(L.OK, L.ENOCONV))
+        info = {"iters": iters.value, "relres": relres.value, "converged": code == L.OK}
+        if history:
+            info["history"] = hist[: iters.value + 1]
+        return x, info
+
+    def _vec_op(self, fn, a, b_or_none):
+        a = self._vec(a, "input")
+        b = None if b_or_none is None else self._vec(b_or_none, "input")
+        out = np.empty(self.n, dtype=np.complex128)
+        L.check_multi(fn(self._m, a.ctypes.data, None if b is None else b.ctypes.data, out.ctypes.data), self._m)
+        return out
+
+    def create_b(self, je, jm=None):
+        return self._vec_op(L.lib().fdfd_multi_create_b, je, jm)
+
+    def h_from_e(self, e, jm=None):
+        return self._vec_op(L.lib().fdfd_multi_h_from_e, e, jm)
+
+    def e_from_h(self, h, je=None):
+        return self._vec_op(L.lib().fdfd_multi_e_from_h, h, je)

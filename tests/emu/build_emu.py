@@ -24,7 +24,7 @@ OUT_DIR = os.path.join(ROOT, "build", "emu_fma" if FMA else "emu")
 OUT_LIB = os.path.join(OUT_DIR, "libfdfd_emu.so")
 FAKE_DIR = os.path.join(OUT_DIR, "fakelibs")
 SOURCES = ["api.cu", "apply_naive.cu", "apply_tiled.cu", "apply_rowpair.cu", "krylov.cu", "qmr.cu", "matparams.cu", "coeffs.cpp", "pattern.cpp", "comm.cpp",
-           "peer.cpp", "tmap.cpp"]
+           "peer.cpp", "tmap.cpp", "multi.cpp"]
 
 
 def _split_top(s):

@@ -88,6 +88,25 @@ def child(rank, world, groups):
             return v[3 * Nx * Ny * k0:3 * Nx * Ny * k1].copy()
         return np.ascontiguousarray(v.reshape(3, Nz, Ny * Nx)[:, k0:k1]).ravel()
 
+    def plane_of(p, v, k):
+        """plane k of a global DOF vector in the halo layout (None outside a non-periodic grid)"""
+        Nx, Ny, Nz = p.N
+        if k < 0 or k >= Nz:
+            if not p.isbloch[2]:
+                return None
+            k %= Nz
+        if p.cmpfirst:
+            return v[3 * Nx * Ny * k:3 * Nx * Ny * (k + 1)].copy()
+        return np.ascontiguousarray(v.reshape(3, Nz, Ny * Nx)[:, k]).ravel()
+
+    def host_halo_apply(A, p, x, k0, k1, transpose=False):
+        """fdfd_apply_host_halos: the caller holds the whole vector, the neighbour planes ride along (no exchange)"""
+        xs, lo, hi = slab_of(p, x, k0, k1), plane_of(p, x, k0 - 1), plane_of(p, x, k1)
+        y = np.full(A.n, np.nan + 1j * np.nan)
+        L.check(L.lib().fdfd_apply_host_halos(A._h, xs.ctypes.data, None if lo is None else lo.ctypes.data,
+                                              None if hi is None else hi.ctypes.data, y.ctypes.data, 1 if transpose else 0), A._h)
+        return y
+
     def dev_apply(A, x, transpose=False):
         y = np.full(A.n, np.nan + 1j * np.nan)
         f = L.lib().fdfd_apply_transpose if transpose else L.lib().fdfd_apply
@@ -111,6 +130,9 @@ def child(rank, world, groups):
         # pointwise symmetric on that slab and once not
         cases.append(dict(N=(21, 18, 4 * world), isbloch=(True, True, True), full_eps=True, with_mu=False, kernel=0, only_slab=1, sym=True))
         cases.append(dict(N=(21, 18, 4 * world), isbloch=(False, True, False), full_eps=True, with_mu=True, kernel=0, only_slab=0, sym=False))
+        # slabs of >= 16 planes: the host-buffer applies run the sub-slab pipeline (per slab, halos from the host vector)
+        cases.append(dict(N=(21, 10, 17 * world), isbloch=(True, False, True), full_eps=True, with_mu=False, kernel=0))
+        cases.append(dict(N=(21, 10, 16 * world + 1), isbloch=(False, True, False), full_eps=False, with_mu=False, kernel=0, real_mass=True))
         for cs in cases:
             kern = cs.pop("kernel")
             lz = cs.pop("lz", 0)
@@ -142,10 +164,14 @@ def child(rank, world, groups):
             e2 = rel(yh, slab_of(p, mf(x), k0, k1))
             yt = dev_apply(A, xs, True)
             A_ref, _ = p.oracle_csc()
-            e3 = rel(yt, slab_of(p, A_ref.to_scipy().T @ x, k0, k1))
+            yT_ref = slab_of(p, A_ref.to_scipy().T @ x, k0, k1)
+            e3 = rel(yt, yT_ref)
+            e4 = rel(host_halo_apply(A, p, x, k0, k1), slab_of(p, mf(x), k0, k1))
+            e5 = rel(host_halo_apply(A, p, x, k0, k1, True), yT_ref)
+            e6 = rel(dev_apply(A, xs), slab_of(p, mf(x), k0, k1))      # and the exchange path still works afterwards
             A.close()
-            assert e1 < 1e-12 and e2 < 1e-12 and e3 < 1e-12, (rank, cs, kern, e1, e2, e3)
-            nchecks += 3
+            assert max(e1, e2, e3, e4, e5, e6) < 1e-12, (rank, cs, kern, e1, e2, e3, e4, e5, e6)
+            nchecks += 6
     if "apply" in groups:
         # eps from objects on z-slabs: every rank rasterises its own planes; the slabs together are the single-slab operator
         from problems import matparams_scene

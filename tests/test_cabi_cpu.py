@@ -32,6 +32,32 @@ def test_library_exports_every_declared_symbol():
     assert b"sm_100a" in lib.fdfd_version()
 
 
+def test_plain_c_consumer_and_struct_layouts(tmp_path):
+    """tests/cabi_smoke.c: the header compiles as plain C, the library links from C, and the struct layouts a foreign
+    binding must reproduce (ctypes here, the Julia struct in julia/FDFDB200.jl) are the C compiler's."""
+    import subprocess
+    L = _lib()
+    exe = str(tmp_path / "cabi_smoke")
+    libdir = os.path.dirname(L.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cabi_smoke.c"),
+                    "-o", exe, "-L", libdir, "-l:" + os.path.basename(L.LIB_PATH), "-Wl,-rpath," + libdir], check=True)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
+    assert "cabi_smoke ok" in out, out
+    offs = dict(l.split() for l in out.splitlines() if re.match(r"^(fdfd_\w+\.\w+|sizeof\.\w+) \d+$", l))
+    for cname, T in (("fdfd_desc", L.Desc), ("fdfd_shape", L.Shape), ("fdfd_matparams_desc", L.MatParamsDesc), ("fdfd_c128", L.c128)):
+        assert int(offs["sizeof." + cname]) == C.sizeof(T), cname
+        for f, _ in T._fields_:
+            key = f"{cname}.{f}"
+            if key in offs:
+                assert int(offs[key]) == getattr(T, f).offset, key
+    assert sum(k.startswith("fdfd_desc.") for k in offs) == len(L.Desc._fields_)
+    # the Julia binding lists the same fields in the same order (isbits struct = C layout)
+    jl = open(os.path.join(ROOT, "julia", "FDFDB200.jl")).read()
+    body = re.search(r"\nstruct Desc\n(.*?)\nend", jl, re.S).group(1)
+    jl_fields = re.findall(r"^\s*(\w+)::", body, re.M)
+    assert jl_fields == [f for f, _ in L.Desc._fields_], jl_fields
+
+
 def test_partition_rule():
     import maxwellfdm_jl_b200 as fb
     for Nz, P in [(1, 1), (7, 3), (768, 8), (512, 8), (5, 5), (200, 7)]:
