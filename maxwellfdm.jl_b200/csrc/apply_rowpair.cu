@@ -504,7 +504,8 @@ __global__ void __launch_bounds__(32 * (NWC + 1), 1) apply_rowpair_kernel(const 
                 // refill the stage while the arithmetic of this step runs - the ring is effectively one stage deeper.  A plane
                 // that carries off-diagonal rows (full tensor) is held to the end of the step, which reads them; so are all
                 // planes of the variants with a q array (their eight extra operands per step leave no registers for it).
-                const bool early = !HAS_Q && !no_early && (!HAS_OFF || !oflag[s_cur]);
+                const bool off_cur = HAS_OFF && oflag[s_cur] != 0;   // read ONCE: after an early release the slot may change
+                const bool early = !HAS_Q && !no_early && !off_cur;
                 if (early) {
                     if (do_out) load_md();
                     __syncwarp();
@@ -603,7 +604,7 @@ __global__ void __launch_bounds__(32 * (NWC + 1), 1) apply_rowpair_kernel(const 
                         // occupancy mask of the producer is per tile, this test is per row pair).
                         bool fC = false;
                         double o01A = 0.0, o02A = 0.0, o12A = 0.0, o01B = 0.0, o02B = 0.0, o12B = 0.0, o01F = 0.0, o12F = 0.0;
-                        if (oflag[s_cur]) {
+                        if (off_cur) {
                             const double *mo = reinterpret_cast<const double *>(ring + s_cur * STAGE + C::MO0) + mo_o;
                             o01A = mo[0]; o02A = mo[1]; o12A = mo[2];
                             o01B = mo[mdr_dB]; o02B = mo[mdr_dB + 1]; o12B = mo[mdr_dB + 2];
