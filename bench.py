@@ -323,6 +323,46 @@ def measure_config(name, w, local, rank, world, steps, kry_iters, gen, extra=Non
     return out
 
 
+def single_call_block(N, per, ngpu, steps, kry_iters):
+    """e2e through the single-call boundary: MultiGpuOperator over `ngpu` devices driven by THIS process alone, on the same
+    replicated-C2 grid as the headline; pinned full-grid host vectors; apply = mul!(y, A, x), solve = A \\ b with a fixed
+    iteration count (b copied in, x copied out)."""
+    import numpy as np
+    import torch
+    import workloads
+    import maxwellfdm_jl_b200 as fb
+    t0 = time.perf_counter()
+    w = workloads.c2_waveguide(N, 0, N[2], period_z=per[2])
+    A = fb.MultiGpuOperator(w["N"], w["isbloch"], w["sdl_e"], w["sdl_m"], w["omega"], w["eps"], None, w["e_mikL"], ngpu=ngpu)
+    del w
+    n = A.n
+    xh = torch.empty(n, dtype=torch.complex128).pin_memory()
+    yh = torch.empty(n, dtype=torch.complex128).pin_memory()
+    g = torch.Generator().manual_seed(7)
+    xh.copy_(torch.randn(n, 2, dtype=torch.float64, generator=g).view(torch.complex128).reshape(-1))
+    A.mul(yh.numpy(), xh.numpy())
+    setup_s = time.perf_counter() - t0
+    ts = []
+    for _ in range(steps):
+        t1 = time.perf_counter()
+        A.mul(yh.numpy(), xh.numpy())
+        ts.append(time.perf_counter() - t1)
+    t_apply = statistics.median(ts)
+    A.solve(xh.numpy(), rtol=1e-300, maxit=3, check_every=1 << 30, out=yh.numpy())
+    yh.zero_()
+    t1 = time.perf_counter()
+    _, info = A.solve(xh.numpy(), rtol=1e-300, maxit=kry_iters, check_every=1 << 30, out=yh.numpy())
+    t_solve = time.perf_counter() - t1
+    A.close()
+    return {"n_gpus": ngpu, "grid": list(N), "dof": n, "apply_gdof_s": n / t_apply / 1e9, "apply_ms": t_apply * 1e3,
+            "apply_gdof_s_per_gpu": n / t_apply / 1e9 / ngpu, "h2d_bytes_per_apply": 16 * n + 32 * (ngpu - 1) * 3 * N[0] * N[1],
+            "d2h_bytes_per_apply": 16 * n, "solve_iters": info["iters"], "solve_seconds": t_solve,
+            "solve_iter_per_s": info["iters"] / t_solve, "solve_gdof_iter_per_s": n * info["iters"] / t_solve / 1e9,
+            "setup_s": setup_s,
+            "note": "ONE process / ONE handle over all GPUs (fdfd_multi_apply, fdfd_multi_solve): host threads = GPUs, halo "
+                    "planes of an apply ride along with the H2D copies, Krylov halos and dots over NCCL"}
+
+
 def parity_block(local, rank, world):
     """UNTIMED correctness check at this N (oracle = checker): a reduced copy of the C2 workload (full 3x3 eps with
     off-diagonals, PML) on world z-slabs - (a) y = A x on this rank's planes against the oracle's matrix-free numpy
@@ -376,6 +416,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-configs", action="store_true", help="skip the per-configuration block (N = 1)")
     ap.add_argument("--no-scale", action="store_true", help="skip the C5 weak / C4 strong scaling blocks")
+    ap.add_argument("--no-single-call", action="store_true", help="skip the one-process / N-GPU boundary measurement")
     ap.add_argument("--diag", action="store_true", help="diagonal-eps variant of the workload (48 B/DOF)")
     ap.add_argument("--dense-off", action="store_true",
                     help="variant with non-zero off-diagonal eps in EVERY cell (dense full-tensor kernel path)")
@@ -544,6 +585,16 @@ def main():
                                                   workloads.c5_objects(N=(1024, 1024, 96 * world)), local, rank, world,
                                                   20, 10, gen))
 
+    # ---- the drop-in boundary itself: ONE process, ONE call, `world` GPUs (fdfd_multi_*) ------------------
+    # Rank 0 alone drives every GPU of the job through a single handle - full-grid pinned host vectors in and out, the
+    # library cuts the z-slabs (one host thread per device) - while the other ranks wait at the barrier below.
+    single_call = None
+    if not args.n and not args.no_single_call:
+        barrier(world)
+        if rank == 0:
+            single_call = guarded(lambda: single_call_block(N, per, world, e2e_steps, args.krylov_iters))
+        barrier(world)
+
     if rank == 0:
         achieved = bpd * (n_tot / world) / (ms_step * 1e-3) / 1e9      # per GPU
         traffic = None
@@ -584,6 +635,8 @@ def main():
                        "error": krylov_error,
                        "qmr_iter_per_s": qmr_it_per_s, "qmr_bytes_per_dof_model": 2 * bpd + 304},
         }
+        if single_call is not None:
+            line["e2e_single_call"] = single_call
         if halo is not None:
             line["halo"] = halo
         if configs is not None:

@@ -57,7 +57,7 @@ struct RowPairParams {
     TmaMap mx, mlo, mhi, mmd, mmo, my;
     int32_t tmap;
     int32_t dbg;   // timing experiments only (FDFD_RP_DEBUG bit mask; results are wrong): 1 no material loads,
-                   // 2 no y stores, 4 no x loads, 8 no arithmetic; 16, 32 (results stay right): no early stage release, no table fill ahead of the item
+                   // 2 no y stores, 4 no x loads, 8 no arithmetic; 16, 32 (results stay right): no early stage release, no table fill ahead of the item; 64: no real-coefficient fast path
 };
 
 template <int NWC, int NST, bool MDR, bool HAS_OFF>
@@ -92,6 +92,23 @@ __device__ __forceinline__ double2 r_mul(double a, double2 z) { return make_doub
 __device__ __forceinline__ double2 r_fma(double a, double2 z, double2 acc) {
     return make_double2(fma(a, z.x, acc.x), fma(a, z.y, acc.y));
 }
+
+// coefficient times value with a compile-time choice of coefficient kind: RC = the coefficient's imaginary part is known to
+// be zero (grid cells outside the PML and away from a Bloch boundary with a complex phase) - half the multiply-adds
+template <bool RC> __device__ __forceinline__ double2 k_mul(double2 a, double2 z) {
+    if (RC) return make_double2(a.x * z.x, a.x * z.y);
+    return c_mul(a, z);
+}
+template <bool RC> __device__ __forceinline__ double2 k_fma(double2 a, double2 z, double2 acc) {
+    if (RC) return make_double2(fma(a.x, z.x, acc.x), fma(a.x, z.y, acc.y));
+    return c_fma(a, z, acc);
+}
+template <bool RC> __device__ __forceinline__ double2 k_fms(double2 a, double2 z, double2 acc) {
+    if (RC) return make_double2(fma(-a.x, z.x, acc.x), fma(-a.x, z.y, acc.y));
+    return c_fms(a, z, acc);
+}
+struct RealCoef { static constexpr bool value = true; };
+struct CplxCoef { static constexpr bool value = false; };
 
 // chunk c of nch over [kb, ke): sizes differ by at most one plane
 __host__ __device__ __forceinline__ int chunk_begin(int kb, int ke, int nch, int c) {
@@ -449,6 +466,18 @@ __global__ void __launch_bounds__(32 * (NWC + 1), 1) apply_rowpair_kernel(const 
             double2 EB0 = es[dB], EB1 = es[dB + EC], EB2 = es[dB + 2 * EC];
             double2 ER1 = es[EC - dB];
             double2 HpxA = c_zero(), HpyA = c_zero(), HpxB = c_zero(), HpyB = c_zero();
+            // REAL-COEFFICIENT FAST PATH: outside the PML (and away from a Bloch boundary with a complex phase) every curl
+            // coefficient is real, so a coefficient times a field value costs two multiply-adds instead of four.  Decided
+            // per warp: x and y tables once per item (rcxy), the z tables of the plane per step - same results, since the
+            // skipped terms are exact zeros times finite values.
+            // (the tables become visible with the first plane of the item: read them after that wait)
+            bool rcxy;
+            {
+                bool re = (a0x.y == 0.0) & (a1x.y == 0.0) & (b0x.y == 0.0) & (b1x.y == 0.0);
+#pragma unroll
+                for (int a = 0; a < 4; ++a) re &= (ty[a * NR - SGY].y == 0.0) & (ty[a * NR].y == 0.0) & (ty[a * NR + SGY].y == 0.0);
+                rcxy = __all_sync(0xffffffffu, re) && !(tp.dbg & 64);
+            }
 
 #pragma unroll 2
             for (int n = 0; n + 1 < nplanes; ++n, ++g) {
@@ -476,6 +505,7 @@ __global__ void __launch_bounds__(32 * (NWC + 1), 1) apply_rowpair_kernel(const 
                 const double2 a0yA = ty[0], a1yA = ty[NR], a0yB = ty[SGY], a1yB = ty[NR + SGY];
                 const double2 a0yR = ty[-SGY], a1yR = ty[NR - SGY];
                 const double2 a0z = tz[n], a1z = tz[LZP + n];
+                const bool rc1 = rcxy && __all_sync(0xffffffffu, (a0z.y == 0.0) & (a1z.y == 0.0));
 
                 // plane k + s1z
                 const int s_nxt = (s_cur + 1 == NST) ? 0 : s_cur + 1;
@@ -485,6 +515,51 @@ __global__ void __launch_bounds__(32 * (NWC + 1), 1) apply_rowpair_kernel(const 
                 const double2 NB0 = en[dB], NB1 = en[dB + EC], NB2 = en[dB + 2 * EC];
                 const double2 NR1 = en[EC - dB];
 
+                double2 cxA = c_zero(), cxB = c_zero(), cyA = c_zero(), cyB = c_zero();
+                auto off_xy = [&]() {
+                    // full tensor, x / y halves of y += Mout [P_off (Min x)] on plane k (model.jl:149-153), formed FIRST so that
+                    // the stage can be released before the curl arithmetic (see EARLY RELEASE below).
+                    // Corner values of plane k: G_x, G_y at this pair's cells (G_y also at the row above the pair, F -
+                    // recomputed like H of the row below), G_x of the forward x-neighbour by shuffle; G_z(k) was formed
+                    // one step earlier.  A warp whose entries are all zero on this plane skips the block (the
+                    // occupancy mask of the producer is per tile, this test is per row pair).
+                    bool fC = false;
+                    double o01A = 0.0, o02A = 0.0, o12A = 0.0, o01B = 0.0, o02B = 0.0, o12B = 0.0, o01F = 0.0, o12F = 0.0;
+                    if (oflag[s_cur]) {
+                        const double *mo = reinterpret_cast<const double *>(ring + s_cur * STAGE + C::MO0) + mo_o;
+                        o01A = mo[0]; o02A = mo[1]; o12A = mo[2];
+                        o01B = mo[mdr_dB]; o02B = mo[mdr_dB + 1]; o12B = mo[mdr_dB + 2];
+                        o01F = mo[2 * mdr_dB]; o12F = mo[2 * mdr_dB + 2];
+                        fC = __any_sync(0xffffffffu, (o01A != 0.0) | (o02A != 0.0) | (o12A != 0.0) | (o01B != 0.0) |
+                                                         (o02B != 0.0) | (o12B != 0.0) | (o01F != 0.0) | (o12F != 0.0));
+                    }
+                    if (fC) {
+                        const double2 mi0x = txo[0], mi1x = txo[TX];
+                        const double2 mi0z = tz[4 * LZP + n], mi1z = tz[5 * LZP + n];
+                        const double2 AxA = c_fma(mi1x, es[-exf], c_mul(mi0x, EA0));
+                        const double2 AxB = c_fma(mi1x, es[dB - exf], c_mul(mi0x, EB0));
+                        const double2 AxF = c_fma(mi1x, es[2 * dB - exf], c_mul(mi0x, EF0));
+                        const double2 AyA = c_fma(ty[5 * NR], ER1, c_mul(ty[4 * NR], EA1));
+                        const double2 AyB = c_fma(ty[5 * NR + SGY], EA1, c_mul(ty[4 * NR + SGY], EB1));
+                        const double2 AzA = c_fma(mi1z, E2pA, c_mul(mi0z, EA2));
+                        const double2 AzB = c_fma(mi1z, E2pB, c_mul(mi0z, EB2));
+                        const double2 AzF = c_fma(mi1z, E2pF, c_mul(mi0z, EF2));
+                        const double2 GxA = r_fma(o02A, AzA, r_mul(o01A, AyA));
+                        const double2 GxB = r_fma(o02B, AzB, r_mul(o01B, AyB));
+                        const double2 GyA = r_fma(o12A, AzA, r_mul(o01A, AxA));
+                        const double2 GyB = r_fma(o12B, AzB, r_mul(o01B, AxB));
+                        const double2 GyF = r_fma(o12F, AzF, r_mul(o01F, AxF));
+                        double2 GxAp, GxBp;   // G_x of the forward x-neighbour: the next lane
+                        GxAp.x = __shfl_down_sync(0xffffffffu, GxA.x, 1); GxAp.y = __shfl_down_sync(0xffffffffu, GxA.y, 1);
+                        GxBp.x = __shfl_down_sync(0xffffffffu, GxB.x, 1); GxBp.y = __shfl_down_sync(0xffffffffu, GxB.y, 1);
+                        const double2 mo0x = txo[2 * TX], mo1x = txo[3 * TX];
+                        cxA = c_fma(mo1x, GxAp, c_mul(mo0x, GxA));
+                        cxB = c_fma(mo1x, GxBp, c_mul(mo0x, GxB));
+                        cyA = c_fma(ty[7 * NR], GyB, c_mul(ty[6 * NR], GyA));
+                        cyB = c_fma(ty[7 * NR + SGY], GyF, c_mul(ty[6 * NR + SGY], GyB));
+                    }
+                };
+                if (HAS_OFF && !HAS_Q && do_out) off_xy();
                 // material of plane k: same ring stage as E(k)
                 double2 mdA0 = p.md_uniform, mdA1 = p.md_uniform, mdA2 = p.md_uniform;
                 double2 mdB0 = p.md_uniform, mdB1 = p.md_uniform, mdB2 = p.md_uniform;
@@ -501,11 +576,9 @@ __global__ void __launch_bounds__(32 * (NWC + 1), 1) apply_rowpair_kernel(const 
                     }
                 };
                 // EARLY RELEASE: everything this warp needs from stage es (plane k) now sits in registers, so the producer may
-                // refill the stage while the arithmetic of this step runs - the ring is effectively one stage deeper.  A plane
-                // that carries off-diagonal rows (full tensor) is held to the end of the step, which reads them; so are all
-                // planes of the variants with a q array (their eight extra operands per step leave no registers for it).
-                const bool off_cur = HAS_OFF && oflag[s_cur] != 0;   // read ONCE: after an early release the slot may change
-                const bool early = !HAS_Q && !no_early && !off_cur;
+                // refill the stage while the arithmetic of this step runs - the ring is effectively one stage deeper.  Only the
+                // variants with a q array hold the stage to the end (their eight extra operands per step leave no registers).
+                const bool early = !HAS_Q && !no_early;
                 if (early) {
                     if (do_out) load_md();
                     __syncwarp();
@@ -514,16 +587,20 @@ __global__ void __launch_bounds__(32 * (NWC + 1), 1) apply_rowpair_kernel(const 
 
                 double2 HxA, HyA, HzA, HxB, HyB, HzB, HxR, HzR;
                 if (!RP_ABL || !(tp.dbg & 8)) {
-                    // H(k) = C1 E :  Hx = Dy Ez - Dz Ey,  Hy = Dz Ex - Dx Ez,  Hz = Dx Ey - Dy Ex
-                    HxA = c_mul(a0yA, EA2); HxA = c_fma(a1yA, EB2, HxA); HxA = c_fms(a0z, EA1, HxA); HxA = c_fms(a1z, NA1, HxA);
-                    HyA = c_mul(a0z, EA0);  HyA = c_fma(a1z, NA0, HyA);  HyA = c_fms(a0x, EA2, HyA); HyA = c_fms(a1x, EA2x, HyA);
-                    HzA = c_mul(a0x, EA1);  HzA = c_fma(a1x, EA1x, HzA); HzA = c_fms(a0yA, EA0, HzA); HzA = c_fms(a1yA, EB0, HzA);
-                    HxB = c_mul(a0yB, EB2); HxB = c_fma(a1yB, EF2, HxB); HxB = c_fms(a0z, EB1, HxB); HxB = c_fms(a1z, NB1, HxB);
-                    HyB = c_mul(a0z, EB0);  HyB = c_fma(a1z, NB0, HyB);  HyB = c_fms(a0x, EB2, HyB); HyB = c_fms(a1x, EB2x, HyB);
-                    HzB = c_mul(a0x, EB1);  HzB = c_fma(a1x, EB1x, HzB); HzB = c_fms(a0yB, EB0, HzB); HzB = c_fms(a1yB, EF0, HzB);
-                    // the two components of the row below that this pair's second curl needs (recomputed, not exchanged)
-                    HxR = c_mul(a0yR, ER2); HxR = c_fma(a1yR, EA2, HxR); HxR = c_fms(a0z, ER1, HxR); HxR = c_fms(a1z, NR1, HxR);
-                    HzR = c_mul(a0x, ER1);  HzR = c_fma(a1x, ER1x, HzR); HzR = c_fms(a0yR, ER0, HzR); HzR = c_fms(a1yR, EA0, HzR);
+                    auto curl1 = [&](auto kind) {
+                        constexpr bool R = decltype(kind)::value;
+                        // H(k) = C1 E :  Hx = Dy Ez - Dz Ey,  Hy = Dz Ex - Dx Ez,  Hz = Dx Ey - Dy Ex
+                        HxA = k_mul<R>(a0yA, EA2); HxA = k_fma<R>(a1yA, EB2, HxA); HxA = k_fms<R>(a0z, EA1, HxA); HxA = k_fms<R>(a1z, NA1, HxA);
+                        HyA = k_mul<R>(a0z, EA0);  HyA = k_fma<R>(a1z, NA0, HyA);  HyA = k_fms<R>(a0x, EA2, HyA); HyA = k_fms<R>(a1x, EA2x, HyA);
+                        HzA = k_mul<R>(a0x, EA1);  HzA = k_fma<R>(a1x, EA1x, HzA); HzA = k_fms<R>(a0yA, EA0, HzA); HzA = k_fms<R>(a1yA, EB0, HzA);
+                        HxB = k_mul<R>(a0yB, EB2); HxB = k_fma<R>(a1yB, EF2, HxB); HxB = k_fms<R>(a0z, EB1, HxB); HxB = k_fms<R>(a1z, NB1, HxB);
+                        HyB = k_mul<R>(a0z, EB0);  HyB = k_fma<R>(a1z, NB0, HyB);  HyB = k_fms<R>(a0x, EB2, HyB); HyB = k_fms<R>(a1x, EB2x, HyB);
+                        HzB = k_mul<R>(a0x, EB1);  HzB = k_fma<R>(a1x, EB1x, HzB); HzB = k_fms<R>(a0yB, EB0, HzB); HzB = k_fms<R>(a1yB, EF0, HzB);
+                        // the two components of the row below that this pair's second curl needs (recomputed, not exchanged)
+                        HxR = k_mul<R>(a0yR, ER2); HxR = k_fma<R>(a1yR, EA2, HxR); HxR = k_fms<R>(a0z, ER1, HxR); HxR = k_fms<R>(a1z, NR1, HxR);
+                        HzR = k_mul<R>(a0x, ER1);  HzR = k_fma<R>(a1x, ER1x, HzR); HzR = k_fms<R>(a0yR, ER0, HzR); HzR = k_fms<R>(a1yR, EA0, HzR);
+                    };
+                    if (rc1) curl1(RealCoef{}); else curl1(CplxCoef{});
                 } else {   // timing experiment: touch every operand, no curl arithmetic
                     HxA = c_add(EA2, EB2); HyA = c_add(NA0, EA2x); HzA = c_add(EA1x, EB0);
                     HxB = c_add(EF2, NB1); HyB = c_add(NB0, EB2x); HzB = c_add(EB1x, EF0);
@@ -567,16 +644,21 @@ __global__ void __launch_bounds__(32 * (NWC + 1), 1) apply_rowpair_kernel(const 
                     HzBm.x = __shfl_up_sync(0xffffffffu, HzB.x, 1); HzBm.y = __shfl_up_sync(0xffffffffu, HzB.y, 1);
                     const double2 b0yA = ty[2 * NR], b1yA = ty[3 * NR], b0yB = ty[2 * NR + SGY], b1yB = ty[3 * NR + SGY];
                     const double2 b0z = tz[2 * LZP + n], b1z = tz[3 * LZP + n];
+                    const bool rc2 = rcxy && __all_sync(0xffffffffu, (b0z.y == 0.0) & (b1z.y == 0.0));
                     if (!early) load_md();
                     double2 yxA, yyA, yzA, yxB, yyB, yzB;
                     if (!RP_ABL || !(tp.dbg & 8)) {
-                        // y = C2 H :  yx = Dy Hz - Dz Hy,  yy = Dz Hx - Dx Hz,  yz = Dx Hy - Dy Hx
-                        yxA = c_mul(b0yA, HzA); yxA = c_fma(b1yA, HzR, yxA);  yxA = c_fms(b0z, HyA, yxA); yxA = c_fms(b1z, HpyA, yxA);
-                        yyA = c_mul(b0z, HxA);  yyA = c_fma(b1z, HpxA, yyA);  yyA = c_fms(b0x, HzA, yyA); yyA = c_fms(b1x, HzAm, yyA);
-                        yzA = c_mul(b0x, HyA);  yzA = c_fma(b1x, HyAm, yzA);  yzA = c_fms(b0yA, HxA, yzA); yzA = c_fms(b1yA, HxR, yzA);
-                        yxB = c_mul(b0yB, HzB); yxB = c_fma(b1yB, HzA, yxB);  yxB = c_fms(b0z, HyB, yxB); yxB = c_fms(b1z, HpyB, yxB);
-                        yyB = c_mul(b0z, HxB);  yyB = c_fma(b1z, HpxB, yyB);  yyB = c_fms(b0x, HzB, yyB); yyB = c_fms(b1x, HzBm, yyB);
-                        yzB = c_mul(b0x, HyB);  yzB = c_fma(b1x, HyBm, yzB);  yzB = c_fms(b0yB, HxB, yzB); yzB = c_fms(b1yB, HxA, yzB);
+                        auto curl2 = [&](auto kind) {
+                            constexpr bool R = decltype(kind)::value;
+                            // y = C2 H :  yx = Dy Hz - Dz Hy,  yy = Dz Hx - Dx Hz,  yz = Dx Hy - Dy Hx
+                            yxA = k_mul<R>(b0yA, HzA); yxA = k_fma<R>(b1yA, HzR, yxA);  yxA = k_fms<R>(b0z, HyA, yxA); yxA = k_fms<R>(b1z, HpyA, yxA);
+                            yyA = k_mul<R>(b0z, HxA);  yyA = k_fma<R>(b1z, HpxA, yyA);  yyA = k_fms<R>(b0x, HzA, yyA); yyA = k_fms<R>(b1x, HzAm, yyA);
+                            yzA = k_mul<R>(b0x, HyA);  yzA = k_fma<R>(b1x, HyAm, yzA);  yzA = k_fms<R>(b0yA, HxA, yzA); yzA = k_fms<R>(b1yA, HxR, yzA);
+                            yxB = k_mul<R>(b0yB, HzB); yxB = k_fma<R>(b1yB, HzA, yxB);  yxB = k_fms<R>(b0z, HyB, yxB); yxB = k_fms<R>(b1z, HpyB, yxB);
+                            yyB = k_mul<R>(b0z, HxB);  yyB = k_fma<R>(b1z, HpxB, yyB);  yyB = k_fms<R>(b0x, HzB, yyB); yyB = k_fms<R>(b1x, HzBm, yyB);
+                            yzB = k_mul<R>(b0x, HyB);  yzB = k_fma<R>(b1x, HyBm, yzB);  yzB = k_fms<R>(b0yB, HxB, yzB); yzB = k_fms<R>(b1yB, HxA, yzB);
+                        };
+                        if (rc2) curl2(RealCoef{}); else curl2(CplxCoef{});
                         if (p.has_mass) {
                             if (MDR && md_tile) {   // real coefficient: two fused multiply-adds per component
                                 yxA.x = fma(mdA0.x, EA0.x, yxA.x); yxA.y = fma(mdA0.x, EA0.y, yxA.y);
@@ -597,46 +679,10 @@ __global__ void __launch_bounds__(32 * (NWC + 1), 1) apply_rowpair_kernel(const 
                         yxA = c_add(yxA, b0z); yyA = c_add(yyA, b1z); yzA = c_add(yzA, b1yA); yxB = c_add(yxB, b0yB);
                     }
                     if (HAS_OFF) {
-                        // ---- off-diagonal part of the mass operator: y += Mout [P_off (Min x)] (model.jl:149-153) --------
-                        // corner values of plane k: G_x, G_y at this pair's cells (G_y also at the row above the pair, F -
-                        // recomputed like H of the row below), G_x of the forward x-neighbour by shuffle; G_z(k) was formed
-                        // one step earlier.  A warp whose entries are all zero on this plane skips the block (the
-                        // occupancy mask of the producer is per tile, this test is per row pair).
-                        bool fC = false;
-                        double o01A = 0.0, o02A = 0.0, o12A = 0.0, o01B = 0.0, o02B = 0.0, o12B = 0.0, o01F = 0.0, o12F = 0.0;
-                        if (off_cur) {
-                            const double *mo = reinterpret_cast<const double *>(ring + s_cur * STAGE + C::MO0) + mo_o;
-                            o01A = mo[0]; o02A = mo[1]; o12A = mo[2];
-                            o01B = mo[mdr_dB]; o02B = mo[mdr_dB + 1]; o12B = mo[mdr_dB + 2];
-                            o01F = mo[2 * mdr_dB]; o12F = mo[2 * mdr_dB + 2];
-                            fC = __any_sync(0xffffffffu, (o01A != 0.0) | (o02A != 0.0) | (o12A != 0.0) | (o01B != 0.0) |
-                                                             (o02B != 0.0) | (o12B != 0.0) | (o01F != 0.0) | (o12F != 0.0));
-                        }
-                        if (fC) {
-                            const double2 mi0x = txo[0], mi1x = txo[TX];
-                            const double2 mi0z = tz[4 * LZP + n], mi1z = tz[5 * LZP + n];
-                            const double2 AxA = c_fma(mi1x, es[-exf], c_mul(mi0x, EA0));
-                            const double2 AxB = c_fma(mi1x, es[dB - exf], c_mul(mi0x, EB0));
-                            const double2 AxF = c_fma(mi1x, es[2 * dB - exf], c_mul(mi0x, EF0));
-                            const double2 AyA = c_fma(ty[5 * NR], ER1, c_mul(ty[4 * NR], EA1));
-                            const double2 AyB = c_fma(ty[5 * NR + SGY], EA1, c_mul(ty[4 * NR + SGY], EB1));
-                            const double2 AzA = c_fma(mi1z, E2pA, c_mul(mi0z, EA2));
-                            const double2 AzB = c_fma(mi1z, E2pB, c_mul(mi0z, EB2));
-                            const double2 AzF = c_fma(mi1z, E2pF, c_mul(mi0z, EF2));
-                            const double2 GxA = r_fma(o02A, AzA, r_mul(o01A, AyA));
-                            const double2 GxB = r_fma(o02B, AzB, r_mul(o01B, AyB));
-                            const double2 GyA = r_fma(o12A, AzA, r_mul(o01A, AxA));
-                            const double2 GyB = r_fma(o12B, AzB, r_mul(o01B, AxB));
-                            const double2 GyF = r_fma(o12F, AzF, r_mul(o01F, AxF));
-                            double2 GxAp, GxBp;   // G_x of the forward x-neighbour: the next lane
-                            GxAp.x = __shfl_down_sync(0xffffffffu, GxA.x, 1); GxAp.y = __shfl_down_sync(0xffffffffu, GxA.y, 1);
-                            GxBp.x = __shfl_down_sync(0xffffffffu, GxB.x, 1); GxBp.y = __shfl_down_sync(0xffffffffu, GxB.y, 1);
-                            const double2 mo0x = txo[2 * TX], mo1x = txo[3 * TX];
-                            yxA = c_fma(mo0x, GxA, yxA); yxA = c_fma(mo1x, GxAp, yxA);
-                            yxB = c_fma(mo0x, GxB, yxB); yxB = c_fma(mo1x, GxBp, yxB);
-                            yyA = c_fma(ty[6 * NR], GyA, yyA); yyA = c_fma(ty[7 * NR], GyB, yyA);
-                            yyB = c_fma(ty[6 * NR + SGY], GyB, yyB); yyB = c_fma(ty[7 * NR + SGY], GyF, yyB);
-                        }
+                        // ---- off-diagonal part of the mass operator: y += Mout [P_off (Min x)] (model.jl:149-153); the x / y
+                        // halves were formed at the top of the step (off_xy), the z half needs G_z of both planes
+                        if (HAS_Q) off_xy();   // (stage still held: no early release with a q array)
+                        yxA = c_add(yxA, cxA); yxB = c_add(yxB, cxB); yyA = c_add(yyA, cyA); yyB = c_add(yyB, cyB);
                         next_gz();
                         if (fCz || fN) {
                             const double2 mo0z = tz[6 * LZP + n], mo1z = tz[7 * LZP + n];

@@ -107,6 +107,11 @@ inline T emu_shfl_idx(T v, int src) {
 template <class T> inline T __shfl_up_sync(unsigned, T v, unsigned d) { const int l = emu::lane_id(); return emu_shfl_idx(v, l - (int)d < 0 ? l : l - (int)d); }
 template <class T> inline T __shfl_down_sync(unsigned, T v, unsigned d) { const int l = emu::lane_id(); return emu_shfl_idx(v, l + (int)d > 31 ? l : l + (int)d); }
 template <class T> inline T __shfl_sync(unsigned, T v, int src) { return emu_shfl_idx(v, src & 31); }
+inline int __all_sync(unsigned m, int pred) {
+    int v = pred ? 1 : 0;
+    for (int o = 16; o > 0; o >>= 1) v &= __shfl_xor_sync(m, v, o);
+    return v;
+}
 inline int __any_sync(unsigned m, int pred) {   // warp vote as a butterfly of exchanges
     int v = pred ? 1 : 0;
     for (int o = 16; o > 0; o >>= 1) v |= __shfl_xor_sync(m, v, o);

@@ -775,7 +775,9 @@ def test_objects_on_reduced_models():
     kernel on the extruded scene; analytic harmonic / arithmetic means across a planar interface, and the oracle's
     smoothing of the scene the K-dimensional one stands for (1e-10, as for the 3-D pipeline)"""
     from problems import reduced_objects_check
-    assert reduced_objects_check(_fb()) == 22@pytest.mark.gpu
+    assert reduced_objects_check(_fb()) == 22
+
+
 @pytest.mark.parametrize("N", [(3, 3, 2), (33, 17, 9), (70, 45, 6), (31, 40, 5), (61, 29, 7)])
 def test_apply_fused_full_tensor_rowpair(N):
     """Fused full-tensor shape of the row-pair kernel (symmetric tensor, real entries: diagonal and off-diagonal rows travel
@@ -794,7 +796,6 @@ def test_apply_fused_full_tensor_rowpair(N):
         assert err < TOL and errT < TOL, (N, isbloch, err, errT)
 
 
-@pytest.mark.gpu
 def test_fused_full_tensor_partly_empty_blocks_arrangements_and_solve():
     """Fused row-pair shape on a deeper grid (several z-chunks and items per CTA) whose off-diagonal entries vanish on
     whole planes / half-spaces (tile occupancy mask, per-row-pair skip), on the default, mirrored and a mixed
