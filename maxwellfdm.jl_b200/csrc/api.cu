@@ -525,8 +525,15 @@ int apply_device(Ctx *c, const double2 *x, double2 *y, bool transpose) {
     // before the NCCL kernel gets one.  The gated spin is bounded (traps after ~4 s) so this shows as an error,
     // not a hang.  See DESIGN.md section 10 for the fix that is planned (copy-engine / peer-memory transfer).
     static const bool inkernel_wait = getenv("FDFD_INKERNEL_HALO_WAIT") != nullptr;
-    if (c->d.nranks > 1 && use_tiled && inkernel_wait && c->d.order_cmpfirst && !dbg_skip_halo && stream_write_u32_available() &&
-        tiled_plan_nchunk(p) >= 4) {
+    // Second generation of the same idea, on the persistent row-pair kernel (FDFD_HALO_OVERLAP=0 turns it off): its grid
+    // leaves a few SMs to the NCCL kernels (FDFD_HALO_SM_RESERVE, default 4), so the exchange can always make progress
+    // next to the apply, the boundary z-chunks of every tile column are walked last, and only the producer warp of a CTA
+    // waits - for the flag word, right before its first load of a neighbour's plane.
+    static const bool halo_overlap = [] { const char *e = getenv("FDFD_HALO_OVERLAP"); return !e || atoi(e) != 0; }();
+    const bool overlap_rp = halo_overlap && c->d.nranks > 1 && use_tiled && !dbg_skip_halo &&
+                            stream_write_u32_available() && rowpair_halo_overlap_ok(p);
+    if (overlap_rp || (c->d.nranks > 1 && use_tiled && inkernel_wait && c->d.order_cmpfirst && !dbg_skip_halo &&
+                       stream_write_u32_available() && tiled_plan_nchunk(p) >= 4)) {
         if (!c->halo_flag) {
             FDFD_CUDA(c, cudaMalloc((void **)&c->halo_flag, sizeof(uint32_t)));
             FDFD_CUDA(c, cudaMemset(c->halo_flag, 0, sizeof(uint32_t)));

@@ -56,6 +56,7 @@ struct RowPairParams {
     // and y (store boxes of 30 cells x 2 rows); tmap = 0: 1-D bulk row copies instead
     TmaMap mx, mlo, mhi, mmd, mmo, my;
     int32_t tmap;
+    int32_t halo_last;   // z-slabs, in-kernel halo wait (a.halo_flag): the two z-chunks that touch a neighbour's plane run last
     int32_t dbg;   // timing experiments only (FDFD_RP_DEBUG bit mask; results are wrong): 1 no material loads,
                    // 2 no y stores, 4 no x loads, 8 no arithmetic; 16, 32 (results stay right): no early stage release, no table fill ahead of the item; 64: no real-coefficient fast path
 };
@@ -110,6 +111,13 @@ template <bool RC> __device__ __forceinline__ double2 k_fms(double2 a, double2 z
 struct RealCoef { static constexpr bool value = true; };
 struct CplxCoef { static constexpr bool value = false; };
 
+// order of the z-chunks of a tile column: bottom to top, or - when the halo planes are still in flight at launch - the
+// interior chunks first and the two that read a neighbour's plane last
+__device__ __forceinline__ int rp_chunk(int c, int nch, int halo_last) {
+    if (!halo_last || nch < 3) return c;
+    return c < nch - 2 ? c + 1 : (c == nch - 2 ? 0 : nch - 1);
+}
+
 // chunk c of nch over [kb, ke): sizes differ by at most one plane
 __host__ __device__ __forceinline__ int chunk_begin(int kb, int ke, int nch, int c) {
     return kb + (int)(((int64_t)(ke - kb) * c) / nch);
@@ -125,6 +133,7 @@ template <bool CMPFIRST, bool HAS_Q, bool DOT, int ARR, bool MDR, bool HAS_OFF, 
 __global__ void __launch_bounds__(32 * (NWC + 1), 1) apply_rowpair_kernel(const __grid_constant__ RowPairParams tp) {
     static_assert(!MDR || CMPFIRST, "real material rows exist for the cmp-first layout only");
     static_assert(!HAS_OFF || MDR, "the fused full-tensor variant is built for real, symmetric material");
+    static_assert(!HAS_OFF || RPCfg<NWC, NST, MDR, HAS_OFF>::LZP <= 32, "one occupancy flag per lane");
     using C = RPCfg<NWC, NST, MDR, HAS_OFF>;
     constexpr int NR = C::NR, NM = C::NM, NT = C::NT, STAGE = C::STAGE, MD0 = C::MD0, TX = RP_TX, LZP = C::LZP;
     constexpr int NTAB = C::NTAB;
@@ -179,11 +188,12 @@ __global__ void __launch_bounds__(32 * (NWC + 1), 1) apply_rowpair_kernel(const 
         // item, when that item is long enough for the same argument (its load NST has been waited for) - then the global
         // loads below overlap the wait for a free stage instead of delaying the item's first planes.
         bool tabs_ready = false;
+        bool halo_ok = false;
         auto fill_tables = [&](int it, int itcount) {
             int b = it;
             const int tile_x = b % tp.ntx; b /= tp.ntx;
             const int tile_y = b % tp.nty;
-            const int chunk = b / tp.nty;
+            const int chunk = rp_chunk(b / tp.nty, tp.nchunk, tp.halo_last);
             const int ox = tile_x * (TX - 2) - 1, oy = tile_y * (2 * NWC) - 1;
             const int kc0 = chunk_begin(tp.kl_begin, tp.kl_end, tp.nchunk, chunk);
             const int kc1 = chunk_begin(tp.kl_begin, tp.kl_end, tp.nchunk, chunk + 1);
@@ -214,7 +224,7 @@ __global__ void __launch_bounds__(32 * (NWC + 1), 1) apply_rowpair_kernel(const 
             int b = item;
             const int tile_x = b % tp.ntx; b /= tp.ntx;
             const int tile_y = b % tp.nty;
-            const int chunk = b / tp.nty;
+            const int chunk = rp_chunk(b / tp.nty, tp.nchunk, tp.halo_last);
             const int ox = tile_x * (TX - 2) - 1, oy = tile_y * (2 * NWC) - 1;
             const int kc0 = chunk_begin(tp.kl_begin, tp.kl_end, tp.nchunk, chunk);
             const int kc1 = chunk_begin(tp.kl_begin, tp.kl_end, tp.nchunk, chunk + 1);
@@ -265,6 +275,10 @@ __global__ void __launch_bounds__(32 * (NWC + 1), 1) apply_rowpair_kernel(const 
             }
             const bool has_wrap = (lwrap || rwrap || ywrap_rows) && !(tp.dbg & 4);
             const uint32_t g_item = g;
+            // full tensor: occupancy flags of this tile's planes, lane n <-> march step n (at most 32 planes per item)
+            int mask_n = 1;
+            if (HAS_OFF && p.offmask != nullptr && lane < nplanes)
+                mask_n = __ldg(&p.offmask[(int64_t)(kof(lane) + 1) * (tp.ntx * tp.nty) + tile_y * tp.ntx + tile_x]);
             // bytes of the 1-D wrap pieces of one plane: in-domain rows contribute their wrapped cells, wrapped rows
             // their whole run
             uint32_t wrap_bytes = 0;
@@ -303,6 +317,21 @@ __global__ void __launch_bounds__(32 * (NWC + 1), 1) apply_rowpair_kernel(const 
                 if (n == 0 && !tabs_ready) fill_tables(item, itc);
                 if (n == 0) tabs_ready = false;
                 const int kk = kof(n);
+                if (p.halo_flag != nullptr && !halo_ok && (kk < 0 || kk >= p.nzl)) {
+                    // z-slabs, exchange overlapped with the interior chunks: the neighbours' planes are final once the flag
+                    // word (written by a stream memory operation behind the exchange) has reached this apply's epoch.  The
+                    // spin is bounded: a transfer that never arrives traps instead of hanging the GPU.
+                    if (lane == 0) {
+                        uint32_t spins = 0;
+                        while ((int32_t)(ld_acquire_sys(p.halo_flag) - p.halo_expect) < 0) {
+                            __nanosleep(100);
+                            if (++spins > 40000000u) __trap();
+                        }
+                    }
+                    __syncwarp();
+                    fence_proxy_async_all();   // the planes were written through the generic proxy, the TMA unit reads them
+                    halo_ok = true;
+                }
                 const bool want_m = md_tile && n >= 1 && n + 1 < nplanes;    // output planes only
                 const bool skip_x = (tp.dbg & 4) != 0;
                 double2 *dst = ring + s * STAGE;
@@ -312,8 +341,8 @@ __global__ void __launch_bounds__(32 * (NWC + 1), 1) apply_rowpair_kernel(const 
                     if (HAS_OFF) {
                         // off-diagonal rows of plane kk feed G(kk): needed from the first output plane on, skipped when the
                         // (tile, plane) block holds none (occupancy mask of the 30 x 14 tiles, built by tiled_build_offmask)
-                        want_o = n >= 1 && !(tp.dbg & 1) &&
-                                 (p.offmask == nullptr || __ldg(&p.offmask[(int64_t)(kk + 1) * (tp.ntx * tp.nty) + tile_y * tp.ntx + tile_x]) != 0);
+                        // (the item's mask bytes were fetched once, one plane per lane - no global load per plane here)
+                        want_o = n >= 1 && !(tp.dbg & 1) && (__shfl_sync(0xffffffffu, mask_n, n & 31) != 0);
                         if (lane == 0) oflag[s] = want_o ? 1 : 0;
                     }
                     const uint32_t box_bytes = (skip_x ? 0u : (uint32_t)(NR * TX * 48)) + (want_m ? (uint32_t)(NM * C::MDROW * 16) : 0u) +
@@ -412,7 +441,7 @@ __global__ void __launch_bounds__(32 * (NWC + 1), 1) apply_rowpair_kernel(const 
             int b = item;
             const int tile_x = b % tp.ntx; b /= tp.ntx;
             const int tile_y = b % tp.nty;
-            const int chunk = b / tp.nty;
+            const int chunk = rp_chunk(b / tp.nty, tp.nchunk, tp.halo_last);
             const int ox = tile_x * (TX - 2) - 1, oy = tile_y * (2 * NWC) - 1;
             const int kc0 = chunk_begin(tp.kl_begin, tp.kl_end, tp.nchunk, chunk);
             const int kc1 = chunk_begin(tp.kl_begin, tp.kl_end, tp.nchunk, chunk + 1);
@@ -880,6 +909,16 @@ static bool rp_fused_ok(const ApplyParams &p) {
 }
 
 // shape for this launch: real material rows when the handle built them (tensor-map path, cmp-first layout)
+// SMs left to the NCCL exchange while an apply with the in-kernel halo wait runs (its CTAs own a whole SM each)
+static int rp_sm_reserve() {
+    static const int v = [] { const char *e = getenv("FDFD_HALO_SM_RESERVE"); const int r = e ? atoi(e) : 4; return r < 1 ? 1 : r; }();
+    return v;
+}
+static int rp_grid_cap(const ApplyParams &p) {
+    const int nsm = sm_count();
+    return p.halo_flag != nullptr ? std::max(1, nsm - rp_sm_reserve()) : nsm;
+}
+
 static int rp_pick_shape(const ApplyParams &p, int kl_begin, int kl_end, int *nchunk) {
     static const int want_nch = env_int("FDFD_RP_NCHUNK");
     const int n = kl_end - kl_begin;
@@ -891,7 +930,7 @@ static int rp_pick_shape(const ApplyParams &p, int kl_begin, int kl_end, int *nc
     }
     const int nwc = RP_SHAPES[i].nwc, nst = RP_SHAPES[i].nst, lzmax = rp_lzmax(i);
     const int ntx = (p.Nx + RP_TX - 3) / (RP_TX - 2), nty = (p.Ny + 2 * nwc - 1) / (2 * nwc);
-    int nch = rp_pick_nchunk(ntx * nty, n, sm_count(), nst, lzmax, nullptr);
+    int nch = rp_pick_nchunk(ntx * nty, n, rp_grid_cap(p), nst, lzmax, nullptr);
     if (want_nch >= 1 && n / want_nch >= std::max(1, nst - 2) && (n + want_nch - 1) / want_nch <= lzmax) nch = want_nch;
     if (nch < 1) return -1;
     *nchunk = nch;
@@ -903,9 +942,30 @@ bool rowpair_fused_available(const ApplyParams &p) { return rp_fused_ok(p); }
 bool rowpair_supported(const ApplyParams &p, int kl_begin, int kl_end) {
     for (int w = 0; w < 3; ++w)
         if (p.s1[w] != 1 && p.s1[w] != -1) return false;
-    if (p.halo_flag != nullptr) return false;               // in-kernel halo wait: first-generation kernel only
     int nch = 0;
-    return kl_end > kl_begin && rp_pick_shape(p, kl_begin, kl_end, &nch) >= 0;
+    if (!(kl_end > kl_begin && rp_pick_shape(p, kl_begin, kl_end, &nch) >= 0)) return false;
+    // in-kernel halo wait: whole slab in one launch, tensor-map path, and interior chunks to hide the exchange behind
+    if (p.halo_flag != nullptr && !(kl_begin == 0 && kl_end == p.nzl && nch >= 3 && p.cmpfirst && want_tmap())) return false;
+    return true;
+}
+
+// would an apply of the whole slab with the exchange overlapped (in-kernel halo wait) run on the row-pair kernel?
+bool rowpair_halo_overlap_ok(const ApplyParams &p) {
+    static const bool other_kernel = [] {   // A/B overrides that send the operator to the first-generation kernel
+        const char *g = getenv("FDFD_K1_GEN"), *t = getenv("FDFD_TY");
+        return (g && atoi(g) == 1) || (t && atoi(t) != 0);
+    }();
+    if (other_kernel) return false;
+    ApplyParams q = p;
+    uint32_t dummy = 0;
+    q.halo_flag = &dummy;                      // plan as the gated launch would
+    if (q.has_off && q.has_mass && !rp_fused_ok(q)) {
+        if (!(p.offmask && p.offmask_ty == 8)) return false;   // dense, not fusable: first-generation kernel
+        q.has_off = 0;                                         // sparse plan: the diagonal part runs on this kernel
+    }
+    for (int w = 0; w < 3; ++w)
+        if (q.s1[w] != 1 && q.s1[w] != -1) return false;
+    return rowpair_supported(q, 0, q.nzl);
 }
 
 // Tensor maps are cached by (address, geometry): a Krylov solve applies the operator to a handful of workspace
@@ -958,7 +1018,8 @@ static cudaError_t launch_rp_shape(RowPairParams &tp, const ApplyParams &p, cuda
     tp.ntx = (p.Nx + RP_TX - 3) / (RP_TX - 2);
     tp.nty = (p.Ny + 2 * NWC - 1) / (2 * NWC);
     tp.nitems = tp.ntx * tp.nty * tp.nchunk;
-    int grid = std::min(tp.nitems, sm_count());
+    int grid = std::min(tp.nitems, rp_grid_cap(p));
+    tp.halo_last = p.halo_flag != nullptr ? 1 : 0;
     static const int want_grid = env_int("FDFD_RP_GRID");   // tuning / test override of the persistent grid size
     if (want_grid >= 1) grid = std::min(tp.nitems, want_grid);
     const bool dot = p.dot_mode == 2;
@@ -989,7 +1050,7 @@ cudaError_t launch_apply_rowpair(const ApplyParams &p, int kl_begin, int kl_end,
     tp.kl_end = kl_end;
     static const int dbg = env_int("FDFD_RP_DEBUG");
     tp.dbg = dbg;
-    const int shape = (p.s1[0] * p.s1[0] == 1 && p.s1[1] * p.s1[1] == 1 && p.s1[2] * p.s1[2] == 1 && !p.halo_flag)
+    const int shape = (p.s1[0] * p.s1[0] == 1 && p.s1[1] * p.s1[1] == 1 && p.s1[2] * p.s1[2] == 1)
                           ? rp_pick_shape(p, kl_begin, kl_end, &tp.nchunk) : -1;
     static const bool verbose = getenv("FDFD_VERBOSE") != nullptr;
     if (verbose) fprintf(stderr, "fdfd: row-pair kernel shape %d (%s), %d z-chunk(s), planes [%d, %d)\n", shape,

@@ -238,6 +238,7 @@ bool tiled_supported(const ApplyParams &p);
 // apply_rowpair.cu: second-generation K1 (persistent, warp-specialised; diagonal mass parameter) over local planes
 // [kl_begin, kl_end); cudaErrorNotSupported when the configuration is outside its range
 bool rowpair_supported(const ApplyParams &p, int kl_begin, int kl_end);
+bool rowpair_halo_overlap_ok(const ApplyParams &p);   // whole-slab apply with the in-kernel halo wait on this kernel?
 bool rowpair_fused_available(const ApplyParams &p);   // fused full-tensor shape: arrays, layout and mask fit
 int64_t mdr_row_pitch(int Nx);   // doubles per row of ApplyParams::md_aos_r
 cudaError_t launch_apply_rowpair(const ApplyParams &p, int kl_begin, int kl_end, cudaStream_t s);

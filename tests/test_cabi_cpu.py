@@ -171,6 +171,34 @@ def test_export_pattern_variants():
     assert np.array_equal(rv, A.julia_pattern()[1]) and np.all(nz != 0) and (np.diff(cp) < 13).any()
 
 
+@pytest.mark.parametrize("cfg", ["C1 40^3", "C2 reduced", "C3 reduced"])
+def test_export_pattern_at_config_shapes(cfg):
+    """the bit-exact index pattern on the BASELINE configurations themselves - C1 at its full 40^3 size
+    (192 000 unknowns, 10-cell PML), C2 (full 3x3 eps, PML) and C3 (Bloch x / y with a complex phase, PML in z) at
+    reduced sizes - built by the same workload generators the bench uses (model.jl:236-237 is what the export mirrors)."""
+    import sys
+    sys.path.insert(0, ROOT)
+    import workloads
+    from oracle import operators as op
+    w = {"C1 40^3": lambda: workloads.c1_vacuum_box((40, 40, 40)),
+         "C2 reduced": lambda: workloads.c2_waveguide((36, 40, 30), npml=6),
+         "C3 reduced": lambda: workloads.c3_phc_slab((32, 32, 24))}[cfg]()
+    sei = tuple(1 / a for a in w["sdl_e"])
+    smi = tuple(1 / a for a in w["sdl_m"])
+    mu = np.zeros(w["eps"].shape, complex)
+    for v in range(3):
+        mu[..., v, v] = 1
+    Ce, Cm = op.create_curls(sei, smi, (EE, EE, EE), w["isbloch"], w["e_mikL"])
+    Pe, Pm = op.create_paramops(w["eps"], mu, w["sdl_e"], w["sdl_m"], sei, smi, (EE, EE, EE), w["isbloch"], w["e_mikL"])
+    A = op.create_A(EE, w["omega"], Pe, Pm, Ce, Cm)
+    cp_ref, rv_ref = A.julia_pattern()
+    H = workloads.make_operator(w, device=-2)
+    cp, rv, nz = H.export_pattern()
+    H.close()
+    assert np.array_equal(cp, cp_ref) and np.array_equal(rv, rv_ref), cfg
+    assert np.abs(nz - A.nzval).max() <= 1e-13 * np.abs(A.nzval).max()
+
+
 def test_export_capacity_and_errors():
     L = _lib()
     p = Problem((3, 3, 3))
