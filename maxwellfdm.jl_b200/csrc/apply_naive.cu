@@ -213,9 +213,61 @@ __global__ void __launch_bounds__(256, SKIPZ ? 2 : 0) offdiag_march_kernel(const
                                                              int kl_end) {
     const int4 item = items[blockIdx.x];
     const int ks = max(item.y, kl_begin), ke = min(item.z, kl_end);
-    if (ks >= ke) return;
     __shared__ double2 gs[2][2][256];   // [plane parity][G_x, G_y][thread]
     const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+    // Fused Krylov dots: this pass changes (y,x) and (y,y) by exact deltas.  They are added to the sums the main kernel has
+    // published in a FIXED order: every CTA stores its deltas in its own slot at the far end of the partial buffer, the last
+    // CTA (atomic ticket) adds the slots in index order - bit-reproducible from run to run, unlike per-CTA atomic adds.
+    __shared__ double red[8][3];
+    __shared__ bool last_cta;
+    auto publish_deltas = [&](double d_re, double d_im, double d_tt) {
+        double v3[3] = {d_re, d_im, d_tt};
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v3[q] += __shfl_xor_sync(0xffffffffu, v3[q], o);
+            if ((tid & 31) == 0) red[tid >> 5][q] = v3[q];
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double *pp = p.dot_partial + ((size_t)p.dot_cap - 1 - blockIdx.x) * 4;
+            for (int q = 0; q < 3; ++q) {
+                double a = 0.0;
+                for (int w = 0; w < 8; ++w) a += red[w][q];
+                pp[q] = a;
+            }
+            __threadfence();
+            last_cta = atomicAdd(p.dot_ticket, 1u) == gridDim.x - 1;
+        }
+        __syncthreads();
+        if (!last_cta) return;
+        __threadfence();
+        double s3[3] = {0.0, 0.0, 0.0};
+        for (int b = tid; b < (int)gridDim.x; b += 256) {
+            const double *pp = p.dot_partial + ((size_t)p.dot_cap - 1 - b) * 4;
+            s3[0] += __ldcg(pp); s3[1] += __ldcg(pp + 1); s3[2] += __ldcg(pp + 2);
+        }
+        __syncthreads();   // red[] is reused
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s3[q] += __shfl_xor_sync(0xffffffffu, s3[q], o);
+            if ((tid & 31) == 0) red[tid >> 5][q] = s3[q];
+        }
+        __syncthreads();
+        if (tid == 0) {
+            for (int q = 0; q < 3; ++q) {
+                double a = 0.0;
+                for (int w = 0; w < 8; ++w) a += red[w][q];
+                p.dot_out[q] += a;       // single writer: the main kernel's sums were published before this launch began
+            }
+            *p.dot_ticket = 0;
+        }
+    };
+    if (ks >= ke) {
+        if (p.dot_mode == 2) publish_deltas(0.0, 0.0, 0.0);
+        return;
+    }
     const int gi = (item.x % ntx) * 30 - 1 + tx, gj = (item.x / ntx) * 6 - 1 + ty;
     const int ci = ((gi % p.Nx) + p.Nx) % p.Nx, cj = ((gj % p.Ny) + p.Ny) % p.Ny;
     const int SGX = p.s1[0], SGY = p.s1[1], SG = p.s1[2];
@@ -299,9 +351,9 @@ __global__ void __launch_bounds__(256, SKIPZ ? 2 : 0) offdiag_march_kernel(const
                     if (SKIPZ && !have_s) { sx = g.E(0, ci, cj, k); sy = g.E(1, ci, cj, k); sz = g.E(2, ci, cj, k); }
                     d_re += tx_.x * sx.x + tx_.y * sx.y + ty_.x * sy.x + ty_.y * sy.y + tz_.x * sz.x + tz_.y * sz.y;
                     d_im += tx_.x * sx.y - tx_.y * sx.x + ty_.x * sy.y - ty_.y * sy.x + tz_.x * sz.y - tz_.y * sz.x;
-                    d_tt += (n0.x * n0.x + n0.y * n0.y - o0.x * o0.x - o0.y * o0.y) +
-                            (n1.x * n1.x + n1.y * n1.y - o1.x * o1.x - o1.y * o1.y) +
-                            (n2.x * n2.x + n2.y * n2.y - o2.x * o2.x - o2.y * o2.y);
+                    // |o + d|^2 - |o|^2 = 2 Re(conj(o) d) + |d|^2  (no cancellation when the correction is small)
+                    d_tt += 2.0 * (o0.x * tx_.x + o0.y * tx_.y + o1.x * ty_.x + o1.y * ty_.y + o2.x * tz_.x + o2.y * tz_.y) +
+                            (tx_.x * tx_.x + tx_.y * tx_.y + ty_.x * ty_.x + ty_.y * ty_.y + tz_.x * tz_.x + tz_.y * tz_.y);
                 }
             }
         }
@@ -310,22 +362,7 @@ __global__ void __launch_bounds__(256, SKIPZ ? 2 : 0) offdiag_march_kernel(const
         Gcz = Gnz;
         __syncthreads();
     }
-    if (p.dot_mode == 2) {   // add this CTA's deltas to the sums the main kernel's last CTA has already published
-        __shared__ double red[8][3];
-        double v3[3] = {d_re, d_im, d_tt};
-#pragma unroll
-        for (int q = 0; q < 3; ++q) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v3[q] += __shfl_xor_sync(0xffffffffu, v3[q], o);
-            if ((tid & 31) == 0) red[tid >> 5][q] = v3[q];
-        }
-        __syncthreads();
-        if (tid < 3) {
-            double a = 0.0;
-            for (int w = 0; w < 8; ++w) a += red[w][tid];
-            if (a != 0.0) atomicAdd(&p.dot_out[tid], a);
-        }
-    }
+    if (p.dot_mode == 2) publish_deltas(d_re, d_im, d_tt);
 }
 
 }  // namespace
@@ -340,6 +377,7 @@ cudaError_t launch_apply_naive(const ApplyParams &p, cudaStream_t s) {
 cudaError_t launch_offdiag_correction(const ApplyParams &p, const int4 *items, int count, int ntx, int kl_begin,
                                       int kl_end, cudaStream_t s) {
     if (count <= 0) return cudaSuccess;
+    if (p.dot_mode == 2 && (int64_t)count + 8192 > p.dot_cap) return cudaErrorInvalidConfiguration;   // delta slots
     static const bool skipz = getenv("FDFD_CORR_SKIP_ZERO") != nullptr;   // opt-in until it has been timed on hardware
     if (skipz) offdiag_march_kernel<true><<<count, 256, 0, s>>>(p, items, ntx, kl_begin, kl_end);
     else       offdiag_march_kernel<false><<<count, 256, 0, s>>>(p, items, ntx, kl_begin, kl_end);
