@@ -58,7 +58,7 @@ struct RowPairParams {
     int32_t tmap;
     int32_t halo_last;   // z-slabs, in-kernel halo wait (a.halo_flag): the two z-chunks that touch a neighbour's plane run last
     int32_t dbg;   // timing experiments only (FDFD_RP_DEBUG bit mask; results are wrong): 1 no material loads,
-                   // 2 no y stores, 4 no x loads, 8 no arithmetic; 16, 32 (results stay right): no early stage release, no table fill ahead of the item; 64: no real-coefficient fast path
+                   // 2 no y stores, 4 no x loads, 8 no arithmetic; 16, 32 (results stay right): no early stage release, no table fill ahead of the item; 64: no real-coefficient fast path; 128 (results wrong): fused shape skips the off-diagonal arithmetic
 };
 
 template <int NWC, int NST, bool MDR, bool HAS_OFF>
@@ -588,7 +588,7 @@ __global__ void __launch_bounds__(32 * (NWC + 1), 1) apply_rowpair_kernel(const 
                         cyB = c_fma(ty[7 * NR + SGY], GyF, c_mul(ty[6 * NR + SGY], GyB));
                     }
                 };
-                if (HAS_OFF && !HAS_Q && do_out) off_xy();
+                if (HAS_OFF && !HAS_Q && do_out && !(tp.dbg & 128)) off_xy();
                 // material of plane k: same ring stage as E(k)
                 double2 mdA0 = p.md_uniform, mdA1 = p.md_uniform, mdA2 = p.md_uniform;
                 double2 mdB0 = p.md_uniform, mdB1 = p.md_uniform, mdB2 = p.md_uniform;
@@ -649,7 +649,7 @@ __global__ void __launch_bounds__(32 * (NWC + 1), 1) apply_rowpair_kernel(const 
                 double2 GzAn = c_zero(), GzBn = c_zero();
                 bool fN = false;
                 auto next_gz = [&]() {
-                    if (!oflag[s_nxt]) return;
+                    if ((tp.dbg & 128) || !oflag[s_nxt]) return;
                     const double *mo = reinterpret_cast<const double *>(ring + s_nxt * STAGE + C::MO0) + mo_o;
                     const double o02A = mo[1], o12A = mo[2], o02B = mo[mdr_dB + 1], o12B = mo[mdr_dB + 2];
                     fN = __any_sync(0xffffffffu, (o02A != 0.0) | (o12A != 0.0) | (o02B != 0.0) | (o12B != 0.0));
@@ -865,7 +865,7 @@ cudaError_t launch_rp(const RowPairParams &tp, int grid, cudaStream_t s) {
 // stages of 46 KB; shape 1: real material rows (MDR), 5 stages of 35 KB; shape 2: the fused full tensor (real diagonal
 // and off-diagonal rows), 4 stages of 47 KB.
 struct RpShape { int nwc, nst; bool mdr, off; };
-constexpr RpShape RP_SHAPES[] = {{7, 4, false, false}, {7, 5, true, false}, {7, 4, true, true}};
+constexpr RpShape RP_SHAPES[] = {{7, 4, false, false}, {7, 5, true, false}, {7, 4, true, true}, {7, 4, true, false}};   // [3]: A/B timing only (FDFD_RP_NST4)
 constexpr int RP_NSHAPES = sizeof(RP_SHAPES) / sizeof(RP_SHAPES[0]);
 
 }  // namespace
@@ -923,7 +923,8 @@ static int rp_pick_shape(const ApplyParams &p, int kl_begin, int kl_end, int *nc
     static const int want_nch = env_int("FDFD_RP_NCHUNK");
     const int n = kl_end - kl_begin;
     const bool mdr = p.cmpfirst && p.has_mass && p.md[0] != nullptr && p.md_aos_r != nullptr && want_tmap();
-    int i = mdr ? 1 : 0;
+    static const bool nst4 = getenv("FDFD_RP_NST4") != nullptr;   // A/B timing: real-row shape with a 4-stage ring
+    int i = mdr ? (nst4 ? 3 : 1) : 0;
     if (p.has_off && p.has_mass) {
         if (!rp_fused_ok(p)) return -1;
         i = 2;
@@ -1060,6 +1061,7 @@ cudaError_t launch_apply_rowpair(const ApplyParams &p, int kl_begin, int kl_end,
         case 0: return launch_rp_shape<RP_SHAPES[0].nwc, RP_SHAPES[0].nst, RP_SHAPES[0].mdr, RP_SHAPES[0].off>(tp, p, s);
         case 1: return launch_rp_shape<RP_SHAPES[1].nwc, RP_SHAPES[1].nst, RP_SHAPES[1].mdr, RP_SHAPES[1].off>(tp, p, s);
         case 2: return launch_rp_shape<RP_SHAPES[2].nwc, RP_SHAPES[2].nst, RP_SHAPES[2].mdr, RP_SHAPES[2].off>(tp, p, s);
+        case 3: return launch_rp_shape<RP_SHAPES[3].nwc, RP_SHAPES[3].nst, RP_SHAPES[3].mdr, RP_SHAPES[3].off>(tp, p, s);
         default: return cudaErrorNotSupported;
     }
 }
