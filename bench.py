@@ -332,9 +332,14 @@ def single_call_block(N, per, ngpu, steps, kry_iters):
     import workloads
     import maxwellfdm_jl_b200 as fb
     t0 = time.perf_counter()
-    w = workloads.c2_waveguide(N, 0, N[2], period_z=per[2])
-    A = fb.MultiGpuOperator(w["N"], w["isbloch"], w["sdl_e"], w["sdl_m"], w["omega"], w["eps"], None, w["e_mikL"], ngpu=ngpu)
-    del w
+    # one period of the replicated-C2 cross-section, tiled along z in the memory layout the C ABI takes (the Julia
+    # column-major (Nx,Ny,Nz,3,3) array = C-order (3,3,Nz,Ny,Nx)): no 9 GB transposing copy at 8 GPUs
+    w1 = workloads.c2_waveguide(per, 0, per[2])
+    eps = np.tile(np.ascontiguousarray(w1["eps"].transpose(4, 3, 2, 1, 0)), (1, 1, ngpu, 1, 1))
+    del w1
+    w = workloads._common(N, 20.0, (False, False, False), ((10,) * 3, (10,) * 3))
+    A = fb.MultiGpuOperator(w["N"], w["isbloch"], w["sdl_e"], w["sdl_m"], w["omega"], eps, None, w["e_mikL"], ngpu=ngpu)
+    del w, eps
     n = A.n
     xh = torch.empty(n, dtype=torch.complex128).pin_memory()
     yh = torch.empty(n, dtype=torch.complex128).pin_memory()

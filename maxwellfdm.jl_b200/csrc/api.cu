@@ -525,11 +525,14 @@ int apply_device(Ctx *c, const double2 *x, double2 *y, bool transpose) {
     // before the NCCL kernel gets one.  The gated spin is bounded (traps after ~4 s) so this shows as an error,
     // not a hang.  See DESIGN.md section 10 for the fix that is planned (copy-engine / peer-memory transfer).
     static const bool inkernel_wait = getenv("FDFD_INKERNEL_HALO_WAIT") != nullptr;
-    // Second generation of the same idea, on the persistent row-pair kernel (FDFD_HALO_OVERLAP=0 turns it off): its grid
-    // leaves a few SMs to the NCCL kernels (FDFD_HALO_SM_RESERVE, default 4), so the exchange can always make progress
-    // next to the apply, the boundary z-chunks of every tile column are walked last, and only the producer warp of a CTA
-    // waits - for the flag word, right before its first load of a neighbour's plane.
-    static const bool halo_overlap = [] { const char *e = getenv("FDFD_HALO_OVERLAP"); return !e || atoi(e) != 0; }();
+    // Second generation of the same idea, on the persistent row-pair kernel (opt-in: FDFD_HALO_OVERLAP=1): its grid
+    // leaves a few SMs to the NCCL kernels (FDFD_HALO_SM_RESERVE, default 8), the boundary z-chunks of every tile column
+    // are walked last, and only the producer warp of a CTA waits - for the flag word, right before its first load of a
+    // neighbour's plane.  Measured on 2x B200 (gpurun_out/r02c16_*): correct with 8 SMs reserved, but the NCCL send/recv
+    // kernel does not make progress on 4 or 2 free SMs (the bounded spin trapped), and giving up 8 of 148 SMs costs the
+    // apply more (item quantisation: 735 items over 140 instead of 148 CTAs) than the ~22 us exchange it hides - so the
+    // default stays "exchange, then launch".  What it needs to pay off is an exchange that uses no SM at all (peer.cpp).
+    static const bool halo_overlap = [] { const char *e = getenv("FDFD_HALO_OVERLAP"); return e && atoi(e) != 0; }();
     const bool overlap_rp = halo_overlap && c->d.nranks > 1 && use_tiled && !dbg_skip_halo &&
                             stream_write_u32_available() && rowpair_halo_overlap_ok(p);
     if (overlap_rp || (c->d.nranks > 1 && use_tiled && inkernel_wait && c->d.order_cmpfirst && !dbg_skip_halo &&

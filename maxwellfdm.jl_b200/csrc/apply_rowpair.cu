@@ -911,7 +911,7 @@ static bool rp_fused_ok(const ApplyParams &p) {
 // shape for this launch: real material rows when the handle built them (tensor-map path, cmp-first layout)
 // SMs left to the NCCL exchange while an apply with the in-kernel halo wait runs (its CTAs own a whole SM each)
 static int rp_sm_reserve() {
-    static const int v = [] { const char *e = getenv("FDFD_HALO_SM_RESERVE"); const int r = e ? atoi(e) : 4; return r < 1 ? 1 : r; }();
+    static const int v = [] { const char *e = getenv("FDFD_HALO_SM_RESERVE"); const int r = e ? atoi(e) : 8; return r < 0 ? 0 : r; }();
     return v;
 }
 static int rp_grid_cap(const ApplyParams &p) {
