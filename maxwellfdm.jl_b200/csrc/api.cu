@@ -525,16 +525,19 @@ int apply_device(Ctx *c, const double2 *x, double2 *y, bool transpose) {
     // before the NCCL kernel gets one.  The gated spin is bounded (traps after ~4 s) so this shows as an error,
     // not a hang.  See DESIGN.md section 10 for the fix that is planned (copy-engine / peer-memory transfer).
     static const bool inkernel_wait = getenv("FDFD_INKERNEL_HALO_WAIT") != nullptr;
-    // Second generation of the same idea, on the persistent row-pair kernel (opt-in: FDFD_HALO_OVERLAP=1): its grid
-    // leaves a few SMs to the NCCL kernels (FDFD_HALO_SM_RESERVE, default 8), the boundary z-chunks of every tile column
-    // are walked last, and only the producer warp of a CTA waits - for the flag word, right before its first load of a
-    // neighbour's plane.  Measured on 2x B200 (gpurun_out/r02c16_*): correct with 8 SMs reserved, but the NCCL send/recv
-    // kernel does not make progress on 4 or 2 free SMs (the bounded spin trapped), and giving up 8 of 148 SMs costs the
-    // apply more (item quantisation: 735 items over 140 instead of 148 CTAs) than the ~22 us exchange it hides - so the
-    // default stays "exchange, then launch".  What it needs to pay off is an exchange that uses no SM at all (peer.cpp).
-    static const bool halo_overlap = [] { const char *e = getenv("FDFD_HALO_OVERLAP"); return e && atoi(e) != 0; }();
-    const bool overlap_rp = halo_overlap && c->d.nranks > 1 && use_tiled && !dbg_skip_halo &&
-                            stream_write_u32_available() && rowpair_halo_overlap_ok(p);
+    // Second generation of the same idea, on the persistent row-pair kernel: the boundary z-chunks of every tile column
+    // are walked last and only the producer warp of a CTA waits - for the flag word, right before its first load of a
+    // neighbour's plane.  ON by default when the planes travel by the copy-engine peer exchange (peer.cpp: the transfer
+    // needs no SM, the apply keeps all 148 CTAs); with NCCL as the data plane it is opt-in (FDFD_HALO_OVERLAP=1) and
+    // leaves FDFD_HALO_SM_RESERVE (8) SMs to the NCCL kernels.  Measured on 2x B200, C2 per GPU (gpurun_out/r02c16_*,
+    // r02c18_*): NCCL, exchange then launch 219 GDOF/s; peer exchange then launch 217; NCCL overlapped, 8 SMs reserved
+    // 189 (item quantisation: 735 items over 140 CTAs; with 4 or 2 free SMs the NCCL kernel made no progress and the
+    // bounded spin trapped); peer exchange overlapped 245 = 2 x the single-GPU rate.  FDFD_HALO_OVERLAP=0 turns it off.
+    static const int halo_overlap_env = [] { const char *e = getenv("FDFD_HALO_OVERLAP"); return e ? (atoi(e) != 0 ? 1 : 0) : -1; }();
+    const bool halo_overlap = halo_overlap_env >= 0 ? halo_overlap_env == 1 : c->peer.ready;
+    p.halo_sm_free = c->peer.ready ? 1 : 0;
+    const bool overlap_rp = halo_overlap && c->d.nranks > 1 && use_tiled && !dbg_skip_halo && stream_write_u32_available() &&
+                            rowpair_halo_overlap_ok(p);
     if (overlap_rp || (c->d.nranks > 1 && use_tiled && inkernel_wait && c->d.order_cmpfirst && !dbg_skip_halo &&
                        stream_write_u32_available() && tiled_plan_nchunk(p) >= 4)) {
         if (!c->halo_flag) {

@@ -909,14 +909,15 @@ static bool rp_fused_ok(const ApplyParams &p) {
 }
 
 // shape for this launch: real material rows when the handle built them (tensor-map path, cmp-first layout)
-// SMs left to the NCCL exchange while an apply with the in-kernel halo wait runs (its CTAs own a whole SM each)
-static int rp_sm_reserve() {
-    static const int v = [] { const char *e = getenv("FDFD_HALO_SM_RESERVE"); const int r = e ? atoi(e) : 8; return r < 0 ? 0 : r; }();
-    return v;
+// SMs left to the exchange while an apply with the in-kernel halo wait runs (its CTAs own a whole SM each): none when the
+// planes travel by copy engine (peer exchange), 8 for the NCCL send / recv kernels (they did not progress on 4)
+static int rp_sm_reserve(const ApplyParams &p) {
+    static const int v = [] { const char *e = getenv("FDFD_HALO_SM_RESERVE"); return e ? std::max(0, atoi(e)) : -1; }();
+    return v >= 0 ? v : (p.halo_sm_free ? 0 : 8);
 }
 static int rp_grid_cap(const ApplyParams &p) {
     const int nsm = sm_count();
-    return p.halo_flag != nullptr ? std::max(1, nsm - rp_sm_reserve()) : nsm;
+    return p.halo_flag != nullptr ? std::max(1, nsm - rp_sm_reserve(p)) : nsm;
 }
 
 static int rp_pick_shape(const ApplyParams &p, int kl_begin, int kl_end, int *nchunk) {

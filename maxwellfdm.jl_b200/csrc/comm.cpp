@@ -6,6 +6,7 @@
 // a process which already loaded torch's bundled libnccl.so.2 shares that copy.
 #include <dlfcn.h>
 #include <cstdlib>
+#include <cstdio>
 #include <cstring>
 
 #include "fdfd_internal.h"
@@ -104,7 +105,37 @@ int comm_init(Ctx *c, const char id[128]) {
     FDFD_NCCL(c, api->CommInitRank(&comm, c->d.nranks, uid, c->d.rank));
     c->comm = comm;
     c->dirty = true;  // material ghost planes must be exchanged
-    if (getenv("FDFD_PEER_HALO") || getenv("FDFD_PEER_DIRECT")) return peer_halo_init(c);   // experimental, see PeerHalo
+    // Halo data plane: the copy-engine peer exchange of peer.cpp (no SM-resident collective) when every rank can map its
+    // neighbours' buffers with CUDA IPC - one process per GPU on one node - else NCCL send / recv.  FDFD_PEER_HALO=0 forces
+    // NCCL, FDFD_PEER_HALO=1 (or FDFD_PEER_DIRECT) makes a failure of the peer set-up an error instead of a fallback.
+    const char *pe = getenv("FDFD_PEER_HALO");
+    const bool required = (pe && atoi(pe) != 0) || getenv("FDFD_PEER_DIRECT") != nullptr;
+    if (pe && atoi(pe) == 0 && !required) return FDFD_OK;
+    if (c->d.nranks == 1 || !c->d.order_cmpfirst) return FDFD_OK;
+    const int rp = peer_halo_init(c);
+    // every rank must take the same data plane: agree on the outcome
+    double *flag = nullptr;
+    const double bad_local = (rp != FDFD_OK || !c->peer.ready) ? 1.0 : 0.0;
+    cudaGetLastError();   // a failed cudaIpcOpenMemHandle (same-process handles, no peer access) is not sticky
+    FDFD_CUDA(c, cudaMalloc((void **)&flag, sizeof(double)));
+    FDFD_CUDA(c, cudaMemcpy(flag, &bad_local, sizeof(double), cudaMemcpyHostToDevice));
+    int ra = allreduce_sum(c, flag, 1, c->stream);
+    double bad = 1.0;
+    if (ra == FDFD_OK) {
+        FDFD_CUDA(c, cudaMemcpyAsync(&bad, flag, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        FDFD_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    cudaFree(flag);
+    if (ra != FDFD_OK) return ra;
+    if (bad > 0.0) {
+        const std::string why = c->err;
+        peer_halo_destroy(c);
+        if (required) return set_err(c, FDFD_ECUDA, "peer halo exchange requested but not available on every rank: " + why);
+        c->err.clear();
+        if (getenv("FDFD_VERBOSE")) fprintf(stderr, "fdfd rank %d: peer halo exchange unavailable (%s) - NCCL send/recv\n", c->d.rank, why.c_str());
+    } else if (getenv("FDFD_VERBOSE")) {
+        fprintf(stderr, "fdfd rank %d: halo planes by copy-engine peer exchange\n", c->d.rank);
+    }
     return FDFD_OK;
 }
 

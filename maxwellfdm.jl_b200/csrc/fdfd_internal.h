@@ -69,6 +69,7 @@ struct ApplyParams {
     // halo_expect (written by a stream memory operation behind the NCCL exchange); null = halos already in place
     const uint32_t *halo_flag;
     uint32_t halo_expect;
+    int32_t halo_sm_free;          // the exchange behind halo_flag uses no SM (copy-engine peer exchange): keep the whole grid
     const unsigned char *offmask;  // occupancy mask of the off-diagonal material (tiled kernel), or null
     int32_t offmask_ty;            // tile height the mask was built for
     const int4 *corr_list;         // sparse off-diagonals: work items (tile, ks, ke) of the correction pass
