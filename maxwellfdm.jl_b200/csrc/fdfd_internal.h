@@ -90,8 +90,7 @@ struct ApplyParams {
 // ---------------------------------------------------------------------------------------------
 struct NcclApi;  // comm.cpp
 
-// Halo exchange over NVLink peer memory without any SM-resident collective (EXPERIMENTAL, FDFD_PEER_HALO, written in
-// round 1 and NOT yet run on hardware): neighbours' halo buffers and flag words are mapped with CUDA IPC; a plane
+// Halo exchange over NVLink peer memory without any SM-resident collective (default data plane since round 2, peer.cpp): neighbours' halo buffers and flag words are mapped with CUDA IPC; a plane
 // travels by a copy-engine cudaMemcpyAsync into the neighbour's buffer, ordering is by stream memory operations.
 struct PeerHalo {
     bool ready = false;
@@ -101,7 +100,7 @@ struct PeerHalo {
     uint32_t *up_flags = nullptr, *dn_flags = nullptr;
     void *mapped[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // bases to cudaIpcCloseMemHandle
     uint32_t epoch = 0;
-    // Peer-direct reads (EXPERIMENTAL, FDFD_PEER_DIRECT, not yet run on hardware): inside BiCGSTAB the neighbours'
+    // Peer-direct reads (opt-in, FDFD_PEER_DIRECT; ran correctly on 2x B200 in round 2, no gain): inside BiCGSTAB the neighbours'
     // Krylov workspaces are mapped too and the apply kernel reads their boundary planes IN PLACE over NVLink (its
     // bulk copies of the first / last z-chunk address peer memory) - no halo copy at all, only a flag per direction.
     bool direct = false;                 // workspaces mapped
