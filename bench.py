@@ -298,6 +298,11 @@ def measure_config(name, w, local, rank, world, steps, kry_iters, gen, extra=Non
         batch.append(max_over_ranks(ms / per, world))
     ms_med, ms_min = statistics.median(batch), min(batch)
     bpd, off, sym = bytes_per_dof(A, w)
+    if world > 1:      # slabs differ (a sphere / a pillar layer touches some of them only): report the mean over the ranks
+        import torch.distributed as dist
+        t = torch.tensor([bpd, off], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t)
+        bpd, off = float(t[0]) / world, float(t[1]) / world
     peak, _ = peaks()
     n_tot = 3 * w["N"][0] * w["N"][1] * w["N"][2]
     out = {"config": name, "grid": list(w["N"]), "dof": n_tot, "n_gpus": world, "applies_timed": nb * per,
@@ -503,8 +508,12 @@ def main():
             halo = {"bytes_sent_per_rank": nbm, "us": us, "gbs_per_direction": nbm / 2 / (us * 1e-6) / 1e9 if us > 0 else None,
                     "nvlink_frac": (nbm / 2 / (us * 1e-6) / 1e9 / NVLINK_PEER_GBS) if us > 0 else None,
                     "nvlink_peak_gbs": NVLINK_PEER_GBS, "share_of_apply": us / (ms_step * 1e3),
-                    "note": "grouped ncclSend/ncclRecv of the two boundary planes, timed alone (serialised in front of "
-                            "a plain apply; started early and hidden behind the vector kernels inside BiCGSTAB)"}
+                    "data_plane": A.halo_data_plane,
+                    "note": "the exchange of the two boundary planes timed alone. data_plane 'peer': copy-engine copies into "
+                            "IPC-mapped neighbour buffers ordered by stream memory operations, hidden behind the interior "
+                            "z-chunks of the apply kernel (in-kernel halo wait); 'nccl': grouped ncclSend/ncclRecv, serialised "
+                            "in front of a plain apply. Inside BiCGSTAB either one starts early and hides behind the vector "
+                            "kernels"}
         except Exception as e:  # noqa: BLE001
             halo = {"error": f"{type(e).__name__}: {e}"}
 

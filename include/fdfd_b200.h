@@ -201,6 +201,12 @@ int fdfd_bench_solve(fdfd_handle h, int method, const fdfd_c128 *b_dev, fdfd_c12
 /* z-slabs: the halo exchange of one apply by itself (the two boundary planes of x_dev to / from the z-neighbours),
  * `iters` times back to back; *bytes_sent = bytes this rank sends per exchange (0 on a single slab). */
 int fdfd_bench_halo(fdfd_handle h, const fdfd_c128 *x_dev, int warmup, int iters, double *ms_total, uint64_t *bytes_sent);
+/* Tell a slab handle that it is one of several driven by host threads of ONE process (fdfd_multi_* does this itself): the
+ * Krylov loops of such handles take turns issuing an iteration's launches instead of contending for the CUDA driver. */
+int fdfd_set_shared_process(fdfd_handle h, int on);
+/* Which data plane moves this handle's halo planes: 0 = none (single slab), 1 = grouped ncclSend / ncclRecv, 2 = copy-engine
+ * peer exchange into CUDA-IPC-mapped neighbour buffers (the default when every rank can set it up). */
+int fdfd_halo_data_plane(fdfd_handle h, int *kind);
 /* Fraction of the (x-y tile, z-plane) blocks of this slab that hold a non-zero off-diagonal eps entry.  The
  * tiled kernel skips the six off-diagonal streams on empty blocks (subpixel smoothing puts off-diagonal
  * entries only at material interfaces), so the bytes an apply must move are (48 + 32*frac) B/DOF. */

@@ -81,6 +81,8 @@ SYMBOLS = {
     "fdfd_bench_solve": (C.c_int, [P, C.c_int, P, P, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "fdfd_mass_bytes_per_dof": (C.c_int, [P, C.POINTER(C.c_double)]),
     "fdfd_bench_halo": (C.c_int, [P, P, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
+    "fdfd_halo_data_plane": (C.c_int, [P, C.POINTER(C.c_int)]),
+    "fdfd_set_shared_process": (C.c_int, [P, C.c_int]),
     "fdfd_offdiag_fraction": (C.c_int, [P, C.POINTER(C.c_double)]),
     "fdfd_offdiag_bytes_per_dof": (C.c_int, [P, C.POINTER(C.c_double)]),
     "fdfd_offdiag_symmetric": (C.c_int, [P, C.POINTER(C.c_int)]),

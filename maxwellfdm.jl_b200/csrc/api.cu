@@ -3,7 +3,9 @@
 #include <cstdio>
 #include <algorithm>
 #include <cstdlib>
+#include <condition_variable>
 #include <cstring>
+#include <mutex>
 #include <new>
 
 #include "cplx.cuh"
@@ -12,6 +14,26 @@
 namespace fdfd {
 
 static thread_local std::string g_create_err;
+
+namespace {
+std::mutex g_turn_mu;
+std::condition_variable g_turn_cv;
+uint64_t g_turn_next = 0, g_turn_serving = 0;
+}  // namespace
+BurstTurn::BurstTurn(const Ctx *c) : held(c && c->shared_process) {
+    if (!held) return;
+    std::unique_lock<std::mutex> lk(g_turn_mu);
+    const uint64_t mine = g_turn_next++;
+    g_turn_cv.wait(lk, [&] { return g_turn_serving == mine; });
+}
+BurstTurn::~BurstTurn() {
+    if (!held) return;
+    {
+        std::lock_guard<std::mutex> lk(g_turn_mu);
+        ++g_turn_serving;
+    }
+    g_turn_cv.notify_all();
+}
 
 int set_err(Ctx *c, int code, const std::string &msg) {
     if (c) c->err = msg;
@@ -1413,6 +1435,20 @@ int fdfd_bench_halo(fdfd_handle h, const fdfd_c128 *x, int warmup, int iters, do
     cudaEventDestroy(e1);
     if (ms_total) *ms_total = ms;
     if (bytes_sent) *bytes_sent = (uint64_t)((up >= 0) + (dn >= 0)) * (uint64_t)c->plane * sizeof(double2);
+    return FDFD_OK;
+}
+
+int fdfd_set_shared_process(fdfd_handle h, int on) {
+    if (!h) return set_err(nullptr, FDFD_EINVAL, "null handle");
+    static_cast<Ctx *>(h)->shared_process = on != 0;
+    return FDFD_OK;
+}
+
+int fdfd_halo_data_plane(fdfd_handle h, int *kind) {
+    if (!h) return set_err(nullptr, FDFD_EINVAL, "null handle");
+    Ctx *c = static_cast<Ctx *>(h);
+    if (!kind) return set_err(c, FDFD_EINVAL, "null argument");
+    *kind = (c->d.nranks <= 1 || !c->comm) ? 0 : (c->peer.ready ? 2 : 1);
     return FDFD_OK;
 }
 

@@ -169,6 +169,7 @@ struct Ctx {
     cudaEvent_t ev_x = nullptr, ev_halo = nullptr, ev_bnd = nullptr;
     const double2 *halo_for = nullptr;  // vector whose halo planes are (being) exchanged ahead of its apply
     bool comm_pending = false;          // an NCCL op may still be running on stream_comm (ordered by ev_halo)
+    bool shared_process = false;        // one of several slab handles driven by host threads of ONE process (fdfd_multi_*)
     bool halo_preloaded = false;        // halo_lo / halo_hi were filled by the caller (host halos): apply_device skips the exchange
     double off_frac = 1.0;             // fraction of (tile, plane) blocks holding off-diagonal material
     bool off_sym = false;              // off-diagonal mass entries pointwise symmetric: three arrays, three aliases
@@ -202,6 +203,17 @@ struct Ctx {
 };
 
 int set_err(Ctx *c, int code, const std::string &msg);
+
+// Slab handles of ONE process (fdfd_multi_*): every host thread issues ~35 driver calls per Krylov iteration, and N threads
+// doing so at once contend for the driver's locks (measured on 8 GPUs: 50 iterations/s against 450 with one process per
+// GPU).  The threads therefore take turns: a whole iteration's launches are issued under a process-wide FIFO ticket lock -
+// first come, first served, so no slab runs more than one iteration ahead of one that is waiting - and nothing that blocks
+// on the device is ever called while holding it.
+struct BurstTurn {
+    explicit BurstTurn(const Ctx *c);
+    ~BurstTurn();
+    bool held;
+};
 
 #define FDFD_CUDA(c, call)                                                                         \
     do {                                                                                            \

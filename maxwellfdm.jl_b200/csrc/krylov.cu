@@ -301,7 +301,11 @@ static int bicgstab(Ctx *c, const double2 *b, double2 *x, double rtol, int maxit
             c->launches += graph_launches;
             it += 2;
         } else {
-            int ri = enqueue_iter(it);
+            int ri;
+            {
+                BurstTurn turn(c);   // slabs of one process take turns issuing an iteration (fdfd_internal.h)
+                ri = enqueue_iter(it);
+            }
             if (ri != FDFD_OK) { cleanup2(); cleanup(); return ri; }
             ++it;
         }

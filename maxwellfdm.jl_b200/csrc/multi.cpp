@@ -201,6 +201,7 @@ int fdfd_multi_create(fdfd_multi *out, const fdfd_desc *desc, int32_t ngpu, cons
         d.nranks = m->n;
         const int v = fdfd_create(&m->h[r], &d);
         if (v != FDFD_OK) { const char *e = fdfd_last_error(nullptr); cerr_[r] = e ? e : ""; }
+        else if (m->n > 1) fdfd_set_shared_process(m->h[r], 1);   // the slab threads take turns in the Krylov loops
         return v;
     });
     if (rc != FDFD_OK) {

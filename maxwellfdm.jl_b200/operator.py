@@ -305,6 +305,13 @@ class FdfdOperator:
         return tot.value, int(nb.value)
 
     @property
+    def halo_data_plane(self):
+        """'none' (single slab), 'nccl' (grouped ncclSend / ncclRecv) or 'peer' (copy-engine exchange into IPC-mapped buffers)"""
+        k = C.c_int()
+        L.check(L.lib().fdfd_halo_data_plane(self._h, C.byref(k)), self._h)
+        return ("none", "nccl", "peer")[k.value]
+
+    @property
     def offdiag_fraction(self):
         f = C.c_double()
         L.check(L.lib().fdfd_offdiag_fraction(self._h, C.byref(f)), self._h)
