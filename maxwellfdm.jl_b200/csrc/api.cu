@@ -674,16 +674,19 @@ static int stage_buffers(Ctx *c) {
 
 // fdfd_apply with HOST buffers, pipelined over z sub-slabs: H2D of sub-slab s+1, the kernel of sub-slab s and
 // D2H of sub-slab s-1 run concurrently on three streams (PCIe is full duplex), so the call costs about one
-// direction's transfer time instead of H2D + kernel + D2H.  Needs a single slab, the cmp-first layout (a
-// z sub-slab is contiguous) and the tiled kernel; other configurations use the plain staged path.
+// direction's transfer time instead of H2D + kernel + D2H.  Needs the cmp-first layout (a z sub-slab is contiguous)
+// and the tiled kernel; other configurations use the plain staged path.  On z-slabs the halo planes come either from
+// the caller's host vector (fdfd_apply_host_halos) or from a device exchange of the two boundary planes, which are
+// copied up first.
 static bool can_pipeline(Ctx *c, bool host_halos) {
-    return (c->d.nranks == 1 || host_halos) && c->d.order_cmpfirst && c->d.kernel != FDFD_KERNEL_NAIVE && (c->k1 - c->k0) >= 16;
+    return (c->d.nranks == 1 || host_halos || c->comm != nullptr) && c->d.order_cmpfirst && c->d.kernel != FDFD_KERNEL_NAIVE &&
+           (c->k1 - c->k0) >= 16;
 }
 
 // xlo_h / xhi_h (z-slabs only): host pointers to the plane below / above this slab (null: symmetry boundary, the halo
 // buffer keeps its zeros) - the caller holds the whole vector in host memory, so no exchange between GPUs is needed
-static int apply_host_pipelined(Ctx *c, const double2 *xh, double2 *yh, bool transpose, const double2 *xlo_h = nullptr,
-                                const double2 *xhi_h = nullptr) {
+static int apply_host_pipelined(Ctx *c, const double2 *xh, double2 *yh, bool transpose, bool host_halos = false,
+                                const double2 *xlo_h = nullptr, const double2 *xhi_h = nullptr) {
     const int64_t nzl = c->k1 - c->k0, pl = c->plane;
     static const int s_env = [] { const char *e = getenv("FDFD_PIPE_SLABS"); return e ? atoi(e) : 0; }();
     const int S = (int)std::max<int64_t>(1, std::min<int64_t>(s_env > 0 ? s_env : 16, nzl / 2));
@@ -705,10 +708,26 @@ static int apply_host_pipelined(Ctx *c, const double2 *xh, double2 *yh, bool tra
         // the wrap plane (x_lo = plane nzl-1) first, then the sub-slabs in order
         FDFD_CUDA(c, cudaMemcpyAsync(c->stage_x + (nzl - 1) * pl, xh + (nzl - 1) * pl, (size_t)pl * sizeof(double2),
                                      cudaMemcpyHostToDevice, c->stream_copy));
-    } else {
+    } else if (host_halos) {
         // z-slab: the neighbours' boundary planes come straight from the caller's host vector
         if (xlo_h) FDFD_CUDA(c, cudaMemcpyAsync(c->halo_lo, xlo_h, (size_t)pl * sizeof(double2), cudaMemcpyHostToDevice, c->stream_copy));
         if (xhi_h) FDFD_CUDA(c, cudaMemcpyAsync(c->halo_hi, xhi_h, (size_t)pl * sizeof(double2), cudaMemcpyHostToDevice, c->stream_copy));
+    } else {
+        // z-slab, one process per GPU: this rank's two boundary planes go up first and are exchanged on the device
+        // (peer exchange or NCCL) while the sub-slabs follow; the kernels wait for the exchange below
+        FDFD_CUDA(c, cudaMemcpyAsync(c->stage_x, xh, (size_t)pl * sizeof(double2), cudaMemcpyHostToDevice, c->stream_copy));
+        FDFD_CUDA(c, cudaMemcpyAsync(c->stage_x + (nzl - 1) * pl, xh + (nzl - 1) * pl, (size_t)pl * sizeof(double2),
+                                     cudaMemcpyHostToDevice, c->stream_copy));
+        FDFD_CUDA(c, cudaEventRecord(c->ev_x, c->stream_copy));
+        FDFD_CUDA(c, cudaStreamWaitEvent(c->stream_comm, c->ev_x, 0));
+        // the exchange releases the halo buffers of the previous epoch to the neighbours: it must also be ordered behind
+        // whatever this handle's compute stream still holds (nothing, after a blocking API call - but cheap to state)
+        FDFD_CUDA(c, cudaEventRecord(c->ev_bnd, c->stream));
+        FDFD_CUDA(c, cudaStreamWaitEvent(c->stream_comm, c->ev_bnd, 0));
+        int rh = halo_exchange(c, c->stage_x, c->halo_lo, c->halo_hi, c->stream_comm);
+        if (rh != FDFD_OK) return rh;
+        FDFD_CUDA(c, cudaEventRecord(c->ev_halo, c->stream_comm));
+        FDFD_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_halo, 0));
     }
     FDFD_CUDA(c, cudaEventRecord(c->ev_h2d[S], c->stream_copy));
     for (int s = 0; s < S; ++s) {
@@ -738,8 +757,14 @@ static int apply_host(Ctx *c, const fdfd_c128 *x, fdfd_c128 *y, bool transpose) 
     int r;
     if ((r = stage_buffers(c)) != FDFD_OK) return r;
     if ((r = ensure_ready(c)) != FDFD_OK) return r;
-    if (can_pipeline(c, false))
+    if (can_pipeline(c, false)) {
+        if (c->d.nranks > 1) {   // order after anything a Krylov prefetch left on the communication stream
+            if (c->comm_pending) { FDFD_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_halo, 0)); FDFD_CUDA(c, cudaStreamSynchronize(c->stream)); }
+            c->comm_pending = false;
+            c->halo_for = nullptr;
+        }
         return apply_host_pipelined(c, reinterpret_cast<const double2 *>(x), reinterpret_cast<double2 *>(y), transpose);
+    }
     const size_t bytes = (size_t)c->nloc * sizeof(double2);
     FDFD_CUDA(c, cudaMemcpyAsync(c->stage_x, x, bytes, cudaMemcpyHostToDevice, c->stream));
     if ((r = apply_device(c, c->stage_x, c->stage_y, transpose)) != FDFD_OK) return r;
@@ -761,7 +786,7 @@ static int apply_host_halos(Ctx *c, const fdfd_c128 *x, const fdfd_c128 *xlo, co
     }
     c->halo_for = nullptr;
     if (can_pipeline(c, true))
-        return apply_host_pipelined(c, reinterpret_cast<const double2 *>(x), reinterpret_cast<double2 *>(y), transpose,
+        return apply_host_pipelined(c, reinterpret_cast<const double2 *>(x), reinterpret_cast<double2 *>(y), transpose, true,
                                     reinterpret_cast<const double2 *>(xlo), reinterpret_cast<const double2 *>(xhi));
     const size_t bytes = (size_t)c->nloc * sizeof(double2), pb = (size_t)c->plane * sizeof(double2);
     FDFD_CUDA(c, cudaMemcpyAsync(c->stage_x, x, bytes, cudaMemcpyHostToDevice, c->stream));
