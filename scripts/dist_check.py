@@ -96,6 +96,30 @@ def main():
             fails.append(("apply", cs, kern, e1, e2))
         A.close()
 
+    # deep slabs (>= 16 planes per rank, several z-chunks per tile column): the host-buffer apply runs the sub-slab pipeline
+    # (boundary planes up first, exchanged on the device), the device apply overlaps the exchange with the interior z-chunks
+    # (in-kernel halo wait) when the peer exchange is the data plane; back-to-back applies advance the halo epochs
+    for isbloch, kw in (((True, False, True), dict(full_eps=True)),
+                        ((False, True, False), dict(full_eps=True, real_mass=True, sym_real_off=True)),
+                        ((True, True, True), dict(full_eps=False, real_mass=True))):
+        p = Problem((40, 31, 18 * world + 1), isbloch, **kw)
+        x = p.random_x()
+        y_ref = p.oracle_matfree()(x)
+        A, k0, k1 = slab_operator(p)
+        xs = slab_of(p, x, k0, k1)
+        xd = torch.from_numpy(xs).cuda()
+        for rep in range(3):
+            yd = A @ xd
+        e1 = rel(gather(p, yd.cpu().numpy(), k0, k1), y_ref)
+        for rep in range(2):
+            yh = A @ xs
+        e2 = rel(gather(p, yh, k0, k1), y_ref)
+        e3 = rel(gather(p, (A @ xd).cpu().numpy(), k0, k1), y_ref)     # device path again after host applies
+        if not (e1 < 1e-12 and e2 < 1e-12 and e3 < 1e-12):
+            fails.append(("deep slabs", isbloch, kw, A.halo_data_plane, e1, e2, e3))
+        A.close()
+    cases = cases + ["deep"] * 3
+
     # Krylov across slabs (allreduced dots): vacuum-like PML box with a point-like right-hand side
     from oracle.grid import Grid, create_stretched_dls
     n, nz = 16, max(16, 4 * world)
