@@ -450,8 +450,10 @@ def main():
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N > 1")
     torch.cuda.set_device(local)
+    cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        cpu_group = dist.new_group(backend="gloo")     # host-side rendezvous that keeps the GPUs idle (single-call block)
     gen = torch.Generator(device="cuda").manual_seed(20261017 + rank)
     peak, peak_src = peaks()
 
@@ -604,10 +606,13 @@ def main():
     # library cuts the z-slabs (one host thread per device) - while the other ranks wait at the barrier below.
     single_call = None
     if not args.n and not args.no_single_call:
+        # the other ranks must leave their GPUs IDLE while rank 0 drives them: an NCCL barrier would park a spinning kernel
+        # of another process on every GPU (measured: 319 instead of 660 it/s at 2 GPUs), so they wait on a CPU (gloo) barrier
         barrier(world)
         if rank == 0:
             single_call = guarded(lambda: single_call_block(N, per, world, e2e_steps, args.krylov_iters))
-        barrier(world)
+        if world > 1:
+            dist.barrier(group=cpu_group)
 
     if rank == 0:
         achieved = bpd * (n_tot / world) / (ms_step * 1e-3) / 1e9      # per GPU

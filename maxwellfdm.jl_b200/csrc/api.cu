@@ -21,6 +21,8 @@ std::condition_variable g_turn_cv;
 uint64_t g_turn_next = 0, g_turn_serving = 0;
 }  // namespace
 BurstTurn::BurstTurn(const Ctx *c) : held(c && c->shared_process) {
+    static const bool off = getenv("FDFD_NO_TURNS") != nullptr;   // A/B timing: let the slab threads contend
+    if (off) held = false;
     if (!held) return;
     std::unique_lock<std::mutex> lk(g_turn_mu);
     const uint64_t mine = g_turn_next++;
