@@ -61,10 +61,10 @@ struct RowPairParams {
                    // 2 no y stores, 4 no x loads, 8 no arithmetic; 16, 32 (results stay right): no early stage release, no table fill ahead of the item; 64: no real-coefficient fast path; 128 (results wrong): fused shape skips the off-diagonal arithmetic
 };
 
-template <int NWC, int NST, bool MDR, bool HAS_OFF>
+template <int NWC, int NST, bool MDR, bool HAS_OFF, int RPW = 2>
 struct RPCfg {
-    static constexpr int NR = 2 * NWC + 2;            // E rows per ring stage
-    static constexpr int NM = 2 * NWC;                // diagonal-material rows per ring stage (output rows only)
+    static constexpr int NR = RPW * NWC + 2;          // E rows per ring stage (RPW = tile rows per compute warp)
+    static constexpr int NM = RPW * NWC;              // diagonal-material rows per ring stage (output rows only)
     static constexpr int NO = HAS_OFF ? NM + 1 : 0;   // off-diagonal-material rows (output rows + the row the last G_y needs)
     static constexpr int NT = 32 * (NWC + 1);
     static constexpr int MD0 = NR * RP_TX * 3;        // offset of the material rows inside a stage
@@ -75,7 +75,7 @@ struct RPCfg {
     static constexpr int MO0 = (MD0 + NM * MDROW + 7) / 8 * 8;   // offset of the off-diagonal rows (tensor-map boxes land on 128-byte boundaries)
     static constexpr int STAGE = (MO0 + NO * MDROW + 7) / 8 * 8;             // double2 per ring stage (128-byte multiple)
     static constexpr int FPAD = 8;                    // slack below stage 0 / above the last stage (halo-lane over-reads)
-    static constexpr int YW = 2 * RP_TX * 3;          // per-warp y staging (two rows)
+    static constexpr int YW = RPW * RP_TX * 3;        // per-warp y staging (RPW rows)
     // per-item tables: a0,a1,b0,b1 (+ mi0,mi1,mo0,mo1 for the full tensor) for y (NR rows) and z (planes); the
     // full-tensor variant also keeps the x tables of the two averages here (the curl's x tables live in registers)
     static constexpr int NTAB = HAS_OFF ? 8 : 4;
@@ -129,12 +129,18 @@ __host__ __device__ __forceinline__ int chunk_begin(int kb, int ke, int nch, int
 // HAS_OFF: the fused full 3x3 tensor (symmetric, real entries): the three off-diagonal entries of every corner travel
 // through the ring as a third group of rows; G = P_off (M_in x) is formed one plane ahead, its z component in registers,
 // and planes whose (tile, plane) block holds no off-diagonal material are skipped (occupancy mask, as in apply_tiled.cu).
-template <bool CMPFIRST, bool HAS_Q, bool DOT, int ARR, bool MDR, bool HAS_OFF, int NWC, int NST>
+// RPW = 1 (A/B experiment, FDFD_RP_RPW1): ONE tile row per compute warp (one cell per thread): fewer registers per thread
+// and more warps per scheduler, but the H values of the row below are still recomputed (2 of 6 components, +33 % flops), the
+// row above is read from the ring instead of registers, and every per-step cost is paid per row - measured slower than the
+// row-pair form (RP_SHAPES below).
+template <bool CMPFIRST, bool HAS_Q, bool DOT, int ARR, bool MDR, bool HAS_OFF, int NWC, int NST, int RPW = 2>
 __global__ void __launch_bounds__(32 * (NWC + 1), 1) apply_rowpair_kernel(const __grid_constant__ RowPairParams tp) {
+    static_assert(RPW == 2 || (RPW == 1 && !HAS_OFF), "one row per warp: diagonal mass parameter only");
+    constexpr bool PAIR = RPW == 2;
     static_assert(!MDR || CMPFIRST, "real material rows exist for the cmp-first layout only");
     static_assert(!HAS_OFF || MDR, "the fused full-tensor variant is built for real, symmetric material");
-    static_assert(!HAS_OFF || RPCfg<NWC, NST, MDR, HAS_OFF>::LZP <= 32, "one occupancy flag per lane");
-    using C = RPCfg<NWC, NST, MDR, HAS_OFF>;
+    static_assert(!HAS_OFF || RPCfg<NWC, NST, MDR, HAS_OFF, RPW>::LZP <= 32, "one occupancy flag per lane");
+    using C = RPCfg<NWC, NST, MDR, HAS_OFF, RPW>;
     constexpr int NR = C::NR, NM = C::NM, NT = C::NT, STAGE = C::STAGE, MD0 = C::MD0, TX = RP_TX, LZP = C::LZP;
     constexpr int NTAB = C::NTAB;
     const ApplyParams &p = tp.a;
@@ -173,7 +179,7 @@ __global__ void __launch_bounds__(32 * (NWC + 1), 1) apply_rowpair_kernel(const 
     constexpr int EX = CMPFIRST ? 3 : 1;              //         x-neighbour stride
     constexpr int ER = CMPFIRST ? 3 * TX : TX;        //         row stride
     constexpr int MC = CMPFIRST ? 1 : NM * TX;        // material rows: component stride (row / x strides as for E)
-    constexpr int YC = CMPFIRST ? 1 : 2 * TX;         // y staging: component stride (two rows per warp)
+    constexpr int YC = CMPFIRST ? 1 : RPW * TX;       // y staging: component stride (RPW rows per warp)
     constexpr int YR = CMPFIRST ? 3 * TX : TX;
 
     uint32_t g = 0;   // running index of plane loads of this CTA (ring stage g % NST, phase (g / NST) & 1)
@@ -194,7 +200,7 @@ __global__ void __launch_bounds__(32 * (NWC + 1), 1) apply_rowpair_kernel(const 
             const int tile_x = b % tp.ntx; b /= tp.ntx;
             const int tile_y = b % tp.nty;
             const int chunk = rp_chunk(b / tp.nty, tp.nchunk, tp.halo_last);
-            const int ox = tile_x * (TX - 2) - 1, oy = tile_y * (2 * NWC) - 1;
+            const int ox = tile_x * (TX - 2) - 1, oy = tile_y * C::NM - 1;
             const int kc0 = chunk_begin(tp.kl_begin, tp.kl_end, tp.nchunk, chunk);
             const int kc1 = chunk_begin(tp.kl_begin, tp.kl_end, tp.nchunk, chunk + 1);
             const int nplanes = kc1 - kc0 + 2;
@@ -225,7 +231,7 @@ __global__ void __launch_bounds__(32 * (NWC + 1), 1) apply_rowpair_kernel(const 
             const int tile_x = b % tp.ntx; b /= tp.ntx;
             const int tile_y = b % tp.nty;
             const int chunk = rp_chunk(b / tp.nty, tp.nchunk, tp.halo_last);
-            const int ox = tile_x * (TX - 2) - 1, oy = tile_y * (2 * NWC) - 1;
+            const int ox = tile_x * (TX - 2) - 1, oy = tile_y * C::NM - 1;
             const int kc0 = chunk_begin(tp.kl_begin, tp.kl_end, tp.nchunk, chunk);
             const int kc1 = chunk_begin(tp.kl_begin, tp.kl_end, tp.nchunk, chunk + 1);
             const int nplanes = kc1 - kc0 + 2;   // planes kc0-1 .. kc1
@@ -415,7 +421,7 @@ __global__ void __launch_bounds__(32 * (NWC + 1), 1) apply_rowpair_kernel(const 
         // =============================== compute warps ======================================================
         // logical (along the first curl's direction) -> physical tile coordinates
         const int ptx = SGX > 0 ? lane : TX - 1 - lane;
-        const int rA = SGY > 0 ? 2 * wid + 1 : NR - 2 - 2 * wid;      // physical tile row of cell A; B = A + s1y
+        const int rA = SGY > 0 ? RPW * wid + 1 : NR - 2 - RPW * wid;  // physical tile row of cell A; B = A + s1y (pairs)
         const int rB = rA + SGY;
         const int eA = rA * ER + ptx * EX;                // E element of cell A, component 0, inside a stage
         const int dB = SGY * ER;                          // A -> B; R (row below the pair) = A - dB, F = A + 2 dB
@@ -424,14 +430,14 @@ __global__ void __launch_bounds__(32 * (NWC + 1), 1) apply_rowpair_kernel(const 
         const int mdr_dB = SGY * C::MDCELLS * 3;          // real material rows (doubles): cell A -> cell B
         // y staging: row slot 0 <-> the physically lower row of the pair
         double2 *yw = ybase + wid * C::YW;
-        const int ysA = SGY > 0 ? 0 : 1;
+        const int ysA = (PAIR && SGY < 0) ? 1 : 0;
         const bool tmap = CMPFIRST && tp.tmap != 0;
         // tensor-map stores take a dense box: 30 output cells per row (no halo columns in the staging rows)
         const int yA = tmap ? (ysA * (TX - 2) + ptx - 1) * 3 : ysA * YR + ptx * EX;
         const int yB = tmap ? ((1 - ysA) * (TX - 2) + ptx - 1) * 3 : (1 - ysA) * YR + ptx * EX;
-        const int rlo = SGY > 0 ? rA : rB;                // physical tile row of staging slot 0
+        const int rlo = (PAIR && SGY < 0) ? rB : rA;      // physical tile row of staging slot 0
         const bool lane_out = (lane >= 1) && (lane <= TX - 2);
-        constexpr int NSTORE1D = CMPFIRST ? 2 : 6;
+        constexpr int NSTORE1D = CMPFIRST ? RPW : 3 * RPW;
         const int NSTORE = tmap ? 1 : NSTORE1D;           // lanes that issue this warp's bulk stores
 
         const bool no_early = (tp.dbg & 16) != 0;         // A/B timing: hold every stage to the end of its step
@@ -442,7 +448,7 @@ __global__ void __launch_bounds__(32 * (NWC + 1), 1) apply_rowpair_kernel(const 
             const int tile_x = b % tp.ntx; b /= tp.ntx;
             const int tile_y = b % tp.nty;
             const int chunk = rp_chunk(b / tp.nty, tp.nchunk, tp.halo_last);
-            const int ox = tile_x * (TX - 2) - 1, oy = tile_y * (2 * NWC) - 1;
+            const int ox = tile_x * (TX - 2) - 1, oy = tile_y * C::NM - 1;
             const int kc0 = chunk_begin(tp.kl_begin, tp.kl_end, tp.nchunk, chunk);
             const int kc1 = chunk_begin(tp.kl_begin, tp.kl_end, tp.nchunk, chunk + 1);
             const int nplanes = kc1 - kc0 + 2;
@@ -451,7 +457,7 @@ __global__ void __launch_bounds__(32 * (NWC + 1), 1) apply_rowpair_kernel(const 
             const int gi = ox + ptx, gjA = oy + rA, gjB = oy + rB;
             const int mdr_o = ((rA - 1) * C::MDCELLS + ptx + (ox & 1)) * 3;   // real material rows: cell A, component 0
             const int ci = ((gi % Nx) + Nx) % Nx;
-            const bool okA = lane_out && gi < Nx && gjA < Ny, okB = lane_out && gi < Nx && gjB < Ny;
+            const bool okA = lane_out && gi < Nx && gjA < Ny, okB = PAIR && lane_out && gi < Nx && gjB < Ny;
             // x tables in registers
             const double2 a0x = ldg2(&p.c.a0[0][ci]), a1x = ldg2(&p.c.a1[0][ci]);
             const double2 b0x = ldg2(&p.c.b0[0][ci]), b1x = ldg2(&p.c.b1[0][ci]);
@@ -466,7 +472,7 @@ __global__ void __launch_bounds__(32 * (NWC + 1), 1) apply_rowpair_kernel(const 
             const int64_t dN = SGZ * Nxy;
             // store geometry of this item (lanes < NSTORE): row / component handled by this lane, in-domain columns
             const int c0 = ox + 1, c1 = min(ox + TX - 1, Nx);
-            const int st_slot = CMPFIRST ? lane : lane % 2, st_c = CMPFIRST ? 0 : lane / 2;
+            const int st_slot = CMPFIRST ? lane : lane % RPW, st_c = CMPFIRST ? 0 : lane / RPW;
             const int st_j = oy + rlo + st_slot;
             const bool st_on = lane < NSTORE && (tmap || (st_j < Ny && c1 > c0)) && !(tp.dbg & 2);
             const int st_x = 6 * (ox + 1), st_y = oy + rlo;   // tensor-map store: box origin (clipped by the hardware)
@@ -511,25 +517,32 @@ __global__ void __launch_bounds__(32 * (NWC + 1), 1) apply_rowpair_kernel(const 
 #pragma unroll 2
             for (int n = 0; n + 1 < nplanes; ++n, ++g) {
                 const bool do_out = n >= 1;
-                double2 qA0, qA1, qA2, qB0, qB1, qB2, qR0, qR2;
+                double2 qA0, qA1, qA2, qB0 = c_zero(), qB1 = c_zero(), qB2 = c_zero(), qR0, qR2;
                 if (HAS_Q) {
                     const int64_t o = (int64_t)n * dN;
                     qA0 = ldg2(&p.q[0][qA + o]); qA1 = ldg2(&p.q[1][qA + o]); qA2 = ldg2(&p.q[2][qA + o]);
-                    qB0 = ldg2(&p.q[0][qB + o]); qB1 = ldg2(&p.q[1][qB + o]); qB2 = ldg2(&p.q[2][qB + o]);
+                    if (PAIR) { qB0 = ldg2(&p.q[0][qB + o]); qB1 = ldg2(&p.q[1][qB + o]); qB2 = ldg2(&p.q[2][qB + o]); }
                     qR0 = ldg2(&p.q[0][qR + o]); qR2 = ldg2(&p.q[2][qR + o]);
                     if (n + 4 < nplanes) {
                         prefetch_l2(&p.q[0][qA + o + 3 * dN]); prefetch_l2(&p.q[1][qA + o + 3 * dN]);
                         prefetch_l2(&p.q[2][qA + o + 3 * dN]);
-                        prefetch_l2(&p.q[0][qB + o + 3 * dN]); prefetch_l2(&p.q[1][qB + o + 3 * dN]);
-                        prefetch_l2(&p.q[2][qB + o + 3 * dN]);
+                        if (PAIR) {
+                            prefetch_l2(&p.q[0][qB + o + 3 * dN]); prefetch_l2(&p.q[1][qB + o + 3 * dN]);
+                            prefetch_l2(&p.q[2][qB + o + 3 * dN]);
+                        }
                     }
                 }
 
                 // plane k (stage es, complete since the previous step): the neighbours the first curl needs
                 const double2 EA1x = es[EC + exf], EA2x = es[2 * EC + exf];
-                const double2 EB1x = es[dB + EC + exf], EB2x = es[dB + 2 * EC + exf];
+                double2 EB1x = c_zero(), EB2x = c_zero(), EF0 = c_zero(), EF2 = c_zero();
+                if (PAIR) {
+                    EB1x = es[dB + EC + exf]; EB2x = es[dB + 2 * EC + exf];
+                    EF0 = es[2 * dB]; EF2 = es[2 * dB + 2 * EC];
+                } else {   // one row per warp: the row above is not in registers
+                    EB0 = es[dB]; EB2 = es[dB + 2 * EC];
+                }
                 const double2 ER1x = es[EC - dB + exf];
-                const double2 EF0 = es[2 * dB], EF2 = es[2 * dB + 2 * EC];
                 const double2 ER0 = es[-dB], ER2 = es[2 * EC - dB];
                 const double2 a0yA = ty[0], a1yA = ty[NR], a0yB = ty[SGY], a1yB = ty[NR + SGY];
                 const double2 a0yR = ty[-SGY], a1yR = ty[NR - SGY];
@@ -541,7 +554,8 @@ __global__ void __launch_bounds__(32 * (NWC + 1), 1) apply_rowpair_kernel(const 
                 mbar_wait(&full[s_nxt], ((g + 1) / NST) & 1);
                 const double2 *en = ring + s_nxt * STAGE + eA;
                 const double2 NA0 = en[0], NA1 = en[EC], NA2 = en[2 * EC];
-                const double2 NB0 = en[dB], NB1 = en[dB + EC], NB2 = en[dB + 2 * EC];
+                double2 NB0 = c_zero(), NB1 = c_zero(), NB2 = c_zero();
+                if (PAIR) { NB0 = en[dB]; NB1 = en[dB + EC]; NB2 = en[dB + 2 * EC]; }
                 const double2 NR1 = en[EC - dB];
 
                 double2 cxA = c_zero(), cxB = c_zero(), cyA = c_zero(), cyB = c_zero();
@@ -597,11 +611,13 @@ __global__ void __launch_bounds__(32 * (NWC + 1), 1) apply_rowpair_kernel(const 
                     if (MDR) {   // 3 doubles per cell, rows of 32 cells
                         const double *mr = reinterpret_cast<const double *>(ring + s_cur * STAGE + MD0) + mdr_o;
                         mdA0 = make_double2(mr[0], 0.0); mdA1 = make_double2(mr[1], 0.0); mdA2 = make_double2(mr[2], 0.0);
-                        mdB0 = make_double2(mr[mdr_dB], 0.0); mdB1 = make_double2(mr[mdr_dB + 1], 0.0);
-                        mdB2 = make_double2(mr[mdr_dB + 2], 0.0);
+                        if (PAIR) {
+                            mdB0 = make_double2(mr[mdr_dB], 0.0); mdB1 = make_double2(mr[mdr_dB + 1], 0.0);
+                            mdB2 = make_double2(mr[mdr_dB + 2], 0.0);
+                        }
                     } else {
                         mdA0 = es[mdo]; mdA1 = es[mdo + MC]; mdA2 = es[mdo + 2 * MC];
-                        mdB0 = es[mdo + dB]; mdB1 = es[mdo + dB + MC]; mdB2 = es[mdo + dB + 2 * MC];
+                        if (PAIR) { mdB0 = es[mdo + dB]; mdB1 = es[mdo + dB + MC]; mdB2 = es[mdo + dB + 2 * MC]; }
                     }
                 };
                 // EARLY RELEASE: everything this warp needs from stage es (plane k) now sits in registers, so the producer may
@@ -614,7 +630,7 @@ __global__ void __launch_bounds__(32 * (NWC + 1), 1) apply_rowpair_kernel(const 
                     if (lane == 0) mbar_arrive(&empty[s_cur]);
                 }
 
-                double2 HxA, HyA, HzA, HxB, HyB, HzB, HxR, HzR;
+                double2 HxA, HyA, HzA, HxB = c_zero(), HyB = c_zero(), HzB = c_zero(), HxR, HzR;
                 if (!RP_ABL || !(tp.dbg & 8)) {
                     auto curl1 = [&](auto kind) {
                         constexpr bool R = decltype(kind)::value;
@@ -622,9 +638,11 @@ __global__ void __launch_bounds__(32 * (NWC + 1), 1) apply_rowpair_kernel(const 
                         HxA = k_mul<R>(a0yA, EA2); HxA = k_fma<R>(a1yA, EB2, HxA); HxA = k_fms<R>(a0z, EA1, HxA); HxA = k_fms<R>(a1z, NA1, HxA);
                         HyA = k_mul<R>(a0z, EA0);  HyA = k_fma<R>(a1z, NA0, HyA);  HyA = k_fms<R>(a0x, EA2, HyA); HyA = k_fms<R>(a1x, EA2x, HyA);
                         HzA = k_mul<R>(a0x, EA1);  HzA = k_fma<R>(a1x, EA1x, HzA); HzA = k_fms<R>(a0yA, EA0, HzA); HzA = k_fms<R>(a1yA, EB0, HzA);
-                        HxB = k_mul<R>(a0yB, EB2); HxB = k_fma<R>(a1yB, EF2, HxB); HxB = k_fms<R>(a0z, EB1, HxB); HxB = k_fms<R>(a1z, NB1, HxB);
-                        HyB = k_mul<R>(a0z, EB0);  HyB = k_fma<R>(a1z, NB0, HyB);  HyB = k_fms<R>(a0x, EB2, HyB); HyB = k_fms<R>(a1x, EB2x, HyB);
-                        HzB = k_mul<R>(a0x, EB1);  HzB = k_fma<R>(a1x, EB1x, HzB); HzB = k_fms<R>(a0yB, EB0, HzB); HzB = k_fms<R>(a1yB, EF0, HzB);
+                        if (PAIR) {
+                            HxB = k_mul<R>(a0yB, EB2); HxB = k_fma<R>(a1yB, EF2, HxB); HxB = k_fms<R>(a0z, EB1, HxB); HxB = k_fms<R>(a1z, NB1, HxB);
+                            HyB = k_mul<R>(a0z, EB0);  HyB = k_fma<R>(a1z, NB0, HyB);  HyB = k_fms<R>(a0x, EB2, HyB); HyB = k_fms<R>(a1x, EB2x, HyB);
+                            HzB = k_mul<R>(a0x, EB1);  HzB = k_fma<R>(a1x, EB1x, HzB); HzB = k_fms<R>(a0yB, EB0, HzB); HzB = k_fms<R>(a1yB, EF0, HzB);
+                        }
                         // the two components of the row below that this pair's second curl needs (recomputed, not exchanged)
                         HxR = k_mul<R>(a0yR, ER2); HxR = k_fma<R>(a1yR, EA2, HxR); HxR = k_fms<R>(a0z, ER1, HxR); HxR = k_fms<R>(a1z, NR1, HxR);
                         HzR = k_mul<R>(a0x, ER1);  HzR = k_fma<R>(a1x, ER1x, HzR); HzR = k_fms<R>(a0yR, ER0, HzR); HzR = k_fms<R>(a1yR, EA0, HzR);
@@ -640,7 +658,7 @@ __global__ void __launch_bounds__(32 * (NWC + 1), 1) apply_rowpair_kernel(const 
                 }
                 if (HAS_Q) {
                     HxA = c_mul(qA0, HxA); HyA = c_mul(qA1, HyA); HzA = c_mul(qA2, HzA);
-                    HxB = c_mul(qB0, HxB); HyB = c_mul(qB1, HyB); HzB = c_mul(qB2, HzB);
+                    if (PAIR) { HxB = c_mul(qB0, HxB); HyB = c_mul(qB1, HyB); HzB = c_mul(qB2, HzB); }
                     HxR = c_mul(qR0, HxR); HzR = c_mul(qR2, HzR);
                 }
 
@@ -666,16 +684,18 @@ __global__ void __launch_bounds__(32 * (NWC + 1), 1) apply_rowpair_kernel(const 
 
                 if (do_out) {
                     // H_y, H_z of the x-neighbour opposite to the first curl's direction: from the previous lane
-                    double2 HyAm, HzAm, HyBm, HzBm;
+                    double2 HyAm, HzAm, HyBm = c_zero(), HzBm = c_zero();
                     HyAm.x = __shfl_up_sync(0xffffffffu, HyA.x, 1); HyAm.y = __shfl_up_sync(0xffffffffu, HyA.y, 1);
                     HzAm.x = __shfl_up_sync(0xffffffffu, HzA.x, 1); HzAm.y = __shfl_up_sync(0xffffffffu, HzA.y, 1);
-                    HyBm.x = __shfl_up_sync(0xffffffffu, HyB.x, 1); HyBm.y = __shfl_up_sync(0xffffffffu, HyB.y, 1);
-                    HzBm.x = __shfl_up_sync(0xffffffffu, HzB.x, 1); HzBm.y = __shfl_up_sync(0xffffffffu, HzB.y, 1);
+                    if (PAIR) {
+                        HyBm.x = __shfl_up_sync(0xffffffffu, HyB.x, 1); HyBm.y = __shfl_up_sync(0xffffffffu, HyB.y, 1);
+                        HzBm.x = __shfl_up_sync(0xffffffffu, HzB.x, 1); HzBm.y = __shfl_up_sync(0xffffffffu, HzB.y, 1);
+                    }
                     const double2 b0yA = ty[2 * NR], b1yA = ty[3 * NR], b0yB = ty[2 * NR + SGY], b1yB = ty[3 * NR + SGY];
                     const double2 b0z = tz[2 * LZP + n], b1z = tz[3 * LZP + n];
                     const bool rc2 = rcxy && __all_sync(0xffffffffu, (b0z.y == 0.0) & (b1z.y == 0.0));
                     if (!early) load_md();
-                    double2 yxA, yyA, yzA, yxB, yyB, yzB;
+                    double2 yxA, yyA, yzA, yxB = c_zero(), yyB = c_zero(), yzB = c_zero();
                     if (!RP_ABL || !(tp.dbg & 8)) {
                         auto curl2 = [&](auto kind) {
                             constexpr bool R = decltype(kind)::value;
@@ -683,9 +703,11 @@ __global__ void __launch_bounds__(32 * (NWC + 1), 1) apply_rowpair_kernel(const 
                             yxA = k_mul<R>(b0yA, HzA); yxA = k_fma<R>(b1yA, HzR, yxA);  yxA = k_fms<R>(b0z, HyA, yxA); yxA = k_fms<R>(b1z, HpyA, yxA);
                             yyA = k_mul<R>(b0z, HxA);  yyA = k_fma<R>(b1z, HpxA, yyA);  yyA = k_fms<R>(b0x, HzA, yyA); yyA = k_fms<R>(b1x, HzAm, yyA);
                             yzA = k_mul<R>(b0x, HyA);  yzA = k_fma<R>(b1x, HyAm, yzA);  yzA = k_fms<R>(b0yA, HxA, yzA); yzA = k_fms<R>(b1yA, HxR, yzA);
-                            yxB = k_mul<R>(b0yB, HzB); yxB = k_fma<R>(b1yB, HzA, yxB);  yxB = k_fms<R>(b0z, HyB, yxB); yxB = k_fms<R>(b1z, HpyB, yxB);
-                            yyB = k_mul<R>(b0z, HxB);  yyB = k_fma<R>(b1z, HpxB, yyB);  yyB = k_fms<R>(b0x, HzB, yyB); yyB = k_fms<R>(b1x, HzBm, yyB);
-                            yzB = k_mul<R>(b0x, HyB);  yzB = k_fma<R>(b1x, HyBm, yzB);  yzB = k_fms<R>(b0yB, HxB, yzB); yzB = k_fms<R>(b1yB, HxA, yzB);
+                            if (PAIR) {
+                                yxB = k_mul<R>(b0yB, HzB); yxB = k_fma<R>(b1yB, HzA, yxB);  yxB = k_fms<R>(b0z, HyB, yxB); yxB = k_fms<R>(b1z, HpyB, yxB);
+                                yyB = k_mul<R>(b0z, HxB);  yyB = k_fma<R>(b1z, HpxB, yyB);  yyB = k_fms<R>(b0x, HzB, yyB); yyB = k_fms<R>(b1x, HzBm, yyB);
+                                yzB = k_mul<R>(b0x, HyB);  yzB = k_fma<R>(b1x, HyBm, yzB);  yzB = k_fms<R>(b0yB, HxB, yzB); yzB = k_fms<R>(b1yB, HxA, yzB);
+                            }
                         };
                         if (rc2) curl2(RealCoef{}); else curl2(CplxCoef{});
                         if (p.has_mass) {
@@ -693,12 +715,14 @@ __global__ void __launch_bounds__(32 * (NWC + 1), 1) apply_rowpair_kernel(const 
                                 yxA.x = fma(mdA0.x, EA0.x, yxA.x); yxA.y = fma(mdA0.x, EA0.y, yxA.y);
                                 yyA.x = fma(mdA1.x, EA1.x, yyA.x); yyA.y = fma(mdA1.x, EA1.y, yyA.y);
                                 yzA.x = fma(mdA2.x, EA2.x, yzA.x); yzA.y = fma(mdA2.x, EA2.y, yzA.y);
-                                yxB.x = fma(mdB0.x, EB0.x, yxB.x); yxB.y = fma(mdB0.x, EB0.y, yxB.y);
-                                yyB.x = fma(mdB1.x, EB1.x, yyB.x); yyB.y = fma(mdB1.x, EB1.y, yyB.y);
-                                yzB.x = fma(mdB2.x, EB2.x, yzB.x); yzB.y = fma(mdB2.x, EB2.y, yzB.y);
+                                if (PAIR) {
+                                    yxB.x = fma(mdB0.x, EB0.x, yxB.x); yxB.y = fma(mdB0.x, EB0.y, yxB.y);
+                                    yyB.x = fma(mdB1.x, EB1.x, yyB.x); yyB.y = fma(mdB1.x, EB1.y, yyB.y);
+                                    yzB.x = fma(mdB2.x, EB2.x, yzB.x); yzB.y = fma(mdB2.x, EB2.y, yzB.y);
+                                }
                             } else {
                                 yxA = c_fma(mdA0, EA0, yxA); yyA = c_fma(mdA1, EA1, yyA); yzA = c_fma(mdA2, EA2, yzA);
-                                yxB = c_fma(mdB0, EB0, yxB); yyB = c_fma(mdB1, EB1, yyB); yzB = c_fma(mdB2, EB2, yzB);
+                                if (PAIR) { yxB = c_fma(mdB0, EB0, yxB); yyB = c_fma(mdB1, EB1, yyB); yzB = c_fma(mdB2, EB2, yzB); }
                             }
                         }
                     } else {
@@ -736,7 +760,7 @@ __global__ void __launch_bounds__(32 * (NWC + 1), 1) apply_rowpair_kernel(const 
                     __syncwarp();
                     if (!tmap || lane_out) {
                         yw[yA] = yxA; yw[yA + YC] = yyA; yw[yA + 2 * YC] = yzA;
-                        yw[yB] = yxB; yw[yB + YC] = yyB; yw[yB + 2 * YC] = yzB;
+                        if (PAIR) { yw[yB] = yxB; yw[yB + YC] = yyB; yw[yB + 2 * YC] = yzB; }
                     }
                     fence_proxy_async();   // generic-proxy writes -> visible to the bulk-copy (async) proxy
                 }
@@ -756,9 +780,10 @@ __global__ void __launch_bounds__(32 * (NWC + 1), 1) apply_rowpair_kernel(const 
                     GzA = GzAn; GzB = GzBn; fCz = fN;
                     E2pA = EA2; E2pB = EB2; E2pF = EF2;
                 }
-                HpxA = HxA; HpyA = HyA; HpxB = HxB; HpyB = HyB;
+                HpxA = HxA; HpyA = HyA;
+                if (PAIR) { HpxB = HxB; HpyB = HyB; }
                 EA0 = NA0; EA1 = NA1; EA2 = NA2;
-                EB0 = NB0; EB1 = NB1; EB2 = NB2;
+                if (PAIR) { EB0 = NB0; EB1 = NB1; EB2 = NB2; }
                 ER1 = NR1;
                 es = en;
                 s_cur = s_nxt;
@@ -840,13 +865,13 @@ int sm_count() {
     return n[dev];
 }
 
-template <bool CMPFIRST, bool HAS_Q, bool DOT, int ARR, bool MDR, bool HAS_OFF, int NWC, int NST>
+template <bool CMPFIRST, bool HAS_Q, bool DOT, int ARR, bool MDR, bool HAS_OFF, int NWC, int NST, int RPW>
 cudaError_t launch_rp(const RowPairParams &tp, int grid, cudaStream_t s) {
-    if constexpr (MDR && !CMPFIRST) {
+    if constexpr ((MDR && !CMPFIRST) || (RPW == 1 && (HAS_Q || HAS_OFF || !CMPFIRST))) {
         return cudaErrorInvalidConfiguration;
     } else {
-        auto kern = apply_rowpair_kernel<CMPFIRST, HAS_Q, DOT, ARR, MDR, HAS_OFF, NWC, NST>;
-        const size_t smem = RPCfg<NWC, NST, MDR, HAS_OFF>::smem_bytes();
+        auto kern = apply_rowpair_kernel<CMPFIRST, HAS_Q, DOT, ARR, MDR, HAS_OFF, NWC, NST, RPW>;
+        const size_t smem = RPCfg<NWC, NST, MDR, HAS_OFF, RPW>::smem_bytes();
         static bool attr_set[64] = {};
         int dev = 0;
         cudaGetDevice(&dev);
@@ -864,8 +889,11 @@ cudaError_t launch_rp(const RowPairParams &tp, int grid, cudaStream_t s) {
 // ceil(warps / 4): 8 warps (7 compute + producer) may use 255 registers.  Shape 0: complex material rows, 4 ring
 // stages of 46 KB; shape 1: real material rows (MDR), 5 stages of 35 KB; shape 2: the fused full tensor (real diagonal
 // and off-diagonal rows), 4 stages of 47 KB.
-struct RpShape { int nwc, nst; bool mdr, off; };
-constexpr RpShape RP_SHAPES[] = {{7, 4, false, false}, {7, 5, true, false}, {7, 4, true, true}, {7, 4, true, false}};   // [3]: A/B timing only (FDFD_RP_NST4)
+struct RpShape { int nwc, nst; bool mdr, off; int rpw; };
+// [3], [4]: A/B timing only - the real-row shape on a 4-stage ring (FDFD_RP_NST4: same speed, the ring depth is not what
+// limits the kernel) and ONE tile row per compute warp (FDFD_RP_RPW1: 10 compute warps at 166 registers - measured 108 vs
+// 123 GDOF/s on C2, 121 vs 127 on C4; with 14 warps the kernel spills at 128 registers: 70 GDOF/s - so two rows per warp stay)
+constexpr RpShape RP_SHAPES[] = {{7, 4, false, false, 2}, {7, 5, true, false, 2}, {7, 4, true, true, 2}, {7, 4, true, false, 2}, {10, 6, true, false, 1}};
 constexpr int RP_NSHAPES = sizeof(RP_SHAPES) / sizeof(RP_SHAPES[0]);
 
 }  // namespace
@@ -899,7 +927,7 @@ static bool want_tmap() {
     return v;
 }
 
-static int rp_lzmax(int shape) { return RP_SHAPES[shape].off ? RPCfg<7, 4, true, true>::LZMAX : RP_LZMAX; }
+static int rp_lzmax(int shape) { return RP_SHAPES[shape].off ? RPCfg<7, 4, true, true, 2>::LZMAX : RP_LZMAX; }
 
 // can the fused full-tensor shape run p?  (cmp-first layout, tensor maps, real diagonal and real symmetric off-diagonal
 // rows built by the handle, the occupancy mask - if there is one - on this shape's 30 x 14 tiles)
@@ -925,13 +953,15 @@ static int rp_pick_shape(const ApplyParams &p, int kl_begin, int kl_end, int *nc
     const int n = kl_end - kl_begin;
     const bool mdr = p.cmpfirst && p.has_mass && p.md[0] != nullptr && p.md_aos_r != nullptr && want_tmap();
     static const bool nst4 = getenv("FDFD_RP_NST4") != nullptr;   // A/B timing: real-row shape with a 4-stage ring
-    int i = mdr ? (nst4 ? 3 : 1) : 0;
+    static const bool rpw1 = [] { const char *e = getenv("FDFD_RP_RPW1"); return e && atoi(e) != 0; }();   // A/B timing
+    int i = mdr ? (nst4 ? 3 : (rpw1 && !p.has_q ? 4 : 1)) : 0;
     if (p.has_off && p.has_mass) {
         if (!rp_fused_ok(p)) return -1;
         i = 2;
     }
     const int nwc = RP_SHAPES[i].nwc, nst = RP_SHAPES[i].nst, lzmax = rp_lzmax(i);
-    const int ntx = (p.Nx + RP_TX - 3) / (RP_TX - 2), nty = (p.Ny + 2 * nwc - 1) / (2 * nwc);
+    const int nrow = RP_SHAPES[i].rpw * nwc;
+    const int ntx = (p.Nx + RP_TX - 3) / (RP_TX - 2), nty = (p.Ny + nrow - 1) / nrow;
     int nch = rp_pick_nchunk(ntx * nty, n, rp_grid_cap(p), nst, lzmax, nullptr);
     if (want_nch >= 1 && n / want_nch >= std::max(1, nst - 2) && (n + want_nch - 1) / want_nch <= lzmax) nch = want_nch;
     if (nch < 1) return -1;
@@ -994,31 +1024,32 @@ static bool cached_map(TmaMap *out, const void *base, uint64_t d0, uint64_t d1, 
     return true;
 }
 
-template <int NWC, int NST, bool MDR, bool HAS_OFF>
+template <int NWC, int NST, bool MDR, bool HAS_OFF, int RPW>
 static cudaError_t launch_rp_shape(RowPairParams &tp, const ApplyParams &p, cudaStream_t s) {
+    constexpr int NROW = RPW * NWC;   // output rows of a tile
     // tensor-map TMA path (cmp-first layout): boxes of 32 cells x (E rows | material rows), y boxes of 30 cells x 2 rows
     tp.tmap = 0;
     if (want_tmap() && p.cmpfirst && p.x.base && p.y) {
         const uint64_t d0 = 6ull * p.Nx, d1 = (uint64_t)p.Ny;
         const bool md_tile = p.has_mass && p.md[0] != nullptr;
-        bool ok = cached_map(&tp.mx, p.x.base, d0, d1, (uint64_t)p.nzl, 6 * RP_TX, 2 * NWC + 2) &&
-                  cached_map(&tp.mlo, p.x.lo, d0, d1, 1, 6 * RP_TX, 2 * NWC + 2) &&
-                  cached_map(&tp.mhi, p.x.hi, d0, d1, 1, 6 * RP_TX, 2 * NWC + 2) &&
-                  cached_map(&tp.my, p.y, d0, d1, (uint64_t)p.nzl, 6 * (RP_TX - 2), 2);
+        bool ok = cached_map(&tp.mx, p.x.base, d0, d1, (uint64_t)p.nzl, 6 * RP_TX, NROW + 2) &&
+                  cached_map(&tp.mlo, p.x.lo, d0, d1, 1, 6 * RP_TX, NROW + 2) &&
+                  cached_map(&tp.mhi, p.x.hi, d0, d1, 1, 6 * RP_TX, NROW + 2) &&
+                  cached_map(&tp.my, p.y, d0, d1, (uint64_t)p.nzl, 6 * (RP_TX - 2), RPW);
         if (ok && md_tile) {
-            if (MDR) ok = p.md_aos_r != nullptr && cached_map(&tp.mmd, p.md_aos_r, d0 / 2, d1, (uint64_t)p.nzl + 2, 3 * (RP_TX + 2), 2 * NWC,
+            if (MDR) ok = p.md_aos_r != nullptr && cached_map(&tp.mmd, p.md_aos_r, d0 / 2, d1, (uint64_t)p.nzl + 2, 3 * (RP_TX + 2), NROW,
                                                                  mdr_row_pitch(p.Nx));
-            else ok = p.md_aos != nullptr && cached_map(&tp.mmd, p.md_aos, d0, d1, (uint64_t)p.nzl + 2, 6 * RP_TX, 2 * NWC);
+            else ok = p.md_aos != nullptr && cached_map(&tp.mmd, p.md_aos, d0, d1, (uint64_t)p.nzl + 2, 6 * RP_TX, NROW);
         }
         if (ok && HAS_OFF)   // off-diagonal rows: padded by one cell / row on either side (wrapped copies or zeros)
             ok = p.mo_aos_r != nullptr && cached_map(&tp.mmo, p.mo_aos_r, 3ull * (p.Nx + 2), (uint64_t)p.Ny + 2, (uint64_t)p.nzl + 2,
-                                                     3 * (RP_TX + 2), 2 * NWC + 1, mdr_row_pitch(p.Nx + 2));
+                                                     3 * (RP_TX + 2), NROW + 1, mdr_row_pitch(p.Nx + 2));
         tp.tmap = ok ? 1 : 0;
     }
     if (MDR && !tp.tmap) return cudaErrorNotSupported;   // the handle keeps complex rows whenever tensor maps are unavailable
     if (HAS_OFF && p.offmask && p.offmask_ty != 16) return cudaErrorInvalidConfiguration;
     tp.ntx = (p.Nx + RP_TX - 3) / (RP_TX - 2);
-    tp.nty = (p.Ny + 2 * NWC - 1) / (2 * NWC);
+    tp.nty = (p.Ny + NROW - 1) / NROW;
     tp.nitems = tp.ntx * tp.nty * tp.nchunk;
     int grid = std::min(tp.nitems, rp_grid_cap(p));
     tp.halo_last = p.halo_flag != nullptr ? 1 : 0;
@@ -1030,9 +1061,9 @@ static cudaError_t launch_rp_shape(RowPairParams &tp, const ApplyParams &p, cuda
     const int nfwd = (p.s1[0] > 0) + (p.s1[1] > 0) + (p.s1[2] > 0);
     const int arr = nfwd == 3 ? 0 : nfwd == 0 ? 1 : 2;
 #define W(CF, Q, D)                                                                                          \
-    (arr == 0 ? launch_rp<CF, Q, D, 0, MDR, HAS_OFF, NWC, NST>(tp, grid, s)                                  \
-              : arr == 1 ? launch_rp<CF, Q, D, 1, MDR, HAS_OFF, NWC, NST>(tp, grid, s)                       \
-                         : launch_rp<CF, Q, D, 2, MDR, HAS_OFF, NWC, NST>(tp, grid, s))
+    (arr == 0 ? launch_rp<CF, Q, D, 0, MDR, HAS_OFF, NWC, NST, RPW>(tp, grid, s)                             \
+              : arr == 1 ? launch_rp<CF, Q, D, 1, MDR, HAS_OFF, NWC, NST, RPW>(tp, grid, s)                  \
+                         : launch_rp<CF, Q, D, 2, MDR, HAS_OFF, NWC, NST, RPW>(tp, grid, s))
 #define V(CF, Q) (dot ? W(CF, Q, true) : W(CF, Q, false))
     if (cf) return q ? V(true, true) : V(true, false);
     if constexpr (MDR) return cudaErrorInvalidConfiguration;
@@ -1056,13 +1087,14 @@ cudaError_t launch_apply_rowpair(const ApplyParams &p, int kl_begin, int kl_end,
                           ? rp_pick_shape(p, kl_begin, kl_end, &tp.nchunk) : -1;
     static const bool verbose = getenv("FDFD_VERBOSE") != nullptr;
     if (verbose) fprintf(stderr, "fdfd: row-pair kernel shape %d (%s), %d z-chunk(s), planes [%d, %d)\n", shape,
-                         shape == 2 ? "fused full tensor" : shape == 1 ? "real diagonal mass" : shape == 0 ? "complex diagonal mass" : "unsupported",
+                         shape == 2 ? "fused full tensor" : shape == 1 ? "real diagonal mass" : shape == 0 ? "complex diagonal mass" : shape == 3 ? "real diagonal mass, 4 stages" : shape >= 4 ? "real diagonal mass, one row per warp" : "unsupported",
                          tp.nchunk, kl_begin, kl_end);
     switch (shape) {
-        case 0: return launch_rp_shape<RP_SHAPES[0].nwc, RP_SHAPES[0].nst, RP_SHAPES[0].mdr, RP_SHAPES[0].off>(tp, p, s);
-        case 1: return launch_rp_shape<RP_SHAPES[1].nwc, RP_SHAPES[1].nst, RP_SHAPES[1].mdr, RP_SHAPES[1].off>(tp, p, s);
-        case 2: return launch_rp_shape<RP_SHAPES[2].nwc, RP_SHAPES[2].nst, RP_SHAPES[2].mdr, RP_SHAPES[2].off>(tp, p, s);
-        case 3: return launch_rp_shape<RP_SHAPES[3].nwc, RP_SHAPES[3].nst, RP_SHAPES[3].mdr, RP_SHAPES[3].off>(tp, p, s);
+        case 0: return launch_rp_shape<RP_SHAPES[0].nwc, RP_SHAPES[0].nst, RP_SHAPES[0].mdr, RP_SHAPES[0].off, RP_SHAPES[0].rpw>(tp, p, s);
+        case 1: return launch_rp_shape<RP_SHAPES[1].nwc, RP_SHAPES[1].nst, RP_SHAPES[1].mdr, RP_SHAPES[1].off, RP_SHAPES[1].rpw>(tp, p, s);
+        case 2: return launch_rp_shape<RP_SHAPES[2].nwc, RP_SHAPES[2].nst, RP_SHAPES[2].mdr, RP_SHAPES[2].off, RP_SHAPES[2].rpw>(tp, p, s);
+        case 3: return launch_rp_shape<RP_SHAPES[3].nwc, RP_SHAPES[3].nst, RP_SHAPES[3].mdr, RP_SHAPES[3].off, RP_SHAPES[3].rpw>(tp, p, s);
+        case 4: return launch_rp_shape<RP_SHAPES[4].nwc, RP_SHAPES[4].nst, RP_SHAPES[4].mdr, RP_SHAPES[4].off, RP_SHAPES[4].rpw>(tp, p, s);
         default: return cudaErrorNotSupported;
     }
 }
