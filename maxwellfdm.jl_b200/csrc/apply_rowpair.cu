@@ -326,12 +326,14 @@ __global__ void __launch_bounds__(32 * (NWC + 1), 1) apply_rowpair_kernel(const 
                 if (p.halo_flag != nullptr && !halo_ok && (kk < 0 || kk >= p.nzl)) {
                     // z-slabs, exchange overlapped with the interior chunks: the neighbours' planes are final once the flag
                     // word (written by a stream memory operation behind the exchange) has reached this apply's epoch.  The
-                    // spin is bounded: a transfer that never arrives traps instead of hanging the GPU.
+                    // spin is bounded, generously: ranks may enter an apply seconds apart (a neighbour still building its
+                    // material arrays), but a transfer that never arrives (mismatched calls across ranks) must trap after a
+                    // few minutes instead of hanging the GPU for ever.
                     if (lane == 0) {
                         uint32_t spins = 0;
                         while ((int32_t)(ld_acquire_sys(p.halo_flag) - p.halo_expect) < 0) {
-                            __nanosleep(100);
-                            if (++spins > 40000000u) __trap();
+                            __nanosleep(spins < 1000000u ? 100 : 1000);
+                            if (++spins > 300000000u) __trap();
                         }
                     }
                     __syncwarp();
