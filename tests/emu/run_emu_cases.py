@@ -157,6 +157,20 @@ def g_fused():
     return n + 1
 
 
+def g_multi():
+    """the single-call handle (fdfd_multi_*, csrc/multi.cpp) with ONE slab - what can run without several devices: full-grid
+    host arrays in, apply / transposed apply on both DOF layouts, BiCGSTAB / QMR, the model-level call create_A(..., ngpu=1);
+    several slabs (host threads, NCCL between them) are checked on the GPU boxes by scripts/multi_check.py"""
+    import types
+    sys.modules.setdefault("torch", types.SimpleNamespace(cuda=types.SimpleNamespace(device_count=lambda: 1)))
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    import multi_check
+    n, fails = multi_check.check(1)
+    if fails:
+        raise AssertionError(f"single-call handle: {fails[:3]}")
+    return n
+
+
 def g_boundft():
     """all 2^3 boundft choices, both formulations, forward and transposed (ARR = 0 / 1 / 2 instantiations)"""
     n = 0
@@ -377,7 +391,7 @@ def g_reduced():
     return n
 
 
-GROUPS = {"fused": g_fused, "realmass": g_realmass, "reduced": g_reduced, "matparams": g_matparams, "apply": g_apply, "boundft": g_boundft, "layouts": g_layouts, "deep": g_deep, "solve": g_solve, "aux": g_aux}
+GROUPS = {"multi": g_multi, "fused": g_fused, "realmass": g_realmass, "reduced": g_reduced, "matparams": g_matparams, "apply": g_apply, "boundft": g_boundft, "layouts": g_layouts, "deep": g_deep, "solve": g_solve, "aux": g_aux}
 
 
 def main():

@@ -96,6 +96,23 @@ def test_no_cpu_fallback_without_gpu():
         A.solve(p.random_x())
 
 
+def test_single_call_handle_needs_gpus_too():
+    """fdfd_multi_* owns ordinary slab handles: without a CUDA device it must fail loudly (no CPU fallback), with the failing
+    slab named in the message"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import maxwellfdm_jl_b200 as fb
+    L = _lib()
+    p = Problem((4, 3, 6))
+    with pytest.raises(L.FdfdError) as ei:
+        fb.MultiGpuOperator(p.N, p.isbloch, p.sdl_e, p.sdl_m, p.omega, p.eps, None, p.ph, ngpu=2)
+    assert ei.value.code == L.ECUDA and "no CPU fallback" in str(ei.value) and "slab" in str(ei.value)
+    with pytest.raises(L.FdfdError) as ei2:        # more slabs than z-planes
+        fb.MultiGpuOperator(p.N, p.isbloch, p.sdl_e, p.sdl_m, p.omega, p.eps, None, p.ph, ngpu=7)
+    assert ei2.value.code == L.EINVAL
+
+
 def test_output_buffers_are_validated_before_the_c_call():
     """mul!(y, A, x) / solve(b, x0): the library writes y / reads x0 through raw pointers, so the Python mirror rejects
     a wrong dtype, size, stride or a host / device mix instead of handing it to the C ABI."""

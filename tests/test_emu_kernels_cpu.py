@@ -48,6 +48,20 @@ def test_emulated_real_mass_rows(emu_lib):
     assert "checks ok" in out, out
 
 
+def test_emulated_fused_full_tensor_shape(emu_lib):
+    """fused full-tensor shape of the row-pair kernel (real symmetric off-diagonal rows through the TMA ring): every boundary
+    combination, partly empty blocks, three arrangements, transposed apply, fused dots; eager copies + shuffled warps is the
+    mode that found the stale per-stage flag after an early release"""
+    out = _run(emu_lib, ["fused"], "eager", 7)
+    assert "checks ok" in out, out
+
+
+def test_emulated_single_call_handle(emu_lib):
+    """fdfd_multi_* with one slab: the host-side plumbing of csrc/multi.cpp (worker thread, full-grid arrays, layouts)"""
+    out = _run(emu_lib, ["multi"], "eager", 0)
+    assert "checks ok" in out, out
+
+
 def test_emulated_row_pair_kernel_without_tensor_maps(emu_lib):
     """the 1-D bulk-copy path of the row-pair kernel (FDFD_RP_TMAP=0; also what the component-major layout takes)"""
     out = _run(emu_lib, ["apply", "deep"], "lazy", 4, FDFD_RP_TMAP="0", FDFD_RP_GRID="3")
@@ -90,20 +104,23 @@ def test_emulated_krylov_solvers(emu_lib):
 
 
 def _run_dist(world, groups, **modes):
-    env = dict(os.environ, **{k: "1" for k in modes})
+    env = dict(os.environ, **{k: str(v) for k, v in modes.items()})
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emu", "run_emu_dist.py"), str(world), *groups],
                        env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and r.stdout.count("checks ok") == world, f"{world} {groups} {modes}\n{r.stdout[-2000:]}\n{r.stderr[-4000:]}"
 
 
-@pytest.mark.parametrize("world,groups,modes", [(3, ["apply"], {}), (2, ["apply"], {"FDFD_PEER_HALO": 1}),
+@pytest.mark.parametrize("world,groups,modes", [(3, ["apply"], {}), (2, ["apply"], {"FDFD_PEER_HALO": 0}),
+                                                (2, ["apply"], {"FDFD_PEER_HALO": 0, "FDFD_HALO_OVERLAP": 1}),
                                                 (3, ["krylov"], {"FDFD_PEER_DIRECT": 1}),
                                                 (2, ["apply"], {"FDFD_SPLIT_OVERLAP": 1}),
-                                                (2, ["apply"], {"FDFD_INKERNEL_HALO_WAIT": 1})],
-                         ids=["nccl-3", "peer-halo-2", "peer-direct-3", "split-overlap-2", "inkernel-wait-2"])
+                                                (2, ["apply"], {"FDFD_PEER_HALO": 0, "FDFD_INKERNEL_HALO_WAIT": 1, "FDFD_K1_GEN": 1})],
+                         ids=["default-peer-overlap-3", "nccl-2", "nccl-overlap-2", "peer-direct-3", "split-overlap-2",
+                              "gen1-inkernel-wait-2"])
 def test_emulated_z_slab_ranks(emu_lib, world, groups, modes):
     """one process per rank as on the GPU box; NCCL / driver entry points replaced by tests/emu/fakelibs, device memory
-    in named shared memory so that the CUDA-IPC peer-halo path maps between the processes: halo exchange on every
+    in named shared memory so that the CUDA-IPC peer-halo path (the default data plane) maps between the processes; NCCL
+    send/recv forced with FDFD_PEER_HALO=0, the in-kernel halo wait on either plane: halo exchange on every
     arrangement and layout, Bloch wrap between the first and last rank, back-to-back applies (protocol epochs), host
     and device paths, transposed apply, BiCGSTAB / QMR with allreduced dots"""
     _run_dist(world, groups, **modes)
