@@ -280,11 +280,12 @@ def _build(ft, w, Ps, Cs, device=-1, rank=0, nranks=1, kernel=0, weighted_out_av
         from .operator import MultiGpuOperator
         if nranks != 1 or rank != 0:
             raise ValueError("ngpu (one process, several GPUs) and rank / nranks (one process per GPU) exclude each other")
-        if objects:
-            raise ValueError("ngpu: device_materials is not available through the single-call handle yet")
-        A = MultiGpuOperator(g.N, g.isbloch, g.sdl_e, g.sdl_m, w, Pe.arr, mu, g.e_mikL, boundft=g.boundft, ft=ft,
-                             order_cmpfirst=g.order_cmpfirst, ngpu=ngpu, devices=devices, kernel=kernel,
+        A = MultiGpuOperator(g.N, g.isbloch, g.sdl_e, g.sdl_m, w, None if objects else Pe.arr, mu, g.e_mikL, boundft=g.boundft,
+                             ft=ft, order_cmpfirst=g.order_cmpfirst, ngpu=ngpu, devices=devices, kernel=kernel,
                              weighted_out_avg=weighted_out_avg)
+        if objects:
+            lprim, shapes, pinds, params = objects
+            A.set_eps_objects(lprim, shapes, pinds, params, boundft=g.boundft)
         g.ops[key] = A
         return A
     from .operator import partition

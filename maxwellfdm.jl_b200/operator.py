@@ -27,6 +27,29 @@ def _c128(z):
     return L.c128(z.real, z.imag)
 
 
+def _matparams_desc(N, isbloch, lprim, shapes, pinds, params, boundft, field_ortho_shape):
+    """fdfd_matparams_desc for an object list (+ the buffers it points into, which the caller must keep alive)"""
+    from .shapes import _as_tensor
+    sh = (L.Shape * len(shapes))()
+    for s, shp, pi in zip(sh, shapes, pinds):
+        s.kind, s.axis, s.pind = shp.kind, shp.axis, int(pi)
+        s.c[:] = shp.c
+        s.r[:] = shp.r
+    prm = np.ascontiguousarray(np.stack([_as_tensor(P) for P in params]).reshape(-1, 9))
+    lp = [np.ascontiguousarray(a, dtype=np.float64) for a in lprim]
+    d = L.MatParamsDesc()
+    d.N[:] = N
+    d.isbloch[:] = [1 if b else 0 for b in isbloch]
+    d.boundft_is_E[:] = [1 if str(b).upper().startswith("E") or b == 0 else 0 for b in boundft]
+    d.field_type = L.FT_EE
+    d.field_ortho_shape = 1 if field_ortho_shape else 0
+    d.lprim[:] = [a.ctypes.data for a in lp]
+    d.nshape, d.nparam = len(shapes), prm.shape[0]
+    d.shapes = C.cast(sh, C.c_void_p).value
+    d.params = prm.ctypes.data
+    return d, (sh, prm, lp)
+
+
 class FdfdOperator:
     """Matrix-free A = C2 q C1 - w^2 P on one z-slab of the grid.
 
@@ -129,24 +152,8 @@ class FdfdOperator:
         """eps straight from objects (shapes.py): this rank's slab is rasterised and subpixel-smoothed on the device,
         directly into the operator's material arrays - no (Nx,Ny,Nz,3,3) host array.  lprim: the Grid's ghosted primal
         planes; shapes / pinds / params as for calc_matparams_array; boundft / isbloch must be the handle's."""
-        from .shapes import _as_tensor
-        sh = (L.Shape * len(shapes))()
-        for s, shp, pi in zip(sh, shapes, pinds):
-            s.kind, s.axis, s.pind = shp.kind, shp.axis, int(pi)
-            s.c[:] = shp.c
-            s.r[:] = shp.r
-        prm = np.ascontiguousarray(np.stack([_as_tensor(P) for P in params]).reshape(-1, 9))
-        lp = [np.ascontiguousarray(a, dtype=np.float64) for a in lprim]
-        d = L.MatParamsDesc()
-        d.N[:] = self.N
-        d.isbloch[:] = [1 if b else 0 for b in (self._isbloch if isbloch is None else isbloch)]
-        d.boundft_is_E[:] = [1 if str(b).upper().startswith("E") or b == 0 else 0 for b in boundft]
-        d.field_type = L.FT_EE
-        d.field_ortho_shape = 1 if field_ortho_shape else 0
-        d.lprim[:] = [a.ctypes.data for a in lp]
-        d.nshape, d.nparam = len(shapes), prm.shape[0]
-        d.shapes = C.cast(sh, C.c_void_p).value
-        d.params = prm.ctypes.data
+        d, keep = _matparams_desc(self.N, self._isbloch if isbloch is None else isbloch, lprim, shapes, pinds, params, boundft,
+                                  field_ortho_shape)
         L.check(L.lib().fdfd_set_eps_objects(self._h, C.byref(d)), self._h)
 
     def set_mu(self, mu):
@@ -393,6 +400,7 @@ class MultiGpuOperator:
         self._m = m
         self.ft = 0 if d.field_type == L.FT_EE else 1
         self.N = tuple(int(n) for n in N)
+        self._isbloch = tuple(bool(b) for b in isbloch)
         self.ngpu = int(ngpu)
         self.n = 3 * self.N[0] * self.N[1] * self.N[2]
         self.shape = (self.n, self.n)
@@ -420,6 +428,11 @@ class MultiGpuOperator:
         if a.shape != (Nx, Ny, Nz, 3, 3):
             raise ValueError(f"{name} must have shape (Nx,Ny,Nz,3,3) = {(Nx, Ny, Nz, 3, 3)} (the whole grid)")
         return FdfdOperator._julia_layout(a)
+
+    def set_eps_objects(self, lprim, shapes, pinds, params, boundft=("E", "E", "E"), field_ortho_shape=False):
+        """eps straight from objects: every slab rasterises and smooths its own planes on its device (fdfd_multi_set_eps_objects)"""
+        d, keep = _matparams_desc(self.N, self._isbloch, lprim, shapes, pinds, params, boundft, field_ortho_shape)
+        L.check_multi(L.lib().fdfd_multi_set_eps_objects(self._m, C.byref(d)), self._m)
 
     def close(self):
         if self._m is not None:

@@ -81,6 +81,21 @@ def check(ngpu):
         fails.append((ngpu, "model-level create_linsys", e))
     A.close()
     A1.close()
+    # objects instead of arrays (device_materials): every slab rasterises and smooths its own planes on its device
+    mdl2 = fb.ModelFull(g)
+    fb.set_wpml(mdl2, 0.9)
+    fb.set_Npml(mdl2, ((0, 0, 2), (0, 0, 2)))
+    fb.add_obj(mdl2, "bg", fb.Box([6.0, 4.5, N[2] / 2.0], [12.0, 9.0, float(N[2])]), eps=2.1)
+    fb.add_obj(mdl2, "ball", fb.Ball([5.7, 4.2, N[2] / 2.0 + 0.3], 2.6), eps=11.7)
+    Ps, Cs = fb.create_paramops(mdl2, device_materials=True), fb.create_curls(mdl2)
+    Am = fb.create_A(EE, 0.9, Ps, Cs, ngpu=ngpu)
+    As = fb.create_A(EE, 0.9, Ps, Cs)
+    e = rel(Am @ xv, As @ xv)
+    n += 1
+    if not e < 1e-13:
+        fails.append((ngpu, "objects through the single-call handle", e))
+    Am.close()
+    As.close()
     return n, fails
 
 
