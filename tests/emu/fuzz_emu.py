@@ -1,7 +1,10 @@
 """TEST INFRASTRUCTURE ONLY - randomised campaign of the tiled kernel under the CPU logic-check build against the
 matrix-free oracle: random grid sizes (incl. sizes just around the tile and chunk boundaries), boundary conditions,
 arrangements, layouts, material kinds, sparse / dense off-diagonal patterns, forced z-chunk lengths (FDFD_LZ) and,
-per process, a forced tile height (FDFD_TY).
+per process, a forced tile height (FDFD_TY).  Since round 2 half of the cases have real diagonal mass entries (MDR shape of
+the row-pair kernel) and half of those a real symmetric off-diagonal tensor (fused shape, or - below FDFD_RP_FUSE_MIN - the
+two-pass plan on the row-pair kernel); per process the row-pair plan can be bent with FDFD_RP_NCHUNK / FDFD_RP_GRID /
+FDFD_RP_FUSE_MIN / FDFD_RP_DEBUG=16|32|64.
 
     FDFD_B200_LIB=build/emu/libfdfd_emu.so [FDFD_TY=16] python tests/emu/fuzz_emu.py SEED NCASES
 """
@@ -33,9 +36,9 @@ def main():
     seed, ncases = int(sys.argv[1]), int(sys.argv[2])
     assert "EMULATED" in L.lib().fdfd_version().decode()
     rng = np.random.default_rng(seed)
-    nx_pool = [1, 2, 3, 7, 29, 30, 31, 32, 33, 59, 60, 61, 62, 64]
-    ny_pool = [1, 2, 3, 5, 6, 7, 8, 11, 12, 13, 14, 15, 20, 29]
-    nz_pool = [1, 2, 3, 4, 5, 7, 9, 16, 23, 41, 44]
+    nx_pool = [1, 2, 3, 7, 29, 30, 31, 32, 33, 59, 60, 61, 62, 64, 89, 91]
+    ny_pool = [1, 2, 3, 5, 6, 7, 8, 11, 12, 13, 14, 15, 20, 27, 28, 29, 30]
+    nz_pool = [1, 2, 3, 4, 5, 7, 9, 16, 23, 31, 32, 33, 41, 44, 63]
     for case in range(ncases):
         N = (int(rng.choice(nx_pool)), int(rng.choice(ny_pool)), int(rng.choice(nz_pool)))
         isbloch = tuple(bool(b) for b in rng.integers(0, 2, 3))
@@ -45,7 +48,10 @@ def main():
         full = bool(rng.integers(0, 2))
         with_mu = bool(rng.integers(0, 2))
         full_mass = full
-        kw = dict(full_eps=full_mass and ft == EE, full_mu=full_mass and ft == HH, with_mu=with_mu or ft == HH)
+        real_mass = bool(rng.integers(0, 2))
+        sym_real = real_mass and full_mass and bool(rng.integers(0, 2))
+        kw = dict(full_eps=full_mass and ft == EE, full_mu=full_mass and ft == HH, with_mu=with_mu or ft == HH,
+                  real_mass=real_mass, sym_real_off=sym_real)
         p = Problem(N, isbloch, boundft, ft=ft, cmpfirst=cmpfirst, seed=int(rng.integers(1 << 30)), npml=int(rng.integers(0, 4)), **kw)
         mass = p.eps if ft == EE else p.mu
         pattern = int(rng.integers(0, 3))
@@ -62,7 +68,8 @@ def main():
             os.environ["FDFD_LZ"] = str(lz)
         else:
             os.environ.pop("FDFD_LZ", None)
-        tag = f"case {case}: N={N} bloch={isbloch} boundft={boundft} ft={ft} cmpfirst={cmpfirst} full={full_mass} mu={with_mu} pattern={pattern} lz={lz}"
+        tag = (f"case {case}: N={N} bloch={isbloch} boundft={boundft} ft={ft} cmpfirst={cmpfirst} full={full_mass} mu={with_mu} "
+               f"pattern={pattern} lz={lz} real_mass={real_mass} sym_real_off={sym_real}")
         try:
             A = p.operator(device=0, kernel=2)
             x = p.random_x()
